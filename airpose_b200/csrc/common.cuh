@@ -1,0 +1,50 @@
+// Shared host-side plumbing for libairpose_b200: error reporting and launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/airpose_b200.h"
+
+namespace airpose {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define AP_CHECK_CUDA(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      airpose::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,              \
+                         cudaGetErrorString(_e));                                        \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+#define AP_REQUIRE(cond, ...)                                                            \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      airpose::set_error(__VA_ARGS__);                                                   \
+      return 2;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+#define AP_LAUNCH_CHECK()                                                                \
+  do {                                                                                   \
+    airpose::count_launch();                                                             \
+    AP_CHECK_CUDA(cudaGetLastError());                                                   \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+template <class T>
+int device_upload(T** dst, const T* src_host, size_t count) {
+  AP_CHECK_CUDA(cudaMalloc((void**)dst, count * sizeof(T)));
+  AP_CHECK_CUDA(cudaMemcpy(*dst, src_host, count * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+}  // namespace airpose

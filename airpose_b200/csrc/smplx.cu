@@ -1,0 +1,555 @@
+// SMPL-X forward for the AirPose hot path: blend shapes, kinematic chain, linear blend
+// skinning, extra joints + landmarks, camera transform and 2D projection.
+//
+// Replaces (paths relative to /root/reference/copenet/src/copenet):
+//   smplx/smplx/body_models.py:820-994  SMPLX.forward(pose2rot=False)
+//   smplx/smplx/lbs.py:135-222,245-266,225-242,316-370,96-132
+//   smplx/smplx/vertex_joint_selector.py:73-77
+//   utils/utils.py:237-256 transform_smpl, utils/geometry.py:63-91 perspective_projection
+//
+// Three kernels per call (DESIGN.md "SMPL-X path"):
+//   1. smplx_pose_kernel    one CTA per mesh: joints from the pre-contracted regressor
+//                           (J = J_template + J_shapedirs.beta, exact by linearity), the
+//                           kinematic chain, A_j = G_j - [0 | G_j j_rest], pose feature.
+//   2. smplx_vertex_kernel  CTA = 128 vertices x MB meshes: pose-corrective offsets as a
+//                           register-tiled fp32 contraction, shape blend, sparse skinning
+//                           from smem-resident A, optional camera transform.
+//   3. smplx_joints_kernel  one CTA per mesh: 55 + 21 + 51 joints, camera transform,
+//                           perspective projection.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace airpose {
+
+constexpr int kMaxJoints = 64;
+constexpr int kMaxShape = 20;
+constexpr int kVertsPerCta = 128;
+constexpr int kMeshTile = 16;
+
+struct SmplxDev {
+  int V, J, NS, P, L, E, KW;
+  const float* v_template;   // [V,3]
+  const float* shapedirs;    // [V,3,NS]
+  const float* posedirs;     // [P, V*3]
+  const float* J_template;   // [J,3]
+  const float* J_shapedirs;  // [J,3,NS]
+  const int* parents;        // [J]
+  const int* skin_idx;       // [KW,V]
+  const float* skin_w;       // [KW,V]
+  const int* lmk_vidx;       // [L,3]
+  const float* lmk_bary;     // [L,3]
+  const int* extra_idx;      // [E]
+};
+
+struct PoseArgs {
+  int B, nb, n_active;       // n_active = joints 1..n_active feed the pose feature
+  const float* betas; int betas_stride;
+  const float* seg[3]; int seg_stride[3];   // joint 0 | joints 1..21 | joints 22..J-1
+  float* A;                  // [B,J,12]
+  float* Jt;                 // [B,J,3]
+  float* feat;               // [B,PF]
+};
+
+__device__ __forceinline__ void load_rot(const PoseArgs& a, int b, int j, float R[9]) {
+  const float* src = nullptr;
+  if (j == 0) {
+    if (a.seg[0]) src = a.seg[0] + (size_t)b * a.seg_stride[0];
+  } else if (j < 22) {
+    if (a.seg[1]) src = a.seg[1] + (size_t)b * a.seg_stride[1] + (j - 1) * 9;
+  } else {
+    if (a.seg[2]) src = a.seg[2] + (size_t)b * a.seg_stride[2] + (j - 22) * 9;
+  }
+#pragma unroll
+  for (int e = 0; e < 9; ++e) R[e] = src ? __ldg(src + e) : ((e % 4 == 0) ? 1.f : 0.f);
+}
+
+// lbs.py:316-370 batch_rigid_transform, one mesh per CTA, one joint per thread.
+__global__ void __launch_bounds__(kMaxJoints) smplx_pose_kernel(SmplxDev m, PoseArgs a) {
+  __shared__ float Ts[kMaxJoints][12];
+  __shared__ float Js[kMaxJoints][3];
+  __shared__ float beta_s[kMaxShape];
+  __shared__ int par_s[kMaxJoints];
+  const int b = blockIdx.x, j = threadIdx.x;
+  if (j < kMaxShape) beta_s[j] = (j < a.nb) ? __ldg(a.betas + (size_t)b * a.betas_stride + j) : 0.f;
+  if (j < m.J) par_s[j] = m.parents[j];
+  __syncthreads();
+  float R[9];
+  if (j < m.J) {
+    load_rot(a, b, j, R);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float acc = __ldg(m.J_template + j * 3 + k);
+      const float* sd = m.J_shapedirs + ((size_t)j * 3 + k) * m.NS;
+      for (int l = 0; l < a.nb; ++l) acc = fmaf(__ldg(sd + l), beta_s[l], acc);
+      Js[j][k] = acc;
+    }
+  }
+  __syncthreads();
+  if (j < m.J) {
+    const int p = par_s[j];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      Ts[j][r * 4 + 0] = R[r * 3 + 0];
+      Ts[j][r * 4 + 1] = R[r * 3 + 1];
+      Ts[j][r * 4 + 2] = R[r * 3 + 2];
+      Ts[j][r * 4 + 3] = Js[j][r] - (p >= 0 ? Js[p][r] : 0.f);   // rel_joints (:343-345)
+    }
+  }
+  __syncthreads();
+  if (j >= m.J) return;
+  // G_j = T_root ... T_parent T_j, accumulated from the leaf upwards.
+  float G[12];
+#pragma unroll
+  for (int e = 0; e < 12; ++e) G[e] = Ts[j][e];
+  for (int p = par_s[j]; p >= 0; p = par_s[p]) {
+    float N[12];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float t0 = Ts[p][r * 4 + 0], t1 = Ts[p][r * 4 + 1], t2 = Ts[p][r * 4 + 2];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v = t0 * G[0 * 4 + c];
+        v = fmaf(t1, G[1 * 4 + c], v);
+        v = fmaf(t2, G[2 * 4 + c], v);
+        if (c == 3) v += Ts[p][r * 4 + 3];
+        N[r * 4 + c] = v;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 12; ++e) G[e] = N[e];
+  }
+  float* Jt = a.Jt + ((size_t)b * m.J + j) * 3;
+  Jt[0] = G[3]; Jt[1] = G[7]; Jt[2] = G[11];                    // posed joints (:360)
+  float* A = a.A + ((size_t)b * m.J + j) * 12;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {                                  // rel_transforms (:365-368)
+    const float gj = G[r * 4 + 0] * Js[j][0] + G[r * 4 + 1] * Js[j][1] + G[r * 4 + 2] * Js[j][2];
+    A[r * 4 + 0] = G[r * 4 + 0];
+    A[r * 4 + 1] = G[r * 4 + 1];
+    A[r * 4 + 2] = G[r * 4 + 2];
+    A[r * 4 + 3] = G[r * 4 + 3] - gj;
+  }
+  if (j >= 1 && j <= a.n_active) {                               // pose_feature (lbs.py:197)
+    float* f = a.feat + (size_t)b * (a.n_active * 9) + (j - 1) * 9;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) f[e] = R[e] - ((e % 4 == 0) ? 1.f : 0.f);
+  }
+}
+
+struct VertexArgs {
+  int B, nb, PF;
+  const float* betas; int betas_stride;
+  const float* A;            // [B,J,12]
+  const float* feat;         // [B,PF]
+  const float* transl;       // [B,3] or null
+  const float* root_R; int root_R_stride;
+  const float* root_t; int root_t_stride;
+  float* out;                // [B,V,3]
+  float* out_cam;            // [B,V,3] or null
+};
+
+template <int MB>
+__global__ void __launch_bounds__(kVertsPerCta) smplx_vertex_kernel(SmplxDev m, VertexArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* f_s = smem;                                   // [PF][MB]
+  float* A_s = f_s + (size_t)a.PF * MB;                // [MB][J*12]
+  float* beta_s = A_s + (size_t)MB * m.J * 12;         // [MB][kMaxShape]
+  float* cam_s = beta_s + MB * kMaxShape;              // [MB][16]: R(9) t(3) transl(3)
+  const int tid = threadIdx.x;
+  const int v = blockIdx.x * kVertsPerCta + tid;
+  const int mesh0 = blockIdx.y * MB;
+  const int nmesh = min(MB, a.B - mesh0);
+  const bool valid = v < m.V;
+  const int vc = valid ? v : m.V - 1;
+
+  for (int i = tid; i < a.PF * MB; i += kVertsPerCta) {
+    const int p = i / MB, b = i % MB;
+    f_s[i] = (b < nmesh) ? __ldg(a.feat + (size_t)(mesh0 + b) * a.PF + p) : 0.f;
+  }
+  const int A_per_mesh = m.J * 12;
+  for (int i = tid; i < MB * A_per_mesh; i += kVertsPerCta) {
+    const int b = i / A_per_mesh;
+    A_s[i] = (b < nmesh) ? __ldg(a.A + (size_t)(mesh0 + b) * A_per_mesh + (i - b * A_per_mesh)) : 0.f;
+  }
+  for (int i = tid; i < MB * kMaxShape; i += kVertsPerCta) {
+    const int b = i / kMaxShape, l = i % kMaxShape;
+    beta_s[i] = (b < nmesh && l < a.nb) ? __ldg(a.betas + (size_t)(mesh0 + b) * a.betas_stride + l) : 0.f;
+  }
+  for (int i = tid; i < MB * 16; i += kVertsPerCta) {
+    const int b = i / 16, e = i % 16;
+    float val = 0.f;
+    if (b < nmesh) {
+      if (e < 9) val = a.root_R ? __ldg(a.root_R + (size_t)(mesh0 + b) * a.root_R_stride + e) : ((e % 4 == 0) ? 1.f : 0.f);
+      else if (e < 12) val = a.root_t ? __ldg(a.root_t + (size_t)(mesh0 + b) * a.root_t_stride + (e - 9)) : 0.f;
+      else if (e < 15) val = a.transl ? __ldg(a.transl + (size_t)(mesh0 + b) * 3 + (e - 12)) : 0.f;
+    }
+    cam_s[i] = val;
+  }
+  __syncthreads();
+
+  // pose-corrective offsets: acc[b][k] = sum_p feat[b][p] * posedirs[p][3v+k]   (lbs.py:200-201)
+  float acc[MB][3];
+#pragma unroll
+  for (int b = 0; b < MB; ++b) acc[b][0] = acc[b][1] = acc[b][2] = 0.f;
+  const float* Pv = m.posedirs + (size_t)vc * 3;
+  const size_t prow = (size_t)m.V * 3;
+#pragma unroll 2
+  for (int p = 0; p < a.PF; ++p) {
+    const float p0 = __ldg(Pv + p * prow), p1 = __ldg(Pv + p * prow + 1), p2 = __ldg(Pv + p * prow + 2);
+    const float4* fr = reinterpret_cast<const float4*>(f_s + (size_t)p * MB);
+#pragma unroll
+    for (int q = 0; q < MB / 4; ++q) {
+      const float4 f4 = fr[q];
+      const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        acc[q * 4 + r][0] = fmaf(fv[r], p0, acc[q * 4 + r][0]);
+        acc[q * 4 + r][1] = fmaf(fv[r], p1, acc[q * 4 + r][1]);
+        acc[q * 4 + r][2] = fmaf(fv[r], p2, acc[q * 4 + r][2]);
+      }
+    }
+  }
+
+  const float vt0 = __ldg(m.v_template + vc * 3), vt1 = __ldg(m.v_template + vc * 3 + 1),
+              vt2 = __ldg(m.v_template + vc * 3 + 2);
+  const float* Sv = m.shapedirs + (size_t)vc * 3 * m.NS;
+#pragma unroll
+  for (int b = 0; b < MB; ++b) {
+    if (b >= nmesh) break;
+    // v_shaped + pose offsets (lbs.py:179,203)
+    float x = vt0, y = vt1, z = vt2;
+    for (int l = 0; l < a.nb; ++l) {
+      const float be = beta_s[b * kMaxShape + l];
+      x = fmaf(__ldg(Sv + l), be, x);
+      y = fmaf(__ldg(Sv + m.NS + l), be, y);
+      z = fmaf(__ldg(Sv + 2 * m.NS + l), be, z);
+    }
+    x += acc[b][0]; y += acc[b][1]; z += acc[b][2];
+    // T = sum_j w_vj A_j over the non-zero weights (lbs.py:209-213)
+    float T[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) T[e] = 0.f;
+    for (int k = 0; k < m.KW; ++k) {
+      const float w = __ldg(m.skin_w + (size_t)k * m.V + vc);
+      const int jn = __ldg(m.skin_idx + (size_t)k * m.V + vc);
+      const float4* Aj = reinterpret_cast<const float4*>(A_s + (size_t)b * A_per_mesh + jn * 12);
+      const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+      T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+      T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+      T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+    }
+    const float* cs = cam_s + b * 16;
+    // v = T [v_posed; 1]  (lbs.py:215-220), then += transl (body_models.py:980-982)
+    const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3]))) + cs[12];
+    const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7]))) + cs[13];
+    const float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11]))) + cs[14];
+    if (valid) {
+      float* o = a.out + ((size_t)(mesh0 + b) * m.V + v) * 3;
+      o[0] = ox; o[1] = oy; o[2] = oz;
+      if (a.out_cam) {   // transform_smpl (utils.py:237-239): R v + t about the origin
+        float* oc = a.out_cam + ((size_t)(mesh0 + b) * m.V + v) * 3;
+        oc[0] = fmaf(cs[0], ox, fmaf(cs[1], oy, cs[2] * oz)) + cs[9];
+        oc[1] = fmaf(cs[3], ox, fmaf(cs[4], oy, cs[5] * oz)) + cs[10];
+        oc[2] = fmaf(cs[6], ox, fmaf(cs[7], oy, cs[8] * oz)) + cs[11];
+      }
+    }
+  }
+}
+
+struct JointArgs {
+  int B;
+  const float* verts;        // [B,V,3] (transl already applied)
+  const float* Jt;           // [B,J,3]
+  const float* transl;
+  const float* root_R; int root_R_stride;
+  const float* root_t; int root_t_stride;
+  float fx, fy;
+  const float* center; int center_stride;
+  float* joints; float* joints_cam; float* j2d;
+};
+
+__global__ void __launch_bounds__(128) smplx_joints_kernel(SmplxDev m, JointArgs a) {
+  const int b = blockIdx.x;
+  const int nj = m.J + m.E + m.L;
+  const float* vb = a.verts + (size_t)b * m.V * 3;
+  for (int i = threadIdx.x; i < nj; i += blockDim.x) {
+    float x, y, z;
+    if (i < m.J) {
+      const float* s = a.Jt + ((size_t)b * m.J + i) * 3;
+      x = s[0]; y = s[1]; z = s[2];
+      if (a.transl) { x += a.transl[b * 3]; y += a.transl[b * 3 + 1]; z += a.transl[b * 3 + 2]; }
+    } else if (i < m.J + m.E) {                       // vertex_joint_selector.py:73-77 (pure gather)
+      const float* s = vb + (size_t)m.extra_idx[i - m.J] * 3;
+      x = s[0]; y = s[1]; z = s[2];
+    } else {                                          // vertices2landmarks (lbs.py:96-132)
+      const int l = i - m.J - m.E;
+      x = y = z = 0.f;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        const float w = m.lmk_bary[l * 3 + f];
+        const float* s = vb + (size_t)m.lmk_vidx[l * 3 + f] * 3;
+        x = fmaf(s[0], w, x); y = fmaf(s[1], w, y); z = fmaf(s[2], w, z);
+      }
+    }
+    float* o = a.joints + ((size_t)b * nj + i) * 3;
+    o[0] = x; o[1] = y; o[2] = z;
+    if (a.joints_cam || a.j2d) {
+      float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
+      if (a.root_R) for (int e = 0; e < 9; ++e) R[e] = a.root_R[(size_t)b * a.root_R_stride + e];
+      if (a.root_t) for (int e = 0; e < 3; ++e) t[e] = a.root_t[(size_t)b * a.root_t_stride + e];
+      const float cx = fmaf(R[0], x, fmaf(R[1], y, R[2] * z)) + t[0];
+      const float cy = fmaf(R[3], x, fmaf(R[4], y, R[5] * z)) + t[1];
+      const float cz = fmaf(R[6], x, fmaf(R[7], y, R[8] * z)) + t[2];
+      if (a.joints_cam) {
+        float* oc = a.joints_cam + ((size_t)b * nj + i) * 3;
+        oc[0] = cx; oc[1] = cy; oc[2] = cz;
+      }
+      if (a.j2d) {   // perspective_projection (geometry.py:63-91) with rotation = I, translation = 0
+        const float px = a.center ? a.center[(size_t)b * a.center_stride] : 0.f;
+        const float py = a.center ? a.center[(size_t)b * a.center_stride + 1] : 0.f;
+        float* o2 = a.j2d + ((size_t)b * nj + i) * 2;
+        o2[0] = fmaf(a.fx, cx / cz, px);
+        o2[1] = fmaf(a.fy, cy / cz, py);
+      }
+    }
+  }
+}
+
+__global__ void rot6d_kernel(const float* __restrict__ x, int64_t groups, int per_group, int64_t row_stride,
+                             float* __restrict__ R) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * per_group) return;
+  const float* s = x + (i / per_group) * row_stride + (i % per_group) * 6;
+  // reshape(-1,3,2): a1 = elements (0,2,4), a2 = (1,3,5)   (geometry.py:55-57)
+  const float a1x = s[0], a1y = s[2], a1z = s[4], a2x = s[1], a2y = s[3], a2z = s[5];
+  const float n1 = fmaxf(sqrtf(a1x * a1x + a1y * a1y + a1z * a1z), 1e-12f);   // F.normalize eps
+  const float b1x = a1x / n1, b1y = a1y / n1, b1z = a1z / n1;
+  const float d = b1x * a2x + b1y * a2y + b1z * a2z;
+  const float ux = a2x - d * b1x, uy = a2y - d * b1y, uz = a2z - d * b1z;
+  const float n2 = fmaxf(sqrtf(ux * ux + uy * uy + uz * uz), 1e-12f);
+  const float b2x = ux / n2, b2y = uy / n2, b2z = uz / n2;
+  const float b3x = b1y * b2z - b1z * b2y, b3y = b1z * b2x - b1x * b2z, b3z = b1x * b2y - b1y * b2x;
+  float* o = R + i * 9;          // columns (b1,b2,b3)  (geometry.py:61)
+  o[0] = b1x; o[1] = b2x; o[2] = b3x;
+  o[3] = b1y; o[4] = b2y; o[5] = b3y;
+  o[6] = b1z; o[7] = b2z; o[8] = b3z;
+}
+
+__global__ void j14_gather_kernel(const float* __restrict__ joints, int B, int nj, const int* __restrict__ map,
+                                  int nmap, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * nmap * 3) return;
+  const int c = i % 3, k = (i / 3) % nmap, b = i / (3 * nmap);
+  out[i] = joints[((size_t)b * nj + map[k]) * 3 + c];
+}
+
+}  // namespace airpose
+
+using namespace airpose;
+
+struct airpose_smplx {
+  int device = 0;
+  SmplxDev d{};
+  std::vector<void*> owned;
+  float* ws = nullptr;
+  size_t ws_floats = 0;
+};
+
+extern "C" int airpose_smplx_create(airpose_smplx_t** out, const airpose_smplx_model_host* mh, int device) {
+  AP_REQUIRE(out && mh, "airpose_smplx_create: null argument");
+  const int V = mh->num_verts, J = mh->num_joints, NS = mh->num_shape, P = mh->num_pose_basis;
+  AP_REQUIRE(J >= 1 && J <= kMaxJoints, "airpose_smplx_create: num_joints %d out of range [1,%d]", J, kMaxJoints);
+  AP_REQUIRE(NS >= 0 && NS <= kMaxShape, "airpose_smplx_create: num_shape %d > %d", NS, kMaxShape);
+  AP_REQUIRE(P == (J - 1) * 9, "airpose_smplx_create: num_pose_basis %d != (J-1)*9", P);
+  AP_REQUIRE(mh->parents[0] < 0, "airpose_smplx_create: parents[0] must be -1");
+  for (int j = 1; j < J; ++j)
+    AP_REQUIRE(mh->parents[j] >= 0 && mh->parents[j] < j, "airpose_smplx_create: parents[%d]=%lld is not < %d", j,
+               (long long)mh->parents[j], j);
+  AP_CHECK_CUDA(cudaSetDevice(device));
+  auto* h = new airpose_smplx();
+  h->device = device;
+  SmplxDev& d = h->d;
+  d.V = V; d.J = J; d.NS = NS; d.P = P; d.L = mh->num_landmarks; d.E = mh->num_extra;
+
+  // Joint regressor contracted with the template and the shape basis (exact by linearity of
+  // lbs.py:179-183): J = J_regressor (v_template + shapedirs beta).
+  std::vector<float> Jt((size_t)J * 3), Js((size_t)J * 3 * NS);
+  for (int j = 0; j < J; ++j) {
+    double t[3] = {0, 0, 0};
+    std::vector<double> s((size_t)3 * NS, 0.0);
+    for (int v = 0; v < V; ++v) {
+      const double w = mh->J_regressor[(size_t)j * V + v];
+      if (w == 0.0) continue;
+      for (int k = 0; k < 3; ++k) {
+        t[k] += w * mh->v_template[(size_t)v * 3 + k];
+        for (int l = 0; l < NS; ++l) s[(size_t)k * NS + l] += w * mh->shapedirs[((size_t)v * 3 + k) * NS + l];
+      }
+    }
+    for (int k = 0; k < 3; ++k) {
+      Jt[j * 3 + k] = (float)t[k];
+      for (int l = 0; l < NS; ++l) Js[((size_t)j * 3 + k) * NS + l] = (float)s[(size_t)k * NS + l];
+    }
+  }
+  // Skinning weights in ELL form: exactly the non-zeros of lbs_weights, widest row decides KW.
+  int KW = 1;
+  for (int v = 0; v < V; ++v) {
+    int n = 0;
+    for (int j = 0; j < J; ++j) n += mh->lbs_weights[(size_t)v * J + j] != 0.f;
+    KW = std::max(KW, n);
+  }
+  d.KW = KW;
+  std::vector<int> sidx((size_t)KW * V, 0);
+  std::vector<float> sw((size_t)KW * V, 0.f);
+  for (int v = 0; v < V; ++v) {
+    int n = 0;
+    for (int j = 0; j < J; ++j) {
+      const float w = mh->lbs_weights[(size_t)v * J + j];
+      if (w != 0.f) { sidx[(size_t)n * V + v] = j; sw[(size_t)n * V + v] = w; ++n; }
+    }
+  }
+  std::vector<int> par(J), lv((size_t)d.L * 3), ex(d.E);
+  for (int j = 0; j < J; ++j) par[j] = (int)mh->parents[j];
+  for (int l = 0; l < d.L; ++l) {
+    const int64_t f = mh->lmk_faces_idx[l];
+    AP_REQUIRE(f >= 0 && f < mh->num_faces, "airpose_smplx_create: lmk_faces_idx[%d] out of range", l);
+    for (int k = 0; k < 3; ++k) {
+      const int64_t vi = mh->faces[f * 3 + k];
+      AP_REQUIRE(vi >= 0 && vi < V, "airpose_smplx_create: face vertex id out of range");
+      lv[l * 3 + k] = (int)vi;
+    }
+  }
+  for (int e = 0; e < d.E; ++e) {
+    AP_REQUIRE(mh->extra_joint_idx[e] >= 0 && mh->extra_joint_idx[e] < V, "airpose_smplx_create: extra joint id out of range");
+    ex[e] = (int)mh->extra_joint_idx[e];
+  }
+
+  float* fp; int* ip;
+#define UP_F(field, src, n) do { if (device_upload(&fp, (const float*)(src), (size_t)(n))) return 1; d.field = fp; h->owned.push_back(fp); } while (0)
+#define UP_I(field, src, n) do { if (device_upload(&ip, (const int*)(src), (size_t)(n))) return 1; d.field = ip; h->owned.push_back(ip); } while (0)
+  UP_F(v_template, mh->v_template, (size_t)V * 3);
+  UP_F(shapedirs, mh->shapedirs, (size_t)V * 3 * NS);
+  UP_F(posedirs, mh->posedirs, (size_t)P * V * 3);
+  UP_F(J_template, Jt.data(), Jt.size());
+  UP_F(J_shapedirs, Js.data(), std::max<size_t>(Js.size(), 1));
+  UP_I(parents, par.data(), par.size());
+  UP_I(skin_idx, sidx.data(), sidx.size());
+  UP_F(skin_w, sw.data(), sw.size());
+  UP_I(lmk_vidx, lv.data(), std::max<size_t>(lv.size(), 1));
+  UP_F(lmk_bary, mh->lmk_bary_coords, std::max<size_t>((size_t)d.L * 3, 1));
+  UP_I(extra_idx, ex.data(), std::max<size_t>(ex.size(), 1));
+#undef UP_F
+#undef UP_I
+  *out = h;
+  return 0;
+}
+
+extern "C" int airpose_smplx_destroy(airpose_smplx_t* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  for (void* p : h->owned) cudaFree(p);
+  cudaFree(h->ws);
+  delete h;
+  return 0;
+}
+
+extern "C" int airpose_smplx_skin_nnz(const airpose_smplx_t* h) { return h ? h->d.KW : -1; }
+
+extern "C" int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_args* g, void* stream_) {
+  AP_REQUIRE(h && g, "airpose_smplx_fwd: null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const SmplxDev& d = h->d;
+  const int B = g->batch;
+  AP_REQUIRE(B >= 0, "airpose_smplx_fwd: negative batch");
+  if (B == 0) return 0;
+  AP_REQUIRE(g->betas && g->out_vertices && g->out_joints, "airpose_smplx_fwd: betas/out_vertices/out_joints are required");
+  AP_REQUIRE(g->num_betas >= 0 && g->num_betas <= d.NS, "airpose_smplx_fwd: num_betas %d > shapedirs columns %d", g->num_betas, d.NS);
+  AP_REQUIRE(!g->tail_pose || d.J > 22, "airpose_smplx_fwd: tail_pose given but the model has %d joints", d.J);
+  AP_REQUIRE(d.J == 55 || (!g->body_pose && !g->tail_pose) || d.J >= 22, "airpose_smplx_fwd: unsupported joint count %d", d.J);
+  const int n_active = g->tail_pose ? d.J - 1 : (g->body_pose ? std::min(21, d.J - 1) : 0);
+  const int PF = n_active * 9;
+
+  const size_t need = (size_t)B * d.J * 12 + (size_t)B * d.J * 3 + (size_t)B * std::max(PF, 1);
+  if (need > h->ws_floats) {
+    AP_CHECK_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(h->ws);
+    h->ws = nullptr; h->ws_floats = 0;
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->ws, need * sizeof(float)));
+    h->ws_floats = need;
+  }
+  float* A = h->ws;
+  float* Jt = A + (size_t)B * d.J * 12;
+  float* feat = Jt + (size_t)B * d.J * 3;
+
+  PoseArgs pa{};
+  pa.B = B; pa.nb = g->num_betas; pa.n_active = n_active;
+  pa.betas = g->betas; pa.betas_stride = g->betas_stride;
+  pa.seg[0] = g->global_orient; pa.seg_stride[0] = g->global_orient_stride;
+  pa.seg[1] = g->body_pose; pa.seg_stride[1] = g->body_pose_stride;
+  pa.seg[2] = g->tail_pose; pa.seg_stride[2] = g->tail_pose_stride;
+  pa.A = A; pa.Jt = Jt; pa.feat = feat;
+  smplx_pose_kernel<<<B, kMaxJoints, 0, stream>>>(d, pa);
+  AP_LAUNCH_CHECK();
+
+  VertexArgs va{};
+  va.B = B; va.nb = g->num_betas; va.PF = PF;
+  va.betas = g->betas; va.betas_stride = g->betas_stride;
+  va.A = A; va.feat = feat; va.transl = g->transl;
+  va.root_R = g->root_R; va.root_R_stride = g->root_R_stride;
+  va.root_t = g->root_t; va.root_t_stride = g->root_t_stride;
+  va.out = g->out_vertices; va.out_cam = g->out_vertices_cam;
+  constexpr int MB = kMeshTile;
+  const size_t smem = ((size_t)PF * MB + (size_t)MB * d.J * 12 + MB * kMaxShape + MB * 16) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  AP_REQUIRE(smem <= 160 * 1024, "airpose_smplx_fwd: shared memory %zu too large", smem);
+  dim3 grid(ceil_div(d.V, kVertsPerCta), ceil_div(B, MB));
+  smplx_vertex_kernel<MB><<<grid, kVertsPerCta, smem, stream>>>(d, va);
+  AP_LAUNCH_CHECK();
+
+  JointArgs ja{};
+  ja.B = B; ja.verts = g->out_vertices; ja.Jt = Jt; ja.transl = g->transl;
+  ja.root_R = g->root_R; ja.root_R_stride = g->root_R_stride;
+  ja.root_t = g->root_t; ja.root_t_stride = g->root_t_stride;
+  ja.fx = g->focal_x; ja.fy = g->focal_y; ja.center = g->center; ja.center_stride = g->center_stride;
+  ja.joints = g->out_joints; ja.joints_cam = g->out_joints_cam; ja.j2d = g->out_joints_2d;
+  smplx_joints_kernel<<<B, 128, 0, stream>>>(d, ja);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int airpose_rot6d_to_rotmat_strided(const float* x, int64_t groups, int32_t per_group, int64_t row_stride,
+                                               float* R, void* stream) {
+  AP_REQUIRE(x && R && groups >= 0 && per_group > 0, "airpose_rot6d_to_rotmat: bad argument");
+  const int64_t n = groups * per_group;
+  if (n == 0) return 0;
+  rot6d_kernel<<<(unsigned)ceil_div64(n, 128), 128, 0, (cudaStream_t)stream>>>(x, groups, per_group, row_stride, R);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int airpose_rot6d_to_rotmat(const float* x, int64_t n, float* R, void* stream) {
+  return airpose_rot6d_to_rotmat_strided(x, n, 1, 6, R, stream);
+}
+
+extern "C" int airpose_j14_gather(const float* joints, int32_t batch, int32_t num_joints, const int32_t* map_host,
+                                  float* out, void* stream) {
+  AP_REQUIRE(joints && out && batch >= 0 && num_joints > 0, "airpose_j14_gather: bad argument");
+  static const int32_t ref_map[14] = {15, 12, 17, 19, 21, 16, 18, 20, 2, 5, 8, 1, 4, 7};
+  const int32_t* mp = map_host ? map_host : ref_map;
+  for (int i = 0; i < 14; ++i) AP_REQUIRE(mp[i] >= 0 && mp[i] < num_joints, "airpose_j14_gather: map[%d]=%d out of range", i, mp[i]);
+  if (batch == 0) return 0;
+  // the map is tiny: pass it through a per-call device buffer on the stream
+  int* dmap = nullptr;
+  AP_CHECK_CUDA(cudaMallocAsync((void**)&dmap, 14 * sizeof(int), (cudaStream_t)stream));
+  AP_CHECK_CUDA(cudaMemcpyAsync(dmap, mp, 14 * sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  j14_gather_kernel<<<ceil_div(batch * 14 * 3, 128), 128, 0, (cudaStream_t)stream>>>(joints, batch, num_joints, dmap, 14, out);
+  AP_LAUNCH_CHECK();
+  AP_CHECK_CUDA(cudaFreeAsync(dmap, (cudaStream_t)stream));
+  return 0;
+}

@@ -1,0 +1,253 @@
+"""Drop-in ``copenet`` network (ResNet-50 trunk + two-view IEF regressor) on sm_100a kernels.
+
+Mirrors copenet/src/copenet/models/model_copenet.py of the reference:
+
+    model = getcopenet(smpl_mean_params_path, pretrained=False)
+    pose0, betas0, pose1, betas1 = model(x0=, x1=, bb0=, bb1=, init_position0=,
+                                         init_position1=, iters=3)         # :112-159
+
+The module owns ordinary ``nn.Conv2d`` / ``nn.BatchNorm2d`` / ``nn.Linear`` children with the
+reference's names, so ``state_dict()`` has the same 331 keys, Lightning checkpoints
+(``model.``-prefixed) and ``load_state_dict(resnet50.state_dict(), strict=False)`` load, and
+``.fc1/.fc2/.decpose/.decshape/.deccam`` / ``.parameters()`` are there for optimizers.  The
+children are parameter containers only: ``forward`` hands their tensors to
+libairpose_b200 (bf16 tcgen05 implicit-GEMM convs with fused BN/ReLU/residual; split-bf16
+tcgen05 GEMMs for the regressor).  Eval mode only for now: training-mode BatchNorm
+statistics and dropout arrive with the backward kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class Bottleneck(nn.Module):
+    """Parameter container with the reference block's names (model_copenet.py:8-25)."""
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        raise RuntimeError("airpose_b200 Bottleneck is a parameter container; call copenet.forward_feat_ext")
+
+
+class copenet(nn.Module):
+    def __init__(self, block, layers, smpl_mean_params):
+        super().__init__()
+        if list(layers) != [3, 4, 6, 3] or block is not Bottleneck:
+            raise NotImplementedError("the sm_100a trunk is built for ResNet-50 ([3,4,6,3] Bottleneck)")
+        self.inplanes = 64
+        npose = 21 * 6
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.layer1 = self._make_layer(block, 64, layers[0])
+        self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
+        self.layer3 = self._make_layer(block, 256, layers[2], stride=2)
+        self.layer4 = self._make_layer(block, 512, layers[3], stride=2)
+        self.avgpool = nn.AvgPool2d(7, stride=1)
+        self.fc1 = nn.Linear(512 * block.expansion + 3 + 3 + 6 + npose + 10 + npose + 10, 1024)
+        self.drop1 = nn.Dropout()
+        self.fc2 = nn.Linear(1024, 1024)
+        self.drop2 = nn.Dropout()
+        self.decpose = nn.Linear(1024, 3 + 6 + npose)
+        self.decshape = nn.Linear(1024, 10)
+        self.deccam = nn.Linear(1024, 3)
+        for dec in (self.decpose, self.decshape, self.deccam):
+            nn.init.xavier_uniform_(dec.weight, gain=0.01)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                m.weight.data.normal_(0, math.sqrt(2.0 / n))
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+        mean_params = np.load(smpl_mean_params)
+        self.register_buffer("init_pose", torch.from_numpy(mean_params["pose"][:]).unsqueeze(0))
+        self.register_buffer("init_shape", torch.from_numpy(mean_params["shape"][:].astype("float32")).unsqueeze(0))
+        self.register_buffer("init_cam", torch.from_numpy(mean_params["cam"]).unsqueeze(0))
+        self._handle = None
+        self._handle_key = None
+        self._loaded_key = None
+        self.max_images = 0
+
+    def _make_layer(self, block, planes, blocks, stride=1):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = nn.Sequential(
+                nn.Conv2d(self.inplanes, planes * block.expansion, kernel_size=1, stride=stride, bias=False),
+                nn.BatchNorm2d(planes * block.expansion))
+        layers = [block(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes))
+        return nn.Sequential(*layers)
+
+    # ------------------------------------------------------------------ native handle
+    def _conv_bn_pairs(self):
+        pairs = [(self.conv1, self.bn1)]
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                pairs += [(blk.conv1, blk.bn1), (blk.conv2, blk.bn2), (blk.conv3, blk.bn3)]
+                if blk.downsample is not None:
+                    pairs.append((blk.downsample[0], blk.downsample[1]))
+        return pairs
+
+    def _weight_tensors(self):
+        ts = []
+        for conv, bn in self._conv_bn_pairs():
+            ts += [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        ts += [self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, self.decpose.weight, self.decpose.bias,
+               self.decshape.weight, self.decshape.bias, self.init_pose, self.init_shape]
+        return ts
+
+    def _ensure(self, n_images, device):
+        if device.type != "cuda":
+            raise _lib.AirposeError("airpose_b200.copenet runs on CUDA only (module is on {}); there is no CPU path".format(device))
+        if self.training:
+            raise NotImplementedError("airpose_b200.copenet: training-mode forward (batch-statistics BatchNorm, dropout) "
+                                      "is not built yet; call .eval()")
+        lib = _lib.load()
+        if self._handle is None or self._handle_key != device or n_images > self.max_images:
+            self._release()
+            cap = max(n_images, self.max_images, 1)
+            h = C.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(lib.airpose_net_create(C.byref(h), cap, device.index or 0), "airpose_net_create")
+            self._handle, self._handle_key, self.max_images, self._loaded_key = h, device, cap, None
+        ts = self._weight_tensors()
+        key = tuple((t.data_ptr(), t._version) for t in ts)
+        if key != self._loaded_key:
+            for t in ts:
+                if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise _lib.AirposeError("copenet parameters must be contiguous float32 tensors on {}".format(device))
+            p = _lib.NetParams()
+            for i, (conv, bn) in enumerate(self._conv_bn_pairs()):
+                p.conv[i].weight = conv.weight.data_ptr()
+                p.conv[i].bn_weight = bn.weight.data_ptr()
+                p.conv[i].bn_bias = bn.bias.data_ptr()
+                p.conv[i].bn_mean = bn.running_mean.data_ptr()
+                p.conv[i].bn_var = bn.running_var.data_ptr()
+            p.fc1_w, p.fc1_b = self.fc1.weight.data_ptr(), self.fc1.bias.data_ptr()
+            p.fc2_w, p.fc2_b = self.fc2.weight.data_ptr(), self.fc2.bias.data_ptr()
+            p.decpose_w, p.decpose_b = self.decpose.weight.data_ptr(), self.decpose.bias.data_ptr()
+            p.decshape_w, p.decshape_b = self.decshape.weight.data_ptr(), self.decshape.bias.data_ptr()
+            p.init_pose, p.init_shape = self.init_pose.data_ptr(), self.init_shape.data_ptr()
+            p.bn_eps = float(self.bn1.eps)
+            with torch.cuda.device(device):
+                _lib.check(lib.airpose_net_load(self._handle, C.byref(p), _lib.current_stream()), "airpose_net_load")
+            self._loaded_key = key
+        return lib, self._handle
+
+    def _release(self):
+        if getattr(self, "_handle", None) is not None:
+            try:
+                _lib.load().airpose_net_destroy(self._handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def __del__(self):
+        self._release()
+
+    # ------------------------------------------------------------------ forward pieces
+    def forward_feat_ext(self, x):
+        """model_copenet.py:161-176: [n,3,224,224] -> [n,2048]."""
+        if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
+            raise ValueError("forward_feat_ext expects [n,3,224,224], got {}".format(tuple(x.shape)))
+        device = self.conv1.weight.device
+        x = x.detach().to(device=device, dtype=torch.float32).contiguous()
+        n = x.shape[0]
+        lib, h = self._ensure(n, device)
+        out = torch.empty(n, 2048, device=device, dtype=torch.float32)
+        with torch.cuda.device(device):
+            _lib.check(lib.airpose_backbone_fwd(h, x.data_ptr(), n, out.data_ptr(), _lib.current_stream()),
+                       "airpose_backbone_fwd")
+        return out
+
+    def _ief(self, xf0, xf1, bb0, bb1, pos0, pos1, theta0, theta1, shape0, shape1, iters):
+        device = self.conv1.weight.device
+        f = lambda t: None if t is None else t.detach().to(device=device, dtype=torch.float32).contiguous()
+        xf0, xf1, bb0, bb1, pos0, pos1 = map(f, (xf0, xf1, bb0, bb1, pos0, pos1))
+        theta0, theta1, shape0, shape1 = map(f, (theta0, theta1, shape0, shape1))
+        B = xf0.shape[0]
+        lib, h = self._ensure(0, device)
+        outs = [torch.empty(B, 135, device=device), torch.empty(B, 10, device=device),
+                torch.empty(B, 135, device=device), torch.empty(B, 10, device=device)]
+        a = _lib.IefArgs()
+        a.batch, a.iters = B, int(iters)
+        a.xf0, a.xf1, a.bb0, a.bb1, a.pos0, a.pos1 = (t.data_ptr() for t in (xf0, xf1, bb0, bb1, pos0, pos1))
+
+        def per_sample(t, width):
+            if t is None:
+                return None, 0
+            if t.shape[0] != B:
+                t = t.expand(B, -1).contiguous()        # the reference's .expand(batch_size, -1) (:125-135)
+            assert t.shape[1] >= width
+            return t, t.stride(0)
+
+        theta0, s0 = per_sample(theta0, 132)
+        theta1, s1 = per_sample(theta1, 132)
+        if (theta0 is None) != (theta1 is None) or (theta0 is not None and s0 != s1):
+            init = self.init_pose.expand(B, -1).contiguous()
+            theta0 = theta0 if theta0 is not None else init
+            theta1 = theta1 if theta1 is not None else init
+            theta0 = theta0[:, :132].contiguous(); theta1 = theta1[:, :132].contiguous(); s0 = 132
+        shape0, t0 = per_sample(shape0, 10)
+        shape1, t1 = per_sample(shape1, 10)
+        if (shape0 is None) != (shape1 is None) or (shape0 is not None and t0 != t1):
+            init = self.init_shape.expand(B, -1).contiguous()
+            shape0 = (shape0 if shape0 is not None else init).contiguous()
+            shape1 = (shape1 if shape1 is not None else init).contiguous()
+            t0 = shape0.stride(0)
+        if theta0 is not None:
+            a.init_theta0, a.init_theta1, a.init_theta_stride = theta0.data_ptr(), theta1.data_ptr(), s0
+        if shape0 is not None:
+            a.init_shape0, a.init_shape1, a.init_shape_stride = shape0.data_ptr(), shape1.data_ptr(), t0
+        a.out_pose0, a.out_betas0, a.out_pose1, a.out_betas1 = (t.data_ptr() for t in outs)
+        with torch.cuda.device(device):
+            _lib.check(lib.airpose_ief_fwd(h, C.byref(a), _lib.current_stream()), "airpose_ief_fwd")
+        return tuple(outs)
+
+    def forward_reg(self, xf0, xf1, bb0, bb1, pred_position0, pred_position1, pred_orient0, pred_orient1,
+                    pred_art_pose0, pred_art_pose1, pred_shape0, pred_shape1):
+        """One regressor pass (model_copenet.py:178-204), eval mode."""
+        th0 = torch.cat([pred_orient0, pred_art_pose0], dim=1)
+        th1 = torch.cat([pred_orient1, pred_art_pose1], dim=1)
+        return self._ief(xf0, xf1, bb0, bb1, pred_position0, pred_position1, th0, th1, pred_shape0, pred_shape1, 1)
+
+    def forward(self, x0, x1, bb0, bb1, init_position0, init_position1, init_theta0=None, init_theta1=None,
+                init_shape0=None, init_shape1=None, iters=3):
+        """model_copenet.py:112-159.  Both views go through the trunk in one call (eval-mode
+        BatchNorm makes images independent); the regressor keeps the two views of a pair together."""
+        B = x0.shape[0]
+        xf = self.forward_feat_ext(torch.cat([x0, x1], dim=0))
+        return self._ief(xf[:B], xf[B:], bb0, bb1, init_position0, init_position1, init_theta0, init_theta1,
+                         init_shape0, init_shape1, iters)
+
+
+def getcopenet(smpl_mean_params, pretrained=True, **kwargs):
+    """model_copenet.getcopenet (:229-239).  ``pretrained=True`` loads torchvision's ImageNet
+    ResNet-50 into the trunk exactly like the reference (needs network access or a cached file)."""
+    model = copenet(Bottleneck, [3, 4, 6, 3], smpl_mean_params, **kwargs)
+    if pretrained:
+        import torchvision.models.resnet as resnet
+        model.load_state_dict(resnet.resnet50(pretrained=True).state_dict(), strict=False)
+    return model

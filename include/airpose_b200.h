@@ -1,0 +1,208 @@
+/*
+ * airpose_b200 -- C ABI of the B200-native AirPose hot path (copenet_twoview forward).
+ *
+ * The reference has no FFI: its boundary is the Python object protocol of
+ * `model_copenet.getcopenet()` / `smplx.SMPLX`.  This header is
+ * what the Python shim in airpose_b200/ binds with ctypes; every entry point names the
+ * reference call it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message is available
+ *     from airpose_last_error() (thread-local).  Nothing throws.
+ *   - all tensor arguments are DEVICE pointers owned by the caller unless the name ends
+ *     in `_host`; the library allocates nothing persistent except the opaque handles
+ *     (which own packed weights and activation workspaces).
+ *   - every launch is asynchronous on the `stream` argument (a cudaStream_t passed as
+ *     void*); one handle per GPU / rank; handles are thread-compatible, not thread-safe.
+ *   - fp32 tensors are contiguous row-major exactly as the reference's torch tensors.
+ */
+#ifndef AIRPOSE_B200_H_
+#define AIRPOSE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AIRPOSE_B200_ABI_VERSION 1
+
+const char* airpose_last_error(void);
+int airpose_abi_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * SMPL-X body model  (copenet/src/copenet/smplx/smplx/body_models.py:648-994, lbs.py)
+ * ---------------------------------------------------------------------------------- */
+typedef struct airpose_smplx airpose_smplx_t;
+
+/* Host-side description of the buffers SMPL.__init__/SMPLX.__init__ register
+ * (body_models.py:205-296,727-730).  All pointers are HOST pointers, read during create. */
+typedef struct {
+  int32_t num_verts;        /* V = 10475 */
+  int32_t num_joints;       /* J = 55 */
+  int32_t num_shape;        /* shapedirs columns (20: 10 betas + 10 expression) */
+  int32_t num_pose_basis;   /* (J-1)*9 = 486 */
+  int32_t num_faces;
+  int32_t num_landmarks;    /* 51 static face landmarks */
+  int32_t num_extra;        /* 21 vertex-picked joints (vertex_joint_selector.py:38-68) */
+  const float*   v_template;      /* [V,3] */
+  const float*   shapedirs;       /* [V,3,num_shape] */
+  const float*   posedirs;        /* [num_pose_basis, V*3]  (already transposed, body_models.py:284-288) */
+  const float*   J_regressor;     /* [J,V] dense */
+  const int64_t* parents;         /* [J], parents[0] = -1 */
+  const float*   lbs_weights;     /* [V,J] */
+  const int64_t* faces;           /* [F,3] */
+  const int64_t* lmk_faces_idx;   /* [L] */
+  const float*   lmk_bary_coords; /* [L,3] */
+  const int64_t* extra_joint_idx; /* [E] */
+} airpose_smplx_model_host;
+
+int airpose_smplx_create(airpose_smplx_t** out, const airpose_smplx_model_host* model, int device);
+int airpose_smplx_destroy(airpose_smplx_t* h);
+/* max non-zeros per row found in lbs_weights (the skinning kernel iterates exactly these) */
+int airpose_smplx_skin_nnz(const airpose_smplx_t* h);
+
+/* Arguments of one SMPL-X forward.  Replaces, in one call:
+ *   SMPLX.forward(pose2rot=False)      body_models.py:820-994  (lbs.py:135-222, :96-132, :316-370)
+ *   VertexJointSelector.forward        vertex_joint_selector.py:73-77
+ *   transform_smpl                     copenet/src/copenet/utils/utils.py:237-256   (if root_R/root_t given)
+ *   perspective_projection             copenet/src/copenet/utils/geometry.py:63-91  (if out_j2d given)
+ * Rotation inputs are row-major 3x3 matrices.  A NULL rotation segment means identity
+ * (what the reference obtains from its zero Parameters via batch_rodrigues, :878-925).
+ * `*_stride` are in floats between consecutive meshes (so a [B,55,3,3] full_pose can be
+ * passed as three segments of one buffer with stride 495). */
+typedef struct {
+  int32_t batch;
+  int32_t num_betas;             /* columns of `betas` actually supplied (10, or 20 with expression) */
+  const float* betas;            /* [B,num_betas] */
+  int32_t betas_stride;
+  const float* global_orient;    /* joint 0        [B,1,3,3] or NULL */
+  int32_t global_orient_stride;
+  const float* body_pose;        /* joints 1..21   [B,21,3,3] or NULL */
+  int32_t body_pose_stride;
+  const float* tail_pose;        /* joints 22..54  [B,33,3,3] (jaw, eyes, hands) or NULL */
+  int32_t tail_pose_stride;
+  const float* transl;           /* [B,3] or NULL  (body_models.py:980-982) */
+  const float* root_R;           /* [B,3,3] or NULL: camera-frame rotation about the origin */
+  int32_t root_R_stride;
+  const float* root_t;           /* [B,3] or NULL */
+  int32_t root_t_stride;
+  float focal_x, focal_y;        /* constants.py:7 */
+  const float* center;           /* [B,2] principal point, or NULL */
+  int32_t center_stride;
+  float* out_vertices;           /* [B,V,3]   ModelOutput.vertices */
+  float* out_joints;             /* [B,127,3] ModelOutput.joints (55 + 21 + 51) */
+  float* out_vertices_cam;       /* [B,V,3]   or NULL */
+  float* out_joints_cam;         /* [B,127,3] or NULL */
+  float* out_joints_2d;          /* [B,127,2] or NULL */
+} airpose_smplx_fwd_args;
+
+int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * geometry helpers
+ * ---------------------------------------------------------------------------------- */
+/* rot6d_to_rotmat (copenet/src/copenet/utils/geometry.py:47-61): x [n,6] -> R [n,3,3].
+ * `x_row_stride` floats between rows of 6 (lets callers pass pred_pose[:,3:] in place). */
+int airpose_rot6d_to_rotmat(const float* x, int64_t n, float* R, void* stream);
+/* strided form: `groups` rows of `per_group` consecutive 6-vectors, rows `row_stride` floats apart */
+int airpose_rot6d_to_rotmat_strided(const float* x, int64_t groups, int32_t per_group, int64_t row_stride,
+                                    float* R, void* stream);
+/* SMPL joint -> 14 OpenPose joints (copenet_real_data/scripts/bundle_adj.py:48,116):
+ * out[b,i,:] = joints[b,map[i],:], a bit-exact gather. map=NULL selects the reference map. */
+int airpose_j14_gather(const float* joints, int32_t batch, int32_t num_joints, const int32_t* map_host,
+                       float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * ResNet-50 trunk + IEF regressor  (copenet/src/copenet/models/model_copenet.py)
+ * ---------------------------------------------------------------------------------- */
+typedef struct airpose_net airpose_net_t;
+
+/* One conv + its eval-mode BatchNorm, in the reference's parameter layout (DEVICE pointers,
+ * fp32).  Order of the 53 entries = forward order, see airpose_b200/synthetic.py conv_specs(). */
+typedef struct {
+  const float* weight;        /* [Cout,Cin,k,k]  nn.Conv2d.weight */
+  const float* bn_weight;     /* [Cout] gamma */
+  const float* bn_bias;       /* [Cout] beta */
+  const float* bn_mean;       /* [Cout] running_mean */
+  const float* bn_var;        /* [Cout] running_var */
+} airpose_conv_params;
+
+typedef struct {
+  airpose_conv_params conv[53];
+  const float* fc1_w;  const float* fc1_b;          /* [1024,2332], [1024] */
+  const float* fc2_w;  const float* fc2_b;          /* [1024,1024], [1024] */
+  const float* decpose_w;  const float* decpose_b;  /* [135,1024], [135] */
+  const float* decshape_w; const float* decshape_b; /* [10,1024], [10] */
+  const float* init_pose;                           /* [144] */
+  const float* init_shape;                          /* [10] */
+  float bn_eps;                                     /* 1e-5 */
+} airpose_net_params;
+
+/* max_images bounds the workspace: images per trunk call (two views of B pairs = 2B). */
+int airpose_net_create(airpose_net_t** out, int max_images, int device);
+int airpose_net_destroy(airpose_net_t* h);
+/* (Re)pack weights: bf16 K-major conv matrices, folded BN scale/shift, split-bf16 IEF matrices. */
+int airpose_net_load(airpose_net_t* h, const airpose_net_params* p, void* stream);
+
+/* copenet.forward_feat_ext (model_copenet.py:161-176), eval mode:
+ * x [n,3,224,224] fp32 NCHW -> feat [n,2048] fp32.  bf16 operands, fp32 accumulate. */
+int airpose_backbone_fwd(airpose_net_t* h, const float* x_nchw, int n_images, float* out_feat, void* stream);
+
+/* The regressor half of copenet.forward (model_copenet.py:118-159,178-204), eval mode.
+ * xf0/xf1 [B,2048]; bb0/bb1 [B,3]; pos0/pos1 [B,3] (already scaled, copenet_twoview.py:199-203);
+ * init_theta0/1 [B,>=132] or NULL (module init_pose); init_shape0/1 [B,10] or NULL.
+ * Outputs pred_pose [B,135], pred_betas [B,10] per view. */
+typedef struct {
+  int32_t batch;
+  int32_t iters;
+  const float* xf0; const float* xf1;
+  const float* bb0; const float* bb1;
+  const float* pos0; const float* pos1;
+  const float* init_theta0; const float* init_theta1; int32_t init_theta_stride;
+  const float* init_shape0; const float* init_shape1; int32_t init_shape_stride;
+  float* out_pose0; float* out_betas0; float* out_pose1; float* out_betas1;
+} airpose_ief_args;
+int airpose_ief_fwd(airpose_net_t* h, const airpose_ief_args* a, void* stream);
+
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+int64_t airpose_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * low-level building blocks, exported for the per-layer parity tests
+ * ---------------------------------------------------------------------------------- */
+/* D[M,N] = A[M,K] * B[N,K]^T on tcgen05 (bf16 operands, fp32 accumulate in TMEM).
+ * Epilogue: v = acc*scale[n] + shift[n] (+ residual[m,n] bf16) ; relu ; store bf16 and/or fp32.
+ * lda/ldb/ldd in elements.  scale may be NULL (=1). */
+typedef struct {
+  const void* A; int64_t lda;      /* bf16 [M,K] */
+  const void* B; int64_t ldb;      /* bf16 [N,K] */
+  int32_t M, N, K;
+  const float* scale; const float* shift;
+  const void* residual; int64_t ldr; /* bf16 [M,N] or NULL */
+  int32_t relu;
+  void*  out_bf16; int64_t ldd;     /* bf16 [M,N] or NULL */
+  float* out_f32;  int64_t ldf;     /* fp32 [M,N] or NULL */
+} airpose_gemm_args;
+int airpose_gemm_bf16(const airpose_gemm_args* g, void* stream);
+
+/* Implicit-GEMM convolution on NHWC bf16 through TMA im2col (3x3 / strided 1x1 convs).
+ * x [n,H,W,Cin] bf16, w [Cout, kh*kw*Cin] bf16 (tap-major, channel-minor), out [n,Ho,Wo,Cout]. */
+typedef struct {
+  const void* x; int32_t n, H, W, Cin;
+  const void* w; int32_t Cout, ksize, stride, pad;
+  const float* scale; const float* shift;
+  const void* residual;             /* bf16 [n,Ho,Wo,Cout] or NULL */
+  int32_t relu;
+  void* out;                        /* bf16 [n,Ho,Wo,Cout] */
+} airpose_conv_args;
+int airpose_conv_bf16(const airpose_conv_args* c, void* stream);
+
+/* Stem only (conv 7x7 s2 + BN + ReLU + MaxPool 3x3 s2, model_copenet.py:163-166):
+ * x [n,3,224,224] fp32 NCHW -> out [n,56,56,64] bf16 NHWC.  n <= the handle's chunk size. */
+int airpose_backbone_stem(airpose_net_t* h, const float* x_nchw, int n_images, void* out_nhwc_bf16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AIRPOSE_B200_H_ */

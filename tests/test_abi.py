@@ -1,0 +1,87 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/airpose_b200.h declares (no compute without a GPU), the ctypes table matches the
+header, the product path refuses to run without CUDA, and the module keeps the reference's
+state_dict keys."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from airpose_b200 import _lib, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "airpose_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(airpose_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = header_functions()
+    assert len(names) >= 17
+    lib = _lib.load()
+    for n in names:
+        assert hasattr(lib, n), "libairpose_b200.so does not export " + n
+    assert sorted(_lib.SYMBOLS) == names
+    assert lib.airpose_abi_version() == 1
+    assert lib.airpose_launch_count() == 0
+    assert lib.airpose_last_error() == b""
+
+
+def test_error_channel_reports_bad_arguments():
+    lib = _lib.load()
+    rc = lib.airpose_rot6d_to_rotmat(None, 4, None, None)     # rejected before any CUDA call
+    assert rc != 0
+    assert b"airpose_rot6d_to_rotmat" in lib.airpose_last_error()
+
+
+def test_no_cpu_fallback(tmp_path):
+    from airpose_b200.model_copenet import getcopenet
+    from airpose_b200.smplx import SMPLX
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+    net = getcopenet(mp, pretrained=False).eval()
+    with pytest.raises(_lib.AirposeError):
+        net.forward_feat_ext(torch.zeros(1, 3, 224, 224))
+    synthetic.write_smplx_model(str(tmp_path), 0)
+    sm = SMPLX(str(tmp_path), batch_size=1, create_transl=False)
+    with pytest.raises(_lib.AirposeError):
+        sm.forward(betas=torch.zeros(1, 10), body_pose=torch.eye(3).expand(1, 21, 3, 3), pose2rot=False)
+
+
+def test_state_dict_keys_match_reference_layout(tmp_path, net_state):
+    """331 entries, same names as the reference module."""
+    from airpose_b200.model_copenet import getcopenet
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+    net = getcopenet(mp, pretrained=False)
+    sd = net.state_dict()
+    assert len(sd) == 331
+    assert set(sd) == set(net_state)
+    assert sum(p.numel() for p in net.parameters()) == 27098324
+    assert tuple(sd["fc1.weight"].shape) == (1024, 2332)
+    for k, v in net_state.items():
+        assert tuple(sd[k].shape) == tuple(np.asarray(v).shape), k
+    specs = list(synthetic.conv_specs())
+    assert len(specs) == 53
+    assert [s[0] for s in specs] == [n[:-7] for n, m in ((n + ".weight", m) for n, m in net.named_modules()
+                                                       if isinstance(m, torch.nn.Conv2d))]
+    # Lightning checkpoints prefix the network with "model." (airpose_server/server.py:16-22)
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in net_state.items()}, strict=True)
+
+
+def test_smplx_module_surface(tmp_path):
+    from airpose_b200.smplx import SMPLX, ModelOutput
+    synthetic.write_smplx_model(str(tmp_path), 0)
+    sm = SMPLX(str(tmp_path), batch_size=3, create_transl=False)
+    assert sm.batch_size == 3 and not hasattr(sm, "transl")
+    assert tuple(sm.v_template.shape) == (10475, 3) and sm.faces.shape == (20908, 3)
+    assert tuple(sm.posedirs.shape) == (486, 31425) and int(sm.parents[0]) == -1
+    assert sm.faces_tensor.dtype == torch.long
+    assert tuple(sm.betas.shape) == (3, 10) and tuple(sm.expression.shape) == (3, 10)
+    assert sm.vertex_joint_selector.extra_joints_idxs.tolist()[:5] == [9120, 9929, 9448, 616, 6]
+    assert ModelOutput._fields[:2] == ("vertices", "joints")
+    with pytest.raises(NotImplementedError):
+        sm.forward(betas=torch.zeros(3, 10), pose2rot=True)

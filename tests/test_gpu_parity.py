@@ -1,0 +1,328 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the numpy oracle, the golden
+fixtures made from the real reference, and -- for the floating-point GEMM/conv kernels --
+a plain PyTorch fp32 reference of the same op on bf16-rounded operands."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import airpose_oracle as orc
+from airpose_b200 import _lib, synthetic
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def smplx_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("smplx_model")
+    synthetic.write_smplx_model(str(d), 0)
+    return str(d)
+
+
+@pytest.fixture(scope="module")
+def smplx_gpu(smplx_dir):
+    from airpose_b200.smplx import SMPLX
+    return SMPLX(smplx_dir, batch_size=4, create_transl=False).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def net_gpu(tmp_path_factory, net_state):
+    from airpose_b200.model_copenet import getcopenet
+    mp = synthetic.write_mean_params(str(tmp_path_factory.mktemp("mean") / "smpl_mean_params.npz"))
+    net = getcopenet(mp, pretrained=False)
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in net_state.items()}, strict=True)
+    return net.to(DEV).eval()
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+# ----------------------------------------------------------------------------- SMPL-X
+@pytest.mark.parametrize("B", [1, 5, 33])
+def test_smplx_matches_oracle(smplx_gpu, smplx_oracle, B):
+    li = synthetic.make_lbs_inputs(B, seed=100 + B)
+    eye = torch.eye(3, device=DEV).view(1, 1, 3, 3).repeat(B, 1, 1, 1)
+    out = smplx_gpu.forward(betas=t(li["betas"]), body_pose=t(li["body_pose"]), global_orient=eye,
+                            transl=torch.zeros(B, 3, device=DEV), pose2rot=False)
+    v, j = orc.smplx_forward(smplx_oracle, li["betas"], li["body_pose"], transl=np.zeros((B, 3), np.float32))
+    assert out.vertices.shape == (B, 10475, 3) and out.joints.shape == (B, 127, 3)
+    ev, ej = rel_err(out.vertices.cpu().numpy(), v), rel_err(out.joints.cpu().numpy(), j)
+    print("smplx B=%d rel err verts %.3e joints %.3e" % (B, ev, ej))
+    assert ev < 1e-5 and ej < 1e-5          # north_star tolerance is 1e-3 relative fp32
+    # KAT 4: the 21 extra joints are a bit-exact gather of the kernel's own vertices
+    idx = torch.from_numpy(orc.SMPLX_EXTRA_JOINT_VERTS).to(DEV)
+    assert torch.equal(out.joints[:, 55:76], out.vertices[:, idx])
+
+
+def test_smplx_matches_reference_golden(smplx_gpu, golden_lbs):
+    B = int(golden_lbs["batch"])
+    li = synthetic.make_lbs_inputs(B, seed=int(golden_lbs["lbs_seed"]))
+    out = smplx_gpu.forward(betas=t(li["betas"]), body_pose=t(li["body_pose"]), pose2rot=False,
+                            transl=torch.zeros(B, 3, device=DEV))
+    assert rel_err(out.vertices.cpu().numpy(), golden_lbs["vertices"]) < 1e-5
+    assert rel_err(out.joints.cpu().numpy(), golden_lbs["joints"]) < 1e-5
+    # reduced call: module's zero betas (copenet_twoview.py:575-582); batch_size=4 module, B=3 poses -> use B rows
+    from airpose_b200.smplx import SMPLX
+    out0 = smplx_gpu.forward(betas=torch.zeros(B, 10, device=DEV), body_pose=t(li["body_pose"]), pose2rot=False)
+    assert rel_err(out0.joints.cpu().numpy(), golden_lbs["joints_zero_betas"]) < 1e-5
+
+
+def test_smplx_rest_pose_kat(smplx_gpu, smplx_oracle):
+    eye = torch.eye(3, device=DEV).view(1, 1, 3, 3).repeat(2, 21, 1, 1)
+    out = smplx_gpu.forward(betas=torch.zeros(2, 10, device=DEV), body_pose=eye, pose2rot=False)
+    assert np.abs(out.vertices[0].cpu().numpy() - smplx_oracle.v_template).max() < 1e-6
+    jr = smplx_oracle.J_regressor @ smplx_oracle.v_template
+    assert np.abs(out.joints[1, :55].cpu().numpy() - jr).max() < 1e-6
+
+
+def test_smplx_full_pose_and_expression(smplx_gpu, smplx_oracle):
+    """All 25 body/face joints rotated and a non-zero expression: the general path of lbs()."""
+    B = 3
+    rng = np.random.default_rng(5)
+    six = np.tile(np.array([1, 0, 0, 1, 0, 0], np.float32), (B, 55, 1)) + rng.standard_normal((B, 55, 6)).astype(np.float32) * 0.3
+    R = synthetic.rot6d_to_rotmat_np(six.reshape(-1, 6)).reshape(B, 55, 3, 3)
+    R[:, 25:] = np.eye(3, dtype=np.float32)          # hands stay at the module's zero parameters
+    betas = rng.standard_normal((B, 10)).astype(np.float32)
+    expr = rng.standard_normal((B, 10)).astype(np.float32)
+    transl = rng.standard_normal((B, 3)).astype(np.float32)
+    out = smplx_gpu.forward(betas=t(betas), expression=t(expr), global_orient=t(R[:, :1]), body_pose=t(R[:, 1:22]),
+                            jaw_pose=t(R[:, 22:23]), leye_pose=t(R[:, 23:24]), reye_pose=t(R[:, 24:25]),
+                            transl=t(transl), pose2rot=False, return_full_pose=True)
+    v, j = orc.lbs(np.concatenate([betas, expr], 1), R, smplx_oracle)
+    ev = rel_err(out.vertices.cpu().numpy(), v + transl[:, None])
+    ej = rel_err(out.joints[:, :55].cpu().numpy(), j + transl[:, None])
+    print("full pose rel err verts %.3e joints %.3e" % (ev, ej))
+    assert ev < 1e-5 and ej < 1e-5
+    assert out.full_pose.shape == (B, 55, 3, 3)
+
+
+def test_smplx_fused_camera_outputs(smplx_gpu, smplx_oracle):
+    B = 4
+    li = synthetic.make_lbs_inputs(B, seed=9)
+    rng = np.random.default_rng(9)
+    Rr = synthetic.rot6d_to_rotmat_np(np.array([1, 0, 0, 1, 0, 0], np.float32) + rng.standard_normal((B, 6)).astype(np.float32) * 0.4)
+    tr = (np.array([0, 0, 9], np.float32) + rng.standard_normal((B, 3)).astype(np.float32))
+    cc = np.tile(np.array([960.0, 540.0], np.float32), (B, 1))
+    mo, cam = smplx_gpu.forward_camera(betas=t(li["betas"]), body_pose=t(li["body_pose"]), pose2rot=False,
+                                       root_R=t(Rr), root_t=t(tr), focal_length=(1475.0, 1475.0), camera_center=t(cc))
+    v, j = orc.smplx_forward(smplx_oracle, li["betas"], li["body_pose"])
+    vc, jc = orc.transform_smpl(np.concatenate([Rr, tr[:, :, None]], 2), v, j)
+    j2 = orc.perspective_projection(jc, (1475.0, 1475.0), cc)
+    assert rel_err(cam["vertices_cam"].cpu().numpy(), vc) < 1e-5
+    assert rel_err(cam["joints_cam"].cpu().numpy(), jc) < 1e-5
+    assert rel_err(cam["joints_2d"].cpu().numpy(), j2) < 1e-5
+    # KAT 5: shifting the translation shifts the camera-frame vertices by exactly that much
+    _, cam2 = smplx_gpu.forward_camera(betas=t(li["betas"]), body_pose=t(li["body_pose"]), pose2rot=False,
+                                       root_R=t(Rr), root_t=t(tr + np.float32(0.5)))
+    assert (cam2["vertices_cam"] - cam["vertices_cam"] - 0.5).abs().max().item() < 1e-5
+
+
+def test_rot6d_and_j14():
+    from airpose_b200.smplx import rot6d_to_rotmat, joints_to_j14
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((7, 135)).astype(np.float32)
+    R = rot6d_to_rotmat(t(x)[:, 3:]).cpu().numpy()
+    assert rel_err(R, orc.rot6d_to_rotmat(x[:, 3:])) < 1e-6
+    j = rng.standard_normal((5, 127, 3)).astype(np.float32)
+    assert np.array_equal(joints_to_j14(t(j)).cpu().numpy(), orc.j14_from_joints(j))     # bit-exact index map
+
+
+# ----------------------------------------------------------------------------- GEMM / conv
+def _bf16(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 64, 128), (300, 192, 320), (4, 64, 96), (1000, 256, 2304),
+                                   (6272, 2048, 512), (25088, 64, 64), (128, 1024, 6144)])
+def test_gemm_bf16_matches_torch(M, N, K):
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = _bf16(torch.randn(M, K, generator=g)).to(DEV)
+    Bm = _bf16(torch.randn(N, K, generator=g)).to(DEV)
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+    a = _lib.GemmArgs()
+    a.A, a.lda, a.B, a.ldb = A.data_ptr(), K, Bm.data_ptr(), K
+    a.M, a.N, a.K = M, N, K
+    a.out_f32, a.ldf = out.data_ptr(), N
+    _lib.check(lib.airpose_gemm_bf16(C.byref(a), _lib.current_stream()), "gemm")
+    torch.cuda.synchronize()
+    ref = A.float() @ Bm.float().t()
+    err = (out - ref).abs().max().item() / ref.abs().max().item()
+    print("gemm %dx%dx%d rel err %.3e" % (M, N, K, err))
+    assert err < 1e-5
+
+
+def test_gemm_epilogue_scale_shift_residual_relu():
+    lib = _lib.load()
+    M, N, K = 700, 256, 192
+    g = torch.Generator(device="cpu").manual_seed(1)
+    A = _bf16(torch.randn(M, K, generator=g)).to(DEV)
+    Bm = _bf16(torch.randn(N, K, generator=g)).to(DEV)
+    scale = torch.rand(N, generator=g).to(DEV) + 0.5
+    shift = torch.randn(N, generator=g).to(DEV)
+    res = _bf16(torch.randn(M, N, generator=g)).to(DEV)
+    out = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    a = _lib.GemmArgs()
+    a.A, a.lda, a.B, a.ldb = A.data_ptr(), K, Bm.data_ptr(), K
+    a.M, a.N, a.K = M, N, K
+    a.scale, a.shift, a.residual, a.ldr, a.relu = scale.data_ptr(), shift.data_ptr(), res.data_ptr(), N, 1
+    a.out_bf16, a.ldd = out.data_ptr(), N
+    _lib.check(lib.airpose_gemm_bf16(C.byref(a), _lib.current_stream()), "gemm")
+    torch.cuda.synchronize()
+    ref = torch.relu((A.float() @ Bm.float().t()) * scale + shift + res.float())
+    # one bf16 rounding of the output: half an ulp = 2^-9 relative
+    assert ((out.float() - ref).abs() <= ref.abs() * 2.0 ** -8 + 1e-3).all()
+
+
+@pytest.mark.parametrize("n,H,Cin,Cout,k,stride", [(2, 56, 64, 64, 3, 1), (3, 28, 128, 128, 3, 2), (2, 56, 256, 512, 1, 2),
+                                                   (5, 14, 256, 256, 3, 1), (3, 14, 512, 512, 3, 2), (1, 7, 512, 512, 3, 1),
+                                                   (2, 56, 64, 256, 1, 1)])
+def test_conv_implicit_gemm_matches_torch(n, H, Cin, Cout, k, stride):
+    lib = _lib.load()
+    pad = k // 2
+    g = torch.Generator(device="cpu").manual_seed(n * H + Cin + Cout + k)
+    x = _bf16(torch.randn(n, H, H, Cin, generator=g)).to(DEV)                          # NHWC
+    w = _bf16(torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (k * k * Cin)) ** 0.5).to(DEV)
+    wk = w.permute(0, 2, 3, 1).contiguous().view(Cout, k * k * Cin)                    # [Cout][tap][Cin]
+    scale = (torch.rand(Cout, generator=g) + 0.5).to(DEV)
+    shift = torch.randn(Cout, generator=g).to(DEV)
+    Ho = (H + 2 * pad - k) // stride + 1
+    res = _bf16(torch.randn(n, Ho, Ho, Cout, generator=g)).to(DEV)
+    out = torch.zeros(n, Ho, Ho, Cout, device=DEV, dtype=torch.bfloat16)
+    a = _lib.ConvArgs()
+    a.x, a.n, a.H, a.W, a.Cin = x.data_ptr(), n, H, H, Cin
+    a.w, a.Cout, a.ksize, a.stride, a.pad = wk.data_ptr(), Cout, k, stride, pad
+    a.scale, a.shift, a.residual, a.relu, a.out = scale.data_ptr(), shift.data_ptr(), res.data_ptr(), 1, out.data_ptr()
+    _lib.check(lib.airpose_conv_bf16(C.byref(a), _lib.current_stream()), "conv")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), stride=stride, padding=pad)
+    ref = torch.relu(ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + res.float().permute(0, 3, 1, 2))
+    got = out.float().permute(0, 3, 1, 2)
+    bad = ((got - ref).abs() > ref.abs() * 2.0 ** -8 + 2e-3)
+    print("conv n=%d H=%d %d->%d k=%d s=%d: max abs err %.3e, bad %d / %d" %
+          (n, H, Cin, Cout, k, stride, (got - ref).abs().max().item(), int(bad.sum()), bad.numel()))
+    assert not bad.any()
+
+
+# ----------------------------------------------------------------------------- network
+def test_trunk_matches_oracle_and_golden(net_gpu, net_state, golden_twoview):
+    x = synthetic.make_inputs(2, int(golden_twoview["in_seed"]))
+    xf = net_gpu.forward_feat_ext(t(np.concatenate([x["im0"], x["im1"]]))).cpu().numpy()
+    gold = np.concatenate([golden_twoview["bf16/xf0"], golden_twoview["bf16/xf1"]])
+    gold32 = np.concatenate([golden_twoview["fp32/xf0"], golden_twoview["fp32/xf1"]])
+    e_b, e_f = rel_err(xf, gold), rel_err(xf, gold32)
+    m_b = np.abs(xf - gold).mean() / np.abs(gold).mean()
+    print("trunk vs reference(bf16 rounding points): max-rel %.3e mean-rel %.3e ; vs reference fp32: %.3e" % (e_b, m_b, e_f))
+    # two bf16 implementations agree to ~1e-3 after 53 layers (tests/test_oracle_golden.py); bf16-vs-fp32 is 2.8e-3
+    assert e_b < 5e-3 and m_b < 2.5e-3
+    assert e_f < 1e-2
+
+
+def _conv_abi(x_nhwc, w_oihw, bn, sd, stride, pad, residual=None, relu=True):
+    """One conv+BN(+residual)+ReLU through airpose_conv_bf16 with weights packed here."""
+    lib = _lib.load()
+    Cout, Cin, k, _ = w_oihw.shape
+    wk = torch.from_numpy(w_oihw).to(DEV).to(torch.bfloat16).permute(0, 2, 3, 1).contiguous().view(Cout, k * k * Cin)
+    scale = sd[bn + ".weight"] / np.sqrt(sd[bn + ".running_var"] + np.float32(1e-5))
+    shift = sd[bn + ".bias"] - sd[bn + ".running_mean"] * scale
+    scale, shift = t(scale.astype(np.float32)), t(shift.astype(np.float32))
+    n, H, W, _ = x_nhwc.shape
+    Ho = (H + 2 * pad - k) // stride + 1
+    out = torch.zeros(n, Ho, Ho, Cout, device=DEV, dtype=torch.bfloat16)
+    a = _lib.ConvArgs()
+    a.x, a.n, a.H, a.W, a.Cin = x_nhwc.data_ptr(), n, H, W, Cin
+    a.w, a.Cout, a.ksize, a.stride, a.pad = wk.data_ptr(), Cout, k, stride, pad
+    a.scale, a.shift, a.relu, a.out = scale.data_ptr(), shift.data_ptr(), int(relu), out.data_ptr()
+    if residual is not None:
+        a.residual = residual.data_ptr()
+    _lib.check(lib.airpose_conv_bf16(C.byref(a), _lib.current_stream()), "conv")
+    torch.cuda.synchronize()
+    return out
+
+
+def test_stem_and_first_block_tight(net_gpu, net_state):
+    """Stem and the first bottleneck against the oracle with identical rounding points: errors
+    here are single bf16 ulps, not 53 layers of drift."""
+    lib = _lib.load()
+    x = synthetic.make_inputs(2, 77)["im0"]
+    sd = net_state
+    y = np.maximum(orc.batchnorm_eval(orc.conv2d(orc.round_bf16(x), orc.round_bf16(sd["conv1.weight"]), 2, 3), sd, "bn1"), 0)
+    y = orc.round_bf16(orc.maxpool_3x3_s2_p1(y))                                       # NCHW [2,64,56,56]
+    net_gpu.forward_feat_ext(t(x))                                                     # builds + loads the handle
+    stem = torch.zeros(2, 56, 56, 64, device=DEV, dtype=torch.bfloat16)
+    _lib.check(lib.airpose_backbone_stem(net_gpu._handle, t(x).data_ptr(), 2, stem.data_ptr(), _lib.current_stream()), "stem")
+    torch.cuda.synchronize()
+    got = stem.float().permute(0, 3, 1, 2).cpu().numpy()
+    d = np.abs(got - y)
+    frac = (d > np.abs(y) * 2.0 ** -7 + 1e-3).mean()
+    print("stem: max abs err %.3e (max %.3e), fraction off by more than one bf16 ulp %.2e" % (d.max(), np.abs(y).max(), frac))
+    assert frac < 1e-3 and d.max() < 0.02 * np.abs(y).max()
+
+    ref = orc.bottleneck(y, sd, "layer1.0", 1, True, True)                             # NCHW
+    xin = t(y.transpose(0, 2, 3, 1)).to(torch.bfloat16).contiguous()
+    p = "layer1.0"
+    t1 = _conv_abi(xin, sd[p + ".conv1.weight"], p + ".bn1", sd, 1, 0)
+    t2 = _conv_abi(t1, sd[p + ".conv2.weight"], p + ".bn2", sd, 1, 1)
+    ds = _conv_abi(xin, sd[p + ".downsample.0.weight"], p + ".downsample.1", sd, 1, 0, relu=False)
+    o = _conv_abi(t2, sd[p + ".conv3.weight"], p + ".bn3", sd, 1, 0, residual=ds)
+    got = o.float().permute(0, 3, 1, 2).cpu().numpy()
+    d = np.abs(got - ref)
+    frac = (d > np.abs(ref) * 2.0 ** -7 + 2e-3).mean()
+    print("layer1.0: max abs err %.3e (max %.3e), fraction off by more than one bf16 ulp %.2e" % (d.max(), np.abs(ref).max(), frac))
+    assert frac < 1e-3 and d.max() < 0.03 * np.abs(ref).max()
+
+
+def test_ief_matches_oracle(net_gpu, net_state):
+    B = 6
+    rng = np.random.default_rng(3)
+    xf0 = np.abs(rng.standard_normal((B, 2048))).astype(np.float32) * 0.6
+    xf1 = np.abs(rng.standard_normal((B, 2048))).astype(np.float32) * 0.6
+    bb0 = rng.uniform(-1, 1, (B, 3)).astype(np.float32)
+    bb1 = rng.uniform(-1, 1, (B, 3)).astype(np.float32)
+    pos = np.tile(np.array([0, 0, 0.5], np.float32), (B, 1))
+    for iters in (1, 3):
+        got = net_gpu._ief(t(xf0), t(xf1), t(bb0), t(bb1), t(pos), t(pos), None, None, None, None, iters)
+        ref = orc.ief_forward(net_state, xf0, xf1, bb0, bb1, pos, pos, iters)
+        errs = [rel_err(g.cpu().numpy(), r) for g, r in zip(got, ref)]
+        print("ief iters=%d rel errs %s" % (iters, ["%.2e" % e for e in errs]))
+        assert max(errs) < 1e-4          # split-bf16 tensor-core GEMMs, ~2^-16 per product
+
+
+def test_twoview_end_to_end(net_gpu, net_state, smplx_dir, smplx_oracle, golden_twoview, tmp_path):
+    from argparse import Namespace
+    from airpose_b200.copenet_twoview import copenet_twoview
+    g = golden_twoview
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+    mod = copenet_twoview(Namespace(smpl_mean_params=mp, smplx_model_dir=smplx_dir, batch_size=2, val_batch_size=2,
+                                    reg_iters=3))
+    mod.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in net_state.items()})
+    mod = mod.to(DEV).eval()
+    x = synthetic.make_inputs(2, int(g["in_seed"]))
+    out = mod.fwd_pass({k: t(v) for k, v in x.items()})
+    # (1) against the reference run with bf16 rounding points in the trunk
+    for v in (0, 1):
+        ep = np.abs(out["pred_pose%d" % v].cpu().numpy() - g["bf16/pred_pose%d" % v]).max()
+        e2 = np.abs(out["pred_joints_2d_cam%d" % v].cpu().numpy() - g["bf16/pred_joints_2d_cam%d" % v]).max()
+        print("view %d vs reference(bf16 points): pose max abs %.3e, j2d max abs %.3f px" % (v, ep, e2))
+        assert ep < 2e-2 and e2 < 10.0
+    # (2) everything downstream of the trunk against the oracle fed with OUR features: tight
+    xf = mod.model.forward_feat_ext(t(np.concatenate([x["im0"], x["im1"]]))).cpu().numpy()
+    ref = orc.twoview_forward(net_state, smplx_oracle, x, feats=(xf[:2], xf[2:]))
+    for v in (0, 1):
+        for k in ("pred_pose", "pred_betas", "pred_rotmat", "pred_vertices_cam", "pred_joints_cam", "pred_joints_2d_cam"):
+            e = rel_err(out["%s%d" % (k, v)].cpu().numpy(), ref["%s%d" % (k, v)])
+            print("  %s%d rel err %.3e" % (k, v, e))
+            assert e < 1e-3, (k, v, e)                      # north_star: 1e-3 relative fp32
+        assert rel_err(out["pred_output_cam%d" % v].vertices.cpu().numpy(), ref["vertices%d" % v]) < 1e-3
+        assert rel_err(out["pred_output_cam%d" % v].joints.cpu().numpy(), ref["joints%d" % v]) < 1e-3
+    # KAT 6: swapping the views swaps the outputs
+    xs = {k: t(v) for k, v in x.items()}
+    for k in ("im", "bb", "intr"):
+        xs[k + "0"], xs[k + "1"] = xs[k + "1"], xs[k + "0"]
+    outs = mod.fwd_pass(xs)
+    assert torch.equal(outs["pred_pose0"], out["pred_pose1"]) and torch.equal(outs["pred_betas1"], out["pred_betas0"])
