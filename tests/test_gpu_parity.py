@@ -127,7 +127,7 @@ def test_rot6d_and_j14():
     rng = np.random.default_rng(2)
     x = rng.standard_normal((7, 135)).astype(np.float32)
     R = rot6d_to_rotmat(t(x)[:, 3:]).cpu().numpy()
-    assert rel_err(R, orc.rot6d_to_rotmat(x[:, 3:])) < 1e-6
+    assert rel_err(R, orc.rot6d_to_rotmat(x[:, 3:])) < 5e-6   # fp32 rounding of the two normalisations
     j = rng.standard_normal((5, 127, 3)).astype(np.float32)
     assert np.array_equal(joints_to_j14(t(j)).cpu().numpy(), orc.j14_from_joints(j))     # bit-exact index map
 
