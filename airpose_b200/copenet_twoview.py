@@ -38,7 +38,16 @@ class copenet_twoview(nn.Module):
         return self.model(**kwargs)
 
     @torch.no_grad()
-    def fwd_pass(self, input_batch):
+    def fwd_pass(self, input_batch, profile=None):
+        """``profile``: optional dict that receives CUDA event pairs around the trunk, the regressor
+        and the two SMPL-X calls (bench.py reads the stage times from them)."""
+
+        def mark(name, done=False):
+            if profile is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                profile.setdefault(name, []).append(ev)
+
         im0, im1 = input_batch["im0"].float(), input_batch["im1"].float()
         bb0, bb1 = input_batch["bb0"], input_batch["bb1"]
         intr = (input_batch["intr0"], input_batch["intr1"])
@@ -46,9 +55,14 @@ class copenet_twoview(nn.Module):
         dev = im0.device
         in_trans = torch.tensor([0.0, 0.0, 10.0], device=dev).expand(B, -1).clone() * TRANS_SCALE      # :184-203
         reg_iters = getattr(self.hparams, "reg_iters", 3)
-        pred = self.forward(x0=im0, x1=im1, bb0=bb0, bb1=bb1, init_position0=in_trans, init_position1=in_trans,
-                            iters=reg_iters)
+        mark("trunk")
+        xf = self.model.forward_feat_ext(torch.cat([im0, im1], dim=0))          # both views, one call (eval-mode BN)
+        mark("trunk")
+        mark("ief")
+        pred = self.model._ief(xf[:B], xf[B:], bb0, bb1, in_trans, in_trans, None, None, None, None, reg_iters)
+        mark("ief")
         out = {}
+        mark("smplx")
         for v in (0, 1):
             pose, betas = pred[2 * v], pred[2 * v + 1]
             pose[:, :3] /= TRANS_SCALE                                   # in-place on the view, like :214-218
@@ -65,4 +79,5 @@ class copenet_twoview(nn.Module):
                         "pred_output_cam%d" % v: mo,
                         "pred_vertices_cam%d" % v: cam["vertices_cam"], "pred_joints_cam%d" % v: cam["joints_cam"],
                         "pred_joints_2d_cam%d" % v: cam["joints_2d"]})
+        mark("smplx")
         return out

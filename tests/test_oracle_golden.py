@@ -116,3 +116,17 @@ def test_round_bf16_matches_torch():
     import torch
     x = np.random.default_rng(0).standard_normal(4096).astype(np.float32) * 37.0
     assert np.array_equal(orc.round_bf16(x), torch.from_numpy(x).to(torch.bfloat16).float().numpy())
+
+
+def test_torch_port_matches_reference(net_state, smplx_data, golden_twoview):
+    """The PyTorch-CPU port timed as bench.py's reference arm reproduces the real reference."""
+    import torch
+    import torch_port as tp
+    g = golden_twoview
+    x = {k: torch.from_numpy(v) for k, v in synthetic.make_inputs(2, int(g["in_seed"])).items()}
+    with torch.no_grad():
+        out = tp.twoview_forward(tp.to_torch(net_state), tp.Smplx(smplx_data), x)
+    for v in (0, 1):
+        for k in ("pred_pose", "pred_betas", "pred_vertices_cam", "pred_joints_cam", "pred_joints_2d_cam"):
+            assert rel_err(out["%s%d" % (k, v)].numpy(), g["fp32/%s%d" % (k, v)]) < 2e-5, k
+    assert rel_err(out["xf0"].numpy(), g["fp32/xf0"]) < 1e-5
