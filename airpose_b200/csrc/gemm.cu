@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -332,6 +333,16 @@ int num_sms() {
   return n;
 }
 
+bool use_tma_epilogue() {
+  static const bool on = getenv("AIRPOSE_NO_TMA_EPI") == nullptr;
+  return on;
+}
+
+bool use_pdl() {
+  static const bool on = getenv("AIRPOSE_NO_PDL") == nullptr;
+  return on;
+}
+
 int pick_block_n(int M, int N) {
   const int tiles_m = ceil_div(M, kBlockM);
   if (N % 256 == 0 && (int64_t)tiles_m * (N / 256) >= 2 * num_sms()) return 256;
@@ -354,6 +365,7 @@ static int launch_bn(const GemmLaunch& L, const KParams& kp, cudaStream_t stream
 }
 
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
+  if (L.tma_epi) return launch_gemm_tma(L, stream);
   AP_REQUIRE(L.M > 0 && L.N > 0 && L.K > 0, "launch_gemm: empty problem %dx%dx%d", L.M, L.N, L.K);
   AP_REQUIRE(L.N % 8 == 0, "launch_gemm: N=%d must be a multiple of 8", L.N);
   const Epilogue& e = L.epi;
@@ -401,6 +413,7 @@ extern "C" int airpose_gemm_bf16(const airpose_gemm_args* g, void* stream) {
   L.epi.relu = g->relu;
   L.epi.out_bf16 = g->out_bf16; L.epi.ldd = g->ldd;
   L.epi.out_f32 = g->out_f32; L.epi.ldf = g->ldf;
+  if (use_tma_epilogue() && tma_epilogue_eligible(L) && enable_tma_epilogue(&L)) return 1;
   return launch_gemm(L, (cudaStream_t)stream);
 }
 
@@ -421,5 +434,6 @@ extern "C" int airpose_conv_bf16(const airpose_conv_args* c, void* stream) {
   L.epi.residual = c->residual; L.epi.ldr = c->Cout;
   L.epi.relu = c->relu;
   L.epi.out_bf16 = c->out; L.epi.ldd = c->Cout;
+  if (use_tma_epilogue() && tma_epilogue_eligible(L) && enable_tma_epilogue(&L)) return 1;
   return launch_gemm(L, (cudaStream_t)stream);
 }

@@ -29,12 +29,22 @@ struct ConvGeom {
 struct GemmLaunch {
   CUtensorMap tmA;     // tiled [M,K] map, or im2col map over (C,W,H,N)
   CUtensorMap tmB;     // tiled [N,K] map
+  CUtensorMap tmD;     // tma_epi: tiled [M,N] bf16 output map, box 128 rows x 64 cols, 128B swizzle
+  CUtensorMap tmR;     // tma_epi: same shape over the bf16 residual (valid when epi.residual != null)
   int M = 0, N = 0, K = 0;
   int block_n = 128;   // 64, 128 or 256
   int im2col = 0;
+  int tma_epi = 0;     // 1: bf16 output through smem staging + TMA store (gemm_tma.cu); 0: direct stores (gemm.cu)
+  int pdl = 0;         // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
   ConvGeom geom;
   Epilogue epi;
 };
+
+// True when the epilogue can run through TMA (bf16 output only, whole 64-column chunks).
+bool tma_epilogue_eligible(const GemmLaunch& L);
+// Builds tmD / tmR from epi.out_bf16 / epi.residual and sets tma_epi (call after epi is filled in).
+int enable_tma_epilogue(GemmLaunch* L);
+int launch_gemm_tma(const GemmLaunch& L, cudaStream_t stream);
 
 // Tensor maps (cuTensorMapEncode* resolved through cudaGetDriverEntryPoint; no libcuda link).
 int make_tmap_tiled_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems,
@@ -43,6 +53,8 @@ int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, const ConvGeom& g,
                           int pixels_per_column);
 
 int pick_block_n(int M, int N);
+bool use_tma_epilogue();   // off with AIRPOSE_NO_TMA_EPI=1 (A/B runs)
+bool use_pdl();            // off with AIRPOSE_NO_PDL=1
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream);
 int num_sms();
 

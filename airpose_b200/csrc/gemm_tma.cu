@@ -1,0 +1,356 @@
+// tcgen05 GEMM / implicit conv with a TMA epilogue -- the kernel every conv of the ResNet-50
+// trunk runs on (copenet/src/copenet/models/model_copenet.py:27-47,161-176).
+//
+// Same mainloop as gemm.cu (TMA -> 128B-swizzled smem ring -> tcgen05.mma into a
+// double-buffered TMEM accumulator); what changes is everything that touches HBM in the
+// epilogue, because most of the trunk's layers are bound by bytes, not flops:
+//   - the bf16 residual tile arrives through TMA into swizzled smem (its own 2-deep ring),
+//   - the output tile is packed to bf16 in 128x64 chunks in swizzled smem and leaves through
+//     TMA stores (full 128-byte lines, M tail clipped by the tensor map),
+//   - the kernel is launched with programmatic stream serialization: barrier init, TMEM
+//     allocation and descriptor prefetch overlap the previous layer's tail.
+//
+// CTA = 7 warps, one CTA per SM, static round-robin over 128 x BN tiles:
+//   warp 0    A/B TMA producer     warp 1   MMA issuer     warp 2   residual TMA producer
+//   warps 3-6 epilogue: tcgen05.ld -> scale/shift (+residual) -> relu -> bf16 -> smem -> TMA store
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace airpose {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kThreads = 224;
+constexpr int kEpiWarp0 = 3;
+constexpr int kEpiThreads = 128;
+constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr int kChunkN = 64;                       // epilogue chunk: 128 rows x 64 bf16 = one 128B-swizzle box
+constexpr int kChunkBytes = kBlockM * kChunkN * 2;
+constexpr int kResBufs = 2;
+
+struct KP {
+  int M, N, K;
+  int num_kb, tiles_m, tiles_n;
+  int im2col, cblks, ksize, stride, pad, Wo, HoWo;
+  int has_res, relu;
+  const float* scale;
+  const float* shift;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  // 3 output buffers need one barrier per chunk; BN=256 has room for 2 only and pays a second barrier
+  static constexpr int kOutBufs = (BN == 256) ? 2 : 3;
+  static constexpr int kRing = kStages * kStageBytes;
+  static constexpr int kOutOff = kRing;
+  static constexpr int kResOff = kOutOff + kOutBufs * kChunkBytes;
+  static constexpr int kBarOff = kResOff + kResBufs * kChunkBytes;
+  static constexpr int kNumBars = 2 * kStages + 4 + 2 * kResBufs;
+  static constexpr int kScaleOff = kBarOff + kNumBars * 8 + 16;
+  static constexpr int kSmemBytes = 1024 + kScaleOff + 2 * 2 * BN * 4;
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const KP p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* rfull_bar = tempty_bar + 2;
+  uint64_t* rempty_bar = rfull_bar + kResBufs;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty_bar + kResBufs);
+  float* sc_s = reinterpret_cast<float*>(smem + C::kScaleOff);   // [2][BN]
+  float* sh_s = sc_s + 2 * BN;                                   // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmD);
+    if (p.has_res) ptx::prefetch_tmap(&tmR);
+    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], kEpiThreads / 32); }
+    for (int s = 0; s < kResBufs; ++s) { ptx::mbar_init(&rfull_bar[s], 1); ptx::mbar_init(&rempty_bar[s], kEpiThreads / 32); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Everything above overlapped the previous kernel; its output (our A operand / residual) is
+  // visible only after this point.
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ A/B TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+        const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
+        int cw = 0, ch = 0, cn = 0;
+        if (p.im2col) {
+          cn = m0 / p.HoWo;
+          const int rem = m0 - cn * p.HoWo;
+          const int po = rem / p.Wo, qo = rem - po * p.Wo;
+          cw = qo * p.stride - p.pad;
+          ch = po * p.stride - p.pad;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+          uint8_t* sa = smem + stage * C::kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+          if (p.im2col) {
+            const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
+            const int r = tap / p.ksize, s = tap - r * p.ksize;
+            ptx::tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * kBlockK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+          } else {
+            ptx::tma_load_2d(&tmA, &full_bar[stage], sa, kb * kBlockK, m0);
+          }
+          ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * kBlockK, n0);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, 200 + as);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase, 300 + stage);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
+          const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ residual TMA producer
+    if (lane == 0 && p.has_res) {
+      int rs = 0; uint32_t rphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+        const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
+        for (int c = 0; c < BN / kChunkN; ++c) {
+          if (n0 + c * kChunkN >= p.N) break;
+          ptx::mbar_wait(&rempty_bar[rs], rphase ^ 1, 500 + rs);
+          ptx::mbar_arrive_expect_tx(&rfull_bar[rs], kChunkBytes);
+          ptx::tma_load_2d(&tmR, &rfull_bar[rs], smem + C::kResOff + rs * kChunkBytes, n0 + c * kChunkN, m0);
+          if (++rs == kResBufs) { rs = 0; rphase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int et = threadIdx.x - kEpiWarp0 * 32;     // 0..127
+    const int quad = warp & 3;                       // TMEM lane quarter this warp may read
+    const int row = quad * 32 + lane;                // row of the tile == TMEM lane
+    const uint32_t swz = (uint32_t)(row & 7);
+    int it = 0, oc = 0, rs = 0;
+    uint32_t rphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+      const int m_blk = tile / p.tiles_n, n_blk = tile - m_blk * p.tiles_n;
+      const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
+      for (int i = et; i < BN; i += kEpiThreads) {
+        const int n = n0 + i;
+        sc_s[as * BN + i] = (n < p.N) ? (p.scale ? __ldg(p.scale + n) : 1.f) : 0.f;
+        sh_s[as * BN + i] = (n < p.N && p.shift) ? __ldg(p.shift + n) : 0.f;
+      }
+      ptx::named_bar_sync(1, kEpiThreads);
+      ptx::mbar_wait(&tfull_bar[as], aphase, 400 + as);
+      ptx::tc_fence_after();
+      int nchunks = (p.N - n0 + kChunkN - 1) / kChunkN;
+      if (nchunks > BN / kChunkN) nchunks = BN / kChunkN;
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t r[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + c * kChunkN;
+        ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        ptx::tmem_ld_wait();
+        if (c == nchunks - 1) {                      // accumulator drained: hand it back to the MMA warp
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+        }
+        const float4* sc4 = reinterpret_cast<const float4*>(sc_s + as * BN + c * kChunkN);
+        const float4* sh4 = reinterpret_cast<const float4*>(sh_s + as * BN + c * kChunkN);
+        float v[64];
+#pragma unroll
+        for (int g = 0; g < 16; ++g) {
+          const float4 s4 = sc4[g], h4 = sh4[g];
+          v[4 * g + 0] = fmaf(__uint_as_float(r[4 * g + 0]), s4.x, h4.x);
+          v[4 * g + 1] = fmaf(__uint_as_float(r[4 * g + 1]), s4.y, h4.y);
+          v[4 * g + 2] = fmaf(__uint_as_float(r[4 * g + 2]), s4.z, h4.z);
+          v[4 * g + 3] = fmaf(__uint_as_float(r[4 * g + 3]), s4.w, h4.w);
+        }
+        if (p.has_res) {
+          ptx::mbar_wait(&rfull_bar[rs], rphase, 600 + rs);
+          const uint8_t* rb = smem + C::kResOff + rs * kChunkBytes + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4*>(rb + (((uint32_t)j ^ swz) << 4));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              v[j * 8 + 2 * h] += __uint_as_float(w[h] << 16);
+              v[j * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xFFFF0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&rempty_bar[rs]);
+          if (++rs == kResBufs) { rs = 0; rphase ^= 1; }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        uint8_t* ob = smem + C::kOutOff + (oc % C::kOutBufs) * kChunkBytes;
+        uint8_t* orow = ob + row * 128;
+        if (C::kOutBufs == 2) ptx::named_bar_sync(2, kEpiThreads);   // thread 0 arrives after its wait_read<1>
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 q;
+          q.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]); q.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+          q.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]); q.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+          *reinterpret_cast<uint4*>(orow + (((uint32_t)j ^ swz) << 4)) = q;
+        }
+        ptx::fence_proxy_async();
+        ptx::named_bar_sync(1, kEpiThreads);
+        if (et == 0) {
+          ptx::tma_store_2d(&tmD, ob, n0 + c * kChunkN, m0);
+          ptx::tma_store_commit();
+          // 3 buffers: chunk k+1 reuses the buffer of store k-2 -- all but the newest store have left smem
+          // before thread 0 reaches the next barrier.  2 buffers: the extra barrier above orders it.
+          ptx::tma_store_wait_read<1>();
+        }
+        ++oc;
+      }
+    }
+    if (et == 0) ptx::tma_store_wait_all<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int BN>
+int launch_bn(const GemmLaunch& L, const KP& kp, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    AP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+    configured = true;
+  }
+  const int tiles = kp.tiles_m * kp.tiles_n;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)std::min(tiles, num_sms()));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg<BN>::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = L.pdl ? 1 : 0;
+  AP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<BN>, L.tmA, L.tmB, L.tmD, L.epi.residual ? L.tmR : L.tmD, kp));
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+
+bool tma_epilogue_eligible(const GemmLaunch& L) {
+  const Epilogue& e = L.epi;
+  return e.out_bf16 && !e.out_f32 && !e.out_split && L.N % kChunkN == 0 && e.ldd % 8 == 0 &&
+         (reinterpret_cast<uintptr_t>(e.out_bf16) & 15) == 0 &&
+         (!e.residual || (!e.residual_f32 && e.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(e.residual) & 15) == 0));
+}
+
+int enable_tma_epilogue(GemmLaunch* L) {
+  AP_REQUIRE(tma_epilogue_eligible(*L), "enable_tma_epilogue: epilogue is not eligible for the TMA path");
+  if (make_tmap_tiled_bf16(&L->tmD, L->epi.out_bf16, L->M, L->N, L->epi.ldd, kBlockM, kChunkN)) return 1;
+  if (L->epi.residual && make_tmap_tiled_bf16(&L->tmR, L->epi.residual, L->M, L->N, L->epi.ldr, kBlockM, kChunkN)) return 1;
+  L->tma_epi = 1;
+  return 0;
+}
+
+int launch_gemm_tma(const GemmLaunch& L, cudaStream_t stream) {
+  AP_REQUIRE(L.M > 0 && L.N > 0 && L.K > 0, "launch_gemm_tma: empty problem %dx%dx%d", L.M, L.N, L.K);
+  AP_REQUIRE(L.tma_epi, "launch_gemm_tma: tensor maps of the epilogue were not built");
+  KP kp{};
+  kp.M = L.M; kp.N = L.N; kp.K = L.K;
+  kp.num_kb = ceil_div(L.K, kBlockK);
+  kp.tiles_m = ceil_div(L.M, kBlockM);
+  kp.tiles_n = ceil_div(L.N, L.block_n);
+  kp.im2col = L.im2col;
+  if (L.im2col) {
+    const ConvGeom& g = L.geom;
+    AP_REQUIRE(g.Cin % kBlockK == 0, "launch_gemm_tma: im2col needs Cin %% 64 == 0 (Cin=%d)", g.Cin);
+    AP_REQUIRE(L.K == g.ksize * g.ksize * g.Cin, "launch_gemm_tma: K=%d does not match the conv geometry", L.K);
+    kp.cblks = g.Cin / kBlockK; kp.ksize = g.ksize; kp.stride = g.stride; kp.pad = g.pad;
+    kp.Wo = g.Wo; kp.HoWo = g.Ho * g.Wo;
+  }
+  kp.has_res = L.epi.residual != nullptr;
+  kp.relu = L.epi.relu;
+  kp.scale = L.epi.scale; kp.shift = L.epi.shift;
+  switch (L.block_n) {
+    case 64: return launch_bn<64>(L, kp, stream);
+    case 128: return launch_bn<128>(L, kp, stream);
+    case 256: return launch_bn<256>(L, kp, stream);
+    default: AP_REQUIRE(false, "launch_gemm_tma: unsupported block_n %d", L.block_n);
+  }
+  return 0;
+}
+
+}  // namespace airpose

@@ -375,6 +375,8 @@ static int conv_launch(airpose_net* h, int idx, const __nv_bfloat16* x, int n, i
   L->epi.residual = residual; L->epi.ldr = s.cout;
   L->epi.relu = relu;
   L->epi.out_bf16 = out; L->epi.ldd = s.cout;
+  if (use_tma_epilogue() && tma_epilogue_eligible(*L) && enable_tma_epilogue(L)) return 1;
+  L->pdl = use_pdl();
   return 0;
 }
 
@@ -387,6 +389,7 @@ static int build_trunk_plan(airpose_net* h, int n, TrunkPlan* plan) {
     if (make_tmap_tiled_bf16(&L.tmB, h->wq[0], 64, kStemK, kStemK, 64, 64)) return 1;
     L.epi.scale = h->scale[0]; L.epi.shift = h->shift[0]; L.epi.relu = 1;
     L.epi.out_bf16 = h->stem_out; L.epi.ldd = 64;
+    if (use_tma_epilogue() && enable_tma_epilogue(&L)) return 1;
     plan->gemms.push_back(L);
   }
   const int layers[4] = {3, 4, 6, 3};

@@ -157,6 +157,43 @@ def test_gemm_bf16_matches_torch(M, N, K):
     assert err < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K,res,relu", [(128, 64, 64, False, False), (300, 192, 320, True, True), (1000, 256, 2304, True, False),
+                                            (6272, 2048, 512, True, True), (25088, 64, 576, False, True), (77, 320, 128, True, True),
+                                            (12545, 512, 128, True, True), (3000, 1024, 256, False, True)])
+def test_gemm_tma_epilogue_bf16_out(M, N, K, res, relu):
+    """bf16 output with N % 64 == 0 runs the TMA-epilogue kernel (gemm_tma.cu): swizzled smem staging,
+    TMA residual loads and TMA stores, M tails clipped by the tensor map."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(M * 3 + N + K)
+    A = _bf16(torch.randn(M, K, generator=g)).to(DEV)
+    Bm = _bf16(torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    scale = (torch.rand(N, generator=g) + 0.5).to(DEV)
+    shift = torch.randn(N, generator=g).to(DEV)
+    R = _bf16(torch.randn(M, N, generator=g)).to(DEV) if res else None
+    guard = 64
+    out = torch.full((M + guard, N), 7.0, device=DEV, dtype=torch.bfloat16)     # rows past M must stay untouched
+    a = _lib.GemmArgs()
+    a.A, a.lda, a.B, a.ldb = A.data_ptr(), K, Bm.data_ptr(), K
+    a.M, a.N, a.K = M, N, K
+    a.scale, a.shift, a.relu = scale.data_ptr(), shift.data_ptr(), int(relu)
+    if res:
+        a.residual, a.ldr = R.data_ptr(), N
+    a.out_bf16, a.ldd = out.data_ptr(), N
+    for _ in range(2):          # twice: the second launch exercises PDL back-to-back on the same buffers
+        _lib.check(lib.airpose_gemm_bf16(C.byref(a), _lib.current_stream()), "gemm")
+    torch.cuda.synchronize()
+    ref = (A.float() @ Bm.float().t()) * scale + shift
+    if res:
+        ref = ref + R.float()
+    if relu:
+        ref = torch.relu(ref)
+    got = out[:M].float()
+    bad = (got - ref).abs() > ref.abs() * 2.0 ** -8 + 2e-3
+    print("gemm-tma %dx%dx%d res=%d relu=%d: max abs err %.3e bad %d" % (M, N, K, res, relu, (got - ref).abs().max().item(), int(bad.sum())))
+    assert not bad.any()
+    assert (out[M:] == 7.0).all()
+
+
 def test_gemm_epilogue_scale_shift_residual_relu():
     lib = _lib.load()
     M, N, K = 700, 256, 192
