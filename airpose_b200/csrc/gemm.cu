@@ -279,7 +279,7 @@ static void* driver_fn(const char* name) {
 }
 
 int make_tmap_tiled_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems,
-                         int box_rows, int box_cols) {
+                         int box_rows, int box_cols, int swizzle_bytes) {
   static EncodeTiledFn fn = (EncodeTiledFn)driver_fn("cuTensorMapEncodeTiled");
   AP_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from the driver");
   AP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld_elems % 8) == 0,
@@ -289,9 +289,12 @@ int make_tmap_tiled_bf16(CUtensorMap* out, const void* base, int64_t rows, int64
   const cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
   const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
+  AP_REQUIRE((swizzle_bytes == 128 || swizzle_bytes == 64) && box_cols * 2 == swizzle_bytes,
+             "make_tmap_tiled_bf16: box of %d columns does not match a %d-byte swizzle", box_cols, swizzle_bytes);
   const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   AP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rows=%lld cols=%lld ld=%lld box=%dx%d)", (int)r,
              (long long)rows, (long long)cols, (long long)ld_elems, box_rows, box_cols);
   return 0;

@@ -34,6 +34,11 @@ struct GemmLaunch {
   int M = 0, N = 0, K = 0;
   int block_n = 128;   // 64, 128 or 256
   int im2col = 0;
+  // stem mode (gemm_tma.cu only): K blocks of 32 (64-byte swizzle); k-block r reads the A rows
+  // img*stem_img_stride + stem_tap_off[r] + (m % stem_img_rows) of a plain [rows,32] matrix.
+  int stem = 0;
+  int stem_img_rows = 0, stem_img_stride = 0;
+  int stem_tap_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int tma_epi = 0;     // 1: bf16 output through smem staging + TMA store (gemm_tma.cu); 0: direct stores (gemm.cu)
   int pdl = 0;         // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
   ConvGeom geom;
@@ -48,7 +53,7 @@ int launch_gemm_tma(const GemmLaunch& L, cudaStream_t stream);
 
 // Tensor maps (cuTensorMapEncode* resolved through cudaGetDriverEntryPoint; no libcuda link).
 int make_tmap_tiled_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems,
-                         int box_rows, int box_cols);
+                         int box_rows, int box_cols, int swizzle_bytes = 128);
 int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, const ConvGeom& g, int channels_per_pixel,
                           int pixels_per_column);
 

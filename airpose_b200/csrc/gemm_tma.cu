@@ -26,12 +26,10 @@ namespace airpose {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kThreads = 224;
 constexpr int kEpiWarp0 = 3;
 constexpr int kEpiThreads = 128;
-constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kChunkN = 64;                       // epilogue chunk: 128 rows x 64 bf16 = one 128B-swizzle box
 constexpr int kChunkBytes = kBlockM * kChunkN * 2;
 constexpr int kResBufs = 2;
@@ -40,15 +38,18 @@ struct KP {
   int M, N, K;
   int num_kb, tiles_m, tiles_n;
   int im2col, cblks, ksize, stride, pad, Wo, HoWo;
+  int stem, stem_img_rows, stem_img_stride;
+  int stem_tap_off[8];
   int has_res, relu;
   const float* scale;
   const float* shift;
 };
 
-template <int BN>
+template <int BN, int BK>
 struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
-  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStages = (BK == 32) ? 8 : ((BN == 256) ? 3 : (BN == 128 ? 4 : 6));
+  static constexpr int kABytes = kBlockM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
   // 3 output buffers need one barrier per chunk; BN=256 has room for 2 only and pays a second barrier
@@ -68,11 +69,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int BN>
+template <int BN, int BK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const KP p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, BK>;
+  constexpr int kBlockK = BK;
+  constexpr int kABytes = C::kABytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kBarOff);
@@ -127,12 +130,19 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           cw = qo * p.stride - p.pad;
           ch = po * p.stride - p.pad;
         }
+        int stem_row = 0;
+        if (BK == 32) {                                // stem: tiles never straddle images (12544 = 98 * 128)
+          const int img = m0 / p.stem_img_rows;
+          stem_row = img * p.stem_img_stride + (m0 - img * p.stem_img_rows);
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
           uint8_t* sa = smem + stage * C::kStageBytes;
           uint8_t* sb = sa + kABytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-          if (p.im2col) {
+          if (BK == 32) {
+            ptx::tma_load_2d(&tmA, &full_bar[stage], sa, 0, stem_row + p.stem_tap_off[kb]);
+          } else if (p.im2col) {
             const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
             const int r = tap / p.ksize, s = tap - r * p.ksize;
             ptx::tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * kBlockK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
@@ -159,8 +169,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ptx::mbar_wait(&full_bar[stage], phase, 300 + stage);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
-          const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sa + kABytes);
+          const uint64_t adesc = ptx::make_kmajor_desc(sa, BK * 2);
+          const uint64_t bdesc = ptx::make_kmajor_desc(sa + kABytes, BK * 2);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
             ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
@@ -285,25 +295,25 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <int BN>
+template <int BN, int BK>
 int launch_bn(const GemmLaunch& L, const KP& kp, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemBytes));
+    AP_CHECK_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, BK>::kSmemBytes));
     configured = true;
   }
   const int tiles = kp.tiles_m * kp.tiles_n;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)std::min(tiles, num_sms()));
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg<BN>::kSmemBytes;
+  cfg.dynamicSmemBytes = Cfg<BN, BK>::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = L.pdl ? 1 : 0;
-  AP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<BN>, L.tmA, L.tmB, L.tmD, L.epi.residual ? L.tmR : L.tmD, kp));
+  AP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tma_kernel<BN, BK>, L.tmA, L.tmB, L.tmD, L.epi.residual ? L.tmR : L.tmD, kp));
   count_launch();
   return 0;
 }
@@ -330,6 +340,7 @@ int launch_gemm_tma(const GemmLaunch& L, cudaStream_t stream) {
   AP_REQUIRE(L.tma_epi, "launch_gemm_tma: tensor maps of the epilogue were not built");
   KP kp{};
   kp.M = L.M; kp.N = L.N; kp.K = L.K;
+  const int kBlockK = L.stem ? 32 : 64;
   kp.num_kb = ceil_div(L.K, kBlockK);
   kp.tiles_m = ceil_div(L.M, kBlockM);
   kp.tiles_n = ceil_div(L.N, L.block_n);
@@ -341,13 +352,22 @@ int launch_gemm_tma(const GemmLaunch& L, cudaStream_t stream) {
     kp.cblks = g.Cin / kBlockK; kp.ksize = g.ksize; kp.stride = g.stride; kp.pad = g.pad;
     kp.Wo = g.Wo; kp.HoWo = g.Ho * g.Wo;
   }
+  if (L.stem) {
+    AP_REQUIRE(L.block_n == 64 && kp.num_kb <= 8 && L.stem_img_rows % kBlockM == 0, "launch_gemm_tma: bad stem geometry");
+    kp.stem = 1; kp.stem_img_rows = L.stem_img_rows; kp.stem_img_stride = L.stem_img_stride;
+    for (int i = 0; i < 8; ++i) kp.stem_tap_off[i] = L.stem_tap_off[i];
+    kp.has_res = L.epi.residual != nullptr;
+    kp.relu = L.epi.relu;
+    kp.scale = L.epi.scale; kp.shift = L.epi.shift;
+    return launch_bn<64, 32>(L, kp, stream);
+  }
   kp.has_res = L.epi.residual != nullptr;
   kp.relu = L.epi.relu;
   kp.scale = L.epi.scale; kp.shift = L.epi.shift;
   switch (L.block_n) {
-    case 64: return launch_bn<64>(L, kp, stream);
-    case 128: return launch_bn<128>(L, kp, stream);
-    case 256: return launch_bn<256>(L, kp, stream);
+    case 64: return launch_bn<64, 64>(L, kp, stream);
+    case 128: return launch_bn<128, 64>(L, kp, stream);
+    case 256: return launch_bn<256, 64>(L, kp, stream);
     default: AP_REQUIRE(false, "launch_gemm_tma: unsupported block_n %d", L.block_n);
   }
   return 0;

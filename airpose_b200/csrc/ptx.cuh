@@ -152,6 +152,18 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Same for a tile whose rows are `swizzle_bytes` (128 or 64) wide: SWIZZLE_128B / SWIZZLE_64B,
+// 8-row groups 8*swizzle_bytes apart.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, int swizzle_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * swizzle_bytes) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(swizzle_bytes == 128 ? 2 : 4) << 61;
+  return d;
+}
+
 // Instruction descriptor, kind::f16: bf16 A/B (K-major), fp32 accumulator, M x N tile.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -11,6 +11,7 @@
 
 #include <cstdlib>
 #include <map>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -37,7 +38,12 @@ static std::vector<ConvSpec> resnet50_specs() {      // forward order, see synth
   return v;
 }
 
-constexpr int kStemK = 192;            // 3*7*7 = 147 padded to a multiple of 64
+// Stem operand layout (DESIGN.md "stem"): per input row h and output column q the 7 taps x 3 channels
+// along W (21 values, padded to 32) are packed once; rows are split by parity so that for a fixed
+// vertical tap r the 128 output pixels of a tile read 128 CONSECUTIVE packed rows.
+constexpr int kStemTapK = 32;          // 7*3 = 21 padded to 32 bf16 = one 64-byte swizzle row
+constexpr int kStemK = 7 * kStemTapK;  // 224
+constexpr int kStemPlaneRows = 115;    // 2 zero rows + 112 + 1 zero row  (vertical taps reach p-2 .. p+1)
 constexpr int kFeat = 2048;
 constexpr int kState = 284, kStatePad = 320;
 constexpr int kHid = 1024;
@@ -50,8 +56,9 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int o = (int)(i / kpad), kk = (int)(i % kpad);
     float val = 0.f;
-    if (stem) {                       // natural (c, r, s) order, zero padded
-      if (kk < cin * k * k) val = w[(int64_t)o * cin * k * k + kk];
+    if (stem) {                       // [o][r][s*3+c], 21 -> 32 zero padded per vertical tap r
+      const int r = kk / kStemTapK, e = kk % kStemTapK;
+      if (e < 21) val = w[(((int64_t)o * cin + (e % 3)) * k + r) * k + e / 3];
     } else {                          // (r, s, c): tap-major, channel-minor = the im2col K order
       const int tap = kk / cin, c = kk % cin;
       val = w[(((int64_t)o * cin + c) * k * k) + tap];
@@ -105,27 +112,34 @@ __global__ void concat_bias_kernel(const float* a, int na, const float* b, int n
 }
 
 // ------------------------------------------------------------------------------ trunk kernels
-// Stem im2col: x fp32 NCHW [n,3,224,224] -> bf16 [n*112*112, 192], K index = c*49 + r*7 + s
-// (7x7, stride 2, pad 3; model_copenet.py:57-58).  One thread writes 8 consecutive K entries.
-__global__ void stem_im2col_kernel(const float* __restrict__ x, int n, __nv_bfloat16* __restrict__ col) {
-  const int64_t total = (int64_t)n * 112 * 112 * (kStemK / 8);
+// Stem operand pack: x fp32 NCHW [n,3,224,224] -> bf16 [n][2 parities][115 rows][112 q][32]:
+//   out[n][par][hp][q][s*3+c] = x[n][c][2*(hp-2)+par][2q-3+s]   (zero outside the image / for hp in {0,1,114})
+// (7x7, stride 2, pad 3; model_copenet.py:57-58).  One thread packs one (row, q): 64 bytes.
+__global__ void stem_pack_kernel(const float* __restrict__ x, int n, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)n * 2 * kStemPlaneRows * 112;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int kg = (int)(i % (kStemK / 8));
-    const int64_t pix = i / (kStemK / 8);
-    const int q = (int)(pix % 112), pr = (int)((pix / 112) % 112), img = (int)(pix / (112 * 112));
-    __align__(16) __nv_bfloat16 vals[8];
+    const int q = (int)(i % 112);
+    const int hp = (int)((i / 112) % kStemPlaneRows);
+    const int par = (int)((i / (112 * kStemPlaneRows)) % 2);
+    const int img = (int)(i / (112 * kStemPlaneRows * 2));
+    const int h = 2 * (hp - 2) + par;
+    __align__(16) __nv_bfloat16 vals[kStemTapK];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int kk = kg * 8 + j;
-      float v = 0.f;
-      if (kk < 147) {
-        const int c = kk / 49, r = (kk % 49) / 7, s = kk % 7;
-        const int h = pr * 2 - 3 + r, w = q * 2 - 3 + s;
-        if (h >= 0 && h < 224 && w >= 0 && w < 224) v = __ldg(x + (((int64_t)img * 3 + c) * 224 + h) * 224 + w);
+    for (int e = 0; e < kStemTapK; ++e) vals[e] = __float2bfloat16_rn(0.f);
+    if (hp >= 2 && hp < 114) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* row = x + (((int64_t)img * 3 + c) * 224 + h) * 224;
+#pragma unroll
+        for (int sx = 0; sx < 7; ++sx) {
+          const int w = 2 * q - 3 + sx;
+          if (w >= 0 && w < 224) vals[sx * 3 + c] = __float2bfloat16_rn(__ldg(row + w));
+        }
       }
-      vals[j] = __float2bfloat16_rn(v);
     }
-    *reinterpret_cast<uint4*>(col + pix * kStemK + kg * 8) = *reinterpret_cast<const uint4*>(vals);
+    uint4* o = reinterpret_cast<uint4*>(out + i * kStemTapK);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = reinterpret_cast<const uint4*>(vals)[j];
   }
 }
 
@@ -230,7 +244,7 @@ __global__ void ief_update_kernel(int B, const float* d, float* pose, float* sha
 using namespace airpose;
 
 struct TrunkPlan {
-  std::vector<GemmLaunch> gemms;       // in launch order: stem, then per block conv1, conv2, [down], conv3
+  std::vector<GemmLaunch> gemms;       // in launch order: [stem,] then per block conv1, conv2, [down], conv3
   const __nv_bfloat16* final_act = nullptr;
 };
 
@@ -252,8 +266,11 @@ struct airpose_net {
   // workspaces
   __nv_bfloat16* col = nullptr;
   __nv_bfloat16* stem_out = nullptr;
-  __nv_bfloat16* act[4] = {nullptr, nullptr, nullptr, nullptr};
-  std::map<int, TrunkPlan> plans;
+  __nv_bfloat16* act[4] = {nullptr, nullptr, nullptr, nullptr};    // stage A (stem, layer1, layer2): `chunk` images
+  __nv_bfloat16* actB[4] = {nullptr, nullptr, nullptr, nullptr};   // stage B (layer3, layer4): `group` images
+  int group = 0;
+  std::map<std::pair<int, int>, TrunkPlan> plansA;                 // (images, slot inside the group)
+  std::map<int, TrunkPlan> plansB;                                 // images
   // IEF workspace (grown on demand)
   int ief_cap = 0;
   __nv_bfloat16 *xf_split = nullptr, *state_split = nullptr, *y1_split = nullptr, *y2_split = nullptr;
@@ -261,11 +278,17 @@ struct airpose_net {
   std::map<int, IefPlan> ief_plans;
 };
 
-static int default_chunk() {
-  const char* e = getenv("AIRPOSE_TRUNK_CHUNK");
-  const int c = e ? atoi(e) : 32;
-  return c > 0 ? c : 32;
+// Stage A (56x56 / 28x28 activations) runs in chunks small enough that a layer's output is still in
+// L2 when the next layer reads it; stage B (14x14 / 7x7) runs on a larger group so that its GEMMs
+// have enough 128-row tiles to fill 148 SMs.  (DESIGN.md "trunk schedule")
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  const int c = e ? atoi(e) : dflt;
+  return c > 0 ? c : dflt;
 }
+static int default_chunk() { return env_int("AIRPOSE_TRUNK_CHUNK", 32); }
+static int default_group() { return env_int("AIRPOSE_TRUNK_GROUP", 128); }
+constexpr size_t kStageBElems = 28 * 28 * 512;      // per image: the largest stage-B tensor (layer3 input)
 
 extern "C" int airpose_net_create(airpose_net_t** out, int max_images, int device) {
   AP_REQUIRE(out && max_images > 0, "airpose_net_create: bad argument");
@@ -274,6 +297,7 @@ extern "C" int airpose_net_create(airpose_net_t** out, int max_images, int devic
   h->device = device;
   h->max_images = max_images;
   h->chunk = std::min(max_images, default_chunk());
+  h->group = std::max(h->chunk, std::min(max_images, default_group()) / h->chunk * h->chunk);
   h->specs = resnet50_specs();
   const size_t nconv = h->specs.size();
   h->wq.resize(nconv); h->scale.resize(nconv); h->shift.resize(nconv);
@@ -294,9 +318,10 @@ extern "C" int airpose_net_create(airpose_net_t** out, int max_images, int devic
   AP_CHECK_CUDA(cudaMalloc((void**)&h->init_pose, 144 * sizeof(float)));
   AP_CHECK_CUDA(cudaMalloc((void**)&h->init_shape, 10 * sizeof(float)));
   const size_t act_elems = (size_t)h->chunk * 112 * 112 * 64;       // == 56*56*256, the largest activation
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->col, (size_t)h->chunk * 112 * 112 * kStemK * 2));
+  AP_CHECK_CUDA(cudaMalloc((void**)&h->col, (size_t)h->chunk * 2 * kStemPlaneRows * 112 * kStemTapK * 2));
   AP_CHECK_CUDA(cudaMalloc((void**)&h->stem_out, act_elems * 2));
   for (int i = 0; i < 4; ++i) AP_CHECK_CUDA(cudaMalloc((void**)&h->act[i], act_elems * 2));
+  for (int i = 0; i < 4; ++i) AP_CHECK_CUDA(cudaMalloc((void**)&h->actB[i], (size_t)h->group * kStageBElems * 2));
   *out = h;
   return 0;
 }
@@ -308,7 +333,7 @@ extern "C" int airpose_net_destroy(airpose_net_t* h) {
   for (auto p : h->scale) cudaFree(p);
   for (auto p : h->shift) cudaFree(p);
   void* ptrs[] = {h->w1a, h->w1b, h->w2, h->wd, h->b1, h->b2, h->bd, h->init_pose, h->init_shape, h->col, h->stem_out,
-                  h->act[0], h->act[1], h->act[2], h->act[3], h->xf_split, h->state_split, h->y1_split, h->y2_split,
+                  h->act[0], h->act[1], h->act[2], h->act[3], h->actB[0], h->actB[1], h->actB[2], h->actB[3], h->xf_split, h->state_split, h->y1_split, h->y2_split,
                   h->hbuf, h->dbuf, h->pose, h->shape};
   for (void* p : ptrs) cudaFree(p);
   delete h;
@@ -380,44 +405,85 @@ static int conv_launch(airpose_net* h, int idx, const __nv_bfloat16* x, int n, i
   return 0;
 }
 
-static int build_trunk_plan(airpose_net* h, int n, TrunkPlan* plan) {
-  plan->gemms.clear();
-  {   // stem as an explicit-im2col GEMM: [n*112*112, 192] x [64, 192]^T, BN + ReLU
-    GemmLaunch L{};
-    L.M = n * 112 * 112; L.N = 64; L.K = kStemK; L.block_n = 64;
-    if (make_tmap_tiled_bf16(&L.tmA, h->col, L.M, kStemK, kStemK, 128, 64)) return 1;
-    if (make_tmap_tiled_bf16(&L.tmB, h->wq[0], 64, kStemK, kStemK, 64, 64)) return 1;
-    L.epi.scale = h->scale[0]; L.epi.shift = h->shift[0]; L.epi.relu = 1;
-    L.epi.out_bf16 = h->stem_out; L.epi.ldd = 64;
-    if (use_tma_epilogue() && enable_tma_epilogue(&L)) return 1;
-    plan->gemms.push_back(L);
+static int build_stem_gemm(airpose_net* h, int n, GemmLaunch* Lp) {
+  // stem: 7 k-blocks (one per vertical tap) over the packed operand, BN + ReLU in the epilogue
+  GemmLaunch& L = *Lp;
+  L.M = n * 112 * 112; L.N = 64; L.K = kStemK; L.block_n = 64;
+  L.stem = 1;
+  L.stem_img_rows = 112 * 112;
+  L.stem_img_stride = 2 * kStemPlaneRows * 112;
+  for (int r = 0; r < 7; ++r) {       // input row 2p-3+r: parity (r+1)&1, plane row p + c_r + 2
+    const int par = (r + 1) & 1;
+    const int cr = (r - 3 - par) / 2;            // exact: r-3-par is even
+    L.stem_tap_off[r] = (par * kStemPlaneRows + 2 + cr) * 112;
   }
+  if (make_tmap_tiled_bf16(&L.tmA, h->col, (int64_t)n * 2 * kStemPlaneRows * 112, kStemTapK, kStemTapK, 128, kStemTapK, 64)) return 1;
+  if (make_tmap_tiled_bf16(&L.tmB, h->wq[0], 64, kStemK, kStemK, 64, kStemTapK, 64)) return 1;
+  L.epi.scale = h->scale[0]; L.epi.shift = h->shift[0]; L.epi.relu = 1;
+  L.epi.out_bf16 = h->stem_out; L.epi.ldd = 64;
+  return enable_tma_epilogue(&L);
+}
+
+// Bottleneck blocks of layers [l0, l1) on `n` images, input in buf[0] at H x H; the last block's
+// output goes to `final_out` when given (else stays in one of buf[]).
+static int build_blocks(airpose_net* h, int n, int l0, int l1, int H, __nv_bfloat16* const buf[4], __nv_bfloat16* final_out,
+                        TrunkPlan* plan) {
   const int layers[4] = {3, 4, 6, 3};
-  int a = 0, b = 1, c = 2, d = 3;          // act buffer roles: X, T1/OUT, T2, DS
-  int H = 56, idx = 1;
-  for (int li = 0; li < 4; ++li)
+  int idx = 1;
+  for (int li = 0; li < l0; ++li) idx += 3 * layers[li] + 1;
+  int a = 0, b = 1, c = 2, d = 3;          // buffer roles: X, T1/OUT, T2, DS
+  for (int li = l0; li < l1; ++li)
     for (int blk = 0; blk < layers[li]; ++blk) {
       const bool down = blk == 0;
+      const bool last = (li == l1 - 1) && (blk == layers[li] - 1);
       const int stride = h->specs[idx + 1].stride;
       const int Ho = H / stride;
       GemmLaunch L1{}, L2{}, L3{}, LD{};
-      if (conv_launch(h, idx, h->act[a], n, H, H, nullptr, 1, h->act[b], &L1)) return 1;
-      if (conv_launch(h, idx + 1, h->act[b], n, H, H, nullptr, 1, h->act[c], &L2)) return 1;
+      if (conv_launch(h, idx, buf[a], n, H, H, nullptr, 1, buf[b], &L1)) return 1;
+      if (conv_launch(h, idx + 1, buf[b], n, H, H, nullptr, 1, buf[c], &L2)) return 1;
       plan->gemms.push_back(L1);
       plan->gemms.push_back(L2);
-      const __nv_bfloat16* res = h->act[a];
+      const __nv_bfloat16* res = buf[a];
       if (down) {
-        if (conv_launch(h, idx + 3, h->act[a], n, H, H, nullptr, 0, h->act[d], &LD)) return 1;
+        if (conv_launch(h, idx + 3, buf[a], n, H, H, nullptr, 0, buf[d], &LD)) return 1;
         plan->gemms.push_back(LD);
-        res = h->act[d];
+        res = buf[d];
       }
-      if (conv_launch(h, idx + 2, h->act[c], n, Ho, Ho, res, 1, h->act[b], &L3)) return 1;
+      __nv_bfloat16* out = (last && final_out) ? final_out : buf[b];
+      if (conv_launch(h, idx + 2, buf[c], n, Ho, Ho, res, 1, out, &L3)) return 1;
       plan->gemms.push_back(L3);
+      plan->final_act = out;
       std::swap(a, b);
       idx += down ? 4 : 3;
       H = Ho;
     }
-  plan->final_act = h->act[a];
+  return 0;
+}
+
+// stage A: stem GEMM + layer1 + layer2 on `n` <= chunk images; output [n,28,28,512] lands in slot
+// `slot` of the stage-B input buffer.
+static int build_plan_a(airpose_net* h, int n, int slot, TrunkPlan* plan) {
+  plan->gemms.clear();
+  GemmLaunch L{};
+  if (build_stem_gemm(h, n, &L)) return 1;
+  plan->gemms.push_back(L);
+  __nv_bfloat16* out = slot >= 0 ? h->actB[0] + (size_t)slot * h->chunk * kStageBElems : nullptr;
+  return build_blocks(h, n, 0, 2, 56, h->act, out, plan);
+}
+
+// stage B: layer3 + layer4 on `n` <= group images, input in actB[0].
+static int build_plan_b(airpose_net* h, int n, TrunkPlan* plan) {
+  plan->gemms.clear();
+  return build_blocks(h, n, 2, 4, 28, h->actB, nullptr, plan);
+}
+
+static int launch_stem_front(airpose_net* h, const float* x, int n, const GemmLaunch& stem, __nv_bfloat16* pooled, cudaStream_t st) {
+  const int64_t work = (int64_t)n * 2 * kStemPlaneRows * 112;
+  stem_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(work, 128), 148 * 32), 128, 0, st>>>(x, n, h->col);
+  AP_LAUNCH_CHECK();
+  if (launch_gemm(stem, st)) return 1;
+  maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64((int64_t)n * 56 * 56 * 8, 256), 148 * 16), 256, 0, st>>>(h->stem_out, n, pooled);
+  AP_LAUNCH_CHECK();
   return 0;
 }
 
@@ -426,26 +492,32 @@ extern "C" int airpose_backbone_fwd(airpose_net_t* h, const float* x, int n_imag
   AP_REQUIRE(h->loaded, "airpose_backbone_fwd: weights not loaded (call airpose_net_load)");
   AP_REQUIRE(n_images >= 0, "airpose_backbone_fwd: negative image count");
   cudaStream_t st = (cudaStream_t)stream_;
-  for (int i0 = 0; i0 < n_images; i0 += h->chunk) {
-    const int n = std::min(h->chunk, n_images - i0);
-    auto it = h->plans.find(n);
-    if (it == h->plans.end()) {
+  for (int g0 = 0; g0 < n_images; g0 += h->group) {
+    const int ng = std::min(h->group, n_images - g0);
+    for (int i0 = 0, slot = 0; i0 < ng; i0 += h->chunk, ++slot) {
+      const int n = std::min(h->chunk, ng - i0);
+      auto key = std::make_pair(n, slot);
+      auto it = h->plansA.find(key);
+      if (it == h->plansA.end()) {
+        TrunkPlan plan;
+        if (build_plan_a(h, n, slot, &plan)) return 1;
+        it = h->plansA.emplace(key, std::move(plan)).first;
+      }
+      const TrunkPlan& plan = it->second;
+      if (launch_stem_front(h, x + (size_t)(g0 + i0) * 3 * 224 * 224, n, plan.gemms[0], h->act[0], st)) return 1;
+      for (size_t g = 1; g < plan.gemms.size(); ++g)
+        if (launch_gemm(plan.gemms[g], st)) return 1;
+    }
+    auto it = h->plansB.find(ng);
+    if (it == h->plansB.end()) {
       TrunkPlan plan;
-      if (build_trunk_plan(h, n, &plan)) return 1;
-      it = h->plans.emplace(n, std::move(plan)).first;
+      if (build_plan_b(h, ng, &plan)) return 1;
+      it = h->plansB.emplace(ng, std::move(plan)).first;
     }
     const TrunkPlan& plan = it->second;
-    const int64_t work = (int64_t)n * 112 * 112 * (kStemK / 8);
-    stem_im2col_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(work, 256), 148 * 16), 256, 0, st>>>(
-        x + (size_t)i0 * 3 * 224 * 224, n, h->col);
-    AP_LAUNCH_CHECK();
-    if (launch_gemm(plan.gemms[0], st)) return 1;
-    maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64((int64_t)n * 56 * 56 * 8, 256), 148 * 16), 256, 0, st>>>(
-        h->stem_out, n, h->act[0]);
-    AP_LAUNCH_CHECK();
-    for (size_t g = 1; g < plan.gemms.size(); ++g)
+    for (size_t g = 0; g < plan.gemms.size(); ++g)
       if (launch_gemm(plan.gemms[g], st)) return 1;
-    avgpool_kernel<<<ceil_div(n * kFeat, 256), 256, 0, st>>>(plan.final_act, n, out_feat + (size_t)i0 * kFeat);
+    avgpool_kernel<<<ceil_div(ng * kFeat, 256), 256, 0, st>>>(plan.final_act, ng, out_feat + (size_t)g0 * kFeat);
     AP_LAUNCH_CHECK();
   }
   return 0;
@@ -455,21 +527,9 @@ extern "C" int airpose_backbone_stem(airpose_net_t* h, const float* x, int n, vo
   AP_REQUIRE(h && x && out, "airpose_backbone_stem: null argument");
   AP_REQUIRE(h->loaded, "airpose_backbone_stem: weights not loaded (call airpose_net_load)");
   AP_REQUIRE(n > 0 && n <= h->chunk, "airpose_backbone_stem: n=%d exceeds the chunk size %d", n, h->chunk);
-  cudaStream_t st = (cudaStream_t)stream_;
-  auto it = h->plans.find(n);
-  if (it == h->plans.end()) {
-    TrunkPlan plan;
-    if (build_trunk_plan(h, n, &plan)) return 1;
-    it = h->plans.emplace(n, std::move(plan)).first;
-  }
-  const int64_t work = (int64_t)n * 112 * 112 * (kStemK / 8);
-  stem_im2col_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(work, 256), 148 * 16), 256, 0, st>>>(x, n, h->col);
-  AP_LAUNCH_CHECK();
-  if (launch_gemm(it->second.gemms[0], st)) return 1;
-  maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64((int64_t)n * 56 * 56 * 8, 256), 148 * 16), 256, 0, st>>>(
-      h->stem_out, n, (__nv_bfloat16*)out);
-  AP_LAUNCH_CHECK();
-  return 0;
+  GemmLaunch stem{};
+  if (build_stem_gemm(h, n, &stem)) return 1;
+  return launch_stem_front(h, x, n, stem, (__nv_bfloat16*)out, (cudaStream_t)stream_);
 }
 
 static int ensure_ief_ws(airpose_net* h, int B, cudaStream_t st) {
