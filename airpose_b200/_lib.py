@@ -101,6 +101,7 @@ SYMBOLS = {
     "airpose_net_destroy": (C.c_int, [C.c_void_p]),
     "airpose_net_load": (C.c_int, [C.c_void_p, C.POINTER(NetParams), C.c_void_p]),
     "airpose_backbone_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "airpose_backbone_fwd_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "airpose_ief_fwd": (C.c_int, [C.c_void_p, C.POINTER(IefArgs), C.c_void_p]),
     "airpose_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "airpose_conv_bf16": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),

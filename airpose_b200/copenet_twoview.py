@@ -56,7 +56,7 @@ class copenet_twoview(nn.Module):
         in_trans = torch.tensor([0.0, 0.0, 10.0], device=dev).expand(B, -1).clone() * TRANS_SCALE      # :184-203
         reg_iters = getattr(self.hparams, "reg_iters", 3)
         mark("trunk")
-        xf = self.model.forward_feat_ext(torch.cat([im0, im1], dim=0))          # both views, one call (eval-mode BN)
+        xf = self.model.forward_feat_ext_pair(im0, im1)                         # both views, one call (eval-mode BN)
         mark("trunk")
         mark("ief")
         pred = self.model._ief(xf[:B], xf[B:], bb0, bb1, in_trans, in_trans, None, None, None, None, reg_iters)

@@ -1,0 +1,60 @@
+// The per-GPU network handle shared by trunk.cu (ResNet-50) and ief.cu (regressor).
+#pragma once
+#include <cuda_bf16.h>
+
+#include <map>
+#include <utility>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace airpose {
+
+struct ConvSpec { int cout, cin, k, stride, pad; };
+
+struct TrunkPlan {
+  std::vector<GemmLaunch> gemms;       // in launch order: [stem,] then per block conv1, conv2, [down], conv3
+  const __nv_bfloat16* final_act = nullptr;
+};
+
+constexpr int kFeat = 2048;            // trunk feature width (model_copenet.py:173-174)
+
+// Collapsed regressor (ief.cu): G = Wdec * W2 * W1, stored transposed and padded for coalesced reads.
+struct IefState {
+  float* GxT = nullptr;        // [2048][160]  columns of G that multiply the image feature
+  float* GuT = nullptr;        // [284][160]   columns of G that multiply the iterated state
+  float* g = nullptr;          // [160]        Wdec (W2 b1 + b2) + bdec
+  double* T = nullptr;         // [145][1024]  Wdec * W2 (load-time scratch, fp64)
+  float* init_pose = nullptr;  // [144]
+  float* init_shape = nullptr; // [10]
+  float* partial = nullptr;    // [kIefKSlices][rows][160] split-K partials of GxT . xf
+  int partial_rows = 0;
+};
+
+}  // namespace airpose
+
+struct airpose_net {
+  int device = 0;
+  int max_images = 0;
+  int chunk = 0;
+  bool loaded = false;
+  std::vector<airpose::ConvSpec> specs;
+  std::vector<__nv_bfloat16*> wq;       // packed conv weights
+  std::vector<float*> scale, shift;     // folded BN
+  airpose::IefState ief;
+  // workspaces
+  __nv_bfloat16* col = nullptr;         // packed stem operand
+  __nv_bfloat16* stem_out = nullptr;
+  __nv_bfloat16* act[4] = {nullptr, nullptr, nullptr, nullptr};    // stage A (stem, layer1, layer2): `chunk` images
+  __nv_bfloat16* actB[4] = {nullptr, nullptr, nullptr, nullptr};   // stage B (layer3, layer4): `group` images
+  int group = 0;
+  std::map<std::pair<int, int>, airpose::TrunkPlan> plansA;        // (images, first image inside the group)
+  std::map<int, airpose::TrunkPlan> plansB;                        // images
+};
+
+namespace airpose {
+int ief_create(airpose_net* h);
+void ief_destroy(airpose_net* h);
+int ief_load(airpose_net* h, const airpose_net_params* p, cudaStream_t st);
+}  // namespace airpose

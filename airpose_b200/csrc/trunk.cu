@@ -1,8 +1,7 @@
-// ResNet-50 trunk and IEF regressor of copenet, eval mode.
+// ResNet-50 trunk of copenet, eval mode (the IEF regressor lives in ief.cu).
 //
 // Replaces (paths relative to /root/reference/copenet/src/copenet/models):
 //   model_copenet.py:161-176  copenet.forward_feat_ext  (stem, 16 Bottlenecks :27-47, AvgPool2d(7))
-//   model_copenet.py:118-159,178-204  the 3-iteration regressor loop / forward_reg
 //
 // Data layout: activations NHWC bf16 in a per-handle workspace, processed in
 // chunks of images so consecutive layers meet in L2; conv weights bf16 [Cout][tap][Cin];
@@ -16,10 +15,9 @@
 
 #include "common.cuh"
 #include "gemm.cuh"
+#include "net.cuh"
 
 namespace airpose {
-
-struct ConvSpec { int cout, cin, k, stride, pad; };
 
 static std::vector<ConvSpec> resnet50_specs() {      // forward order, see synthetic.conv_specs()
   std::vector<ConvSpec> v;
@@ -44,10 +42,6 @@ static std::vector<ConvSpec> resnet50_specs() {      // forward order, see synth
 constexpr int kStemTapK = 32;          // 7*3 = 21 padded to 32 bf16 = one 64-byte swizzle row
 constexpr int kStemK = 7 * kStemTapK;  // 224
 constexpr int kStemPlaneRows = 115;    // 2 zero rows + 112 + 1 zero row  (vertical taps reach p-2 .. p+1)
-constexpr int kFeat = 2048;
-constexpr int kState = 284, kStatePad = 320;
-constexpr int kHid = 1024;
-constexpr int kDec = 145, kDecPad = 160;
 
 // ------------------------------------------------------------------------------ pack kernels
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cout, int cin,
@@ -75,40 +69,6 @@ __global__ void fold_bn_kernel(const float* __restrict__ g, const float* __restr
   const float s = g[i] / sqrtf(var[i] + eps);
   scale[i] = s;
   shift[i] = b[i] - mean[i] * s;
-}
-
-// W [rows, src_ld] columns [col0, col0+ncols) -> bf16 [rows_pad, 3*kp] = [hi | hi | lo]
-__global__ void pack_split_weight_kernel(const float* __restrict__ w, int rows, int64_t src_ld, int col0, int ncols,
-                                         __nv_bfloat16* __restrict__ out, int rows_pad, int kp) {
-  const int64_t total = (int64_t)rows_pad * kp;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / kp), k = (int)(i % kp);
-    const float v = (r < rows && k < ncols) ? w[(int64_t)r * src_ld + col0 + k] : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    __nv_bfloat16* o = out + (int64_t)r * 3 * kp;
-    o[k] = hi; o[kp + k] = hi; o[2 * kp + k] = lo;
-  }
-}
-
-// x fp32 [rows, ld] -> bf16 [rows, 3*kp] = [hi | lo | hi]
-__global__ void split_act_kernel(const float* __restrict__ x, int rows, int64_t ld, int ncols,
-                                 __nv_bfloat16* __restrict__ out, int kp) {
-  const int64_t total = (int64_t)rows * kp;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / kp), k = (int)(i % kp);
-    const float v = (k < ncols) ? x[(int64_t)r * ld + k] : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    __nv_bfloat16* o = out + (int64_t)r * 3 * kp;
-    o[k] = hi; o[kp + k] = lo; o[2 * kp + k] = hi;
-  }
-}
-
-__global__ void concat_bias_kernel(const float* a, int na, const float* b, int nb, float* out, int npad) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npad) return;
-  out[i] = i < na ? a[i] : (i < na + nb ? b[i - na] : 0.f);
 }
 
 // ------------------------------------------------------------------------------ trunk kernels
@@ -185,108 +145,20 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, int n, float
   out[i] = s / 49.f;
 }
 
-// ------------------------------------------------------------------------------ IEF kernels
-// rows m in [0,2B): view v = m / B, sample b = m % B.
-__global__ void ief_init_kernel(int B, const float* pos0, const float* pos1, const float* init_pose,
-                                const float* th0, const float* th1, int th_stride, const float* init_shape,
-                                const float* sh0, const float* sh1, int sh_stride, float* pose, float* shape) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * B * 145) return;
-  const int m = i / 145, e = i % 145, v = m / B, b = m % B;
-  if (e < 3) pose[m * 135 + e] = (v ? pos1 : pos0)[b * 3 + e];
-  else if (e < 135) {
-    const float* th = v ? th1 : th0;
-    pose[m * 135 + e] = th ? th[(int64_t)b * th_stride + (e - 3)] : init_pose[e - 3];   // model_copenet.py:121-132
-  } else {
-    const float* sh = v ? sh1 : sh0;
-    shape[m * 10 + (e - 135)] = sh ? sh[(int64_t)b * sh_stride + (e - 135)] : init_shape[e - 135];
-  }
-}
-
-// fc1 input minus the image feature: [bb, pos, orient, art_self, shape_self, art_other, shape_other]
-// (model_copenet.py:185,192), written as the split-bf16 operand [hi | lo | hi] of width 3*320.
-__global__ void ief_state_kernel(int B, const float* bb0, const float* bb1, const float* pose, const float* shape,
-                                 __nv_bfloat16* out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * B * kStatePad) return;
-  const int m = i / kStatePad, k = i % kStatePad, v = m / B, b = m % B, mo = (1 - v) * B + b;
-  float x = 0.f;
-  if (k < 3) x = (v ? bb1 : bb0)[b * 3 + k];
-  else if (k < 138) x = pose[m * 135 + (k - 3)];
-  else if (k < 148) x = shape[m * 10 + (k - 138)];
-  else if (k < 274) x = pose[mo * 135 + 9 + (k - 148)];
-  else if (k < kState) x = shape[mo * 10 + (k - 274)];
-  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-  __nv_bfloat16* o = out + (int64_t)m * 3 * kStatePad;
-  o[k] = hi; o[kStatePad + k] = lo; o[2 * kStatePad + k] = hi;
-}
-
-// pred_pose = cat(pos, orient, art) + decpose(xc); pred_shape = shape + decshape(xc)  (:195-202)
-__global__ void ief_update_kernel(int B, const float* d, float* pose, float* shape, float* out_pose0, float* out_betas0,
-                                  float* out_pose1, float* out_betas1) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * B * 145) return;
-  const int m = i / 145, e = i % 145, v = m / B, b = m % B;
-  if (e < 135) {
-    const float val = pose[m * 135 + e] + d[m * kDecPad + e];
-    pose[m * 135 + e] = val;
-    if (out_pose0) (v ? out_pose1 : out_pose0)[b * 135 + e] = val;
-  } else {
-    const float val = shape[m * 10 + (e - 135)] + d[m * kDecPad + e];
-    shape[m * 10 + (e - 135)] = val;
-    if (out_betas0) (v ? out_betas1 : out_betas0)[b * 10 + (e - 135)] = val;
-  }
-}
-
 }  // namespace airpose
 
 using namespace airpose;
 
-struct TrunkPlan {
-  std::vector<GemmLaunch> gemms;       // in launch order: [stem,] then per block conv1, conv2, [down], conv3
-  const __nv_bfloat16* final_act = nullptr;
-};
-
-struct IefPlan {
-  GemmLaunch g0, g1, g2, g3;
-};
-
-struct airpose_net {
-  int device = 0;
-  int max_images = 0;
-  int chunk = 0;
-  bool loaded = false;
-  std::vector<ConvSpec> specs;
-  std::vector<__nv_bfloat16*> wq;       // packed conv weights
-  std::vector<float*> scale, shift;     // folded BN
-  // IEF
-  __nv_bfloat16 *w1a = nullptr, *w1b = nullptr, *w2 = nullptr, *wd = nullptr;
-  float *b1 = nullptr, *b2 = nullptr, *bd = nullptr, *init_pose = nullptr, *init_shape = nullptr;
-  // workspaces
-  __nv_bfloat16* col = nullptr;
-  __nv_bfloat16* stem_out = nullptr;
-  __nv_bfloat16* act[4] = {nullptr, nullptr, nullptr, nullptr};    // stage A (stem, layer1, layer2): `chunk` images
-  __nv_bfloat16* actB[4] = {nullptr, nullptr, nullptr, nullptr};   // stage B (layer3, layer4): `group` images
-  int group = 0;
-  std::map<std::pair<int, int>, TrunkPlan> plansA;                 // (images, slot inside the group)
-  std::map<int, TrunkPlan> plansB;                                 // images
-  // IEF workspace (grown on demand)
-  int ief_cap = 0;
-  __nv_bfloat16 *xf_split = nullptr, *state_split = nullptr, *y1_split = nullptr, *y2_split = nullptr;
-  float *hbuf = nullptr, *dbuf = nullptr, *pose = nullptr, *shape = nullptr;
-  std::map<int, IefPlan> ief_plans;
-};
-
-// Stage A (56x56 / 28x28 activations) runs in chunks small enough that a layer's output is still in
-// L2 when the next layer reads it; stage B (14x14 / 7x7) runs on a larger group so that its GEMMs
-// have enough 128-row tiles to fill 148 SMs.  (DESIGN.md "trunk schedule")
+// Stage A (56x56 / 28x28 activations) runs in chunks of images, stage B (14x14 / 7x7) on a larger group
+// so that its GEMMs have enough 128-row tiles to fill 148 SMs.  Measured on B200 (profiles/): every
+// launch costs ~5 us of ramp-up/drain even with PDL, which outweighs L2 residency of smaller chunks
+// (128 images: chunk 8 -> 4.63 ms, 16 -> 3.38, 32 -> 3.01, 64 -> 2.73).  (DESIGN.md "trunk schedule")
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   const int c = e ? atoi(e) : dflt;
   return c > 0 ? c : dflt;
 }
-static int default_chunk() { return env_int("AIRPOSE_TRUNK_CHUNK", 32); }
+static int default_chunk() { return env_int("AIRPOSE_TRUNK_CHUNK", 64); }
 static int default_group() { return env_int("AIRPOSE_TRUNK_GROUP", 128); }
 constexpr size_t kStageBElems = 28 * 28 * 512;      // per image: the largest stage-B tensor (layer3 input)
 
@@ -308,15 +180,7 @@ extern "C" int airpose_net_create(airpose_net_t** out, int max_images, int devic
     AP_CHECK_CUDA(cudaMalloc((void**)&h->scale[i], s.cout * sizeof(float)));
     AP_CHECK_CUDA(cudaMalloc((void**)&h->shift[i], s.cout * sizeof(float)));
   }
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->w1a, (size_t)kHid * 3 * kFeat * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->w1b, (size_t)kHid * 3 * kStatePad * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->w2, (size_t)kHid * 3 * kHid * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->wd, (size_t)kDecPad * 3 * kHid * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->b1, kHid * sizeof(float)));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->b2, kHid * sizeof(float)));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->bd, kDecPad * sizeof(float)));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->init_pose, 144 * sizeof(float)));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->init_shape, 10 * sizeof(float)));
+  if (ief_create(h)) return 1;
   const size_t act_elems = (size_t)h->chunk * 112 * 112 * 64;       // == 56*56*256, the largest activation
   AP_CHECK_CUDA(cudaMalloc((void**)&h->col, (size_t)h->chunk * 2 * kStemPlaneRows * 112 * kStemTapK * 2));
   AP_CHECK_CUDA(cudaMalloc((void**)&h->stem_out, act_elems * 2));
@@ -332,9 +196,8 @@ extern "C" int airpose_net_destroy(airpose_net_t* h) {
   for (auto p : h->wq) cudaFree(p);
   for (auto p : h->scale) cudaFree(p);
   for (auto p : h->shift) cudaFree(p);
-  void* ptrs[] = {h->w1a, h->w1b, h->w2, h->wd, h->b1, h->b2, h->bd, h->init_pose, h->init_shape, h->col, h->stem_out,
-                  h->act[0], h->act[1], h->act[2], h->act[3], h->actB[0], h->actB[1], h->actB[2], h->actB[3], h->xf_split, h->state_split, h->y1_split, h->y2_split,
-                  h->hbuf, h->dbuf, h->pose, h->shape};
+  ief_destroy(h);
+  void* ptrs[] = {h->col, h->stem_out, h->act[0], h->act[1], h->act[2], h->act[3], h->actB[0], h->actB[1], h->actB[2], h->actB[3]};
   for (void* p : ptrs) cudaFree(p);
   delete h;
   return 0;
@@ -354,27 +217,7 @@ extern "C" int airpose_net_load(airpose_net_t* h, const airpose_net_params* p, v
                                                           h->scale[i], h->shift[i]);
     AP_LAUNCH_CHECK();
   }
-  AP_REQUIRE(p->fc1_w && p->fc1_b && p->fc2_w && p->fc2_b && p->decpose_w && p->decpose_b && p->decshape_w &&
-             p->decshape_b && p->init_pose && p->init_shape, "airpose_net_load: regressor parameter is null");
-  const int fc1_in = kFeat + kState;
-  pack_split_weight_kernel<<<512, 256, 0, st>>>(p->fc1_w, kHid, fc1_in, 0, kFeat, h->w1a, kHid, kFeat);
-  AP_LAUNCH_CHECK();
-  pack_split_weight_kernel<<<256, 256, 0, st>>>(p->fc1_w, kHid, fc1_in, kFeat, kState, h->w1b, kHid, kStatePad);
-  AP_LAUNCH_CHECK();
-  pack_split_weight_kernel<<<512, 256, 0, st>>>(p->fc2_w, kHid, kHid, 0, kHid, h->w2, kHid, kHid);
-  AP_LAUNCH_CHECK();
-  // decoder rows: 0..134 decpose, 135..144 decshape, 145..159 zero
-  AP_CHECK_CUDA(cudaMemsetAsync(h->wd, 0, (size_t)kDecPad * 3 * kHid * 2, st));
-  pack_split_weight_kernel<<<128, 256, 0, st>>>(p->decpose_w, 135, kHid, 0, kHid, h->wd, 135, kHid);
-  AP_LAUNCH_CHECK();
-  pack_split_weight_kernel<<<32, 256, 0, st>>>(p->decshape_w, 10, kHid, 0, kHid, h->wd + (size_t)135 * 3 * kHid, 10, kHid);
-  AP_LAUNCH_CHECK();
-  AP_CHECK_CUDA(cudaMemcpyAsync(h->b1, p->fc1_b, kHid * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  AP_CHECK_CUDA(cudaMemcpyAsync(h->b2, p->fc2_b, kHid * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  concat_bias_kernel<<<1, 256, 0, st>>>(p->decpose_b, 135, p->decshape_b, 10, h->bd, kDecPad);
-  AP_LAUNCH_CHECK();
-  AP_CHECK_CUDA(cudaMemcpyAsync(h->init_pose, p->init_pose, 144 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  AP_CHECK_CUDA(cudaMemcpyAsync(h->init_shape, p->init_shape, 10 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (ief_load(h, p, st)) return 1;
   h->loaded = true;
   return 0;
 }
@@ -460,14 +303,14 @@ static int build_blocks(airpose_net* h, int n, int l0, int l1, int H, __nv_bfloa
   return 0;
 }
 
-// stage A: stem GEMM + layer1 + layer2 on `n` <= chunk images; output [n,28,28,512] lands in slot
-// `slot` of the stage-B input buffer.
-static int build_plan_a(airpose_net* h, int n, int slot, TrunkPlan* plan) {
+// stage A: stem GEMM + layer1 + layer2 on `n` <= chunk images; output [n,28,28,512] lands at image
+// offset `first` of the stage-B input buffer.
+static int build_plan_a(airpose_net* h, int n, int first, TrunkPlan* plan) {
   plan->gemms.clear();
   GemmLaunch L{};
   if (build_stem_gemm(h, n, &L)) return 1;
   plan->gemms.push_back(L);
-  __nv_bfloat16* out = slot >= 0 ? h->actB[0] + (size_t)slot * h->chunk * kStageBElems : nullptr;
+  __nv_bfloat16* out = h->actB[0] + (size_t)first * kStageBElems;
   return build_blocks(h, n, 0, 2, 56, h->act, out, plan);
 }
 
@@ -487,24 +330,26 @@ static int launch_stem_front(airpose_net* h, const float* x, int n, const GemmLa
   return 0;
 }
 
-extern "C" int airpose_backbone_fwd(airpose_net_t* h, const float* x, int n_images, float* out_feat, void* stream_) {
-  AP_REQUIRE(h && x && out_feat, "airpose_backbone_fwd: null argument");
-  AP_REQUIRE(h->loaded, "airpose_backbone_fwd: weights not loaded (call airpose_net_load)");
-  AP_REQUIRE(n_images >= 0, "airpose_backbone_fwd: negative image count");
-  cudaStream_t st = (cudaStream_t)stream_;
+// Images [0, n0) come from x0, images [n0, n_images) from x1 (the two views of a batch of pairs).
+static int backbone_fwd_segments(airpose_net_t* h, const float* x0, int n0, const float* x1, int n_images, float* out_feat,
+                                 cudaStream_t st) {
+  const size_t img = (size_t)3 * 224 * 224;
+  auto src = [&](int i) { return i < n0 ? x0 + (size_t)i * img : x1 + (size_t)(i - n0) * img; };
   for (int g0 = 0; g0 < n_images; g0 += h->group) {
     const int ng = std::min(h->group, n_images - g0);
-    for (int i0 = 0, slot = 0; i0 < ng; i0 += h->chunk, ++slot) {
-      const int n = std::min(h->chunk, ng - i0);
-      auto key = std::make_pair(n, slot);
+    for (int i0 = 0, n = 0; i0 < ng; i0 += n) {
+      n = std::min(h->chunk, ng - i0);
+      const int first = g0 + i0;
+      if (first < n0 && first + n > n0) n = n0 - first;      // a chunk never straddles the two input tensors
+      auto key = std::make_pair(n, i0);
       auto it = h->plansA.find(key);
       if (it == h->plansA.end()) {
         TrunkPlan plan;
-        if (build_plan_a(h, n, slot, &plan)) return 1;
+        if (build_plan_a(h, n, i0, &plan)) return 1;
         it = h->plansA.emplace(key, std::move(plan)).first;
       }
       const TrunkPlan& plan = it->second;
-      if (launch_stem_front(h, x + (size_t)(g0 + i0) * 3 * 224 * 224, n, plan.gemms[0], h->act[0], st)) return 1;
+      if (launch_stem_front(h, src(first), n, plan.gemms[0], h->act[0], st)) return 1;
       for (size_t g = 1; g < plan.gemms.size(); ++g)
         if (launch_gemm(plan.gemms[g], st)) return 1;
     }
@@ -523,6 +368,21 @@ extern "C" int airpose_backbone_fwd(airpose_net_t* h, const float* x, int n_imag
   return 0;
 }
 
+extern "C" int airpose_backbone_fwd(airpose_net_t* h, const float* x, int n_images, float* out_feat, void* stream_) {
+  AP_REQUIRE(h && x && out_feat, "airpose_backbone_fwd: null argument");
+  AP_REQUIRE(h->loaded, "airpose_backbone_fwd: weights not loaded (call airpose_net_load)");
+  AP_REQUIRE(n_images >= 0, "airpose_backbone_fwd: negative image count");
+  return backbone_fwd_segments(h, x, n_images, x, n_images, out_feat, (cudaStream_t)stream_);
+}
+
+extern "C" int airpose_backbone_fwd_pair(airpose_net_t* h, const float* x0, const float* x1, int n_pairs, float* out_feat,
+                                         void* stream_) {
+  AP_REQUIRE(h && x0 && x1 && out_feat, "airpose_backbone_fwd_pair: null argument");
+  AP_REQUIRE(h->loaded, "airpose_backbone_fwd_pair: weights not loaded (call airpose_net_load)");
+  AP_REQUIRE(n_pairs >= 0, "airpose_backbone_fwd_pair: negative pair count");
+  return backbone_fwd_segments(h, x0, n_pairs, x1, 2 * n_pairs, out_feat, (cudaStream_t)stream_);
+}
+
 extern "C" int airpose_backbone_stem(airpose_net_t* h, const float* x, int n, void* out, void* stream_) {
   AP_REQUIRE(h && x && out, "airpose_backbone_stem: null argument");
   AP_REQUIRE(h->loaded, "airpose_backbone_stem: weights not loaded (call airpose_net_load)");
@@ -530,81 +390,4 @@ extern "C" int airpose_backbone_stem(airpose_net_t* h, const float* x, int n, vo
   GemmLaunch stem{};
   if (build_stem_gemm(h, n, &stem)) return 1;
   return launch_stem_front(h, x, n, stem, (__nv_bfloat16*)out, (cudaStream_t)stream_);
-}
-
-static int ensure_ief_ws(airpose_net* h, int B, cudaStream_t st) {
-  if (B <= h->ief_cap) return 0;
-  AP_CHECK_CUDA(cudaStreamSynchronize(st));
-  void* old[] = {h->xf_split, h->state_split, h->y1_split, h->y2_split, h->hbuf, h->dbuf, h->pose, h->shape};
-  for (void* p : old) cudaFree(p);
-  h->ief_plans.clear();
-  const size_t M = (size_t)2 * B;
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->xf_split, M * 3 * kFeat * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->state_split, M * 3 * kStatePad * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->y1_split, M * 3 * kHid * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->y2_split, M * 3 * kHid * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->hbuf, M * kHid * sizeof(float)));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->dbuf, M * kDecPad * sizeof(float)));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->pose, M * 135 * sizeof(float)));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->shape, M * 10 * sizeof(float)));
-  h->ief_cap = B;
-  return 0;
-}
-
-static int make_ief_gemm(GemmLaunch* L, const __nv_bfloat16* A, int M, int K3, const __nv_bfloat16* W, int N) {
-  L->M = M; L->N = N; L->K = K3;
-  L->block_n = 64;                     // M is small: narrow tiles spread the N dimension over more SMs
-  if (make_tmap_tiled_bf16(&L->tmA, A, M, K3, K3, 128, 64)) return 1;
-  if (make_tmap_tiled_bf16(&L->tmB, W, N, K3, K3, 64, 64)) return 1;
-  return 0;
-}
-
-extern "C" int airpose_ief_fwd(airpose_net_t* h, const airpose_ief_args* a, void* stream_) {
-  AP_REQUIRE(h && a, "airpose_ief_fwd: null argument");
-  AP_REQUIRE(h->loaded, "airpose_ief_fwd: weights not loaded (call airpose_net_load)");
-  AP_REQUIRE(a->batch >= 0 && a->iters >= 1, "airpose_ief_fwd: bad batch/iters");
-  AP_REQUIRE(a->xf0 && a->xf1 && a->bb0 && a->bb1 && a->pos0 && a->pos1 && a->out_pose0 && a->out_pose1 &&
-             a->out_betas0 && a->out_betas1, "airpose_ief_fwd: null tensor");
-  const int B = a->batch, M = 2 * B;
-  if (B == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream_;
-  if (ensure_ief_ws(h, B, st)) return 1;
-  auto it = h->ief_plans.find(B);
-  if (it == h->ief_plans.end()) {
-    IefPlan p;
-    if (make_ief_gemm(&p.g0, h->xf_split, M, 3 * kFeat, h->w1a, kHid)) return 1;
-    p.g0.epi.shift = h->b1; p.g0.epi.out_f32 = h->hbuf; p.g0.epi.ldf = kHid;
-    if (make_ief_gemm(&p.g1, h->state_split, M, 3 * kStatePad, h->w1b, kHid)) return 1;
-    p.g1.epi.residual = h->hbuf; p.g1.epi.ldr = kHid; p.g1.epi.residual_f32 = 1;
-    p.g1.epi.out_split = h->y1_split; p.g1.epi.lds = 3 * kHid;
-    if (make_ief_gemm(&p.g2, h->y1_split, M, 3 * kHid, h->w2, kHid)) return 1;
-    p.g2.epi.shift = h->b2; p.g2.epi.out_split = h->y2_split; p.g2.epi.lds = 3 * kHid;
-    if (make_ief_gemm(&p.g3, h->y2_split, M, 3 * kHid, h->wd, kDecPad)) return 1;
-    p.g3.epi.shift = h->bd; p.g3.epi.out_f32 = h->dbuf; p.g3.epi.ldf = kDecPad;
-    it = h->ief_plans.emplace(B, p).first;
-  }
-  const IefPlan& p = it->second;
-  const int nthr = 256;
-  split_act_kernel<<<ceil_div(B * kFeat, nthr), nthr, 0, st>>>(a->xf0, B, kFeat, kFeat, h->xf_split, kFeat);
-  AP_LAUNCH_CHECK();
-  split_act_kernel<<<ceil_div(B * kFeat, nthr), nthr, 0, st>>>(a->xf1, B, kFeat, kFeat, h->xf_split + (size_t)B * 3 * kFeat, kFeat);
-  AP_LAUNCH_CHECK();
-  if (launch_gemm(p.g0, st)) return 1;
-  ief_init_kernel<<<ceil_div(M * 145, nthr), nthr, 0, st>>>(B, a->pos0, a->pos1, h->init_pose, a->init_theta0, a->init_theta1,
-                                                           a->init_theta_stride, h->init_shape, a->init_shape0,
-                                                           a->init_shape1, a->init_shape_stride, h->pose, h->shape);
-  AP_LAUNCH_CHECK();
-  for (int iter = 0; iter < a->iters; ++iter) {
-    ief_state_kernel<<<ceil_div(M * kStatePad, nthr), nthr, 0, st>>>(B, a->bb0, a->bb1, h->pose, h->shape, h->state_split);
-    AP_LAUNCH_CHECK();
-    if (launch_gemm(p.g1, st)) return 1;
-    if (launch_gemm(p.g2, st)) return 1;
-    if (launch_gemm(p.g3, st)) return 1;
-    const bool last = iter == a->iters - 1;
-    ief_update_kernel<<<ceil_div(M * 145, nthr), nthr, 0, st>>>(B, h->dbuf, h->pose, h->shape, last ? a->out_pose0 : nullptr,
-                                                             last ? a->out_betas0 : nullptr, last ? a->out_pose1 : nullptr,
-                                                             last ? a->out_betas1 : nullptr);
-    AP_LAUNCH_CHECK();
-  }
-  return 0;
 }

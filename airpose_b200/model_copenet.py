@@ -11,8 +11,8 @@ reference's names, so ``state_dict()`` has the same 331 keys, Lightning checkpoi
 (``model.``-prefixed) and ``load_state_dict(resnet50.state_dict(), strict=False)`` load, and
 ``.fc1/.fc2/.decpose/.decshape/.deccam`` / ``.parameters()`` are there for optimizers.  The
 children are parameter containers only: ``forward`` hands their tensors to
-libairpose_b200 (bf16 tcgen05 implicit-GEMM convs with fused BN/ReLU/residual; split-bf16
-tcgen05 GEMMs for the regressor).  Eval mode only for now: training-mode BatchNorm
+libairpose_b200 (bf16 tcgen05 implicit-GEMM convs with fused BN/ReLU/residual; the regressor's
+affine chain collapsed into one fp32 matrix, csrc/ief.cu).  Eval mode only for now: training-mode BatchNorm
 statistics and dropout arrive with the backward kernels.
 """
 from __future__ import annotations
@@ -162,7 +162,10 @@ class copenet(nn.Module):
                 _lib.load().airpose_net_destroy(self._handle)
             except Exception:
                 pass
-            self._handle = None
+            try:
+                object.__setattr__(self, "_handle", None)      # also safe during interpreter shutdown
+            except Exception:
+                pass
 
     def __del__(self):
         self._release()
@@ -180,6 +183,25 @@ class copenet(nn.Module):
         with torch.cuda.device(device):
             _lib.check(lib.airpose_backbone_fwd(h, x.data_ptr(), n, out.data_ptr(), _lib.current_stream()),
                        "airpose_backbone_fwd")
+        return out
+
+    def forward_feat_ext_pair(self, x0, x1):
+        """Both trunk passes of ``forward`` (model_copenet.py:140-141) in one native call, no concatenation:
+        returns [2B,2048] with rows [0,B) = view 0 and [B,2B) = view 1."""
+        for x in (x0, x1):
+            if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
+                raise ValueError("forward_feat_ext_pair expects [B,3,224,224], got {}".format(tuple(x.shape)))
+        if x0.shape[0] != x1.shape[0]:
+            raise ValueError("the two views must have the same batch size")
+        device = self.conv1.weight.device
+        x0 = x0.detach().to(device=device, dtype=torch.float32).contiguous()
+        x1 = x1.detach().to(device=device, dtype=torch.float32).contiguous()
+        B = x0.shape[0]
+        lib, h = self._ensure(2 * B, device)
+        out = torch.empty(2 * B, 2048, device=device, dtype=torch.float32)
+        with torch.cuda.device(device):
+            _lib.check(lib.airpose_backbone_fwd_pair(h, x0.data_ptr(), x1.data_ptr(), B, out.data_ptr(), _lib.current_stream()),
+                       "airpose_backbone_fwd_pair")
         return out
 
     def _ief(self, xf0, xf1, bb0, bb1, pos0, pos1, theta0, theta1, shape0, shape1, iters):
@@ -238,7 +260,7 @@ class copenet(nn.Module):
         """model_copenet.py:112-159.  Both views go through the trunk in one call (eval-mode
         BatchNorm makes images independent); the regressor keeps the two views of a pair together."""
         B = x0.shape[0]
-        xf = self.forward_feat_ext(torch.cat([x0, x1], dim=0))
+        xf = self.forward_feat_ext_pair(x0, x1)
         return self._ief(xf[:B], xf[B:], bb0, bb1, init_position0, init_position1, init_theta0, init_theta1,
                          init_shape0, init_shape1, iters)
 

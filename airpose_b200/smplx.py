@@ -191,7 +191,10 @@ class SMPLX(nn.Module):
                 _lib.load().airpose_smplx_destroy(self._handle)
             except Exception:
                 pass
-            self._handle = None
+            try:
+                object.__setattr__(self, "_handle", None)      # also safe during interpreter shutdown
+            except Exception:
+                pass
 
     def __del__(self):
         self._release()

@@ -142,14 +142,22 @@ typedef struct {
 /* max_images bounds the workspace: images per trunk call (two views of B pairs = 2B). */
 int airpose_net_create(airpose_net_t** out, int max_images, int device);
 int airpose_net_destroy(airpose_net_t* h);
-/* (Re)pack weights: bf16 K-major conv matrices, folded BN scale/shift, split-bf16 IEF matrices. */
+/* (Re)pack weights: bf16 K-major conv matrices, folded BN scale/shift, the collapsed regressor
+ * matrix G = Wdec*W2*W1 (formed in fp64; ief.cu). */
 int airpose_net_load(airpose_net_t* h, const airpose_net_params* p, void* stream);
 
 /* copenet.forward_feat_ext (model_copenet.py:161-176), eval mode:
  * x [n,3,224,224] fp32 NCHW -> feat [n,2048] fp32.  bf16 operands, fp32 accumulate. */
 int airpose_backbone_fwd(airpose_net_t* h, const float* x_nchw, int n_images, float* out_feat, void* stream);
+/* The two trunk passes of copenet.forward (model_copenet.py:140-141) in one call, without concatenating
+ * the views: x0, x1 [B,3,224,224] -> out_feat [2B,2048] (rows [0,B) = view 0, [B,2B) = view 1).
+ * Eval-mode BatchNorm makes images independent, so both views share every launch. */
+int airpose_backbone_fwd_pair(airpose_net_t* h, const float* x0_nchw, const float* x1_nchw, int n_pairs,
+                              float* out_feat, void* stream);
 
-/* The regressor half of copenet.forward (model_copenet.py:118-159,178-204), eval mode.
+/* The regressor half of copenet.forward (model_copenet.py:118-159,178-204), eval mode: with dropout
+ * inactive the three Linears have no nonlinearity between them, so the pass is evaluated as one
+ * affine map per iteration (fp32 FMA; differs from the reference chain by summation order only).
  * xf0/xf1 [B,2048]; bb0/bb1 [B,3]; pos0/pos1 [B,3] (already scaled, copenet_twoview.py:199-203);
  * init_theta0/1 [B,>=132] or NULL (module init_pose); init_shape0/1 [B,10] or NULL.
  * Outputs pred_pose [B,135], pred_betas [B,10] per view. */

@@ -260,6 +260,21 @@ def test_trunk_matches_oracle_and_golden(net_gpu, net_state, golden_twoview):
     assert e_f < 1e-2
 
 
+@pytest.mark.parametrize("B", [3, 70])
+def test_trunk_pair_entry_matches_single_entry(net_gpu, B):
+    """airpose_backbone_fwd_pair (two input tensors, chunks that never straddle them, groups of 128 images)
+    gives bit-identical features to the concatenated single-tensor call: images are independent in eval mode."""
+    g = torch.Generator(device="cpu").manual_seed(B)
+    x0 = torch.randn(B, 3, 224, 224, generator=g).to(DEV)
+    x1 = torch.randn(B, 3, 224, 224, generator=g).to(DEV)
+    a = net_gpu.forward_feat_ext_pair(x0, x1)
+    b = net_gpu.forward_feat_ext(torch.cat([x0, x1]))
+    assert a.shape == (2 * B, 2048)
+    assert torch.equal(a, b)
+    c = net_gpu.forward_feat_ext(x1[:2])
+    assert torch.equal(c, a[B:B + 2])
+
+
 def _conv_abi(x_nhwc, w_oihw, bn, sd, stride, pad, residual=None, relu=True):
     """One conv+BN(+residual)+ReLU through airpose_conv_bf16 with weights packed here."""
     lib = _lib.load()
