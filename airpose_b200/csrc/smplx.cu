@@ -21,36 +21,26 @@
 #include <vector>
 
 #include "common.cuh"
+#include "smplx.cuh"
 
 namespace airpose {
 
-constexpr int kMaxJoints = 64;
-constexpr int kMaxShape = 20;
 constexpr int kVertsPerCta = 128;
 constexpr int kMeshTile = 16;
-
-struct SmplxDev {
-  int V, J, NS, P, L, E, KW;
-  const float* v_template;   // [V,3]
-  const float* shapedirs;    // [V,3,NS]
-  const float* posedirs;     // [P, V*3]
-  const float* J_template;   // [J,3]
-  const float* J_shapedirs;  // [J,3,NS]
-  const int* parents;        // [J]
-  const int* skin_idx;       // [KW,V]
-  const float* skin_w;       // [KW,V]
-  const int* lmk_vidx;       // [L,3]
-  const float* lmk_bary;     // [L,3]
-  const int* extra_idx;      // [E]
-};
 
 struct PoseArgs {
   int B, nb, n_active;       // n_active = joints 1..n_active feed the pose feature
   const float* betas; int betas_stride;
   const float* seg[3]; int seg_stride[3];   // joint 0 | joints 1..21 | joints 22..J-1
-  float* A;                  // [B,J,12]
+  float* A;                  // [B,J,12]  (generic vertex kernel) or null
   float* Jt;                 // [B,J,3]
-  float* feat;               // [B,PF]
+  float* feat;               // [B,PF]    (generic vertex kernel) or null
+  // tensor-core vertex kernel (smplx_tc.cu): per-mesh record + split-fp16 pose feature
+  float* rec;                // [Bpad, kTcRecFloats] or null
+  __half* fh; __half* fl;    // [B, kTcK]
+  const float* transl;
+  const float* root_R; int root_R_stride;
+  const float* root_t; int root_t_stride;
 };
 
 __device__ __forceinline__ void load_rot(const PoseArgs& a, int b, int j, float R[9]) {
@@ -123,19 +113,49 @@ __global__ void __launch_bounds__(kMaxJoints) smplx_pose_kernel(SmplxDev m, Pose
   }
   float* Jt = a.Jt + ((size_t)b * m.J + j) * 3;
   Jt[0] = G[3]; Jt[1] = G[7]; Jt[2] = G[11];                    // posed joints (:360)
-  float* A = a.A + ((size_t)b * m.J + j) * 12;
+  float Aj[12];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {                                  // rel_transforms (:365-368)
     const float gj = G[r * 4 + 0] * Js[j][0] + G[r * 4 + 1] * Js[j][1] + G[r * 4 + 2] * Js[j][2];
-    A[r * 4 + 0] = G[r * 4 + 0];
-    A[r * 4 + 1] = G[r * 4 + 1];
-    A[r * 4 + 2] = G[r * 4 + 2];
-    A[r * 4 + 3] = G[r * 4 + 3] - gj;
+    Aj[r * 4 + 0] = G[r * 4 + 0];
+    Aj[r * 4 + 1] = G[r * 4 + 1];
+    Aj[r * 4 + 2] = G[r * 4 + 2];
+    Aj[r * 4 + 3] = G[r * 4 + 3] - gj;
   }
-  if (j >= 1 && j <= a.n_active) {                               // pose_feature (lbs.py:197)
+  if (a.A) {
+    float* A = a.A + ((size_t)b * m.J + j) * 12;
+#pragma unroll
+    for (int e = 0; e < 12; ++e) A[e] = Aj[e];
+  }
+  if (a.feat && j >= 1 && j <= a.n_active) {                     // pose_feature (lbs.py:197)
     float* f = a.feat + (size_t)b * (a.n_active * 9) + (j - 1) * 9;
 #pragma unroll
     for (int e = 0; e < 9; ++e) f[e] = R[e] - ((e % 4 == 0) ? 1.f : 0.f);
+  }
+  if (a.rec) {
+    float* rec = a.rec + (size_t)b * kTcRecFloats;
+    if (j < kTcBodyJoints) {
+#pragma unroll
+      for (int e = 0; e < 12; e += 4) *reinterpret_cast<float4*>(rec + j * 12 + e) = make_float4(Aj[e], Aj[e + 1], Aj[e + 2], Aj[e + 3]);
+    }
+    if (j >= 1 && j < kTcBodyJoints) {                           // split-fp16 pose feature: f = hi + lo
+#pragma unroll
+      for (int e = 0; e < 9; ++e) {
+        const float f = R[e] - ((e % 4 == 0) ? 1.f : 0.f);
+        const __half hi = __float2half_rn(f);
+        a.fh[(size_t)b * kTcK + (j - 1) * 9 + e] = hi;
+        a.fl[(size_t)b * kTcK + (j - 1) * 9 + e] = __float2half_rn(f - __half2float(hi));
+      }
+    }
+    if (j < kTcK - 189) {                                        // zero the K padding
+      a.fh[(size_t)b * kTcK + 189 + j] = __float2half_rn(0.f);
+      a.fl[(size_t)b * kTcK + 189 + j] = __float2half_rn(0.f);
+    }
+    if (j < 12) rec[kTcRecBetas + j] = j < a.nb ? beta_s[j] : 0.f;
+    if (j >= 12 && j < 21) rec[kTcRecCam + (j - 12)] = a.root_R ? __ldg(a.root_R + (size_t)b * a.root_R_stride + (j - 12))
+                                                                  : (((j - 12) % 4 == 0) ? 1.f : 0.f);
+    if (j >= 21 && j < 24) rec[kTcRecCam + 9 + (j - 21)] = a.root_t ? __ldg(a.root_t + (size_t)b * a.root_t_stride + (j - 21)) : 0.f;
+    if (j >= 24 && j < 28) rec[kTcRecTransl + (j - 24)] = (a.transl && j < 27) ? __ldg(a.transl + (size_t)b * 3 + (j - 24)) : 0.f;
   }
 }
 
@@ -353,6 +373,7 @@ using namespace airpose;
 struct airpose_smplx {
   int device = 0;
   SmplxDev d{};
+  SmplxTc tc;
   std::vector<void*> owned;
   float* ws = nullptr;
   size_t ws_floats = 0;
@@ -442,6 +463,7 @@ extern "C" int airpose_smplx_create(airpose_smplx_t** out, const airpose_smplx_m
   UP_I(extra_idx, ex.data(), std::max<size_t>(ex.size(), 1));
 #undef UP_F
 #undef UP_I
+  if (smplx_tc_create(mh, d, &h->tc, &h->owned)) return 1;
   *out = h;
   return 0;
 }
@@ -471,7 +493,12 @@ extern "C" int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_arg
   const int n_active = g->tail_pose ? d.J - 1 : (g->body_pose ? std::min(21, d.J - 1) : 0);
   const int PF = n_active * 9;
 
-  const size_t need = (size_t)B * d.J * 12 + (size_t)B * d.J * 3 + (size_t)B * std::max(PF, 1);
+  // tensor-core vertex kernel for the hot-path call pattern (smplx_tc.cu), generic fp32 kernel otherwise
+  const bool use_tc = h->tc.ok && g->body_pose && !g->tail_pose && g->num_betas <= 10 && d.J == 55;
+  const int Bpad = ceil_div(B, kTcMeshTile) * kTcMeshTile;
+  const size_t n_jt = ((size_t)B * d.J * 3 + 3) & ~size_t(3);    // keeps the record block 16-byte aligned
+  const size_t need = use_tc ? n_jt + (size_t)Bpad * kTcRecFloats + (size_t)B * kTcK      // Jt | records | fh+fl (2 x B x 192 halves)
+                             : n_jt + (size_t)B * d.J * 12 + (size_t)B * std::max(PF, 1);   // Jt | A | feat
   if (need > h->ws_floats) {
     AP_CHECK_CUDA(cudaStreamSynchronize(stream));
     cudaFree(h->ws);
@@ -479,9 +506,12 @@ extern "C" int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_arg
     AP_CHECK_CUDA(cudaMalloc((void**)&h->ws, need * sizeof(float)));
     h->ws_floats = need;
   }
-  float* A = h->ws;
-  float* Jt = A + (size_t)B * d.J * 12;
-  float* feat = Jt + (size_t)B * d.J * 3;
+  float* Jt = h->ws;
+  float* A = use_tc ? nullptr : Jt + n_jt;
+  float* feat = use_tc ? nullptr : A + (size_t)B * d.J * 12;
+  float* rec = use_tc ? Jt + n_jt : nullptr;
+  __half* fh = use_tc ? reinterpret_cast<__half*>(rec + (size_t)Bpad * kTcRecFloats) : nullptr;
+  __half* fl = use_tc ? fh + (size_t)B * kTcK : nullptr;
 
   PoseArgs pa{};
   pa.B = B; pa.nb = g->num_betas; pa.n_active = n_active;
@@ -490,27 +520,39 @@ extern "C" int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_arg
   pa.seg[1] = g->body_pose; pa.seg_stride[1] = g->body_pose_stride;
   pa.seg[2] = g->tail_pose; pa.seg_stride[2] = g->tail_pose_stride;
   pa.A = A; pa.Jt = Jt; pa.feat = feat;
+  pa.rec = rec; pa.fh = fh; pa.fl = fl;
+  pa.transl = g->transl;
+  pa.root_R = g->root_R; pa.root_R_stride = g->root_R_stride;
+  pa.root_t = g->root_t; pa.root_t_stride = g->root_t_stride;
   smplx_pose_kernel<<<B, kMaxJoints, 0, stream>>>(d, pa);
   AP_LAUNCH_CHECK();
 
-  VertexArgs va{};
-  va.B = B; va.nb = g->num_betas; va.PF = PF;
-  va.betas = g->betas; va.betas_stride = g->betas_stride;
-  va.A = A; va.feat = feat; va.transl = g->transl;
-  va.root_R = g->root_R; va.root_R_stride = g->root_R_stride;
-  va.root_t = g->root_t; va.root_t_stride = g->root_t_stride;
-  va.out = g->out_vertices; va.out_cam = g->out_vertices_cam;
-  constexpr int MB = kMeshTile;
-  const size_t smem = ((size_t)PF * MB + (size_t)MB * d.J * 12 + MB * kMaxShape + MB * 16) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
+  if (use_tc) {
+    TcCall tcall{};
+    tcall.B = B; tcall.nb = g->num_betas;
+    tcall.rec = rec; tcall.fh = fh; tcall.fl = fl;
+    tcall.out = g->out_vertices; tcall.out_cam = g->out_vertices_cam;
+    if (smplx_tc_forward(d, h->tc, tcall, stream)) return 1;
+  } else {
+    VertexArgs va{};
+    va.B = B; va.nb = g->num_betas; va.PF = PF;
+    va.betas = g->betas; va.betas_stride = g->betas_stride;
+    va.A = A; va.feat = feat; va.transl = g->transl;
+    va.root_R = g->root_R; va.root_R_stride = g->root_R_stride;
+    va.root_t = g->root_t; va.root_t_stride = g->root_t_stride;
+    va.out = g->out_vertices; va.out_cam = g->out_vertices_cam;
+    constexpr int MB = kMeshTile;
+    const size_t smem = ((size_t)PF * MB + (size_t)MB * d.J * 12 + MB * kMaxShape + MB * 16) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set = true;
+    }
+    AP_REQUIRE(smem <= 160 * 1024, "airpose_smplx_fwd: shared memory %zu too large", smem);
+    dim3 grid(ceil_div(d.V, kVertsPerCta), ceil_div(B, MB));
+    smplx_vertex_kernel<MB><<<grid, kVertsPerCta, smem, stream>>>(d, va);
+    AP_LAUNCH_CHECK();
   }
-  AP_REQUIRE(smem <= 160 * 1024, "airpose_smplx_fwd: shared memory %zu too large", smem);
-  dim3 grid(ceil_div(d.V, kVertsPerCta), ceil_div(B, MB));
-  smplx_vertex_kernel<MB><<<grid, kVertsPerCta, smem, stream>>>(d, va);
-  AP_LAUNCH_CHECK();
 
   JointArgs ja{};
   ja.B = B; ja.verts = g->out_vertices; ja.Jt = Jt; ja.transl = g->transl;

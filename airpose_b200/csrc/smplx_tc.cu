@@ -1,0 +1,398 @@
+// SMPL-X vertex kernel of the hot path on tcgen05: pose-corrective blend shapes as a tensor-core
+// contraction, shape blend + linear blend skinning + camera transform in its epilogue.
+//
+// Replaces lbs.py:179 (blend_shapes), :197-203 (pose offsets), :209-220 (skinning),
+// body_models.py:980-982 (+transl) and utils/utils.py:237-239 (transform_smpl on the vertices) of
+// /root/reference/copenet/src/copenet[/smplx/smplx] for the call pattern of copenet_twoview.py:281-292:
+// 21 body rotations given, joints 22..54 identity, <= 10 betas, zero expression.
+//
+// The pose-corrective term  offsets[b, 3v+c] = sum_p feat[b,p] * posedirs[p, 3v+c]  (189 x 3 FMAs per
+// vertex and mesh) is what bound the first kernel (2 % of the HBM roofline).  Here
+//   D_c[v, b] = P_c[v, :] . F[b, :]^T      c = x,y,z;  M = 128 vertices, N = 32 meshes, K = 192
+// runs on tcgen05 with P = fp16(posedirs * 2^10) RESIDENT in shared memory (144 KB per 128-vertex
+// tile) and the feature F = R - I split into two fp16 terms (hi + lo, 22 significant bits) streamed
+// through a TMA ring: 2 MMAs per k-step, fp32 accumulation in TMEM.  The only rounding beyond fp32 is
+// the 11-bit mantissa of the stored posedirs: <= 1e-5 of the vertex scale (tests; north_star 1e-3).
+//
+// Everything else stays fp32 on the CUDA cores, in the epilogue, straight out of TMEM (TMEM lane =
+// vertex, so per-vertex constants live in registers and a warp's stores of one mesh are contiguous):
+//   v_shaped = v_template + shapedirs . beta;  v_posed = v_shaped + D * 2^-10
+//   T = sum_k w_k A[b, joint_k]  over the vertex's non-zero skinning weights (A per mesh in smem)
+//   v = T [v_posed; 1] + transl;  v_cam = R v + t
+// On this call pattern A_j == A_ancestor(j) for every joint j >= 22 (identity local rotation:
+// G_j = G_p [I | J_j - J_p]  =>  A_j = [R_p | t_p + R_p (J_j - J_p) - R_p J_j] = A_p), so only 22
+// matrices per mesh are staged and the weights of folded joints are merged at create time.
+//
+// CTA = (128-vertex tile, range of mesh tiles), 11 warps:
+//   warp 0   TMA: P once, then F k-blocks (3-stage ring)      warp 1   MMA issuer (TMEM double-buffered)
+//   warp 2   bulk copies of per-mesh records (A, betas, camera; 16 meshes per copy, 3-stage ring)
+//   warps 3-10  epilogue: lane quarter = warp % 4, mesh half = (warp - 3) / 4
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ptx.cuh"
+#include "smplx.cuh"
+
+namespace airpose {
+
+namespace {
+
+constexpr int kThreads = 352;
+constexpr int kEpiWarp0 = 3;
+constexpr int kEpiWarps = 8;
+constexpr int kPTileBytes = 128 * 128;                 // 128 vertices x 64 fp16
+constexpr int kPBytes = 9 * kPTileBytes;               // 3 coordinates x 3 k-blocks
+constexpr int kFStages = 3;
+constexpr int kFHalfBytes = kTcMeshTile * 128;         // 32 meshes x 64 fp16
+constexpr int kFStageBytes = 2 * kFHalfBytes;          // hi + lo
+constexpr int kRStages = 3;
+constexpr int kRecBytes = kTcRecFloats * 4;
+constexpr int kRStageBytes = kTcSub * kRecBytes;
+constexpr int kFOff = kPBytes;
+constexpr int kROff = kFOff + kFStages * kFStageBytes;
+constexpr int kBarOff = kROff + kRStages * kRStageBytes;
+constexpr int kNumBars = 1 + 2 * kFStages + 4 + 2 * kRStages;
+constexpr int kSmemBytes = 1024 + kBarOff + kNumBars * 8 + 16;
+constexpr int kTmemCols = 256;                         // 2 buffers x 3 coordinates x 32 columns = 192
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
+static_assert(kRStageBytes % 16 == 0 && kROff % 16 == 0, "bulk copies need 16-byte alignment");
+
+struct KArgs {
+  int V, B, nb, NS, KW;
+  int tiles_total, tiles_per_cta;
+  const float* v_template;
+  const float* shapedirs;
+  const int* sk_off;
+  const float* sk_w;
+  const int* sk_cnt;
+  const float* rec;
+  float* out;
+  float* out_cam;
+  int vrows;                 // rows per coordinate plane of P
+};
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(ptx::smem_u32(dst)), "l"(src), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// kind::f16 instruction descriptor with fp16 A/B (format 0), fp32 accumulator.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmFh,
+                       const __grid_constant__ CUtensorMap tmFl, const KArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* p_full = reinterpret_cast<uint64_t*>(smem + kBarOff);
+  uint64_t* f_full = p_full + 1;
+  uint64_t* f_empty = f_full + kFStages;
+  uint64_t* tfull = f_empty + kFStages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* r_full = tempty + 2;
+  uint64_t* r_empty = r_full + kRStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + kRStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vtile = blockIdx.x;
+  const int t0 = blockIdx.y * a.tiles_per_cta;
+  const int t1 = min(a.tiles_total, t0 + a.tiles_per_cta);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmP);
+    ptx::prefetch_tmap(&tmFh);
+    ptx::prefetch_tmap(&tmFl);
+    ptx::mbar_init(p_full, 1);
+    for (int s = 0; s < kFStages; ++s) { ptx::mbar_init(&f_full[s], 1); ptx::mbar_init(&f_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], kEpiWarps); }
+    for (int s = 0; s < kRStages; ++s) { ptx::mbar_init(&r_full[s], 1); ptx::mbar_init(&r_empty[s], kEpiWarps / 2); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ P (once) + F ring
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(p_full, kPBytes);
+      for (int c = 0; c < 3; ++c)
+        for (int kb = 0; kb < 3; ++kb)
+          ptx::tma_load_2d(&tmP, p_full, smem + (c * 3 + kb) * kPTileBytes, kb * 64, c * a.vrows + vtile * 128);
+      int stage = 0; uint32_t phase = 0;
+      for (int t = t0; t < t1; ++t)
+        for (int kb = 0; kb < 3; ++kb) {
+          ptx::mbar_wait(&f_empty[stage], phase ^ 1, 100 + stage);
+          uint8_t* fs = smem + kFOff + stage * kFStageBytes;
+          ptx::mbar_arrive_expect_tx(&f_full[stage], kFStageBytes);
+          ptx::tma_load_2d(&tmFh, &f_full[stage], fs, kb * 64, t * kTcMeshTile);
+          ptx::tma_load_2d(&tmFl, &f_full[stage], fs + kFHalfBytes, kb * 64, t * kTcMeshTile);
+          if (++stage == kFStages) { stage = 0; phase ^= 1; }
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, kTcMeshTile);
+      ptx::mbar_wait(p_full, 0, 200);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int t = t0; t < t1; ++t, ++it) {
+        const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+        ptx::mbar_wait(&tempty[as], aphase ^ 1, 210 + as);
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < 3; ++kb) {
+          ptx::mbar_wait(&f_full[stage], phase, 220 + stage);
+          ptx::tc_fence_after();
+          const uint32_t fs = ptx::smem_u32(smem + kFOff + stage * kFStageBytes);
+          const uint64_t bh = ptx::make_kmajor_sw128_desc(fs);
+          const uint64_t bl = ptx::make_kmajor_sw128_desc(fs + kFHalfBytes);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const uint64_t ad = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + (c * 3 + kb) * kPTileBytes));
+            const uint32_t d_tmem = tmem_base + as * 96 + c * kTcMeshTile;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              ptx::umma_bf16(d_tmem, ad + 2 * k, bh + 2 * k, idesc, (kb | k) != 0);
+              ptx::umma_bf16(d_tmem, ad + 2 * k, bl + 2 * k, idesc, 1);
+            }
+          }
+          ptx::umma_commit(&f_empty[stage]);
+          if (++stage == kFStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull[as]);
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ per-mesh records: 16 meshes per bulk copy
+    if (lane == 0) {
+      int s = 0;
+      for (int t = t0; t < t1; ++t)
+        for (int hf = 0; hf < 2; ++hf, ++s) {
+          const int slot = s % kRStages; const uint32_t ph = (s / kRStages) & 1;
+          ptx::mbar_wait(&r_empty[slot], ph ^ 1, 300 + slot);
+          ptx::mbar_arrive_expect_tx(&r_full[slot], kRStageBytes);
+          bulk_load(smem + kROff + slot * kRStageBytes, a.rec + (size_t)(t * kTcMeshTile + hf * kTcSub) * kTcRecFloats,
+                    kRStageBytes, &r_full[slot]);
+        }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int quad = warp & 3;                        // TMEM lane quarter this warp may read
+    const int hf = (warp - kEpiWarp0) >> 2;           // which 16 meshes of the tile
+    const int v = vtile * 128 + quad * 32 + lane;
+    const bool valid = v < a.V;
+    const int vc = valid ? v : a.V - 1;
+    // per-vertex constants
+    const float vt0 = __ldg(a.v_template + vc * 3), vt1 = __ldg(a.v_template + vc * 3 + 1), vt2 = __ldg(a.v_template + vc * 3 + 2);
+    float S[3][10];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int l = 0; l < 10; ++l) S[c][l] = l < a.nb ? __ldg(a.shapedirs + ((size_t)vc * 3 + c) * a.NS + l) : 0.f;
+    const int cnt = __ldg(a.sk_cnt + vc);
+    int joff[kTcMaxKW]; float jw[kTcMaxKW];
+#pragma unroll
+    for (int k = 0; k < kTcMaxKW; ++k) {
+      const bool on = k < cnt;
+      joff[k] = on ? __ldg(a.sk_off + (size_t)k * a.V + vc) : 0;
+      jw[k] = on ? __ldg(a.sk_w + (size_t)k * a.V + vc) : 0.f;
+    }
+    const float inv_scale = 1.f / kTcPScale;
+    int it = 0;
+    for (int t = t0; t < t1; ++t, ++it) {
+      const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+      const int s = 2 * it + hf;
+      const int slot = s % kRStages; const uint32_t rph = (s / kRStages) & 1;
+      ptx::mbar_wait(&tfull[as], aphase, 400 + as);
+      ptx::tc_fence_after();
+      uint32_t dx[16], dy[16], dz[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 96 + hf * kTcSub;
+      tmem_ld_32x16(taddr, dx);
+      tmem_ld_32x16(taddr + kTcMeshTile, dy);
+      tmem_ld_32x16(taddr + 2 * kTcMeshTile, dz);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[as]);   // accumulator is in registers: MMA may refill it
+      ptx::mbar_wait(&r_full[slot], rph, 410 + slot);
+      const uint8_t* rbase = smem + kROff + slot * kRStageBytes;
+      const int mesh0 = t * kTcMeshTile + hf * kTcSub;
+#pragma unroll
+      for (int m = 0; m < kTcSub; ++m) {
+        const int b = mesh0 + m;
+        if (b >= a.B) break;                           // uniform across the CTA
+        const float* rec = reinterpret_cast<const float*>(rbase + m * kRecBytes);
+        // v_shaped (lbs.py:179) + pose offsets (:203)
+        const float4 b0 = *reinterpret_cast<const float4*>(rec + kTcRecBetas);
+        const float4 b1 = *reinterpret_cast<const float4*>(rec + kTcRecBetas + 4);
+        const float2 b2 = *reinterpret_cast<const float2*>(rec + kTcRecBetas + 8);
+        const float be[10] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
+        float x = vt0, y = vt1, z = vt2;
+#pragma unroll
+        for (int l = 0; l < 10; ++l) {
+          x = fmaf(S[0][l], be[l], x);
+          y = fmaf(S[1][l], be[l], y);
+          z = fmaf(S[2][l], be[l], z);
+        }
+        x = fmaf(__uint_as_float(dx[m]), inv_scale, x);
+        y = fmaf(__uint_as_float(dy[m]), inv_scale, y);
+        z = fmaf(__uint_as_float(dz[m]), inv_scale, z);
+        // T = sum_k w_k A_k (lbs.py:209-213)
+        float T[12];
+#pragma unroll
+        for (int e = 0; e < 12; ++e) T[e] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kTcMaxKW; ++k) {
+          if (k >= a.KW) break;                        // uniform
+          const float w = jw[k];
+          const float4* Aj = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(rec) + joff[k]);
+          const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+          T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+          T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+          T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+        }
+        const float4 c0 = *reinterpret_cast<const float4*>(rec + kTcRecCam);
+        const float4 c1 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 4);
+        const float4 c2 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 8);
+        const float4 tr = *reinterpret_cast<const float4*>(rec + kTcRecTransl);
+        // v = T [v_posed; 1] (lbs.py:215-220) + transl (body_models.py:980-982)
+        const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3]))) + tr.x;
+        const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7]))) + tr.y;
+        const float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11]))) + tr.z;
+        if (valid) {
+          float* o = a.out + ((size_t)b * a.V + v) * 3;
+          o[0] = ox; o[1] = oy; o[2] = oz;
+          if (a.out_cam) {       // transform_smpl (utils.py:237-239): R v + t about the origin; camR = c0.xyz c0.w c1.xy | c1.zw c2.x, t = c2.yzw
+            float* oc = a.out_cam + ((size_t)b * a.V + v) * 3;
+            oc[0] = fmaf(c0.x, ox, fmaf(c0.y, oy, c0.z * oz)) + c2.y;
+            oc[1] = fmaf(c0.w, ox, fmaf(c1.x, oy, c1.y * oz)) + c2.z;
+            oc[2] = fmaf(c1.z, ox, fmaf(c1.w, oy, c2.x * oz)) + c2.w;
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&r_empty[slot]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace
+
+int smplx_tc_create(const airpose_smplx_model_host* mh, const SmplxDev& d, SmplxTc* tc, std::vector<void*>* owned) {
+  tc->ok = false;
+  const int V = d.V, J = d.J;
+  if (J <= kTcBodyJoints || d.P != (J - 1) * 9 || getenv("AIRPOSE_SMPLX_GENERIC")) return 0;
+  // fold joints >= 22 onto their nearest body ancestor and merge the weights
+  std::vector<int> anc(J);
+  for (int j = 0; j < J; ++j) anc[j] = j < kTcBodyJoints ? j : anc[(int)mh->parents[j]];
+  std::vector<int> cnt(V, 0);
+  std::vector<std::vector<std::pair<int, float>>> rows(V);
+  int KW = 1;
+  for (int v = 0; v < V; ++v) {
+    for (int j = 0; j < J; ++j) {
+      const float w = mh->lbs_weights[(size_t)v * J + j];
+      if (w == 0.f) continue;
+      bool merged = false;
+      for (auto& e : rows[v])
+        if (e.first == anc[j]) { e.second += w; merged = true; break; }
+      if (!merged) rows[v].push_back({anc[j], w});
+    }
+    cnt[v] = (int)rows[v].size();
+    KW = std::max(KW, cnt[v]);
+  }
+  if (KW > kTcMaxKW) return 0;          // unusually dense skinning: the generic kernel handles it
+  std::vector<int> off((size_t)KW * V, 0);
+  std::vector<float> w((size_t)KW * V, 0.f);
+  for (int v = 0; v < V; ++v)
+    for (int k = 0; k < cnt[v]; ++k) { off[(size_t)k * V + v] = rows[v][k].first * 48; w[(size_t)k * V + v] = rows[v][k].second; }
+  // P[c][v][p] = fp16(posedirs[p][3v+c] * 2^10), p < 189; zero padded to 192 columns / vtiles*128 rows
+  const int vtiles = ceil_div(V, 128), vrows = vtiles * 128;
+  std::vector<__half> P((size_t)3 * vrows * kTcK, __float2half_rn(0.f));
+  for (int p = 0; p < 189; ++p) {
+    const float* src = mh->posedirs + (size_t)p * V * 3;
+    for (int v = 0; v < V; ++v)
+      for (int c = 0; c < 3; ++c) P[((size_t)c * vrows + v) * kTcK + p] = __float2half_rn(src[(size_t)v * 3 + c] * kTcPScale);
+  }
+  __half* dP; int* doff; float* dw; int* dcnt;
+  if (device_upload(&dP, P.data(), P.size())) return 1;
+  owned->push_back(dP);
+  if (device_upload(&doff, off.data(), off.size())) return 1;
+  owned->push_back(doff);
+  if (device_upload(&dw, w.data(), w.size())) return 1;
+  owned->push_back(dw);
+  if (device_upload(&dcnt, cnt.data(), cnt.size())) return 1;
+  owned->push_back(dcnt);
+  tc->P = dP; tc->sk_off = doff; tc->sk_w = dw; tc->sk_cnt = dcnt;
+  tc->KW = KW; tc->vtiles = vtiles;
+  if (make_tmap_tiled_bf16(&tc->tmP, dP, (int64_t)3 * vrows, kTcK, kTcK, 128, 64)) return 1;   // 2-byte elements: fp16 rides the bf16 map
+  tc->ok = true;
+  return 0;
+}
+
+// Mesh tiles per CTA: enough CTAs to fill the SMs, few enough that the 144 KB of P per CTA amortise.
+static int pick_tiles_per_cta(int vtiles, int tiles_total) {
+  const int sms = num_sms();
+  double best = 1e30; int best_s = 1;
+  for (int s = 1; s <= std::min(tiles_total, 32); ++s) {
+    const int per = ceil_div(tiles_total, s);
+    const int waves = ceil_div(vtiles * s, sms);
+    const double cost = waves * (1.5 + per);         // P load ~ 1.5 tile times
+    if (cost < best) { best = cost; best_s = s; }
+  }
+  return ceil_div(tiles_total, best_s);
+}
+
+int smplx_tc_forward(const SmplxDev& d, const SmplxTc& tc, const TcCall& c, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  CUtensorMap tmFh, tmFl;
+  if (make_tmap_tiled_bf16(&tmFh, c.fh, c.B, kTcK, kTcK, kTcMeshTile, 64)) return 1;
+  if (make_tmap_tiled_bf16(&tmFl, c.fl, c.B, kTcK, kTcK, kTcMeshTile, 64)) return 1;
+  KArgs a{};
+  a.V = d.V; a.B = c.B; a.nb = c.nb; a.NS = d.NS; a.KW = tc.KW;
+  a.tiles_total = ceil_div(c.B, kTcMeshTile);
+  a.tiles_per_cta = pick_tiles_per_cta(tc.vtiles, a.tiles_total);
+  a.v_template = d.v_template; a.shapedirs = d.shapedirs;
+  a.sk_off = tc.sk_off; a.sk_w = tc.sk_w; a.sk_cnt = tc.sk_cnt;
+  a.rec = c.rec; a.out = c.out; a.out_cam = c.out_cam;
+  a.vrows = tc.vtiles * 128;
+  dim3 grid(tc.vtiles, ceil_div(a.tiles_total, a.tiles_per_cta));
+  smplx_vertex_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace airpose
