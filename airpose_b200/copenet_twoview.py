@@ -71,7 +71,7 @@ class copenet_twoview(nn.Module):
             mo, cam = self.smplx.forward_camera(
                 betas=betas, body_pose=rotmat[:, 1:],
                 global_orient=None,                                       # identity (:283)
-                transl=torch.zeros(B, 3, device=dev), pose2rot=False,
+                transl=None, pose2rot=False,                              # the reference passes zeros (:284); None skips the add
                 root_R=rotmat[:, 0], root_t=trans,                        # transform_smpl (:287-292)
                 focal_length=self.focal_length, camera_center=intr[v][:, :2, 2])   # :307-317
             out.update({"pred_pose%d" % v: pose, "pred_betas%d" % v: betas, "pred_rotmat%d" % v: rotmat,

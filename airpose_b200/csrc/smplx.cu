@@ -529,7 +529,7 @@ extern "C" int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_arg
 
   if (use_tc) {
     TcCall tcall{};
-    tcall.B = B; tcall.nb = g->num_betas;
+    tcall.B = B; tcall.nb = g->num_betas; tcall.has_transl = g->transl != nullptr;
     tcall.rec = rec; tcall.fh = fh; tcall.fl = fl;
     tcall.out = g->out_vertices; tcall.out_cam = g->out_vertices_cam;
     if (smplx_tc_forward(d, h->tc, tcall, stream)) return 1;

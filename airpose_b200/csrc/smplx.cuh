@@ -51,7 +51,7 @@ struct SmplxTc {
 };
 
 struct TcCall {
-  int B, nb;
+  int B, nb, has_transl;
   const float* rec;            // [Bpad][292]
   const __half* fh;            // [B][192]
   const __half* fl;            // [B][192]

@@ -62,7 +62,7 @@ static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 static_assert(kRStageBytes % 16 == 0 && kROff % 16 == 0, "bulk copies need 16-byte alignment");
 
 struct KArgs {
-  int V, B, nb, NS, KW;
+  int V, B, nb, NS, KW, has_transl;
   int tiles_total, tiles_per_cta;
   const float* v_template;
   const float* shapedirs;
@@ -96,6 +96,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+template <bool kHasCam>
 __global__ void __launch_bounds__(kThreads, 1)
 smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmFh,
                        const __grid_constant__ CUtensorMap tmFl, const KArgs a) {
@@ -220,6 +221,7 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
       joff[k] = on ? __ldg(a.sk_off + (size_t)k * a.V + vc) : 0;
       jw[k] = on ? __ldg(a.sk_w + (size_t)k * a.V + vc) : 0.f;
     }
+    const int kw_warp = __reduce_max_sync(0xffffffffu, cnt);     // this warp's 32 vertices need at most this many joints
     const float inv_scale = 1.f / kTcPScale;
     int it = 0;
     for (int t = t0; t < t1; ++t, ++it) {
@@ -266,7 +268,7 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
         for (int e = 0; e < 12; ++e) T[e] = 0.f;
 #pragma unroll
         for (int k = 0; k < kTcMaxKW; ++k) {
-          if (k >= a.KW) break;                        // uniform
+          if (k >= kw_warp) break;                     // warp-uniform
           const float w = jw[k];
           const float4* Aj = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(rec) + joff[k]);
           const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
@@ -274,18 +276,21 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
           T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
           T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
         }
-        const float4 c0 = *reinterpret_cast<const float4*>(rec + kTcRecCam);
-        const float4 c1 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 4);
-        const float4 c2 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 8);
-        const float4 tr = *reinterpret_cast<const float4*>(rec + kTcRecTransl);
         // v = T [v_posed; 1] (lbs.py:215-220) + transl (body_models.py:980-982)
-        const float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3]))) + tr.x;
-        const float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7]))) + tr.y;
-        const float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11]))) + tr.z;
+        float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
+        float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
+        float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
+        if (a.has_transl) {
+          const float4 tr = *reinterpret_cast<const float4*>(rec + kTcRecTransl);
+          ox += tr.x; oy += tr.y; oz += tr.z;
+        }
         if (valid) {
           float* o = a.out + ((size_t)b * a.V + v) * 3;
           o[0] = ox; o[1] = oy; o[2] = oz;
-          if (a.out_cam) {       // transform_smpl (utils.py:237-239): R v + t about the origin; camR = c0.xyz c0.w c1.xy | c1.zw c2.x, t = c2.yzw
+          if (kHasCam) {         // transform_smpl (utils.py:237-239): R v + t about the origin; camR = c0.xyz c0.w c1.xy | c1.zw c2.x, t = c2.yzw
+            const float4 c0 = *reinterpret_cast<const float4*>(rec + kTcRecCam);
+            const float4 c1 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 4);
+            const float4 c2 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 8);
             float* oc = a.out_cam + ((size_t)b * a.V + v) * 3;
             oc[0] = fmaf(c0.x, ox, fmaf(c0.y, oy, c0.z * oz)) + c2.y;
             oc[1] = fmaf(c0.w, ox, fmaf(c1.x, oy, c1.y * oz)) + c2.z;
@@ -375,14 +380,15 @@ static int pick_tiles_per_cta(int vtiles, int tiles_total) {
 int smplx_tc_forward(const SmplxDev& d, const SmplxTc& tc, const TcCall& c, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
   CUtensorMap tmFh, tmFl;
   if (make_tmap_tiled_bf16(&tmFh, c.fh, c.B, kTcK, kTcK, kTcMeshTile, 64)) return 1;
   if (make_tmap_tiled_bf16(&tmFl, c.fl, c.B, kTcK, kTcK, kTcMeshTile, 64)) return 1;
   KArgs a{};
-  a.V = d.V; a.B = c.B; a.nb = c.nb; a.NS = d.NS; a.KW = tc.KW;
+  a.V = d.V; a.B = c.B; a.nb = c.nb; a.NS = d.NS; a.KW = tc.KW; a.has_transl = c.has_transl;
   a.tiles_total = ceil_div(c.B, kTcMeshTile);
   a.tiles_per_cta = pick_tiles_per_cta(tc.vtiles, a.tiles_total);
   a.v_template = d.v_template; a.shapedirs = d.shapedirs;
@@ -390,7 +396,8 @@ int smplx_tc_forward(const SmplxDev& d, const SmplxTc& tc, const TcCall& c, cuda
   a.rec = c.rec; a.out = c.out; a.out_cam = c.out_cam;
   a.vrows = tc.vtiles * 128;
   dim3 grid(tc.vtiles, ceil_div(a.tiles_total, a.tiles_per_cta));
-  smplx_vertex_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
+  if (c.out_cam) smplx_vertex_tc_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
+  else smplx_vertex_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
   AP_LAUNCH_CHECK();
   return 0;
 }
