@@ -20,10 +20,14 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --
     --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
 echo "ncu launches exit $?"
 # full capture: trunk GEMM kernels (a spread of layers) and the SMPL-X vertex kernel
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16_kernel -s 60 -c 56 \
+timeout 600 ncu --set full --clock-control none -k regex:gemm_ -s 60 -c 56 \
     -o $OUT/prof_trunk python tools/run_once.py trunk 32 2 > $OUT/ncu_trunk.log 2>&1
 echo "ncu trunk exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:smplx_ -s 3 -c 3 \
     -o $OUT/prof_lbs python tools/run_once.py lbs 8192 2 > $OUT/ncu_lbs.log 2>&1
 echo "ncu lbs exit $?"
+for f in trunk lbs; do ncu -i $OUT/prof_$f.ncu-rep --page raw --csv > $OUT/prof_${f}_raw.csv 2>/dev/null; done
+ncu -i $OUT/prof_lbs.ncu-rep --page source --csv > $OUT/prof_lbs_source.csv 2>/dev/null
+# keep gpurun_out under the 64 MiB return limit
+find $OUT -name "*.ncu-rep" -size +24M -delete
 ls -la $OUT
