@@ -85,6 +85,19 @@ class ConvArgs(C.Structure):
                 ("relu", C.c_int32), ("out", C.c_void_p)]
 
 
+class LossArgs(C.Structure):
+    _fields_ = ([("batch", C.c_int32), ("num_verts", C.c_int32), ("num_joints", C.c_int32),
+                 ("trans0", C.c_void_p), ("trans1", C.c_void_p), ("trans_stride", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("rotmat0", "rotmat1", "betas0", "betas1", "verts0", "verts1", "joints0", "joints1",
+                                           "j2d0", "j2d1", "gt_pose_rotmat", "gt_trans0", "gt_trans1", "gt_orient0",
+                                           "gt_orient1", "gt_verts", "gt_joints", "gt_j2d0", "gt_j2d1")] +
+                [(n, C.c_float) for n in ("w_shape", "w_kp2d", "w_kp3d", "w_limbs3d", "w_limbstheta", "w_trans",
+                                          "w_rootrot", "w_pose", "w_beta")] +
+                [("out", C.c_void_p)] +
+                [(n, C.c_void_p) for n in ("g_verts0", "g_verts1", "g_joints0", "g_joints1", "g_j2d0", "g_j2d1",
+                                           "g_rotmat0", "g_rotmat1", "g_betas0", "g_betas1", "g_trans0", "g_trans1")])
+
+
 # name -> (restype, argtypes); every symbol include/airpose_b200.h declares
 SYMBOLS = {
     "airpose_last_error": (C.c_char_p, []),
@@ -103,6 +116,7 @@ SYMBOLS = {
     "airpose_backbone_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "airpose_backbone_fwd_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "airpose_ief_fwd": (C.c_int, [C.c_void_p, C.POINTER(IefArgs), C.c_void_p]),
+    "airpose_twoview_loss": (C.c_int, [C.POINTER(LossArgs), C.c_void_p]),
     "airpose_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "airpose_conv_bf16": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "airpose_backbone_stem": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

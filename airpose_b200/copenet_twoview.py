@@ -8,16 +8,23 @@ orientation, rigid transform about the origin, perspective projection.  SMPL-X,
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 
 import torch
 import torch.nn as nn
 
-from . import model_copenet
+from . import _lib, model_copenet
 from .smplx import SMPLX, rot6d_to_rotmat
 
 FOCAL_LENGTH = [1475, 1475]          # copenet/src/copenet/constants.py:7
 TRANS_SCALE = 0.05                   # copenet_twoview.py:199-203
+# default loss weights, copenet_twoview.py:655-677
+LOSS_WEIGHTS = {"shape_loss_weight": 50.0, "keypoint2d_loss_weight": 0.002, "keypoint3d_loss_weight": 1.0,
+                "limbs3d_loss_weight": 3.0, "limbstheta_loss_weight": 1.0, "trans_loss_weight": 10.0,
+                "rootrot_loss_weight": 1.0, "pose_loss_weight": 50.0, "beta_loss_weight": 1.0}
+LOSS_NAMES = ("loss", "loss_regr_trans", "loss_keypoints", "loss_keypoints_3d", "loss_regr_shape", "loss_rootrot",
+              "loss_regr_pose", "loss_regul_betas")           # order of the reference's `losses` dict (:152-159)
 
 
 class copenet_twoview(nn.Module):
@@ -81,3 +88,83 @@ class copenet_twoview(nn.Module):
                         "pred_joints_2d_cam%d" % v: cam["joints_2d"]})
         mark("smplx")
         return out
+
+    def _hp(self, name):
+        return float(getattr(self.hparams, name, LOSS_WEIGHTS[name]))
+
+    @torch.no_grad()
+    def get_loss(self, input_batch, pred_smpltrans0, pred_smpltrans1, pred_rotmat0, pred_rotmat1, pred_betas0,
+                 pred_betas1, pred_output_cam0, pred_output_cam1, pred_joints_2d_cam0, pred_joints_2d_cam1,
+                 with_grads=False):
+        """copenet_twoview.get_loss (copenet_twoview.py:83-161), same argument list.  Returns
+        ``(loss, losses)`` where ``loss`` is a 0-d device tensor and ``losses`` a dict of 0-d device
+        tensors (views of ONE 8-float buffer: read them with a single ``.cpu()`` instead of the
+        reference's eight ``.item()`` syncs).  ``with_grads=True`` also returns, as a third value, the
+        gradient of ``loss`` with respect to every prediction (the backward of this function)."""
+        dev = pred_betas0.device
+        if dev.type != "cuda":
+            raise _lib.AirposeError("get_loss runs on CUDA only; there is no CPU path")
+        lib = _lib.load()
+        f = lambda t: t.float().contiguous()
+        B = pred_betas0.shape[0]
+        v0, v1 = f(pred_output_cam0.vertices), f(pred_output_cam1.vertices)
+        j0, j1 = f(pred_output_cam0.joints), f(pred_output_cam1.joints)
+        keep = [v0, v1, j0, j1]
+        a = _lib.LossArgs()
+        a.batch, a.num_verts, a.num_joints = B, v0.shape[1], j0.shape[1]
+        if pred_smpltrans0.stride(-1) != 1 or pred_smpltrans0.stride(0) != pred_smpltrans1.stride(0):
+            pred_smpltrans0, pred_smpltrans1 = f(pred_smpltrans0), f(pred_smpltrans1)
+        keep += [pred_smpltrans0, pred_smpltrans1]
+        a.trans0, a.trans1, a.trans_stride = pred_smpltrans0.data_ptr(), pred_smpltrans1.data_ptr(), pred_smpltrans0.stride(0)
+        names = {"rotmat0": pred_rotmat0, "rotmat1": pred_rotmat1, "betas0": pred_betas0, "betas1": pred_betas1,
+                 "j2d0": pred_joints_2d_cam0, "j2d1": pred_joints_2d_cam1,
+                 "gt_pose_rotmat": input_batch["smplpose_rotmat"], "gt_trans0": input_batch["smpltrans_rel0"],
+                 "gt_trans1": input_batch["smpltrans_rel1"], "gt_orient0": input_batch["smplorient_rel0"],
+                 "gt_orient1": input_batch["smplorient_rel1"], "gt_verts": input_batch["smpl_vertices"],
+                 "gt_joints": input_batch["smpl_joints"], "gt_j2d0": input_batch["smpl_joints_2d0"],
+                 "gt_j2d1": input_batch["smpl_joints_2d1"]}
+        for n, t in names.items():
+            t = f(t.to(dev))
+            keep.append(t)
+            setattr(a, n, t.data_ptr())
+        a.verts0, a.verts1, a.joints0, a.joints1 = v0.data_ptr(), v1.data_ptr(), j0.data_ptr(), j1.data_ptr()
+        a.w_shape, a.w_kp2d, a.w_kp3d = self._hp("shape_loss_weight"), self._hp("keypoint2d_loss_weight"), self._hp("keypoint3d_loss_weight")
+        a.w_limbs3d, a.w_limbstheta, a.w_trans = self._hp("limbs3d_loss_weight"), self._hp("limbstheta_loss_weight"), self._hp("trans_loss_weight")
+        a.w_rootrot, a.w_pose, a.w_beta = self._hp("rootrot_loss_weight"), self._hp("pose_loss_weight"), self._hp("beta_loss_weight")
+        out = torch.empty(8, device=dev, dtype=torch.float32)
+        a.out = out.data_ptr()
+        grads = None
+        if with_grads:
+            grads = {"vertices0": torch.empty_like(v0), "vertices1": torch.empty_like(v1), "joints0": torch.empty_like(j0),
+                     "joints1": torch.empty_like(j1), "joints_2d0": torch.empty(B, j0.shape[1], 2, device=dev),
+                     "joints_2d1": torch.empty(B, j0.shape[1], 2, device=dev), "rotmat0": torch.empty(B, 22, 3, 3, device=dev),
+                     "rotmat1": torch.empty(B, 22, 3, 3, device=dev), "betas0": torch.empty(B, 10, device=dev),
+                     "betas1": torch.empty(B, 10, device=dev), "smpltrans0": torch.empty(B, 3, device=dev),
+                     "smpltrans1": torch.empty(B, 3, device=dev)}
+            for field, key in (("g_verts0", "vertices0"), ("g_verts1", "vertices1"), ("g_joints0", "joints0"),
+                               ("g_joints1", "joints1"), ("g_j2d0", "joints_2d0"), ("g_j2d1", "joints_2d1"),
+                               ("g_rotmat0", "rotmat0"), ("g_rotmat1", "rotmat1"), ("g_betas0", "betas0"),
+                               ("g_betas1", "betas1"), ("g_trans0", "smpltrans0"), ("g_trans1", "smpltrans1")):
+                setattr(a, field, grads[key].data_ptr())
+        with torch.cuda.device(dev):
+            _lib.check(lib.airpose_twoview_loss(C.byref(a), _lib.current_stream()), "airpose_twoview_loss")
+        del keep
+        losses = {n: out[i] for i, n in enumerate(LOSS_NAMES)}
+        return (out[0], losses, grads) if with_grads else (out[0], losses)
+
+    @torch.no_grad()
+    def fwd_pass_and_loss(self, input_batch, is_test=False, is_val=False):
+        """copenet_twoview.fwd_pass_and_loss (copenet_twoview.py:164-374): forward + get_loss + the
+        reference's output dict.  (The backward half of the training step is not built yet: DESIGN.md.)"""
+        out = self.fwd_pass(input_batch)
+        if is_test:
+            loss, losses = None, None
+        else:
+            loss, losses = self.get_loss(input_batch, out["pred_smpltrans0"], out["pred_smpltrans1"], out["pred_rotmat0"],
+                                         out["pred_rotmat1"], out["pred_betas0"], out["pred_betas1"],
+                                         out["pred_output_cam0"], out["pred_output_cam1"],
+                                         out["pred_joints_2d_cam0"], out["pred_joints_2d_cam1"])
+        output = {"pred_vertices_cam0": out["pred_vertices_cam0"], "pred_vertices_cam1": out["pred_vertices_cam1"],   # :362-372
+                  "pred_smpltrans0": out["pred_smpltrans0"], "pred_smpltrans1": out["pred_smpltrans1"],
+                  "in_smpltrans0": out["in_smpltrans0"], "in_smpltrans1": out["in_smpltrans1"]}
+        return output, losses, loss

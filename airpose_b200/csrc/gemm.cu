@@ -346,7 +346,32 @@ bool use_pdl() {
   return on;
 }
 
-int pick_block_n(int M, int N) {
+bool use_stream_k() {
+  static const bool on = getenv("AIRPOSE_GEMM_V1") == nullptr;
+  return on;
+}
+
+// Which kernel runs a [M,N,K] problem with a bf16 TMA epilogue (measured per layer on B200,
+// profiles/r01d_layers_*.txt): the stream-K kernel (gemm_sk.cu, 128x256 tiles cut at k-block granularity)
+// wins where tiles are long in K and few enough to quantise badly on 148 SMs -- the 3x3 convs of
+// layer3/layer4 -- and loses 5-15 % elsewhere to its per-cut-tile fix-up, so everything else keeps the
+// round-robin kernel (gemm_tma.cu).  AIRPOSE_GEMM_V1=1 / AIRPOSE_GEMM_SK=1 force one or the other.
+bool prefers_stream_k(int M, int N, int K) {
+  static const bool force_sk = getenv("AIRPOSE_GEMM_SK") != nullptr;
+  if (!use_stream_k()) return false;
+  if (force_sk) return true;
+  static const int min_kb = getenv("AIRPOSE_SK_MINKB") ? atoi(getenv("AIRPOSE_SK_MINKB")) : 36;
+  const int bn = N % 256 == 0 ? 256 : (N > 64 ? 128 : 64);
+  const int tiles = ceil_div(M, kBlockM) * ceil_div(N, bn);
+  return ceil_div(K, 64) >= min_kb && tiles < 8 * num_sms() && tiles % num_sms() != 0;
+}
+
+int pick_block_n(int M, int N, int K) {
+  if (prefers_stream_k(M, N, K)) {   // stream-K removes the wave-quantisation penalty of wide tiles
+    if (N % 256 == 0) return 256;
+    if (N > 64) return 128;
+    return 64;
+  }
   const int tiles_m = ceil_div(M, kBlockM);
   if (N % 256 == 0 && (int64_t)tiles_m * (N / 256) >= 2 * num_sms()) return 256;
   if (N > 64) return 128;
@@ -368,7 +393,7 @@ static int launch_bn(const GemmLaunch& L, const KParams& kp, cudaStream_t stream
 }
 
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
-  if (L.tma_epi) return launch_gemm_tma(L, stream);
+  if (L.tma_epi) return (!L.stem && prefers_stream_k(L.M, L.N, L.K)) ? launch_gemm_sk(L, stream) : launch_gemm_tma(L, stream);
   AP_REQUIRE(L.M > 0 && L.N > 0 && L.K > 0, "launch_gemm: empty problem %dx%dx%d", L.M, L.N, L.K);
   AP_REQUIRE(L.N % 8 == 0, "launch_gemm: N=%d must be a multiple of 8", L.N);
   const Epilogue& e = L.epi;
@@ -408,7 +433,7 @@ extern "C" int airpose_gemm_bf16(const airpose_gemm_args* g, void* stream) {
   AP_REQUIRE(g && g->A && g->B, "airpose_gemm_bf16: null argument");
   GemmLaunch L{};
   L.M = g->M; L.N = g->N; L.K = g->K;
-  L.block_n = pick_block_n(g->M, g->N);
+  L.block_n = pick_block_n(g->M, g->N, g->K);
   if (make_tmap_tiled_bf16(&L.tmA, g->A, g->M, g->K, g->lda, kBlockM, kBlockK)) return 1;
   if (make_tmap_tiled_bf16(&L.tmB, g->B, g->N, g->K, g->ldb, L.block_n, kBlockK)) return 1;
   L.epi.scale = g->scale; L.epi.shift = g->shift;
@@ -429,7 +454,7 @@ extern "C" int airpose_conv_bf16(const airpose_conv_args* c, void* stream) {
   g.Ho = (c->H + 2 * c->pad - c->ksize) / c->stride + 1;
   g.Wo = (c->W + 2 * c->pad - c->ksize) / c->stride + 1;
   L.M = c->n * g.Ho * g.Wo; L.N = c->Cout; L.K = c->ksize * c->ksize * c->Cin;
-  L.block_n = pick_block_n(L.M, L.N);
+  L.block_n = pick_block_n(L.M, L.N, L.K);
   L.im2col = 1;
   if (make_tmap_im2col_bf16(&L.tmA, c->x, g, kBlockK, kBlockM)) return 1;
   if (make_tmap_tiled_bf16(&L.tmB, c->w, L.N, L.K, L.K, L.block_n, kBlockK)) return 1;

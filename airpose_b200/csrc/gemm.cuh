@@ -50,6 +50,10 @@ bool tma_epilogue_eligible(const GemmLaunch& L);
 // Builds tmD / tmR from epi.out_bf16 / epi.residual and sets tma_epi (call after epi is filled in).
 int enable_tma_epilogue(GemmLaunch* L);
 int launch_gemm_tma(const GemmLaunch& L, cudaStream_t stream);
+// Second-generation kernel (gemm_sk.cu): stream-K split, two epilogue warpgroups, resident weights.
+// Chosen per problem by prefers_stream_k(); AIRPOSE_GEMM_V1=1 / AIRPOSE_GEMM_SK=1 force one kernel for A/B runs.
+int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream);
+bool use_stream_k();
 
 // Tensor maps (cuTensorMapEncode* resolved through cudaGetDriverEntryPoint; no libcuda link).
 int make_tmap_tiled_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems,
@@ -57,7 +61,8 @@ int make_tmap_tiled_bf16(CUtensorMap* out, const void* base, int64_t rows, int64
 int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, const ConvGeom& g, int channels_per_pixel,
                           int pixels_per_column);
 
-int pick_block_n(int M, int N);
+int pick_block_n(int M, int N, int K);
+bool prefers_stream_k(int M, int N, int K);
 bool use_tma_epilogue();   // off with AIRPOSE_NO_TMA_EPI=1 (A/B runs)
 bool use_pdl();            // off with AIRPOSE_NO_PDL=1
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream);

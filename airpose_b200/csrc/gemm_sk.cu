@@ -1,0 +1,539 @@
+// Stream-K tcgen05 GEMM / implicit conv with a TMA epilogue -- second generation of the kernel every
+// conv of the ResNet-50 trunk runs on (copenet/src/copenet/models/model_copenet.py:27-47,161-176).
+//
+// What the ncu captures of the first TMA-epilogue kernel (gemm_tma.cu; profiles/r01c_*) showed and
+// what changes here:
+//   * K-heavy layers (3x3 convs, layer3/4) moved 7-10 TB/s through the L2->SM crossbar with
+//     128x128 tiles and lost up to a third of a wave to tile quantisation (196 or 392 tiles on 148
+//     SMs).  Work is now split STREAM-K: the tiles x k-blocks iteration space is cut into one
+//     contiguous range per CTA, so every SM gets the same number of k-blocks whatever the tile count
+//     and 128x256 tiles (half the operand traffic per flop) can be used whenever Cout allows.  A tile
+//     cut by a range boundary is finished by the CTA that owns its first k-block; the CTAs holding the
+//     rest add their fp32 partial accumulators through an L2-resident workspace (at most one partial
+//     per CTA, written at the START of that CTA's range, consumed at the END of the owner's range, so
+//     nobody waits in practice).
+//   * memory-bound layers (1x1 convs of layer1/2 with the residual) were latency-bound in a 4-warp
+//     epilogue with a 2-chunk residual ring: there are now two epilogue warpgroups working on
+//     alternate 64-column chunks, the shared-memory partition is chosen per launch (deep residual
+//     ring when K is short, deep operand ring when K is long), and weights that fit stay RESIDENT in
+//     shared memory for the whole launch instead of being re-fetched per tile.
+//   * shared memory is addressed through the shared window (LDS/STS), not generic LD/ST.
+//
+// CTA = 11 warps, one CTA per SM:
+//   warp 0    A/B TMA producer     warp 1   MMA issuer (TMEM double-buffered)    warp 2   residual TMA producer
+//   warps 3-6 / 7-10   epilogue groups 0 / 1: tcgen05.ld -> scale/shift (+residual) -> relu -> bf16 ->
+//                      swizzled smem -> TMA store; chunk q of the launch belongs to group q & 1.
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace airpose {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kUmmaK = 16;
+constexpr int kEpiWarp0 = 3;
+constexpr int kEpiGroups = 2;
+constexpr int kGroupThreads = 128;
+constexpr int kThreads = 32 * (kEpiWarp0 + 4 * kEpiGroups);     // 352
+constexpr int kChunkN = 64;                       // epilogue chunk: 128 rows x 64 bf16 = one 128B-swizzle box
+constexpr int kChunkBytes = kBlockM * kChunkN * 2;
+constexpr int kMaxStages = 8;
+constexpr int kMaxRes = 6;
+constexpr int kBarBytes = 512;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kMaxGrid = 512;                     // flag slots
+
+struct KP {
+  int M, N, K;
+  int num_kb, tiles_m, tiles_n;
+  int im2col, cblks, ksize, stride, pad, Wo, HoWo;
+  int stem, stem_img_rows, stem_img_stride;
+  int stem_tap_off[8];
+  int has_res, relu;
+  int stages, res_bufs, b_res;      // shared-memory partition of this launch
+  int split;                        // 1: stream-K (ranges of k-blocks)  0: whole tiles, round-robin over the CTAs
+  const float* scale;
+  const float* shift;
+  float* ws;                        // [grid][128 x BN] fp32 partial accumulators
+  uint32_t* flags;                  // [grid][2]  == epoch once that CTA's partial (per epilogue group) is in ws
+  uint32_t epoch;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// explicit shared-window accesses (the dynamic smem base is realigned by hand, which hides the
+// address space from the compiler)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One contiguous piece of a CTA's range: k-blocks [kb0, kb1) of `tile`.
+struct Seg { int tile, kb0, kb1; };
+struct SegIter {
+  int u, u1, num_kb, step;          // step == 0: stream-K range [u, u1) of k-block units; else tiles u, u+step, ... < u1
+  __device__ SegIter(int cta, int grid, int units, int nkb, int split)
+      : u(split ? (int)((int64_t)cta * units / grid) : cta), u1(split ? (int)((int64_t)(cta + 1) * units / grid) : units / nkb),
+        num_kb(nkb), step(split ? 0 : grid) {}
+  __device__ bool next(Seg& s) {
+    if (u >= u1) return false;
+    if (step) {
+      s.tile = u; s.kb0 = 0; s.kb1 = num_kb;
+      u += step;
+      return true;
+    }
+    s.tile = u / num_kb;
+    s.kb0 = u - s.tile * num_kb;
+    const int len = min(num_kb - s.kb0, u1 - u);
+    s.kb1 = s.kb0 + len;
+    u += len;
+    return true;
+  }
+};
+
+template <int BN, int BK>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const KP p) {
+  constexpr int kABytes = kBlockM * BK * 2;
+  constexpr int kBBytes = BN * BK * 2;
+  constexpr int kTmemCols = 2 * BN;
+  constexpr int kChunks = BN / kChunkN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
+  const uint32_t smem_base = ptx::smem_u32(smem);
+
+  const int stage_bytes = p.b_res ? kABytes : kABytes + kBBytes;
+  const int ring_bytes = p.stages * stage_bytes;
+  const int bres_off = ring_bytes;
+  const int out_off = bres_off + (p.b_res ? p.num_kb * kBBytes : 0);
+  const int res_off = out_off + kEpiGroups * kChunkBytes;
+  const int bar_off = res_off + p.res_bufs * kChunkBytes;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + bar_off);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* rfull_bar = tempty_bar + 2;
+  uint64_t* rempty_bar = rfull_bar + kMaxRes;
+  uint64_t* bfull_bar = rempty_bar + kMaxRes;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int units = p.tiles_m * p.tiles_n * p.num_kb;
+  const int cta = blockIdx.x, grid = gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmD);
+    if (p.has_res) ptx::prefetch_tmap(&tmR);
+    for (int s = 0; s < kMaxStages; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull_bar[s], 1); ptx::mbar_init(&tempty_bar[s], 4 * kEpiGroups); }
+    for (int s = 0; s < kMaxRes; ++s) { ptx::mbar_init(&rfull_bar[s], 1); ptx::mbar_init(&rempty_bar[s], 4); }
+    ptx::mbar_init(bfull_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Everything above overlapped the previous kernel; its output (our A operand / residual) and the
+  // stream-K workspace are ours only after this point.
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ A/B TMA producer
+    if (lane == 0) {
+      if (p.b_res) {                                   // the whole weight matrix, once
+        ptx::mbar_arrive_expect_tx(bfull_bar, p.num_kb * kBBytes);
+        for (int kb = 0; kb < p.num_kb; ++kb) ptx::tma_load_2d(&tmB, bfull_bar, smem + bres_off + kb * kBBytes, kb * BK, 0);
+      }
+      int stage = 0; uint32_t phase = 0;
+      SegIter it(cta, grid, units, p.num_kb, p.split);
+      Seg s;
+      while (it.next(s)) {
+        const int m_blk = s.tile / p.tiles_n, n_blk = s.tile - m_blk * p.tiles_n;
+        const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
+        int cw = 0, ch = 0, cn = 0;
+        if (p.im2col) {
+          cn = m0 / p.HoWo;
+          const int rem = m0 - cn * p.HoWo;
+          const int po = rem / p.Wo, qo = rem - po * p.Wo;
+          cw = qo * p.stride - p.pad;
+          ch = po * p.stride - p.pad;
+        }
+        int stem_row = 0;
+        if (BK == 32) {                                // stem: tiles never straddle images (12544 = 98 * 128)
+          const int img = m0 / p.stem_img_rows;
+          stem_row = img * p.stem_img_stride + (m0 - img * p.stem_img_rows);
+        }
+        for (int kb = s.kb0; kb < s.kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+          uint8_t* sa = smem + stage * stage_bytes;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+          if (BK == 32) {
+            ptx::tma_load_2d(&tmA, &full_bar[stage], sa, 0, stem_row + p.stem_tap_off[kb]);
+          } else if (p.im2col) {
+            const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
+            const int r = tap / p.ksize, sx = tap - r * p.ksize;
+            ptx::tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, cw, ch, cn, (uint16_t)sx, (uint16_t)r);
+          } else {
+            ptx::tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
+          }
+          if (!p.b_res) ptx::tma_load_2d(&tmB, &full_bar[stage], sa + kABytes, kb * BK, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BN);
+      if (p.b_res) ptx::mbar_wait(bfull_bar, 0, 250);
+      int stage = 0; uint32_t phase = 0;
+      int n = 0;
+      SegIter it(cta, grid, units, p.num_kb, p.split);
+      Seg s;
+      while (it.next(s)) {
+        const int as = n & 1; const uint32_t aphase = (n >> 1) & 1;
+        ++n;
+        ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, 200 + as);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = s.kb0; kb < s.kb1; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase, 300 + stage);
+          ptx::tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = p.b_res ? smem_base + bres_off + kb * kBBytes : sa + kABytes;
+          const uint64_t adesc = ptx::make_kmajor_desc(sa, BK * 2);
+          const uint64_t bdesc = ptx::make_kmajor_desc(sb, BK * 2);
+#pragma unroll
+          for (int k = 0; k < BK / kUmmaK; ++k)
+            ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != s.kb0 || k != 0) ? 1u : 0u);
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ residual TMA producer
+    if (lane == 0 && p.has_res) {
+      int rq = 0;
+      SegIter it(cta, grid, units, p.num_kb, p.split);
+      Seg s;
+      while (it.next(s)) {
+        if (s.kb0 != 0) continue;                      // a partial handed to the tile's owner: no epilogue here
+        const int m_blk = s.tile / p.tiles_n, n_blk = s.tile - m_blk * p.tiles_n;
+        const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
+        const int nchunks = min(kChunks, (p.N - n0) / kChunkN);
+        for (int c = 0; c < nchunks; ++c, ++rq) {
+          const int rs = rq % p.res_bufs; const uint32_t rphase = (rq / p.res_bufs) & 1;
+          ptx::mbar_wait(&rempty_bar[rs], rphase ^ 1, 500 + rs);
+          ptx::mbar_arrive_expect_tx(&rfull_bar[rs], kChunkBytes);
+          ptx::tma_load_2d(&tmR, &rfull_bar[rs], smem + res_off + rs * kChunkBytes, n0 + c * kChunkN, m0);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue groups
+    const int g = (warp - kEpiWarp0) >> 2;           // epilogue group
+    const int quad = warp & 3;                       // TMEM lane quarter this warp may read
+    const int row = quad * 32 + lane;                // row of the tile == TMEM lane
+    const bool elected = ((warp - kEpiWarp0) & 3) == 0 && lane == 0;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t ob = smem_base + out_off + g * kChunkBytes;
+    const uint32_t orow = ob + row * 128;
+    const int bar_id = 1 + g;
+    float4* ws_mine = reinterpret_cast<float4*>(p.ws) + (size_t)cta * (kBlockM * BN / 4);
+    int n = 0, q = 0, rq = 0;
+    SegIter it(cta, grid, units, p.num_kb, p.split);
+    Seg s;
+    while (it.next(s)) {
+      const int as = n & 1; const uint32_t aphase = (n >> 1) & 1;
+      ++n;
+      const int m_blk = s.tile / p.tiles_n, n_blk = s.tile - m_blk * p.tiles_n;
+      const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
+      const int nchunks = min(kChunks, (p.N - n0) / kChunkN);
+      const bool contributor = s.kb0 != 0;
+      const bool gather = !contributor && s.kb1 < p.num_kb;     // owner of a tile other CTAs finish
+      ptx::mbar_wait(&tfull_bar[as], aphase, 400 + as);
+      ptx::tc_fence_after();
+      int mine_left = 0;
+      for (int c = 0; c < nchunks; ++c) mine_left += (((q + c) & 1) == g);
+      if (mine_left == 0) {                          // nothing of this accumulator is ours: release it
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+      }
+      if (gather) {                                  // wait for every CTA that holds the rest of this tile
+        int need = p.num_kb - s.kb1, cc = cta + 1;
+        while (need > 0) {
+          const int a0 = (int)((int64_t)cc * units / grid), a1 = (int)((int64_t)(cc + 1) * units / grid);
+          if (a1 > a0) {
+            uint32_t spins = 0;
+            while (ld_acquire(p.flags + 2 * cc) != p.epoch || ld_acquire(p.flags + 2 * cc + 1) != p.epoch) {
+              if (++spins > (1u << 22)) {
+                printf("airpose: stream-K flag timeout cta=%d waits for %d\n", cta, cc);
+                __trap();
+              }
+            }
+            need -= min(a1 - a0, need);
+          }
+          ++cc;
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        if (((q + c) & 1) != g) continue;
+        uint32_t r[64];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + c * kChunkN;
+        ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        ptx::tmem_ld_wait();
+        if (--mine_left == 0) {                      // our part of the accumulator is in registers
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+        }
+        if (contributor) {                           // fp32 partial -> workspace (coalesced: 16 B x 32 lanes)
+          float4* dst = ws_mine + (size_t)c * 16 * kBlockM + row;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            __stcg(dst + j * kBlockM, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+          continue;
+        }
+        float v[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+        if (gather) {
+          int need = p.num_kb - s.kb1, cc = cta + 1;
+          while (need > 0) {
+            const int a0 = (int)((int64_t)cc * units / grid), a1 = (int)((int64_t)(cc + 1) * units / grid);
+            if (a1 > a0) {
+              const float4* src = reinterpret_cast<const float4*>(p.ws) + (size_t)cc * (kBlockM * BN / 4) +
+                                  (size_t)c * 16 * kBlockM + row;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 t = __ldcg(src + j * kBlockM);
+                v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+              }
+              need -= min(a1 - a0, need);
+            }
+            ++cc;
+          }
+        }
+        {
+          const int nb = n0 + c * kChunkN;
+          const float4* sc4 = reinterpret_cast<const float4*>(p.scale + nb);
+          const float4* sh4 = reinterpret_cast<const float4*>(p.shift + nb);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 s4 = p.scale ? __ldg(sc4 + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 h4 = p.shift ? __ldg(sh4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * j + 0] = fmaf(v[4 * j + 0], s4.x, h4.x);
+            v[4 * j + 1] = fmaf(v[4 * j + 1], s4.y, h4.y);
+            v[4 * j + 2] = fmaf(v[4 * j + 2], s4.z, h4.z);
+            v[4 * j + 3] = fmaf(v[4 * j + 3], s4.w, h4.w);
+          }
+        }
+        if (p.has_res) {
+          // chunks of owner segments are numbered rq, rq+1, ... in the producer's order
+          const int rc = rq + c;
+          const int rs = rc % p.res_bufs; const uint32_t rphase = (rc / p.res_bufs) & 1;
+          ptx::mbar_wait(&rfull_bar[rs], rphase, 600 + rs);
+          const uint32_t rb = smem_base + res_off + rs * kChunkBytes + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 w4 = lds128(rb + (((uint32_t)j ^ swz) << 4));
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              v[j * 8 + 2 * h] += __uint_as_float(w[h] << 16);
+              v[j * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xFFFF0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&rempty_bar[rs]);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        // the group's staging buffer is free once its previous store has been read out of smem
+        if (elected) ptx::tma_store_wait_read<0>();
+        ptx::named_bar_sync(bar_id, kGroupThreads);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 o;
+          o.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]); o.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+          o.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]); o.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+          sts128(orow + (((uint32_t)j ^ swz) << 4), o);
+        }
+        ptx::fence_proxy_async();
+        ptx::named_bar_sync(bar_id, kGroupThreads);
+        if (elected) {
+          ptx::tma_store_2d(&tmD, smem + out_off + g * kChunkBytes, n0 + c * kChunkN, m0);
+          ptx::tma_store_commit();
+        }
+      }
+      if (contributor) {                             // publish this group's part of the partial
+        __threadfence();
+        ptx::named_bar_sync(bar_id, kGroupThreads);
+        if (elected) st_release(p.flags + 2 * cta + g, p.epoch);
+      }
+      q += nchunks;
+      if (!contributor && p.has_res) rq += nchunks;
+    }
+    if (elected) ptx::tma_store_wait_all<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+struct SkWorkspace {
+  float* ws = nullptr;
+  uint32_t* flags = nullptr;
+  uint32_t epoch = 0;
+  int device = -1;
+};
+SkWorkspace g_ws[16];
+
+int get_workspace(SkWorkspace** out) {
+  int dev = 0;
+  AP_CHECK_CUDA(cudaGetDevice(&dev));
+  AP_REQUIRE(dev >= 0 && dev < 16, "gemm_sk: device index %d out of range", dev);
+  SkWorkspace& w = g_ws[dev];
+  if (!w.ws) {
+    AP_CHECK_CUDA(cudaMalloc((void**)&w.ws, (size_t)kMaxGrid * kBlockM * 256 * sizeof(float)));
+    AP_CHECK_CUDA(cudaMalloc((void**)&w.flags, (size_t)kMaxGrid * 2 * sizeof(uint32_t)));
+    AP_CHECK_CUDA(cudaMemset(w.flags, 0, (size_t)kMaxGrid * 2 * sizeof(uint32_t)));
+    AP_CHECK_CUDA(cudaDeviceSynchronize());
+    w.device = dev;
+  }
+  *out = &w;
+  return 0;
+}
+
+template <int BN, int BK>
+int launch_bn(const GemmLaunch& L, KP& kp, cudaStream_t stream) {
+  constexpr int kABytes = kBlockM * BK * 2, kBBytes = BN * BK * 2;
+  static bool configured = false;
+  if (!configured) {
+    AP_CHECK_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    configured = true;
+  }
+  // shared-memory partition: [operand ring | resident B | 2 output chunks | residual ring | barriers]
+  const int fixed = 1024 + kBarBytes + kEpiGroups * kChunkBytes;
+  kp.res_bufs = kp.has_res ? (kp.num_kb <= 2 ? 4 : 2) : 0;
+  int avail = kSmemLimit - fixed - kp.res_bufs * kChunkBytes;
+  const int b_total = kp.num_kb * kBBytes;
+  kp.b_res = (kp.tiles_n == 1 && kp.tiles_m > num_sms() && b_total <= 80 * 1024 && avail - b_total >= 4 * kABytes &&
+              !getenv("AIRPOSE_NO_BRES")) ? 1 : 0;
+  if (kp.b_res) avail -= b_total;
+  const int stage_bytes = kp.b_res ? kABytes : kABytes + kBBytes;
+  kp.stages = std::min(kMaxStages, avail / stage_bytes);
+  AP_REQUIRE(kp.stages >= 2, "gemm_sk: shared memory partition failed (BN=%d)", BN);
+  const int smem_bytes = 1024 + kp.stages * stage_bytes + (kp.b_res ? b_total : 0) + kEpiGroups * kChunkBytes +
+                         kp.res_bufs * kChunkBytes + kBarBytes;
+  SkWorkspace* w = nullptr;
+  if (get_workspace(&w)) return 1;
+  kp.ws = w->ws; kp.flags = w->flags; kp.epoch = ++w->epoch;
+  const int units = kp.tiles_m * kp.tiles_n * kp.num_kb;
+  cudaLaunchConfig_t cfg{};
+  // Stream-K pays a fixed price per cut tile (a 128 x BN fp32 partial through L2 and a gather at the end of
+  // the owner's range): worth it when tiles are long in K and the tile count quantises badly on the SMs
+  // (measured: layer3/4 3x3 convs -20..30 %, short-K layers +10..30 %).  Everything else runs whole
+  // tiles round-robin.  Tiny problems are never split finer than 8 k-blocks per CTA.
+  const int tiles = kp.tiles_m * kp.tiles_n;
+  const int sms = std::min(num_sms(), kMaxGrid);
+  static const int min_kb = getenv("AIRPOSE_SK_SPLIT_MINKB") ? atoi(getenv("AIRPOSE_SK_SPLIT_MINKB")) : 16;
+  kp.split = (kp.num_kb >= min_kb && tiles < 8 * sms && tiles % sms != 0) ? 1 : 0;
+  cfg.gridDim = dim3((unsigned)(kp.split ? std::min(sms, std::max(std::min(tiles, sms), units / 8)) : std::min(tiles, sms)));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = L.pdl ? 1 : 0;
+  AP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_sk_kernel<BN, BK>, L.tmA, L.tmB, L.tmD, L.epi.residual ? L.tmR : L.tmD, kp));
+  count_launch();
+  return 0;
+}
+
+}  // namespace
+
+int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream) {
+  AP_REQUIRE(L.M > 0 && L.N > 0 && L.K > 0, "launch_gemm_sk: empty problem %dx%dx%d", L.M, L.N, L.K);
+  AP_REQUIRE(L.tma_epi, "launch_gemm_sk: tensor maps of the epilogue were not built");
+  KP kp{};
+  kp.M = L.M; kp.N = L.N; kp.K = L.K;
+  const int kBlockK = L.stem ? 32 : 64;
+  kp.num_kb = ceil_div(L.K, kBlockK);
+  kp.tiles_m = ceil_div(L.M, kBlockM);
+  kp.tiles_n = ceil_div(L.N, L.block_n);
+  kp.im2col = L.im2col;
+  kp.has_res = L.epi.residual != nullptr;
+  kp.relu = L.epi.relu;
+  kp.scale = L.epi.scale; kp.shift = L.epi.shift;
+  if (L.im2col) {
+    const ConvGeom& g = L.geom;
+    AP_REQUIRE(g.Cin % kBlockK == 0, "launch_gemm_sk: im2col needs Cin %% 64 == 0 (Cin=%d)", g.Cin);
+    AP_REQUIRE(L.K == g.ksize * g.ksize * g.Cin, "launch_gemm_sk: K=%d does not match the conv geometry", L.K);
+    kp.cblks = g.Cin / kBlockK; kp.ksize = g.ksize; kp.stride = g.stride; kp.pad = g.pad;
+    kp.Wo = g.Wo; kp.HoWo = g.Ho * g.Wo;
+  }
+  if (L.stem) {
+    AP_REQUIRE(L.block_n == 64 && kp.num_kb <= 8 && L.stem_img_rows % kBlockM == 0, "launch_gemm_sk: bad stem geometry");
+    kp.stem = 1; kp.stem_img_rows = L.stem_img_rows; kp.stem_img_stride = L.stem_img_stride;
+    for (int i = 0; i < 8; ++i) kp.stem_tap_off[i] = L.stem_tap_off[i];
+    return launch_bn<64, 32>(L, kp, stream);
+  }
+  switch (L.block_n) {
+    case 64: return launch_bn<64, 64>(L, kp, stream);
+    case 128: return launch_bn<128, 64>(L, kp, stream);
+    case 256: return launch_bn<256, 64>(L, kp, stream);
+    default: AP_REQUIRE(false, "launch_gemm_sk: unsupported block_n %d", L.block_n);
+  }
+  return 0;
+}
+
+}  // namespace airpose

@@ -323,7 +323,8 @@ int launch_bn(const GemmLaunch& L, const KP& kp, cudaStream_t stream) {
 bool tma_epilogue_eligible(const GemmLaunch& L) {
   const Epilogue& e = L.epi;
   return e.out_bf16 && !e.out_f32 && !e.out_split && L.N % kChunkN == 0 && e.ldd % 8 == 0 &&
-         (reinterpret_cast<uintptr_t>(e.out_bf16) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(e.out_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.scale) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(e.shift) & 15) == 0 &&
          (!e.residual || (!e.residual_f32 && e.ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(e.residual) & 15) == 0));
 }
 

@@ -230,7 +230,7 @@ static int conv_launch(airpose_net* h, int idx, const __nv_bfloat16* x, int n, i
   g.Ho = (H + 2 * s.pad - s.k) / s.stride + 1;
   g.Wo = (W + 2 * s.pad - s.k) / s.stride + 1;
   L->M = n * g.Ho * g.Wo; L->N = s.cout; L->K = s.k * s.k * s.cin;
-  L->block_n = pick_block_n(L->M, L->N);
+  L->block_n = pick_block_n(L->M, L->N, L->K);
   if (s.k == 1 && s.stride == 1) {
     L->im2col = 0;
     if (make_tmap_tiled_bf16(&L->tmA, x, L->M, L->K, L->K, 128, 64)) return 1;

@@ -173,6 +173,36 @@ typedef struct {
 } airpose_ief_args;
 int airpose_ief_fwd(airpose_net_t* h, const airpose_ief_args* a, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * training-step loss  (copenet/src/copenet/copenet_twoview.py:83-161, get_loss)
+ * ---------------------------------------------------------------------------------- */
+/* All seven MSE terms, their weighted sum x60 and (optionally) the gradient of the total loss with
+ * respect to every prediction, in one pass.  Shapes follow the reference tensors; `trans*` may be a
+ * strided view (pred_pose[:, :3], stride 135).  `out` receives 8 floats in the order of the reference's
+ * `losses` dict: loss, loss_regr_trans, loss_keypoints, loss_keypoints_3d, loss_regr_shape, loss_rootrot,
+ * loss_regr_pose, loss_regul_betas -- one device buffer instead of eight `.item()` syncs.
+ * Gradient buffers: all NULL (forward only) or all given; same shapes as the predictions (g_trans* dense [B,3]). */
+typedef struct {
+  int32_t batch, num_verts, num_joints;                 /* B, 10475, 127 */
+  const float* trans0; const float* trans1; int32_t trans_stride;        /* pred_smpltrans  [B,3] */
+  const float* rotmat0; const float* rotmat1;           /* pred_rotmat        [B,22,3,3] */
+  const float* betas0; const float* betas1;             /* pred_betas         [B,10] */
+  const float* verts0; const float* verts1;             /* pred_output_cam.vertices [B,V,3] (canonical) */
+  const float* joints0; const float* joints1;           /* pred_output_cam.joints   [B,127,3] */
+  const float* j2d0; const float* j2d1;                 /* pred_joints_2d_cam [B,127,2] */
+  const float* gt_pose_rotmat;                          /* smplpose_rotmat    [B,21,3,3] */
+  const float* gt_trans0; const float* gt_trans1;       /* smpltrans_rel{0,1} [B,3] */
+  const float* gt_orient0; const float* gt_orient1;     /* smplorient_rel{0,1} [B,1,3,3] */
+  const float* gt_verts;                                /* smpl_vertices      [B,1,V,3] */
+  const float* gt_joints;                               /* smpl_joints        [B,1,127,3] */
+  const float* gt_j2d0; const float* gt_j2d1;           /* smpl_joints_2d{0,1} [B,1,127,2] */
+  float w_shape, w_kp2d, w_kp3d, w_limbs3d, w_limbstheta, w_trans, w_rootrot, w_pose, w_beta;   /* :655-677 */
+  float* out;                                           /* [8] */
+  float* g_verts0; float* g_verts1; float* g_joints0; float* g_joints1; float* g_j2d0; float* g_j2d1;
+  float* g_rotmat0; float* g_rotmat1; float* g_betas0; float* g_betas1; float* g_trans0; float* g_trans1;
+} airpose_twoview_loss_args;
+int airpose_twoview_loss(const airpose_twoview_loss_args* a, void* stream);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t airpose_launch_count(void);
 

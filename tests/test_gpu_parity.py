@@ -186,7 +186,12 @@ def test_gemm_bf16_matches_torch(M, N, K):
 
 @pytest.mark.parametrize("M,N,K,res,relu", [(128, 64, 64, False, False), (300, 192, 320, True, True), (1000, 256, 2304, True, False),
                                             (6272, 2048, 512, True, True), (25088, 64, 576, False, True), (77, 320, 128, True, True),
-                                            (12545, 512, 128, True, True), (3000, 1024, 256, False, True)])
+                                            (12545, 512, 128, True, True), (3000, 1024, 256, False, True),
+                                            # stream-K splits (gemm_sk.cu): tiles cut across 2..16 CTAs, resident weights,
+                                            # the deep residual ring, and the trunk's own layer3/layer4 shapes
+                                            (256, 256, 8192, True, True), (25088, 256, 2304, False, True),
+                                            (6272, 512, 4608, True, True), (50176, 256, 64, True, True),
+                                            (50176, 64, 576, False, True), (1500, 128, 1152, True, False)])
 def test_gemm_tma_epilogue_bf16_out(M, N, K, res, relu):
     """bf16 output with N % 64 == 0 runs the TMA-epilogue kernel (gemm_tma.cu): swizzled smem staging,
     TMA residual loads and TMA stores, M tails clipped by the tensor map."""
@@ -290,16 +295,21 @@ def test_trunk_matches_oracle_and_golden(net_gpu, net_state, golden_twoview):
 @pytest.mark.parametrize("B", [3, 70])
 def test_trunk_pair_entry_matches_single_entry(net_gpu, B):
     """airpose_backbone_fwd_pair (two input tensors, chunks that never straddle them, groups of 128 images)
-    gives bit-identical features to the concatenated single-tensor call: images are independent in eval mode."""
+    gives the features of the concatenated single-tensor call: images are independent in eval mode.  Not
+    bit-identical any more: the stream-K layers (layer3/4 3x3 convs) cut their K loops at positions that
+    depend on the image count, which changes the fp32 summation order (one-ulp bf16 flips downstream).
+    The same call twice IS bit-identical (no atomics anywhere)."""
     g = torch.Generator(device="cpu").manual_seed(B)
     x0 = torch.randn(B, 3, 224, 224, generator=g).to(DEV)
     x1 = torch.randn(B, 3, 224, 224, generator=g).to(DEV)
     a = net_gpu.forward_feat_ext_pair(x0, x1)
     b = net_gpu.forward_feat_ext(torch.cat([x0, x1]))
     assert a.shape == (2 * B, 2048)
-    assert torch.equal(a, b)
+    assert torch.equal(a, net_gpu.forward_feat_ext_pair(x0, x1))
+    tol = 5e-3          # two bf16 evaluations with different summation order (see test_trunk_matches_oracle_and_golden)
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < tol
     c = net_gpu.forward_feat_ext(x1[:2])
-    assert torch.equal(c, a[B:B + 2])
+    assert rel_err(c.cpu().numpy(), a[B:B + 2].cpu().numpy()) < tol
 
 
 def _conv_abi(x_nhwc, w_oihw, bn, sd, stride, pad, residual=None, relu=True):
@@ -399,9 +409,99 @@ def test_twoview_end_to_end(net_gpu, net_state, smplx_dir, smplx_oracle, golden_
             assert e < 1e-3, (k, v, e)                      # north_star: 1e-3 relative fp32
         assert rel_err(out["pred_output_cam%d" % v].vertices.cpu().numpy(), ref["vertices%d" % v]) < 1e-3
         assert rel_err(out["pred_output_cam%d" % v].joints.cpu().numpy(), ref["joints%d" % v]) < 1e-3
-    # KAT 6: swapping the views swaps the outputs
+    # KAT 6: swapping the views swaps the outputs (to the trunk's bf16 summation-order tolerance: the
+    # stream-K layers cut an image's K loop at positions that depend on where the image sits in the batch)
     xs = {k: t(v) for k, v in x.items()}
     for k in ("im", "bb", "intr"):
         xs[k + "0"], xs[k + "1"] = xs[k + "1"], xs[k + "0"]
     outs = mod.fwd_pass(xs)
-    assert torch.equal(outs["pred_pose0"], out["pred_pose1"]) and torch.equal(outs["pred_betas1"], out["pred_betas0"])
+    assert rel_err(outs["pred_pose0"].cpu().numpy(), out["pred_pose1"].cpu().numpy()) < 2e-3
+    assert rel_err(outs["pred_betas1"].cpu().numpy(), out["pred_betas0"].cpu().numpy()) < 2e-3
+    assert rel_err(outs["pred_vertices_cam0"].cpu().numpy(), out["pred_vertices_cam1"].cpu().numpy()) < 2e-3
+
+
+# ----------------------------------------------------------------------------- loss (copenet_twoview.get_loss)
+def _loss_module(tmp_path, smplx_dir):
+    from argparse import Namespace
+    from airpose_b200.copenet_twoview import copenet_twoview
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+    return copenet_twoview(Namespace(smpl_mean_params=mp, smplx_model_dir=smplx_dir, batch_size=2, val_batch_size=2, reg_iters=3))
+
+
+def _loss_call(mod, gt, pred, with_grads=False):
+    from types import SimpleNamespace
+    cams = [SimpleNamespace(vertices=t(pred["vertices%d" % v]), joints=t(pred["joints%d" % v])) for v in (0, 1)]
+    return mod.get_loss({k: t(v) for k, v in gt.items()},
+                        t(pred["pred_pose0"])[:, :3], t(pred["pred_pose1"])[:, :3], t(pred["pred_rotmat0"]), t(pred["pred_rotmat1"]),
+                        t(pred["pred_betas0"]), t(pred["pred_betas1"]), cams[0], cams[1],
+                        t(pred["pred_joints_2d_cam0"]), t(pred["pred_joints_2d_cam1"]), with_grads=with_grads)
+
+
+def test_loss_matches_reference_golden(tmp_path, smplx_dir, golden_twoview):
+    """The CUDA get_loss on the reference's own fp32 predictions reproduces the loss values the real
+    reference module returned (tests/golden/twoview_b2.npz, made by oracle/gen_golden.py)."""
+    g = golden_twoview
+    mod = _loss_module(tmp_path, smplx_dir)
+    x = synthetic.make_inputs(2, int(g["in_seed"]))
+    gt = {k[3:]: g[k] for k in g if k.startswith("gt/")}
+    gt.update({k: x[k] for k in ("smpltrans_rel0", "smpltrans_rel1")})
+    pred = {k[5:]: g[k] for k in g if k.startswith("fp32/")}
+    loss, losses = _loss_call(mod, gt, pred)
+    vals = torch.stack([losses[n] for n in losses]).cpu().numpy()          # one D2H for all eight numbers
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    for n, val in zip(losses, vals):
+        ref = float(g["loss/" + n])
+        print("%-20s cuda %.8g reference %.8g" % (n, val, ref))
+        assert abs(val - ref) <= 1e-5 * abs(ref) + 1e-9
+
+
+@pytest.mark.parametrize("B", [1, 7])
+def test_loss_and_gradients_match_autograd(tmp_path, smplx_dir, B):
+    """Loss and d(loss)/d(prediction) against torch autograd (fp64) over the numpy oracle's formula."""
+    mod = _loss_module(tmp_path, smplx_dir)
+    rng = np.random.default_rng(B)
+    f = lambda *s: rng.standard_normal(s).astype(np.float32)
+    pred = {"pred_pose0": f(B, 135), "pred_pose1": f(B, 135), "pred_rotmat0": f(B, 22, 3, 3), "pred_rotmat1": f(B, 22, 3, 3),
+            "pred_betas0": f(B, 10), "pred_betas1": f(B, 10), "vertices0": f(B, 10475, 3), "vertices1": f(B, 10475, 3),
+            "joints0": f(B, 127, 3), "joints1": f(B, 127, 3), "pred_joints_2d_cam0": f(B, 127, 2) * 100,
+            "pred_joints_2d_cam1": f(B, 127, 2) * 100}
+    gt = {"smplpose_rotmat": f(B, 21, 3, 3), "smplorient_rel0": f(B, 1, 3, 3), "smplorient_rel1": f(B, 1, 3, 3),
+          "smpl_vertices": f(B, 1, 10475, 3), "smpl_joints": f(B, 1, 127, 3), "smpl_joints_2d0": f(B, 1, 127, 2) * 100,
+          "smpl_joints_2d1": f(B, 1, 127, 2) * 100, "smpltrans_rel0": f(B, 3), "smpltrans_rel1": f(B, 3)}
+    loss, losses, grads = _loss_call(mod, gt, pred, with_grads=True)
+    # reference: the oracle's get_loss formula (copenet_twoview.py:83-161) in torch fp64 with autograd
+    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in pred.items()}
+    G = {k: torch.tensor(v, dtype=torch.float64) for k, v in gt.items()}
+    hp = orc.DEFAULT_LOSS_WEIGHTS
+    mse = lambda a, b: (a - b) ** 2
+    tr0, tr1 = P["pred_pose0"][:, :3], P["pred_pose1"][:, :3]
+    gv, gj = G["smpl_vertices"].squeeze(1), G["smpl_joints"].squeeze(1)
+    w3 = torch.ones(22, dtype=torch.float64); w3[[4, 5, 18, 19]] = hp["limbs3d_loss_weight"]; w3[[7, 8, 20, 21]] = hp["limbs3d_loss_weight"] ** 2
+    wt = torch.ones(21, dtype=torch.float64); wt[[3, 4, 17, 18]] = hp["limbstheta_loss_weight"]; wt[[6, 7, 19, 20]] = hp["limbstheta_loss_weight"] ** 2
+    l_kp = sum(mse(P["pred_joints_2d_cam%d" % v][:, :22], G["smpl_joints_2d%d" % v].squeeze(1)[:, :22]).mean() for v in (0, 1))
+    l3 = (mse(P["joints0"][:, :22], gj[:, :22]) + mse(P["joints1"][:, :22], gj[:, :22]) + mse(P["joints0"][:, :22], P["joints1"][:, :22]))
+    l_kp3d = (l3 * w3.view(1, 22, 1)).mean()
+    l_shape = mse(P["vertices0"], gv).mean() + mse(P["vertices1"], gv).mean() + mse(P["vertices0"], P["vertices1"]).mean()
+    l_trans = mse(tr0, G["smpltrans_rel0"]).mean() + mse(tr1, G["smpltrans_rel1"]).mean()
+    l_root = sum(mse(P["pred_rotmat%d" % v][:, :1], G["smplorient_rel%d" % v]).mean() for v in (0, 1))
+    lr = (mse(P["pred_rotmat0"][:, 1:], G["smplpose_rotmat"]) + mse(P["pred_rotmat1"][:, 1:], G["smplpose_rotmat"])
+          + mse(P["pred_rotmat0"][:, 1:], P["pred_rotmat1"][:, 1:]))
+    l_pose = (lr * wt.view(1, 21, 1, 1)).mean()
+    b0, b1 = P["pred_betas0"], P["pred_betas1"]
+    l_beta = (b0 * b0).mean() + (b1 * b1).mean() + mse(b0, b1).mean()
+    ref = 60 * (hp["trans_loss_weight"] * l_trans + hp["keypoint2d_loss_weight"] * l_kp + hp["keypoint3d_loss_weight"] * l_kp3d
+                + hp["shape_loss_weight"] * l_shape + hp["rootrot_loss_weight"] * l_root + hp["pose_loss_weight"] * l_pose
+                + hp["beta_loss_weight"] * l_beta)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 2e-6 * abs(float(ref))
+    pairs = {"vertices0": P["vertices0"].grad, "vertices1": P["vertices1"].grad, "joints0": P["joints0"].grad,
+             "joints1": P["joints1"].grad, "joints_2d0": P["pred_joints_2d_cam0"].grad, "joints_2d1": P["pred_joints_2d_cam1"].grad,
+             "rotmat0": P["pred_rotmat0"].grad, "rotmat1": P["pred_rotmat1"].grad, "betas0": b0.grad, "betas1": b1.grad,
+             "smpltrans0": P["pred_pose0"].grad[:, :3], "smpltrans1": P["pred_pose1"].grad[:, :3]}
+    for k, gref in pairs.items():
+        e = rel_err(grads[k].cpu().numpy(), gref.numpy())
+        print("grad %-12s rel err %.2e" % (k, e))
+        assert e < 1e-5, k
+    # deterministic: a second call gives the same bits
+    loss2, _, grads2 = _loss_call(mod, gt, pred, with_grads=True)
+    assert torch.equal(loss, loss2) and torch.equal(grads["vertices0"], grads2["vertices0"])
