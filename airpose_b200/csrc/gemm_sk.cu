@@ -18,6 +18,11 @@
 //     ring when K is short, deep operand ring when K is long), and weights that fit stay RESIDENT in
 //     shared memory for the whole launch instead of being re-fetched per tile.
 //   * shared memory is addressed through the shared window (LDS/STS), not generic LD/ST.
+//   * what finally bounds the K-heavy layers is the L2->SM fabric (~45-50 B/clk per SM with all 148 SMs
+//     pulling): a 128xBN tile needs 64*(128+BN)/BN B/clk at full tensor rate, i.e. at most 22 / 33 / 44 % of
+//     the tensor peak for BN = 64 / 128 / 256 -- exactly the tensor-pipe numbers ncu reports.  MT = 2 gives a
+//     CTA two 128-row sub-tiles that share every B k-block (a 256xBN tile: half the B traffic per flop,
+//     accumulators MT*BN TMEM columns, double-buffered only while 2*MT*BN <= 512).
 //
 // CTA = 11 warps, one CTA per SM:
 //   warp 0    A/B TMA producer     warp 1   MMA issuer (TMEM double-buffered)    warp 2   residual TMA producer
@@ -113,14 +118,18 @@ struct SegIter {
   }
 };
 
-template <int BN, int BK>
+template <int BN, int BK, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR, const KP p) {
-  constexpr int kABytes = kBlockM * BK * 2;
+  constexpr int kASub = kBlockM * BK * 2;           // one 128-row sub-tile of A
+  constexpr int kABytes = MT * kASub;
   constexpr int kBBytes = BN * BK * 2;
-  constexpr int kTmemCols = 2 * BN;
+  constexpr int kAccCols = MT * BN;                 // TMEM columns of one accumulator set
+  constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;
+  constexpr int kTmemCols = kAccBufs * kAccCols;
   constexpr int kChunks = BN / kChunkN;
+  constexpr int kTileM = MT * kBlockM;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_u32 & 1023u)) & 1023u);
@@ -183,32 +192,44 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       Seg s;
       while (it.next(s)) {
         const int m_blk = s.tile / p.tiles_n, n_blk = s.tile - m_blk * p.tiles_n;
-        const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
-        int cw = 0, ch = 0, cn = 0;
-        if (p.im2col) {
-          cn = m0 / p.HoWo;
-          const int rem = m0 - cn * p.HoWo;
-          const int po = rem / p.Wo, qo = rem - po * p.Wo;
-          cw = qo * p.stride - p.pad;
-          ch = po * p.stride - p.pad;
+        const int m0 = m_blk * kTileM, n0 = n_blk * BN;
+        const int vmt = min(MT, (p.M - m0 + kBlockM - 1) / kBlockM);     // sub-tiles that hold rows of the problem
+        int cw[MT], ch[MT], cn[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          cw[mt] = ch[mt] = cn[mt] = 0;
+          if (p.im2col) {
+            const int mm = m0 + mt * kBlockM;
+            cn[mt] = mm / p.HoWo;
+            const int rem = mm - cn[mt] * p.HoWo;
+            const int po = rem / p.Wo, qo = rem - po * p.Wo;
+            cw[mt] = qo * p.stride - p.pad;
+            ch[mt] = po * p.stride - p.pad;
+          }
         }
         int stem_row = 0;
         if (BK == 32) {                                // stem: tiles never straddle images (12544 = 98 * 128)
           const int img = m0 / p.stem_img_rows;
           stem_row = img * p.stem_img_stride + (m0 - img * p.stem_img_rows);
         }
+        const int tx_bytes = vmt * kASub + (p.b_res ? 0 : kBBytes);
         for (int kb = s.kb0; kb < s.kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
           uint8_t* sa = smem + stage * stage_bytes;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
-          if (BK == 32) {
-            ptx::tma_load_2d(&tmA, &full_bar[stage], sa, 0, stem_row + p.stem_tap_off[kb]);
-          } else if (p.im2col) {
-            const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
-            const int r = tap / p.ksize, sx = tap - r * p.ksize;
-            ptx::tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, cw, ch, cn, (uint16_t)sx, (uint16_t)r);
-          } else {
-            ptx::tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m0);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            if (mt >= vmt) break;
+            uint8_t* sam = sa + mt * kASub;
+            if (BK == 32) {
+              ptx::tma_load_2d(&tmA, &full_bar[stage], sam, 0, stem_row + p.stem_tap_off[kb]);
+            } else if (p.im2col) {
+              const int tap = kb / p.cblks, cb = kb - tap * p.cblks;
+              const int r = tap / p.ksize, sx = tap - r * p.ksize;
+              ptx::tma_load_im2col_4d(&tmA, &full_bar[stage], sam, cb * BK, cw[mt], ch[mt], cn[mt], (uint16_t)sx, (uint16_t)r);
+            } else {
+              ptx::tma_load_2d(&tmA, &full_bar[stage], sam, kb * BK, m0 + mt * kBlockM);
+            }
           }
           if (!p.b_res) ptx::tma_load_2d(&tmB, &full_bar[stage], sa + kABytes, kb * BK, n0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -225,21 +246,27 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       SegIter it(cta, grid, units, p.num_kb, p.split);
       Seg s;
       while (it.next(s)) {
-        const int as = n & 1; const uint32_t aphase = (n >> 1) & 1;
+        const int as = n % kAccBufs; const uint32_t aphase = (n / kAccBufs) & 1;
         ++n;
+        const int m_blk = s.tile / p.tiles_n;
+        const int vmt = min(MT, (p.M - m_blk * kTileM + kBlockM - 1) / kBlockM);
         ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, 200 + as);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_base + as * kAccCols;
         for (int kb = s.kb0; kb < s.kb1; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase, 300 + stage);
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = p.b_res ? smem_base + bres_off + kb * kBBytes : sa + kABytes;
-          const uint64_t adesc = ptx::make_kmajor_desc(sa, BK * 2);
           const uint64_t bdesc = ptx::make_kmajor_desc(sb, BK * 2);
 #pragma unroll
-          for (int k = 0; k < BK / kUmmaK; ++k)
-            ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != s.kb0 || k != 0) ? 1u : 0u);
+          for (int mt = 0; mt < MT; ++mt) {
+            if (mt >= vmt) break;
+            const uint64_t adesc = ptx::make_kmajor_desc(sa + mt * kASub, BK * 2);
+#pragma unroll
+            for (int k = 0; k < BK / kUmmaK; ++k)
+              ptx::umma_bf16(d_tmem + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != s.kb0 || k != 0) ? 1u : 0u);
+          }
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -255,13 +282,15 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       while (it.next(s)) {
         if (s.kb0 != 0) continue;                      // a partial handed to the tile's owner: no epilogue here
         const int m_blk = s.tile / p.tiles_n, n_blk = s.tile - m_blk * p.tiles_n;
-        const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
-        const int nchunks = min(kChunks, (p.N - n0) / kChunkN);
-        for (int c = 0; c < nchunks; ++c, ++rq) {
+        const int m0 = m_blk * kTileM, n0 = n_blk * BN;
+        const int vmt = min(MT, (p.M - m0 + kBlockM - 1) / kBlockM);
+        const int ncn = min(kChunks, (p.N - n0) / kChunkN);
+        for (int c = 0; c < vmt * ncn; ++c, ++rq) {
+          const int mt = c / ncn, cn = c - mt * ncn;
           const int rs = rq % p.res_bufs; const uint32_t rphase = (rq / p.res_bufs) & 1;
           ptx::mbar_wait(&rempty_bar[rs], rphase ^ 1, 500 + rs);
           ptx::mbar_arrive_expect_tx(&rfull_bar[rs], kChunkBytes);
-          ptx::tma_load_2d(&tmR, &rfull_bar[rs], smem + res_off + rs * kChunkBytes, n0 + c * kChunkN, m0);
+          ptx::tma_load_2d(&tmR, &rfull_bar[rs], smem + res_off + rs * kChunkBytes, n0 + cn * kChunkN, m0 + mt * kBlockM);
         }
       }
     }
@@ -269,22 +298,25 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ epilogue groups
     const int g = (warp - kEpiWarp0) >> 2;           // epilogue group
     const int quad = warp & 3;                       // TMEM lane quarter this warp may read
-    const int row = quad * 32 + lane;                // row of the tile == TMEM lane
+    const int row = quad * 32 + lane;                // row of the sub-tile == TMEM lane
     const bool elected = ((warp - kEpiWarp0) & 3) == 0 && lane == 0;
     const uint32_t swz = (uint32_t)(row & 7);
     const uint32_t ob = smem_base + out_off + g * kChunkBytes;
     const uint32_t orow = ob + row * 128;
     const int bar_id = 1 + g;
-    float4* ws_mine = reinterpret_cast<float4*>(p.ws) + (size_t)cta * (kBlockM * BN / 4);
+    constexpr int kSlotF4 = kTileM * BN / 4;         // float4s per CTA slot of the workspace
+    float4* ws_mine = reinterpret_cast<float4*>(p.ws) + (size_t)cta * kSlotF4;
     int n = 0, q = 0, rq = 0;
     SegIter it(cta, grid, units, p.num_kb, p.split);
     Seg s;
     while (it.next(s)) {
-      const int as = n & 1; const uint32_t aphase = (n >> 1) & 1;
+      const int as = n % kAccBufs; const uint32_t aphase = (n / kAccBufs) & 1;
       ++n;
       const int m_blk = s.tile / p.tiles_n, n_blk = s.tile - m_blk * p.tiles_n;
-      const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
-      const int nchunks = min(kChunks, (p.N - n0) / kChunkN);
+      const int m0 = m_blk * kTileM, n0 = n_blk * BN;
+      const int vmt = min(MT, (p.M - m0 + kBlockM - 1) / kBlockM);
+      const int ncn = min(kChunks, (p.N - n0) / kChunkN);
+      const int nchunks = vmt * ncn;
       const bool contributor = s.kb0 != 0;
       const bool gather = !contributor && s.kb1 < p.num_kb;     // owner of a tile other CTAs finish
       ptx::mbar_wait(&tfull_bar[as], aphase, 400 + as);
@@ -315,8 +347,10 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int c = 0; c < nchunks; ++c) {
         if (((q + c) & 1) != g) continue;
+        const int mt = c / ncn, cn = c - mt * ncn;
+        const int slot_c = (mt * kChunks + cn) * 16 * kBlockM + row;     // float4 index of this thread's part of chunk c
         uint32_t r[64];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * BN + c * kChunkN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kAccCols + mt * BN + cn * kChunkN;
         ptx::tmem_ld_32x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
         ptx::tmem_ld_32x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
         ptx::tmem_ld_wait();
@@ -326,7 +360,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
         }
         if (contributor) {                           // fp32 partial -> workspace (coalesced: 16 B x 32 lanes)
-          float4* dst = ws_mine + (size_t)c * 16 * kBlockM + row;
+          float4* dst = ws_mine + slot_c;
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             __stcg(dst + j * kBlockM, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -341,8 +375,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           while (need > 0) {
             const int a0 = (int)((int64_t)cc * units / grid), a1 = (int)((int64_t)(cc + 1) * units / grid);
             if (a1 > a0) {
-              const float4* src = reinterpret_cast<const float4*>(p.ws) + (size_t)cc * (kBlockM * BN / 4) +
-                                  (size_t)c * 16 * kBlockM + row;
+              const float4* src = reinterpret_cast<const float4*>(p.ws) + (size_t)cc * kSlotF4 + slot_c;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const float4 t = __ldcg(src + j * kBlockM);
@@ -354,7 +387,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         {
-          const int nb = n0 + c * kChunkN;
+          const int nb = n0 + cn * kChunkN;
           const float4* sc4 = reinterpret_cast<const float4*>(p.scale + nb);
           const float4* sh4 = reinterpret_cast<const float4*>(p.shift + nb);
 #pragma unroll
@@ -403,7 +436,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::fence_proxy_async();
         ptx::named_bar_sync(bar_id, kGroupThreads);
         if (elected) {
-          ptx::tma_store_2d(&tmD, smem + out_off + g * kChunkBytes, n0 + c * kChunkN, m0);
+          ptx::tma_store_2d(&tmD, smem + out_off + g * kChunkBytes, n0 + cn * kChunkN, m0 + mt * kBlockM);
           ptx::tma_store_commit();
         }
       }
@@ -434,6 +467,7 @@ struct SkWorkspace {
   int device = -1;
 };
 SkWorkspace g_ws[16];
+constexpr int kMaxMT = 2;
 
 int get_workspace(SkWorkspace** out) {
   int dev = 0;
@@ -441,7 +475,7 @@ int get_workspace(SkWorkspace** out) {
   AP_REQUIRE(dev >= 0 && dev < 16, "gemm_sk: device index %d out of range", dev);
   SkWorkspace& w = g_ws[dev];
   if (!w.ws) {
-    AP_CHECK_CUDA(cudaMalloc((void**)&w.ws, (size_t)kMaxGrid * kBlockM * 256 * sizeof(float)));
+    AP_CHECK_CUDA(cudaMalloc((void**)&w.ws, (size_t)kMaxGrid * kMaxMT * kBlockM * 256 * sizeof(float)));
     AP_CHECK_CUDA(cudaMalloc((void**)&w.flags, (size_t)kMaxGrid * 2 * sizeof(uint32_t)));
     AP_CHECK_CUDA(cudaMemset(w.flags, 0, (size_t)kMaxGrid * 2 * sizeof(uint32_t)));
     AP_CHECK_CUDA(cudaDeviceSynchronize());
@@ -451,25 +485,26 @@ int get_workspace(SkWorkspace** out) {
   return 0;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int MT>
 int launch_bn(const GemmLaunch& L, KP& kp, cudaStream_t stream) {
-  constexpr int kABytes = kBlockM * BK * 2, kBBytes = BN * BK * 2;
+  constexpr int kABytes = MT * kBlockM * BK * 2, kBBytes = BN * BK * 2;
   static bool configured = false;
   if (!configured) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    AP_CHECK_CUDA(cudaFuncSetAttribute(gemm_sk_kernel<BN, BK, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     configured = true;
   }
+  kp.tiles_m = ceil_div(kp.M, MT * kBlockM);
   // shared-memory partition: [operand ring | resident B | 2 output chunks | residual ring | barriers]
   const int fixed = 1024 + kBarBytes + kEpiGroups * kChunkBytes;
   kp.res_bufs = kp.has_res ? (kp.num_kb <= 2 ? 4 : 2) : 0;
   int avail = kSmemLimit - fixed - kp.res_bufs * kChunkBytes;
   const int b_total = kp.num_kb * kBBytes;
-  kp.b_res = (kp.tiles_n == 1 && kp.tiles_m > num_sms() && b_total <= 80 * 1024 && avail - b_total >= 4 * kABytes &&
+  kp.b_res = (kp.tiles_n == 1 && kp.tiles_m > num_sms() && b_total <= 80 * 1024 && avail - b_total >= 3 * kABytes &&
               !getenv("AIRPOSE_NO_BRES")) ? 1 : 0;
   if (kp.b_res) avail -= b_total;
   const int stage_bytes = kp.b_res ? kABytes : kABytes + kBBytes;
   kp.stages = std::min(kMaxStages, avail / stage_bytes);
-  AP_REQUIRE(kp.stages >= 2, "gemm_sk: shared memory partition failed (BN=%d)", BN);
+  AP_REQUIRE(kp.stages >= 2, "gemm_sk: shared memory partition failed (BN=%d MT=%d)", BN, MT);
   const int smem_bytes = 1024 + kp.stages * stage_bytes + (kp.b_res ? b_total : 0) + kEpiGroups * kChunkBytes +
                          kp.res_bufs * kChunkBytes + kBarBytes;
   SkWorkspace* w = nullptr;
@@ -477,13 +512,13 @@ int launch_bn(const GemmLaunch& L, KP& kp, cudaStream_t stream) {
   kp.ws = w->ws; kp.flags = w->flags; kp.epoch = ++w->epoch;
   const int units = kp.tiles_m * kp.tiles_n * kp.num_kb;
   cudaLaunchConfig_t cfg{};
-  // Stream-K pays a fixed price per cut tile (a 128 x BN fp32 partial through L2 and a gather at the end of
+  // Stream-K pays a fixed price per cut tile (an fp32 partial tile through L2 and a gather at the end of
   // the owner's range): worth it when tiles are long in K and the tile count quantises badly on the SMs
   // (measured: layer3/4 3x3 convs -20..30 %, short-K layers +10..30 %).  Everything else runs whole
   // tiles round-robin.  Tiny problems are never split finer than 8 k-blocks per CTA.
   const int tiles = kp.tiles_m * kp.tiles_n;
   const int sms = std::min(num_sms(), kMaxGrid);
-  static const int min_kb = getenv("AIRPOSE_SK_SPLIT_MINKB") ? atoi(getenv("AIRPOSE_SK_SPLIT_MINKB")) : 16;
+  static const int min_kb = getenv("AIRPOSE_SK_SPLIT_MINKB") ? atoi(getenv("AIRPOSE_SK_SPLIT_MINKB")) : 8;
   kp.split = (kp.num_kb >= min_kb && tiles < 8 * sms && tiles % sms != 0) ? 1 : 0;
   cfg.gridDim = dim3((unsigned)(kp.split ? std::min(sms, std::max(std::min(tiles, sms), units / 8)) : std::min(tiles, sms)));
   cfg.blockDim = dim3(kThreads);
@@ -494,7 +529,7 @@ int launch_bn(const GemmLaunch& L, KP& kp, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = L.pdl ? 1 : 0;
-  AP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_sk_kernel<BN, BK>, L.tmA, L.tmB, L.tmD, L.epi.residual ? L.tmR : L.tmD, kp));
+  AP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_sk_kernel<BN, BK, MT>, L.tmA, L.tmB, L.tmD, L.epi.residual ? L.tmR : L.tmD, kp));
   count_launch();
   return 0;
 }
@@ -508,7 +543,6 @@ int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream) {
   kp.M = L.M; kp.N = L.N; kp.K = L.K;
   const int kBlockK = L.stem ? 32 : 64;
   kp.num_kb = ceil_div(L.K, kBlockK);
-  kp.tiles_m = ceil_div(L.M, kBlockM);
   kp.tiles_n = ceil_div(L.N, L.block_n);
   kp.im2col = L.im2col;
   kp.has_res = L.epi.residual != nullptr;
@@ -525,12 +559,19 @@ int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream) {
     AP_REQUIRE(L.block_n == 64 && kp.num_kb <= 8 && L.stem_img_rows % kBlockM == 0, "launch_gemm_sk: bad stem geometry");
     kp.stem = 1; kp.stem_img_rows = L.stem_img_rows; kp.stem_img_stride = L.stem_img_stride;
     for (int i = 0; i < 8; ++i) kp.stem_tap_off[i] = L.stem_tap_off[i];
-    return launch_bn<64, 32>(L, kp, stream);
+    return launch_bn<64, 32, 1>(L, kp, stream);
   }
+  // MT = 2 (two 128-row sub-tiles sharing each B k-block, 256 x BN tiles) is kept for experiments only:
+  // measured SLOWER than MT = 1 on every trunk layer (layer3 3x3: 47.7 vs 39.6 us, layer4 3x3: 54 vs 41 us;
+  // profiles/r01e_layers_mt2.txt).  It trades the L2->SM traffic for a single-buffered accumulator, and the
+  // binding limit of a cta_group::1 tile is shared-memory bandwidth (MMA operand reads + TMA writes share
+  // 128 B/clk: a 128x256 tile needs 192 B/clk at full tensor rate), which MT = 2 barely changes (160 B/clk).
+  static const bool want_mt2 = getenv("AIRPOSE_SK_MT2") != nullptr;
+  const bool mt2 = want_mt2 && L.M > kBlockM;
   switch (L.block_n) {
-    case 64: return launch_bn<64, 64>(L, kp, stream);
-    case 128: return launch_bn<128, 64>(L, kp, stream);
-    case 256: return launch_bn<256, 64>(L, kp, stream);
+    case 64: return mt2 ? launch_bn<64, 64, 2>(L, kp, stream) : launch_bn<64, 64, 1>(L, kp, stream);
+    case 128: return mt2 ? launch_bn<128, 64, 2>(L, kp, stream) : launch_bn<128, 64, 1>(L, kp, stream);
+    case 256: return mt2 ? launch_bn<256, 64, 2>(L, kp, stream) : launch_bn<256, 64, 1>(L, kp, stream);
     default: AP_REQUIRE(false, "launch_gemm_sk: unsupported block_n %d", L.block_n);
   }
   return 0;

@@ -9,3 +9,4 @@ run() { # name, env
 }
 run new ""
 if [ -n "$2" ]; then run alt "$2"; fi
+if [ -n "$3" ]; then run alt2 "$3"; fi
