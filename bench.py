@@ -30,6 +30,9 @@ GFLOP_PER_IMAGE = 8.174272512          # 4,087,136,256 MAC
 LBS_BYTES_PER_MESH = 128420
 LBS_CONST_BYTES = 68338900
 CPU_SAMPLE_PAIRS = 8
+# dram__bytes_read.sum + dram__bytes_write.sum summed over the 77 conv-GEMM launches of one 128-image trunk
+# forward (64 pairs), from the ncu capture profiles/r01d_layers_dispatch_vs_v1.txt (cold-cache, serialised)
+TRUNK_DRAM_BYTES_PER_64_PAIRS = 4808.5e6
 
 
 def load_peaks():
@@ -255,10 +258,8 @@ def run_ours(args):
         lbs_ms = e0.elapsed_time(e1) / 5
         lbs = (nb, lbs_ms)
 
-    if world > 1:
-        t = torch.tensor([ms, e2e_ms, trunk_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, trunk_ms = t.tolist()
+    from airpose_b200 import parallel
+    ms, e2e_ms, trunk_ms = parallel.max_over_ranks([ms, e2e_ms, trunk_ms], device=dev)
     if rank == 0:
         peaks = load_peaks()
         value = world * B / (ms * 1e-3)
@@ -274,17 +275,21 @@ def run_ours(args):
                     "note": "pinned host fp32 images -> H2D (double-buffered on a copy stream) -> fwd_pass -> D2H of pose/betas/vertices_cam/joints_cam/joints_2d"},
             "gpu_launches": launches,
             "stage_ms": {"trunk": trunk_ms, "ief": ief_ms, "smplx_x2": smplx_ms},
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05 implicit-GEMM convs of the ResNet-50 trunk, both views)",
+            "roofline": {"bound": "tensor", "kernel": "gemm_tma_kernel / gemm_sk_kernel (tcgen05 implicit-GEMM convs of the ResNet-50 trunk, both views; 77 launches per 128 images)",
                          "achieved": tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tflops_sustained"],
-                         "traffic": None, "peak_source": peaks["source"] + ", sustained bf16"},
+                         "traffic": TRUNK_DRAM_BYTES_PER_64_PAIRS * B / 64.0,
+                         "traffic_note": "bytes per step summed over the trunk's GEMM launches (ncu, profiles/r01d_*); algorithmic HBM bytes 56.4 MB/image",
+                         "peak_source": peaks["source"] + ", sustained bf16"},
             "clocks": clocks,
         }
         if lbs:
             nb, lbs_ms = lbs
             gbs = (nb * LBS_BYTES_PER_MESH + LBS_CONST_BYTES) / (lbs_ms * 1e-3) / 1e9
-            out["roofline_lbs"] = {"bound": "hbm", "kernel": "smplx_vertex_kernel (+pose/joints kernels), lbs() batch=%d" % nb,
+            out["roofline_lbs"] = {"bound": "hbm", "kernel": "smplx_vertex_tc_kernel (+pose/joints kernels), lbs() batch=%d" % nb,
                                    "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                                   "meshes_per_s": nb / (lbs_ms * 1e-3), "traffic": None, "peak_source": peaks["source"]}
+                                   "meshes_per_s": nb / (lbs_ms * 1e-3), "traffic": 1073.6e6,
+                                   "traffic_note": "dram read+write of smplx_vertex_tc_kernel per launch at B=8192 (ncu, profiles/r01c_ncu_full_lbs_b8192.csv)",
+                                   "peak_source": peaks["source"]}
             if not args.no_cpu_baseline:
                 v, cms, cores = cpu_reference(CPU_SAMPLE_PAIRS, 3, 1)
                 out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
