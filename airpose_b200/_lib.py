@@ -44,7 +44,7 @@ class SmplxFwdArgs(C.Structure):
                 ("center", C.c_void_p), ("center_stride", C.c_int32),
                 ("out_vertices", C.c_void_p), ("out_joints", C.c_void_p),
                 ("out_vertices_cam", C.c_void_p), ("out_joints_cam", C.c_void_p),
-                ("out_joints_2d", C.c_void_p)]
+                ("out_joints_2d", C.c_void_p), ("proj_t", C.c_void_p), ("proj_t_stride", C.c_int32)]
 
 
 class ConvParams(C.Structure):
@@ -58,6 +58,23 @@ class NetParams(C.Structure):
                 ("decpose_w", C.c_void_p), ("decpose_b", C.c_void_p),
                 ("decshape_w", C.c_void_p), ("decshape_b", C.c_void_p),
                 ("init_pose", C.c_void_p), ("init_shape", C.c_void_p), ("bn_eps", C.c_float)]
+
+
+class HmrParams(C.Structure):
+    _fields_ = [("conv", ConvParams * 53),
+                ("fc1_w", C.c_void_p), ("fc1_b", C.c_void_p), ("fc2_w", C.c_void_p), ("fc2_b", C.c_void_p),
+                ("decpose_w", C.c_void_p), ("decpose_b", C.c_void_p),
+                ("decshape_w", C.c_void_p), ("decshape_b", C.c_void_p),
+                ("deccam_w", C.c_void_p), ("deccam_b", C.c_void_p),
+                ("init_pose", C.c_void_p), ("init_shape", C.c_void_p), ("init_cam", C.c_void_p), ("bn_eps", C.c_float)]
+
+
+class HmrIefArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("iters", C.c_int32), ("xf", C.c_void_p),
+                ("init_theta", C.c_void_p), ("init_theta_stride", C.c_int32),
+                ("init_shape", C.c_void_p), ("init_shape_stride", C.c_int32),
+                ("init_cam", C.c_void_p), ("init_cam_stride", C.c_int32),
+                ("out_pose", C.c_void_p), ("out_betas", C.c_void_p), ("out_cam", C.c_void_p)]
 
 
 class IefArgs(C.Structure):
@@ -116,6 +133,8 @@ SYMBOLS = {
     "airpose_backbone_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "airpose_backbone_fwd_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "airpose_ief_fwd": (C.c_int, [C.c_void_p, C.POINTER(IefArgs), C.c_void_p]),
+    "airpose_hmr_load": (C.c_int, [C.c_void_p, C.POINTER(HmrParams), C.c_void_p]),
+    "airpose_hmr_ief_fwd": (C.c_int, [C.c_void_p, C.POINTER(HmrIefArgs), C.c_void_p]),
     "airpose_twoview_loss": (C.c_int, [C.POINTER(LossArgs), C.c_void_p]),
     "airpose_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "airpose_conv_bf16": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),

@@ -27,26 +27,24 @@ constexpr int kIefKPer = kFeat / kIefKSlices;
 constexpr int kIefRows = 8;            // rows of [xf0; xf1] per CTA in the base product
 
 // ------------------------------------------------------------------------------ load-time kernels
-__device__ __forceinline__ const float* dec_row(const float* decpose_w, const float* decshape_w, int o) {
-  return o < 135 ? decpose_w + (size_t)o * kHid : decshape_w + (size_t)(o - 135) * kHid;
-}
+// Both regressors decode 145 numbers: two-view [decpose 135 | decshape 10] (model_copenet.py:71-72),
+// hmr [decpose 132 | decshape 10 | deccam 3] (model_hmr.py:69-71).  The decoder matrices are copied into
+// one contiguous Wdec [145][1024] / bdec [145] at load so the fold kernels serve both.
 
 // T[o][j] = sum_i Wdec[o][i] * W2[i][j]      (145 x 1024, fp64)
-__global__ void ief_fold_t_kernel(const float* __restrict__ decpose_w, const float* __restrict__ decshape_w,
-                                  const float* __restrict__ fc2_w, double* __restrict__ T) {
+__global__ void ief_fold_t_kernel(const float* __restrict__ wdec, const float* __restrict__ fc2_w, double* __restrict__ T) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, o = blockIdx.y;
   if (j >= kHid) return;
-  const float* wd = dec_row(decpose_w, decshape_w, o);
+  const float* wd = wdec + (size_t)o * kHid;
   double acc = 0.0;
   for (int i = 0; i < kHid; ++i) acc += (double)__ldg(wd + i) * (double)__ldg(fc2_w + (size_t)i * kHid + j);
   T[(size_t)o * kHid + j] = acc;
 }
 
 // G[o][k] = sum_j T[o][j] * W1[j][k]  -> GxT[k][o] (k < 2048) / GuT[k-2048][o]
-__global__ void ief_fold_g_kernel(const double* __restrict__ T, const float* __restrict__ fc1_w, float* __restrict__ GxT,
-                                  float* __restrict__ GuT) {
+__global__ void ief_fold_g_kernel(const double* __restrict__ T, const float* __restrict__ fc1_w, int fc1_in,
+                                  float* __restrict__ GxT, float* __restrict__ GuT) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x, o = blockIdx.y;
-  const int fc1_in = kFeat + kState;
   if (k >= fc1_in) return;
   double acc = 0.0;
   for (int j = 0; j < kHid; ++j) acc += T[(size_t)o * kHid + j] * (double)__ldg(fc1_w + (size_t)j * fc1_in + k);
@@ -56,14 +54,13 @@ __global__ void ief_fold_g_kernel(const double* __restrict__ T, const float* __r
 
 // g[o] = T[o] . b1 + Wdec[o] . b2 + bdec[o]
 __global__ void ief_fold_bias_kernel(const double* __restrict__ T, const float* __restrict__ fc1_b,
-                                     const float* __restrict__ decpose_w, const float* __restrict__ decshape_w,
-                                     const float* __restrict__ fc2_b, const float* __restrict__ decpose_b,
-                                     const float* __restrict__ decshape_b, float* __restrict__ g) {
+                                     const float* __restrict__ wdec, const float* __restrict__ fc2_b,
+                                     const float* __restrict__ bdec, float* __restrict__ g) {
   const int o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= kDecPad) return;
   if (o >= kDec) { g[o] = 0.f; return; }
-  const float* wd = dec_row(decpose_w, decshape_w, o);
-  double acc = o < 135 ? (double)decpose_b[o] : (double)decshape_b[o - 135];
+  const float* wd = wdec + (size_t)o * kHid;
+  double acc = (double)bdec[o];
   for (int j = 0; j < kHid; ++j) acc += T[(size_t)o * kHid + j] * (double)fc1_b[j] + (double)wd[j] * (double)fc2_b[j];
   g[o] = (float)acc;
 }
@@ -79,6 +76,31 @@ __global__ void __launch_bounds__(kDecPad) ief_base_kernel(int B, const float* _
     float v = 0.f;
     if (m < M) v = __ldg((m < B ? xf0 + (size_t)m * kFeat : xf1 + (size_t)(m - B) * kFeat) + ks * kIefKPer + k);
     xs[r][k] = v;
+  }
+  __syncthreads();
+  float acc[kIefRows];
+#pragma unroll
+  for (int r = 0; r < kIefRows; ++r) acc[r] = 0.f;
+  const float* gp = GxT + (size_t)ks * kIefKPer * kDecPad + o;
+#pragma unroll 4
+  for (int k = 0; k < kIefKPer; ++k) {
+    const float gv = __ldg(gp + (size_t)k * kDecPad);
+#pragma unroll
+    for (int r = 0; r < kIefRows; ++r) acc[r] = fmaf(gv, xs[r][k], acc[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < kIefRows; ++r)
+    if (m0 + r < M) partial[((size_t)ks * M + m0 + r) * kDecPad + o] = acc[r];
+}
+
+// same product for a single feature tensor (hmr): partial[ks][m][o], rows m in [0,M)
+__global__ void __launch_bounds__(kDecPad) ief_base_rows_kernel(int M, const float* __restrict__ xf, const float* __restrict__ GxT,
+                                                                float* __restrict__ partial) {
+  __shared__ float xs[kIefRows][kIefKPer];
+  const int m0 = blockIdx.x * kIefRows, ks = blockIdx.y, o = threadIdx.x;
+  for (int i = threadIdx.x; i < kIefRows * kIefKPer; i += kDecPad) {
+    const int r = i / kIefKPer, k = i % kIefKPer, m = m0 + r;
+    xs[r][k] = m < M ? __ldg(xf + (size_t)m * kFeat + ks * kIefKPer + k) : 0.f;
   }
   __syncthreads();
   float acc[kIefRows];
@@ -153,41 +175,136 @@ __global__ void __launch_bounds__(2 * kDecPad) ief_iter_kernel(IefIterArgs a) {
   else if (o < kDec) (v ? a.out_betas1 : a.out_betas0)[(size_t)b * 10 + (o - 135)] = st[v][o];
 }
 
-int ief_create(airpose_net* h) {
-  IefState& s = h->ief;
+// hmr regressor (model_hmr.py:112-172): single view, state = [pose 132 | shape 10 | cam 3] is also the
+// iterated part of the fc1 input (:161), so one iteration is  state += base + Gu state.
+// One CTA per image, thread o = output; base = g + fixed-order sum of the split-K partials.
+struct HmrIterArgs {
+  int B, iters;
+  const float *th; int th_stride;
+  const float *sh; int sh_stride;
+  const float *cam; int cam_stride;
+  const float *init_pose, *init_shape, *init_cam;
+  const float *partial, *GuT, *g;
+  float *out_pose, *out_betas, *out_cam;
+};
+
+__global__ void __launch_bounds__(kDecPad) hmr_iter_kernel(HmrIterArgs a) {
+  __shared__ float st[kDecPad];
+  const int b = blockIdx.x, o = threadIdx.x;
+  float base = 0.f;
+  if (o < kDec) {
+    base = __ldg(a.g + o);
+    for (int ks = 0; ks < kIefKSlices; ++ks) base += __ldg(a.partial + ((size_t)ks * a.B + b) * kDecPad + o);
+  }
+  if (o < 132) st[o] = a.th ? a.th[(size_t)b * a.th_stride + o] : a.init_pose[o];                   // model_hmr.py:116-119
+  else if (o < 142) st[o] = a.sh ? a.sh[(size_t)b * a.sh_stride + (o - 132)] : a.init_shape[o - 132];
+  else if (o < kDec) st[o] = a.cam ? a.cam[(size_t)b * a.cam_stride + (o - 142)] : a.init_cam[o - 142];
+  else st[o] = 0.f;
+  __syncthreads();
+  const float* gu = a.GuT + o;
+  for (int it = 0; it < a.iters; ++it) {
+    float d = base;
+    if (o < kDec) {
+#pragma unroll 5
+      for (int k = 0; k < kDec; ++k) d = fmaf(__ldg(gu + (size_t)k * kDecPad), st[k], d);
+    }
+    __syncthreads();
+    if (o < kDec) st[o] += d;               // pred = decoder output + previous (:168-170)
+    __syncthreads();
+  }
+  if (o < 132) a.out_pose[(size_t)b * 132 + o] = st[o];
+  else if (o < 142) a.out_betas[(size_t)b * 10 + (o - 132)] = st[o];
+  else if (o < kDec) a.out_cam[(size_t)b * 3 + (o - 142)] = st[o];
+}
+
+static int ief_state_create(IefState& s, int state_width) {
   AP_CHECK_CUDA(cudaMalloc((void**)&s.GxT, (size_t)kFeat * kDecPad * sizeof(float)));
-  AP_CHECK_CUDA(cudaMalloc((void**)&s.GuT, (size_t)kState * kDecPad * sizeof(float)));
+  AP_CHECK_CUDA(cudaMalloc((void**)&s.GuT, (size_t)state_width * kDecPad * sizeof(float)));
   AP_CHECK_CUDA(cudaMalloc((void**)&s.g, kDecPad * sizeof(float)));
   AP_CHECK_CUDA(cudaMalloc((void**)&s.T, (size_t)kDec * kHid * sizeof(double)));
+  AP_CHECK_CUDA(cudaMalloc((void**)&s.wdec, (size_t)kDec * kHid * sizeof(float)));
+  AP_CHECK_CUDA(cudaMalloc((void**)&s.bdec, kDec * sizeof(float)));
   AP_CHECK_CUDA(cudaMalloc((void**)&s.init_pose, 144 * sizeof(float)));
   AP_CHECK_CUDA(cudaMalloc((void**)&s.init_shape, 10 * sizeof(float)));
+  AP_CHECK_CUDA(cudaMalloc((void**)&s.init_cam, 3 * sizeof(float)));
   AP_CHECK_CUDA(cudaMemset(s.GxT, 0, (size_t)kFeat * kDecPad * sizeof(float)));
-  AP_CHECK_CUDA(cudaMemset(s.GuT, 0, (size_t)kState * kDecPad * sizeof(float)));
+  AP_CHECK_CUDA(cudaMemset(s.GuT, 0, (size_t)state_width * kDecPad * sizeof(float)));
   return 0;
 }
 
-void ief_destroy(airpose_net* h) {
-  IefState& s = h->ief;
-  void* ptrs[] = {s.GxT, s.GuT, s.g, s.T, s.init_pose, s.init_shape, s.partial};
+static void ief_state_destroy(IefState& s) {
+  void* ptrs[] = {s.GxT, s.GuT, s.g, s.T, s.wdec, s.bdec, s.init_pose, s.init_shape, s.init_cam, s.partial};
   for (void* p : ptrs) cudaFree(p);
   s = IefState();
+}
+
+// Wdec / bdec from up to three decoders, then G = Wdec W2 W1 and g (fp64 accumulation)
+struct DecPart { const float* w; const float* b; int rows; };
+static int ief_fold(IefState& s, const DecPart* parts, int nparts, const float* fc1_w, const float* fc1_b, int state_width,
+                    const float* fc2_w, const float* fc2_b, cudaStream_t st) {
+  int row = 0;
+  for (int i = 0; i < nparts; ++i) {
+    AP_CHECK_CUDA(cudaMemcpyAsync(s.wdec + (size_t)row * kHid, parts[i].w, (size_t)parts[i].rows * kHid * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, st));
+    AP_CHECK_CUDA(cudaMemcpyAsync(s.bdec + row, parts[i].b, parts[i].rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    row += parts[i].rows;
+  }
+  AP_REQUIRE(row == kDec, "ief_fold: decoders have %d rows, expected %d", row, kDec);
+  const int fc1_in = kFeat + state_width;
+  ief_fold_t_kernel<<<dim3(ceil_div(kHid, 128), kDec), 128, 0, st>>>(s.wdec, fc2_w, s.T);
+  AP_LAUNCH_CHECK();
+  ief_fold_g_kernel<<<dim3(ceil_div(fc1_in, 128), kDec), 128, 0, st>>>(s.T, fc1_w, fc1_in, s.GxT, s.GuT);
+  AP_LAUNCH_CHECK();
+  ief_fold_bias_kernel<<<1, kDecPad, 0, st>>>(s.T, fc1_b, s.wdec, fc2_b, s.bdec, s.g);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+static int ensure_partial(IefState& s, int rows, cudaStream_t st) {
+  if (rows > s.partial_rows) {
+    AP_CHECK_CUDA(cudaStreamSynchronize(st));
+    cudaFree(s.partial);
+    s.partial = nullptr; s.partial_rows = 0;
+    AP_CHECK_CUDA(cudaMalloc((void**)&s.partial, (size_t)kIefKSlices * rows * kDecPad * sizeof(float)));
+    s.partial_rows = rows;
+  }
+  return 0;
+}
+
+int ief_create(airpose_net* h) {
+  if (ief_state_create(h->ief, kState)) return 1;
+  return ief_state_create(h->ief_hmr, kDec);
+}
+
+void ief_destroy(airpose_net* h) {
+  ief_state_destroy(h->ief);
+  ief_state_destroy(h->ief_hmr);
 }
 
 int ief_load(airpose_net* h, const airpose_net_params* p, cudaStream_t st) {
   AP_REQUIRE(p->fc1_w && p->fc1_b && p->fc2_w && p->fc2_b && p->decpose_w && p->decpose_b && p->decshape_w &&
              p->decshape_b && p->init_pose && p->init_shape, "airpose_net_load: regressor parameter is null");
   IefState& s = h->ief;
-  ief_fold_t_kernel<<<dim3(ceil_div(kHid, 128), kDec), 128, 0, st>>>(p->decpose_w, p->decshape_w, p->fc2_w, s.T);
-  AP_LAUNCH_CHECK();
-  ief_fold_g_kernel<<<dim3(ceil_div(kFeat + kState, 128), kDec), 128, 0, st>>>(s.T, p->fc1_w, s.GxT, s.GuT);
-  AP_LAUNCH_CHECK();
-  ief_fold_bias_kernel<<<1, kDecPad, 0, st>>>(s.T, p->fc1_b, p->decpose_w, p->decshape_w, p->fc2_b, p->decpose_b,
-                                              p->decshape_b, s.g);
-  AP_LAUNCH_CHECK();
+  const DecPart parts[2] = {{p->decpose_w, p->decpose_b, 135}, {p->decshape_w, p->decshape_b, 10}};
+  if (ief_fold(s, parts, 2, p->fc1_w, p->fc1_b, kState, p->fc2_w, p->fc2_b, st)) return 1;
   AP_CHECK_CUDA(cudaMemcpyAsync(s.init_pose, p->init_pose, 144 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   AP_CHECK_CUDA(cudaMemcpyAsync(s.init_shape, p->init_shape, 10 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return 0;
 }
+
+int ief_load_hmr(airpose_net* h, const airpose_hmr_params* p, cudaStream_t st) {
+  AP_REQUIRE(p->fc1_w && p->fc1_b && p->fc2_w && p->fc2_b && p->decpose_w && p->decpose_b && p->decshape_w &&
+             p->decshape_b && p->deccam_w && p->deccam_b && p->init_pose && p->init_shape && p->init_cam,
+             "airpose_hmr_load: regressor parameter is null");
+  IefState& s = h->ief_hmr;
+  const DecPart parts[3] = {{p->decpose_w, p->decpose_b, 132}, {p->decshape_w, p->decshape_b, 10}, {p->deccam_w, p->deccam_b, 3}};
+  if (ief_fold(s, parts, 3, p->fc1_w, p->fc1_b, kDec, p->fc2_w, p->fc2_b, st)) return 1;
+  AP_CHECK_CUDA(cudaMemcpyAsync(s.init_pose, p->init_pose, 144 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  AP_CHECK_CUDA(cudaMemcpyAsync(s.init_shape, p->init_shape, 10 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  AP_CHECK_CUDA(cudaMemcpyAsync(s.init_cam, p->init_cam, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
 
 }  // namespace airpose
 
@@ -195,7 +312,7 @@ using namespace airpose;
 
 extern "C" int airpose_ief_fwd(airpose_net_t* h, const airpose_ief_args* a, void* stream_) {
   AP_REQUIRE(h && a, "airpose_ief_fwd: null argument");
-  AP_REQUIRE(h->loaded, "airpose_ief_fwd: weights not loaded (call airpose_net_load)");
+  AP_REQUIRE(h->loaded && !h->hmr_loaded, "airpose_ief_fwd: two-view weights not loaded (call airpose_net_load)");
   AP_REQUIRE(a->batch >= 0 && a->iters >= 1, "airpose_ief_fwd: bad batch/iters");
   AP_REQUIRE(a->xf0 && a->xf1 && a->bb0 && a->bb1 && a->pos0 && a->pos1 && a->out_pose0 && a->out_pose1 &&
              a->out_betas0 && a->out_betas1, "airpose_ief_fwd: null tensor");
@@ -205,13 +322,7 @@ extern "C" int airpose_ief_fwd(airpose_net_t* h, const airpose_ief_args* a, void
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream_;
   IefState& s = h->ief;
-  if (M > s.partial_rows) {
-    AP_CHECK_CUDA(cudaStreamSynchronize(st));
-    cudaFree(s.partial);
-    s.partial = nullptr; s.partial_rows = 0;
-    AP_CHECK_CUDA(cudaMalloc((void**)&s.partial, (size_t)kIefKSlices * M * kDecPad * sizeof(float)));
-    s.partial_rows = M;
-  }
+  if (ensure_partial(s, M, st)) return 1;
   ief_base_kernel<<<dim3(ceil_div(M, kIefRows), kIefKSlices), kDecPad, 0, st>>>(B, a->xf0, a->xf1, s.GxT, s.partial);
   AP_LAUNCH_CHECK();
   IefIterArgs k{};
@@ -223,6 +334,32 @@ extern "C" int airpose_ief_fwd(airpose_net_t* h, const airpose_ief_args* a, void
   k.partial = s.partial; k.GuT = s.GuT; k.g = s.g;
   k.out_pose0 = a->out_pose0; k.out_betas0 = a->out_betas0; k.out_pose1 = a->out_pose1; k.out_betas1 = a->out_betas1;
   ief_iter_kernel<<<B, 2 * kDecPad, 0, st>>>(k);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int airpose_hmr_ief_fwd(airpose_net_t* h, const airpose_hmr_ief_args* a, void* stream_) {
+  AP_REQUIRE(h && a, "airpose_hmr_ief_fwd: null argument");
+  AP_REQUIRE(h->hmr_loaded, "airpose_hmr_ief_fwd: hmr weights not loaded (call airpose_hmr_load)");
+  AP_REQUIRE(a->batch >= 0 && a->iters >= 1, "airpose_hmr_ief_fwd: bad batch/iters");
+  AP_REQUIRE(a->xf && a->out_pose && a->out_betas && a->out_cam, "airpose_hmr_ief_fwd: null tensor");
+  const int B = a->batch;
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream_;
+  IefState& s = h->ief_hmr;
+  if (ensure_partial(s, B, st)) return 1;
+  // base product: the two-view kernel with "view 1" empty (rows [0,B) come from xf)
+  ief_base_rows_kernel<<<dim3(ceil_div(B, kIefRows), kIefKSlices), kDecPad, 0, st>>>(B, a->xf, s.GxT, s.partial);
+  AP_LAUNCH_CHECK();
+  HmrIterArgs k{};
+  k.B = B; k.iters = a->iters;
+  k.th = a->init_theta; k.th_stride = a->init_theta_stride;
+  k.sh = a->init_shape; k.sh_stride = a->init_shape_stride;
+  k.cam = a->init_cam; k.cam_stride = a->init_cam_stride;
+  k.init_pose = s.init_pose; k.init_shape = s.init_shape; k.init_cam = s.init_cam;
+  k.partial = s.partial; k.GuT = s.GuT; k.g = s.g;
+  k.out_pose = a->out_pose; k.out_betas = a->out_betas; k.out_cam = a->out_cam;
+  hmr_iter_kernel<<<B, kDecPad, 0, st>>>(k);
   AP_LAUNCH_CHECK();
   return 0;
 }

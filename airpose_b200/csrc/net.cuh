@@ -26,8 +26,11 @@ struct IefState {
   float* GuT = nullptr;        // [284][160]   columns of G that multiply the iterated state
   float* g = nullptr;          // [160]        Wdec (W2 b1 + b2) + bdec
   double* T = nullptr;         // [145][1024]  Wdec * W2 (load-time scratch, fp64)
+  float* wdec = nullptr;       // [145][1024] the decoders, concatenated at load
+  float* bdec = nullptr;       // [145]
   float* init_pose = nullptr;  // [144]
   float* init_shape = nullptr; // [10]
+  float* init_cam = nullptr;   // [3]   (hmr only)
   float* partial = nullptr;    // [kIefKSlices][rows][160] split-K partials of GxT . xf
   int partial_rows = 0;
 };
@@ -42,7 +45,9 @@ struct airpose_net {
   std::vector<airpose::ConvSpec> specs;
   std::vector<__nv_bfloat16*> wq;       // packed conv weights
   std::vector<float*> scale, shift;     // folded BN
-  airpose::IefState ief;
+  airpose::IefState ief;                // two-view regressor (model_copenet.py)
+  airpose::IefState ief_hmr;            // single-view hmr regressor (model_hmr.py)
+  bool hmr_loaded = false;
   // workspaces
   __nv_bfloat16* col = nullptr;         // packed stem operand
   __nv_bfloat16* stem_out = nullptr;
@@ -57,4 +62,5 @@ namespace airpose {
 int ief_create(airpose_net* h);
 void ief_destroy(airpose_net* h);
 int ief_load(airpose_net* h, const airpose_net_params* p, cudaStream_t st);
+int ief_load_hmr(airpose_net* h, const airpose_hmr_params* p, cudaStream_t st);
 }  // namespace airpose

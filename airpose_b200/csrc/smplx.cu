@@ -288,6 +288,7 @@ struct JointArgs {
   const float* root_t; int root_t_stride;
   float fx, fy;
   const float* center; int center_stride;
+  const float* proj_t; int proj_t_stride;
   float* joints; float* joints_cam; float* j2d;
 };
 
@@ -327,12 +328,17 @@ __global__ void __launch_bounds__(128) smplx_joints_kernel(SmplxDev m, JointArgs
         float* oc = a.joints_cam + ((size_t)b * nj + i) * 3;
         oc[0] = cx; oc[1] = cy; oc[2] = cz;
       }
-      if (a.j2d) {   // perspective_projection (geometry.py:63-91) with rotation = I, translation = 0
+      if (a.j2d) {   // perspective_projection (geometry.py:63-91) with rotation = I, translation = proj_t (or 0)
         const float px = a.center ? a.center[(size_t)b * a.center_stride] : 0.f;
         const float py = a.center ? a.center[(size_t)b * a.center_stride + 1] : 0.f;
+        float qx = cx, qy = cy, qz = cz;
+        if (a.proj_t) {
+          const float* pt = a.proj_t + (size_t)b * a.proj_t_stride;
+          qx += pt[0]; qy += pt[1]; qz += pt[2];
+        }
         float* o2 = a.j2d + ((size_t)b * nj + i) * 2;
-        o2[0] = fmaf(a.fx, cx / cz, px);
-        o2[1] = fmaf(a.fy, cy / cz, py);
+        o2[0] = fmaf(a.fx, qx / qz, px);
+        o2[1] = fmaf(a.fy, qy / qz, py);
       }
     }
   }
@@ -559,6 +565,7 @@ extern "C" int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_arg
   ja.root_R = g->root_R; ja.root_R_stride = g->root_R_stride;
   ja.root_t = g->root_t; ja.root_t_stride = g->root_t_stride;
   ja.fx = g->focal_x; ja.fy = g->focal_y; ja.center = g->center; ja.center_stride = g->center_stride;
+  ja.proj_t = g->proj_t; ja.proj_t_stride = g->proj_t_stride;
   ja.joints = g->out_joints; ja.joints_cam = g->out_joints_cam; ja.j2d = g->out_joints_2d;
   smplx_joints_kernel<<<B, 128, 0, stream>>>(d, ja);
   AP_LAUNCH_CHECK();

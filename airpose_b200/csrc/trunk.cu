@@ -203,22 +203,39 @@ extern "C" int airpose_net_destroy(airpose_net_t* h) {
   return 0;
 }
 
-extern "C" int airpose_net_load(airpose_net_t* h, const airpose_net_params* p, void* stream_) {
-  AP_REQUIRE(h && p, "airpose_net_load: null argument");
-  cudaStream_t st = (cudaStream_t)stream_;
+static int load_trunk(airpose_net_t* h, const airpose_conv_params* conv, float bn_eps, cudaStream_t st) {
   for (size_t i = 0; i < h->specs.size(); ++i) {
     const ConvSpec& s = h->specs[i];
-    const airpose_conv_params& c = p->conv[i];
+    const airpose_conv_params& c = conv[i];
     AP_REQUIRE(c.weight && c.bn_weight && c.bn_bias && c.bn_mean && c.bn_var, "airpose_net_load: conv %zu has a null parameter", i);
     const int kpad = (i == 0) ? kStemK : s.k * s.k * s.cin;
     pack_conv_weight_kernel<<<256, 256, 0, st>>>(c.weight, h->wq[i], s.cout, s.cin, s.k, kpad, i == 0);
     AP_LAUNCH_CHECK();
-    fold_bn_kernel<<<ceil_div(s.cout, 256), 256, 0, st>>>(c.bn_weight, c.bn_bias, c.bn_mean, c.bn_var, p->bn_eps, s.cout,
+    fold_bn_kernel<<<ceil_div(s.cout, 256), 256, 0, st>>>(c.bn_weight, c.bn_bias, c.bn_mean, c.bn_var, bn_eps, s.cout,
                                                           h->scale[i], h->shift[i]);
     AP_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+extern "C" int airpose_net_load(airpose_net_t* h, const airpose_net_params* p, void* stream_) {
+  AP_REQUIRE(h && p, "airpose_net_load: null argument");
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (load_trunk(h, p->conv, p->bn_eps, st)) return 1;
   if (ief_load(h, p, st)) return 1;
   h->loaded = true;
+  h->hmr_loaded = false;
+  return 0;
+}
+
+// Same trunk, the single-view hmr regressor (model_hmr.py:48-92).
+extern "C" int airpose_hmr_load(airpose_net_t* h, const airpose_hmr_params* p, void* stream_) {
+  AP_REQUIRE(h && p, "airpose_hmr_load: null argument");
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (load_trunk(h, p->conv, p->bn_eps, st)) return 1;
+  if (ief_load_hmr(h, p, st)) return 1;
+  h->loaded = true;          // the trunk entry points work with either regressor
+  h->hmr_loaded = true;
   return 0;
 }
 

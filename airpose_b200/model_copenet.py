@@ -48,6 +48,9 @@ class Bottleneck(nn.Module):
 
 
 class copenet(nn.Module):
+    FC1_EXTRA = 3 + 3 + 6 + 21 * 6 + 10 + 21 * 6 + 10      # model_copenet.py:67 (bb, position, orient, art, shape, other view's art, shape)
+    NPOSE_OUT = 3 + 6 + 21 * 6                              # decpose rows (:71)
+
     def __init__(self, block, layers, smpl_mean_params):
         super().__init__()
         if list(layers) != [3, 4, 6, 3] or block is not Bottleneck:
@@ -63,11 +66,11 @@ class copenet(nn.Module):
         self.layer3 = self._make_layer(block, 256, layers[2], stride=2)
         self.layer4 = self._make_layer(block, 512, layers[3], stride=2)
         self.avgpool = nn.AvgPool2d(7, stride=1)
-        self.fc1 = nn.Linear(512 * block.expansion + 3 + 3 + 6 + npose + 10 + npose + 10, 1024)
+        self.fc1 = nn.Linear(512 * block.expansion + self.FC1_EXTRA, 1024)
         self.drop1 = nn.Dropout()
         self.fc2 = nn.Linear(1024, 1024)
         self.drop2 = nn.Dropout()
-        self.decpose = nn.Linear(1024, 3 + 6 + npose)
+        self.decpose = nn.Linear(1024, self.NPOSE_OUT)
         self.decshape = nn.Linear(1024, 10)
         self.deccam = nn.Linear(1024, 3)
         for dec in (self.decpose, self.decshape, self.deccam):
@@ -138,23 +141,29 @@ class copenet(nn.Module):
             for t in ts:
                 if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
                     raise _lib.AirposeError("copenet parameters must be contiguous float32 tensors on {}".format(device))
-            p = _lib.NetParams()
-            for i, (conv, bn) in enumerate(self._conv_bn_pairs()):
-                p.conv[i].weight = conv.weight.data_ptr()
-                p.conv[i].bn_weight = bn.weight.data_ptr()
-                p.conv[i].bn_bias = bn.bias.data_ptr()
-                p.conv[i].bn_mean = bn.running_mean.data_ptr()
-                p.conv[i].bn_var = bn.running_var.data_ptr()
-            p.fc1_w, p.fc1_b = self.fc1.weight.data_ptr(), self.fc1.bias.data_ptr()
-            p.fc2_w, p.fc2_b = self.fc2.weight.data_ptr(), self.fc2.bias.data_ptr()
-            p.decpose_w, p.decpose_b = self.decpose.weight.data_ptr(), self.decpose.bias.data_ptr()
-            p.decshape_w, p.decshape_b = self.decshape.weight.data_ptr(), self.decshape.bias.data_ptr()
-            p.init_pose, p.init_shape = self.init_pose.data_ptr(), self.init_shape.data_ptr()
-            p.bn_eps = float(self.bn1.eps)
             with torch.cuda.device(device):
-                _lib.check(lib.airpose_net_load(self._handle, C.byref(p), _lib.current_stream()), "airpose_net_load")
+                self._load_native(lib)
             self._loaded_key = key
         return lib, self._handle
+
+    def _fill_common(self, p):
+        for i, (conv, bn) in enumerate(self._conv_bn_pairs()):
+            p.conv[i].weight = conv.weight.data_ptr()
+            p.conv[i].bn_weight = bn.weight.data_ptr()
+            p.conv[i].bn_bias = bn.bias.data_ptr()
+            p.conv[i].bn_mean = bn.running_mean.data_ptr()
+            p.conv[i].bn_var = bn.running_var.data_ptr()
+        p.fc1_w, p.fc1_b = self.fc1.weight.data_ptr(), self.fc1.bias.data_ptr()
+        p.fc2_w, p.fc2_b = self.fc2.weight.data_ptr(), self.fc2.bias.data_ptr()
+        p.decpose_w, p.decpose_b = self.decpose.weight.data_ptr(), self.decpose.bias.data_ptr()
+        p.decshape_w, p.decshape_b = self.decshape.weight.data_ptr(), self.decshape.bias.data_ptr()
+        p.init_pose, p.init_shape = self.init_pose.data_ptr(), self.init_shape.data_ptr()
+        p.bn_eps = float(self.bn1.eps)
+        return p
+
+    def _load_native(self, lib):
+        p = self._fill_common(_lib.NetParams())
+        _lib.check(lib.airpose_net_load(self._handle, C.byref(p), _lib.current_stream()), "airpose_net_load")
 
     def _release(self):
         if getattr(self, "_handle", None) is not None:

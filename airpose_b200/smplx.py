@@ -230,10 +230,10 @@ class SMPLX(nn.Module):
     def forward_camera(self, betas=None, global_orient=None, body_pose=None, left_hand_pose=None,
                        right_hand_pose=None, transl=None, expression=None, jaw_pose=None, leye_pose=None,
                        reye_pose=None, return_verts=True, return_full_pose=False, pose2rot=True,
-                       root_R=None, root_t=None, focal_length=None, camera_center=None):
+                       root_R=None, root_t=None, focal_length=None, camera_center=None, proj_translation=None):
         """``forward`` plus, fused into the same kernels, ``transform_smpl`` (utils/utils.py:237-256;
         ``root_R`` [B,3,3], ``root_t`` [B,3]) and ``perspective_projection`` (utils/geometry.py:63-91;
-        ``focal_length`` pair, ``camera_center`` [B,2]).  Returns (ModelOutput, dict of camera outputs)."""
+        ``focal_length`` pair, ``camera_center`` [B,2], ``proj_translation`` [B,3] = its ``translation``).  Returns (ModelOutput, dict of camera outputs)."""
         if pose2rot:
             raise NotImplementedError("airpose_b200.SMPLX implements the rotation-matrix path only: pass pose2rot=False")
         if self.joint_mapper is not None:
@@ -316,6 +316,8 @@ class SMPLX(nn.Module):
             a.focal_x, a.focal_y = float(focal_length[0]), float(focal_length[1])
             if camera_center is not None:
                 cc = self._f32c(camera_center, device).reshape(B, 2); a.center = cc.data_ptr(); a.center_stride = 2; keep.append(cc)
+            if proj_translation is not None:
+                pt = self._f32c(proj_translation, device).reshape(B, 3); a.proj_t = pt.data_ptr(); a.proj_t_stride = 3; keep.append(pt)
             cam["joints_2d"] = torch.empty(B, nj, 2, device=device, dtype=torch.float32)
             a.out_joints_2d = cam["joints_2d"].data_ptr()
         a.out_vertices = vertices.data_ptr()

@@ -204,8 +204,12 @@ def conv_specs():
             inplanes = planes * 4
 
 
-def make_network_state(seed: int = 123, dec_gain: float = 0.25, mean_seed: int = 1) -> dict:
-    """Random copenet state_dict (numpy arrays, reference key names).
+FC1_IN_HMR = 2048 + 22 * 6 + 10 + 3                          # 2193, model_hmr.py:66
+
+
+def make_network_state(seed: int = 123, dec_gain: float = 0.25, mean_seed: int = 1, variant: str = "twoview") -> dict:
+    """Random copenet state_dict (numpy arrays, reference key names).  ``variant="hmr"`` gives the
+    single-view model of model_hmr.py (fc1 in 2193, decpose 132 rows; same trunk draw as "twoview").
 
     Conv init is the reference's He fan-out normal (model_copenet.py:78-81).  BN running
     statistics and affine parameters are randomised and the decoder gains raised as
@@ -235,9 +239,10 @@ def make_network_state(seed: int = 123, dec_gain: float = 0.25, mean_seed: int =
         sd[name + ".weight"] = rng.uniform(-bound_w, bound_w, size=(cout, cin)).astype(np.float32)
         sd[name + ".bias"] = rng.uniform(-bound_b, bound_b, size=cout).astype(np.float32)
 
-    linear("fc1", 1024, FC1_IN, 1.0 / np.sqrt(FC1_IN), 1.0 / np.sqrt(FC1_IN))
+    fc1_in = FC1_IN if variant == "twoview" else FC1_IN_HMR
+    linear("fc1", 1024, fc1_in, 1.0 / np.sqrt(fc1_in), 1.0 / np.sqrt(fc1_in))
     linear("fc2", 1024, 1024, 1.0 / 32.0, 1.0 / 32.0)
-    for name, cout in (("decpose", 3 + 6 + NPOSE), ("decshape", 10), ("deccam", 3)):
+    for name, cout in (("decpose", 3 + 6 + NPOSE if variant == "twoview" else 22 * 6), ("decshape", 10), ("deccam", 3)):
         bound = dec_gain * np.sqrt(6.0 / (1024 + cout))
         linear(name, cout, 1024, bound, 1.0 / 32.0)
 

@@ -95,6 +95,9 @@ typedef struct {
   float* out_vertices_cam;       /* [B,V,3]   or NULL */
   float* out_joints_cam;         /* [B,127,3] or NULL */
   float* out_joints_2d;          /* [B,127,2] or NULL */
+  const float* proj_t;           /* [B,3] or NULL: `translation` of perspective_projection (geometry.py:63-91), added
+                                    to the camera-frame joints for the projection only (hmr.py:149-158) */
+  int32_t proj_t_stride;
 } airpose_smplx_fwd_args;
 
 int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_args* args, void* stream);
@@ -172,6 +175,40 @@ typedef struct {
   float* out_pose0; float* out_betas0; float* out_pose1; float* out_betas1;
 } airpose_ief_args;
 int airpose_ief_fwd(airpose_net_t* h, const airpose_ief_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * hmr baseline: single view, same trunk  (copenet/src/copenet/models/model_hmr.py:48-172; BASELINE config 1)
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  airpose_conv_params conv[53];
+  const float* fc1_w;  const float* fc1_b;          /* [1024,2193], [1024]   2193 = 2048 + 132 + 10 + 3 (:66) */
+  const float* fc2_w;  const float* fc2_b;          /* [1024,1024], [1024] */
+  const float* decpose_w;  const float* decpose_b;  /* [132,1024], [132] */
+  const float* decshape_w; const float* decshape_b; /* [10,1024], [10] */
+  const float* deccam_w;   const float* deccam_b;   /* [3,1024], [3] */
+  const float* init_pose;                           /* [144], the first 132 are used (:117) */
+  const float* init_shape;                          /* [10] */
+  const float* init_cam;                            /* [3] */
+  float bn_eps;
+} airpose_hmr_params;
+/* Loads the trunk and the hmr regressor into a handle made by airpose_net_create (the trunk entry points
+ * airpose_backbone_fwd* then serve model_hmr.forward_feat_ext :143-158). */
+int airpose_hmr_load(airpose_net_t* h, const airpose_hmr_params* p, void* stream);
+
+/* The regressor loop of model_hmr.copenet.forward (:112-141, forward_reg :160-172), eval mode, collapsed to one
+ * affine map per iteration like airpose_ief_fwd.  xf [B,2048]; init_theta [B,>=132] / init_shape [B,10] /
+ * init_cam [B,3] or NULL (module buffers).  Outputs pred_pose [B,132] (6D, before rot6d_to_rotmat :140),
+ * pred_betas [B,10], pred_cam [B,3]. */
+typedef struct {
+  int32_t batch;
+  int32_t iters;
+  const float* xf;
+  const float* init_theta; int32_t init_theta_stride;
+  const float* init_shape; int32_t init_shape_stride;
+  const float* init_cam;   int32_t init_cam_stride;
+  float* out_pose; float* out_betas; float* out_cam;
+} airpose_hmr_ief_args;
+int airpose_hmr_ief_fwd(airpose_net_t* h, const airpose_hmr_ief_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * training-step loss  (copenet/src/copenet/copenet_twoview.py:83-161, get_loss)

@@ -148,6 +148,44 @@ def copenet_forward(sd, x0, x1, bb0, bb1, init_position0, init_position1, iters=
 
 
 # --------------------------------------------------------------------------------------
+# hmr baseline: copenet/src/copenet/models/model_hmr.py:112-172, copenet/src/copenet/hmr.py:127-158
+# --------------------------------------------------------------------------------------
+
+def hmr_forward_reg(sd, xf, pose, shape, cam):
+    """model_hmr.copenet.forward_reg in eval mode (model_hmr.py:160-172)."""
+    xc = np.concatenate([xf, pose, shape, cam], axis=1)
+    xc = linear(linear(xc, sd, "fc1"), sd, "fc2")
+    return (linear(xc, sd, "decpose") + pose, linear(xc, sd, "decshape") + shape, linear(xc, sd, "deccam") + cam)
+
+
+def hmr_forward(sd, x, iters=3, bf16=False, feats=None):
+    """model_hmr.copenet.forward (model_hmr.py:112-141): returns (rotmat [B,22,3,3], betas, cam, pose6d)."""
+    xf = forward_feat_ext(x, sd, bf16) if feats is None else feats
+    b = xf.shape[0]
+    pose = np.broadcast_to(sd["init_pose"][:, :22 * 6], (b, 132))
+    shape = np.broadcast_to(sd["init_shape"], (b, 10))
+    cam = np.broadcast_to(sd["init_cam"], (b, 3))
+    for _ in range(int(iters)):
+        pose, shape, cam = hmr_forward_reg(sd, xf, pose, shape, cam)
+    pose, shape, cam = pose.astype(np.float32), shape.astype(np.float32), cam.astype(np.float32)
+    return rot6d_to_rotmat(pose).reshape(b, 22, 3, 3), shape, cam, pose
+
+
+def hmr_fwd_pass(sd, m, x, iters=3, bf16=False, feats=None, focal_length=(1475.0, 1475.0), img_res=224):
+    """hmr.fwd_pass_and_loss without the loss (hmr.py:127-158)."""
+    rotmat, betas, cam, pose = hmr_forward(sd, x, iters, bf16, feats)
+    b = rotmat.shape[0]
+    verts, joints = smplx_forward(m, betas, rotmat[:, 1:], transl=np.zeros((b, 3), np.float32))             # :139-143
+    tm = np.concatenate([rotmat[:, 0], np.zeros((b, 3, 1), np.float32)], axis=2)                             # :144
+    pv, pj = transform_smpl(tm, verts, joints)                                                               # :146-148
+    cam_t = np.stack([cam[:, 1], cam[:, 2], np.float32(2 * focal_length[0]) / (np.float32(img_res) * cam[:, 0] + np.float32(1e-9))],
+                     axis=-1).astype(np.float32)                                                              # :149-151
+    j2d = perspective_projection(pj + cam_t[:, None, :], focal_length, np.zeros((b, 2), np.float32))        # :153-157
+    return {"pred_rotmat": rotmat, "pred_betas": betas, "pred_camera": cam, "pred_pose6d": pose, "pred_cam_t": cam_t,
+            "vertices": verts, "joints": joints, "pred_vertices": pv, "pred_joints": pj, "pred_joints_2d_cam": j2d}
+
+
+# --------------------------------------------------------------------------------------
 # geometry: copenet/src/copenet/utils/geometry.py, utils/utils.py
 # --------------------------------------------------------------------------------------
 

@@ -85,3 +85,17 @@ def test_smplx_module_surface(tmp_path):
     assert ModelOutput._fields[:2] == ("vertices", "joints")
     with pytest.raises(NotImplementedError):
         sm.forward(betas=torch.zeros(3, 10), pose2rot=True)
+
+
+def test_hmr_state_dict_keys_match_reference_layout(tmp_path):
+    """model_hmr.getcopenet: fc1 takes 2193 inputs, decpose decodes 132 numbers, same 331 keys."""
+    from airpose_b200.model_hmr import getcopenet
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+    net = getcopenet(mp, pretrained=False)
+    state = synthetic.make_network_state(123, variant="hmr")
+    sd = net.state_dict()
+    assert len(sd) == 331 and set(sd) == set(state)
+    assert tuple(sd["fc1.weight"].shape) == (1024, 2193) and tuple(sd["decpose.weight"].shape) == (132, 1024)
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()}, strict=True)
+    with pytest.raises(_lib.AirposeError):
+        net.eval()(torch.zeros(1, 3, 224, 224))

@@ -505,3 +505,44 @@ def test_loss_and_gradients_match_autograd(tmp_path, smplx_dir, B):
     # deterministic: a second call gives the same bits
     loss2, _, grads2 = _loss_call(mod, gt, pred, with_grads=True)
     assert torch.equal(loss, loss2) and torch.equal(grads["vertices0"], grads2["vertices0"])
+
+
+# ----------------------------------------------------------------------------- hmr (BASELINE config 1)
+def test_hmr_matches_oracle_and_reference_golden(tmp_path, smplx_dir, smplx_oracle):
+    """model_hmr / hmr.fwd_pass on the CUDA path: regressor + SMPL-X + projection against the oracle fed
+    with OUR trunk features (tight), the whole thing against the real reference run with bf16 rounding
+    points (tests/golden/hmr_b2.npz), and the batch-1 case of BASELINE configs[0]."""
+    from argparse import Namespace
+    from conftest import GOLDEN
+    from airpose_b200.hmr import hmr
+    g = dict(np.load(os.path.join(GOLDEN, "hmr_b2.npz")))
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+    mod = hmr(Namespace(smpl_mean_params=mp, smplx_model_dir=smplx_dir, batch_size=2, reg_iters=3))
+    sd = synthetic.make_network_state(int(g["net_seed"]), variant="hmr")
+    mod.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    mod = mod.to(DEV).eval()
+    x = synthetic.make_inputs(2, int(g["in_seed"]))["im0"]
+    out = mod.fwd_pass({"im0": t(x)})
+    xf = mod.model.forward_feat_ext(t(x)).cpu().numpy()
+    assert rel_err(xf, g["bf16/xf"]) < 5e-3                      # two bf16 evaluations of the trunk
+    ref = orc.hmr_fwd_pass(sd, smplx_oracle, x, feats=xf)
+    for k in ("pred_rotmat", "pred_betas", "pred_camera", "pred_cam_t", "pred_vertices", "pred_joints", "pred_joints_2d_cam"):
+        e = rel_err(out[k].cpu().numpy(), ref[k])
+        print("hmr %-20s rel err %.3e" % (k, e))
+        assert e < 1e-3, k                                        # north_star: 1e-3 relative fp32 (measured ~1e-6)
+    assert rel_err(out["pred_output_cam"].vertices.cpu().numpy(), ref["vertices"]) < 1e-3
+    e_ref = np.abs(out["pred_rotmat"].cpu().numpy() - g["bf16/pred_rotmat"]).max()
+    e_j2d = np.abs(out["pred_joints_2d_cam"].cpu().numpy() - g["bf16/pred_joints_2d_cam"]).max()
+    print("hmr vs reference(bf16 points): rotmat max abs %.3e, j2d max abs %.3f px" % (e_ref, e_j2d))
+    assert e_ref < 2e-2 and e_j2d < 5.0
+    # BASELINE configs[0]: batch of ONE image
+    r1, b1, c1 = mod.model(x=t(x[:1]), iters=3)
+    assert rel_err(r1.cpu().numpy(), out["pred_rotmat"][:1].cpu().numpy()) < 2e-3
+    assert rel_err(c1.cpu().numpy(), g["b1/pred_camera"]) < 2e-2
+    # one regressor pass through the public forward_reg == first iteration of the loop
+    p1 = mod.model.forward_reg(t(xf), mod.model.init_pose[:, :132].expand(2, -1), mod.model.init_shape.expand(2, -1),
+                               mod.model.init_cam.expand(2, -1))
+    o1 = orc.hmr_forward_reg(sd, xf, np.broadcast_to(sd["init_pose"][:, :132], (2, 132)), np.broadcast_to(sd["init_shape"], (2, 10)),
+                             np.broadcast_to(sd["init_cam"], (2, 3)))
+    for a, b in zip(p1, o1):
+        assert rel_err(a.cpu().numpy(), b) < 1e-5

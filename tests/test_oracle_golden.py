@@ -1,6 +1,7 @@
 """Pin the numpy oracle against outputs of the real reference (tests/golden, made by
 oracle/gen_golden.py) and against the known-answer identities of SURVEY.md section 8(c)."""
 import numpy as np
+import pytest
 
 import airpose_oracle as orc
 from airpose_b200 import synthetic
@@ -130,3 +131,36 @@ def test_torch_port_matches_reference(net_state, smplx_data, golden_twoview):
         for k in ("pred_pose", "pred_betas", "pred_vertices_cam", "pred_joints_cam", "pred_joints_2d_cam"):
             assert rel_err(out["%s%d" % (k, v)].numpy(), g["fp32/%s%d" % (k, v)]) < 2e-5, k
     assert rel_err(out["xf0"].numpy(), g["fp32/xf0"]) < 1e-5
+
+
+# ----------------------------------------------------------------------------- hmr (BASELINE config 1)
+@pytest.fixture(scope="module")
+def golden_hmr():
+    import os
+    from conftest import GOLDEN
+    return dict(np.load(os.path.join(GOLDEN, "hmr_b2.npz")))
+
+
+def test_hmr_oracle_matches_reference(smplx_oracle, golden_hmr):
+    """The numpy restatement of model_hmr.forward + hmr.fwd_pass against the real reference run
+    (oracle/gen_golden_hmr.py), regressor and geometry fed with the reference's trunk features."""
+    g = golden_hmr
+    sd = synthetic.make_network_state(int(g["net_seed"]), variant="hmr")
+    x = synthetic.make_inputs(2, int(g["in_seed"]))["im0"]
+    out = orc.hmr_fwd_pass(sd, smplx_oracle, x, feats=g["fp32/xf"])
+    for k in ("pred_rotmat", "pred_betas", "pred_camera", "pred_cam_t", "vertices", "joints", "pred_vertices", "pred_joints",
+              "pred_joints_2d_cam"):
+        assert rel_err(out[k], g["fp32/" + k]) < 1e-5, k
+    # config 1 proper: a batch of one image gives the same numbers (eval-mode BatchNorm)
+    one = orc.hmr_forward(sd, x[:1], feats=g["fp32/xf"][:1])
+    assert rel_err(one[0], g["b1/pred_rotmat"]) < 1e-5 and rel_err(one[2], g["b1/pred_camera"]) < 1e-5
+
+
+def test_hmr_trunk_oracle_batch1_cpu(golden_hmr):
+    """BASELINE configs[0] end to end on CPU: trunk (fp32 oracle) + regressor for ONE image."""
+    g = golden_hmr
+    sd = synthetic.make_network_state(int(g["net_seed"]), variant="hmr")
+    x = synthetic.make_inputs(2, int(g["in_seed"]))["im0"][:1]
+    rotmat, betas, cam, _ = orc.hmr_forward(sd, x)
+    assert rel_err(rotmat, g["b1/pred_rotmat"]) < 5e-5
+    assert rel_err(betas, g["b1/pred_betas"]) < 5e-5 and rel_err(cam, g["b1/pred_camera"]) < 5e-5
