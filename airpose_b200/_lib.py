@@ -115,6 +115,12 @@ class LossArgs(C.Structure):
                                            "g_rotmat0", "g_rotmat1", "g_betas0", "g_betas1", "g_trans0", "g_trans1")])
 
 
+class AdamArgs(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("max_exp_avg_sq", C.c_void_p), ("n", C.c_int64), ("lr", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int32), ("grad_scale", C.c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/airpose_b200.h declares
 SYMBOLS = {
     "airpose_last_error": (C.c_char_p, []),
@@ -135,6 +141,7 @@ SYMBOLS = {
     "airpose_ief_fwd": (C.c_int, [C.c_void_p, C.POINTER(IefArgs), C.c_void_p]),
     "airpose_hmr_load": (C.c_int, [C.c_void_p, C.POINTER(HmrParams), C.c_void_p]),
     "airpose_hmr_ief_fwd": (C.c_int, [C.c_void_p, C.POINTER(HmrIefArgs), C.c_void_p]),
+    "airpose_adam_step": (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),
     "airpose_twoview_loss": (C.c_int, [C.POINTER(LossArgs), C.c_void_p]),
     "airpose_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "airpose_conv_bf16": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),

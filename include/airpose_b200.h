@@ -240,6 +240,19 @@ typedef struct {
 } airpose_twoview_loss_args;
 int airpose_twoview_loss(const airpose_twoview_loss_args* a, void* stream);
 
+/* torch.optim.Adam(..., weight_decay=0, amsgrad=True) (copenet_twoview.py:416-425) over a FLAT fp32 buffer:
+ * one launch per step for all 27.1 M parameters.  `step` is the 1-based step count (bias corrections are
+ * formed on the host in fp64 like torch's python scalars).  max_exp_avg_sq = NULL gives plain Adam.
+ * grad_scale (0 = 1) multiplies the gradient on the fly (e.g. 1/world_size after a sum all-reduce). */
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq; float* max_exp_avg_sq;
+  int64_t n;
+  float lr, beta1, beta2, eps;
+  int32_t step;
+  float grad_scale;
+} airpose_adam_args;
+int airpose_adam_step(const airpose_adam_args* a, void* stream);
+
 /* Number of kernels launched by this library since load (bench.py's gpu_launches). */
 int64_t airpose_launch_count(void);
 

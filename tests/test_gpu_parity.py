@@ -546,3 +546,27 @@ def test_hmr_matches_oracle_and_reference_golden(tmp_path, smplx_dir, smplx_orac
                              np.broadcast_to(sd["init_cam"], (2, 3)))
     for a, b in zip(p1, o1):
         assert rel_err(a.cpu().numpy(), b) < 1e-5
+
+
+# ----------------------------------------------------------------------------- optimizer (copenet_twoview.py:416-425)
+@pytest.mark.parametrize("amsgrad", [True, False])
+def test_adam_matches_torch(amsgrad):
+    """airpose_b200.optim.Adam (one launch over a flat buffer) against torch.optim.Adam for 5 steps."""
+    from airpose_b200.optim import Adam
+    g = torch.Generator(device="cpu").manual_seed(3)
+    shapes = [(64, 3, 7, 7), (64,), (1024, 2332), (145,), (3, 5, 7)]
+    ours = [torch.nn.Parameter(torch.randn(*s, generator=g).to(DEV)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ours]
+    opt = Adam(ours, lr=5e-5, amsgrad=amsgrad)
+    topt = torch.optim.Adam(ref, lr=5e-5, weight_decay=0, amsgrad=amsgrad)
+    for step in range(5):
+        opt.zero_grad()
+        for p, r in zip(ours, ref):
+            gr = (torch.randn(p.shape, generator=g) * (10.0 ** (step - 2))).to(DEV)
+            p.grad.copy_(gr)
+            r.grad = gr.clone()
+        opt.step()
+        topt.step()
+    for p, r in zip(ours, ref):
+        assert rel_err(p.detach().cpu().numpy(), r.detach().cpu().numpy()) < 1e-6
+        assert p.data_ptr() >= opt.flat.data_ptr() and p.data_ptr() < opt.flat.data_ptr() + opt.flat.numel() * 4
