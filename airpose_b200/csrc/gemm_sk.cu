@@ -32,6 +32,8 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <utility>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -466,14 +468,14 @@ struct SkWorkspace {
   uint32_t epoch = 0;
   int device = -1;
 };
-SkWorkspace g_ws[16];
+// one workspace per (device, stream): stream-K launches on different streams may run concurrently
+std::map<std::pair<int, cudaStream_t>, SkWorkspace> g_ws;
 constexpr int kMaxMT = 2;
 
-int get_workspace(SkWorkspace** out) {
+int get_workspace(cudaStream_t stream, SkWorkspace** out) {
   int dev = 0;
   AP_CHECK_CUDA(cudaGetDevice(&dev));
-  AP_REQUIRE(dev >= 0 && dev < 16, "gemm_sk: device index %d out of range", dev);
-  SkWorkspace& w = g_ws[dev];
+  SkWorkspace& w = g_ws[std::make_pair(dev, stream)];
   if (!w.ws) {
     AP_CHECK_CUDA(cudaMalloc((void**)&w.ws, (size_t)kMaxGrid * kMaxMT * kBlockM * 256 * sizeof(float)));
     AP_CHECK_CUDA(cudaMalloc((void**)&w.flags, (size_t)kMaxGrid * 2 * sizeof(uint32_t)));
@@ -508,7 +510,7 @@ int launch_bn(const GemmLaunch& L, KP& kp, cudaStream_t stream) {
   const int smem_bytes = 1024 + kp.stages * stage_bytes + (kp.b_res ? b_total : 0) + kEpiGroups * kChunkBytes +
                          kp.res_bufs * kChunkBytes + kBarBytes;
   SkWorkspace* w = nullptr;
-  if (get_workspace(&w)) return 1;
+  if (get_workspace(stream, &w)) return 1;
   kp.ws = w->ws; kp.flags = w->flags; kp.epoch = ++w->epoch;
   const int units = kp.tiles_m * kp.tiles_n * kp.num_kb;
   cudaLaunchConfig_t cfg{};

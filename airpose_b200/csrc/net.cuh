@@ -49,12 +49,18 @@ struct airpose_net {
   airpose::IefState ief_hmr;            // single-view hmr regressor (model_hmr.py)
   bool hmr_loaded = false;
   // workspaces
-  __nv_bfloat16* col = nullptr;         // packed stem operand
-  __nv_bfloat16* stem_out = nullptr;
-  __nv_bfloat16* act[4] = {nullptr, nullptr, nullptr, nullptr};    // stage A (stem, layer1, layer2): `chunk` images
+  // stage A (stem, layer1, layer2) works on `chunk` images at a time; consecutive chunks alternate between two
+  // buffer sets and two streams so that one chunk's kernel tails overlap the other's ramp-up (trunk.cu)
+  static constexpr int kSets = 2;
+  __nv_bfloat16* colS[kSets] = {nullptr, nullptr};         // packed stem operand
+  __nv_bfloat16* stem_outS[kSets] = {nullptr, nullptr};
+  __nv_bfloat16* actS[kSets][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int sets = 1;
   __nv_bfloat16* actB[4] = {nullptr, nullptr, nullptr, nullptr};   // stage B (layer3, layer4): `group` images
   int group = 0;
-  std::map<std::pair<int, int>, airpose::TrunkPlan> plansA;        // (images, first image inside the group)
+  std::map<std::pair<int, int>, airpose::TrunkPlan> plansA;        // (images, 2 * first image inside the group + buffer set)
   std::map<int, airpose::TrunkPlan> plansB;                        // images
 };
 

@@ -182,9 +182,18 @@ extern "C" int airpose_net_create(airpose_net_t** out, int max_images, int devic
   }
   if (ief_create(h)) return 1;
   const size_t act_elems = (size_t)h->chunk * 112 * 112 * 64;       // == 56*56*256, the largest activation
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->col, (size_t)h->chunk * 2 * kStemPlaneRows * 112 * kStemTapK * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->stem_out, act_elems * 2));
-  for (int i = 0; i < 4; ++i) AP_CHECK_CUDA(cudaMalloc((void**)&h->act[i], act_elems * 2));
+  // two stage-A buffer sets (and a side stream) only when a call can have more than one chunk
+  h->sets = (max_images > h->chunk && !getenv("AIRPOSE_TRUNK_ONE_STREAM")) ? airpose_net::kSets : 1;
+  for (int s = 0; s < h->sets; ++s) {
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->colS[s], (size_t)h->chunk * 2 * kStemPlaneRows * 112 * kStemTapK * 2));
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->stem_outS[s], act_elems * 2));
+    for (int i = 0; i < 4; ++i) AP_CHECK_CUDA(cudaMalloc((void**)&h->actS[s][i], act_elems * 2));
+  }
+  if (h->sets > 1) {
+    AP_CHECK_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    AP_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    AP_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
   for (int i = 0; i < 4; ++i) AP_CHECK_CUDA(cudaMalloc((void**)&h->actB[i], (size_t)h->group * kStageBElems * 2));
   *out = h;
   return 0;
@@ -197,8 +206,15 @@ extern "C" int airpose_net_destroy(airpose_net_t* h) {
   for (auto p : h->scale) cudaFree(p);
   for (auto p : h->shift) cudaFree(p);
   ief_destroy(h);
-  void* ptrs[] = {h->col, h->stem_out, h->act[0], h->act[1], h->act[2], h->act[3], h->actB[0], h->actB[1], h->actB[2], h->actB[3]};
+  void* ptrs[] = {h->actB[0], h->actB[1], h->actB[2], h->actB[3]};
   for (void* p : ptrs) cudaFree(p);
+  for (int s = 0; s < airpose_net::kSets; ++s) {
+    cudaFree(h->colS[s]); cudaFree(h->stem_outS[s]);
+    for (int i = 0; i < 4; ++i) cudaFree(h->actS[s][i]);
+  }
+  if (h->side_stream) cudaStreamDestroy(h->side_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
   return 0;
 }
@@ -265,7 +281,7 @@ static int conv_launch(airpose_net* h, int idx, const __nv_bfloat16* x, int n, i
   return 0;
 }
 
-static int build_stem_gemm(airpose_net* h, int n, GemmLaunch* Lp) {
+static int build_stem_gemm(airpose_net* h, int n, int set, GemmLaunch* Lp) {
   // stem: 7 k-blocks (one per vertical tap) over the packed operand, BN + ReLU in the epilogue
   GemmLaunch& L = *Lp;
   L.M = n * 112 * 112; L.N = 64; L.K = kStemK; L.block_n = 64;
@@ -277,10 +293,10 @@ static int build_stem_gemm(airpose_net* h, int n, GemmLaunch* Lp) {
     const int cr = (r - 3 - par) / 2;            // exact: r-3-par is even
     L.stem_tap_off[r] = (par * kStemPlaneRows + 2 + cr) * 112;
   }
-  if (make_tmap_tiled_bf16(&L.tmA, h->col, (int64_t)n * 2 * kStemPlaneRows * 112, kStemTapK, kStemTapK, 128, kStemTapK, 64)) return 1;
+  if (make_tmap_tiled_bf16(&L.tmA, h->colS[set], (int64_t)n * 2 * kStemPlaneRows * 112, kStemTapK, kStemTapK, 128, kStemTapK, 64)) return 1;
   if (make_tmap_tiled_bf16(&L.tmB, h->wq[0], 64, kStemK, kStemK, 64, kStemTapK, 64)) return 1;
   L.epi.scale = h->scale[0]; L.epi.shift = h->shift[0]; L.epi.relu = 1;
-  L.epi.out_bf16 = h->stem_out; L.epi.ldd = 64;
+  L.epi.out_bf16 = h->stem_outS[set]; L.epi.ldd = 64;
   return enable_tma_epilogue(&L);
 }
 
@@ -322,13 +338,13 @@ static int build_blocks(airpose_net* h, int n, int l0, int l1, int H, __nv_bfloa
 
 // stage A: stem GEMM + layer1 + layer2 on `n` <= chunk images; output [n,28,28,512] lands at image
 // offset `first` of the stage-B input buffer.
-static int build_plan_a(airpose_net* h, int n, int first, TrunkPlan* plan) {
+static int build_plan_a(airpose_net* h, int n, int first, int set, TrunkPlan* plan) {
   plan->gemms.clear();
   GemmLaunch L{};
-  if (build_stem_gemm(h, n, &L)) return 1;
+  if (build_stem_gemm(h, n, set, &L)) return 1;
   plan->gemms.push_back(L);
   __nv_bfloat16* out = h->actB[0] + (size_t)first * kStageBElems;
-  return build_blocks(h, n, 0, 2, 56, h->act, out, plan);
+  return build_blocks(h, n, 0, 2, 56, h->actS[set], out, plan);
 }
 
 // stage B: layer3 + layer4 on `n` <= group images, input in actB[0].
@@ -337,12 +353,12 @@ static int build_plan_b(airpose_net* h, int n, TrunkPlan* plan) {
   return build_blocks(h, n, 2, 4, 28, h->actB, nullptr, plan);
 }
 
-static int launch_stem_front(airpose_net* h, const float* x, int n, const GemmLaunch& stem, __nv_bfloat16* pooled, cudaStream_t st) {
+static int launch_stem_front(airpose_net* h, const float* x, int n, int set, const GemmLaunch& stem, __nv_bfloat16* pooled, cudaStream_t st) {
   const int64_t work = (int64_t)n * 2 * kStemPlaneRows * 112;
-  stem_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(work, 128), 148 * 32), 128, 0, st>>>(x, n, h->col);
+  stem_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(work, 128), 148 * 32), 128, 0, st>>>(x, n, h->colS[set]);
   AP_LAUNCH_CHECK();
   if (launch_gemm(stem, st)) return 1;
-  maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64((int64_t)n * 56 * 56 * 8, 256), 148 * 16), 256, 0, st>>>(h->stem_out, n, pooled);
+  maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64((int64_t)n * 56 * 56 * 8, 256), 148 * 16), 256, 0, st>>>(h->stem_outS[set], n, pooled);
   AP_LAUNCH_CHECK();
   return 0;
 }
@@ -354,21 +370,37 @@ static int backbone_fwd_segments(airpose_net_t* h, const float* x0, int n0, cons
   auto src = [&](int i) { return i < n0 ? x0 + (size_t)i * img : x1 + (size_t)(i - n0) * img; };
   for (int g0 = 0; g0 < n_images; g0 += h->group) {
     const int ng = std::min(h->group, n_images - g0);
-    for (int i0 = 0, n = 0; i0 < ng; i0 += n) {
+    // Stage A: consecutive chunks alternate between two buffer sets on two streams (fork/join with events).
+    // The kernels are persistent, one CTA per SM, so two of them never share an SM -- but the CTAs of the
+    // second stream's kernel start on every SM the first one's tail has already left, which hides the
+    // ~5 us of ramp-up/drain each launch costs.  Stream order keeps each set's reuse safe.
+    const bool fork = h->sets > 1 && ng > h->chunk;
+    if (fork) {
+      AP_CHECK_CUDA(cudaEventRecord(h->ev_fork, st));
+      AP_CHECK_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    }
+    int chunk_no = 0;
+    for (int i0 = 0, n = 0; i0 < ng; i0 += n, ++chunk_no) {
       n = std::min(h->chunk, ng - i0);
       const int first = g0 + i0;
       if (first < n0 && first + n > n0) n = n0 - first;      // a chunk never straddles the two input tensors
-      auto key = std::make_pair(n, i0);
+      const int set = fork ? (chunk_no & 1) : 0;
+      cudaStream_t cst = set ? h->side_stream : st;
+      auto key = std::make_pair(n, 2 * i0 + set);
       auto it = h->plansA.find(key);
       if (it == h->plansA.end()) {
         TrunkPlan plan;
-        if (build_plan_a(h, n, i0, &plan)) return 1;
+        if (build_plan_a(h, n, i0, set, &plan)) return 1;
         it = h->plansA.emplace(key, std::move(plan)).first;
       }
       const TrunkPlan& plan = it->second;
-      if (launch_stem_front(h, src(first), n, plan.gemms[0], h->act[0], st)) return 1;
+      if (launch_stem_front(h, src(first), n, set, plan.gemms[0], h->actS[set][0], cst)) return 1;
       for (size_t g = 1; g < plan.gemms.size(); ++g)
-        if (launch_gemm(plan.gemms[g], st)) return 1;
+        if (launch_gemm(plan.gemms[g], cst)) return 1;
+    }
+    if (fork) {
+      AP_CHECK_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+      AP_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
     }
     auto it = h->plansB.find(ng);
     if (it == h->plansB.end()) {
@@ -405,6 +437,6 @@ extern "C" int airpose_backbone_stem(airpose_net_t* h, const float* x, int n, vo
   AP_REQUIRE(h->loaded, "airpose_backbone_stem: weights not loaded (call airpose_net_load)");
   AP_REQUIRE(n > 0 && n <= h->chunk, "airpose_backbone_stem: n=%d exceeds the chunk size %d", n, h->chunk);
   GemmLaunch stem{};
-  if (build_stem_gemm(h, n, &stem)) return 1;
-  return launch_stem_front(h, x, n, stem, (__nv_bfloat16*)out, (cudaStream_t)stream_);
+  if (build_stem_gemm(h, n, 0, &stem)) return 1;
+  return launch_stem_front(h, x, n, 0, stem, (__nv_bfloat16*)out, (cudaStream_t)stream_);
 }
