@@ -47,6 +47,21 @@ class SmplxFwdArgs(C.Structure):
                 ("out_joints_2d", C.c_void_p), ("proj_t", C.c_void_p), ("proj_t_stride", C.c_int32)]
 
 
+class SmplxBwdArgs(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("num_betas", C.c_int32),
+                ("betas", C.c_void_p), ("betas_stride", C.c_int32),
+                ("global_orient", C.c_void_p), ("global_orient_stride", C.c_int32),
+                ("body_pose", C.c_void_p), ("body_pose_stride", C.c_int32),
+                ("joints", C.c_void_p),
+                ("root_R", C.c_void_p), ("root_R_stride", C.c_int32),
+                ("root_t", C.c_void_p), ("root_t_stride", C.c_int32),
+                ("focal_x", C.c_float), ("focal_y", C.c_float),
+                ("grad_vertices", C.c_void_p), ("grad_joints", C.c_void_p), ("grad_joints_cam", C.c_void_p),
+                ("grad_joints_2d", C.c_void_p),
+                ("grad_betas", C.c_void_p), ("grad_body_pose", C.c_void_p), ("grad_global_orient", C.c_void_p),
+                ("grad_root_R", C.c_void_p), ("grad_root_t", C.c_void_p)]
+
+
 class ConvParams(C.Structure):
     _fields_ = [("weight", C.c_void_p), ("bn_weight", C.c_void_p), ("bn_bias", C.c_void_p),
                 ("bn_mean", C.c_void_p), ("bn_var", C.c_void_p)]
@@ -130,8 +145,11 @@ SYMBOLS = {
     "airpose_smplx_destroy": (C.c_int, [C.c_void_p]),
     "airpose_smplx_skin_nnz": (C.c_int, [C.c_void_p]),
     "airpose_smplx_fwd": (C.c_int, [C.c_void_p, C.POINTER(SmplxFwdArgs), C.c_void_p]),
+    "airpose_smplx_bwd": (C.c_int, [C.c_void_p, C.POINTER(SmplxBwdArgs), C.c_void_p]),
     "airpose_rot6d_to_rotmat": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "airpose_rot6d_to_rotmat_strided": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "airpose_rot6d_to_rotmat_bwd_strided": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                                      C.c_int64, C.c_void_p]),
     "airpose_j14_gather": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_i32_p, C.c_void_p, C.c_void_p]),
     "airpose_net_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "airpose_net_destroy": (C.c_int, [C.c_void_p]),

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, model_copenet
-from .smplx import SMPLX, rot6d_to_rotmat
+from .smplx import SMPLX, rot6d_to_rotmat, rot6d_to_rotmat_backward, smplx_backward
 
 FOCAL_LENGTH = [1475, 1475]          # copenet/src/copenet/constants.py:7
 TRANS_SCALE = 0.05                   # copenet_twoview.py:199-203
@@ -60,7 +60,7 @@ class copenet_twoview(nn.Module):
         intr = (input_batch["intr0"], input_batch["intr1"])
         B = im0.shape[0]
         dev = im0.device
-        in_trans = torch.tensor([0.0, 0.0, 10.0], device=dev).expand(B, -1).clone() * TRANS_SCALE      # :184-203
+        in_trans = torch.tensor([0.0, 0.0, 10.0], device=dev, dtype=torch.float32).expand(B, -1).clone() * TRANS_SCALE      # :184-203
         reg_iters = getattr(self.hparams, "reg_iters", 3)
         mark("trunk")
         xf = self.model.forward_feat_ext_pair(im0, im1)                         # both views, one call (eval-mode BN)
@@ -136,11 +136,11 @@ class copenet_twoview(nn.Module):
         grads = None
         if with_grads:
             grads = {"vertices0": torch.empty_like(v0), "vertices1": torch.empty_like(v1), "joints0": torch.empty_like(j0),
-                     "joints1": torch.empty_like(j1), "joints_2d0": torch.empty(B, j0.shape[1], 2, device=dev),
-                     "joints_2d1": torch.empty(B, j0.shape[1], 2, device=dev), "rotmat0": torch.empty(B, 22, 3, 3, device=dev),
-                     "rotmat1": torch.empty(B, 22, 3, 3, device=dev), "betas0": torch.empty(B, 10, device=dev),
-                     "betas1": torch.empty(B, 10, device=dev), "smpltrans0": torch.empty(B, 3, device=dev),
-                     "smpltrans1": torch.empty(B, 3, device=dev)}
+                     "joints1": torch.empty_like(j1), "joints_2d0": torch.empty(B, j0.shape[1], 2, device=dev, dtype=torch.float32),
+                     "joints_2d1": torch.empty(B, j0.shape[1], 2, device=dev, dtype=torch.float32), "rotmat0": torch.empty(B, 22, 3, 3, device=dev, dtype=torch.float32),
+                     "rotmat1": torch.empty(B, 22, 3, 3, device=dev, dtype=torch.float32), "betas0": torch.empty(B, 10, device=dev, dtype=torch.float32),
+                     "betas1": torch.empty(B, 10, device=dev, dtype=torch.float32), "smpltrans0": torch.empty(B, 3, device=dev, dtype=torch.float32),
+                     "smpltrans1": torch.empty(B, 3, device=dev, dtype=torch.float32)}
             for field, key in (("g_verts0", "vertices0"), ("g_verts1", "vertices1"), ("g_joints0", "joints0"),
                                ("g_joints1", "joints1"), ("g_j2d0", "joints_2d0"), ("g_j2d1", "joints_2d1"),
                                ("g_rotmat0", "rotmat0"), ("g_rotmat1", "rotmat1"), ("g_betas0", "betas0"),
@@ -168,3 +168,31 @@ class copenet_twoview(nn.Module):
                   "pred_smpltrans0": out["pred_smpltrans0"], "pred_smpltrans1": out["pred_smpltrans1"],
                   "in_smpltrans0": out["in_smpltrans0"], "in_smpltrans1": out["in_smpltrans1"]}
         return output, losses, loss
+
+    @torch.no_grad()
+    def loss_and_head_backward(self, input_batch, out):
+        """get_loss and the backward pass from the loss down to the regressor outputs: d loss / d pred_pose{0,1}
+        [B,135] (as the network returned them, i.e. before the translation un-scaling of :214-218) and
+        d loss / d pred_betas{0,1} [B,10] -- the part of ``loss.backward()`` (copenet_twoview.py:378-386) that runs
+        through get_loss, perspective_projection, transform_smpl, SMPL-X and rot6d_to_rotmat.  ``out`` is the dict
+        ``fwd_pass`` returned.  The backward through the regressor and the trunk is not built yet."""
+        loss, losses, g = self.get_loss(input_batch, out["pred_smpltrans0"], out["pred_smpltrans1"], out["pred_rotmat0"],
+                                        out["pred_rotmat1"], out["pred_betas0"], out["pred_betas1"], out["pred_output_cam0"],
+                                        out["pred_output_cam1"], out["pred_joints_2d_cam0"], out["pred_joints_2d_cam1"],
+                                        with_grads=True)
+        grads = {}
+        for v in (0, 1):
+            rotmat, pose, betas = out["pred_rotmat%d" % v], out["pred_pose%d" % v], out["pred_betas%d" % v]
+            sg = smplx_backward(self.smplx, betas, rotmat[:, 1:], None, grad_vertices=g["vertices%d" % v],
+                                grad_joints=g["joints%d" % v], grad_joints_2d=g["joints_2d%d" % v],
+                                joints=out["pred_output_cam%d" % v].joints, root_R=rotmat[:, 0], root_t=pose[:, :3],
+                                focal_length=self.focal_length)
+            g_rot = g["rotmat%d" % v].clone()
+            g_rot[:, 1:] += sg["body_pose"]
+            g_rot[:, 0] += sg["root_R"]
+            g_pose = torch.empty_like(pose)
+            g_pose[:, 3:] = rot6d_to_rotmat_backward(pose[:, 3:], g_rot.view(-1, 3, 3))
+            g_pose[:, :3] = (g["smpltrans%d" % v] + sg["root_t"]) / TRANS_SCALE          # pose[:, :3] /= trans_scale (:214-218)
+            grads["pred_pose%d" % v] = g_pose
+            grads["pred_betas%d" % v] = g["betas%d" % v] + sg["betas"]
+        return loss, losses, grads

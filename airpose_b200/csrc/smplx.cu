@@ -364,6 +364,40 @@ __global__ void rot6d_kernel(const float* __restrict__ x, int64_t groups, int pe
   o[6] = b1z; o[7] = b2z; o[8] = b3z;
 }
 
+// Backward of rot6d_to_rotmat (geometry.py:47-61): gR [n,3,3] -> gx (6 per rotation, same strided layout as x).
+__global__ void rot6d_bwd_kernel(const float* __restrict__ x, int64_t groups, int per_group, int64_t row_stride,
+                                 const float* __restrict__ gR, float* __restrict__ gx, int64_t gx_row_stride) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * per_group) return;
+  const float* s = x + (i / per_group) * row_stride + (i % per_group) * 6;
+  const float a1[3] = {s[0], s[2], s[4]}, a2[3] = {s[1], s[3], s[5]};
+  const float n1 = fmaxf(sqrtf(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]), 1e-12f);
+  const float b1[3] = {a1[0] / n1, a1[1] / n1, a1[2] / n1};
+  const float d = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
+  const float u[3] = {a2[0] - d * b1[0], a2[1] - d * b1[1], a2[2] - d * b1[2]};
+  const float n2 = fmaxf(sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), 1e-12f);
+  const float b2[3] = {u[0] / n2, u[1] / n2, u[2] / n2};
+  const float* g = gR + i * 9;
+  float gb1[3] = {g[0], g[3], g[6]}, gb2[3] = {g[1], g[4], g[7]};
+  const float gb3[3] = {g[2], g[5], g[8]};
+  // b3 = b1 x b2:  gb1 += b2 x gb3,  gb2 += gb3 x b1
+  gb1[0] += b2[1] * gb3[2] - b2[2] * gb3[1]; gb1[1] += b2[2] * gb3[0] - b2[0] * gb3[2]; gb1[2] += b2[0] * gb3[1] - b2[1] * gb3[0];
+  gb2[0] += gb3[1] * b1[2] - gb3[2] * b1[1]; gb2[1] += gb3[2] * b1[0] - gb3[0] * b1[2]; gb2[2] += gb3[0] * b1[1] - gb3[1] * b1[0];
+  // b2 = u / |u|
+  const float p2 = b2[0] * gb2[0] + b2[1] * gb2[1] + b2[2] * gb2[2];
+  const float gu[3] = {(gb2[0] - b2[0] * p2) / n2, (gb2[1] - b2[1] * p2) / n2, (gb2[2] - b2[2] * p2) / n2};
+  // u = a2 - (b1.a2) b1
+  const float q = gu[0] * b1[0] + gu[1] * b1[1] + gu[2] * b1[2];
+  const float ga2[3] = {gu[0] - q * b1[0], gu[1] - q * b1[1], gu[2] - q * b1[2]};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) gb1[k] -= q * a2[k] + d * gu[k];
+  // b1 = a1 / |a1|
+  const float p1 = b1[0] * gb1[0] + b1[1] * gb1[1] + b1[2] * gb1[2];
+  float* o = gx + (i / per_group) * gx_row_stride + (i % per_group) * 6;
+  o[0] = (gb1[0] - b1[0] * p1) / n1; o[2] = (gb1[1] - b1[1] * p1) / n1; o[4] = (gb1[2] - b1[2] * p1) / n1;
+  o[1] = ga2[0]; o[3] = ga2[1]; o[5] = ga2[2];
+}
+
 __global__ void j14_gather_kernel(const float* __restrict__ joints, int B, int nj, const int* __restrict__ map,
                                   int nmap, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,6 +408,8 @@ __global__ void j14_gather_kernel(const float* __restrict__ joints, int B, int n
 
 }  // namespace airpose
 
+#include "smplx_bwd.inl"
+
 using namespace airpose;
 
 struct airpose_smplx {
@@ -383,6 +419,14 @@ struct airpose_smplx {
   std::vector<void*> owned;
   float* ws = nullptr;
   size_t ws_floats = 0;
+  // backward (smplx_bwd.inl)
+  float* Pt = nullptr;         // [3V][ldq]: posedirs (P columns) then shapedirs (NS columns), vertex-major
+  int ldq = 0;
+  int* xoff = nullptr;         // [V+1] CSR: which extra joints / landmarks gather each vertex ...
+  int* xj = nullptr;           // ... their row in the joints output ...
+  float* xw = nullptr;         // ... and the weight (1 for the vertex-picked joints, barycentric for landmarks)
+  float* bws = nullptr;        // backward workspace
+  size_t bws_floats = 0;
 };
 
 extern "C" int airpose_smplx_create(airpose_smplx_t** out, const airpose_smplx_model_host* mh, int device) {
@@ -470,6 +514,35 @@ extern "C" int airpose_smplx_create(airpose_smplx_t** out, const airpose_smplx_m
 #undef UP_F
 #undef UP_I
   if (smplx_tc_create(mh, d, &h->tc, &h->owned)) return 1;
+  {  // backward constants: [posedirs | shapedirs] vertex-major, and the vertex -> gathered-joint lists
+    h->ldq = (P + NS + 31) / 32 * 32;
+    std::vector<float> Pt((size_t)V * 3 * h->ldq, 0.f);
+    for (int p = 0; p < P; ++p) {
+      const float* src = mh->posedirs + (size_t)p * V * 3;
+      for (size_t r = 0; r < (size_t)V * 3; ++r) Pt[r * h->ldq + p] = src[r];
+    }
+    for (size_t r = 0; r < (size_t)V * 3; ++r)
+      for (int l = 0; l < NS; ++l) Pt[r * h->ldq + P + l] = mh->shapedirs[r * NS + l];
+    if (device_upload(&h->Pt, Pt.data(), Pt.size())) return 1;
+    h->owned.push_back(h->Pt);
+    std::vector<std::vector<std::pair<int, float>>> lists(V);
+    for (int e = 0; e < d.E; ++e) lists[ex[e]].push_back({J + e, 1.f});
+    for (int l = 0; l < d.L; ++l)
+      for (int k = 0; k < 3; ++k) lists[lv[l * 3 + k]].push_back({J + d.E + l, mh->lmk_bary_coords[l * 3 + k]});
+    std::vector<int> xoff(V + 1, 0), xj;
+    std::vector<float> xw;
+    for (int v = 0; v < V; ++v) {
+      for (auto& e : lists[v]) { xj.push_back(e.first); xw.push_back(e.second); }
+      xoff[v + 1] = (int)xj.size();
+    }
+    if (xj.empty()) { xj.push_back(0); xw.push_back(0.f); }
+    if (device_upload(&h->xoff, xoff.data(), xoff.size())) return 1;
+    h->owned.push_back(h->xoff);
+    if (device_upload(&h->xj, xj.data(), xj.size())) return 1;
+    h->owned.push_back(h->xj);
+    if (device_upload(&h->xw, xw.data(), xw.size())) return 1;
+    h->owned.push_back(h->xw);
+  }
   *out = h;
   return 0;
 }
@@ -479,6 +552,7 @@ extern "C" int airpose_smplx_destroy(airpose_smplx_t* h) {
   cudaSetDevice(h->device);
   for (void* p : h->owned) cudaFree(p);
   cudaFree(h->ws);
+  cudaFree(h->bws);
   delete h;
   return 0;
 }
@@ -582,6 +656,17 @@ extern "C" int airpose_rot6d_to_rotmat_strided(const float* x, int64_t groups, i
   return 0;
 }
 
+extern "C" int airpose_rot6d_to_rotmat_bwd_strided(const float* x, int64_t groups, int32_t per_group, int64_t row_stride,
+                                                   const float* grad_R, float* grad_x, int64_t grad_x_row_stride, void* stream) {
+  AP_REQUIRE(x && grad_R && grad_x && groups >= 0 && per_group > 0, "airpose_rot6d_to_rotmat_bwd: bad argument");
+  const int64_t n = groups * per_group;
+  if (n == 0) return 0;
+  rot6d_bwd_kernel<<<(unsigned)ceil_div64(n, 128), 128, 0, (cudaStream_t)stream>>>(x, groups, per_group, row_stride, grad_R,
+                                                                                    grad_x, grad_x_row_stride);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int airpose_rot6d_to_rotmat(const float* x, int64_t n, float* R, void* stream) {
   return airpose_rot6d_to_rotmat_strided(x, n, 1, 6, R, stream);
 }
@@ -600,5 +685,90 @@ extern "C" int airpose_j14_gather(const float* joints, int32_t batch, int32_t nu
   j14_gather_kernel<<<ceil_div(batch * 14 * 3, 128), 128, 0, (cudaStream_t)stream>>>(joints, batch, num_joints, dmap, 14, out);
   AP_LAUNCH_CHECK();
   AP_CHECK_CUDA(cudaFreeAsync(dmap, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int airpose_smplx_bwd(airpose_smplx_t* h, const airpose_smplx_bwd_args* g, void* stream_) {
+  AP_REQUIRE(h && g, "airpose_smplx_bwd: null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const SmplxDev& d = h->d;
+  const int B = g->batch;
+  AP_REQUIRE(B >= 0, "airpose_smplx_bwd: negative batch");
+  if (B == 0) return 0;
+  AP_REQUIRE(g->betas && g->grad_betas, "airpose_smplx_bwd: betas / grad_betas are required");
+  AP_REQUIRE(g->num_betas >= 1 && g->num_betas <= d.NS, "airpose_smplx_bwd: num_betas %d out of range", g->num_betas);
+  AP_REQUIRE(g->grad_vertices || g->grad_joints || g->grad_joints_cam || g->grad_joints_2d, "airpose_smplx_bwd: no upstream gradient");
+  AP_REQUIRE(!(g->grad_joints_cam || g->grad_joints_2d) || g->joints, "airpose_smplx_bwd: the forward joints are needed for camera-frame gradients");
+  AP_REQUIRE(d.J >= 22, "airpose_smplx_bwd: unsupported joint count %d", d.J);
+  const int n_active = g->body_pose ? 21 : 0;
+  const int PF = n_active * 9, NQ = PF + g->num_betas;
+  const int nj = d.J + d.E + d.L;
+  const int vtiles = ceil_div(d.V, kVertsPerCta);
+  auto al4 = [](size_t n) { return (n + 3) & ~size_t(3); };
+  const size_t n_jt = al4((size_t)B * d.J * 3), n_A = al4((size_t)B * d.J * 12), n_feat = al4((size_t)B * std::max(PF, 1)),
+               n_gj = al4((size_t)B * nj * 3), n_gA = al4((size_t)vtiles * B * d.J * 12), n_gq = al4((size_t)vtiles * B * NQ);
+  const size_t need = n_jt + n_A + n_feat + n_gj + n_gA + n_gq;
+  if (need > h->bws_floats) {
+    AP_CHECK_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(h->bws);
+    h->bws = nullptr; h->bws_floats = 0;
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->bws, need * sizeof(float)));
+    h->bws_floats = need;
+  }
+  float* Jt = h->bws;
+  float* A = Jt + n_jt;
+  float* feat = A + n_A;
+  float* gjt = feat + n_feat;
+  float* gA_part = gjt + n_gj;
+  float* gq_part = gA_part + n_gA;
+
+  BwdJointArgs ja{};
+  ja.B = B; ja.nj = nj; ja.joints = g->joints;
+  ja.g_joints = g->grad_joints; ja.g_joints_cam = g->grad_joints_cam; ja.g_j2d = g->grad_joints_2d;
+  ja.root_R = g->root_R; ja.root_R_stride = g->root_R_stride; ja.root_t = g->root_t; ja.root_t_stride = g->root_t_stride;
+  ja.fx = g->focal_x; ja.fy = g->focal_y;
+  ja.g_tot = gjt; ja.g_root_R = g->grad_root_R; ja.g_root_t = g->grad_root_t;
+  smplx_bwd_joints_kernel<<<B, 128, 0, stream>>>(ja);
+  AP_LAUNCH_CHECK();
+
+  PoseArgs pa{};
+  pa.B = B; pa.nb = g->num_betas; pa.n_active = n_active;
+  pa.betas = g->betas; pa.betas_stride = g->betas_stride;
+  pa.seg[0] = g->global_orient; pa.seg_stride[0] = g->global_orient_stride;
+  pa.seg[1] = g->body_pose; pa.seg_stride[1] = g->body_pose_stride;
+  pa.A = A; pa.Jt = Jt; pa.feat = feat;
+  smplx_pose_kernel<<<B, kMaxJoints, 0, stream>>>(d, pa);
+  AP_LAUNCH_CHECK();
+
+  BwdVertexArgs va{};
+  va.B = B; va.nb = g->num_betas; va.PF = PF; va.NQ = NQ; va.ldq = h->ldq; va.nj = nj; va.P = d.P;
+  va.betas = g->betas; va.betas_stride = g->betas_stride;
+  va.A = A; va.feat = feat; va.g_verts = g->grad_vertices; va.g_jtot = gjt;
+  va.Pt = h->Pt; va.xoff = h->xoff; va.xj = h->xj; va.xw = h->xw;
+  va.gA_part = gA_part; va.gq_part = gq_part;
+  {
+    constexpr int MB = kBwdMB;
+    const size_t smem = ((size_t)PF * MB + 2 * (size_t)MB * d.J * 12 + MB * kMaxShape + (size_t)MB * 3 * kVertsPerCta) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_bwd_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set = true;
+    }
+    AP_REQUIRE(smem <= 160 * 1024, "airpose_smplx_bwd: shared memory %zu too large", smem);
+    dim3 grid(vtiles, ceil_div(B, MB));
+    smplx_vertex_bwd_kernel<MB><<<grid, kVertsPerCta, smem, stream>>>(d, va);
+    AP_LAUNCH_CHECK();
+  }
+
+  BwdChainArgs ca{};
+  ca.B = B; ca.nb = g->num_betas; ca.PF = PF; ca.NQ = NQ; ca.n_active = n_active; ca.vtiles = vtiles; ca.nj = nj;
+  ca.betas = g->betas; ca.betas_stride = g->betas_stride;
+  ca.seg[0] = g->global_orient; ca.seg_stride[0] = g->global_orient_stride;
+  ca.seg[1] = g->body_pose; ca.seg_stride[1] = g->body_pose_stride;
+  ca.seg[2] = nullptr; ca.seg_stride[2] = 0;
+  ca.A = A; ca.gA_part = gA_part; ca.gq_part = gq_part; ca.g_jtot = gjt;
+  ca.g_betas = g->grad_betas; ca.g_body_pose = g->grad_body_pose; ca.g_global_orient = g->grad_global_orient;
+  smplx_bwd_chain_kernel<<<B, kMaxJoints, 0, stream>>>(d, ca);
+  AP_LAUNCH_CHECK();
   return 0;
 }

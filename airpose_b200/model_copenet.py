@@ -220,8 +220,8 @@ class copenet(nn.Module):
         theta0, theta1, shape0, shape1 = map(f, (theta0, theta1, shape0, shape1))
         B = xf0.shape[0]
         lib, h = self._ensure(0, device)
-        outs = [torch.empty(B, 135, device=device), torch.empty(B, 10, device=device),
-                torch.empty(B, 135, device=device), torch.empty(B, 10, device=device)]
+        outs = [torch.empty(B, 135, device=device, dtype=torch.float32), torch.empty(B, 10, device=device, dtype=torch.float32),
+                torch.empty(B, 135, device=device, dtype=torch.float32), torch.empty(B, 10, device=device, dtype=torch.float32)]
         a = _lib.IefArgs()
         a.batch, a.iters = B, int(iters)
         a.xf0, a.xf1, a.bb0, a.bb1, a.pos0, a.pos1 = (t.data_ptr() for t in (xf0, xf1, bb0, bb1, pos0, pos1))

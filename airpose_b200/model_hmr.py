@@ -45,9 +45,9 @@ class copenet(_mc.copenet):
         xf, theta, shape, cam = map(f, (xf, theta, shape, cam))
         B = xf.shape[0]
         lib, h = self._ensure(0, device)
-        pose = torch.empty(B, 132, device=device)
-        betas = torch.empty(B, 10, device=device)
-        pcam = torch.empty(B, 3, device=device)
+        pose = torch.empty(B, 132, device=device, dtype=torch.float32)
+        betas = torch.empty(B, 10, device=device, dtype=torch.float32)
+        pcam = torch.empty(B, 3, device=device, dtype=torch.float32)
         a = _lib.HmrIefArgs()
         a.batch, a.iters, a.xf = B, int(iters), xf.data_ptr()
         keep = []

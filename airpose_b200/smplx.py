@@ -128,7 +128,7 @@ class SMPLX(nn.Module):
         rm = np.zeros_like(data["hands_meanr"]) if flat_hand_mean else data["hands_meanr"]
         self.register_buffer("left_hand_mean", torch.tensor(_to_np(lm)))
         self.register_buffer("right_hand_mean", torch.tensor(_to_np(rm)))
-        self.register_buffer("pose_mean", torch.cat([torch.zeros(3 + 63 + 9), self.left_hand_mean, self.right_hand_mean]))
+        self.register_buffer("pose_mean", torch.cat([torch.zeros(3 + 63 + 9, dtype=torch.float32), self.left_hand_mean, self.right_hand_mean]))
 
         def param(name, create, value, shape):
             if not create:
@@ -276,7 +276,7 @@ class SMPLX(nn.Module):
 
         tail = None
         if any(t is not None for t in tail_in[:3]):
-            eye = torch.eye(3, device=device).expand(B, 1, 3, 3)
+            eye = torch.eye(3, device=device, dtype=torch.float32).expand(B, 1, 3, 3)
             parts = [t if t is not None else eye for t in tail_in[:3]] + [eye.expand(B, 30, 3, 3)]
             tail = torch.cat(parts, dim=1).contiguous()
 
@@ -328,7 +328,7 @@ class SMPLX(nn.Module):
 
         full_pose = None
         if return_full_pose:
-            eye = torch.eye(3, device=device).expand(B, 1, 3, 3)
+            eye = torch.eye(3, device=device, dtype=torch.float32).expand(B, 1, 3, 3)
             full_pose = torch.cat([go if go is not None else eye,
                                    bp if bp is not None else eye.expand(B, 21, 3, 3),
                                    tail if tail is not None else eye.expand(B, 33, 3, 3)], dim=1)
@@ -340,6 +340,73 @@ class SMPLX(nn.Module):
                           right_hand_pose=getattr(self, "right_hand_pose", None), jaw_pose=jaw_pose,
                           full_pose=full_pose)
         return out, cam
+
+
+def smplx_backward(module, betas, body_pose, global_orient=None, grad_vertices=None, grad_joints=None,
+                   grad_joints_cam=None, grad_joints_2d=None, joints=None, root_R=None, root_t=None, focal_length=None):
+    """Gradient of ``SMPLX.forward(pose2rot=False)`` (+ ``transform_smpl`` + ``perspective_projection`` when the
+    camera-frame gradients are given) w.r.t. betas, body_pose, global_orient, root_R, root_t -- what autograd derives
+    for the reference (copenet_twoview.py:281-317).  Returns a dict of gradient tensors."""
+    device = module.v_template.device
+    if device.type != "cuda":
+        raise _lib.AirposeError("smplx_backward runs on CUDA only; there is no CPU path")
+    lib = _lib.load()
+    h = module._get_handle(device)
+    f = lambda t: None if t is None else t.detach().to(device=device, dtype=torch.float32).contiguous()
+    betas, body_pose, global_orient = f(betas), f(body_pose), f(global_orient)
+    B = betas.shape[0]
+    a = _lib.SmplxBwdArgs()
+    a.batch, a.num_betas = B, betas.shape[1]
+    a.betas, a.betas_stride = betas.data_ptr(), betas.stride(0)
+    keep = [betas, body_pose, global_orient]
+    out = {"betas": torch.empty(B, betas.shape[1], device=device, dtype=torch.float32)}
+    a.grad_betas = out["betas"].data_ptr()
+    if body_pose is not None:
+        body_pose = body_pose.reshape(B, 21, 3, 3)
+        a.body_pose, a.body_pose_stride = body_pose.data_ptr(), 189
+        out["body_pose"] = torch.empty(B, 21, 3, 3, device=device, dtype=torch.float32)
+        a.grad_body_pose = out["body_pose"].data_ptr()
+    if global_orient is not None:
+        global_orient = global_orient.reshape(B, 1, 3, 3)
+        a.global_orient, a.global_orient_stride = global_orient.data_ptr(), 9
+    out["global_orient"] = torch.empty(B, 1, 3, 3, device=device, dtype=torch.float32)
+    a.grad_global_orient = out["global_orient"].data_ptr()
+    for name, t in (("grad_vertices", grad_vertices), ("grad_joints", grad_joints), ("grad_joints_cam", grad_joints_cam),
+                    ("grad_joints_2d", grad_joints_2d), ("joints", joints)):
+        t = f(t)
+        if t is not None:
+            keep.append(t)
+            setattr(a, name, t.data_ptr())
+    if root_R is not None:
+        rR = f(root_R).reshape(B, 9); keep.append(rR); a.root_R, a.root_R_stride = rR.data_ptr(), 9
+        out["root_R"] = torch.empty(B, 3, 3, device=device, dtype=torch.float32); a.grad_root_R = out["root_R"].data_ptr()
+    if root_t is not None:
+        rt = f(root_t).reshape(B, 3); keep.append(rt); a.root_t, a.root_t_stride = rt.data_ptr(), 3
+        out["root_t"] = torch.empty(B, 3, device=device, dtype=torch.float32); a.grad_root_t = out["root_t"].data_ptr()
+    if focal_length is not None:
+        a.focal_x, a.focal_y = float(focal_length[0]), float(focal_length[1])
+    with torch.cuda.device(device):
+        _lib.check(lib.airpose_smplx_bwd(h, C.byref(a), _lib.current_stream()), "airpose_smplx_bwd")
+    del keep
+    return out
+
+
+def rot6d_to_rotmat_backward(x, grad_R):
+    """Backward of ``rot6d_to_rotmat``: x [B, 6k] (may be a strided view such as pred_pose[:, 3:]), grad_R [B*k,3,3]
+    -> grad_x [B, 6k]."""
+    if x.device.type != "cuda":
+        raise _lib.AirposeError("rot6d_to_rotmat_backward runs on CUDA only; there is no CPU path")
+    lib = _lib.load()
+    x = x.detach().float()
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    B, w = x.shape
+    g = grad_R.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    out = torch.empty(B, w, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.airpose_rot6d_to_rotmat_bwd_strided(x.data_ptr(), B, w // 6, x.stride(0), g.data_ptr(), out.data_ptr(), w,
+                                                           _lib.current_stream()), "airpose_rot6d_to_rotmat_bwd_strided")
+    return out
 
 
 def rot6d_to_rotmat(x):

@@ -102,6 +102,36 @@ typedef struct {
 
 int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_args* args, void* stream);
 
+/* Backward of airpose_smplx_fwd for the training step and for bundle adjustment: what torch autograd derives for
+ * SMPLX.forward(pose2rot=False) + transform_smpl + perspective_projection (copenet_twoview.py:281-317;
+ * copenet_real_data/scripts/bundle_adj.py:301-401).  Call pattern of the hot path: betas, 21 body rotations, optional
+ * global orientation (NULL = identity), joints 22..54 identity, no translation.  Upstream gradients (any subset):
+ * d/d vertices, d/d joints (canonical), d/d joints_cam and d/d joints_2d (these two need the forward's `joints` output
+ * and the same root_R / root_t / focal).  All outputs are fp32; the rotation gradients are with respect to the nine
+ * matrix entries, as autograd gives them.  Deterministic apart from the shared-memory accumulation of dL/dA inside a
+ * 128-vertex tile (fp32 atomics, ~1e-7 relative). */
+typedef struct {
+  int32_t batch;
+  int32_t num_betas;
+  const float* betas;          int32_t betas_stride;          /* [B,num_betas] */
+  const float* global_orient;  int32_t global_orient_stride;  /* [B,1,3,3] or NULL */
+  const float* body_pose;      int32_t body_pose_stride;      /* [B,21,3,3] or NULL */
+  const float* joints;                                        /* [B,127,3] forward output, or NULL */
+  const float* root_R;         int32_t root_R_stride;         /* [B,3,3] or NULL */
+  const float* root_t;         int32_t root_t_stride;         /* [B,3] or NULL */
+  float focal_x, focal_y;
+  const float* grad_vertices;                                 /* [B,V,3] or NULL */
+  const float* grad_joints;                                   /* [B,127,3] or NULL */
+  const float* grad_joints_cam;                               /* [B,127,3] or NULL */
+  const float* grad_joints_2d;                                /* [B,127,2] or NULL */
+  float* grad_betas;                                          /* [B,num_betas] */
+  float* grad_body_pose;                                      /* [B,21,3,3] or NULL */
+  float* grad_global_orient;                                  /* [B,3,3] or NULL */
+  float* grad_root_R;                                         /* [B,3,3] or NULL */
+  float* grad_root_t;                                         /* [B,3] or NULL */
+} airpose_smplx_bwd_args;
+int airpose_smplx_bwd(airpose_smplx_t* h, const airpose_smplx_bwd_args* args, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * geometry helpers
  * ---------------------------------------------------------------------------------- */
@@ -111,6 +141,10 @@ int airpose_rot6d_to_rotmat(const float* x, int64_t n, float* R, void* stream);
 /* strided form: `groups` rows of `per_group` consecutive 6-vectors, rows `row_stride` floats apart */
 int airpose_rot6d_to_rotmat_strided(const float* x, int64_t groups, int32_t per_group, int64_t row_stride,
                                     float* R, void* stream);
+/* backward of the above: grad_R [groups*per_group,3,3] -> grad_x, written with the same strided layout as x
+ * (rows `grad_x_row_stride` floats apart), e.g. straight into d(loss)/d(pred_pose)[:, 3:]. */
+int airpose_rot6d_to_rotmat_bwd_strided(const float* x, int64_t groups, int32_t per_group, int64_t row_stride,
+                                        const float* grad_R, float* grad_x, int64_t grad_x_row_stride, void* stream);
 /* SMPL joint -> 14 OpenPose joints (copenet_real_data/scripts/bundle_adj.py:48,116):
  * out[b,i,:] = joints[b,map[i],:], a bit-exact gather. map=NULL selects the reference map. */
 int airpose_j14_gather(const float* joints, int32_t batch, int32_t num_joints, const int32_t* map_host,

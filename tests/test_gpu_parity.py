@@ -570,3 +570,135 @@ def test_adam_matches_torch(amsgrad):
     for p, r in zip(ours, ref):
         assert rel_err(p.detach().cpu().numpy(), r.detach().cpu().numpy()) < 1e-6
         assert p.data_ptr() >= opt.flat.data_ptr() and p.data_ptr() < opt.flat.data_ptr() + opt.flat.numel() * 4
+
+
+# ----------------------------------------------------------------------------- backward: SMPL-X, rot6d, loss -> regressor outputs
+def _torch_smplx64(smplx_data):
+    import torch_port as tp
+    m = tp.Smplx(smplx_data)
+    for k in ("v_template", "shapedirs", "J_regressor", "weights", "posedirs", "lmk_bary"):
+        setattr(m, k, getattr(m, k).double())
+    return tp, m
+
+
+@pytest.mark.parametrize("B", [1, 5, 11])
+def test_smplx_backward_matches_autograd(smplx_gpu, smplx_data, B):
+    """airpose_smplx_bwd against fp64 autograd through the PyTorch port of the reference's SMPL-X forward
+    (oracle/torch_port.py), with gradients arriving on vertices, canonical joints, camera-frame joints and 2D joints."""
+    from airpose_b200.smplx import smplx_backward
+    tp, m = _torch_smplx64(smplx_data)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        li = synthetic.make_lbs_inputs(B, seed=50 + B)
+        rng = np.random.default_rng(B)
+        gv = rng.standard_normal((B, 10475, 3)).astype(np.float32) * 1e-3
+        gj = rng.standard_normal((B, 127, 3)).astype(np.float32)
+        gjc = rng.standard_normal((B, 127, 3)).astype(np.float32)
+        g2d = rng.standard_normal((B, 127, 2)).astype(np.float32) * 1e-2
+        rootR = synthetic.rot6d_to_rotmat_np(np.array([1, 0, 0, 1, 0, 0], np.float32) + rng.standard_normal((B, 6)).astype(np.float32) * 0.3)
+        roott = (np.array([0, 0, 10], np.float32) + rng.standard_normal((B, 3)).astype(np.float32)).astype(np.float32)
+        betas = torch.tensor(li["betas"], dtype=torch.float64, requires_grad=True)
+        body = torch.tensor(li["body_pose"], dtype=torch.float64, requires_grad=True)
+        R = torch.tensor(rootR, dtype=torch.float64, requires_grad=True)
+        tt = torch.tensor(roott, dtype=torch.float64, requires_grad=True)
+        verts, joints = tp.smplx_forward(m, betas, body)
+        jc = torch.bmm(R, joints.permute(0, 2, 1)).permute(0, 2, 1) + tt[:, None]
+        j2d = torch.stack([1475.0 * jc[:, :, 0] / jc[:, :, 2], 1475.0 * jc[:, :, 1] / jc[:, :, 2]], -1)
+        obj = ((verts * torch.tensor(gv, dtype=torch.float64)).sum() + (joints * torch.tensor(gj, dtype=torch.float64)).sum()
+               + (jc * torch.tensor(gjc, dtype=torch.float64)).sum() + (j2d * torch.tensor(g2d, dtype=torch.float64)).sum())
+        obj.backward()
+    finally:
+        torch.set_default_dtype(old)
+    out = smplx_gpu.forward(betas=t(li["betas"]), body_pose=t(li["body_pose"]), pose2rot=False)
+    g = smplx_backward(smplx_gpu, t(li["betas"]), t(li["body_pose"]), None, grad_vertices=t(gv), grad_joints=t(gj),
+                       grad_joints_cam=t(gjc), grad_joints_2d=t(g2d), joints=out.joints, root_R=t(rootR), root_t=t(roott),
+                       focal_length=[1475, 1475])
+    for k, ref in (("betas", betas.grad), ("body_pose", body.grad), ("root_R", R.grad), ("root_t", tt.grad)):
+        e = rel_err(g[k].cpu().numpy(), ref.numpy())
+        print("smplx bwd B=%d %-10s rel err %.3e" % (B, k, e))
+        assert e < 2e-4, k            # fp32 kernels vs fp64 autograd; joints come from the fp16-posedirs forward (3e-5)
+
+
+def test_rot6d_backward_matches_autograd():
+    from airpose_b200.smplx import rot6d_to_rotmat_backward
+    import torch_port as tp
+    rng = np.random.default_rng(0)
+    x = torch.tensor(rng.standard_normal((7, 135)), dtype=torch.float64, requires_grad=True)
+    gR = torch.tensor(rng.standard_normal((7 * 22, 3, 3)), dtype=torch.float64)
+    (tp.rot6d_to_rotmat(x[:, 3:]) * gR).sum().backward()
+    xg = x.detach().float().to(DEV)
+    got = rot6d_to_rotmat_backward(xg[:, 3:], gR.float().to(DEV))
+    assert rel_err(got.cpu().numpy(), x.grad[:, 3:].numpy()) < 1e-5
+
+
+def test_loss_and_head_backward_matches_autograd(tmp_path, smplx_dir, smplx_data, net_gpu, net_state):
+    """d loss / d (regressor outputs) through get_loss, projection, transform_smpl, SMPL-X and rot6d_to_rotmat, against
+    fp64 autograd over the PyTorch port of the same chain (copenet_twoview.py:205-317 + :83-161)."""
+    mod = _loss_module(tmp_path, smplx_dir)
+    mod.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in net_state.items()})
+    mod = mod.to(DEV).eval()
+    B = 3
+    x = synthetic.make_inputs(B, 77)
+    rng = np.random.default_rng(5)
+    gt_in = synthetic.make_lbs_inputs(B, seed=9)
+    tp, m = _torch_smplx64(smplx_data)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        gv, gj = tp.smplx_forward(m, torch.tensor(gt_in["betas"], dtype=torch.float64), torch.tensor(gt_in["body_pose"], dtype=torch.float64))
+        gt = {"smplpose_rotmat": gt_in["body_pose"],
+              "smplorient_rel0": synthetic.rot6d_to_rotmat_np(np.array([1, 0, 0, 1, 0, 0], np.float32) + rng.standard_normal((B, 6)).astype(np.float32) * 0.3)[:, None],
+              "smplorient_rel1": synthetic.rot6d_to_rotmat_np(np.array([1, 0, 0, 1, 0, 0], np.float32) + rng.standard_normal((B, 6)).astype(np.float32) * 0.3)[:, None],
+              "smpl_vertices": gv.numpy().astype(np.float32)[:, None], "smpl_joints": gj.numpy().astype(np.float32)[:, None],
+              "smpl_joints_2d0": (rng.standard_normal((B, 1, 127, 2)) * 50 + 500).astype(np.float32),
+              "smpl_joints_2d1": (rng.standard_normal((B, 1, 127, 2)) * 50 + 500).astype(np.float32),
+              "smpltrans_rel0": x["smpltrans_rel0"], "smpltrans_rel1": x["smpltrans_rel1"]}
+        batch = {k: t(v) for k, v in {**x, **gt}.items()}
+        out = mod.fwd_pass(batch)
+        raw = {}
+        for v in (0, 1):            # the network's raw outputs: translation still scaled by 0.05
+            p = out["pred_pose%d" % v].clone()
+            p[:, :3] *= 0.05
+            raw["pose%d" % v] = p.cpu().double().requires_grad_(True)
+            raw["betas%d" % v] = out["pred_betas%d" % v].cpu().double().requires_grad_(True)
+        G = {k: torch.tensor(v, dtype=torch.float64) for k, v in gt.items()}
+        hp = orc.DEFAULT_LOSS_WEIGHTS
+        mse = lambda a, b: (a - b) ** 2
+        P = {}
+        for v in (0, 1):
+            pose = raw["pose%d" % v]
+            trans = pose[:, :3] / 0.05
+            R = tp.rot6d_to_rotmat(pose[:, 3:]).view(B, 22, 3, 3)
+            verts, joints = tp.smplx_forward(m, raw["betas%d" % v], R[:, 1:])
+            jc = torch.bmm(R[:, 0], joints.permute(0, 2, 1)).permute(0, 2, 1) + trans[:, None]
+            c = torch.tensor(x["intr%d" % v][:, :2, 2], dtype=torch.float64)
+            j2d = torch.stack([1475.0 * jc[:, :, 0] / jc[:, :, 2] + c[:, None, 0], 1475.0 * jc[:, :, 1] / jc[:, :, 2] + c[:, None, 1]], -1)
+            P[v] = dict(trans=trans, R=R, verts=verts, joints=joints, j2d=j2d, betas=raw["betas%d" % v])
+        w3 = torch.ones(22); w3[[4, 5, 18, 19]] = hp["limbs3d_loss_weight"]; w3[[7, 8, 20, 21]] = hp["limbs3d_loss_weight"] ** 2
+        wt = torch.ones(21); wt[[3, 4, 17, 18]] = hp["limbstheta_loss_weight"]; wt[[6, 7, 19, 20]] = hp["limbstheta_loss_weight"] ** 2
+        gvv, gjj = G["smpl_vertices"].squeeze(1), G["smpl_joints"].squeeze(1)
+        l_kp = sum(mse(P[v]["j2d"][:, :22], G["smpl_joints_2d%d" % v].squeeze(1)[:, :22]).mean() for v in (0, 1))
+        l3 = mse(P[0]["joints"][:, :22], gjj[:, :22]) + mse(P[1]["joints"][:, :22], gjj[:, :22]) + mse(P[0]["joints"][:, :22], P[1]["joints"][:, :22])
+        l_kp3d = (l3 * w3.view(1, 22, 1)).mean()
+        l_shape = mse(P[0]["verts"], gvv).mean() + mse(P[1]["verts"], gvv).mean() + mse(P[0]["verts"], P[1]["verts"]).mean()
+        l_trans = sum(mse(P[v]["trans"], G["smpltrans_rel%d" % v]).mean() for v in (0, 1))
+        l_root = sum(mse(P[v]["R"][:, :1], G["smplorient_rel%d" % v]).mean() for v in (0, 1))
+        lr = mse(P[0]["R"][:, 1:], G["smplpose_rotmat"]) + mse(P[1]["R"][:, 1:], G["smplpose_rotmat"]) + mse(P[0]["R"][:, 1:], P[1]["R"][:, 1:])
+        l_pose = (lr * wt.view(1, 21, 1, 1)).mean()
+        b0, b1 = P[0]["betas"], P[1]["betas"]
+        l_beta = (b0 * b0).mean() + (b1 * b1).mean() + mse(b0, b1).mean()
+        ref = 60 * (hp["trans_loss_weight"] * l_trans + hp["keypoint2d_loss_weight"] * l_kp + hp["keypoint3d_loss_weight"] * l_kp3d
+                    + hp["shape_loss_weight"] * l_shape + hp["rootrot_loss_weight"] * l_root + hp["pose_loss_weight"] * l_pose
+                    + hp["beta_loss_weight"] * l_beta)
+        ref.backward()
+    finally:
+        torch.set_default_dtype(old)
+    loss, losses, grads = mod.loss_and_head_backward(batch, out)
+    print("loss cuda %.6f autograd-port %.6f" % (float(loss), float(ref)))
+    assert abs(float(loss) - float(ref)) <= 2e-4 * abs(float(ref))
+    for v in (0, 1):
+        ep = rel_err(grads["pred_pose%d" % v].cpu().numpy(), raw["pose%d" % v].grad.numpy())
+        eb = rel_err(grads["pred_betas%d" % v].cpu().numpy(), raw["betas%d" % v].grad.numpy())
+        print("view %d: d loss/d pred_pose rel err %.3e, d loss/d pred_betas rel err %.3e" % (v, ep, eb))
+        assert ep < 1e-3 and eb < 1e-3
