@@ -366,7 +366,21 @@ bool prefers_stream_k(int M, int N, int K) {
   return ceil_div(K, 64) >= min_kb && tiles < 8 * num_sms() && tiles % num_sms() != 0;
 }
 
+// The cta_group::2 pair kernel (gemm_sk2.cu) needs N % 256 == 0 and pays off where the mainloop dominates: long K and
+// enough rows.  Measured (profiles/r01g_layers_pair.txt): 8192^3 1166 -> 1413 TFLOP/s; layer3 3x3 (M=25088, K=2304)
+// 40.8 -> 39.5 us; layer4 3x3 (M=6272) 42.0 -> 43.0 us and the K<=2048 1x1 layers 24.6 -> 28.7 us, which therefore stay
+// on the cta_group::1 kernels.  AIRPOSE_GEMM_2CTA=0 disables it; AIRPOSE_2CTA_MINKB / AIRPOSE_2CTA_MINM move the thresholds.
+bool prefers_pair(int M, int N, int K) {
+  static const bool on = getenv("AIRPOSE_GEMM_2CTA") == nullptr || atoi(getenv("AIRPOSE_GEMM_2CTA")) != 0;
+  static const int min_kb = getenv("AIRPOSE_2CTA_MINKB") ? atoi(getenv("AIRPOSE_2CTA_MINKB")) : 36;
+  static const int min_m = getenv("AIRPOSE_2CTA_MINM") ? atoi(getenv("AIRPOSE_2CTA_MINM")) : 16384;
+  return on && use_stream_k() && N % 256 == 0 && K % 64 == 0 && K / 64 >= min_kb && M >= min_m;
+}
+
+int b_box_rows(int M, int N, int K, int block_n) { return prefers_pair(M, N, K) ? 128 : block_n; }
+
 int pick_block_n(int M, int N, int K) {
+  if (prefers_pair(M, N, K)) return 256;
   if (prefers_stream_k(M, N, K)) {   // stream-K removes the wave-quantisation penalty of wide tiles
     if (N % 256 == 0) return 256;
     if (N > 64) return 128;
@@ -393,6 +407,7 @@ static int launch_bn(const GemmLaunch& L, const KParams& kp, cudaStream_t stream
 }
 
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream) {
+  if (L.tma_epi && L.pair_b_box) return launch_gemm_sk2(L, stream);
   if (L.tma_epi) return (!L.stem && prefers_stream_k(L.M, L.N, L.K)) ? launch_gemm_sk(L, stream) : launch_gemm_tma(L, stream);
   AP_REQUIRE(L.M > 0 && L.N > 0 && L.K > 0, "launch_gemm: empty problem %dx%dx%d", L.M, L.N, L.K);
   AP_REQUIRE(L.N % 8 == 0, "launch_gemm: N=%d must be a multiple of 8", L.N);
@@ -435,13 +450,19 @@ extern "C" int airpose_gemm_bf16(const airpose_gemm_args* g, void* stream) {
   L.M = g->M; L.N = g->N; L.K = g->K;
   L.block_n = pick_block_n(g->M, g->N, g->K);
   if (make_tmap_tiled_bf16(&L.tmA, g->A, g->M, g->K, g->lda, kBlockM, kBlockK)) return 1;
-  if (make_tmap_tiled_bf16(&L.tmB, g->B, g->N, g->K, g->ldb, L.block_n, kBlockK)) return 1;
+  const bool tma_ok = use_tma_epilogue() && g->out_bf16 && !g->out_f32 && g->N % 64 == 0;
+  L.pair_b_box = tma_ok && prefers_pair(g->M, g->N, g->K) && g->ldb == g->K;
+  if (make_tmap_tiled_bf16(&L.tmB, g->B, g->N, g->K, g->ldb, L.pair_b_box ? 128 : L.block_n, kBlockK)) return 1;
   L.epi.scale = g->scale; L.epi.shift = g->shift;
   L.epi.residual = g->residual; L.epi.ldr = g->ldr;
   L.epi.relu = g->relu;
   L.epi.out_bf16 = g->out_bf16; L.epi.ldd = g->ldd;
   L.epi.out_f32 = g->out_f32; L.epi.ldf = g->ldf;
   if (use_tma_epilogue() && tma_epilogue_eligible(L) && enable_tma_epilogue(&L)) return 1;
+  if (L.pair_b_box && !L.tma_epi) {      // the pair kernel needs the TMA epilogue: fall back to block_n-row B boxes
+    L.pair_b_box = 0;
+    if (make_tmap_tiled_bf16(&L.tmB, g->B, g->N, g->K, g->ldb, L.block_n, kBlockK)) return 1;
+  }
   return launch_gemm(L, (cudaStream_t)stream);
 }
 
@@ -457,11 +478,16 @@ extern "C" int airpose_conv_bf16(const airpose_conv_args* c, void* stream) {
   L.block_n = pick_block_n(L.M, L.N, L.K);
   L.im2col = 1;
   if (make_tmap_im2col_bf16(&L.tmA, c->x, g, kBlockK, kBlockM)) return 1;
-  if (make_tmap_tiled_bf16(&L.tmB, c->w, L.N, L.K, L.K, L.block_n, kBlockK)) return 1;
+  L.pair_b_box = use_tma_epilogue() && L.N % 64 == 0 && prefers_pair(L.M, L.N, L.K);
+  if (make_tmap_tiled_bf16(&L.tmB, c->w, L.N, L.K, L.K, L.pair_b_box ? 128 : L.block_n, kBlockK)) return 1;
   L.epi.scale = c->scale; L.epi.shift = c->shift;
   L.epi.residual = c->residual; L.epi.ldr = c->Cout;
   L.epi.relu = c->relu;
   L.epi.out_bf16 = c->out; L.epi.ldd = c->Cout;
   if (use_tma_epilogue() && tma_epilogue_eligible(L) && enable_tma_epilogue(&L)) return 1;
+  if (L.pair_b_box && !L.tma_epi) {
+    L.pair_b_box = 0;
+    if (make_tmap_tiled_bf16(&L.tmB, c->w, L.N, L.K, L.K, L.block_n, kBlockK)) return 1;
+  }
   return launch_gemm(L, (cudaStream_t)stream);
 }

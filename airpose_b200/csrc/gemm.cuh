@@ -41,6 +41,7 @@ struct GemmLaunch {
   int stem_tap_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int tma_epi = 0;     // 1: bf16 output through smem staging + TMA store (gemm_tma.cu); 0: direct stores (gemm.cu)
   int pdl = 0;         // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
+  int pair_b_box = 0;  // 1: planned for the cta_group::2 pair kernel (gemm_sk2.cu): block_n = 256, tmB boxes of 128 rows
   ConvGeom geom;
   Epilogue epi;
 };
@@ -54,6 +55,11 @@ int launch_gemm_tma(const GemmLaunch& L, cudaStream_t stream);
 // Chosen per problem by prefers_stream_k(); AIRPOSE_GEMM_V1=1 / AIRPOSE_GEMM_SK=1 force one kernel for A/B runs.
 int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream);
 bool use_stream_k();
+// cta_group::2 pair kernel (gemm_sk2.cu): 256 x 256 tiles on CTA pairs.  prefers_pair() decides per problem.
+int launch_gemm_sk2(const GemmLaunch& L, cudaStream_t stream);
+bool prefers_pair(int M, int N, int K);
+// rows of a tmB box for a launch of this shape (block_n, or 128 when the pair kernel will run it)
+int b_box_rows(int M, int N, int K, int block_n);
 
 // Tensor maps (cuTensorMapEncode* resolved through cudaGetDriverEntryPoint; no libcuda link).
 int make_tmap_tiled_bf16(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld_elems,

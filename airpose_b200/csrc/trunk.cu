@@ -271,12 +271,17 @@ static int conv_launch(airpose_net* h, int idx, const __nv_bfloat16* x, int n, i
     L->im2col = 1;
     if (make_tmap_im2col_bf16(&L->tmA, x, g, 64, 128)) return 1;
   }
-  if (make_tmap_tiled_bf16(&L->tmB, h->wq[idx], L->N, L->K, L->K, L->block_n, 64)) return 1;
+  L->pair_b_box = use_tma_epilogue() && prefers_pair(L->M, L->N, L->K);
+  if (make_tmap_tiled_bf16(&L->tmB, h->wq[idx], L->N, L->K, L->K, L->pair_b_box ? 128 : L->block_n, 64)) return 1;
   L->epi.scale = h->scale[idx]; L->epi.shift = h->shift[idx];
   L->epi.residual = residual; L->epi.ldr = s.cout;
   L->epi.relu = relu;
   L->epi.out_bf16 = out; L->epi.ldd = s.cout;
   if (use_tma_epilogue() && tma_epilogue_eligible(*L) && enable_tma_epilogue(L)) return 1;
+  if (L->pair_b_box && !L->tma_epi) {
+    L->pair_b_box = 0;
+    if (make_tmap_tiled_bf16(&L->tmB, h->wq[idx], L->N, L->K, L->K, L->block_n, 64)) return 1;
+  }
   L->pdl = use_pdl();
   return 0;
 }

@@ -191,7 +191,10 @@ def test_gemm_bf16_matches_torch(M, N, K):
                                             # the deep residual ring, and the trunk's own layer3/layer4 shapes
                                             (256, 256, 8192, True, True), (25088, 256, 2304, False, True),
                                             (6272, 512, 4608, True, True), (50176, 256, 64, True, True),
-                                            (50176, 64, 576, False, True), (1500, 128, 1152, True, False)])
+                                            (50176, 64, 576, False, True), (1500, 128, 1152, True, False),
+                                            # cta_group::2 pair kernel (gemm_sk2.cu; M >= 16384, K >= 2304, N % 256 == 0): a peer
+                                            # half-tile without rows (16500 = 64 pair tiles + 116 rows), residual, two n-tiles
+                                            (16500, 512, 2304, True, True), (20000, 256, 4608, False, False)])
 def test_gemm_tma_epilogue_bf16_out(M, N, K, res, relu):
     """bf16 output with N % 64 == 0 runs the TMA-epilogue kernel (gemm_tma.cu): swizzled smem staging,
     TMA residual loads and TMA stores, M tails clipped by the tensor map."""
@@ -250,7 +253,8 @@ def test_gemm_epilogue_scale_shift_residual_relu():
 
 @pytest.mark.parametrize("n,H,Cin,Cout,k,stride", [(2, 56, 64, 64, 3, 1), (3, 28, 128, 128, 3, 2), (2, 56, 256, 512, 1, 2),
                                                    (5, 14, 256, 256, 3, 1), (3, 14, 512, 512, 3, 2), (1, 7, 512, 512, 3, 1),
-                                                   (2, 56, 64, 256, 1, 1)])
+                                                   (2, 56, 64, 256, 1, 1),
+                                                   (90, 14, 256, 256, 3, 1)])      # M = 17640: im2col through the pair kernel
 def test_conv_implicit_gemm_matches_torch(n, H, Cin, Cout, k, stride):
     lib = _lib.load()
     pad = k // 2
