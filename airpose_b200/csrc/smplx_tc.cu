@@ -91,12 +91,22 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32xN(uint32_t taddr, uint32_t (&r)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32xN(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+
 // kind::f16 instruction descriptor with fp16 A/B (format 0), fp32 accumulator.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <bool kHasCam>
+template <bool kHasCam, int UN>
 __global__ void __launch_bounds__(kThreads, 1)
 smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmFh,
                        const __grid_constant__ CUtensorMap tmFl, const KArgs a) {
@@ -230,71 +240,80 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
       const int slot = s % kRStages; const uint32_t rph = (s / kRStages) & 1;
       ptx::mbar_wait(&tfull[as], aphase, 400 + as);
       ptx::tc_fence_after();
-      uint32_t dx[16], dy[16], dz[16];
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 96 + hf * kTcSub;
-      tmem_ld_32x16(taddr, dx);
-      tmem_ld_32x16(taddr + kTcMeshTile, dy);
-      tmem_ld_32x16(taddr + 2 * kTcMeshTile, dz);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[as]);   // accumulator is in registers: MMA may refill it
       ptx::mbar_wait(&r_full[slot], rph, 410 + slot);
       const uint8_t* rbase = smem + kROff + slot * kRStageBytes;
       const int mesh0 = t * kTcMeshTile + hf * kTcSub;
-#pragma unroll
-      for (int m = 0; m < kTcSub; ++m) {
-        const int b = mesh0 + m;
-        if (b >= a.B) break;                           // uniform across the CTA
-        const float* rec = reinterpret_cast<const float*>(rbase + m * kRecBytes);
-        // v_shaped (lbs.py:179) + pose offsets (:203)
-        const float4 b0 = *reinterpret_cast<const float4*>(rec + kTcRecBetas);
-        const float4 b1 = *reinterpret_cast<const float4*>(rec + kTcRecBetas + 4);
-        const float2 b2 = *reinterpret_cast<const float2*>(rec + kTcRecBetas + 8);
-        const float be[10] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
-        float x = vt0, y = vt1, z = vt2;
-#pragma unroll
-        for (int l = 0; l < 10; ++l) {
-          x = fmaf(S[0][l], be[l], x);
-          y = fmaf(S[1][l], be[l], y);
-          z = fmaf(S[2][l], be[l], z);
+      // UN (2 or 4) meshes per TMEM load and per unrolled body: the fully unrolled 16-mesh body was ~5700 SASS instructions
+      // (91 KB) and spent 12 % of its samples in instruction-fetch stalls (profiles/r01c: stall_no_inst)
+#pragma unroll 1
+      for (int mq = 0; mq < kTcSub / UN; ++mq) {
+        uint32_t dx[UN], dy[UN], dz[UN];
+        tmem_ld_32xN(taddr + mq * UN, dx);
+        tmem_ld_32xN(taddr + kTcMeshTile + mq * UN, dy);
+        tmem_ld_32xN(taddr + 2 * kTcMeshTile + mq * UN, dz);
+        ptx::tmem_ld_wait();
+        if (mq == kTcSub / UN - 1) {                      // accumulator is in registers: MMA may refill it
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[as]);
         }
-        x = fmaf(__uint_as_float(dx[m]), inv_scale, x);
-        y = fmaf(__uint_as_float(dy[m]), inv_scale, y);
-        z = fmaf(__uint_as_float(dz[m]), inv_scale, z);
-        // T = sum_k w_k A_k (lbs.py:209-213)
-        float T[12];
+        if (mesh0 + mq * UN >= a.B) continue;            // uniform across the CTA (the release above still happens)
 #pragma unroll
-        for (int e = 0; e < 12; ++e) T[e] = 0.f;
+        for (int mi = 0; mi < UN; ++mi) {
+          const int m = mq * UN + mi;
+          const int b = mesh0 + m;
+          if (b >= a.B) break;                           // uniform across the CTA
+          const float* rec = reinterpret_cast<const float*>(rbase + m * kRecBytes);
+          // v_shaped (lbs.py:179) + pose offsets (:203)
+          const float4 b0 = *reinterpret_cast<const float4*>(rec + kTcRecBetas);
+          const float4 b1 = *reinterpret_cast<const float4*>(rec + kTcRecBetas + 4);
+          const float2 b2 = *reinterpret_cast<const float2*>(rec + kTcRecBetas + 8);
+          const float be[10] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
+          float x = vt0, y = vt1, z = vt2;
 #pragma unroll
-        for (int k = 0; k < kTcMaxKW; ++k) {
-          if (k >= kw_warp) break;                     // warp-uniform
-          const float w = jw[k];
-          const float4* Aj = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(rec) + joff[k]);
-          const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
-          T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
-          T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
-          T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
-        }
-        // v = T [v_posed; 1] (lbs.py:215-220) + transl (body_models.py:980-982)
-        float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
-        float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
-        float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
-        if (a.has_transl) {
-          const float4 tr = *reinterpret_cast<const float4*>(rec + kTcRecTransl);
-          ox += tr.x; oy += tr.y; oz += tr.z;
-        }
-        if (valid) {
-          float* o = a.out + ((size_t)b * a.V + v) * 3;
-          o[0] = ox; o[1] = oy; o[2] = oz;
-          if (kHasCam) {         // transform_smpl (utils.py:237-239): R v + t about the origin; camR = c0.xyz c0.w c1.xy | c1.zw c2.x, t = c2.yzw
-            const float4 c0 = *reinterpret_cast<const float4*>(rec + kTcRecCam);
-            const float4 c1 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 4);
-            const float4 c2 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 8);
-            float* oc = a.out_cam + ((size_t)b * a.V + v) * 3;
-            oc[0] = fmaf(c0.x, ox, fmaf(c0.y, oy, c0.z * oz)) + c2.y;
-            oc[1] = fmaf(c0.w, ox, fmaf(c1.x, oy, c1.y * oz)) + c2.z;
-            oc[2] = fmaf(c1.z, ox, fmaf(c1.w, oy, c2.x * oz)) + c2.w;
+          for (int l = 0; l < 10; ++l) {
+            x = fmaf(S[0][l], be[l], x);
+            y = fmaf(S[1][l], be[l], y);
+            z = fmaf(S[2][l], be[l], z);
+          }
+          x = fmaf(__uint_as_float(dx[mi]), inv_scale, x);
+          y = fmaf(__uint_as_float(dy[mi]), inv_scale, y);
+          z = fmaf(__uint_as_float(dz[mi]), inv_scale, z);
+          // T = sum_k w_k A_k (lbs.py:209-213)
+          float T[12];
+#pragma unroll
+          for (int e = 0; e < 12; ++e) T[e] = 0.f;
+#pragma unroll
+          for (int k = 0; k < kTcMaxKW; ++k) {
+            if (k >= kw_warp) break;                     // warp-uniform
+            const float w = jw[k];
+            const float4* Aj = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(rec) + joff[k]);
+            const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
+            T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
+            T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
+            T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+          }
+          // v = T [v_posed; 1] (lbs.py:215-220) + transl (body_models.py:980-982)
+          float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
+          float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
+          float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
+          if (a.has_transl) {
+            const float4 tr = *reinterpret_cast<const float4*>(rec + kTcRecTransl);
+            ox += tr.x; oy += tr.y; oz += tr.z;
+          }
+          if (valid) {
+            float* o = a.out + ((size_t)b * a.V + v) * 3;
+            o[0] = ox; o[1] = oy; o[2] = oz;
+            if (kHasCam) {         // transform_smpl (utils.py:237-239): R v + t about the origin; camR = c0.xyz c0.w c1.xy | c1.zw c2.x, t = c2.yzw
+              const float4 c0 = *reinterpret_cast<const float4*>(rec + kTcRecCam);
+              const float4 c1 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 4);
+              const float4 c2 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 8);
+              float* oc = a.out_cam + ((size_t)b * a.V + v) * 3;
+              oc[0] = fmaf(c0.x, ox, fmaf(c0.y, oy, c0.z * oz)) + c2.y;
+              oc[1] = fmaf(c0.w, ox, fmaf(c1.x, oy, c1.y * oz)) + c2.z;
+              oc[2] = fmaf(c1.z, ox, fmaf(c1.w, oy, c2.x * oz)) + c2.w;
+            }
           }
         }
       }
@@ -380,8 +399,10 @@ static int pick_tiles_per_cta(int vtiles, int tiles_total) {
 int smplx_tc_forward(const SmplxDev& d, const SmplxTc& tc, const TcCall& c, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_tc_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_tc_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_tc_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
   CUtensorMap tmFh, tmFl;
@@ -396,8 +417,14 @@ int smplx_tc_forward(const SmplxDev& d, const SmplxTc& tc, const TcCall& c, cuda
   a.rec = c.rec; a.out = c.out; a.out_cam = c.out_cam;
   a.vrows = tc.vtiles * 128;
   dim3 grid(tc.vtiles, ceil_div(a.tiles_total, a.tiles_per_cta));
-  if (c.out_cam) smplx_vertex_tc_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
-  else smplx_vertex_tc_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
+  static const int un = getenv("AIRPOSE_SMPLX_UNROLL") ? atoi(getenv("AIRPOSE_SMPLX_UNROLL")) : 4;
+  if (un == 2) {
+    if (c.out_cam) smplx_vertex_tc_kernel<true, 2><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
+    else smplx_vertex_tc_kernel<false, 2><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
+  } else {
+    if (c.out_cam) smplx_vertex_tc_kernel<true, 4><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
+    else smplx_vertex_tc_kernel<false, 4><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
+  }
   AP_LAUNCH_CHECK();
   return 0;
 }
