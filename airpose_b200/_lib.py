@@ -92,6 +92,19 @@ class HmrIefArgs(C.Structure):
                 ("out_pose", C.c_void_p), ("out_betas", C.c_void_p), ("out_cam", C.c_void_p)]
 
 
+class IefTrainArgs(C.Structure):
+    _fields_ = ([("batch", C.c_int32), ("iters", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("xf0", "xf1", "bb0", "bb1", "pos0", "pos1")] +
+                [("init_theta0", C.c_void_p), ("init_theta1", C.c_void_p), ("init_theta_stride", C.c_int32),
+                 ("init_shape0", C.c_void_p), ("init_shape1", C.c_void_p), ("init_shape_stride", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("fc1_w", "fc1_b", "fc2_w", "fc2_b", "decpose_w", "decpose_b", "decshape_w", "decshape_b",
+                                           "init_pose", "init_shape", "mask1", "mask2", "saved", "workspace",
+                                           "out_pose0", "out_betas0", "out_pose1", "out_betas1",
+                                           "g_pose0", "g_betas0", "g_pose1", "g_betas1",
+                                           "g_fc1_w", "g_fc1_b", "g_fc2_w", "g_fc2_b", "g_decpose_w", "g_decpose_b",
+                                           "g_decshape_w", "g_decshape_b", "g_xf0", "g_xf1")])
+
+
 class IefArgs(C.Structure):
     _fields_ = [("batch", C.c_int32), ("iters", C.c_int32),
                 ("xf0", C.c_void_p), ("xf1", C.c_void_p), ("bb0", C.c_void_p), ("bb1", C.c_void_p),
@@ -157,6 +170,10 @@ SYMBOLS = {
     "airpose_backbone_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "airpose_backbone_fwd_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "airpose_ief_fwd": (C.c_int, [C.c_void_p, C.POINTER(IefArgs), C.c_void_p]),
+    "airpose_ief_train_saved_floats": (C.c_int64, [C.c_int32, C.c_int32]),
+    "airpose_ief_train_workspace_floats": (C.c_int64, [C.c_int32]),
+    "airpose_ief_train_fwd": (C.c_int, [C.POINTER(IefTrainArgs), C.c_void_p]),
+    "airpose_ief_train_bwd": (C.c_int, [C.POINTER(IefTrainArgs), C.c_void_p]),
     "airpose_hmr_load": (C.c_int, [C.c_void_p, C.POINTER(HmrParams), C.c_void_p]),
     "airpose_hmr_ief_fwd": (C.c_int, [C.c_void_p, C.POINTER(HmrIefArgs), C.c_void_p]),
     "airpose_adam_step": (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),

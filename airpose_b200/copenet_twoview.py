@@ -59,8 +59,7 @@ class copenet_twoview(nn.Module):
         bb0, bb1 = input_batch["bb0"], input_batch["bb1"]
         intr = (input_batch["intr0"], input_batch["intr1"])
         B = im0.shape[0]
-        dev = im0.device
-        in_trans = torch.tensor([0.0, 0.0, 10.0], device=dev, dtype=torch.float32).expand(B, -1).clone() * TRANS_SCALE      # :184-203
+        in_trans, in_trans_unscaled = self._init_translation(B, im0.device)
         reg_iters = getattr(self.hparams, "reg_iters", 3)
         mark("trunk")
         xf = self.model.forward_feat_ext_pair(im0, im1)                         # both views, one call (eval-mode BN)
@@ -68,8 +67,26 @@ class copenet_twoview(nn.Module):
         mark("ief")
         pred = self.model._ief(xf[:B], xf[B:], bb0, bb1, in_trans, in_trans, None, None, None, None, reg_iters)
         mark("ief")
-        out = {}
         mark("smplx")
+        out = self._after_regressor(pred, intr, in_trans_unscaled)
+        mark("smplx")
+        return out
+
+    def _init_translation(self, B, dev):
+        """initial translation [0,0,10] * 0.05 (:184-203); cached per (B, device): building it from a Python list is a
+        synchronous host->device copy, i.e. a host sync in every step."""
+        key = (B, str(dev))
+        cache = self.__dict__.setdefault("_init_cache", {})
+        if key not in cache:
+            it = torch.tensor([0.0, 0.0, 10.0], dtype=torch.float32).expand(B, -1).clone()
+            cache[key] = ((it * TRANS_SCALE).to(dev), it.to(dev))
+        return cache[key]
+
+    def _after_regressor(self, pred, intr, in_trans_unscaled):
+        """copenet_twoview.py:214-317 from the regressor outputs on: translation un-scaling, 6D -> rotation matrices,
+        SMPL-X, transform_smpl, perspective_projection (fused into one native call per view)."""
+        B = pred[0].shape[0]
+        out = {}
         for v in (0, 1):
             pose, betas = pred[2 * v], pred[2 * v + 1]
             pose[:, :3] /= TRANS_SCALE                                   # in-place on the view, like :214-218
@@ -82,11 +99,10 @@ class copenet_twoview(nn.Module):
                 root_R=rotmat[:, 0], root_t=trans,                        # transform_smpl (:287-292)
                 focal_length=self.focal_length, camera_center=intr[v][:, :2, 2])   # :307-317
             out.update({"pred_pose%d" % v: pose, "pred_betas%d" % v: betas, "pred_rotmat%d" % v: rotmat,
-                        "pred_smpltrans%d" % v: trans, "in_smpltrans%d" % v: in_trans / TRANS_SCALE,
+                        "pred_smpltrans%d" % v: trans, "in_smpltrans%d" % v: in_trans_unscaled,
                         "pred_output_cam%d" % v: mo,
                         "pred_vertices_cam%d" % v: cam["vertices_cam"], "pred_joints_cam%d" % v: cam["joints_cam"],
                         "pred_joints_2d_cam%d" % v: cam["joints_2d"]})
-        mark("smplx")
         return out
 
     def _hp(self, name):
@@ -196,3 +212,37 @@ class copenet_twoview(nn.Module):
             grads["pred_pose%d" % v] = g_pose
             grads["pred_betas%d" % v] = g["betas%d" % v] + sg["betas"]
         return loss, losses, grads
+
+    # ------------------------------------------------------------------ regressor-only training step
+    def configure_optimizers_reg_only(self):
+        """The optimizer of copenet_twoview.py:416-425 (Adam, amsgrad) over the parameters the reference's
+        ``train_reg_only`` switch leaves trainable (copenet_real/.../copenet_twoview.py:357-372): fc1, fc2, decpose,
+        decshape (deccam has no gradient in the two-view model and is left out)."""
+        from .optim import Adam
+        params = dict(self.model.named_parameters())
+        return Adam([params[n] for n in self.model.REG_PARAMS], lr=float(getattr(self.hparams, "lr", 5e-5)), amsgrad=True)
+
+    @torch.no_grad()
+    def training_step_reg_only(self, input_batch, optimizer, mask1=None, mask2=None):
+        """One data-parallel training step of the regressor with the trunk frozen: the reference's ``train_reg_only``
+        fine-tuning mode with copenet's loss.  Forward: trunk features (frozen, eval-mode BatchNorm -- the reference
+        leaves the module in train mode there, so its frozen trunk still normalises with batch statistics; that
+        training-mode trunk forward is not built), regressor with dropout, SMPL-X, projection, get_loss.  Backward:
+        loss -> SMPL-X -> rot6d -> regressor, parameter gradients written straight into the optimizer's flat
+        gradient buffer.  Then ONE all-reduce of that buffer over the data-parallel ranks (NCCL) and one Adam launch.
+        Returns ``(loss, losses)`` as device tensors (no host sync)."""
+        im0, im1 = input_batch["im0"].float(), input_batch["im1"].float()
+        B = im0.shape[0]
+        in_trans, in_trans_unscaled = self._init_translation(B, im0.device)
+        reg_iters = getattr(self.hparams, "reg_iters", 3)
+        xf = self.model.forward_feat_ext_pair(im0, im1)
+        pred, ctx = self.model.ief_train_forward(xf[:B], xf[B:], input_batch["bb0"], input_batch["bb1"], in_trans, in_trans,
+                                                 iters=reg_iters, mask1=mask1, mask2=mask2)
+        out = self._after_regressor(pred, (input_batch["intr0"], input_batch["intr1"]), in_trans_unscaled)
+        loss, losses, g = self.loss_and_head_backward(input_batch, out)
+        optimizer.zero_grad()
+        self.model.ief_train_backward(ctx, g["pred_pose0"], g["pred_betas0"], g["pred_pose1"], g["pred_betas1"],
+                                      into_param_grads=True)
+        scale = optimizer.allreduce_grads()
+        optimizer.step(grad_scale=scale)
+        return loss, losses

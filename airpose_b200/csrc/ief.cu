@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kDecPad) ief_base_kernel(int B, const float* _
 #pragma unroll
   for (int r = 0; r < kIefRows; ++r) acc[r] = 0.f;
   const float* gp = GxT + (size_t)ks * kIefKPer * kDecPad + o;
-#pragma unroll 4
+#pragma unroll 16
   for (int k = 0; k < kIefKPer; ++k) {
     const float gv = __ldg(gp + (size_t)k * kDecPad);
 #pragma unroll
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kDecPad) ief_base_rows_kernel(int M, const flo
 #pragma unroll
   for (int r = 0; r < kIefRows; ++r) acc[r] = 0.f;
   const float* gp = GxT + (size_t)ks * kIefKPer * kDecPad + o;
-#pragma unroll 4
+#pragma unroll 16
   for (int k = 0; k < kIefKPer; ++k) {
     const float gv = __ldg(gp + (size_t)k * kDecPad);
 #pragma unroll
@@ -164,8 +164,16 @@ __global__ void __launch_bounds__(2 * kDecPad) ief_iter_kernel(IefIterArgs a) {
     __syncthreads();
     float d = base;
     if (o < kDec) {
+      // four partial sums and 16-deep unrolling: the loop is a chain of L2 loads, not of FMAs
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll 4
-      for (int k = 0; k < kState; ++k) d = fmaf(__ldg(gu + (size_t)k * kDecPad), u[v][k], d);
+      for (int k = 0; k < kState; k += 4) {
+        d0 = fmaf(__ldg(gu + (size_t)(k + 0) * kDecPad), u[v][k + 0], d0);
+        d1 = fmaf(__ldg(gu + (size_t)(k + 1) * kDecPad), u[v][k + 1], d1);
+        d2 = fmaf(__ldg(gu + (size_t)(k + 2) * kDecPad), u[v][k + 2], d2);
+        d3 = fmaf(__ldg(gu + (size_t)(k + 3) * kDecPad), u[v][k + 3], d3);
+      }
+      d += (d0 + d1) + (d2 + d3);
     }
     __syncthreads();
     if (o < kDec) st[v][o] += d;          // pred = previous + decoder output  (:195-202)

@@ -257,6 +257,90 @@ class copenet(nn.Module):
             _lib.check(lib.airpose_ief_fwd(h, C.byref(a), _lib.current_stream()), "airpose_ief_fwd")
         return tuple(outs)
 
+    # ------------------------------------------------------------------ training-mode regressor (dropout; forward + backward)
+    REG_PARAMS = ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "decpose.weight", "decpose.bias",
+                  "decshape.weight", "decshape.bias")
+
+    def _ief_train_args(self, ctx):
+        a = _lib.IefTrainArgs()
+        a.batch, a.iters = ctx["B"], ctx["iters"]
+        for n in ("xf0", "xf1", "bb0", "bb1", "pos0", "pos1"):
+            setattr(a, n, ctx[n].data_ptr())
+        a.fc1_w, a.fc1_b = self.fc1.weight.data_ptr(), self.fc1.bias.data_ptr()
+        a.fc2_w, a.fc2_b = self.fc2.weight.data_ptr(), self.fc2.bias.data_ptr()
+        a.decpose_w, a.decpose_b = self.decpose.weight.data_ptr(), self.decpose.bias.data_ptr()
+        a.decshape_w, a.decshape_b = self.decshape.weight.data_ptr(), self.decshape.bias.data_ptr()
+        a.init_pose, a.init_shape = self.init_pose.data_ptr(), self.init_shape.data_ptr()
+        if ctx["mask1"] is not None:
+            a.mask1, a.mask2 = ctx["mask1"].data_ptr(), ctx["mask2"].data_ptr()
+        a.saved, a.workspace = ctx["saved"].data_ptr(), ctx["workspace"].data_ptr()
+        return a
+
+    def ief_train_forward(self, xf0, xf1, bb0, bb1, pos0, pos1, iters=3, mask1=None, mask2=None, p_drop=0.5):
+        """The regressor loop of ``forward`` (model_copenet.py:118-159) with dropout ACTIVE, saving what the backward
+        needs.  ``mask1``/``mask2`` [iters,2,B,1024]: multiplicative dropout masks (0 or 1/(1-p)); drawn here with
+        ``torch.bernoulli`` on the device when omitted, ``False`` disables dropout (eval semantics).
+        Returns ``(pred_pose0, pred_betas0, pred_pose1, pred_betas1), ctx``."""
+        device = self.conv1.weight.device
+        if device.type != "cuda":
+            raise _lib.AirposeError("ief_train_forward runs on CUDA only; there is no CPU path")
+        lib = _lib.load()
+        f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        B = xf0.shape[0]
+        ctx = {"B": B, "iters": int(iters)}
+        for n, t in (("xf0", xf0), ("xf1", xf1), ("bb0", bb0), ("bb1", bb1), ("pos0", pos0), ("pos1", pos1)):
+            ctx[n] = f(t)
+        if mask1 is None and mask2 is None:
+            keep = torch.full((iters, 2, B, 1024), 1.0 - p_drop, device=device, dtype=torch.float32)
+            mask1 = torch.bernoulli(keep) / (1.0 - p_drop)
+            mask2 = torch.bernoulli(keep) / (1.0 - p_drop)
+        if mask1 is False:
+            mask1 = mask2 = None
+        ctx["mask1"] = None if mask1 is None else f(mask1)
+        ctx["mask2"] = None if mask2 is None else f(mask2)
+        ctx["saved"] = torch.empty(int(lib.airpose_ief_train_saved_floats(B, iters)), device=device, dtype=torch.float32)
+        ctx["workspace"] = torch.empty(int(lib.airpose_ief_train_workspace_floats(B)), device=device, dtype=torch.float32)
+        outs = [torch.empty(B, 135, device=device, dtype=torch.float32), torch.empty(B, 10, device=device, dtype=torch.float32),
+                torch.empty(B, 135, device=device, dtype=torch.float32), torch.empty(B, 10, device=device, dtype=torch.float32)]
+        a = self._ief_train_args(ctx)
+        a.out_pose0, a.out_betas0, a.out_pose1, a.out_betas1 = (t.data_ptr() for t in outs)
+        with torch.cuda.device(device):
+            _lib.check(lib.airpose_ief_train_fwd(C.byref(a), _lib.current_stream()), "airpose_ief_train_fwd")
+        return tuple(outs), ctx
+
+    def ief_train_backward(self, ctx, g_pose0, g_betas0, g_pose1, g_betas1, want_feature_grads=False, into_param_grads=False):
+        """Backward of ``ief_train_forward``: returns a dict of gradients keyed like ``state_dict`` (``fc1.weight`` ...),
+        plus ``xf0``/``xf1`` when ``want_feature_grads``.  ``into_param_grads=True`` writes straight into the parameters'
+        ``.grad`` tensors (e.g. the flat gradient buffer of ``airpose_b200.optim.Adam``)."""
+        device = self.conv1.weight.device
+        lib = _lib.load()
+        f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        ups = [f(g_pose0), f(g_betas0), f(g_pose1), f(g_betas1)]
+        params = dict(self.named_parameters())
+        grads = {}
+        for n in self.REG_PARAMS:
+            p = params[n]
+            if into_param_grads:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                grads[n] = p.grad
+            else:
+                grads[n] = torch.empty_like(p)
+        a = self._ief_train_args(ctx)
+        a.g_pose0, a.g_betas0, a.g_pose1, a.g_betas1 = (t.data_ptr() for t in ups)
+        a.g_fc1_w, a.g_fc1_b = grads["fc1.weight"].data_ptr(), grads["fc1.bias"].data_ptr()
+        a.g_fc2_w, a.g_fc2_b = grads["fc2.weight"].data_ptr(), grads["fc2.bias"].data_ptr()
+        a.g_decpose_w, a.g_decpose_b = grads["decpose.weight"].data_ptr(), grads["decpose.bias"].data_ptr()
+        a.g_decshape_w, a.g_decshape_b = grads["decshape.weight"].data_ptr(), grads["decshape.bias"].data_ptr()
+        if want_feature_grads:
+            grads["xf0"] = torch.empty(ctx["B"], 2048, device=device, dtype=torch.float32)
+            grads["xf1"] = torch.empty(ctx["B"], 2048, device=device, dtype=torch.float32)
+            a.g_xf0, a.g_xf1 = grads["xf0"].data_ptr(), grads["xf1"].data_ptr()
+        with torch.cuda.device(device):
+            _lib.check(lib.airpose_ief_train_bwd(C.byref(a), _lib.current_stream()), "airpose_ief_train_bwd")
+        del ups
+        return grads
+
     def forward_reg(self, xf0, xf1, bb0, bb1, pred_position0, pred_position1, pred_orient0, pred_orient1,
                     pred_art_pose0, pred_art_pose1, pred_shape0, pred_shape1):
         """One regressor pass (model_copenet.py:178-204), eval mode."""

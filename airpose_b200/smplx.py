@@ -216,6 +216,19 @@ class SMPLX(nn.Module):
     def _f32c(t, device):
         return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
+    @staticmethod
+    def _rows(t, device, width):
+        """[B, width] row view of ``t`` without a copy when each sample's block is contiguous (e.g. ``rotmat[:, 1:]``,
+        ``pose[:, :3]``: the C ABI takes a row stride); falls back to a contiguous copy.  Returns (tensor, stride)."""
+        t = t.detach()
+        if t.device != device or t.dtype != torch.float32:
+            t = t.to(device=device, dtype=torch.float32)
+        B = t.shape[0]
+        if t.numel() == B * width and B > 0 and t[0].is_contiguous() and (B == 1 or t.stride(0) >= width):
+            return t, (t.stride(0) if B > 1 else width)
+        t = t.contiguous().reshape(B, width)
+        return t, width
+
     # ------------------------------------------------------------------ forward
     def forward(self, betas=None, global_orient=None, body_pose=None, left_hand_pose=None, right_hand_pose=None,
                 transl=None, expression=None, jaw_pose=None, leye_pose=None, reye_pose=None, return_verts=True,
@@ -246,6 +259,8 @@ class SMPLX(nn.Module):
 
         def rot_or_identity(t, name, nj):
             if t is not None:
+                if nj == 21 and t.dim() == 4 and tuple(t.shape[1:]) == (21, 3, 3):
+                    return t                          # body_pose: handed over as a strided row view below
                 return self._f32c(t, device).reshape(-1, nj, 3, 3)
             if not self._is_zero(name):
                 raise NotImplementedError("non-zero module parameter '{}' with pose2rot=False needs batch_rodrigues, "
@@ -297,7 +312,8 @@ class SMPLX(nn.Module):
         if go is not None:
             a.global_orient = go.data_ptr(); a.global_orient_stride = 9
         if bp is not None:
-            a.body_pose = bp.data_ptr(); a.body_pose_stride = 21 * 9
+            bp, bp_stride = self._rows(bp, device, 189)
+            a.body_pose = bp.data_ptr(); a.body_pose_stride = bp_stride
         if tail is not None:
             a.tail_pose = tail.data_ptr(); a.tail_pose_stride = 33 * 9
         if tr is not None:
@@ -305,9 +321,9 @@ class SMPLX(nn.Module):
         keep = [shape_comp, go, bp, tail, tr]
         if root_R is not None or root_t is not None:
             if root_R is not None:
-                rR = self._f32c(root_R, device).reshape(B, 9); a.root_R = rR.data_ptr(); a.root_R_stride = 9; keep.append(rR)
+                rR, st = self._rows(root_R, device, 9); a.root_R = rR.data_ptr(); a.root_R_stride = st; keep.append(rR)
             if root_t is not None:
-                rt = self._f32c(root_t, device).reshape(B, 3); a.root_t = rt.data_ptr(); a.root_t_stride = 3; keep.append(rt)
+                rt, st = self._rows(root_t, device, 3); a.root_t = rt.data_ptr(); a.root_t_stride = st; keep.append(rt)
             cam["vertices_cam"] = torch.empty(B, V, 3, device=device, dtype=torch.float32)
             cam["joints_cam"] = torch.empty(B, nj, 3, device=device, dtype=torch.float32)
             a.out_vertices_cam = cam["vertices_cam"].data_ptr()
@@ -330,7 +346,7 @@ class SMPLX(nn.Module):
         if return_full_pose:
             eye = torch.eye(3, device=device, dtype=torch.float32).expand(B, 1, 3, 3)
             full_pose = torch.cat([go if go is not None else eye,
-                                   bp if bp is not None else eye.expand(B, 21, 3, 3),
+                                   (bp.reshape(B, 21, 3, 3) if bp.dim() == 2 else bp) if bp is not None else eye.expand(B, 21, 3, 3),
                                    tail if tail is not None else eye.expand(B, 33, 3, 3)], dim=1)
         out = ModelOutput(vertices=vertices if return_verts else None, joints=joints,
                           betas=betas if betas is not None else self.betas,

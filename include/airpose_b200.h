@@ -210,6 +210,38 @@ typedef struct {
 } airpose_ief_args;
 int airpose_ief_fwd(airpose_net_t* h, const airpose_ief_args* a, void* stream);
 
+/* Training-mode regressor (dropout active, so no collapse): forward that saves its activations, and the backward pass
+ * autograd would run through copenet.forward's regressor loop (model_copenet.py:118-159,178-204).  Parameters are read
+ * live from the module's fp32 tensors (DEVICE pointers).  mask1/mask2: multiplicative dropout masks
+ * [iters][2 views][B][1024] (0 or 1/(1-p)) drawn by the caller, or both NULL for eval semantics.  `saved` must hold
+ * airpose_ief_train_saved_floats(B, iters) floats and live from fwd to bwd; `workspace` holds
+ * airpose_ief_train_workspace_floats(B) floats.  bwd overwrites every g_* buffer (parameter gradients are summed over
+ * the iterations and views in a fixed order); g_xf0/g_xf1 (d loss / d trunk features, the entry point of the trunk
+ * backward) are optional.  This is the trainable part of copenet_real's `train_reg_only` mode
+ * (copenet_real/src/copenet_real/copenet_twoview.py:357-372). */
+typedef struct {
+  int32_t batch, iters;
+  const float* xf0; const float* xf1;
+  const float* bb0; const float* bb1;
+  const float* pos0; const float* pos1;
+  const float* init_theta0; const float* init_theta1; int32_t init_theta_stride;
+  const float* init_shape0; const float* init_shape1; int32_t init_shape_stride;
+  const float* fc1_w; const float* fc1_b; const float* fc2_w; const float* fc2_b;
+  const float* decpose_w; const float* decpose_b; const float* decshape_w; const float* decshape_b;
+  const float* init_pose; const float* init_shape;
+  const float* mask1; const float* mask2;
+  float* saved; float* workspace;
+  float* out_pose0; float* out_betas0; float* out_pose1; float* out_betas1;               /* fwd */
+  const float* g_pose0; const float* g_betas0; const float* g_pose1; const float* g_betas1; /* bwd: upstream */
+  float* g_fc1_w; float* g_fc1_b; float* g_fc2_w; float* g_fc2_b;
+  float* g_decpose_w; float* g_decpose_b; float* g_decshape_w; float* g_decshape_b;
+  float* g_xf0; float* g_xf1;
+} airpose_ief_train_args;
+int64_t airpose_ief_train_saved_floats(int32_t batch, int32_t iters);
+int64_t airpose_ief_train_workspace_floats(int32_t batch);
+int airpose_ief_train_fwd(const airpose_ief_train_args* a, void* stream);
+int airpose_ief_train_bwd(const airpose_ief_train_args* a, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * hmr baseline: single view, same trunk  (copenet/src/copenet/models/model_hmr.py:48-172; BASELINE config 1)
  * ---------------------------------------------------------------------------------- */

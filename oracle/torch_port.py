@@ -60,6 +60,26 @@ def ief(sd, xf0, xf1, bb0, bb1, pos0, pos1, iters=3):
     return p0, sh0, p1, sh1
 
 
+def ief_train(sd, xf0, xf1, bb0, bb1, pos0, pos1, mask1, mask2, iters=3):
+    """The same loop in training mode (model_copenet.py:186-189: fc1 -> drop1 -> fc2 -> drop2) with the dropout masks
+    given explicitly: mask[it, view] is the multiplicative mask (0 or 1/(1-p)) of that Dropout call.  Differentiable:
+    the parity tests of the CUDA backward run autograd through it."""
+    b = xf0.shape[0]
+    ori0 = ori1 = sd["init_pose"][:, :6].expand(b, -1)
+    art0 = art1 = sd["init_pose"][:, 6:132].expand(b, -1)
+    sh0 = sh1 = sd["init_shape"].expand(b, -1)
+    lin = lambda x, n: F.linear(x, sd[n + ".weight"], sd[n + ".bias"])
+    for it in range(int(iters)):
+        xc0 = lin(lin(torch.cat([xf0, bb0, pos0, ori0, art0, sh0, art1, sh1], 1), "fc1") * mask1[it, 0], "fc2") * mask2[it, 0]
+        xc1 = lin(lin(torch.cat([xf1, bb1, pos1, ori1, art1, sh1, art0, sh0], 1), "fc1") * mask1[it, 1], "fc2") * mask2[it, 1]
+        p0 = torch.cat([pos0, ori0, art0], 1) + lin(xc0, "decpose")
+        p1 = torch.cat([pos1, ori1, art1], 1) + lin(xc1, "decpose")
+        sh0, sh1 = sh0 + lin(xc0, "decshape"), sh1 + lin(xc1, "decshape")
+        pos0, ori0, art0 = p0[:, :3], p0[:, 3:9], p0[:, 9:]
+        pos1, ori1, art1 = p1[:, :3], p1[:, 3:9], p1[:, 9:]
+    return p0, sh0, p1, sh1
+
+
 def rot6d_to_rotmat(x):
     """geometry.py:47-61."""
     x = x.reshape(-1, 3, 2)

@@ -636,6 +636,53 @@ def test_rot6d_backward_matches_autograd():
     assert rel_err(got.cpu().numpy(), x.grad[:, 3:].numpy()) < 1e-5
 
 
+def _port_twoview_loss(tp, m, raw, gt, x, B):
+    """copenet_twoview.py:214-317 + get_loss (:83-161) on the PyTorch port, from the network's raw outputs (translation
+    still scaled by 0.05), in the current default dtype; differentiable."""
+    G = {k: torch.tensor(v, dtype=torch.float64) for k, v in gt.items()}
+    hp = orc.DEFAULT_LOSS_WEIGHTS
+    mse = lambda a, b: (a - b) ** 2
+    P = {}
+    for v in (0, 1):
+        pose = raw["pose%d" % v]
+        trans = pose[:, :3] / 0.05
+        R = tp.rot6d_to_rotmat(pose[:, 3:]).view(B, 22, 3, 3)
+        verts, joints = tp.smplx_forward(m, raw["betas%d" % v], R[:, 1:])
+        jc = torch.bmm(R[:, 0], joints.permute(0, 2, 1)).permute(0, 2, 1) + trans[:, None]
+        c = torch.tensor(x["intr%d" % v][:, :2, 2], dtype=torch.float64)
+        j2d = torch.stack([1475.0 * jc[:, :, 0] / jc[:, :, 2] + c[:, None, 0], 1475.0 * jc[:, :, 1] / jc[:, :, 2] + c[:, None, 1]], -1)
+        P[v] = dict(trans=trans, R=R, verts=verts, joints=joints, j2d=j2d, betas=raw["betas%d" % v])
+    w3 = torch.ones(22); w3[[4, 5, 18, 19]] = hp["limbs3d_loss_weight"]; w3[[7, 8, 20, 21]] = hp["limbs3d_loss_weight"] ** 2
+    wt = torch.ones(21); wt[[3, 4, 17, 18]] = hp["limbstheta_loss_weight"]; wt[[6, 7, 19, 20]] = hp["limbstheta_loss_weight"] ** 2
+    gvv, gjj = G["smpl_vertices"].squeeze(1), G["smpl_joints"].squeeze(1)
+    l_kp = sum(mse(P[v]["j2d"][:, :22], G["smpl_joints_2d%d" % v].squeeze(1)[:, :22]).mean() for v in (0, 1))
+    l3 = mse(P[0]["joints"][:, :22], gjj[:, :22]) + mse(P[1]["joints"][:, :22], gjj[:, :22]) + mse(P[0]["joints"][:, :22], P[1]["joints"][:, :22])
+    l_kp3d = (l3 * w3.view(1, 22, 1)).mean()
+    l_shape = mse(P[0]["verts"], gvv).mean() + mse(P[1]["verts"], gvv).mean() + mse(P[0]["verts"], P[1]["verts"]).mean()
+    l_trans = sum(mse(P[v]["trans"], G["smpltrans_rel%d" % v]).mean() for v in (0, 1))
+    l_root = sum(mse(P[v]["R"][:, :1], G["smplorient_rel%d" % v]).mean() for v in (0, 1))
+    lr = mse(P[0]["R"][:, 1:], G["smplpose_rotmat"]) + mse(P[1]["R"][:, 1:], G["smplpose_rotmat"]) + mse(P[0]["R"][:, 1:], P[1]["R"][:, 1:])
+    l_pose = (lr * wt.view(1, 21, 1, 1)).mean()
+    b0, b1 = P[0]["betas"], P[1]["betas"]
+    l_beta = (b0 * b0).mean() + (b1 * b1).mean() + mse(b0, b1).mean()
+    return 60 * (hp["trans_loss_weight"] * l_trans + hp["keypoint2d_loss_weight"] * l_kp + hp["keypoint3d_loss_weight"] * l_kp3d
+                 + hp["shape_loss_weight"] * l_shape + hp["rootrot_loss_weight"] * l_root + hp["pose_loss_weight"] * l_pose
+                 + hp["beta_loss_weight"] * l_beta)
+
+
+def _synthetic_gt(tp, m, B, x, seed=5):
+    """ground truth for the loss: SMPL-X forward of an independent seeded sample; fp64 default dtype on."""
+    rng = np.random.default_rng(seed)
+    gt_in = synthetic.make_lbs_inputs(B, seed=9)
+    gv, gj = tp.smplx_forward(m, torch.tensor(gt_in["betas"], dtype=torch.float64), torch.tensor(gt_in["body_pose"], dtype=torch.float64))
+    r6 = lambda: synthetic.rot6d_to_rotmat_np(np.array([1, 0, 0, 1, 0, 0], np.float32) + rng.standard_normal((B, 6)).astype(np.float32) * 0.3)[:, None]
+    return {"smplpose_rotmat": gt_in["body_pose"], "smplorient_rel0": r6(), "smplorient_rel1": r6(),
+            "smpl_vertices": gv.numpy().astype(np.float32)[:, None], "smpl_joints": gj.numpy().astype(np.float32)[:, None],
+            "smpl_joints_2d0": (rng.standard_normal((B, 1, 127, 2)) * 50 + 500).astype(np.float32),
+            "smpl_joints_2d1": (rng.standard_normal((B, 1, 127, 2)) * 50 + 500).astype(np.float32),
+            "smpltrans_rel0": x["smpltrans_rel0"], "smpltrans_rel1": x["smpltrans_rel1"]}
+
+
 def test_loss_and_head_backward_matches_autograd(tmp_path, smplx_dir, smplx_data, net_gpu, net_state):
     """d loss / d (regressor outputs) through get_loss, projection, transform_smpl, SMPL-X and rot6d_to_rotmat, against
     fp64 autograd over the PyTorch port of the same chain (copenet_twoview.py:205-317 + :83-161)."""
@@ -666,35 +713,7 @@ def test_loss_and_head_backward_matches_autograd(tmp_path, smplx_dir, smplx_data
             p[:, :3] *= 0.05
             raw["pose%d" % v] = p.cpu().double().requires_grad_(True)
             raw["betas%d" % v] = out["pred_betas%d" % v].cpu().double().requires_grad_(True)
-        G = {k: torch.tensor(v, dtype=torch.float64) for k, v in gt.items()}
-        hp = orc.DEFAULT_LOSS_WEIGHTS
-        mse = lambda a, b: (a - b) ** 2
-        P = {}
-        for v in (0, 1):
-            pose = raw["pose%d" % v]
-            trans = pose[:, :3] / 0.05
-            R = tp.rot6d_to_rotmat(pose[:, 3:]).view(B, 22, 3, 3)
-            verts, joints = tp.smplx_forward(m, raw["betas%d" % v], R[:, 1:])
-            jc = torch.bmm(R[:, 0], joints.permute(0, 2, 1)).permute(0, 2, 1) + trans[:, None]
-            c = torch.tensor(x["intr%d" % v][:, :2, 2], dtype=torch.float64)
-            j2d = torch.stack([1475.0 * jc[:, :, 0] / jc[:, :, 2] + c[:, None, 0], 1475.0 * jc[:, :, 1] / jc[:, :, 2] + c[:, None, 1]], -1)
-            P[v] = dict(trans=trans, R=R, verts=verts, joints=joints, j2d=j2d, betas=raw["betas%d" % v])
-        w3 = torch.ones(22); w3[[4, 5, 18, 19]] = hp["limbs3d_loss_weight"]; w3[[7, 8, 20, 21]] = hp["limbs3d_loss_weight"] ** 2
-        wt = torch.ones(21); wt[[3, 4, 17, 18]] = hp["limbstheta_loss_weight"]; wt[[6, 7, 19, 20]] = hp["limbstheta_loss_weight"] ** 2
-        gvv, gjj = G["smpl_vertices"].squeeze(1), G["smpl_joints"].squeeze(1)
-        l_kp = sum(mse(P[v]["j2d"][:, :22], G["smpl_joints_2d%d" % v].squeeze(1)[:, :22]).mean() for v in (0, 1))
-        l3 = mse(P[0]["joints"][:, :22], gjj[:, :22]) + mse(P[1]["joints"][:, :22], gjj[:, :22]) + mse(P[0]["joints"][:, :22], P[1]["joints"][:, :22])
-        l_kp3d = (l3 * w3.view(1, 22, 1)).mean()
-        l_shape = mse(P[0]["verts"], gvv).mean() + mse(P[1]["verts"], gvv).mean() + mse(P[0]["verts"], P[1]["verts"]).mean()
-        l_trans = sum(mse(P[v]["trans"], G["smpltrans_rel%d" % v]).mean() for v in (0, 1))
-        l_root = sum(mse(P[v]["R"][:, :1], G["smplorient_rel%d" % v]).mean() for v in (0, 1))
-        lr = mse(P[0]["R"][:, 1:], G["smplpose_rotmat"]) + mse(P[1]["R"][:, 1:], G["smplpose_rotmat"]) + mse(P[0]["R"][:, 1:], P[1]["R"][:, 1:])
-        l_pose = (lr * wt.view(1, 21, 1, 1)).mean()
-        b0, b1 = P[0]["betas"], P[1]["betas"]
-        l_beta = (b0 * b0).mean() + (b1 * b1).mean() + mse(b0, b1).mean()
-        ref = 60 * (hp["trans_loss_weight"] * l_trans + hp["keypoint2d_loss_weight"] * l_kp + hp["keypoint3d_loss_weight"] * l_kp3d
-                    + hp["shape_loss_weight"] * l_shape + hp["rootrot_loss_weight"] * l_root + hp["pose_loss_weight"] * l_pose
-                    + hp["beta_loss_weight"] * l_beta)
+        ref = _port_twoview_loss(tp, m, raw, gt, x, B)
         ref.backward()
     finally:
         torch.set_default_dtype(old)
@@ -706,3 +725,112 @@ def test_loss_and_head_backward_matches_autograd(tmp_path, smplx_dir, smplx_data
         eb = rel_err(grads["pred_betas%d" % v].cpu().numpy(), raw["betas%d" % v].grad.numpy())
         print("view %d: d loss/d pred_pose rel err %.3e, d loss/d pred_betas rel err %.3e" % (v, ep, eb))
         assert ep < 1e-3 and eb < 1e-3
+
+
+# ----------------------------------------------------------------------------- training-mode regressor (dropout), fwd + bwd
+@pytest.mark.parametrize("B,dropout", [(3, True), (40, True), (5, False)])
+def test_ief_train_forward_backward_match_autograd(net_gpu, net_state, B, dropout):
+    """airpose_ief_train_fwd / _bwd against fp64 autograd through the PyTorch port of the regressor loop with the SAME
+    dropout masks (oracle/torch_port.ief_train): outputs, all eight parameter gradients and d loss / d trunk features."""
+    import torch_port as tp
+    g = torch.Generator(device="cpu").manual_seed(B)
+    f32 = lambda *s: torch.randn(*s, generator=g)
+    xf0, xf1 = f32(B, 2048).abs(), f32(B, 2048).abs()
+    bb0, bb1, pos0, pos1 = f32(B, 3), f32(B, 3), f32(B, 3), f32(B, 3)
+    if dropout:
+        m1 = torch.bernoulli(torch.full((3, 2, B, 1024), 0.5), generator=g) * 2.0
+        m2 = torch.bernoulli(torch.full((3, 2, B, 1024), 0.5), generator=g) * 2.0
+    else:
+        m1 = m2 = None
+    up = [f32(B, 135), f32(B, 10), f32(B, 135), f32(B, 10)]
+    # reference: fp64 autograd
+    names = ("fc1", "fc2", "decpose", "decshape")
+    sd = {k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in net_state.items() if k.split(".")[0] in names or k.startswith("init_")}
+    for k in list(sd):
+        if k.split(".")[0] in names:
+            sd[k].requires_grad_(True)
+    x64 = [t.double().requires_grad_(True) for t in (xf0, xf1)]
+    one = torch.ones(3, 2, B, 1024, dtype=torch.float64)
+    ref = tp.ief_train(sd, x64[0], x64[1], bb0.double(), bb1.double(), pos0.double(), pos1.double(),
+                       m1.double() if dropout else one, m2.double() if dropout else one, iters=3)
+    sum((r * u.double()).sum() for r, u in zip(ref, up)).backward()
+    # CUDA
+    outs, ctx = net_gpu.ief_train_forward(xf0.to(DEV), xf1.to(DEV), bb0.to(DEV), bb1.to(DEV), pos0.to(DEV), pos1.to(DEV), iters=3,
+                                          mask1=m1.to(DEV) if dropout else False, mask2=m2.to(DEV) if dropout else False)
+    for o, r, n in zip(outs, ref, ("pose0", "betas0", "pose1", "betas1")):
+        e = rel_err(o.cpu().numpy(), r.detach().numpy())
+        assert e < 2e-5, (n, e)
+    if not dropout:          # eval semantics == the collapsed eval-mode kernel
+        ev = net_gpu._ief(xf0.to(DEV), xf1.to(DEV), bb0.to(DEV), bb1.to(DEV), pos0.to(DEV), pos1.to(DEV), None, None, None, None, 3)
+        for o, r in zip(outs, ev):
+            assert rel_err(o.cpu().numpy(), r.cpu().numpy()) < 2e-5
+    grads = net_gpu.ief_train_backward(ctx, *[u.to(DEV) for u in up], want_feature_grads=True)
+    for n in net_gpu.REG_PARAMS:
+        e = rel_err(grads[n].cpu().numpy(), sd[n].grad.numpy())
+        print("ief train B=%d dropout=%d  d/d %-16s rel err %.2e" % (B, dropout, n, e))
+        assert e < 5e-5, n
+    for n, x in (("xf0", x64[0]), ("xf1", x64[1])):
+        assert rel_err(grads[n].cpu().numpy(), x.grad.numpy()) < 5e-5, n
+
+
+def test_training_step_reg_only(tmp_path, smplx_dir, smplx_data, net_state):
+    """One regressor-only training step (frozen trunk, dropout masks given): the gradients that reach the optimizer's
+    flat buffer match fp64 autograd through the PyTorch port of regressor -> rot6d -> SMPL-X -> projection -> get_loss,
+    the Adam update matches torch.optim.Adam(amsgrad=True), and repeated steps on a fixed batch reduce the loss."""
+    import torch_port as tp
+    mod = _loss_module(tmp_path, smplx_dir)
+    # the reference's own decoder gain (xavier 0.01, model_copenet.py:74-76): with dropout doubling half of the hidden
+    # units the raised gains of the parity fixtures throw the poses far off and the projection term dominates everything
+    state = synthetic.make_network_state(123, dec_gain=0.01)
+    mod.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()})
+    mod = mod.to(DEV).eval()
+    opt = mod.configure_optimizers_reg_only()
+    B = 3
+    x = synthetic.make_inputs(B, 31)
+    _, m = _torch_smplx64(smplx_data)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    m1 = torch.bernoulli(torch.full((3, 2, B, 1024), 0.5), generator=g) * 2.0
+    m2 = torch.bernoulli(torch.full((3, 2, B, 1024), 0.5), generator=g) * 2.0
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        gt = _synthetic_gt(tp, m, B, x)
+        batch = {k: t(v) for k, v in {**x, **gt}.items()}
+        xf = mod.model.forward_feat_ext_pair(batch["im0"], batch["im1"]).cpu().double()
+        names = ("fc1", "fc2", "decpose", "decshape")
+        sd = {k: v.detach().cpu().double().clone() for k, v in mod.model.state_dict().items() if k.split(".")[0] in names or k.startswith("init_")}
+        ref_params = [sd[n].requires_grad_(True) for n in mod.model.REG_PARAMS]
+        init = torch.tensor([0.0, 0.0, 10.0]).expand(B, -1) * 0.05
+        p0, s0, p1, s1 = tp.ief_train(sd, xf[:B], xf[B:], torch.tensor(x["bb0"], dtype=torch.float64), torch.tensor(x["bb1"], dtype=torch.float64),
+                                      init, init, m1.double(), m2.double(), iters=3)
+        ref = _port_twoview_loss(tp, m, {"pose0": p0, "betas0": s0, "pose1": p1, "betas1": s1}, gt, x, B)
+        ref.backward()
+        ref_grads = [p.grad.clone() for p in ref_params]
+        topt = torch.optim.Adam(ref_params, lr=5e-5, weight_decay=0, amsgrad=True)
+        topt.step()
+    finally:
+        torch.set_default_dtype(old)
+    before = {n: p.detach().clone() for n, p in mod.model.named_parameters()}
+    loss, losses = mod.training_step_reg_only(batch, opt, mask1=m1.to(DEV), mask2=m2.to(DEV))
+    print("reg-only step: loss cuda %.4f port %.4f" % (float(loss), float(ref)))
+    assert abs(float(loss) - float(ref)) <= 1e-3 * abs(float(ref))
+    params = dict(mod.model.named_parameters())
+    for n, gref, pref in zip(mod.model.REG_PARAMS, ref_grads, ref_params):
+        eg = rel_err(params[n].grad.cpu().numpy(), gref.numpy())
+        # Adam's first step moves every element by ~lr * sign(g): compare the UPDATE, relative to lr, where the
+        # gradient is large enough for its sign to be beyond rounding
+        du = (params[n].detach().cpu().double() - before[n].cpu().double()).numpy()
+        dr = (pref.detach() - before[n].cpu().double()).numpy()
+        big = np.abs(gref.numpy()) > 1e-2 * np.abs(gref.numpy()).max()
+        eu = np.abs(du - dr)[big].max() / 5e-5
+        print("  %-16s grad rel err %.2e, update err / lr %.2e (%d elements)" % (n, eg, eu, int(big.sum())))
+        assert eg < 5e-3, n
+        assert eu < 5e-2, n
+    for n, p in mod.model.named_parameters():           # the trunk stays frozen
+        if n not in mod.model.REG_PARAMS:
+            assert torch.equal(p.detach(), before[n]), n
+    l0 = float(loss)
+    for _ in range(8):
+        loss, _ = mod.training_step_reg_only(batch, opt, mask1=m1.to(DEV), mask2=m2.to(DEV))
+    print("  loss after 9 steps on the same batch: %.4f -> %.4f" % (l0, float(loss)))
+    assert float(loss) < l0

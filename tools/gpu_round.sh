@@ -20,8 +20,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --
     --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_under_ncu.log 2>&1
 echo "ncu launches exit $?"
 # full capture: trunk GEMM kernels (a spread of layers) and the SMPL-X vertex kernel
-timeout 600 ncu --set full --clock-control none -k regex:gemm_ -s 60 -c 56 \
-    -o $OUT/prof_trunk python tools/run_once.py trunk 32 2 > $OUT/ncu_trunk.log 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:gemm_ -s 77 -c 77 \
+    -o $OUT/prof_trunk python tools/run_once.py trunk 128 2 > $OUT/ncu_trunk.log 2>&1
 echo "ncu trunk exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:smplx_ -s 3 -c 3 \
     -o $OUT/prof_lbs python tools/run_once.py lbs 8192 2 > $OUT/ncu_lbs.log 2>&1
