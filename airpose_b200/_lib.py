@@ -75,6 +75,11 @@ class NetParams(C.Structure):
                 ("init_pose", C.c_void_p), ("init_shape", C.c_void_p), ("bn_eps", C.c_float)]
 
 
+class BnTrainParams(C.Structure):
+    _fields_ = [("bn_weight", C.c_void_p * 53), ("bn_bias", C.c_void_p * 53), ("running_mean", C.c_void_p * 53),
+                ("running_var", C.c_void_p * 53), ("momentum", C.c_float), ("eps", C.c_float), ("saved_stats", C.c_void_p)]
+
+
 class HmrParams(C.Structure):
     _fields_ = [("conv", ConvParams * 53),
                 ("fc1_w", C.c_void_p), ("fc1_b", C.c_void_p), ("fc2_w", C.c_void_p), ("fc2_b", C.c_void_p),
@@ -168,6 +173,9 @@ SYMBOLS = {
     "airpose_net_destroy": (C.c_int, [C.c_void_p]),
     "airpose_net_load": (C.c_int, [C.c_void_p, C.POINTER(NetParams), C.c_void_p]),
     "airpose_backbone_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "airpose_bn_saved_stats_floats": (C.c_int64, []),
+    "airpose_backbone_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(BnTrainParams), C.c_void_p, C.c_void_p]),
+    "airpose_net_load_regressor": (C.c_int, [C.c_void_p, C.POINTER(NetParams), C.c_void_p]),
     "airpose_backbone_fwd_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "airpose_ief_fwd": (C.c_int, [C.c_void_p, C.POINTER(IefArgs), C.c_void_p]),
     "airpose_ief_train_saved_floats": (C.c_int64, [C.c_int32, C.c_int32]),

@@ -225,9 +225,9 @@ class copenet_twoview(nn.Module):
     @torch.no_grad()
     def training_step_reg_only(self, input_batch, optimizer, mask1=None, mask2=None):
         """One data-parallel training step of the regressor with the trunk frozen: the reference's ``train_reg_only``
-        fine-tuning mode with copenet's loss.  Forward: trunk features (frozen, eval-mode BatchNorm -- the reference
-        leaves the module in train mode there, so its frozen trunk still normalises with batch statistics; that
-        training-mode trunk forward is not built), regressor with dropout, SMPL-X, projection, get_loss.  Backward:
+        fine-tuning mode with copenet's loss.  Forward: trunk features (frozen; with the module in ``train()`` mode, as
+        the reference leaves it, BatchNorm normalises with batch statistics and updates its running statistics, one
+        trunk call per view; in ``eval()`` mode the folded-BN pair kernel path runs), regressor with dropout, SMPL-X, projection, get_loss.  Backward:
         loss -> SMPL-X -> rot6d -> regressor, parameter gradients written straight into the optimizer's flat
         gradient buffer.  Then ONE all-reduce of that buffer over the data-parallel ranks (NCCL) and one Adam launch.
         Returns ``(loss, losses)`` as device tensors (no host sync)."""
@@ -235,7 +235,10 @@ class copenet_twoview(nn.Module):
         B = im0.shape[0]
         in_trans, in_trans_unscaled = self._init_translation(B, im0.device)
         reg_iters = getattr(self.hparams, "reg_iters", 3)
-        xf = self.model.forward_feat_ext_pair(im0, im1)
+        if self.model.training:       # train() mode, like the reference: batch-statistics BatchNorm, one call per view (:140-141)
+            xf = torch.cat([self.model.forward_feat_ext(im0), self.model.forward_feat_ext(im1)])
+        else:
+            xf = self.model.forward_feat_ext_pair(im0, im1)
         pred, ctx = self.model.ief_train_forward(xf[:B], xf[B:], input_batch["bb0"], input_batch["bb1"], in_trans, in_trans,
                                                  iters=reg_iters, mask1=mask1, mask2=mask2)
         out = self._after_regressor(pred, (input_batch["intr0"], input_batch["intr1"]), in_trans_unscaled)

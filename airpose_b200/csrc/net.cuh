@@ -60,6 +60,12 @@ struct airpose_net {
   int sets = 1;
   __nv_bfloat16* actB[4] = {nullptr, nullptr, nullptr, nullptr};   // stage B (layer3, layer4): `group` images
   int group = 0;
+  // training-mode forward (airpose_backbone_fwd_train): raw conv output, BatchNorm partial sums, scale/shift of the layer
+  __nv_bfloat16* ztrain = nullptr;
+  float* bn_part = nullptr;
+  float* bn_scale = nullptr;
+  float* bn_shift = nullptr;
+  std::vector<int64_t> bn_save_off;
   std::map<std::pair<int, int>, airpose::TrunkPlan> plansA;        // (images, 2 * first image inside the group + buffer set)
   std::map<int, airpose::TrunkPlan> plansB;                        // images
 };

@@ -145,6 +145,98 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, int n, float
   out[i] = s / 49.f;
 }
 
+// ------------------------------------------------------------------------------ training-mode BatchNorm
+// nn.BatchNorm2d in train mode (model_copenet.py:16-21,57-58; torch semantics): normalise with the BATCH mean and
+// biased variance over (n, h, w), update running_mean / running_var (momentum, unbiased variance).  The conv writes its
+// raw output z (bf16 [M, C]); bn_stats sums z and z^2 per channel (fp32 per slab, fp64 across slabs: deterministic);
+// bn_finalize turns them into scale/shift and updates the running statistics; bn_apply writes
+// relu(z * scale + shift (+ residual)) in bf16.  All three are HBM-bound passes over [M, C].
+constexpr int kBnSlabs = 148 * 2;
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, int64_t M, int C, float* __restrict__ part) {
+  __shared__ float red[256][17];
+  const int groups = C / 8;                         // 8 channels (16 B) per thread
+  const int lanes = 256 / groups;                   // row lanes per block (C <= 2048)
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  const int64_t per = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(M, r0 + per);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (rl < lanes)
+    for (int64_t r = r0 + rl; r < r1; r += lanes) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(z + r * C + cg * 8));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = __uint_as_float(u[j] << 16), b = __uint_as_float(u[j] & 0xFFFF0000u);
+        s[2 * j] += a; q[2 * j] = fmaf(a, a, q[2 * j]);
+        s[2 * j + 1] += b; q[2 * j + 1] = fmaf(b, b, q[2 * j + 1]);
+      }
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][8 + j] = q[j]; }
+  __syncthreads();
+  if (threadIdx.x < groups) {                       // fixed-order sum over the row lanes
+    float ts[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ts[j] = 0.f;
+    for (int l = 0; l < lanes; ++l)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ts[j] += red[l * groups + threadIdx.x][j];
+    float* o = part + ((size_t)blockIdx.x * C + threadIdx.x * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[2 * j] = ts[j]; o[2 * j + 1] = ts[8 + j]; }
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ part, int slabs, int64_t M, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < slabs; ++i) { s += part[((size_t)i * C + c) * 2]; q += part[((size_t)i * C + c) * 2 + 1]; }
+  const double mean = s / (double)M;
+  const double var = fmax(q / (double)M - mean * mean, 0.0);            // biased, as F.batch_norm normalises
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)mean * sc;
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * (double)M / (double)max((int64_t)1, M - 1));
+  }
+  if (save_mean) { save_mean[c] = (float)mean; save_invstd[c] = invstd; }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ z, int64_t M, int C, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual,
+                                                       int relu, __nv_bfloat16* __restrict__ y) {
+  const int groups = C / 8;
+  const int64_t total = M * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(z) + i);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8)), h1 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    uint32_t ru[4] = {0, 0, 0, 0};
+    if (residual) { const uint4 r = __ldg(reinterpret_cast<const uint4*>(residual) + i); ru[0] = r.x; ru[1] = r.y; ru[2] = r.z; ru[3] = r.w; }
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = fmaf(__uint_as_float(u[j] << 16), sc[2 * j], sh[2 * j]) + __uint_as_float(ru[j] << 16);
+      float b = fmaf(__uint_as_float(u[j] & 0xFFFF0000u), sc[2 * j + 1], sh[2 * j + 1]) + __uint_as_float(ru[j] & 0xFFFF0000u);
+      if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+      o[2 * j] = __float2bfloat16_rn(a); o[2 * j + 1] = __float2bfloat16_rn(b);
+    }
+    reinterpret_cast<uint4*>(y)[i] = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
 }  // namespace airpose
 
 using namespace airpose;
@@ -206,7 +298,7 @@ extern "C" int airpose_net_destroy(airpose_net_t* h) {
   for (auto p : h->scale) cudaFree(p);
   for (auto p : h->shift) cudaFree(p);
   ief_destroy(h);
-  void* ptrs[] = {h->actB[0], h->actB[1], h->actB[2], h->actB[3]};
+  void* ptrs[] = {h->actB[0], h->actB[1], h->actB[2], h->actB[3], h->ztrain, h->bn_part, h->bn_scale, h->bn_shift};
   for (void* p : ptrs) cudaFree(p);
   for (int s = 0; s < airpose_net::kSets; ++s) {
     cudaFree(h->colS[s]); cudaFree(h->stem_outS[s]);
@@ -256,7 +348,7 @@ extern "C" int airpose_hmr_load(airpose_net_t* h, const airpose_hmr_params* p, v
 }
 
 static int conv_launch(airpose_net* h, int idx, const __nv_bfloat16* x, int n, int H, int W, const __nv_bfloat16* residual,
-                       int relu, __nv_bfloat16* out, GemmLaunch* L) {
+                       int relu, __nv_bfloat16* out, GemmLaunch* L, bool raw = false) {
   const ConvSpec& s = h->specs[idx];
   ConvGeom& g = L->geom;
   g.n = n; g.H = H; g.W = W; g.Cin = s.cin; g.ksize = s.k; g.stride = s.stride; g.pad = s.pad;
@@ -273,7 +365,7 @@ static int conv_launch(airpose_net* h, int idx, const __nv_bfloat16* x, int n, i
   }
   L->pair_b_box = use_tma_epilogue() && prefers_pair(L->M, L->N, L->K);
   if (make_tmap_tiled_bf16(&L->tmB, h->wq[idx], L->N, L->K, L->K, L->pair_b_box ? 128 : L->block_n, 64)) return 1;
-  L->epi.scale = h->scale[idx]; L->epi.shift = h->shift[idx];
+  L->epi.scale = raw ? nullptr : h->scale[idx]; L->epi.shift = raw ? nullptr : h->shift[idx];   // raw: the conv output itself
   L->epi.residual = residual; L->epi.ldr = s.cout;
   L->epi.relu = relu;
   L->epi.out_bf16 = out; L->epi.ldd = s.cout;
@@ -286,7 +378,7 @@ static int conv_launch(airpose_net* h, int idx, const __nv_bfloat16* x, int n, i
   return 0;
 }
 
-static int build_stem_gemm(airpose_net* h, int n, int set, GemmLaunch* Lp) {
+static int build_stem_gemm(airpose_net* h, int n, int set, GemmLaunch* Lp, bool raw = false) {
   // stem: 7 k-blocks (one per vertical tap) over the packed operand, BN + ReLU in the epilogue
   GemmLaunch& L = *Lp;
   L.M = n * 112 * 112; L.N = 64; L.K = kStemK; L.block_n = 64;
@@ -300,7 +392,7 @@ static int build_stem_gemm(airpose_net* h, int n, int set, GemmLaunch* Lp) {
   }
   if (make_tmap_tiled_bf16(&L.tmA, h->colS[set], (int64_t)n * 2 * kStemPlaneRows * 112, kStemTapK, kStemTapK, 128, kStemTapK, 64)) return 1;
   if (make_tmap_tiled_bf16(&L.tmB, h->wq[0], 64, kStemK, kStemK, 64, kStemTapK, 64)) return 1;
-  L.epi.scale = h->scale[0]; L.epi.shift = h->shift[0]; L.epi.relu = 1;
+  L.epi.scale = raw ? nullptr : h->scale[0]; L.epi.shift = raw ? nullptr : h->shift[0]; L.epi.relu = raw ? 0 : 1;
   L.epi.out_bf16 = h->stem_outS[set]; L.epi.ldd = 64;
   return enable_tma_epilogue(&L);
 }
@@ -444,4 +536,105 @@ extern "C" int airpose_backbone_stem(airpose_net_t* h, const float* x, int n, vo
   GemmLaunch stem{};
   if (build_stem_gemm(h, n, 0, &stem)) return 1;
   return launch_stem_front(h, x, n, 0, stem, (__nv_bfloat16*)out, (cudaStream_t)stream_);
+}
+
+// ------------------------------------------------------------------------------ training-mode trunk forward
+// copenet.forward_feat_ext with the module in train() mode (what Lightning's training_step runs, and what the frozen
+// trunk of `train_reg_only` runs too): every BatchNorm normalises with the statistics of THIS batch of n images and
+// updates its running statistics.  Per conv: raw GEMM -> bn_stats -> bn_finalize -> bn_apply (+residual, ReLU).
+// One call = one view (the reference calls forward_feat_ext once per view, so the statistics are per view).
+static int bn_train(airpose_net* h, int idx, const __nv_bfloat16* z, int64_t M, int C, const airpose_bn_train_params* bn,
+                    const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t st) {
+  bn_stats_kernel<<<kBnSlabs, 256, 0, st>>>(z, M, C, h->bn_part);
+  AP_LAUNCH_CHECK();
+  float* save = bn->saved_stats ? bn->saved_stats + h->bn_save_off[idx] : nullptr;
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, bn->bn_weight[idx], bn->bn_bias[idx], bn->eps,
+                                                       bn->momentum, bn->running_mean[idx], bn->running_var[idx], h->bn_scale,
+                                                       h->bn_shift, save, save ? save + C : nullptr);
+  AP_LAUNCH_CHECK();
+  const int64_t total = M * (C / 8);
+  bn_apply_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 16), 256, 0, st>>>(z, M, C, h->bn_scale, h->bn_shift,
+                                                                                                residual, relu, y);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int64_t airpose_bn_saved_stats_floats(void) {
+  int64_t n = 0;
+  for (const ConvSpec& s : resnet50_specs()) n += 2 * s.cout;
+  return n;
+}
+
+extern "C" int airpose_backbone_fwd_train(airpose_net_t* h, const float* x, int n, const airpose_bn_train_params* bn, float* out_feat,
+                                          void* stream_) {
+  AP_REQUIRE(h && x && bn && out_feat, "airpose_backbone_fwd_train: null argument");
+  AP_REQUIRE(h->loaded, "airpose_backbone_fwd_train: weights not loaded (call airpose_net_load)");
+  AP_REQUIRE(n >= 2 && n <= h->chunk, "airpose_backbone_fwd_train: n=%d must be in [2, %d] (batch statistics need at least two images; "
+             "one call handles at most one chunk)", n, h->chunk);
+  for (size_t i = 0; i < h->specs.size(); ++i)
+    AP_REQUIRE(bn->bn_weight[i] && bn->bn_bias[i], "airpose_backbone_fwd_train: BatchNorm %zu has a null parameter", i);
+  cudaStream_t st = (cudaStream_t)stream_;
+  const size_t act_elems = (size_t)h->chunk * 112 * 112 * 64;
+  if (!h->ztrain) {
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->ztrain, act_elems * 2));
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_part, (size_t)kBnSlabs * 2048 * 2 * sizeof(float)));
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_scale, 2048 * sizeof(float)));
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_shift, 2048 * sizeof(float)));
+    int64_t off = 0;
+    h->bn_save_off.clear();
+    for (const ConvSpec& s : h->specs) { h->bn_save_off.push_back(off); off += 2 * s.cout; }
+  }
+  __nv_bfloat16* Z = h->ztrain;
+  __nv_bfloat16* const* buf = h->actS[0];
+  // stem: pack, raw 7x7 conv, BN + ReLU in place, max-pool
+  {
+    const int64_t work = (int64_t)n * 2 * kStemPlaneRows * 112;
+    stem_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(work, 128), 148 * 32), 128, 0, st>>>(x, n, h->colS[0]);
+    AP_LAUNCH_CHECK();
+    GemmLaunch L{};
+    if (build_stem_gemm(h, n, 0, &L, true)) return 1;
+    if (launch_gemm(L, st)) return 1;
+    const int64_t M = (int64_t)n * 112 * 112;
+    if (bn_train(h, 0, h->stem_outS[0], M, 64, bn, nullptr, 1, h->stem_outS[0], st)) return 1;
+    maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64((int64_t)n * 56 * 56 * 8, 256), 148 * 16), 256, 0, st>>>(h->stem_outS[0], n,
+                                                                                                                     buf[0]);
+    AP_LAUNCH_CHECK();
+  }
+  const int layers[4] = {3, 4, 6, 3};
+  int idx = 1, H = 56;
+  int a = 0, b = 1, c = 2, d = 3;          // buffer roles: X, T1/OUT, T2, DS
+  for (int li = 0; li < 4; ++li)
+    for (int blk = 0; blk < layers[li]; ++blk) {
+      const bool down = blk == 0;
+      const int stride = h->specs[idx + 1].stride;
+      const int Ho = H / stride;
+      const int planes = h->specs[idx].cout;
+      GemmLaunch L1{}, L2{}, L3{}, LD{};
+      if (conv_launch(h, idx, buf[a], n, H, H, nullptr, 0, Z, &L1, true) || launch_gemm(L1, st)) return 1;
+      if (bn_train(h, idx, Z, (int64_t)n * H * H, planes, bn, nullptr, 1, buf[b], st)) return 1;
+      if (conv_launch(h, idx + 1, buf[b], n, H, H, nullptr, 0, Z, &L2, true) || launch_gemm(L2, st)) return 1;
+      if (bn_train(h, idx + 1, Z, (int64_t)n * Ho * Ho, planes, bn, nullptr, 1, buf[c], st)) return 1;
+      const __nv_bfloat16* res = buf[a];
+      if (down) {
+        if (conv_launch(h, idx + 3, buf[a], n, H, H, nullptr, 0, Z, &LD, true) || launch_gemm(LD, st)) return 1;
+        if (bn_train(h, idx + 3, Z, (int64_t)n * Ho * Ho, planes * 4, bn, nullptr, 0, buf[d], st)) return 1;
+        res = buf[d];
+      }
+      if (conv_launch(h, idx + 2, buf[c], n, Ho, Ho, nullptr, 0, Z, &L3, true) || launch_gemm(L3, st)) return 1;
+      if (bn_train(h, idx + 2, Z, (int64_t)n * Ho * Ho, planes * 4, bn, res, 1, buf[b], st)) return 1;
+      std::swap(a, b);
+      idx += down ? 4 : 3;
+      H = Ho;
+    }
+  avgpool_kernel<<<ceil_div(n * kFeat, 256), 256, 0, st>>>(buf[a], n, out_feat);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// Only the regressor part of airpose_net_load (the collapsed matrix G): what changes between the steps of a
+// regressor-only training run.
+extern "C" int airpose_net_load_regressor(airpose_net_t* h, const airpose_net_params* p, void* stream_) {
+  AP_REQUIRE(h && p, "airpose_net_load_regressor: null argument");
+  AP_REQUIRE(h->loaded && !h->hmr_loaded, "airpose_net_load_regressor: the two-view network is not loaded");
+  return ief_load(h, p, (cudaStream_t)stream_);
 }

@@ -121,12 +121,13 @@ class copenet(nn.Module):
                self.decshape.weight, self.decshape.bias, self.init_pose, self.init_shape]
         return ts
 
-    def _ensure(self, n_images, device):
+    def _ensure(self, n_images, device, allow_training=False):
         if device.type != "cuda":
             raise _lib.AirposeError("airpose_b200.copenet runs on CUDA only (module is on {}); there is no CPU path".format(device))
-        if self.training:
-            raise NotImplementedError("airpose_b200.copenet: training-mode forward (batch-statistics BatchNorm, dropout) "
-                                      "is not built yet; call .eval()")
+        if self.training and not allow_training:
+            raise NotImplementedError("airpose_b200.copenet: the full forward in training mode needs the trunk backward, which "
+                                      "is not built; use .eval(), or copenet_twoview.training_step_reg_only / "
+                                      "forward_feat_ext (batch-statistics BatchNorm) + ief_train_forward")
         lib = _lib.load()
         if self._handle is None or self._handle_key != device or n_images > self.max_images:
             self._release()
@@ -135,14 +136,23 @@ class copenet(nn.Module):
             with torch.cuda.device(device):
                 _lib.check(lib.airpose_net_create(C.byref(h), cap, device.index or 0), "airpose_net_create")
             self._handle, self._handle_key, self.max_images, self._loaded_key = h, device, cap, None
+        # (data_ptr, version, generation): the generation is bumped by airpose_b200.optim.Adam, whose kernel updates the
+        # parameters through raw pointers and therefore behind torch's version counters
+        stamp = lambda t: (t.data_ptr(), t._version, getattr(t, "_airpose_gen", 0))
         ts = self._weight_tensors()
-        key = tuple((t.data_ptr(), t._version) for t in ts)
+        n_trunk = 5 * len(self._conv_bn_pairs())
+        key = (tuple(stamp(t) for t in ts[:n_trunk]), tuple(stamp(t) for t in ts[n_trunk:]))
         if key != self._loaded_key:
             for t in ts:
                 if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
                     raise _lib.AirposeError("copenet parameters must be contiguous float32 tensors on {}".format(device))
             with torch.cuda.device(device):
-                self._load_native(lib)
+                if self._loaded_key is not None and key[0] == self._loaded_key[0] and type(self) is copenet:
+                    p = self._fill_common(_lib.NetParams())        # only the regressor changed: re-form G, keep the packed convs
+                    _lib.check(lib.airpose_net_load_regressor(self._handle, C.byref(p), _lib.current_stream()),
+                               "airpose_net_load_regressor")
+                else:
+                    self._load_native(lib)
             self._loaded_key = key
         return lib, self._handle
 
@@ -181,17 +191,48 @@ class copenet(nn.Module):
 
     # ------------------------------------------------------------------ forward pieces
     def forward_feat_ext(self, x):
-        """model_copenet.py:161-176: [n,3,224,224] -> [n,2048]."""
+        """model_copenet.py:161-176: [n,3,224,224] -> [n,2048].  In ``train()`` mode every BatchNorm normalises with
+        the statistics of this batch and updates its running statistics (torch semantics; no autograd graph)."""
         if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
             raise ValueError("forward_feat_ext expects [n,3,224,224], got {}".format(tuple(x.shape)))
         device = self.conv1.weight.device
         x = x.detach().to(device=device, dtype=torch.float32).contiguous()
         n = x.shape[0]
+        if self.training:
+            return self._forward_feat_ext_train(x)
         lib, h = self._ensure(n, device)
         out = torch.empty(n, 2048, device=device, dtype=torch.float32)
         with torch.cuda.device(device):
             _lib.check(lib.airpose_backbone_fwd(h, x.data_ptr(), n, out.data_ptr(), _lib.current_stream()),
                        "airpose_backbone_fwd")
+        return out
+
+    def _forward_feat_ext_train(self, x, saved_stats=None):
+        device = x.device
+        n = x.shape[0]
+        lib, h = self._ensure(max(n, 2), device, allow_training=True)
+        bn = _lib.BnTrainParams()
+        pairs = self._conv_bn_pairs()
+        for i, (conv, m) in enumerate(pairs):
+            bn.bn_weight[i], bn.bn_bias[i] = m.weight.data_ptr(), m.bias.data_ptr()
+            if m.track_running_stats and m.running_mean is not None:
+                bn.running_mean[i], bn.running_var[i] = m.running_mean.data_ptr(), m.running_var.data_ptr()
+        momenta = {m.momentum for _, m in pairs}
+        if len(momenta) != 1 or None in momenta:
+            raise NotImplementedError("all BatchNorm layers must share one numeric momentum (the reference uses 0.1)")
+        bn.momentum, bn.eps = float(momenta.pop()), float(self.bn1.eps)
+        if saved_stats is not None:
+            bn.saved_stats = saved_stats.data_ptr()
+        out = torch.empty(n, 2048, device=device, dtype=torch.float32)
+        with torch.cuda.device(device):
+            _lib.check(lib.airpose_backbone_fwd_train(h, x.data_ptr(), n, C.byref(bn), out.data_ptr(), _lib.current_stream()),
+                       "airpose_backbone_fwd_train")
+        tracked = [m.num_batches_tracked for _, m in pairs if m.track_running_stats and m.num_batches_tracked is not None]
+        if tracked:
+            torch._foreach_add_(tracked, 1)
+        for _, m in pairs:     # the running statistics were written through raw pointers: make the eval path re-fold them
+            if m.track_running_stats and m.running_mean is not None:
+                m.running_mean._airpose_gen = getattr(m.running_mean, "_airpose_gen", 0) + 1
         return out
 
     def forward_feat_ext_pair(self, x0, x1):

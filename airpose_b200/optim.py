@@ -77,3 +77,5 @@ class Adam:
         a.step, a.grad_scale = self.step_count, float(grad_scale)
         with torch.cuda.device(self.device):
             _lib.check(lib.airpose_adam_step(C.byref(a), _lib.current_stream()), "airpose_adam_step")
+        for p in self.params:                    # the kernel wrote through raw pointers: tell cached packings they are stale
+            p._airpose_gen = self.step_count

@@ -192,6 +192,29 @@ int airpose_backbone_fwd(airpose_net_t* h, const float* x_nchw, int n_images, fl
 int airpose_backbone_fwd_pair(airpose_net_t* h, const float* x0_nchw, const float* x1_nchw, int n_pairs,
                               float* out_feat, void* stream);
 
+/* copenet.forward_feat_ext with the module in train() mode (Lightning's training_step; also the frozen trunk of
+ * copenet_real's train_reg_only): every BatchNorm normalises with the statistics of this batch of n images (biased
+ * variance) and updates running_mean / running_var in place (momentum 0.1, unbiased variance), torch semantics.  One
+ * call = one view, 2 <= n <= the handle's chunk size.  Conv weights are the ones packed by airpose_net_load; the
+ * BatchNorm affine parameters and running statistics are read / written live (DEVICE pointers, forward order as in
+ * airpose_net_params.conv).  saved_stats (optional, airpose_bn_saved_stats_floats() floats) receives per layer
+ * [mean(C) | invstd(C)] for a backward pass. */
+typedef struct {
+  const float* bn_weight[53];
+  const float* bn_bias[53];
+  float* running_mean[53];     /* may be NULL per layer: no running-statistics update */
+  float* running_var[53];
+  float momentum;              /* 0.1 */
+  float eps;                   /* 1e-5 */
+  float* saved_stats;
+} airpose_bn_train_params;
+int64_t airpose_bn_saved_stats_floats(void);
+int airpose_backbone_fwd_train(airpose_net_t* h, const float* x_nchw, int n_images, const airpose_bn_train_params* bn,
+                               float* out_feat, void* stream);
+/* Re-forms only the collapsed regressor matrix of airpose_net_load (the conv weights stay packed): what changes
+ * between the steps of a regressor-only training run. */
+int airpose_net_load_regressor(airpose_net_t* h, const airpose_net_params* p, void* stream);
+
 /* The regressor half of copenet.forward (model_copenet.py:118-159,178-204), eval mode: with dropout
  * inactive the three Linears have no nonlinearity between them, so the pass is evaluated as one
  * affine map per iteration (fp32 FMA; differs from the reference chain by summation order only).

@@ -834,3 +834,68 @@ def test_training_step_reg_only(tmp_path, smplx_dir, smplx_data, net_state):
         loss, _ = mod.training_step_reg_only(batch, opt, mask1=m1.to(DEV), mask2=m2.to(DEV))
     print("  loss after 9 steps on the same batch: %.4f -> %.4f" % (l0, float(loss)))
     assert float(loss) < l0
+
+
+# ----------------------------------------------------------------------------- training-mode trunk forward (batch-statistics BatchNorm)
+def test_trunk_train_mode_matches_torch(tmp_path, net_state):
+    """forward_feat_ext in train() mode against a plain PyTorch fp32 ResNet-50 forward with F.batch_norm(training=True)
+    and the CUDA path's rounding points (conv operands and every stored activation in bf16): features, the updated
+    running statistics (momentum 0.1, unbiased variance) and num_batches_tracked; then eval() picks the new statistics up."""
+    import torch.nn.functional as F
+    from airpose_b200.model_copenet import getcopenet
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+    net = getcopenet(mp, pretrained=False)
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in net_state.items()}, strict=True)
+    net = net.to(DEV).train()
+    n = 6
+    x = torch.from_numpy(synthetic.make_inputs(n, 5)["im0"]).to(DEV)
+    sd = {k: torch.from_numpy(np.asarray(v)).to(DEV) for k, v in net_state.items()}
+    rb = lambda t: t.to(torch.bfloat16).float()
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    new_stats = {}
+
+    def bn(z, name, res=None, relu=True):
+        z = rb(z)                                                    # the conv output is stored in bf16
+        rm, rv = sd[name + ".running_mean"].clone(), sd[name + ".running_var"].clone()
+        y = F.batch_norm(z, rm, rv, sd[name + ".weight"], sd[name + ".bias"], training=True, momentum=0.1, eps=1e-5)
+        new_stats[name] = (rm, rv)
+        if res is not None:
+            y = y + res
+        return rb(F.relu(y) if relu else y)
+
+    try:
+        conv = lambda t, name, stride, pad: F.conv2d(rb(t), rb(sd[name + ".weight"]), stride=stride, padding=pad)
+        y = bn(conv(x, "conv1", 2, 3), "bn1")
+        y = F.max_pool2d(y, 3, 2, 1)
+        for li, (blocks, planes) in enumerate(zip((3, 4, 6, 3), (64, 128, 256, 512)), start=1):
+            for b in range(blocks):
+                p = "layer%d.%d" % (li, b)
+                s = 2 if (li > 1 and b == 0) else 1
+                o = bn(conv(y, p + ".conv1", 1, 0), p + ".bn1")
+                o = bn(conv(o, p + ".conv2", s, 1), p + ".bn2")
+                res = bn(conv(y, p + ".downsample.0", s, 0), p + ".downsample.1", relu=False) if b == 0 else y
+                y = bn(conv(o, p + ".conv3", 1, 0), p + ".bn3", res=res)
+        ref = y.mean(dim=(2, 3))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    got = net.forward_feat_ext(x)
+    e = rel_err(got.cpu().numpy(), ref.cpu().numpy())
+    em = float((got - ref).abs().mean() / ref.abs().mean())
+    print("train-mode trunk: feature max-rel %.3e mean-rel %.3e" % (e, em))
+    assert e < 4e-2 and em < 1.5e-2      # two bf16 evaluations; batch statistics over 6 images (294 samples per channel in layer4) amplify the one-ulp flips ~5x over the eval-mode trunk
+    mods = dict(net.named_modules())
+    for name in ("bn1", "layer1.0.bn3", "layer2.0.downsample.1", "layer3.5.bn2", "layer4.2.bn3"):
+        rm, rv = new_stats[name]
+        e1 = rel_err(mods[name].running_mean.cpu().numpy(), rm.cpu().numpy())
+        e2 = rel_err(mods[name].running_var.cpu().numpy(), rv.cpu().numpy())
+        print("  %-24s running_mean rel err %.2e running_var rel err %.2e" % (name, e1, e2))
+        assert e1 < 2e-2 and e2 < 2e-2, name
+        assert int(mods[name].num_batches_tracked) == 1
+    # eval() now folds the UPDATED running statistics
+    net.eval()
+    ev = net.forward_feat_ext(x)
+    net2 = getcopenet(mp, pretrained=False)
+    net2.load_state_dict(net.state_dict())
+    ev2 = net2.to(DEV).eval().forward_feat_ext(x)
+    assert torch.equal(ev, ev2)
