@@ -121,7 +121,7 @@ class copenet(nn.Module):
                self.decshape.weight, self.decshape.bias, self.init_pose, self.init_shape]
         return ts
 
-    def _ensure(self, n_images, device, allow_training=False):
+    def _ensure(self, n_images, device, allow_training=False, need_regressor=True):
         if device.type != "cuda":
             raise _lib.AirposeError("airpose_b200.copenet runs on CUDA only (module is on {}); there is no CPU path".format(device))
         if self.training and not allow_training:
@@ -137,23 +137,27 @@ class copenet(nn.Module):
                 _lib.check(lib.airpose_net_create(C.byref(h), cap, device.index or 0), "airpose_net_create")
             self._handle, self._handle_key, self.max_images, self._loaded_key = h, device, cap, None
         # (data_ptr, version, generation): the generation is bumped by airpose_b200.optim.Adam, whose kernel updates the
-        # parameters through raw pointers and therefore behind torch's version counters
+        # parameters through raw pointers and therefore behind torch's version counters.  The trunk (packed conv weights,
+        # folded BN) and the regressor (collapsed matrix G) are tracked separately, and G is re-formed only when an
+        # eval-mode regressor call needs it: a training run changes the regressor every step without ever using G.
         stamp = lambda t: (t.data_ptr(), t._version, getattr(t, "_airpose_gen", 0))
         ts = self._weight_tensors()
         n_trunk = 5 * len(self._conv_bn_pairs())
-        key = (tuple(stamp(t) for t in ts[:n_trunk]), tuple(stamp(t) for t in ts[n_trunk:]))
-        if key != self._loaded_key:
+        trunk_key = tuple(stamp(t) for t in ts[:n_trunk])
+        reg_key = tuple(stamp(t) for t in ts[n_trunk:])
+        loaded = self._loaded_key or (None, None)
+        if trunk_key != loaded[0] or (need_regressor and reg_key != loaded[1]):
             for t in ts:
                 if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
                     raise _lib.AirposeError("copenet parameters must be contiguous float32 tensors on {}".format(device))
             with torch.cuda.device(device):
-                if self._loaded_key is not None and key[0] == self._loaded_key[0] and type(self) is copenet:
-                    p = self._fill_common(_lib.NetParams())        # only the regressor changed: re-form G, keep the packed convs
+                if trunk_key == loaded[0] and type(self) is copenet:
+                    p = self._fill_common(_lib.NetParams())        # only the regressor changed: keep the packed convs
                     _lib.check(lib.airpose_net_load_regressor(self._handle, C.byref(p), _lib.current_stream()),
                                "airpose_net_load_regressor")
                 else:
-                    self._load_native(lib)
-            self._loaded_key = key
+                    self._load_native(lib)                         # packs the convs, folds BN and forms G
+            self._loaded_key = (trunk_key, reg_key)
         return lib, self._handle
 
     def _fill_common(self, p):
@@ -200,7 +204,7 @@ class copenet(nn.Module):
         n = x.shape[0]
         if self.training:
             return self._forward_feat_ext_train(x)
-        lib, h = self._ensure(n, device)
+        lib, h = self._ensure(n, device, need_regressor=False)
         out = torch.empty(n, 2048, device=device, dtype=torch.float32)
         with torch.cuda.device(device):
             _lib.check(lib.airpose_backbone_fwd(h, x.data_ptr(), n, out.data_ptr(), _lib.current_stream()),
@@ -210,7 +214,7 @@ class copenet(nn.Module):
     def _forward_feat_ext_train(self, x, saved_stats=None):
         device = x.device
         n = x.shape[0]
-        lib, h = self._ensure(max(n, 2), device, allow_training=True)
+        lib, h = self._ensure(max(n, 2), device, allow_training=True, need_regressor=False)
         bn = _lib.BnTrainParams()
         pairs = self._conv_bn_pairs()
         for i, (conv, m) in enumerate(pairs):
@@ -247,7 +251,7 @@ class copenet(nn.Module):
         x0 = x0.detach().to(device=device, dtype=torch.float32).contiguous()
         x1 = x1.detach().to(device=device, dtype=torch.float32).contiguous()
         B = x0.shape[0]
-        lib, h = self._ensure(2 * B, device)
+        lib, h = self._ensure(2 * B, device, need_regressor=False)
         out = torch.empty(2 * B, 2048, device=device, dtype=torch.float32)
         with torch.cuda.device(device):
             _lib.check(lib.airpose_backbone_fwd_pair(h, x0.data_ptr(), x1.data_ptr(), B, out.data_ptr(), _lib.current_stream()),
