@@ -133,10 +133,13 @@ __global__ void __launch_bounds__(kMaxJoints) smplx_pose_kernel(SmplxDev m, Pose
     for (int e = 0; e < 9; ++e) f[e] = R[e] - ((e % 4 == 0) ? 1.f : 0.f);
   }
   if (a.rec) {
-    float* rec = a.rec + (size_t)b * kTcRecFloats;
+    // records are stored in PAIRS of meshes, element-interleaved (field f of mesh b at pair_base + 2 f + (b & 1)), so
+    // that the vertex kernel reads {mesh 2p, mesh 2p+1} of a field with one 64-bit load and does its fp32 math with
+    // packed FFMA2 (two meshes per instruction)
+    float* rec = a.rec + (size_t)(b >> 1) * 2 * kTcRecFloats + (b & 1);
     if (j < kTcBodyJoints) {
 #pragma unroll
-      for (int e = 0; e < 12; e += 4) *reinterpret_cast<float4*>(rec + j * 12 + e) = make_float4(Aj[e], Aj[e + 1], Aj[e + 2], Aj[e + 3]);
+      for (int e = 0; e < 12; ++e) rec[2 * (j * 12 + e)] = Aj[e];
     }
     if (j >= 1 && j < kTcBodyJoints) {                           // split-fp16 pose feature: f = hi + lo
 #pragma unroll
@@ -151,11 +154,11 @@ __global__ void __launch_bounds__(kMaxJoints) smplx_pose_kernel(SmplxDev m, Pose
       a.fh[(size_t)b * kTcK + 189 + j] = __float2half_rn(0.f);
       a.fl[(size_t)b * kTcK + 189 + j] = __float2half_rn(0.f);
     }
-    if (j < 12) rec[kTcRecBetas + j] = j < a.nb ? beta_s[j] : 0.f;
-    if (j >= 12 && j < 21) rec[kTcRecCam + (j - 12)] = a.root_R ? __ldg(a.root_R + (size_t)b * a.root_R_stride + (j - 12))
-                                                                  : (((j - 12) % 4 == 0) ? 1.f : 0.f);
-    if (j >= 21 && j < 24) rec[kTcRecCam + 9 + (j - 21)] = a.root_t ? __ldg(a.root_t + (size_t)b * a.root_t_stride + (j - 21)) : 0.f;
-    if (j >= 24 && j < 28) rec[kTcRecTransl + (j - 24)] = (a.transl && j < 27) ? __ldg(a.transl + (size_t)b * 3 + (j - 24)) : 0.f;
+    if (j < 12) rec[2 * (kTcRecBetas + j)] = j < a.nb ? beta_s[j] : 0.f;
+    if (j >= 12 && j < 21) rec[2 * (kTcRecCam + (j - 12))] = a.root_R ? __ldg(a.root_R + (size_t)b * a.root_R_stride + (j - 12))
+                                                                        : (((j - 12) % 4 == 0) ? 1.f : 0.f);
+    if (j >= 21 && j < 24) rec[2 * (kTcRecCam + 9 + (j - 21))] = a.root_t ? __ldg(a.root_t + (size_t)b * a.root_t_stride + (j - 21)) : 0.f;
+    if (j >= 24 && j < 28) rec[2 * (kTcRecTransl + (j - 24))] = (a.transl && j < 27) ? __ldg(a.transl + (size_t)b * 3 + (j - 24)) : 0.f;
   }
 }
 

@@ -101,6 +101,26 @@ __device__ __forceinline__ void tmem_ld_32xN(uint32_t taddr, uint32_t (&r)[4]) {
                : "memory");
 }
 
+// packed fp32 FMA (sm_100: SASS FFMA2): two independent fp32 FMAs per issue slot -- here the two meshes of a pair
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+// explicit shared-window loads (the hand-aligned dynamic smem base hides the address space: generic LD.E otherwise)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+
 // kind::f16 instruction descriptor with fp16 A/B (format 0), fp32 accumulator.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -242,7 +262,7 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 96 + hf * kTcSub;
       ptx::mbar_wait(&r_full[slot], rph, 410 + slot);
-      const uint8_t* rbase = smem + kROff + slot * kRStageBytes;
+      const uint32_t rbase = ptx::smem_u32(smem + kROff + slot * kRStageBytes);
       const int mesh0 = t * kTcMeshTile + hf * kTcSub;
       // UN (2 or 4) meshes per TMEM load and per unrolled body: the fully unrolled 16-mesh body was ~5700 SASS instructions
       // (91 KB) and spent 12 % of its samples in instruction-fetch stalls (profiles/r01c: stall_no_inst)
@@ -260,59 +280,73 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
         }
         if (mesh0 + mq * UN >= a.B) continue;            // uniform across the CTA (the release above still happens)
 #pragma unroll
-        for (int mi = 0; mi < UN; ++mi) {
-          const int m = mq * UN + mi;
+        for (int pi = 0; pi < UN / 2; ++pi) {            // two meshes per pass: every fp32 FMA below is an FFMA2
+          const int m = mq * UN + 2 * pi;
           const int b = mesh0 + m;
           if (b >= a.B) break;                           // uniform across the CTA
-          const float* rec = reinterpret_cast<const float*>(rbase + m * kRecBytes);
+          const bool second = b + 1 < a.B;
+          // pair record: field f of meshes (b, b+1) = one float2 at index f
+          const uint32_t rec = rbase + (uint32_t)(m >> 1) * 2 * kRecBytes;      // byte address; field f of the pair at rec + 8 f
           // v_shaped (lbs.py:179) + pose offsets (:203)
-          const float4 b0 = *reinterpret_cast<const float4*>(rec + kTcRecBetas);
-          const float4 b1 = *reinterpret_cast<const float4*>(rec + kTcRecBetas + 4);
-          const float2 b2 = *reinterpret_cast<const float2*>(rec + kTcRecBetas + 8);
-          const float be[10] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
-          float x = vt0, y = vt1, z = vt2;
+          float2 x = dup2(vt0), y = dup2(vt1), z = dup2(vt2);
 #pragma unroll
-          for (int l = 0; l < 10; ++l) {
-            x = fmaf(S[0][l], be[l], x);
-            y = fmaf(S[1][l], be[l], y);
-            z = fmaf(S[2][l], be[l], z);
+          for (int l = 0; l < 10; l += 2) {
+            const float4 be = lds_f4(rec + 8 * (kTcRecBetas + l));                 // {beta_l(b), beta_l(b+1), beta_l+1(b), beta_l+1(b+1)}
+            const float2 e0 = make_float2(be.x, be.y), e1 = make_float2(be.z, be.w);
+            x = ffma2(dup2(S[0][l]), e0, x); y = ffma2(dup2(S[1][l]), e0, y); z = ffma2(dup2(S[2][l]), e0, z);
+            x = ffma2(dup2(S[0][l + 1]), e1, x); y = ffma2(dup2(S[1][l + 1]), e1, y); z = ffma2(dup2(S[2][l + 1]), e1, z);
           }
-          x = fmaf(__uint_as_float(dx[mi]), inv_scale, x);
-          y = fmaf(__uint_as_float(dy[mi]), inv_scale, y);
-          z = fmaf(__uint_as_float(dz[mi]), inv_scale, z);
+          const float2 is2 = dup2(inv_scale);
+          x = ffma2(make_float2(__uint_as_float(dx[2 * pi]), __uint_as_float(dx[2 * pi + 1])), is2, x);
+          y = ffma2(make_float2(__uint_as_float(dy[2 * pi]), __uint_as_float(dy[2 * pi + 1])), is2, y);
+          z = ffma2(make_float2(__uint_as_float(dz[2 * pi]), __uint_as_float(dz[2 * pi + 1])), is2, z);
           // T = sum_k w_k A_k (lbs.py:209-213)
-          float T[12];
+          float2 T[12];
 #pragma unroll
-          for (int e = 0; e < 12; ++e) T[e] = 0.f;
+          for (int e = 0; e < 12; ++e) T[e] = make_float2(0.f, 0.f);
 #pragma unroll
           for (int k = 0; k < kTcMaxKW; ++k) {
             if (k >= kw_warp) break;                     // warp-uniform
-            const float w = jw[k];
-            const float4* Aj = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(rec) + joff[k]);
-            const float4 r0 = Aj[0], r1 = Aj[1], r2 = Aj[2];
-            T[0] = fmaf(w, r0.x, T[0]); T[1] = fmaf(w, r0.y, T[1]); T[2] = fmaf(w, r0.z, T[2]); T[3] = fmaf(w, r0.w, T[3]);
-            T[4] = fmaf(w, r1.x, T[4]); T[5] = fmaf(w, r1.y, T[5]); T[6] = fmaf(w, r1.z, T[6]); T[7] = fmaf(w, r1.w, T[7]);
-            T[8] = fmaf(w, r2.x, T[8]); T[9] = fmaf(w, r2.y, T[9]); T[10] = fmaf(w, r2.z, T[10]); T[11] = fmaf(w, r2.w, T[11]);
+            const float2 w = dup2(jw[k]);
+            const uint32_t Aj = rec + 2 * joff[k];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {                // 12 matrix entries x 2 meshes = 6 x 16 bytes
+              const float4 r = lds_f4(Aj + 16 * q);
+              T[2 * q] = ffma2(w, make_float2(r.x, r.y), T[2 * q]);
+              T[2 * q + 1] = ffma2(w, make_float2(r.z, r.w), T[2 * q + 1]);
+            }
           }
           // v = T [v_posed; 1] (lbs.py:215-220) + transl (body_models.py:980-982)
-          float ox = fmaf(T[0], x, fmaf(T[1], y, fmaf(T[2], z, T[3])));
-          float oy = fmaf(T[4], x, fmaf(T[5], y, fmaf(T[6], z, T[7])));
-          float oz = fmaf(T[8], x, fmaf(T[9], y, fmaf(T[10], z, T[11])));
+          float2 ox = ffma2(T[0], x, ffma2(T[1], y, ffma2(T[2], z, T[3])));
+          float2 oy = ffma2(T[4], x, ffma2(T[5], y, ffma2(T[6], z, T[7])));
+          float2 oz = ffma2(T[8], x, ffma2(T[9], y, ffma2(T[10], z, T[11])));
           if (a.has_transl) {
-            const float4 tr = *reinterpret_cast<const float4*>(rec + kTcRecTransl);
-            ox += tr.x; oy += tr.y; oz += tr.z;
+            const float2 tx = lds_f2(rec + 8 * kTcRecTransl), ty = lds_f2(rec + 8 * (kTcRecTransl + 1)), tz = lds_f2(rec + 8 * (kTcRecTransl + 2));
+            ox.x += tx.x; ox.y += tx.y; oy.x += ty.x; oy.y += ty.y; oz.x += tz.x; oz.y += tz.y;
           }
           if (valid) {
             float* o = a.out + ((size_t)b * a.V + v) * 3;
-            o[0] = ox; o[1] = oy; o[2] = oz;
-            if (kHasCam) {         // transform_smpl (utils.py:237-239): R v + t about the origin; camR = c0.xyz c0.w c1.xy | c1.zw c2.x, t = c2.yzw
-              const float4 c0 = *reinterpret_cast<const float4*>(rec + kTcRecCam);
-              const float4 c1 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 4);
-              const float4 c2 = *reinterpret_cast<const float4*>(rec + kTcRecCam + 8);
+            o[0] = ox.x; o[1] = oy.x; o[2] = oz.x;
+            if (second) {
+              float* o1 = o + (size_t)a.V * 3;
+              o1[0] = ox.y; o1[1] = oy.y; o1[2] = oz.y;
+            }
+            if (kHasCam) {         // transform_smpl (utils.py:237-239): R v + t about the origin; record: R row-major (9) then t (3)
+              float2 cm[12];
+#pragma unroll
+              for (int q = 0; q < 6; ++q) {
+                const float4 r = lds_f4(rec + 8 * kTcRecCam + 16 * q);
+                cm[2 * q] = make_float2(r.x, r.y); cm[2 * q + 1] = make_float2(r.z, r.w);
+              }
+              const float2 cx = ffma2(cm[0], ox, ffma2(cm[1], oy, ffma2(cm[2], oz, cm[9])));
+              const float2 cy = ffma2(cm[3], ox, ffma2(cm[4], oy, ffma2(cm[5], oz, cm[10])));
+              const float2 cz = ffma2(cm[6], ox, ffma2(cm[7], oy, ffma2(cm[8], oz, cm[11])));
               float* oc = a.out_cam + ((size_t)b * a.V + v) * 3;
-              oc[0] = fmaf(c0.x, ox, fmaf(c0.y, oy, c0.z * oz)) + c2.y;
-              oc[1] = fmaf(c0.w, ox, fmaf(c1.x, oy, c1.y * oz)) + c2.z;
-              oc[2] = fmaf(c1.z, ox, fmaf(c1.w, oy, c2.x * oz)) + c2.w;
+              oc[0] = cx.x; oc[1] = cy.x; oc[2] = cz.x;
+              if (second) {
+                float* oc1 = oc + (size_t)a.V * 3;
+                oc1[0] = cx.y; oc1[1] = cy.y; oc1[2] = cz.y;
+              }
             }
           }
         }
