@@ -77,7 +77,13 @@ class NetParams(C.Structure):
 
 class BnTrainParams(C.Structure):
     _fields_ = [("bn_weight", C.c_void_p * 53), ("bn_bias", C.c_void_p * 53), ("running_mean", C.c_void_p * 53),
-                ("running_var", C.c_void_p * 53), ("momentum", C.c_float), ("eps", C.c_float), ("saved_stats", C.c_void_p)]
+                ("running_var", C.c_void_p * 53), ("momentum", C.c_float), ("eps", C.c_float), ("saved_stats", C.c_void_p),
+                ("tape", C.c_int32)]
+
+
+class TrunkGrads(C.Structure):
+    _fields_ = [("g_weight", C.c_void_p * 53), ("g_bn_weight", C.c_void_p * 53), ("g_bn_bias", C.c_void_p * 53),
+                ("accumulate", C.c_int32)]
 
 
 class HmrParams(C.Structure):
@@ -175,6 +181,14 @@ SYMBOLS = {
     "airpose_backbone_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "airpose_bn_saved_stats_floats": (C.c_int64, []),
     "airpose_backbone_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(BnTrainParams), C.c_void_p, C.c_void_p]),
+    "airpose_backbone_bwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(BnTrainParams), C.c_void_p,
+                                             C.POINTER(TrunkGrads), C.POINTER(C.c_void_p * 53), C.c_void_p]),
+    "airpose_debug_conv_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int, C.c_void_p]),
+    "airpose_debug_bn_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "airpose_debug_tape_get": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "airpose_net_load_trunk": (C.c_int, [C.c_void_p, C.POINTER(NetParams), C.c_void_p]),
     "airpose_net_load_regressor": (C.c_int, [C.c_void_p, C.POINTER(NetParams), C.c_void_p]),
     "airpose_backbone_fwd_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "airpose_ief_fwd": (C.c_int, [C.c_void_p, C.POINTER(IefArgs), C.c_void_p]),

@@ -249,3 +249,43 @@ class copenet_twoview(nn.Module):
         scale = optimizer.allreduce_grads()
         optimizer.step(grad_scale=scale)
         return loss, losses
+
+    # ------------------------------------------------------------------ full training step
+    def configure_optimizers(self):
+        """copenet_twoview.configure_optimizers (copenet_twoview.py:416-425): Adam(lr, weight_decay=0, amsgrad=True) over
+        ``self.model.parameters()``, here as one launch over one flat buffer (``airpose_b200.optim.Adam``)."""
+        from .optim import Adam
+        return Adam(self.model.parameters(), lr=float(getattr(self.hparams, "lr", 5e-5)), amsgrad=True)
+
+    @torch.no_grad()
+    def training_step(self, input_batch, optimizer, mask1=None, mask2=None):
+        """One data-parallel training step of the whole network (copenet_twoview.py:376-386 + Lightning's backward /
+        optimizer step / DDP all-reduce), hand-scheduled instead of autograd-driven:
+
+        forward   trunk in train() mode, one call per view, activations kept on a tape (batch-statistics BatchNorm,
+                  running statistics updated); regressor with dropout; SMPL-X + transform + projection; get_loss
+        backward  loss -> SMPL-X -> rot6d -> regressor (parameter gradients + d loss / d features) -> trunk, view 0 then
+                  view 1 accumulating, every gradient written straight into the optimizer's flat gradient buffer
+        update    ONE all-reduce of the flat buffer over the ranks (NCCL over NVLink), ONE Adam(amsgrad) launch.
+        ``deccam`` takes part with a zero gradient (it is unused by the two-view model, model_copenet.py:73).
+        Returns ``(loss, losses)`` as device tensors (no host sync).  The batch per rank must be a multiple of 8 pairs."""
+        if not self.model.training:
+            raise RuntimeError("training_step needs the module in train() mode (batch-statistics BatchNorm, dropout)")
+        im0, im1 = input_batch["im0"].float(), input_batch["im1"].float()
+        B = im0.shape[0]
+        in_trans, in_trans_unscaled = self._init_translation(B, im0.device)
+        reg_iters = getattr(self.hparams, "reg_iters", 3)
+        xf0 = self.model._forward_feat_ext_train(im0.contiguous(), tape=0)
+        xf1 = self.model._forward_feat_ext_train(im1.contiguous(), tape=1)
+        pred, ctx = self.model.ief_train_forward(xf0, xf1, input_batch["bb0"], input_batch["bb1"], in_trans, in_trans,
+                                                 iters=reg_iters, mask1=mask1, mask2=mask2)
+        out = self._after_regressor(pred, (input_batch["intr0"], input_batch["intr1"]), in_trans_unscaled)
+        loss, losses, g = self.loss_and_head_backward(input_batch, out)
+        optimizer.zero_grad()
+        gr = self.model.ief_train_backward(ctx, g["pred_pose0"], g["pred_betas0"], g["pred_pose1"], g["pred_betas1"],
+                                           want_feature_grads=True, into_param_grads=True)
+        self.model.backward_feat_ext(im0, 0, gr["xf0"], accumulate=False, into_param_grads=True)
+        self.model.backward_feat_ext(im1, 1, gr["xf1"], accumulate=True, into_param_grads=True)
+        scale = optimizer.allreduce_grads()
+        optimizer.step(grad_scale=scale)
+        return loss, losses

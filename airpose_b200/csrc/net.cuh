@@ -66,6 +66,20 @@ struct airpose_net {
   float* bn_scale = nullptr;
   float* bn_shift = nullptr;
   std::vector<int64_t> bn_save_off;
+  // tape of a training-mode forward (one per view): what the trunk backward needs
+  struct Tape {
+    int n = 0, cap = 0;
+    std::vector<__nv_bfloat16*> z, y;   // per conv: raw output, and BN(+residual)+ReLU output
+    __nv_bfloat16* pooled = nullptr;    // max-pooled stem output = input of layer1
+    float* stats = nullptr;             // per conv [mean(C) | invstd(C)]
+  } tape[2];
+  // scratch of the backward pass
+  __nv_bfloat16* bw[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // gradient ping-pong / dz / dpre / dilated
+  __nv_bfloat16* bw_t0 = nullptr;       // transposed dz   [Cout][M]
+  __nv_bfloat16* bw_t1 = nullptr;       // transposed im2col(x) [K][M]
+  __nv_bfloat16* bw_w = nullptr;        // packed dgrad weights / wgrad output
+  float* bw_coef = nullptr;             // [3][2048] BatchNorm backward coefficients
+  int bw_cap = 0;
   std::map<std::pair<int, int>, airpose::TrunkPlan> plansA;        // (images, 2 * first image inside the group + buffer set)
   std::map<int, airpose::TrunkPlan> plansB;                        // images
 };

@@ -559,6 +559,9 @@ static int bn_train(airpose_net* h, int idx, const __nv_bfloat16* z, int64_t M, 
   return 0;
 }
 
+static int backbone_fwd_train_tape(airpose_net* h, const float* x, int n, const airpose_bn_train_params* bn, float* out_feat,
+                                   cudaStream_t st);
+
 extern "C" int64_t airpose_bn_saved_stats_floats(void) {
   int64_t n = 0;
   for (const ConvSpec& s : resnet50_specs()) n += 2 * s.cout;
@@ -584,6 +587,7 @@ extern "C" int airpose_backbone_fwd_train(airpose_net_t* h, const float* x, int 
     h->bn_save_off.clear();
     for (const ConvSpec& s : h->specs) { h->bn_save_off.push_back(off); off += 2 * s.cout; }
   }
+  if (bn->tape >= 0) return backbone_fwd_train_tape(h, x, n, bn, out_feat, st);
   __nv_bfloat16* Z = h->ztrain;
   __nv_bfloat16* const* buf = h->actS[0];
   // stem: pack, raw 7x7 conv, BN + ReLU in place, max-pool
@@ -631,10 +635,574 @@ extern "C" int airpose_backbone_fwd_train(airpose_net_t* h, const float* x, int 
   return 0;
 }
 
+// Only the trunk part of airpose_net_load (packed bf16 conv weights, folded eval BatchNorm): what a full training step
+// invalidates every iteration; the collapsed regressor matrix is re-formed lazily by the next eval-mode regressor call.
+extern "C" int airpose_net_load_trunk(airpose_net_t* h, const airpose_net_params* p, void* stream_) {
+  AP_REQUIRE(h && p, "airpose_net_load_trunk: null argument");
+  if (load_trunk(h, p->conv, p->bn_eps, (cudaStream_t)stream_)) return 1;
+  h->loaded = true;
+  return 0;
+}
+
 // Only the regressor part of airpose_net_load (the collapsed matrix G): what changes between the steps of a
 // regressor-only training run.
 extern "C" int airpose_net_load_regressor(airpose_net_t* h, const airpose_net_params* p, void* stream_) {
   AP_REQUIRE(h && p, "airpose_net_load_regressor: null argument");
   AP_REQUIRE(h->loaded && !h->hmr_loaded, "airpose_net_load_regressor: the two-view network is not loaded");
   return ief_load(h, p, (cudaStream_t)stream_);
+}
+
+// ================================================================================================ trunk backward
+// (see airpose_backbone_bwd_train in include/airpose_b200.h)
+namespace airpose {
+
+// ---- small elementwise / layout kernels of the backward pass
+// g_y[n,7,7,C] = g_feat[n,C] / 49   (AvgPool2d(7) backward)
+__global__ void avgpool_bwd_kernel(const float* __restrict__ g_feat, int n, __nv_bfloat16* __restrict__ gy) {
+  const int64_t total = (int64_t)n * 49 * kFeat;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % kFeat);
+    const int img = (int)(i / (49 * kFeat));
+    gy[i] = __float2bfloat16_rn(g_feat[(size_t)img * kFeat + c] * (1.f / 49.f));
+  }
+}
+
+// partial sums of dpre = dy * [y > 0] and dpre * xhat per channel (xhat = (z - mean) * invstd)
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                                            const __nv_bfloat16* __restrict__ z, const float* __restrict__ stats,
+                                                            int64_t M, int C, float* __restrict__ part) {
+  __shared__ float red[256][17];
+  const int groups = C / 8, lanes = 256 / groups;
+  const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  const int64_t per = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(M, r0 + per);
+  float s[8], q[8], mean[8], istd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = q[j] = 0.f; mean[j] = stats[cg * 8 + j]; istd[j] = stats[C + cg * 8 + j]; }
+  if (rl < lanes)
+    for (int64_t r = r0 + rl; r < r1; r += lanes) {
+      const uint4 vd = __ldg(reinterpret_cast<const uint4*>(dy + r * C + cg * 8));
+      const uint4 vz = __ldg(reinterpret_cast<const uint4*>(z + r * C + cg * 8));
+      uint4 vy = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);     // "positive" when there is no ReLU
+      if (y) vy = __ldg(reinterpret_cast<const uint4*>(y + r * C + cg * 8));
+      const uint32_t ud[4] = {vd.x, vd.y, vd.z, vd.w}, uz[4] = {vz.x, vz.y, vz.z, vz.w}, uy[4] = {vy.x, vy.y, vy.z, vy.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float d0 = __uint_as_float(uy[j] << 16) > 0.f ? __uint_as_float(ud[j] << 16) : 0.f;
+        const float d1 = __uint_as_float(uy[j] & 0xFFFF0000u) > 0.f ? __uint_as_float(ud[j] & 0xFFFF0000u) : 0.f;
+        const float x0 = (__uint_as_float(uz[j] << 16) - mean[2 * j]) * istd[2 * j];
+        const float x1 = (__uint_as_float(uz[j] & 0xFFFF0000u) - mean[2 * j + 1]) * istd[2 * j + 1];
+        s[2 * j] += d0; q[2 * j] = fmaf(d0, x0, q[2 * j]);
+        s[2 * j + 1] += d1; q[2 * j + 1] = fmaf(d1, x1, q[2 * j + 1]);
+      }
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][8 + j] = q[j]; }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    float ts[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ts[j] = 0.f;
+    for (int l = 0; l < lanes; ++l)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ts[j] += red[l * groups + threadIdx.x][j];
+    float* o = part + ((size_t)blockIdx.x * C + threadIdx.x * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[2 * j] = ts[j]; o[2 * j + 1] = ts[8 + j]; }
+  }
+}
+
+// dgamma, dbeta (fp32, overwritten or accumulated) and the coefficients of dz = c1 (dpre - c2 - xhat c3)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int slabs, int64_t M, int C, const float* __restrict__ gamma,
+                                       const float* __restrict__ stats, float* __restrict__ g_gamma, float* __restrict__ g_beta,
+                                       int accumulate, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int i = 0; i < slabs; ++i) { s += part[((size_t)i * C + c) * 2]; q += part[((size_t)i * C + c) * 2 + 1]; }
+  if (g_gamma) { g_gamma[c] = (float)q + (accumulate ? g_gamma[c] : 0.f); g_beta[c] = (float)s + (accumulate ? g_beta[c] : 0.f); }
+  coef[c] = gamma[c] * stats[C + c];
+  coef[2048 + c] = (float)(s / (double)M);
+  coef[4096 + c] = (float)(q / (double)M);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                                           const __nv_bfloat16* __restrict__ z, const float* __restrict__ stats,
+                                                           const float* __restrict__ coef, int64_t M, int C,
+                                                           __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dpre_out) {
+  const int groups = C / 8;
+  const int64_t total = M * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    const uint4 vd = __ldg(reinterpret_cast<const uint4*>(dy) + i);
+    const uint4 vz = __ldg(reinterpret_cast<const uint4*>(z) + i);
+    uint4 vy = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    if (y) vy = __ldg(reinterpret_cast<const uint4*>(y) + i);
+    const uint32_t ud[4] = {vd.x, vd.y, vd.z, vd.w}, uz[4] = {vz.x, vz.y, vz.z, vz.w}, uy[4] = {vy.x, vy.y, vy.z, vy.w};
+    __align__(16) __nv_bfloat16 o[8], p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      const uint32_t wd = ud[j >> 1], wz = uz[j >> 1], wy = uy[j >> 1];
+      const float dv = (j & 1) ? __uint_as_float(wd & 0xFFFF0000u) : __uint_as_float(wd << 16);
+      const float zv = (j & 1) ? __uint_as_float(wz & 0xFFFF0000u) : __uint_as_float(wz << 16);
+      const float yv = (j & 1) ? __uint_as_float(wy & 0xFFFF0000u) : __uint_as_float(wy << 16);
+      const float dp = yv > 0.f ? dv : 0.f;
+      const float xh = (zv - stats[c]) * stats[C + c];
+      o[j] = __float2bfloat16_rn(coef[c] * (dp - coef[2048 + c] - xh * coef[4096 + c]));
+      p[j] = __float2bfloat16_rn(dp);
+    }
+    reinterpret_cast<uint4*>(dz)[i] = *reinterpret_cast<const uint4*>(o);
+    if (dpre_out) reinterpret_cast<uint4*>(dpre_out)[i] = *reinterpret_cast<const uint4*>(p);
+  }
+}
+
+// out[c][m] = in[m][c]   (bf16, 32 x 32 tiles through shared memory)
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t M, int C, __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int64_t m0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t m = m0 + r; const int c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (m < M && c < C) ? in[m * C + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r; const int64_t m = m0 + threadIdx.x;
+    if (c < C && m < M) out[(int64_t)c * M + m] = tile[threadIdx.x][r];
+  }
+}
+
+// out[(tap, c)][m] = x[n, ho*s + r - pad, wo*s + sx - pad, c]  (zero outside): transposed im2col, K-major in the pixel index m
+__global__ void im2colT_kernel(const __nv_bfloat16* __restrict__ x, int n, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                               __nv_bfloat16* __restrict__ out) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int64_t M = (int64_t)n * Ho * Wo;
+  const int64_t m0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tap = blockIdx.z, r = tap / k, sx = tap % k;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t m = m0 + i; const int c = c0 + threadIdx.x;
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (m < M && c < C) {
+      const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), img = (int)(m / ((int64_t)Wo * Ho));
+      const int h = ho * stride + r - pad, w = wo * stride + sx - pad;
+      if (h >= 0 && h < H && w >= 0 && w < W) v = x[(((int64_t)img * H + h) * W + w) * C + c];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i; const int64_t m = m0 + threadIdx.x;
+    if (c < C && m < M) out[((int64_t)tap * C + c) * M + m] = tile[threadIdx.x][i];
+  }
+}
+
+// stem: out[(r*7+s)*3 + c][m] = x_nchw[n, c, 2p - 3 + r, 2q - 3 + s]  (147 rows; rows 147..191 are zero)
+__global__ void stem_im2colT_kernel(const float* __restrict__ x, int n, __nv_bfloat16* __restrict__ out) {
+  const int64_t M = (int64_t)n * 112 * 112;
+  const int kk = blockIdx.y;                      // 0..191
+  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (kk < 147) {
+      const int c = kk % 3, tap = kk / 3, r = tap / 7, s = tap % 7;
+      const int q = (int)(m % 112), p = (int)((m / 112) % 112), img = (int)(m / (112 * 112));
+      const int h = 2 * p - 3 + r, w = 2 * q - 3 + s;
+      if (h >= 0 && h < 224 && w >= 0 && w < 224) v = __ldg(x + (((int64_t)img * 3 + c) * 224 + h) * 224 + w);
+    }
+    out[(int64_t)kk * M + m] = __float2bfloat16_rn(v);
+  }
+}
+
+// [n,Ho,Wo,C] -> [n,2Ho,2Wo,C] with the values at the even positions and zeros elsewhere
+__global__ void dilate2_kernel(const __nv_bfloat16* __restrict__ in, int n, int Ho, int Wo, int C, __nv_bfloat16* __restrict__ out) {
+  const int groups = C / 8;
+  const int64_t total = (int64_t)n * 2 * Ho * 2 * Wo * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % groups);
+    const int64_t pix = i / groups;
+    const int w = (int)(pix % (2 * Wo)), hh = (int)((pix / (2 * Wo)) % (2 * Ho)), img = (int)(pix / ((int64_t)4 * Wo * Ho));
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!(w & 1) && !(hh & 1)) v = __ldg(reinterpret_cast<const uint4*>(in + ((((int64_t)img * Ho + (hh >> 1)) * Wo + (w >> 1)) * C)) + cg);
+    reinterpret_cast<uint4*>(out)[i] = v;
+  }
+}
+
+// dgrad operand: out[cin][(r', s')][cout] = w[cout][cin][k-1-r'][k-1-s']   (bf16; for k = 1 a plain transpose)
+__global__ void pack_dgrad_weight_kernel(const float* __restrict__ w, int cout, int cin, int k, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)cin * k * k * cout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % cout), tap = (int)((i / cout) % (k * k)), c = (int)(i / ((int64_t)cout * k * k));
+    const int r = tap / k, s = tap % k;
+    out[i] = __float2bfloat16_rn(w[(((int64_t)o * cin + c) * k + (k - 1 - r)) * k + (k - 1 - s)]);
+  }
+}
+
+// g_weight[cout][c][tap] (+)= D[cout][tap * cin + c]   (D bf16 with row pitch ldd)
+__global__ void wgrad_unpack_kernel(const __nv_bfloat16* __restrict__ D, int cout, int cin, int kk, int ldd, float* __restrict__ g, int accumulate) {
+  const int64_t total = (int64_t)cout * cin * kk;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % kk), c = (int)((i / kk) % cin), o = (int)(i / ((int64_t)kk * cin));
+    const float v = __bfloat162float(D[(int64_t)o * ldd + tap * cin + c]);
+    g[i] = v + (accumulate ? g[i] : 0.f);
+  }
+}
+
+// MaxPool2d(3, 2, 1) backward on NHWC bf16: every input pixel collects the gradient of the windows whose (first) maximum it is
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy, int n, __nv_bfloat16* __restrict__ gx) {
+  const int64_t total = (int64_t)n * 112 * 112 * 64;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % 64);
+    const int64_t pix = i / 64;
+    const int w = (int)(pix % 112), h = (int)((pix / 112) % 112), img = (int)(pix / (112 * 112));
+    const float xv = __bfloat162float(x[i]);
+    float g = 0.f;
+    // windows (pr, q) that contain (h, w): pr*2-1 <= h <= pr*2+1
+    for (int pr = max(0, (h - 1 + 1) / 2); pr <= min(55, (h + 1) / 2); ++pr)
+      for (int q = max(0, (w - 1 + 1) / 2); q <= min(55, (w + 1) / 2); ++q) {
+        // is (h, w) the first maximum of this window in scan order?
+        bool is_max = true;
+        for (int r = 0; r < 3 && is_max; ++r)
+          for (int s = 0; s < 3; ++s) {
+            const int hh = pr * 2 - 1 + r, ww = q * 2 - 1 + s;
+            if (hh < 0 || hh >= 112 || ww < 0 || ww >= 112) continue;
+            const float o = __bfloat162float(x[(((int64_t)img * 112 + hh) * 112 + ww) * 64 + c]);
+            if (o > xv || (o == xv && (hh < h || (hh == h && ww < w)))) { is_max = false; break; }
+          }
+        if (is_max) g += __bfloat162float(gy[(((int64_t)img * 56 + pr) * 56 + q) * 64 + c]);
+      }
+    gx[i] = __float2bfloat16_rn(g);
+  }
+}
+
+}  // namespace airpose
+
+using namespace airpose;
+
+// ---- per-conv geometry of the trunk in forward order (index = conv index of resnet50_specs)
+struct ConvIO {
+  int in_src;      // index of the conv whose y is this conv's input; -1 = max-pooled stem output; -2 = the image (stem)
+  int res_src;     // residual added before the ReLU: conv index, -1 = pooled, -3 = none
+  int relu;
+  int Hin, Hout;   // input / output spatial size
+};
+static std::vector<ConvIO> resnet50_io() {
+  std::vector<ConvIO> io;
+  io.push_back({-2, -3, 1, 224, 112});
+  const int layers[4] = {3, 4, 6, 3};
+  int idx = 1, H = 56, x_src = -1;
+  for (int li = 0; li < 4; ++li)
+    for (int blk = 0; blk < layers[li]; ++blk) {
+      const bool down = blk == 0;
+      const int stride = (li > 0 && blk == 0) ? 2 : 1;
+      const int Ho = H / stride;
+      io.push_back({x_src, -3, 1, H, H});                       // conv1
+      io.push_back({idx, -3, 1, H, Ho});                        // conv2 (stride on the 3x3)
+      io.push_back({idx + 1, down ? idx + 3 : x_src, 1, Ho, Ho});   // conv3 + residual
+      if (down) io.push_back({x_src, -3, 0, H, Ho});            // downsample conv + BN, no ReLU
+      x_src = idx + 2;
+      idx += down ? 4 : 3;
+      H = Ho;
+    }
+  return io;
+}
+
+static int tape_reserve(airpose_net* h, int t, int n) {
+  airpose_net::Tape& tp = h->tape[t];
+  const std::vector<ConvIO> io = resnet50_io();
+  if (tp.cap < n) {
+    for (auto p : tp.z) cudaFree(p);
+    for (auto p : tp.y) cudaFree(p);
+    cudaFree(tp.pooled); cudaFree(tp.stats);
+    tp.z.assign(io.size(), nullptr); tp.y.assign(io.size(), nullptr);
+    for (size_t i = 0; i < io.size(); ++i) {
+      const size_t elems = (size_t)n * io[i].Hout * io[i].Hout * h->specs[i].cout;
+      AP_CHECK_CUDA(cudaMalloc((void**)&tp.z[i], elems * 2));
+      AP_CHECK_CUDA(cudaMalloc((void**)&tp.y[i], elems * 2));
+    }
+    AP_CHECK_CUDA(cudaMalloc((void**)&tp.pooled, (size_t)n * 56 * 56 * 64 * 2));
+    size_t ns = 0;
+    for (const ConvSpec& s : h->specs) ns += 2 * s.cout;
+    AP_CHECK_CUDA(cudaMalloc((void**)&tp.stats, ns * sizeof(float)));
+    tp.cap = n;
+  }
+  tp.n = n;
+  return 0;
+}
+
+// training-mode forward that keeps every layer's z and y (called from airpose_backbone_fwd_train when bn->tape >= 0)
+static int backbone_fwd_train_tape(airpose_net* h, const float* x, int n, const airpose_bn_train_params* bn, float* out_feat,
+                                   cudaStream_t st) {
+  const int t = bn->tape;
+  AP_REQUIRE(t == 0 || t == 1, "airpose_backbone_fwd_train: tape must be -1, 0 or 1");
+  if (tape_reserve(h, t, n)) return 1;
+  airpose_net::Tape& tp = h->tape[t];
+  const std::vector<ConvIO> io = resnet50_io();
+  airpose_bn_train_params b2 = *bn;
+  b2.saved_stats = tp.stats;
+  {
+    const int64_t work = (int64_t)n * 2 * kStemPlaneRows * 112;
+    stem_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(work, 128), 148 * 32), 128, 0, st>>>(x, n, h->colS[0]);
+    AP_LAUNCH_CHECK();
+    GemmLaunch L{};
+    if (build_stem_gemm(h, n, 0, &L, true)) return 1;
+    L.epi.out_bf16 = tp.z[0];
+    if (enable_tma_epilogue(&L)) return 1;
+    if (launch_gemm(L, st)) return 1;
+    if (bn_train(h, 0, tp.z[0], (int64_t)n * 112 * 112, 64, &b2, nullptr, 1, tp.y[0], st)) return 1;
+    maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64((int64_t)n * 56 * 56 * 8, 256), 148 * 16), 256, 0, st>>>(tp.y[0], n, tp.pooled);
+    AP_LAUNCH_CHECK();
+  }
+  auto src = [&](int s) -> const __nv_bfloat16* { return s == -1 ? tp.pooled : tp.y[s]; };
+  auto run = [&](int i) -> int {
+    GemmLaunch L{};
+    if (conv_launch(h, i, src(io[i].in_src), n, io[i].Hin, io[i].Hin, nullptr, 0, tp.z[i], &L, true) || launch_gemm(L, st)) return 1;
+    const __nv_bfloat16* res = io[i].res_src == -3 ? nullptr : src(io[i].res_src);
+    return bn_train(h, i, tp.z[i], (int64_t)n * io[i].Hout * io[i].Hout, h->specs[i].cout, &b2, res, io[i].relu, tp.y[i], st);
+  };
+  for (int i = 1; i < (int)io.size(); ++i) {
+    if (io[i].res_src > i) {                       // conv3 of a block with a downsample branch: the branch (next index) runs first
+      if (run(io[i].res_src) || run(i)) return 1;
+      ++i;                                         // the downsample entry has been done
+    } else {
+      if (run(i)) return 1;
+    }
+  }
+  // the last block's output: conv3 of layer4.2 = index 51 (52 convs + stem = 53; the last entry in forward order is conv3 of the
+  // last block because downsample entries follow conv3 only in the first block of a layer)
+  const int last = (int)io.size() - 1;
+  avgpool_kernel<<<ceil_div(n * kFeat, 256), 256, 0, st>>>(tp.y[last], n, out_feat);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+static int bw_reserve(airpose_net* h, int n) {
+  if (h->bw_cap >= n) return 0;
+  for (auto& p : h->bw) { cudaFree(p); p = nullptr; }
+  cudaFree(h->bw_t0); cudaFree(h->bw_t1); cudaFree(h->bw_w); cudaFree(h->bw_coef);
+  const size_t act = (size_t)n * 112 * 112 * 64;                 // the largest activation (== 56*56*256)
+  for (auto& p : h->bw) AP_CHECK_CUDA(cudaMalloc((void**)&p, act * 2));
+  AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_t0, act * 2));
+  AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_t1, std::max((size_t)576 * 3136, (size_t)192 * 12544) * n * 2));
+  AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_w, (size_t)512 * 4608 * 2 * 2));
+  AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_coef, 3 * 2048 * sizeof(float)));
+  if (!h->bn_part) AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_part, (size_t)kBnSlabs * 2048 * 2 * sizeof(float)));
+  h->bw_cap = n;
+  return 0;
+}
+
+static unsigned ew_grid(int64_t n) { return (unsigned)std::min<int64_t>(ceil_div64(n, 256), 148 * 16); }
+
+// BatchNorm (+ReLU) backward of conv i: dy -> dz (and dpre when asked), dgamma / dbeta into the output struct
+static int bn_bwd(airpose_net* h, const airpose_net::Tape& tp, int i, int64_t M, const airpose_bn_train_params* bn,
+                  const airpose_trunk_grads* g, const __nv_bfloat16* dy, bool relu, __nv_bfloat16* dz, __nv_bfloat16* dpre,
+                  cudaStream_t st) {
+  const int C = h->specs[i].cout;
+  const float* stats = tp.stats + h->bn_save_off[i];
+  const __nv_bfloat16* y = relu ? tp.y[i] : nullptr;
+  bn_bwd_reduce_kernel<<<kBnSlabs, 256, 0, st>>>(dy, y, tp.z[i], stats, M, C, h->bn_part);
+  AP_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, bn->bn_weight[i], stats, g->g_bn_weight[i],
+                                                           g->g_bn_bias[i], g->accumulate, h->bw_coef);
+  AP_LAUNCH_CHECK();
+  bn_bwd_apply_kernel<<<ew_grid(M * (C / 8)), 256, 0, st>>>(dy, y, tp.z[i], stats, h->bw_coef, M, C, dz, dpre);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// weight gradient of conv i: g_weight (+)= dz^T . im2col(x_in)  on the tensor cores (both operands transposed to K-major)
+static int conv_wgrad(airpose_net* h, int i, const __nv_bfloat16* dz, const __nv_bfloat16* x_in, int n, int Hin, int Hout,
+                      const airpose_trunk_grads* g, cudaStream_t st) {
+  const ConvSpec& s = h->specs[i];
+  const int64_t M = (int64_t)n * Hout * Hout;
+  const int Kdim = s.k * s.k * s.cin;
+  dim3 tb(32, 8);
+  transpose_bf16_kernel<<<dim3((unsigned)ceil_div64(M, 32), ceil_div(s.cout, 32)), tb, 0, st>>>(dz, M, s.cout, h->bw_t0);
+  AP_LAUNCH_CHECK();
+  if (s.k == 1 && s.stride == 1) {
+    transpose_bf16_kernel<<<dim3((unsigned)ceil_div64(M, 32), ceil_div(s.cin, 32)), tb, 0, st>>>(x_in, M, s.cin, h->bw_t1);
+  } else {
+    im2colT_kernel<<<dim3((unsigned)ceil_div64(M, 32), ceil_div(s.cin, 32), s.k * s.k), tb, 0, st>>>(x_in, n, Hin, Hin, s.cin, s.k, s.stride,
+                                                                                                   s.pad, Hout, Hout, h->bw_t1);
+  }
+  AP_LAUNCH_CHECK();
+  airpose_gemm_args ga{};
+  ga.A = h->bw_t0; ga.lda = M; ga.B = h->bw_t1; ga.ldb = M;
+  ga.M = s.cout; ga.N = Kdim; ga.K = (int)M;
+  ga.out_bf16 = h->bw_w; ga.ldd = Kdim;
+  if (airpose_gemm_bf16(&ga, st)) return 1;
+  const int64_t total = (int64_t)s.cout * Kdim;
+  wgrad_unpack_kernel<<<ew_grid(total), 256, 0, st>>>(h->bw_w, s.cout, s.cin, s.k * s.k, Kdim, g->g_weight[i], g->accumulate);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// data gradient of conv i: dx = conv_transpose(dz, W) (+ add), as an implicit-GEMM conv of (dilated) dz with the flipped weights
+static int conv_dgrad(airpose_net* h, int i, const float* w_f32, const __nv_bfloat16* dz, int n, int Hin, int Hout, const __nv_bfloat16* add,
+                      __nv_bfloat16* dx, __nv_bfloat16* scratch, cudaStream_t st) {
+  const ConvSpec& s = h->specs[i];
+  __nv_bfloat16* wd = h->bw_w + (size_t)512 * 4608;              // second half of the weight scratch
+  pack_dgrad_weight_kernel<<<ew_grid((int64_t)s.cin * s.k * s.k * s.cout), 256, 0, st>>>(w_f32, s.cout, s.cin, s.k, wd);
+  AP_LAUNCH_CHECK();
+  if (s.k == 1 && s.stride == 1) {
+    airpose_gemm_args ga{};
+    ga.A = dz; ga.lda = s.cout; ga.B = wd; ga.ldb = s.cout;
+    ga.M = n * Hout * Hout; ga.N = s.cin; ga.K = s.cout;
+    ga.residual = add; ga.ldr = s.cin;
+    ga.out_bf16 = dx; ga.ldd = s.cin;
+    return airpose_gemm_bf16(&ga, st);
+  }
+  if (s.k == 1) {          // 1x1 stride 2 (downsample): GEMM on the strided pixels, then scatter to the even positions
+    AP_REQUIRE(add == nullptr, "conv_dgrad: strided 1x1 with an addend is not used");
+    airpose_gemm_args ga{};
+    ga.A = dz; ga.lda = s.cout; ga.B = wd; ga.ldb = s.cout;
+    ga.M = n * Hout * Hout; ga.N = s.cin; ga.K = s.cout;
+    ga.out_bf16 = scratch; ga.ldd = s.cin;
+    if (airpose_gemm_bf16(&ga, st)) return 1;
+    dilate2_kernel<<<ew_grid((int64_t)n * Hin * Hin * (s.cin / 8)), 256, 0, st>>>(scratch, n, Hout, Hout, s.cin, dx);
+    AP_LAUNCH_CHECK();
+    return 0;
+  }
+  const __nv_bfloat16* src = dz;
+  if (s.stride == 2) {
+    dilate2_kernel<<<ew_grid((int64_t)n * Hin * Hin * (s.cout / 8)), 256, 0, st>>>(dz, n, Hout, Hout, s.cout, scratch);
+    AP_LAUNCH_CHECK();
+    src = scratch;
+  }
+  airpose_conv_args ca{};
+  ca.x = src; ca.n = n; ca.H = Hin; ca.W = Hin; ca.Cin = s.cout;
+  ca.w = wd; ca.Cout = s.cin; ca.ksize = 3; ca.stride = 1; ca.pad = 1;
+  ca.residual = add; ca.relu = 0; ca.out = dx;
+  return airpose_conv_bf16(&ca, st);
+}
+
+extern "C" int airpose_backbone_bwd_train(airpose_net_t* h, const float* x, int n, int t, const airpose_bn_train_params* bn,
+                                          const float* g_feat, const airpose_trunk_grads* g, const float* const* conv_weights,
+                                          void* stream_) {
+  AP_REQUIRE(h && x && bn && g_feat && g && conv_weights, "airpose_backbone_bwd_train: null argument");
+  AP_REQUIRE(t == 0 || t == 1, "airpose_backbone_bwd_train: tape must be 0 or 1");
+  const airpose_net::Tape& tp = h->tape[t];
+  AP_REQUIRE(tp.n == n && n > 0, "airpose_backbone_bwd_train: tape %d holds a forward of %d images, not %d", t, tp.n, n);
+  AP_REQUIRE(n % 8 == 0, "airpose_backbone_bwd_train: n=%d must be a multiple of 8 (16-byte row pitch of the transposed operands)", n);
+  for (size_t i = 0; i < h->specs.size(); ++i)
+    AP_REQUIRE(g->g_weight[i] && g->g_bn_weight[i] && g->g_bn_bias[i] && conv_weights[i], "airpose_backbone_bwd_train: null buffer (conv %zu)", i);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (bw_reserve(h, n)) return 1;
+  const std::vector<ConvIO> io = resnet50_io();
+  auto src = [&](int s) -> const __nv_bfloat16* { return s == -1 ? tp.pooled : tp.y[s]; };
+  __nv_bfloat16 *G = h->bw[0], *G2 = h->bw[1], *DZ = h->bw[2], *DPRE = h->bw[3], *SCR = h->bw[4], *T = h->bw[5];
+  // gradient of the last block's output from the average pool
+  avgpool_bwd_kernel<<<ew_grid((int64_t)n * 49 * kFeat), 256, 0, st>>>(g_feat, n, G);
+  AP_LAUNCH_CHECK();
+  // walk the blocks in reverse
+  const int layers[4] = {3, 4, 6, 3};
+  std::vector<int> first_idx;          // conv1 index of every block, in forward order
+  { int idx = 1; for (int li = 0; li < 4; ++li) for (int b = 0; b < layers[li]; ++b) { first_idx.push_back(idx); idx += (b == 0) ? 4 : 3; } }
+  for (int bi = (int)first_idx.size() - 1; bi >= 0; --bi) {
+    const int i1 = first_idx[bi], i2 = i1 + 1, i3 = i1 + 2;
+    // a block has a downsample branch iff its conv3 takes its residual from conv index i1 + 3
+    const bool has_ds = io[i3].res_src == i1 + 3;
+    const int Hin = io[i1].Hin, Ho = io[i3].Hout;
+    const int64_t Mo = (int64_t)n * Ho * Ho;
+    // conv3 + bn3 (+ residual, ReLU):  G = dL/d(block output)
+    if (bn_bwd(h, tp, i3, Mo, bn, g, G, true, DZ, DPRE, st)) return 1;                       // DPRE = gradient of the residual branch
+    if (conv_wgrad(h, i3, DZ, tp.y[i2], n, Ho, Ho, g, st)) return 1;
+    if (conv_dgrad(h, i3, conv_weights[i3], DZ, n, Ho, Ho, nullptr, G2, SCR, st)) return 1;  // G2 = dL/d y2
+    // conv2 + bn2 + ReLU
+    if (bn_bwd(h, tp, i2, Mo, bn, g, G2, true, DZ, nullptr, st)) return 1;
+    if (conv_wgrad(h, i2, DZ, tp.y[i1], n, Hin, Ho, g, st)) return 1;
+    if (conv_dgrad(h, i2, conv_weights[i2], DZ, n, Hin, Ho, nullptr, G2, SCR, st)) return 1; // G2 = dL/d y1   [n,Hin,Hin,planes]
+    // conv1 + bn1 + ReLU
+    const int64_t Mi = (int64_t)n * Hin * Hin;
+    const __nv_bfloat16* xin = src(io[i1].in_src);
+    if (bn_bwd(h, tp, i1, Mi, bn, g, G2, true, DZ, nullptr, st)) return 1;
+    if (conv_wgrad(h, i1, DZ, xin, n, Hin, Hin, g, st)) return 1;
+    const __nv_bfloat16* addend = DPRE;                                                      // identity residual: dL/dx += dpre3
+    if (has_ds) {
+      const int id = i1 + 3;
+      if (bn_bwd(h, tp, id, Mo, bn, g, DPRE, false, T, nullptr, st)) return 1;               // T = dz of the downsample conv
+      if (conv_wgrad(h, id, T, xin, n, Hin, Ho, g, st)) return 1;
+      if (conv_dgrad(h, id, conv_weights[id], T, n, Hin, Ho, nullptr, G, SCR, st)) return 1; // G = downsample path of dL/dx
+      addend = G;
+      // conv1's data gradient adds the downsample path
+      if (conv_dgrad(h, i1, conv_weights[i1], DZ, n, Hin, Hin, addend, G2, SCR, st)) return 1;
+      std::swap(G, G2);
+    } else {
+      if (conv_dgrad(h, i1, conv_weights[i1], DZ, n, Hin, Hin, addend, G, SCR, st)) return 1;
+    }
+    // G now holds dL/d(block input)
+  }
+  // stem: max-pool backward, bn1 + ReLU backward, weight gradient of the 7x7 conv (no data gradient: the input is the image)
+  maxpool_bwd_kernel<<<ew_grid((int64_t)n * 112 * 112 * 64), 256, 0, st>>>(tp.y[0], G, n, G2);
+  AP_LAUNCH_CHECK();
+  const int64_t M0 = (int64_t)n * 112 * 112;
+  if (bn_bwd(h, tp, 0, M0, bn, g, G2, true, DZ, nullptr, st)) return 1;
+  {
+    dim3 tb(32, 8);
+    transpose_bf16_kernel<<<dim3((unsigned)ceil_div64(M0, 32), 2), tb, 0, st>>>(DZ, M0, 64, h->bw_t0);
+    AP_LAUNCH_CHECK();
+    stem_im2colT_kernel<<<dim3(148 * 4, 192), 256, 0, st>>>(x, n, h->bw_t1);
+    AP_LAUNCH_CHECK();
+    airpose_gemm_args ga{};
+    ga.A = h->bw_t0; ga.lda = M0; ga.B = h->bw_t1; ga.ldb = M0;
+    ga.M = 64; ga.N = 192; ga.K = (int)M0;
+    ga.out_bf16 = h->bw_w; ga.ldd = 192;
+    if (airpose_gemm_bf16(&ga, st)) return 1;
+    wgrad_unpack_kernel<<<ew_grid(64 * 147), 256, 0, st>>>(h->bw_w, 64, 3, 49, 192, g->g_weight[0], g->accumulate);
+    AP_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ---- building blocks of the trunk backward exported for the per-layer parity tests
+extern "C" int airpose_debug_conv_bwd(airpose_net_t* h, int conv_idx, int n, const void* dz, const void* x_in, const float* w_f32,
+                                      const void* add, void* out_dx, float* out_gw, int accumulate, void* stream_) {
+  AP_REQUIRE(h && dz && x_in && w_f32 && out_gw, "airpose_debug_conv_bwd: null argument");
+  AP_REQUIRE(conv_idx >= 1 && conv_idx < (int)h->specs.size() && n > 0 && n % 8 == 0, "airpose_debug_conv_bwd: bad index / n");
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (bw_reserve(h, n)) return 1;
+  const std::vector<ConvIO> io = resnet50_io();
+  airpose_trunk_grads g{};
+  g.g_weight[conv_idx] = out_gw;
+  g.accumulate = accumulate;
+  if (conv_wgrad(h, conv_idx, (const __nv_bfloat16*)dz, (const __nv_bfloat16*)x_in, n, io[conv_idx].Hin, io[conv_idx].Hout, &g, st)) return 1;
+  if (out_dx && conv_dgrad(h, conv_idx, w_f32, (const __nv_bfloat16*)dz, n, io[conv_idx].Hin, io[conv_idx].Hout, (const __nv_bfloat16*)add,
+                           (__nv_bfloat16*)out_dx, h->bw[4], st)) return 1;
+  return 0;
+}
+
+extern "C" int airpose_debug_bn_bwd(airpose_net_t* h, int64_t M, int C, const void* dy, const void* y, const void* z, const float* stats,
+                                    const float* gamma, void* out_dz, void* out_dpre, float* g_gamma, float* g_beta, int accumulate,
+                                    void* stream_) {
+  AP_REQUIRE(h && dy && z && stats && gamma && out_dz && g_gamma && g_beta, "airpose_debug_bn_bwd: null argument");
+  AP_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "airpose_debug_bn_bwd: unsupported channel count %d", C);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (bw_reserve(h, 8)) return 1;
+  bn_bwd_reduce_kernel<<<kBnSlabs, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats, M, C, h->bn_part);
+  AP_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, gamma, stats, g_gamma, g_beta, accumulate, h->bw_coef);
+  AP_LAUNCH_CHECK();
+  bn_bwd_apply_kernel<<<ew_grid(M * (C / 8)), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats,
+                                                            h->bw_coef, M, C, (__nv_bfloat16*)out_dz, (__nv_bfloat16*)out_dpre);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// copies one tensor of a training tape into a caller buffer (tests): which = 0 raw conv output z, 1 normalised output y, 2 pooled stem
+extern "C" int airpose_debug_tape_get(airpose_net_t* h, int t, int conv_idx, int which, void* dst, int64_t dst_elems, void* stream_) {
+  AP_REQUIRE(h && dst && (t == 0 || t == 1), "airpose_debug_tape_get: bad argument");
+  const airpose_net::Tape& tp = h->tape[t];
+  AP_REQUIRE(tp.n > 0, "airpose_debug_tape_get: tape %d is empty", t);
+  const std::vector<ConvIO> io = resnet50_io();
+  const __nv_bfloat16* src;
+  int64_t elems;
+  if (which == 2) { src = tp.pooled; elems = (int64_t)tp.n * 56 * 56 * 64; }
+  else {
+    AP_REQUIRE(conv_idx >= 0 && conv_idx < (int)io.size(), "airpose_debug_tape_get: bad conv index");
+    src = which == 0 ? tp.z[conv_idx] : tp.y[conv_idx];
+    elems = (int64_t)tp.n * io[conv_idx].Hout * io[conv_idx].Hout * h->specs[conv_idx].cout;
+  }
+  AP_REQUIRE(dst_elems == elems, "airpose_debug_tape_get: destination holds %lld elements, the tensor has %lld", (long long)dst_elems, (long long)elems);
+  AP_CHECK_CUDA(cudaMemcpyAsync(dst, src, elems * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+  return 0;
 }

@@ -155,9 +155,14 @@ class copenet(nn.Module):
                     p = self._fill_common(_lib.NetParams())        # only the regressor changed: keep the packed convs
                     _lib.check(lib.airpose_net_load_regressor(self._handle, C.byref(p), _lib.current_stream()),
                                "airpose_net_load_regressor")
+                    self._loaded_key = (trunk_key, reg_key)
+                elif not need_regressor and type(self) is copenet:
+                    p = self._fill_common(_lib.NetParams())        # trunk-only caller: re-pack the convs, leave G for later
+                    _lib.check(lib.airpose_net_load_trunk(self._handle, C.byref(p), _lib.current_stream()), "airpose_net_load_trunk")
+                    self._loaded_key = (trunk_key, loaded[1])
                 else:
                     self._load_native(lib)                         # packs the convs, folds BN and forms G
-            self._loaded_key = (trunk_key, reg_key)
+                    self._loaded_key = (trunk_key, reg_key)
         return lib, self._handle
 
     def _fill_common(self, p):
@@ -211,20 +216,27 @@ class copenet(nn.Module):
                        "airpose_backbone_fwd")
         return out
 
-    def _forward_feat_ext_train(self, x, saved_stats=None):
-        device = x.device
-        n = x.shape[0]
-        lib, h = self._ensure(max(n, 2), device, allow_training=True, need_regressor=False)
+    def _bn_train_params(self, tape=-1, update_running=True):
         bn = _lib.BnTrainParams()
         pairs = self._conv_bn_pairs()
         for i, (conv, m) in enumerate(pairs):
             bn.bn_weight[i], bn.bn_bias[i] = m.weight.data_ptr(), m.bias.data_ptr()
-            if m.track_running_stats and m.running_mean is not None:
+            if update_running and m.track_running_stats and m.running_mean is not None:
                 bn.running_mean[i], bn.running_var[i] = m.running_mean.data_ptr(), m.running_var.data_ptr()
         momenta = {m.momentum for _, m in pairs}
         if len(momenta) != 1 or None in momenta:
             raise NotImplementedError("all BatchNorm layers must share one numeric momentum (the reference uses 0.1)")
         bn.momentum, bn.eps = float(momenta.pop()), float(self.bn1.eps)
+        bn.tape = int(tape)
+        return bn
+
+    def _forward_feat_ext_train(self, x, saved_stats=None, tape=-1):
+        """``tape`` 0 / 1 keeps this call's activations in the native handle for ``backward_feat_ext`` (one tape per view)."""
+        device = x.device
+        n = x.shape[0]
+        lib, h = self._ensure(max(n, 2), device, allow_training=True, need_regressor=False)
+        pairs = self._conv_bn_pairs()
+        bn = self._bn_train_params(tape)
         if saved_stats is not None:
             bn.saved_stats = saved_stats.data_ptr()
         out = torch.empty(n, 2048, device=device, dtype=torch.float32)
@@ -237,6 +249,39 @@ class copenet(nn.Module):
         for _, m in pairs:     # the running statistics were written through raw pointers: make the eval path re-fold them
             if m.track_running_stats and m.running_mean is not None:
                 m.running_mean._airpose_gen = getattr(m.running_mean, "_airpose_gen", 0) + 1
+        return out
+
+    def backward_feat_ext(self, x, tape, g_feat, accumulate=False, into_param_grads=False):
+        """Backward of the training-mode ``forward_feat_ext`` call recorded on ``tape``: gradients of the 53 conv weights
+        and of every BatchNorm weight / bias, given d loss / d features ``g_feat`` [n,2048] and the same images ``x``.
+        Returns a dict keyed like ``state_dict``; ``into_param_grads`` writes into the parameters' ``.grad`` instead
+        (``accumulate`` adds: the second view of a pair)."""
+        device = self.conv1.weight.device
+        lib, h = self._ensure(0, device, allow_training=True, need_regressor=False)
+        x = x.detach().to(device=device, dtype=torch.float32).contiguous()
+        g_feat = g_feat.detach().to(device=device, dtype=torch.float32).contiguous()
+        names = {id(p): n for n, p in self.named_parameters()}
+        out = {}
+        tg = _lib.TrunkGrads()
+        wptr = (C.c_void_p * 53)()
+        for i, (conv, m) in enumerate(self._conv_bn_pairs()):
+            bufs = []
+            for p in (conv.weight, m.weight, m.bias):
+                if into_param_grads:
+                    if p.grad is None:
+                        p.grad = torch.zeros_like(p)
+                    bufs.append(p.grad)
+                else:
+                    bufs.append(torch.zeros_like(p) if accumulate else torch.empty_like(p))
+                out[names[id(p)]] = bufs[-1]
+            tg.g_weight[i], tg.g_bn_weight[i], tg.g_bn_bias[i] = (b.data_ptr() for b in bufs)
+            wptr[i] = conv.weight.data_ptr()
+        tg.accumulate = int(bool(accumulate))
+        bn = self._bn_train_params(tape, update_running=False)
+        with torch.cuda.device(device):
+            _lib.check(lib.airpose_backbone_bwd_train(h, x.data_ptr(), x.shape[0], int(tape), C.byref(bn), g_feat.data_ptr(),
+                                                      C.byref(tg), C.byref(wptr), _lib.current_stream()),
+                       "airpose_backbone_bwd_train")
         return out
 
     def forward_feat_ext_pair(self, x0, x1):

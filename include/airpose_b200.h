@@ -207,10 +207,44 @@ typedef struct {
   float momentum;              /* 0.1 */
   float eps;                   /* 1e-5 */
   float* saved_stats;
+  int32_t tape;                /* 0 / 1: keep every layer's raw and normalised output of this call in the handle's tape
+                                  (one per view) for airpose_backbone_bwd_train; -1: forward only */
 } airpose_bn_train_params;
 int64_t airpose_bn_saved_stats_floats(void);
 int airpose_backbone_fwd_train(airpose_net_t* h, const float* x_nchw, int n_images, const airpose_bn_train_params* bn,
                                float* out_feat, void* stream);
+/* Backward of airpose_backbone_fwd_train for one view (tape 0 / 1): d loss / d features [n,2048] -> gradients of every
+ * conv weight (reference layout [Cout,Cin,kh,kw]) and BatchNorm weight / bias, fp32.  accumulate = 0 overwrites the
+ * output buffers, 1 adds (the second view of a pair: the two views share the weights).  x_nchw: the images of that
+ * forward call (the stem's weight gradient needs them).  n must be a multiple of 8.
+ * bf16 tensor-core GEMMs throughout: data gradients as implicit-GEMM convolutions of dz with the flipped, transposed
+ * weights (stride-2 layers through a zero-dilated dz), weight gradients as [Cout, K] = dz^T . im2col(x) with both operands
+ * transposed to K-major and the long pixel contraction split stream-K over all SMs; BatchNorm backward as two HBM-bound
+ * passes per layer. */
+typedef struct {
+  float* g_weight[53];
+  float* g_bn_weight[53];
+  float* g_bn_bias[53];
+  int32_t accumulate;
+} airpose_trunk_grads;
+int airpose_backbone_bwd_train(airpose_net_t* h, const float* x_nchw, int n_images, int tape, const airpose_bn_train_params* bn,
+                               const float* g_feat, const airpose_trunk_grads* grads, const float* const* conv_weights_f32,
+                               void* stream);    /* conv_weights_f32: the 53 live fp32 conv weights [Cout,Cin,kh,kw] (DEVICE) */
+/* Building blocks of the trunk backward, exported for the per-layer parity tests (same code paths as above).
+ * conv_bwd: weight gradient (fp32 [Cout,Cin,k,k], overwritten or accumulated) and, when out_dx is given, data gradient
+ * (+ add) of trunk conv `conv_idx` for n images: dz bf16 [n,Ho,Wo,Cout], x_in bf16 [n,Hin,Win,Cin].
+ * bn_bwd: BatchNorm(+ReLU) backward on [M,C] bf16: dy, y (post-activation output; NULL = no ReLU), z (conv output),
+ * stats [mean(C) | invstd(C)], gamma -> dz, dpre (optional), dgamma, dbeta. */
+int airpose_debug_conv_bwd(airpose_net_t* h, int conv_idx, int n_images, const void* dz, const void* x_in, const float* w_f32,
+                           const void* add, void* out_dx, float* out_gw, int accumulate, void* stream);
+int airpose_debug_bn_bwd(airpose_net_t* h, int64_t M, int C, const void* dy, const void* y, const void* z, const float* stats,
+                         const float* gamma, void* out_dz, void* out_dpre, float* g_gamma, float* g_beta, int accumulate,
+                         void* stream);
+/* copies one bf16 tensor of a training tape (which: 0 = raw conv output z, 1 = BN(+residual)(+ReLU) output y, 2 = max-pooled
+ * stem output) into a caller buffer of exactly that many elements (tests). */
+int airpose_debug_tape_get(airpose_net_t* h, int tape, int conv_idx, int which, void* dst, int64_t dst_elems, void* stream);
+/* Re-packs only the conv weights / folded BatchNorm of airpose_net_load (what a full training step invalidates). */
+int airpose_net_load_trunk(airpose_net_t* h, const airpose_net_params* p, void* stream);
 /* Re-forms only the collapsed regressor matrix of airpose_net_load (the conv weights stay packed): what changes
  * between the steps of a regressor-only training run. */
 int airpose_net_load_regressor(airpose_net_t* h, const airpose_net_params* p, void* stream);

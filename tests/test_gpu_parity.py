@@ -899,3 +899,227 @@ def test_trunk_train_mode_matches_torch(tmp_path, net_state):
     net2.load_state_dict(net.state_dict())
     ev2 = net2.to(DEV).eval().forward_feat_ext(x)
     assert torch.equal(ev, ev2)
+
+
+# ----------------------------------------------------------------------------- trunk backward (training mode)
+def test_trunk_backward_matches_autograd(tmp_path, net_state):
+    """airpose_backbone_bwd_train (all 53 conv weights, 106 BatchNorm parameters) against torch autograd, layer by layer on
+    the CUDA path's OWN forward activations (read back from the training tape): each layer's local function
+    relu(BN(conv(x_in)) + residual) is rebuilt in fp32 torch from the tape's inputs and differentiated with the incoming
+    gradient, and the data gradients are chained in Python exactly as the network wires them.  (Comparing against an
+    independent bf16 forward instead mixes in its ReLU-mask differences, which 50 BatchNorm backward passes amplify.)"""
+    import torch.nn.functional as F
+    from airpose_b200.model_copenet import getcopenet
+    lib = _lib.load()
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+    net = getcopenet(mp, pretrained=False)
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in net_state.items()}, strict=True)
+    net = net.to(DEV).train()
+    n = 8
+    x = torch.from_numpy(synthetic.make_inputs(n, 5)["im0"]).to(DEV)
+    gfeat = torch.randn(n, 2048, generator=torch.Generator(device="cpu").manual_seed(1)).to(DEV)
+    feat = net._forward_feat_ext_train(x, tape=0)
+    grads = net.backward_feat_ext(x, 0, gfeat)
+    h = net._handle
+    specs = list(synthetic.conv_specs())
+    # geometry: (input source, residual source, relu, Hout) per conv, forward order (mirrors resnet50_io in trunk.cu)
+    io = [(-2, -3, True, 112)]
+    idx, H, xsrc = 1, 56, -1
+    for li, blocks in enumerate((3, 4, 6, 3)):
+        for b in range(blocks):
+            s2 = 2 if (li > 0 and b == 0) else 1
+            Ho = H // s2
+            io += [(xsrc, -3, True, H), (idx, -3, True, Ho), (idx + 1, idx + 3 if b == 0 else xsrc, True, Ho)]
+            if b == 0:
+                io.append((xsrc, -3, False, Ho))
+            xsrc, idx, H = idx + 2, idx + (4 if b == 0 else 3), Ho
+
+    def tape(i, which):
+        if which == 2:
+            shape = (n, 56, 56, 64)
+        else:
+            shape = (n, io[i][3], io[i][3], specs[i][1])
+        tns = torch.empty(shape, device=DEV, dtype=torch.bfloat16)
+        _lib.check(lib.airpose_debug_tape_get(h, 0, i, which, tns.data_ptr(), tns.numel(), _lib.current_stream()), "tape_get")
+        return tns.float().permute(0, 3, 1, 2).contiguous()          # NCHW fp32
+
+    P = {k: torch.from_numpy(np.asarray(v)).to(DEV) for k, v in net_state.items()}
+    rb = lambda t_: t_.to(torch.bfloat16).float()
+    act = lambda s_: tape(0, 2) if s_ == -1 else tape(s_, 1)
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    ref = {}
+    try:
+        last = len(io) - 1
+        assert rel_err(feat.cpu().numpy(), tape(last, 1).mean(dim=(2, 3)).cpu().numpy()) < 1e-5
+        gin = {last: (gfeat / 49.0)[:, :, None, None].expand(n, 2048, 7, 7).contiguous()}      # AvgPool2d(7) backward
+        order = []
+        idx = 1
+        blocks_first = []
+        for li, blocks in enumerate((3, 4, 6, 3)):
+            for b in range(blocks):
+                blocks_first.append((idx, b == 0))
+                idx += 4 if b == 0 else 3
+        for i1, has_ds in reversed(blocks_first):
+            order += [i1 + 2] + ([i1 + 3] if has_ds else []) + [i1 + 1, i1]
+        for i in order:
+            name, cout, cin, k, stride, pad, bn_name = specs[i]
+            xin = act(io[i][0]).requires_grad_(True)
+            w = rb(P[name + ".weight"]).requires_grad_(True)
+            gam, bet = P[bn_name + ".weight"].clone().requires_grad_(True), P[bn_name + ".bias"].clone().requires_grad_(True)
+            res = act(io[i][1]).requires_grad_(True) if io[i][1] != -3 else None
+            z = rb(F.conv2d(xin, w, stride=stride, padding=pad))
+            yv = F.batch_norm(z, None, None, gam, bet, training=True, eps=1e-5)
+            if res is not None:
+                yv = yv + res
+            if io[i][2]:
+                yv = F.relu(yv)
+            (yv * gin.pop(i)).sum().backward()
+            ref[name + ".weight"], ref[bn_name + ".weight"], ref[bn_name + ".bias"] = w.grad, gam.grad, bet.grad
+            for srcidx, gr in ((io[i][0], xin.grad), (io[i][1], res.grad if res is not None else None)):
+                if gr is None or srcidx == -3:
+                    continue
+                gin[srcidx] = gin[srcidx] + gr if srcidx in gin else gr
+        # stem: max-pool, bn1 + ReLU, conv1
+        y0 = tape(0, 1).requires_grad_(True)
+        (F.max_pool2d(y0, 3, 2, 1) * gin.pop(-1)).sum().backward()
+        w = rb(P["conv1.weight"]).requires_grad_(True)
+        gam, bet = P["bn1.weight"].clone().requires_grad_(True), P["bn1.bias"].clone().requires_grad_(True)
+        yv = F.relu(F.batch_norm(rb(F.conv2d(rb(x), w, stride=2, padding=3)), None, None, gam, bet, training=True, eps=1e-5))
+        (yv * y0.grad).sum().backward()
+        ref["conv1.weight"], ref["bn1.weight"], ref["bn1.bias"] = w.grad, gam.grad, bet.grad
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    worst, bad = 0.0, []
+    for name, _, _, _, _, _, bn_name in specs:
+        for k in (name + ".weight", bn_name + ".weight", bn_name + ".bias"):
+            got, rf = grads[k].cpu().numpy(), ref[k].cpu().numpy()
+            e = rel_err(got, rf)
+            cos = float((got * rf).sum() / (np.linalg.norm(got) * np.linalg.norm(rf) + 1e-30))
+            print("  %-34s rel err %.2e  cos %.5f" % (k, e, cos))
+            worst = max(worst, e)
+            if e > 1e-1 or cos < 0.995:          # bf16 dz / bf16 weight-gradient GEMM output against fp32 autograd
+                bad.append((k, e, cos))
+    print("trunk backward: worst rel err %.3e over %d tensors" % (worst, 3 * len(specs)))
+    assert not bad, bad[:6]
+    # second view accumulates into the same buffers
+    net.backward_feat_ext(x, 0, gfeat, into_param_grads=True)
+    g3 = net.backward_feat_ext(x, 0, gfeat, accumulate=True, into_param_grads=True)
+    assert rel_err(g3["layer3.2.conv2.weight"].cpu().numpy(), 2 * grads["layer3.2.conv2.weight"].cpu().numpy()) < 1e-2
+
+
+@pytest.mark.parametrize("conv_idx,name", [(2, "layer1.0.conv2"), (3, "layer1.0.conv3"), (4, "layer1.0.downsample.0"),
+                                           (12, "layer2.0.conv2"), (14, "layer2.0.downsample.0"), (11, "layer2.0.conv1"),
+                                           (44, "layer4.0.conv2"), (52, "layer4.2.conv3")])
+def test_conv_backward_blocks_match_autograd(net_gpu, net_state, conv_idx, name):
+    """Data and weight gradient of single trunk convs (1x1, 3x3, stride 1 and 2) against torch autograd on identical bf16 inputs."""
+    import torch.nn.functional as F
+    lib = _lib.load()
+    specs = list(synthetic.conv_specs())
+    assert specs[conv_idx][0] == name
+    _, cout, cin, k, stride, pad, _ = specs[conv_idx]
+    n = 8
+    layer = int(name[5])
+    out_res, in_res = {1: 56, 2: 28, 3: 14, 4: 7}[layer], {1: 56, 2: 56, 3: 28, 4: 14}[layer]
+    first_block_input = name.split(".")[1] == "0" and (name.endswith("conv1") or name.endswith("conv2") or "downsample" in name)
+    Hin = in_res if first_block_input else out_res
+    Ho = (Hin + 2 * pad - k) // stride + 1
+    g = torch.Generator(device="cpu").manual_seed(conv_idx)
+    x = torch.randn(n, Hin, Hin, cin, generator=g).to(DEV).to(torch.bfloat16)
+    dz = (torch.randn(n, Ho, Ho, cout, generator=g) * 0.1).to(DEV).to(torch.bfloat16)
+    add = torch.randn(n, Hin, Hin, cin, generator=g).to(DEV).to(torch.bfloat16) if k == 3 or stride == 1 else None
+    w = torch.from_numpy(np.asarray(net_state[name + ".weight"])).to(DEV)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        (F.conv2d(xr, wr, stride=stride, padding=pad) * dz.float().permute(0, 3, 1, 2)).sum().backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    lib_h = net_gpu._ensure(16, torch.device(DEV), need_regressor=False)[1]
+    dx = torch.empty(n, Hin, Hin, cin, device=DEV, dtype=torch.bfloat16)
+    gw = torch.empty_like(w)
+    _lib.check(lib.airpose_debug_conv_bwd(lib_h, conv_idx, n, dz.data_ptr(), x.data_ptr(), w.data_ptr(), add.data_ptr() if add is not None else None,
+                                          dx.data_ptr(), gw.data_ptr(), 0, _lib.current_stream()), "conv_bwd")
+    torch.cuda.synchronize()
+    ref_dx = xr.grad.permute(0, 2, 3, 1) + (add.float() if add is not None else 0)
+    e_dx = rel_err(dx.float().cpu().numpy(), ref_dx.cpu().numpy())
+    e_gw = rel_err(gw.cpu().numpy(), wr.grad.cpu().numpy())
+    print("%-24s dgrad rel err %.2e  wgrad rel err %.2e" % (name, e_dx, e_gw))
+    assert e_dx < 1e-2 and e_gw < 1e-2
+
+
+@pytest.mark.parametrize("M,C,relu", [(392, 2048, True), (25088, 64, True), (6272, 512, False)])
+def test_bn_backward_block_matches_autograd(net_gpu, M, C, relu):
+    import torch.nn.functional as F
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(C)
+    z = torch.randn(M, C, generator=g).to(DEV).to(torch.bfloat16)
+    res = torch.randn(M, C, generator=g).to(DEV).to(torch.bfloat16)
+    dy = (torch.randn(M, C, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(DEV).requires_grad_(True)
+    beta = torch.randn(C, generator=g).to(DEV).requires_grad_(True)
+    zr = z.float().requires_grad_(True)
+    pre = F.batch_norm(zr, None, None, gamma, beta, training=True, eps=1e-5) + res.float()
+    y = F.relu(pre) if relu else pre
+    (y * dy.float()).sum().backward()
+    mean = z.float().mean(0)
+    invstd = 1.0 / torch.sqrt(z.float().var(0, unbiased=False) + 1e-5)
+    stats = torch.cat([mean, invstd]).contiguous()
+    yb = y.detach().to(torch.bfloat16)
+    lib_h = net_gpu._ensure(16, torch.device(DEV), need_regressor=False)[1]
+    dz = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    dpre = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    gg, gb = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    _lib.check(lib.airpose_debug_bn_bwd(lib_h, M, C, dy.data_ptr(), yb.data_ptr() if relu else None, z.data_ptr(), stats.data_ptr(),
+                                        gamma.data_ptr(), dz.data_ptr(), dpre.data_ptr(), gg.data_ptr(), gb.data_ptr(), 0,
+                                        _lib.current_stream()), "bn_bwd")
+    torch.cuda.synchronize()
+    e = [rel_err(dz.float().cpu().numpy(), zr.grad.cpu().numpy()), rel_err(gg.cpu().numpy(), gamma.grad.cpu().numpy()),
+         rel_err(gb.cpu().numpy(), beta.grad.cpu().numpy())]
+    print("bn bwd M=%d C=%d relu=%d: dz %.2e dgamma %.2e dbeta %.2e" % (M, C, relu, *e))
+    assert max(e) < 1e-2
+
+
+def test_training_step_full(tmp_path, smplx_dir, smplx_data):
+    """The whole-network training step: every parameter except deccam moves, BatchNorm running statistics are updated,
+    everything stays finite, and repeated steps on a fixed batch (fixed dropout masks) reduce the loss.  (Gradient parity
+    is covered piecewise: loss/SMPL-X/rot6d, regressor, trunk backward, Adam.)"""
+    import torch_port as tp
+    mod = _loss_module(tmp_path, smplx_dir)
+    state = synthetic.make_network_state(123, dec_gain=0.01)
+    mod.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()})
+    mod = mod.to(DEV).train()
+    opt = mod.configure_optimizers()
+    B = 8
+    x = synthetic.make_inputs(B, 31)
+    _, m = _torch_smplx64(smplx_data)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        gt = _synthetic_gt(tp, m, B, x)
+    finally:
+        torch.set_default_dtype(old)
+    batch = {k: t(v) for k, v in {**x, **gt}.items()}
+    g = torch.Generator(device="cpu").manual_seed(4)
+    m1 = (torch.bernoulli(torch.full((3, 2, B, 1024), 0.5), generator=g) * 2.0).to(DEV)
+    m2 = (torch.bernoulli(torch.full((3, 2, B, 1024), 0.5), generator=g) * 2.0).to(DEV)
+    before = {n: p.detach().clone() for n, p in mod.model.named_parameters()}
+    rm0 = mod.model.layer3[2].bn2.running_mean.clone()
+    losses = []
+    for i in range(10):
+        loss, _ = mod.training_step(batch, opt, mask1=m1, mask2=m2)
+        losses.append(float(loss))
+    print("full training step: loss", " ".join("%.1f" % v for v in losses))
+    assert all(np.isfinite(losses)) and losses[-1] < 0.7 * losses[0]
+    for n, p in mod.model.named_parameters():
+        assert torch.isfinite(p).all(), n
+        moved = not torch.equal(p.detach(), before[n])
+        assert moved == (not n.startswith("deccam")), n
+    assert not torch.equal(mod.model.layer3[2].bn2.running_mean, rm0)
+    assert int(mod.model.bn1.num_batches_tracked) == 20          # two views per step
+    # eval mode afterwards uses the updated weights and statistics
+    mod.eval()
+    out = mod.fwd_pass(batch)
+    assert torch.isfinite(out["pred_vertices_cam0"]).all()
