@@ -522,7 +522,10 @@ int launch_bn(const GemmLaunch& L, KP& kp, cudaStream_t stream) {
   const int sms = std::min(num_sms(), kMaxGrid);
   static const int min_kb = getenv("AIRPOSE_SK_SPLIT_MINKB") ? atoi(getenv("AIRPOSE_SK_SPLIT_MINKB")) : 8;
   kp.split = (kp.num_kb >= min_kb && tiles < 8 * sms && tiles % sms != 0) ? 1 : 0;
-  cfg.gridDim = dim3((unsigned)(kp.split ? std::min(sms, std::max(std::min(tiles, sms), units / 8)) : std::min(tiles, sms)));
+  // a tile is never cut into more than 16 ranges: its owner gathers the partials one after the other, which at 70+
+  // partials per tile (weight-gradient GEMMs: 2 tiles, 1500 k-blocks) cost more than the mainloop they parallelised
+  cfg.gridDim = dim3((unsigned)(kp.split ? std::min(sms, std::max(std::min(tiles, sms), std::min(units / 8, tiles * 16)))
+                                         : std::min(tiles, sms)));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;

@@ -21,18 +21,19 @@ namespace {
 constexpr int kF = 2048, kU = 284, kZ = kF + kU, kH = 1024, kD = 145;   // feature, state part of z, fc1 in, hidden, decoded
 
 // C[M,N] = alpha * sum_k A(m,k) B(k,n) + beta * C[M,N];  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]
-constexpr int kTM = 64, kTN = 64, kTK = 16;
+constexpr int kTM = 32, kTN = 32, kTK = 32;      // small tiles: the products have 2B <= 128 rows, parallelism comes from the CTA count
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
                                                     const float* __restrict__ B, int64_t sbk, int64_t sbn,
                                                     float* __restrict__ C, int64_t ldc, int M, int N, int K, float alpha, float beta) {
   __shared__ float As[kTK][kTM + 1], Bs[kTK][kTN + 1];
   const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;        // 16 x 16 threads, 4 x 4 outputs each
-  float acc[4][4];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;        // 16 x 16 threads, 2 x 2 outputs each
+  constexpr int kR = kTM / 16;
+  float acc[kR][kR];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < kR; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < kR; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < K; k0 += kTK) {
     for (int i = threadIdx.x; i < kTM * kTK; i += 256) {
       // pick the faster-varying index along whichever stride is 1 so the loads coalesce
@@ -50,23 +51,23 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kTK; ++k) {
-      float a[4], b[4];
+      float a[kR], b[kR];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+      for (int i = 0; i < kR; ++i) a[i] = As[k][ty * kR + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+      for (int j = 0; j < kR; ++j) b[j] = Bs[k][tx * kR + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < kR; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < kR; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < kR; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+    for (int j = 0; j < kR; ++j) {
+      const int gm = m0 + ty * kR + i, gn = n0 + tx * kR + j;
       if (gm < M && gn < N) {
         float* c = C + gm * ldc + gn;
         *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);

@@ -190,14 +190,26 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
   }
 }
 
+// fixed-order sum of the slab partials of one channel by one warp: lane l takes slabs l, l+32, ..., then a shuffle tree
+__device__ __forceinline__ void slab_sum(const float* __restrict__ part, int slabs, int C, int c, double& s, double& q) {
+  const int lane = threadIdx.x & 31;
+  s = 0.0; q = 0.0;
+  for (int i = lane; i < slabs; i += 32) { s += part[((size_t)i * C + c) * 2]; q += part[((size_t)i * C + c) * 2 + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); q += __shfl_down_sync(0xffffffffu, q, o); }
+  s = __shfl_sync(0xffffffffu, s, 0); q = __shfl_sync(0xffffffffu, q, 0);
+}
+
+// one warp per channel (blockDim = 128 -> 4 channels per CTA)
 __global__ void bn_finalize_kernel(const float* __restrict__ part, int slabs, int64_t M, int C, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int i = 0; i < slabs; ++i) { s += part[((size_t)i * C + c) * 2]; q += part[((size_t)i * C + c) * 2 + 1]; }
+  double s, q;
+  slab_sum(part, slabs, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   const double mean = s / (double)M;
   const double var = fmax(q / (double)M - mean * mean, 0.0);            // biased, as F.batch_norm normalises
   const float invstd = (float)(1.0 / sqrt(var + (double)eps));
@@ -548,7 +560,7 @@ static int bn_train(airpose_net* h, int idx, const __nv_bfloat16* z, int64_t M, 
   bn_stats_kernel<<<kBnSlabs, 256, 0, st>>>(z, M, C, h->bn_part);
   AP_LAUNCH_CHECK();
   float* save = bn->saved_stats ? bn->saved_stats + h->bn_save_off[idx] : nullptr;
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, bn->bn_weight[idx], bn->bn_bias[idx], bn->eps,
+  bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, bn->bn_weight[idx], bn->bn_bias[idx], bn->eps,
                                                        bn->momentum, bn->running_mean[idx], bn->running_var[idx], h->bn_scale,
                                                        h->bn_shift, save, save ? save + C : nullptr);
   AP_LAUNCH_CHECK();
@@ -716,10 +728,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int slabs, int64_t M, int C, const float* __restrict__ gamma,
                                        const float* __restrict__ stats, float* __restrict__ g_gamma, float* __restrict__ g_beta,
                                        int accumulate, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int i = 0; i < slabs; ++i) { s += part[((size_t)i * C + c) * 2]; q += part[((size_t)i * C + c) * 2 + 1]; }
+  double s, q;
+  slab_sum(part, slabs, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   if (g_gamma) { g_gamma[c] = (float)q + (accumulate ? g_gamma[c] : 0.f); g_beta[c] = (float)s + (accumulate ? g_beta[c] : 0.f); }
   coef[c] = gamma[c] * stats[C + c];
   coef[2048 + c] = (float)(s / (double)M);
@@ -1002,7 +1015,7 @@ static int bn_bwd(airpose_net* h, const airpose_net::Tape& tp, int i, int64_t M,
   const __nv_bfloat16* y = relu ? tp.y[i] : nullptr;
   bn_bwd_reduce_kernel<<<kBnSlabs, 256, 0, st>>>(dy, y, tp.z[i], stats, M, C, h->bn_part);
   AP_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, bn->bn_weight[i], stats, g->g_bn_weight[i],
+  bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, bn->bn_weight[i], stats, g->g_bn_weight[i],
                                                            g->g_bn_bias[i], g->accumulate, h->bw_coef);
   AP_LAUNCH_CHECK();
   bn_bwd_apply_kernel<<<ew_grid(M * (C / 8)), 256, 0, st>>>(dy, y, tp.z[i], stats, h->bw_coef, M, C, dz, dpre);
@@ -1180,7 +1193,7 @@ extern "C" int airpose_debug_bn_bwd(airpose_net_t* h, int64_t M, int C, const vo
   if (bw_reserve(h, 8)) return 1;
   bn_bwd_reduce_kernel<<<kBnSlabs, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats, M, C, h->bn_part);
   AP_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, gamma, stats, g_gamma, g_beta, accumulate, h->bw_coef);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, gamma, stats, g_gamma, g_beta, accumulate, h->bw_coef);
   AP_LAUNCH_CHECK();
   bn_bwd_apply_kernel<<<ew_grid(M * (C / 8)), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats,
                                                             h->bw_coef, M, C, (__nv_bfloat16*)out_dz, (__nv_bfloat16*)out_dpre);

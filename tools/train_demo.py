@@ -1,5 +1,6 @@
-"""Regressor-only data-parallel training (the reference's `train_reg_only` mode with copenet's loss) on N GPUs:
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_reg_only_demo.py [--pairs 32] [--steps 20]
+"""Data-parallel training on N GPUs -- the whole network (--full: BASELINE config 4) or the regressor only (the
+reference's `train_reg_only` mode with copenet's loss):
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_demo.py [--pairs 32] [--steps 20]
 Every rank trains on its own shard of a synthetic batch; the one collective of the step is the all-reduce of the
 optimizer's flat gradient buffer (NCCL over NVLink).  Prints one JSON line on rank 0: pairs/s (device time, max over
 ranks), first/last loss, and whether the parameters are still bit-identical across ranks."""
@@ -20,6 +21,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=32, help="pairs per GPU per step (BASELINE config 4: 32)")
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--full", action="store_true", help="train the whole network (trunk backward included), not only the regressor")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -32,8 +34,10 @@ def main():
     synthetic.write_smplx_model(tmp, 0)
     mod = copenet_twoview(Namespace(smpl_mean_params=mp, smplx_model_dir=tmp, batch_size=B, val_batch_size=B, reg_iters=3, lr=5e-5))
     mod.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synthetic.make_network_state(123, dec_gain=0.01).items()})
-    mod = mod.to(dev).eval()
-    opt = mod.configure_optimizers_reg_only()
+    mod = mod.to(dev)
+    mod = mod.train() if args.full else mod.eval()
+    opt = mod.configure_optimizers() if args.full else mod.configure_optimizers_reg_only()
+    step = mod.training_step if args.full else mod.training_step_reg_only
     # global synthetic batch, sharded by pair (no overlap between ranks); GT = SMPL-X forward of an independent sample
     x = synthetic.make_inputs(B * world, 123)
     li = synthetic.make_lbs_inputs(B * world, seed=9)
@@ -49,7 +53,7 @@ def main():
     batch.update({k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in gt.items()})
     losses = []
     for i in range(args.warmup):
-        loss, _ = mod.training_step_reg_only(batch, opt)
+        loss, _ = step(batch, opt)
         losses.append(loss)
     torch.cuda.synchronize()
     if world > 1:
@@ -57,7 +61,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        loss, _ = mod.training_step_reg_only(batch, opt)
+        loss, _ = step(batch, opt)
         losses.append(loss)
     e1.record()
     torch.cuda.synchronize()
@@ -72,7 +76,7 @@ def main():
         same = bool(torch.equal(lo, hi))
     lv = torch.stack(losses).cpu().tolist()
     if rank == 0:
-        print(json.dumps({"mode": "train_reg_only", "n_gpus": world, "pairs_per_gpu": B, "steps": args.steps, "ms_per_step": ms,
+        print(json.dumps({"mode": "train_full" if args.full else "train_reg_only", "n_gpus": world, "pairs_per_gpu": B, "steps": args.steps, "ms_per_step": ms,
                           "pairs_per_s": world * B / (ms * 1e-3), "loss_first": lv[0], "loss_last": lv[-1],
                           "params_identical_across_ranks": same, "trainable_params": int(opt.numel),
                           "collective": "one all-reduce of the flat gradient buffer (%.1f MB) per step" % (opt.numel * 4 / 1e6)}))
