@@ -171,7 +171,8 @@ class copenet_twoview(nn.Module):
     @torch.no_grad()
     def fwd_pass_and_loss(self, input_batch, is_test=False, is_val=False):
         """copenet_twoview.fwd_pass_and_loss (copenet_twoview.py:164-374): forward + get_loss + the
-        reference's output dict.  (The backward half of the training step is not built yet: DESIGN.md.)"""
+        reference's output dict.  (The backward half: ``training_step`` hand-scheduled, or autograd through
+        ``copenet.forward`` in train() mode + ``SMPLX.forward``, see INTEGRATION.md.)"""
         out = self.fwd_pass(input_batch)
         if is_test:
             loss, losses = None, None
@@ -191,7 +192,7 @@ class copenet_twoview(nn.Module):
         [B,135] (as the network returned them, i.e. before the translation un-scaling of :214-218) and
         d loss / d pred_betas{0,1} [B,10] -- the part of ``loss.backward()`` (copenet_twoview.py:378-386) that runs
         through get_loss, perspective_projection, transform_smpl, SMPL-X and rot6d_to_rotmat.  ``out`` is the dict
-        ``fwd_pass`` returned.  The backward through the regressor and the trunk is not built yet."""
+        ``fwd_pass`` returned.  ``training_step`` continues from here through the regressor and the trunk."""
         loss, losses, g = self.get_loss(input_batch, out["pred_smpltrans0"], out["pred_smpltrans1"], out["pred_rotmat0"],
                                         out["pred_rotmat1"], out["pred_betas0"], out["pred_betas1"], out["pred_output_cam0"],
                                         out["pred_output_cam1"], out["pred_joints_2d_cam0"], out["pred_joints_2d_cam1"],
@@ -268,7 +269,7 @@ class copenet_twoview(nn.Module):
                   view 1 accumulating, every gradient written straight into the optimizer's flat gradient buffer
         update    ONE all-reduce of the flat buffer over the ranks (NCCL over NVLink), ONE Adam(amsgrad) launch.
         ``deccam`` takes part with a zero gradient (it is unused by the two-view model, model_copenet.py:73).
-        Returns ``(loss, losses)`` as device tensors (no host sync).  The batch per rank must be a multiple of 8 pairs."""
+        Returns ``(loss, losses)`` as device tensors (no host sync)."""
         if not self.model.training:
             raise RuntimeError("training_step needs the module in train() mode (batch-statistics BatchNorm, dropout)")
         im0, im1 = input_batch["im0"].float(), input_batch["im1"].float()

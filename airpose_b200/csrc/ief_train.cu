@@ -13,6 +13,7 @@
 //
 // This is also the whole trainable part of the reference's `train_reg_only` fine-tuning mode
 // (copenet_real/src/copenet_real/copenet_twoview.py:357-372).
+#include <algorithm>
 #include "common.cuh"
 
 namespace airpose {
@@ -24,7 +25,8 @@ constexpr int kF = 2048, kU = 284, kZ = kF + kU, kH = 1024, kD = 145;   // featu
 constexpr int kTM = 32, kTN = 32, kTK = 32;      // small tiles: the products have 2B <= 128 rows, parallelism comes from the CTA count
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
                                                     const float* __restrict__ B, int64_t sbk, int64_t sbn,
-                                                    float* __restrict__ C, int64_t ldc, int M, int N, int K, float alpha, float beta) {
+                                                    float* __restrict__ C, int64_t ldc, int M, int N, int K, float alpha, float beta,
+                                                    int k_per_split, float* __restrict__ partial) {
   __shared__ float As[kTK][kTM + 1], Bs[kTK][kTN + 1];
   const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;        // 16 x 16 threads, 2 x 2 outputs each
@@ -34,7 +36,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
   for (int i = 0; i < kR; ++i)
 #pragma unroll
     for (int j = 0; j < kR; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += kTK) {
+  // split-K (gridDim.z > 1): this CTA contracts k in [z * k_per_split, ...) and writes its partial tile to partial[z][M][N];
+  // splitk_reduce_kernel adds the partials in a fixed order (no atomics: bitwise reproducible)
+  const int k_begin = blockIdx.z * k_per_split;
+  K = min(K, k_begin + k_per_split);
+  for (int k0 = k_begin; k0 < K; k0 += kTK) {
     for (int i = threadIdx.x; i < kTM * kTK; i += 256) {
       // pick the faster-varying index along whichever stride is 1 so the loads coalesce
       int m, k;
@@ -69,17 +75,50 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
     for (int j = 0; j < kR; ++j) {
       const int gm = m0 + ty * kR + i, gn = n0 + tx * kR + j;
       if (gm < M && gn < N) {
-        float* c = C + gm * ldc + gn;
-        *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);
+        if (gridDim.z > 1) {
+          partial[((size_t)blockIdx.z * M + gm) * N + gn] = acc[i][j];
+        } else {
+          float* c = C + gm * ldc + gn;
+          *c = alpha * acc[i][j] + (beta != 0.f ? beta * *c : 0.f);
+        }
       }
     }
 }
 
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, float* __restrict__ C, int64_t ldc, int M, int N, float beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)M * N) return;
+  float acc = 0.f;
+  for (int z = 0; z < splits; ++z) acc += partial[(size_t)z * M * N + i];
+  float* c = C + (i / N) * ldc + (i % N);
+  *c = acc + (beta != 0.f ? beta * *c : 0.f);
+}
+
+constexpr int64_t kSplitKFloats = (int64_t)4 << 20;     // partial-tile workspace at the end of the caller's workspace (16 MB)
+
 int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc, int M, int N,
-          int K, float beta, cudaStream_t st) {
+          int K, float beta, cudaStream_t st, float* splitk_ws = nullptr) {
   dim3 grid(ceil_div(N, kTN), ceil_div(M, kTM));
-  sgemm_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, 1.f, beta);
+  // the skinny products (2B rows against a 1024 x 2332 weight) have a few dozen tiles and a long serial k loop: cut k
+  int splits = 1;
+  if (splitk_ws) {
+    const int tiles = (int)(grid.x * grid.y);
+    splits = std::min(std::min(16, 592 / std::max(tiles, 1)), K / (4 * kTK));
+    while (splits > 1 && (int64_t)splits * M * N > kSplitKFloats) --splits;
+    splits = std::max(splits, 1);
+  }
+  int k_per = K;
+  if (splits > 1) {
+    k_per = ceil_div(ceil_div(K, splits), kTK) * kTK;
+    splits = ceil_div(K, k_per);
+    grid.z = splits;
+  }
+  sgemm_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, 1.f, beta, k_per, splitk_ws);
   AP_LAUNCH_CHECK();
+  if (splits > 1) {
+    splitk_reduce_kernel<<<(unsigned)ceil_div64((int64_t)M * N, 256), 256, 0, st>>>(splitk_ws, splits, C, ldc, M, N, beta);
+    AP_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -173,7 +212,7 @@ extern "C" int64_t airpose_ief_train_saved_floats(int32_t batch, int32_t iters) 
 }
 extern "C" int64_t airpose_ief_train_workspace_floats(int32_t batch) {
   // state, g_state, d / gd, gz, gh (x2), wdec, bdec, g_wdec, g_bdec
-  return (int64_t)2 * batch * (kD + kD + kD + kZ + kH + kH) + (int64_t)kD * kH * 2 + 2 * kD + 64;
+  return (int64_t)2 * batch * (kD + kD + kD + kZ + kH + kH) + (int64_t)kD * kH * 2 + 2 * kD + 64 + kSplitKFloats;
 }
 
 static int check_common(const airpose_ief_train_args* a, const char* who) {
@@ -190,7 +229,7 @@ static int check_common(const airpose_ief_train_args* a, const char* who) {
 }
 
 struct Ws {
-  float *state, *g_state, *d, *gz, *gh1, *gh2, *wdec, *bdec, *g_wdec, *g_bdec;
+  float *state, *g_state, *d, *gz, *gh1, *gh2, *wdec, *bdec, *g_wdec, *g_bdec, *splitk;
 };
 static Ws carve(float* w, int B) {
   Ws s;
@@ -205,6 +244,7 @@ static Ws carve(float* w, int B) {
   s.g_wdec = w; w += (size_t)kD * kH;
   s.bdec = w; w += kD;
   s.g_bdec = w; w += kD;
+  s.splitk = w + ((16 - ((uintptr_t)w / 4) % 16) % 16);      // 64-byte aligned; the size includes 64 floats of slack
   return s;
 }
 static int load_dec(const airpose_ief_train_args* a, const Ws& s, cudaStream_t st) {
@@ -235,13 +275,13 @@ extern "C" int airpose_ief_train_fwd(const airpose_ief_train_args* a, void* stre
     const float* m2 = a->mask2 ? a->mask2 + (size_t)it * R * kH : nullptr;
     ief_assemble_kernel<<<blocks((int64_t)R * kZ), 256, 0, st>>>(B, a->xf0, a->xf1, a->bb0, a->bb1, s.state, z);
     AP_LAUNCH_CHECK();
-    if (sgemm(z, kZ, 1, a->fc1_w, 1, kZ, h1, kH, R, kH, kZ, 0.f, st)) return 1;                 // h1 = z W1^T
+    if (sgemm(z, kZ, 1, a->fc1_w, 1, kZ, h1, kH, R, kH, kZ, 0.f, st, s.splitk)) return 1;                 // h1 = z W1^T
     bias_mask_kernel<<<blocks((int64_t)R * kH), 256, 0, st>>>(h1, a->fc1_b, m1, R, kH);
     AP_LAUNCH_CHECK();
-    if (sgemm(h1, kH, 1, a->fc2_w, 1, kH, h2, kH, R, kH, kH, 0.f, st)) return 1;                // h2 = h1 W2^T
+    if (sgemm(h1, kH, 1, a->fc2_w, 1, kH, h2, kH, R, kH, kH, 0.f, st, s.splitk)) return 1;                // h2 = h1 W2^T
     bias_mask_kernel<<<blocks((int64_t)R * kH), 256, 0, st>>>(h2, a->fc2_b, m2, R, kH);
     AP_LAUNCH_CHECK();
-    if (sgemm(h2, kH, 1, s.wdec, 1, kH, s.d, kD, R, kD, kH, 0.f, st)) return 1;                 // d = h2 Wdec^T
+    if (sgemm(h2, kH, 1, s.wdec, 1, kH, s.d, kD, R, kD, kH, 0.f, st, s.splitk)) return 1;                 // d = h2 Wdec^T
     state_update_kernel<<<blocks((int64_t)R * kD), 256, 0, st>>>(s.state, s.d, s.bdec, R);
     AP_LAUNCH_CHECK();
   }
@@ -282,24 +322,24 @@ extern "C" int airpose_ief_train_bwd(const airpose_ief_train_args* a, void* stre
     const float* m2 = a->mask2 ? a->mask2 + (size_t)it * R * kH : nullptr;
     const float* gd = s.g_state;                                   // state_new = state_old + d  =>  dL/dd = dL/dstate_new
     // decoders: g_wdec += gd^T h2, g_bdec += colsum(gd), gh2 = (gd Wdec) * m2
-    if (sgemm(gd, 1, kD, h2, kH, 1, s.g_wdec, kH, kD, kH, R, beta, st)) return 1;
+    if (sgemm(gd, 1, kD, h2, kH, 1, s.g_wdec, kH, kD, kH, R, beta, st, s.splitk)) return 1;
     colsum_kernel<<<ceil_div(kD, 128), 128, 0, st>>>(gd, R, kD, s.g_bdec, beta);
     AP_LAUNCH_CHECK();
-    if (sgemm(gd, kD, 1, s.wdec, kH, 1, s.gh2, kH, R, kH, kD, 0.f, st)) return 1;
+    if (sgemm(gd, kD, 1, s.wdec, kH, 1, s.gh2, kH, R, kH, kD, 0.f, st, s.splitk)) return 1;
     mul_mask_kernel<<<blocks((int64_t)R * kH), 256, 0, st>>>(s.gh2, m2, R * kH);
     AP_LAUNCH_CHECK();
     // fc2
-    if (sgemm(s.gh2, 1, kH, h1, kH, 1, a->g_fc2_w, kH, kH, kH, R, beta, st)) return 1;
+    if (sgemm(s.gh2, 1, kH, h1, kH, 1, a->g_fc2_w, kH, kH, kH, R, beta, st, s.splitk)) return 1;
     colsum_kernel<<<ceil_div(kH, 128), 128, 0, st>>>(s.gh2, R, kH, a->g_fc2_b, beta);
     AP_LAUNCH_CHECK();
-    if (sgemm(s.gh2, kH, 1, a->fc2_w, kH, 1, s.gh1, kH, R, kH, kH, 0.f, st)) return 1;
+    if (sgemm(s.gh2, kH, 1, a->fc2_w, kH, 1, s.gh1, kH, R, kH, kH, 0.f, st, s.splitk)) return 1;
     mul_mask_kernel<<<blocks((int64_t)R * kH), 256, 0, st>>>(s.gh1, m1, R * kH);
     AP_LAUNCH_CHECK();
     // fc1
-    if (sgemm(s.gh1, 1, kH, z, kZ, 1, a->g_fc1_w, kZ, kH, kZ, R, beta, st)) return 1;
+    if (sgemm(s.gh1, 1, kH, z, kZ, 1, a->g_fc1_w, kZ, kH, kZ, R, beta, st, s.splitk)) return 1;
     colsum_kernel<<<ceil_div(kH, 128), 128, 0, st>>>(s.gh1, R, kH, a->g_fc1_b, beta);
     AP_LAUNCH_CHECK();
-    if (sgemm(s.gh1, kH, 1, a->fc1_w, kZ, 1, s.gz, kZ, R, kZ, kH, 0.f, st)) return 1;
+    if (sgemm(s.gh1, kH, 1, a->fc1_w, kZ, 1, s.gz, kZ, R, kZ, kH, 0.f, st, s.splitk)) return 1;
     if (a->g_xf0) {
       copy_gxf_kernel<<<blocks((int64_t)R * kF), 256, 0, st>>>(B, s.gz, a->g_xf0, a->g_xf1, beta);
       AP_LAUNCH_CHECK();

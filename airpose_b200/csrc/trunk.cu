@@ -752,17 +752,28 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
     uint4 vy = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
     if (y) vy = __ldg(reinterpret_cast<const uint4*>(y) + i);
     const uint32_t ud[4] = {vd.x, vd.y, vd.z, vd.w}, uz[4] = {vz.x, vz.y, vz.z, vz.w}, uy[4] = {vy.x, vy.y, vy.z, vy.w};
+    // per-channel constants as 16-byte loads (five tables x 8 channels)
+    float mean[8], istd[8], c1[8], c2[8], c3[8];
+    {
+      const float* tabs[5] = {stats + cg * 8, stats + C + cg * 8, coef + cg * 8, coef + 2048 + cg * 8, coef + 4096 + cg * 8};
+      float* dsts[5] = {mean, istd, c1, c2, c3};
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(tabs[k])), b = __ldg(reinterpret_cast<const float4*>(tabs[k]) + 1);
+        dsts[k][0] = a.x; dsts[k][1] = a.y; dsts[k][2] = a.z; dsts[k][3] = a.w;
+        dsts[k][4] = b.x; dsts[k][5] = b.y; dsts[k][6] = b.z; dsts[k][7] = b.w;
+      }
+    }
     __align__(16) __nv_bfloat16 o[8], p[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = cg * 8 + j;
       const uint32_t wd = ud[j >> 1], wz = uz[j >> 1], wy = uy[j >> 1];
       const float dv = (j & 1) ? __uint_as_float(wd & 0xFFFF0000u) : __uint_as_float(wd << 16);
       const float zv = (j & 1) ? __uint_as_float(wz & 0xFFFF0000u) : __uint_as_float(wz << 16);
       const float yv = (j & 1) ? __uint_as_float(wy & 0xFFFF0000u) : __uint_as_float(wy << 16);
       const float dp = yv > 0.f ? dv : 0.f;
-      const float xh = (zv - stats[c]) * stats[C + c];
-      o[j] = __float2bfloat16_rn(coef[c] * (dp - coef[2048 + c] - xh * coef[4096 + c]));
+      const float xh = (zv - mean[j]) * istd[j];
+      o[j] = __float2bfloat16_rn(c1[j] * (dp - c2[j] - xh * c3[j]));
       p[j] = __float2bfloat16_rn(dp);
     }
     reinterpret_cast<uint4*>(dz)[i] = *reinterpret_cast<const uint4*>(o);
@@ -770,45 +781,72 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
   }
 }
 
-// out[c][m] = in[m][c]   (bf16, 32 x 32 tiles through shared memory)
-__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int64_t M, int C, __nv_bfloat16* __restrict__ out) {
-  __shared__ __nv_bfloat16 tile[32][33];
-  const int64_t m0 = (int64_t)blockIdx.x * 32;
-  const int c0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int64_t m = m0 + r; const int c = c0 + threadIdx.x;
-    tile[r][threadIdx.x] = (m < M && c < C) ? in[m * C + c] : __float2bfloat16_rn(0.f);
+// K-major operands of the weight-gradient GEMMs.  One kernel, two sources:
+//   kIm2col = false   out[c][m]        = in[m][c]                                      (a plain transpose)
+//   kIm2col = true    out[(tap, c)][m] = x[n, ho*s + r - pad, wo*s + sx - pad, c]      (zero outside; tap = blockIdx.z)
+// bf16, 64 pixels x 64 channels per CTA through shared memory: 16-byte loads along the channels, 16-byte stores along the
+// pixels (128 contiguous bytes per 8 lanes on both sides).  ld = row pitch of out (a multiple of 8, >= M).
+template <bool kIm2col>
+__global__ void __launch_bounds__(256) transpose64_kernel(const __nv_bfloat16* __restrict__ in, int64_t M, int C, __nv_bfloat16* __restrict__ out,
+                                                          int64_t ld, int H, int W, int k, int stride, int pad, int Ho, int Wo) {
+  __shared__ __align__(16) uint32_t tileT[64][33];          // [channel][pixel pair] (+1 word: conflict-free 4-byte reads below)
+  const int64_t m0 = (int64_t)blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
+  const int tap = kIm2col ? blockIdx.z : 0;
+  const int t = threadIdx.x;
+  {
+    const int cg = t & 7;
+    __nv_bfloat16* tp = reinterpret_cast<__nv_bfloat16*>(&tileT[0][0]);
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int ml = (t >> 3) + rr * 32;
+      const int64_t m = m0 + ml;
+      const int c = c0 + cg * 8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (m < M && c < C) {
+        if (!kIm2col) {
+          v = __ldg(reinterpret_cast<const uint4*>(in + m * C + c));
+        } else {
+          const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), img = (int)(m / ((int64_t)Wo * Ho));
+          const int h = ho * stride + tap / k - pad, w = wo * stride + tap % k - pad;
+          if (h >= 0 && h < H && w >= 0 && w < W) v = __ldg(reinterpret_cast<const uint4*>(in + (((int64_t)img * H + h) * W + w) * C + c));
+        }
+      }
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        tp[(cg * 8 + j) * 66 + ml] = __ushort_as_bfloat16((unsigned short)((j & 1) ? (u[j >> 1] >> 16) : (u[j >> 1] & 0xFFFFu)));
+    }
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    const int c = c0 + r; const int64_t m = m0 + threadIdx.x;
-    if (c < C && m < M) out[(int64_t)c * M + m] = tile[threadIdx.x][r];
+  {
+    const int mg = t & 7;
+    const int64_t m = m0 + mg * 8;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int cl = (t >> 3) + rr * 32;
+      const int c = c0 + cl;
+      if (c >= C || m >= M) continue;
+      __nv_bfloat16* dst = out + ((int64_t)tap * C + c) * ld + m;
+      const uint4 v = make_uint4(tileT[cl][mg * 4], tileT[cl][mg * 4 + 1], tileT[cl][mg * 4 + 2], tileT[cl][mg * 4 + 3]);
+      if (m + 8 <= M) {
+        *reinterpret_cast<uint4*>(dst) = v;
+      } else {
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        for (int j = 0; j < (int)(M - m); ++j)
+          dst[j] = __ushort_as_bfloat16((unsigned short)((j & 1) ? (u[j >> 1] >> 16) : (u[j >> 1] & 0xFFFFu)));
+      }
+    }
   }
 }
 
-// out[(tap, c)][m] = x[n, ho*s + r - pad, wo*s + sx - pad, c]  (zero outside): transposed im2col, K-major in the pixel index m
-__global__ void im2colT_kernel(const __nv_bfloat16* __restrict__ x, int n, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
-                               __nv_bfloat16* __restrict__ out) {
-  __shared__ __nv_bfloat16 tile[32][33];
+static void launch_transpose(const __nv_bfloat16* in, int64_t M, int C, __nv_bfloat16* out, int64_t ld, cudaStream_t st) {
+  transpose64_kernel<false><<<dim3((unsigned)ceil_div64(M, 64), ceil_div(C, 64)), 256, 0, st>>>(in, M, C, out, ld, 0, 0, 1, 1, 0, 1, 1);
+}
+static void launch_im2colT(const __nv_bfloat16* x, int n, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                           __nv_bfloat16* out, int64_t ld, cudaStream_t st) {
   const int64_t M = (int64_t)n * Ho * Wo;
-  const int64_t m0 = (int64_t)blockIdx.x * 32;
-  const int c0 = blockIdx.y * 32;
-  const int tap = blockIdx.z, r = tap / k, sx = tap % k;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int64_t m = m0 + i; const int c = c0 + threadIdx.x;
-    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
-    if (m < M && c < C) {
-      const int wo = (int)(m % Wo), ho = (int)((m / Wo) % Ho), img = (int)(m / ((int64_t)Wo * Ho));
-      const int h = ho * stride + r - pad, w = wo * stride + sx - pad;
-      if (h >= 0 && h < H && w >= 0 && w < W) v = x[(((int64_t)img * H + h) * W + w) * C + c];
-    }
-    tile[i][threadIdx.x] = v;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i; const int64_t m = m0 + threadIdx.x;
-    if (c < C && m < M) out[((int64_t)tap * C + c) * M + m] = tile[threadIdx.x][i];
-  }
+  transpose64_kernel<true><<<dim3((unsigned)ceil_div64(M, 64), ceil_div(C, 64), k * k), 256, 0, st>>>(x, M, C, out, ld, H, W, k, stride, pad, Ho, Wo);
 }
 
 // stem: out[(r*7+s)*3 + c][m] = x_nchw[n, c, 2p - 3 + r, 2q - 3 + s]  (147 rows; rows 147..191 are zero)
@@ -861,30 +899,56 @@ __global__ void wgrad_unpack_kernel(const __nv_bfloat16* __restrict__ D, int cou
   }
 }
 
-// MaxPool2d(3, 2, 1) backward on NHWC bf16: every input pixel collects the gradient of the windows whose (first) maximum it is
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy, int n, __nv_bfloat16* __restrict__ gx) {
-  const int64_t total = (int64_t)n * 112 * 112 * 64;
+// MaxPool2d(3, 2, 1) backward on NHWC bf16: every input pixel collects the gradient of the windows whose (first, in scan
+// order -- PyTorch's tie rule) maximum it is.  Gather form, 8 channels (one 16-byte load) per thread.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy, int n,
+                                                          __nv_bfloat16* __restrict__ gx) {
+  const int64_t total = (int64_t)n * 112 * 112 * 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % 64);
-    const int64_t pix = i / 64;
+    const int cg = (int)(i % 8);
+    const int64_t pix = i / 8;
     const int w = (int)(pix % 112), h = (int)((pix / 112) % 112), img = (int)(pix / (112 * 112));
-    const float xv = __bfloat162float(x[i]);
-    float g = 0.f;
-    // windows (pr, q) that contain (h, w): pr*2-1 <= h <= pr*2+1
-    for (int pr = max(0, (h - 1 + 1) / 2); pr <= min(55, (h + 1) / 2); ++pr)
-      for (int q = max(0, (w - 1 + 1) / 2); q <= min(55, (w + 1) / 2); ++q) {
-        // is (h, w) the first maximum of this window in scan order?
-        bool is_max = true;
-        for (int r = 0; r < 3 && is_max; ++r)
+    float xv[8], g[8];
+    {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + pix * 64 + cg * 8));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { xv[2 * j] = __uint_as_float(u[j] << 16); xv[2 * j + 1] = __uint_as_float(u[j] & 0xFFFF0000u); }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    }
+    // windows (pr, q) that contain (h, w): 2 pr - 1 <= h <= 2 pr + 1
+    for (int pr = h / 2; pr <= min(55, (h + 1) / 2); ++pr)
+      for (int q = w / 2; q <= min(55, (w + 1) / 2); ++q) {
+        unsigned is_max = 0xFFu;                     // bit j: (h, w) is still the first maximum of this window in channel j
+        for (int r = 0; r < 3; ++r) {
+          const int hh = pr * 2 - 1 + r;
+          if (hh < 0 || hh >= 112) continue;
           for (int s = 0; s < 3; ++s) {
-            const int hh = pr * 2 - 1 + r, ww = q * 2 - 1 + s;
-            if (hh < 0 || hh >= 112 || ww < 0 || ww >= 112) continue;
-            const float o = __bfloat162float(x[(((int64_t)img * 112 + hh) * 112 + ww) * 64 + c]);
-            if (o > xv || (o == xv && (hh < h || (hh == h && ww < w)))) { is_max = false; break; }
+            const int ww = q * 2 - 1 + s;
+            if (ww < 0 || ww >= 112 || (hh == h && ww == w)) continue;
+            const bool earlier = hh < h || (hh == h && ww < w);
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)img * 112 + hh) * 112 + ww) * 64 + cg * 8));
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float o = (j & 1) ? __uint_as_float(u[j >> 1] & 0xFFFF0000u) : __uint_as_float(u[j >> 1] << 16);
+              if (o > xv[j] || (earlier && o == xv[j])) is_max &= ~(1u << j);
+            }
           }
-        if (is_max) g += __bfloat162float(gy[(((int64_t)img * 56 + pr) * 56 + q) * 64 + c]);
+        }
+        if (is_max) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(gy + (((int64_t)img * 56 + pr) * 56 + q) * 64 + cg * 8));
+          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (is_max & (1u << j)) g[j] += (j & 1) ? __uint_as_float(u[j >> 1] & 0xFFFF0000u) : __uint_as_float(u[j >> 1] << 16);
+        }
       }
-    gx[i] = __float2bfloat16_rn(g);
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(g[j]);
+    *reinterpret_cast<uint4*>(gx + pix * 64 + cg * 8) = *reinterpret_cast<const uint4*>(o);
   }
 }
 
@@ -995,8 +1059,8 @@ static int bw_reserve(airpose_net* h, int n) {
   cudaFree(h->bw_t0); cudaFree(h->bw_t1); cudaFree(h->bw_w); cudaFree(h->bw_coef);
   const size_t act = (size_t)n * 112 * 112 * 64;                 // the largest activation (== 56*56*256)
   for (auto& p : h->bw) AP_CHECK_CUDA(cudaMalloc((void**)&p, act * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_t0, act * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_t1, std::max((size_t)576 * 3136, (size_t)192 * 12544) * n * 2));
+  AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_t0, (act + 8 * 2048) * 2));                       // + the pitch padding of conv_wgrad
+  AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_t1, (std::max((size_t)576 * 3136, (size_t)192 * 12544) * n + 8 * 4608) * 2));
   AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_w, (size_t)512 * 4608 * 2 * 2));
   AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_coef, 3 * 2048 * sizeof(float)));
   if (!h->bn_part) AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_part, (size_t)kBnSlabs * 2048 * 2 * sizeof(float)));
@@ -1029,18 +1093,16 @@ static int conv_wgrad(airpose_net* h, int i, const __nv_bfloat16* dz, const __nv
   const ConvSpec& s = h->specs[i];
   const int64_t M = (int64_t)n * Hout * Hout;
   const int Kdim = s.k * s.k * s.cin;
-  dim3 tb(32, 8);
-  transpose_bf16_kernel<<<dim3((unsigned)ceil_div64(M, 32), ceil_div(s.cout, 32)), tb, 0, st>>>(dz, M, s.cout, h->bw_t0);
+  // K-major operands [channels][pixels]: the row pitch is rounded up to 8 elements (16-byte TMA pitch) so that any image
+  // count works (196 and 49 pixels per image are not multiples of 8); the GEMM's K extent stays M, the pad is never read
+  const int64_t ld = (M + 7) & ~(int64_t)7;
+  launch_transpose(dz, M, s.cout, h->bw_t0, ld, st);
   AP_LAUNCH_CHECK();
-  if (s.k == 1 && s.stride == 1) {
-    transpose_bf16_kernel<<<dim3((unsigned)ceil_div64(M, 32), ceil_div(s.cin, 32)), tb, 0, st>>>(x_in, M, s.cin, h->bw_t1);
-  } else {
-    im2colT_kernel<<<dim3((unsigned)ceil_div64(M, 32), ceil_div(s.cin, 32), s.k * s.k), tb, 0, st>>>(x_in, n, Hin, Hin, s.cin, s.k, s.stride,
-                                                                                                   s.pad, Hout, Hout, h->bw_t1);
-  }
+  if (s.k == 1 && s.stride == 1) launch_transpose(x_in, M, s.cin, h->bw_t1, ld, st);
+  else launch_im2colT(x_in, n, Hin, Hin, s.cin, s.k, s.stride, s.pad, Hout, Hout, h->bw_t1, ld, st);
   AP_LAUNCH_CHECK();
   airpose_gemm_args ga{};
-  ga.A = h->bw_t0; ga.lda = M; ga.B = h->bw_t1; ga.ldb = M;
+  ga.A = h->bw_t0; ga.lda = ld; ga.B = h->bw_t1; ga.ldb = ld;
   ga.M = s.cout; ga.N = Kdim; ga.K = (int)M;
   ga.out_bf16 = h->bw_w; ga.ldd = Kdim;
   if (airpose_gemm_bf16(&ga, st)) return 1;
@@ -1096,7 +1158,6 @@ extern "C" int airpose_backbone_bwd_train(airpose_net_t* h, const float* x, int 
   AP_REQUIRE(t == 0 || t == 1, "airpose_backbone_bwd_train: tape must be 0 or 1");
   const airpose_net::Tape& tp = h->tape[t];
   AP_REQUIRE(tp.n == n && n > 0, "airpose_backbone_bwd_train: tape %d holds a forward of %d images, not %d", t, tp.n, n);
-  AP_REQUIRE(n % 8 == 0, "airpose_backbone_bwd_train: n=%d must be a multiple of 8 (16-byte row pitch of the transposed operands)", n);
   for (size_t i = 0; i < h->specs.size(); ++i)
     AP_REQUIRE(g->g_weight[i] && g->g_bn_weight[i] && g->g_bn_bias[i] && conv_weights[i], "airpose_backbone_bwd_train: null buffer (conv %zu)", i);
   cudaStream_t st = (cudaStream_t)stream_;
@@ -1146,13 +1207,12 @@ extern "C" int airpose_backbone_bwd_train(airpose_net_t* h, const float* x, int 
     // G now holds dL/d(block input)
   }
   // stem: max-pool backward, bn1 + ReLU backward, weight gradient of the 7x7 conv (no data gradient: the input is the image)
-  maxpool_bwd_kernel<<<ew_grid((int64_t)n * 112 * 112 * 64), 256, 0, st>>>(tp.y[0], G, n, G2);
+  maxpool_bwd_kernel<<<ew_grid((int64_t)n * 112 * 112 * 8), 256, 0, st>>>(tp.y[0], G, n, G2);
   AP_LAUNCH_CHECK();
   const int64_t M0 = (int64_t)n * 112 * 112;
   if (bn_bwd(h, tp, 0, M0, bn, g, G2, true, DZ, nullptr, st)) return 1;
   {
-    dim3 tb(32, 8);
-    transpose_bf16_kernel<<<dim3((unsigned)ceil_div64(M0, 32), 2), tb, 0, st>>>(DZ, M0, 64, h->bw_t0);
+    launch_transpose(DZ, M0, 64, h->bw_t0, M0, st);
     AP_LAUNCH_CHECK();
     stem_im2colT_kernel<<<dim3(148 * 4, 192), 256, 0, st>>>(x, n, h->bw_t1);
     AP_LAUNCH_CHECK();
@@ -1171,7 +1231,7 @@ extern "C" int airpose_backbone_bwd_train(airpose_net_t* h, const float* x, int 
 extern "C" int airpose_debug_conv_bwd(airpose_net_t* h, int conv_idx, int n, const void* dz, const void* x_in, const float* w_f32,
                                       const void* add, void* out_dx, float* out_gw, int accumulate, void* stream_) {
   AP_REQUIRE(h && dz && x_in && w_f32 && out_gw, "airpose_debug_conv_bwd: null argument");
-  AP_REQUIRE(conv_idx >= 1 && conv_idx < (int)h->specs.size() && n > 0 && n % 8 == 0, "airpose_debug_conv_bwd: bad index / n");
+  AP_REQUIRE(conv_idx >= 1 && conv_idx < (int)h->specs.size() && n > 0, "airpose_debug_conv_bwd: bad index / n");
   cudaStream_t st = (cudaStream_t)stream_;
   if (bw_reserve(h, n)) return 1;
   const std::vector<ConvIO> io = resnet50_io();

@@ -125,9 +125,9 @@ class copenet(nn.Module):
         if device.type != "cuda":
             raise _lib.AirposeError("airpose_b200.copenet runs on CUDA only (module is on {}); there is no CPU path".format(device))
         if self.training and not allow_training:
-            raise NotImplementedError("airpose_b200.copenet: the full forward in training mode needs the trunk backward, which "
-                                      "is not built; use .eval(), or copenet_twoview.training_step_reg_only / "
-                                      "forward_feat_ext (batch-statistics BatchNorm) + ief_train_forward")
+            raise NotImplementedError("airpose_b200.copenet: this entry point is eval-mode only (folded BatchNorm, collapsed "
+                                      "regressor); in train() mode call the module itself (forward / autograd), "
+                                      "copenet_twoview.training_step, or forward_feat_ext + ief_train_forward")
         lib = _lib.load()
         if self._handle is None or self._handle_key != device or n_images > self.max_images:
             self._release()
@@ -135,7 +135,7 @@ class copenet(nn.Module):
             h = C.c_void_p()
             with torch.cuda.device(device):
                 _lib.check(lib.airpose_net_create(C.byref(h), cap, device.index or 0), "airpose_net_create")
-            self._handle, self._handle_key, self.max_images, self._loaded_key = h, device, cap, None
+            self._handle, self._handle_key, self.max_images, self._loaded_key, self._packed_conv_key = h, device, cap, None, None
         # (data_ptr, version, generation): the generation is bumped by airpose_b200.optim.Adam, whose kernel updates the
         # parameters through raw pointers and therefore behind torch's version counters.  The trunk (packed conv weights,
         # folded BN) and the regressor (collapsed matrix G) are tracked separately, and G is re-formed only when an
@@ -146,6 +146,12 @@ class copenet(nn.Module):
         trunk_key = tuple(stamp(t) for t in ts[:n_trunk])
         reg_key = tuple(stamp(t) for t in ts[n_trunk:])
         loaded = self._loaded_key or (None, None)
+        if allow_training and not need_regressor:
+            # training-mode trunk calls use only the packed conv weights (BatchNorm works from batch statistics), and each of
+            # them bumps the running statistics: do not re-pack 53 convs and re-fold 53 BatchNorms for that
+            conv_key = trunk_key[0::5]
+            if conv_key == getattr(self, "_packed_conv_key", None) and loaded[0] is not None:
+                return lib, self._handle
         if trunk_key != loaded[0] or (need_regressor and reg_key != loaded[1]):
             for t in ts:
                 if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
@@ -163,6 +169,7 @@ class copenet(nn.Module):
                 else:
                     self._load_native(lib)                         # packs the convs, folds BN and forms G
                     self._loaded_key = (trunk_key, reg_key)
+            self._packed_conv_key = trunk_key[0::5]
         return lib, self._handle
 
     def _fill_common(self, p):
@@ -251,11 +258,11 @@ class copenet(nn.Module):
                 m.running_mean._airpose_gen = getattr(m.running_mean, "_airpose_gen", 0) + 1
         return out
 
-    def backward_feat_ext(self, x, tape, g_feat, accumulate=False, into_param_grads=False):
+    def backward_feat_ext(self, x, tape, g_feat, accumulate=False, into_param_grads=False, grads=None):
         """Backward of the training-mode ``forward_feat_ext`` call recorded on ``tape``: gradients of the 53 conv weights
         and of every BatchNorm weight / bias, given d loss / d features ``g_feat`` [n,2048] and the same images ``x``.
-        Returns a dict keyed like ``state_dict``; ``into_param_grads`` writes into the parameters' ``.grad`` instead
-        (``accumulate`` adds: the second view of a pair)."""
+        Returns a dict keyed like ``state_dict``; ``into_param_grads`` writes into the parameters' ``.grad`` instead,
+        ``grads`` (a dict from an earlier call) into those buffers (``accumulate`` adds: the second view of a pair)."""
         device = self.conv1.weight.device
         lib, h = self._ensure(0, device, allow_training=True, need_regressor=False)
         x = x.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -271,6 +278,8 @@ class copenet(nn.Module):
                     if p.grad is None:
                         p.grad = torch.zeros_like(p)
                     bufs.append(p.grad)
+                elif grads is not None:
+                    bufs.append(grads[names[id(p)]])
                 else:
                     bufs.append(torch.zeros_like(p) if accumulate else torch.empty_like(p))
                 out[names[id(p)]] = bufs[-1]
@@ -443,9 +452,69 @@ class copenet(nn.Module):
         """model_copenet.py:112-159.  Both views go through the trunk in one call (eval-mode
         BatchNorm makes images independent); the regressor keeps the two views of a pair together."""
         B = x0.shape[0]
+        if self.training:
+            # train() mode, as Lightning leaves the module inside training_step (copenet_twoview.py:376-386): batch-statistics
+            # BatchNorm, dropout, and -- under grad mode -- outputs connected to the parameters through ONE autograd node
+            if any(t is not None for t in (init_theta0, init_theta1, init_shape0, init_shape1)):
+                raise NotImplementedError("airpose_b200.copenet: init_theta / init_shape in train() mode are not built "
+                                          "(the reference's training step passes only init_position, copenet_twoview.py:205-211)")
+            params = [p for p in self.parameters()]
+            return _TwoViewTrainFn.apply(self, x0, x1, bb0, bb1, init_position0, init_position1, int(iters), *params)
         xf = self.forward_feat_ext_pair(x0, x1)
         return self._ief(xf[:B], xf[B:], bb0, bb1, init_position0, init_position1, init_theta0, init_theta1,
                          init_shape0, init_shape1, iters)
+
+
+class _TwoViewTrainFn(torch.autograd.Function):
+    """``copenet.forward`` in train() mode as one autograd node, so that the reference's ``loss.backward()``
+    (copenet_twoview.py:378-386) runs the native backward: forward = trunk per view on the two training tapes
+    (``airpose_backbone_fwd_train``) + regressor with dropout (``airpose_ief_train_fwd``); backward = regressor backward
+    (``airpose_ief_train_bwd``) + trunk backward per view (``airpose_backbone_bwd_train``).  The parameters are inputs of the
+    node, so autograd accumulates the returned gradients into ``p.grad`` exactly as it does for the reference module
+    (``deccam`` gets none: it is unused by the two-view model, model_copenet.py:73).  The handle holds ONE pair of tapes:
+    a second train-mode forward before ``backward()`` invalidates the first (checked, raises)."""
+
+    N_FIXED = 8
+
+    @staticmethod
+    def forward(ctx, net, x0, x1, bb0, bb1, pos0, pos1, iters, *params):
+        device = net.conv1.weight.device
+        f = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        for x in (x0, x1):
+            if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
+                raise ValueError("copenet.forward expects [B,3,224,224] images, got {}".format(tuple(x.shape)))
+        x0, x1 = f(x0), f(x1)
+        with torch.no_grad():
+            xf0 = net._forward_feat_ext_train(x0, tape=0)
+            xf1 = net._forward_feat_ext_train(x1, tape=1)
+            # the caller rescales its init translations in place after the call (copenet_twoview.py:214-218): keep copies
+            pred, ictx = net.ief_train_forward(xf0, xf1, bb0.detach().clone(), bb1.detach().clone(), pos0.detach().clone(),
+                                               pos1.detach().clone(), iters=iters)
+        net._tape_generation = getattr(net, "_tape_generation", 0) + 1
+        ctx.net, ctx.ictx, ctx.images, ctx.generation = net, ictx, (x0, x1), net._tape_generation
+        ctx.param_names = [n for n, _ in net.named_parameters()]
+        assert len(ctx.param_names) == len(params)
+        return pred
+
+    @staticmethod
+    def backward(ctx, g_pose0, g_betas0, g_pose1, g_betas1):
+        net, ictx = ctx.net, ctx.ictx
+        if getattr(net, "_tape_generation", 0) != ctx.generation:
+            raise RuntimeError("airpose_b200.copenet: the training tapes of this forward were overwritten by a later train-mode "
+                               "forward; call backward() before the next forward (one outstanding graph per module)")
+        B = ictx["B"]
+        dev = ictx["xf0"].device
+        z = lambda g, w: g if g is not None else torch.zeros(B, w, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            gr = net.ief_train_backward(ictx, z(g_pose0, 135), z(g_betas0, 10), z(g_pose1, 135), z(g_betas1, 10),
+                                        want_feature_grads=True)
+            tg = net.backward_feat_ext(ctx.images[0], 0, gr["xf0"], accumulate=False)
+            net.backward_feat_ext(ctx.images[1], 1, gr["xf1"], accumulate=True, grads=tg)
+        gr.update(tg)
+        out = [None] * _TwoViewTrainFn.N_FIXED
+        for i, n in enumerate(ctx.param_names):
+            out.append(gr.get(n) if ctx.needs_input_grad[_TwoViewTrainFn.N_FIXED + i] else None)
+        return tuple(out)
 
 
 def getcopenet(smpl_mean_params, pretrained=True, **kwargs):

@@ -233,12 +233,45 @@ class SMPLX(nn.Module):
     def forward(self, betas=None, global_orient=None, body_pose=None, left_hand_pose=None, right_hand_pose=None,
                 transl=None, expression=None, jaw_pose=None, leye_pose=None, reye_pose=None, return_verts=True,
                 return_full_pose=False, pose2rot=True, **kwargs):
-        out, _ = self.forward_camera(betas=betas, global_orient=global_orient, body_pose=body_pose,
-                                     left_hand_pose=left_hand_pose, right_hand_pose=right_hand_pose, transl=transl,
-                                     expression=expression, jaw_pose=jaw_pose, leye_pose=leye_pose,
-                                     reye_pose=reye_pose, return_verts=return_verts,
-                                     return_full_pose=return_full_pose, pose2rot=pose2rot)
+        kw = dict(left_hand_pose=left_hand_pose, right_hand_pose=right_hand_pose, expression=expression,
+                  jaw_pose=jaw_pose, leye_pose=leye_pose, reye_pose=reye_pose, return_verts=return_verts,
+                  return_full_pose=return_full_pose, pose2rot=pose2rot)
+        if torch.is_grad_enabled():
+            # the module's own zero ``betas`` Parameter stands in when betas is omitted (body_models.py:875), and it
+            # requires grad like the reference's -- so a call without betas under grad mode is differentiable too
+            diff = [t for t in (betas if betas is not None else getattr(self, "betas", None), body_pose, global_orient, transl)
+                    if t is not None and t.requires_grad]
+            if diff:
+                return self._forward_autograd(betas, global_orient, body_pose, transl, kw)
+        out, _ = self.forward_camera(betas=betas, global_orient=global_orient, body_pose=body_pose, transl=transl, **kw)
         return out
+
+    def _forward_autograd(self, betas, global_orient, body_pose, transl, kw):
+        """``forward`` as ONE autograd node (``_SmplxFn``): what makes ``loss.backward()`` of the reference's training step
+        (copenet_twoview.py:281-317,378-386) run through the native SMPL-X backward.  Only the hot-path call pattern is
+        differentiable: betas / body_pose [B,21,3,3] / global_orient [B,1,3,3] / transl, no expression, jaw, eye or hand poses."""
+        for name in ("left_hand_pose", "right_hand_pose", "expression", "jaw_pose", "leye_pose", "reye_pose"):
+            if kw.get(name) is not None:
+                raise NotImplementedError("airpose_b200.SMPLX: '{}' is not differentiable on the native path (off the AirPose "
+                                          "hot path); call under torch.no_grad() or leave it out".format(name))
+        if body_pose is None:
+            raise NotImplementedError("airpose_b200.SMPLX: the differentiable call needs body_pose [B,21,3,3]")
+        B = body_pose.shape[0]
+        b_in = betas if betas is not None else self.betas
+        if b_in.shape[0] != B:
+            b_in = b_in.expand(B, -1)
+        tr_in = transl if transl is not None else getattr(self, "transl", None)
+        vertices, joints = _SmplxFn.apply(self, b_in, body_pose, global_orient, tr_in)
+        full_pose = None
+        if kw.get("return_full_pose"):
+            eye = torch.eye(3, device=vertices.device, dtype=torch.float32).expand(B, 1, 3, 3)
+            full_pose = torch.cat([global_orient.reshape(B, 1, 3, 3) if global_orient is not None else eye,
+                                   body_pose.reshape(B, 21, 3, 3), eye.expand(B, 33, 3, 3)], dim=1)
+        return ModelOutput(vertices=vertices if kw.get("return_verts", True) else None, joints=joints,
+                           betas=betas if betas is not None else self.betas, expression=getattr(self, "expression", None),
+                           global_orient=getattr(self, "global_orient", None), body_pose=body_pose,
+                           left_hand_pose=getattr(self, "left_hand_pose", None),
+                           right_hand_pose=getattr(self, "right_hand_pose", None), jaw_pose=None, full_pose=full_pose)
 
     def forward_camera(self, betas=None, global_orient=None, body_pose=None, left_hand_pose=None,
                        right_hand_pose=None, transl=None, expression=None, jaw_pose=None, leye_pose=None,
@@ -356,6 +389,37 @@ class SMPLX(nn.Module):
                           right_hand_pose=getattr(self, "right_hand_pose", None), jaw_pose=jaw_pose,
                           full_pose=full_pose)
         return out, cam
+
+
+class _SmplxFn(torch.autograd.Function):
+    """``SMPLX.forward(pose2rot=False)`` -> (vertices, joints) as one autograd node: forward = ``airpose_smplx_fwd``,
+    backward = ``airpose_smplx_bwd`` (gradients w.r.t. betas, body_pose, global_orient; transl is additive, so its gradient
+    is the sum of the upstream gradients over vertices and joints, lbs.py:219 / body_models.py:976-978)."""
+
+    @staticmethod
+    def forward(ctx, module, betas, body_pose, global_orient, transl):
+        with torch.no_grad():
+            out, _ = module.forward_camera(betas=betas, global_orient=global_orient, body_pose=body_pose, transl=transl,
+                                           pose2rot=False)
+        ctx.module = module
+        ctx.has = (global_orient is not None, transl is not None)
+        ctx.shapes = (tuple(betas.shape), tuple(body_pose.shape), None if global_orient is None else tuple(global_orient.shape))
+        ctx.save_for_backward(betas.detach(), body_pose.detach(), None if global_orient is None else global_orient.detach())
+        return out.vertices, out.joints
+
+    @staticmethod
+    def backward(ctx, g_vertices, g_joints):
+        betas, body_pose, global_orient = ctx.saved_tensors
+        g = smplx_backward(ctx.module, betas, body_pose, global_orient, grad_vertices=g_vertices, grad_joints=g_joints)
+        sb, sp, so = ctx.shapes
+        g_transl = None
+        if ctx.has[1] and ctx.needs_input_grad[4]:
+            g_transl = 0
+            for t in (g_vertices, g_joints):
+                if t is not None:
+                    g_transl = g_transl + t.sum(dim=1)
+        return (None, g["betas"].reshape(sb), g["body_pose"].reshape(sp),
+                g["global_orient"].reshape(so) if ctx.has[0] else None, g_transl)
 
 
 def smplx_backward(module, betas, body_pose, global_orient=None, grad_vertices=None, grad_joints=None,

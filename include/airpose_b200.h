@@ -216,7 +216,7 @@ int airpose_backbone_fwd_train(airpose_net_t* h, const float* x_nchw, int n_imag
 /* Backward of airpose_backbone_fwd_train for one view (tape 0 / 1): d loss / d features [n,2048] -> gradients of every
  * conv weight (reference layout [Cout,Cin,kh,kw]) and BatchNorm weight / bias, fp32.  accumulate = 0 overwrites the
  * output buffers, 1 adds (the second view of a pair: the two views share the weights).  x_nchw: the images of that
- * forward call (the stem's weight gradient needs them).  n must be a multiple of 8.
+ * forward call (the stem's weight gradient needs them).  Any n (the reference trains with 30 pairs per rank).
  * bf16 tensor-core GEMMs throughout: data gradients as implicit-GEMM convolutions of dz with the flipped, transposed
  * weights (stride-2 layers through a zero-dilated dz), weight gradients as [Cout, K] = dz^T . im2col(x) with both operands
  * transposed to K-major and the long pixel contraction split stream-K over all SMs; BatchNorm backward as two HBM-bound
