@@ -291,3 +291,39 @@ def make_lbs_inputs(batch: int, seed: int = 7, pose_scale: float = 0.35) -> dict
     six = six + rng.standard_normal(size=(batch, 21, 6)).astype(np.float32) * pose_scale
     body = rot6d_to_rotmat_np(six.reshape(-1, 6)).reshape(batch, 21, 3, 3)
     return {"betas": betas, "body_pose": body}
+
+
+# --------------------------------------------------------------------------------------
+# Camera frames and drone-server messages
+# --------------------------------------------------------------------------------------
+def camera_frame(height: int, width: int, seed: int) -> np.ndarray:
+    """A seeded u8 BGR frame [H,W,3] as cv2.imread would return it: low-frequency structure plus pixel noise, so that a
+    bilinear resize is sensitive to both the sample positions and the weights."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width].astype(np.float64)
+    img = np.empty((height, width, 3), np.float64)
+    for c in range(3):
+        fy, fx, ph = rng.uniform(0.01, 0.08), rng.uniform(0.01, 0.08), rng.uniform(0, 6.28)
+        img[:, :, c] = 127.5 + 80.0 * np.sin(fy * y + fx * x + ph) + rng.normal(0, 25.0, size=(height, width))
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def server_messages(seed: int, frames: int, init_pose: np.ndarray, init_shape: np.ndarray):
+    """Seeded messages in the drone server's wire format (airpose_server/server.py:38-39,91-98,110,125;
+    airpose_client/AirPoseClient.h:20-31), ``frames`` x (stage 0, stage 1, stage 2):
+      stage 0:   u8 stage | 3 x f32 bb (cx/c_x-1, cy/c_y-1, scale) | 224*224*3 u8 BGR
+      stage 1/2: u8 stage | 10 x f32 betas | 126 x f32 articulated 6D pose   (the OTHER drone's previous reply)
+    Returns [(stage, bytes), ...]."""
+    rng = np.random.default_rng(seed)
+    init_pose = np.asarray(init_pose, np.float32).reshape(-1)
+    init_shape = np.asarray(init_shape, np.float32).reshape(-1)
+    msgs = []
+    for f in range(frames):
+        bb = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(0.1, 2.0)], np.float32)
+        img = camera_frame(224, 224, seed * 1000 + f)
+        msgs.append((0, bytes([0]) + bb.tobytes() + img.tobytes()))
+        for stage in (1, 2):
+            betas = (init_shape + rng.normal(0, 0.3, size=10)).astype(np.float32)
+            art = (init_pose[6:22 * 6] + rng.normal(0, 0.1, size=126)).astype(np.float32)
+            msgs.append((stage, bytes([stage]) + betas.tobytes() + art.tobytes()))
+    return msgs

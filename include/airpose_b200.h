@@ -151,6 +151,24 @@ int airpose_j14_gather(const float* joints, int32_t batch, int32_t num_joints, c
                        float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Input preprocessing (the step right before the path)
+ * ---------------------------------------------------------------------------------- */
+/* The drone server's stage-0 conversion (catkin_ws/.../airpose_server/server.py:93-98): u8 BGR [n,size,size,3] (device) ->
+ * fp32 RGB NCHW, x * (1/255) then (x - mean[c]) / std[c] as three separately rounded fp32 operations (bit-exact with the
+ * reference's torch ops).  mean3 / std3 are HOST pointers to three floats each. */
+int airpose_preprocess_bgr8(const uint8_t* bgr_hwc, int32_t n_images, int32_t size, const float* mean3, const float* std3,
+                            float* out_nchw, void* stream);
+/* The dataset's per-camera preprocessing (copenet/src/copenet/dsets/aerialpeople.py:125-141,174; utils/utils.py:214-235):
+ * frame[y0:y1, x0:x1] of a u8 BGR frame -> RGB / 255 -> cv2.resize(INTER_LINEAR) to a longer side of `size` -> zero
+ * letterbox to size x size -> Normalize(mean, std) -> fp32 NCHW.  frames_bgr: n frames of frame_h x frame_w x 3 bytes on the
+ * device, frame_stride_bytes apart (0: every crop is taken from the same frame);
+ * rects_dev: int32 [n,4] = (y0, y1, x0, x1) on the device.  The bilinear arithmetic follows cv2's CV_64F path (double work
+ * type, float coefficients) so the result agrees with the reference to the final float32 rounding. */
+int airpose_preprocess_crop_resize(const uint8_t* frames_bgr, int64_t frame_stride_bytes, int32_t frame_h, int32_t frame_w,
+                                   const int32_t* rects_dev, int32_t n_images, int32_t size, const float* mean3, const float* std3,
+                                   float* out_nchw, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * ResNet-50 trunk + IEF regressor  (copenet/src/copenet/models/model_copenet.py)
  * ---------------------------------------------------------------------------------- */
 typedef struct airpose_net airpose_net_t;

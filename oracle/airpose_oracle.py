@@ -419,3 +419,120 @@ DEFAULT_LOSS_WEIGHTS = {   # copenet_twoview.py:655-677
     "shape_loss_weight": 50, "keypoint2d_loss_weight": 0.002, "keypoint3d_loss_weight": 1,
     "limbs3d_loss_weight": 3, "limbstheta_loss_weight": 1, "trans_loss_weight": 10,
     "rootrot_loss_weight": 1, "pose_loss_weight": 50, "beta_loss_weight": 1}
+
+
+# --------------------------------------------------------------------------------------
+# input preprocessing and the staged drone-server protocol
+# --------------------------------------------------------------------------------------
+IMAGENET_MEAN = np.array([0.485, 0.456, 0.406], np.float32)      # server.py:75-76, aerialpeople.py (Normalize)
+IMAGENET_STD = np.array([0.229, 0.224, 0.225], np.float32)
+SERVER_SIZE = 224                                                # server.py:37
+SERVER_BUFFERSIZE = 1 + 3 * 4 + SERVER_SIZE * SERVER_SIZE * 3    # server.py:38: u8 stage, 3 x f32 bb, BGR bytes
+SERVER_BUFFERSIZE_STAGES = 1 + (10 + 21 * 6) * 4                 # server.py:39: u8 stage, 136 x f32 (betas | articulated pose)
+
+
+def server_preprocess(data) -> np.ndarray:
+    """Stage-0 image decoding of airpose_server/server.py:91-98: BGR bytes -> RGB -> CHW -> * (1/255) -> (x - mean) / std,
+    each step one float32 operation.  Returns [1,3,224,224] float32."""
+    npimg = np.frombuffer(data, dtype=np.uint8, count=SERVER_SIZE * SERVER_SIZE * 3, offset=1 + 3 * 4)
+    npimg = npimg.reshape(SERVER_SIZE, SERVER_SIZE, 3)[:, :, [2, 1, 0]].transpose(2, 0, 1)
+    frame = npimg[None].astype(np.float32) * np.float32(1.0 / 255)
+    frame = (frame - IMAGENET_MEAN[None, :, None, None]) / IMAGENET_STD[None, :, None, None]
+    return frame.astype(np.float32)
+
+
+def server_forward_reg(sd, xf0, bb0, pos0, ori0, art0, art1, sh0, sh1):
+    """The server model's single-view regressor pass (airpose_server/airpose.py:179-195; eval mode)."""
+    xc0 = np.concatenate([xf0, bb0, pos0, ori0, art0, sh0, art1, sh1], axis=1)
+    xc0 = linear(linear(xc0, sd, "fc1"), sd, "fc2")
+    return (np.concatenate([pos0, ori0, art0], axis=1) + linear(xc0, sd, "decpose")).astype(np.float32), \
+           (sh0 + linear(xc0, sd, "decshape")).astype(np.float32)
+
+
+class ServerState:
+    """The globals of airpose_server/server.py:69-73 (one connection's network state)."""
+
+    def __init__(self, sd):
+        self.xf = np.zeros((1, 2048), np.float32)
+        self.bb = np.zeros((1, 3), np.float32)
+        self.curr_pose = np.array(sd["init_pose"], np.float32).copy()        # [1,144]; replaced by pose[:, 3:] ([1,132]) after a stage
+        self.curr_shape = np.array(sd["init_shape"], np.float32).copy()
+        self.curr_position = np.array([[0, 0, 0.5]], np.float32)
+
+
+def server_process(sd, state: ServerState, data, stage: int, feat_fn=None, bf16=False) -> np.ndarray:
+    """``process(data, metainfo, stage)`` of airpose_server/server.py:78-150: returns the reply as a float32 vector
+    (136 floats for stages 0-1: betas | articulated pose; 145 for stage 2: betas | full pose) and advances ``state``.
+    ``feat_fn(frame) -> [1,2048]`` replaces the oracle trunk (tests feed the device features to isolate the regressor)."""
+    init_pose, init_shape = np.asarray(sd["init_pose"], np.float32), np.asarray(sd["init_shape"], np.float32)
+    if stage == 0:
+        state.bb = np.frombuffer(data, dtype=np.float32, count=3, offset=1)[None].copy()
+        frame = server_preprocess(data)
+        state.xf = feat_fn(frame) if feat_fn is not None else forward_feat_ext(frame, sd, bf16=bf16)
+        pose, shape = server_forward_reg(sd, state.xf, state.bb, np.array([[0, 0, 0.5]], np.float32), init_pose[:, :6],
+                                         init_pose[:, 6:22 * 6], init_pose[:, 6:22 * 6], init_shape, init_shape)
+        reply = np.concatenate([shape[0], pose[0, 9:]])
+    elif stage in (1, 2):
+        shape2 = np.frombuffer(data, dtype=np.float32, count=10, offset=1)[None]
+        art2 = np.frombuffer(data, dtype=np.float32, count=126, offset=41)[None]
+        pose, shape = server_forward_reg(sd, state.xf, state.bb, state.curr_position, state.curr_pose[:, :6],
+                                         state.curr_pose[:, 6:22 * 6], art2, state.curr_shape, shape2)
+        reply = np.concatenate([shape[0], pose[0, 9:] if stage == 1 else pose[0]])
+    else:
+        raise ValueError("Invalid stage number {}".format(stage))            # server.py:141-142 prints; nothing to reply
+    state.curr_position, state.curr_pose, state.curr_shape = pose[:, :3], pose[:, 3:], shape     # server.py:144-146
+    return reply.astype(np.float32)
+
+
+def _cv_linear_coef(dst_size: int, src_size: int):
+    """Source index and weight per destination index of cv2.resize(INTER_LINEAR) on a CV_64F image (OpenCV imgproc/resize.cpp):
+    scale = 1 / (dst / src); f = (d + 0.5) * scale - 0.5; s = floor(f); f -= s; clamped at both ends (s < 0 -> s = 0, f = 0;
+    s >= src - 1 -> s = src - 1, f = 0).  All in double: measured against the cv2 4.13.0 of the build container, whose
+    sample positions on a ramp image are exact to 1e-14 (the reference pins opencv-python 4.5.1.48, requirements.txt:4,
+    which is not installable offline; a float-coefficient variant would differ by <= 4e-5 on [0,1] pixel values)."""
+    scale = 1.0 / (float(dst_size) / float(src_size))
+    d = np.arange(dst_size, dtype=np.float64)
+    f = (d + 0.5) * scale - 0.5
+    s = np.floor(f).astype(np.int64)
+    f = f - s
+    lo = s < 0
+    f[lo] = 0; s[lo] = 0
+    hi = s >= src_size - 1
+    f[hi] = 0; s[hi] = src_size - 1
+    return s, f
+
+
+def cv_resize_linear(img: np.ndarray, dst_w: int, dst_h: int) -> np.ndarray:
+    """cv2.resize(img, (dst_w, dst_h)) for a float64 [H,W,C] image: bilinear, pixel-centre aligned, no antialiasing,
+    horizontal pass then vertical pass in double (what resize_with_pad calls, utils.py:224)."""
+    img = np.asarray(img, np.float64)
+    h, w = img.shape[:2]
+    sx, fx = _cv_linear_coef(dst_w, w)
+    sy, fy = _cv_linear_coef(dst_h, h)
+    sx1, sy1 = np.minimum(sx + 1, w - 1), np.minimum(sy + 1, h - 1)
+    rows = img[:, sx] * (1.0 - fx)[None, :, None] + img[:, sx1] * fx[None, :, None]      # [H, dst_w, C]
+    return rows[sy] * (1.0 - fy)[:, None, None] + rows[sy1] * fy[:, None, None]
+
+
+def resize_with_pad(img: np.ndarray, size: int = 224):
+    """utils.resize_with_pad (copenet/src/copenet/utils/utils.py:214-235): longer side -> size, zero letterbox."""
+    bigger = img.shape[0] if img.shape[0] > img.shape[1] else img.shape[1]
+    scale = size / bigger
+    out = cv_resize_linear(img, int(scale * img.shape[1]), int(scale * img.shape[0]))
+    pad_top = (size - out.shape[0]) // 2
+    pad_left = (size - out.shape[1]) // 2
+    full = np.zeros((size, size, img.shape[2]), np.float64)
+    full[pad_top:pad_top + out.shape[0], pad_left:pad_left + out.shape[1]] = out
+    return full, scale, [pad_left, pad_top]
+
+
+def dataset_preprocess(frame_bgr_u8: np.ndarray, rect, size: int = 224):
+    """The per-camera image path of aerialpeople.__getitem__ (dsets/aerialpeople.py:125-141,174): BGR u8 frame ->
+    [:, :, ::-1] / 255. -> crop rect = (y0, y1, x0, x1) -> resize_with_pad -> CHW float32 -> Normalize(mean, std).
+    Returns (image [3,size,size] float32, scale, [pad_left, pad_top])."""
+    y0, y1, x0, x1 = (int(v) for v in rect)
+    img = frame_bgr_u8[:, :, ::-1] / 255.
+    img, scale, pad = resize_with_pad(img[y0:y1, x0:x1, :], size)
+    chw = img.transpose(2, 0, 1).astype(np.float32)
+    chw = (chw - IMAGENET_MEAN[:, None, None]) / IMAGENET_STD[:, None, None]
+    return chw.astype(np.float32), scale, pad

@@ -1278,3 +1278,98 @@ def test_autograd_training_step_matches_hand_scheduled(tmp_path, smplx_dir, smpl
     net(x0=batch["im0"], x1=batch["im1"], bb0=batch["bb0"], bb1=batch["bb1"], init_position0=in_trans, init_position1=in_trans, iters=3)
     with pytest.raises(RuntimeError, match="overwritten"):
         q0.sum().backward()
+
+
+# ----------------------------------------------------------------------------- preprocessing, staged server
+def _golden(name):
+    return dict(np.load(os.path.join(os.path.dirname(__file__), "golden", name)))
+
+
+def test_preprocess_bgr8_is_bit_exact(net_state):
+    """airpose_preprocess_bgr8 against the reference's torch ops on the same message (server.py:93-98; golden frame made
+    by oracle/gen_golden_server.py) and against the oracle: bit for bit."""
+    from airpose_b200.preprocess import bgr8_to_normalized
+    g = _golden("server_stages.npz")
+    msgs = synthetic.server_messages(int(g["seed"]), 2, net_state["init_pose"], net_state["init_shape"])
+    raw = np.frombuffer(msgs[0][1], dtype=np.uint8, count=224 * 224 * 3, offset=13).reshape(1, 224, 224, 3)
+    out = bgr8_to_normalized(t(raw.copy())).cpu().numpy()
+    assert np.array_equal(out, g["frame_0"])
+    assert np.array_equal(out, orc.server_preprocess(msgs[0][1]))
+    # a batch, and a flat byte view
+    raw2 = np.stack([raw[0], raw[0][::-1].copy()])
+    out2 = bgr8_to_normalized(t(raw2).view(-1), size=224).cpu().numpy()
+    assert np.array_equal(out2[0], g["frame_0"][0]) and np.array_equal(out2[1], g["frame_0"][0][:, ::-1])
+
+
+def test_crop_resize_matches_reference_golden():
+    """airpose_preprocess_crop_resize against the reference's resize_with_pad (cv2) + Normalize on seeded frames
+    (tests/golden/preprocess.npz): agreement to the final float32 rounding (5e-7 on the normalised value), identical scale
+    and padding, the letterbox exactly (0 - mean) / std; plus a batch of crops from one shared full-HD frame against the oracle."""
+    from airpose_b200.preprocess import crop_resize_pad_normalize
+    g = _golden("preprocess.npz")
+    for i, case in enumerate(g["cases"]):
+        h, w, seed, y0, y1, x0, x1 = (int(v) for v in case)
+        frame = synthetic.camera_frame(h, w, seed)
+        img, scales, pads = crop_resize_pad_normalize(t(frame), [(y0, y1, x0, x1)])
+        e = float(np.abs(img[0].cpu().numpy() - g["image_%d" % i]).max())
+        print("crop_resize case %d (%dx%d crop): max abs err %.2e" % (i, y1 - y0, x1 - x0, e))
+        assert e <= 5e-7
+        assert scales[0] == float(g["scale_%d" % i]) and pads[0] == g["pad_%d" % i].tolist()
+    frame = synthetic.camera_frame(1080, 1920, 3)
+    rects = [(100, 900, 600, 1300), (0, 1080, 0, 1920), (500, 520, 30, 400), (13, 1001, 1500, 1920)]
+    imgs, scales, pads = crop_resize_pad_normalize(t(frame), rects)
+    for k, r in enumerate(rects):
+        ref, s, pad = orc.dataset_preprocess(frame, r)
+        assert np.abs(imgs[k].cpu().numpy() - ref).max() <= 5e-7 and scales[k] == s and pads[k] == pad
+    # per-crop frames [n,H,W,3]
+    frames = np.stack([synthetic.camera_frame(120, 200, 5), synthetic.camera_frame(120, 200, 6)])
+    imgs, _, _ = crop_resize_pad_normalize(t(frames), [(0, 120, 0, 200), (10, 100, 20, 90)])
+    for k, r in enumerate([(0, 120, 0, 200), (10, 100, 20, 90)]):
+        assert np.abs(imgs[k].cpu().numpy() - orc.dataset_preprocess(frames[k], r)[0]).max() <= 5e-7
+    with pytest.raises(ValueError):
+        crop_resize_pad_normalize(t(frame), [(0, 2000, 0, 10)])
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_staged_server_matches_oracle_and_reference(tmp_path, net_state, graph):
+    """StagedServer.process on two frames x (stage 0, 1, 2) in the reference's wire format: every reply against the oracle's
+    restatement of process() fed with the device's own trunk features (1e-4 relative: the collapsed fp32 regressor), the
+    trunk features against the bf16-hooked reference trunk (5e-3), the replies against the reference's own replies
+    (tests/golden/server_stages.npz, bf16-hooked trunk; absolute, the 6D pose entries are O(1)).  ``graph=True`` replays
+    each stage from a CUDA graph and must give the same bytes as the eager run."""
+    from airpose_b200 import server
+    g = _golden("server_stages.npz")
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+    model = server.getmodel(mp)
+    model.load_state_dict(server.fix_state_dict({"model." + k: torch.from_numpy(np.asarray(v)) for k, v in net_state.items()}), strict=True)
+    srv = server.StagedServer(model, device=DEV, graph=graph)
+    msgs = synthetic.server_messages(int(g["seed"]), 2, net_state["init_pose"], net_state["init_shape"])
+    assert len(msgs[0][1]) == server.BUFFERSIZE and len(msgs[1][1]) == server.BUFFERSIZE_STAGES
+    state = orc.ServerState(net_state)
+    frame_no, worst, worst_ref = -1, 0.0, 0.0
+    replies = []
+    for i, (stage, data) in enumerate(msgs):
+        reply = np.frombuffer(srv.process(bytearray(data), None, stage), dtype=np.float32)
+        replies.append(reply.copy())
+        assert reply.shape == ((145,) if stage == 2 else (136,))
+        if stage == 0:
+            frame_no += 1
+            xf = srv.xf.cpu().numpy()
+            assert rel_err(xf, g["bf16_xf_%d" % frame_no]) < 5e-3
+            assert np.array_equal(srv.bb.cpu().numpy()[0], np.frombuffer(data, np.float32, 3, 1))
+        ref = orc.server_process(net_state, state, data, stage, feat_fn=lambda fr: xf)
+        worst = max(worst, rel_err(reply, ref))
+        worst_ref = max(worst_ref, float(np.abs(reply - g["bf16_reply_%d" % i]).max()))
+    print("staged server (graph=%s): worst rel err vs oracle %.2e, worst abs err vs the reference's replies %.2e" % (graph, worst, worst_ref))
+    assert worst < 1e-4 and worst_ref < 2e-2
+    # stage byte taken from the message when not given; bad stage / short message are rejected
+    r0 = np.frombuffer(srv.process(msgs[0][1]), dtype=np.float32)
+    assert np.array_equal(r0, replies[0])              # stage 0 does not depend on the carried state
+    with pytest.raises(ValueError):
+        srv.process(b"\x03" + bytes(600))
+    with pytest.raises(ValueError):
+        srv.process(msgs[0][1][:100], None, 0)
+    if graph:
+        eager = server.StagedServer(model, device=DEV, graph=False)
+        for i, (stage, data) in enumerate(msgs):
+            assert np.array_equal(np.frombuffer(eager.process(data, None, stage), dtype=np.float32), replies[i]), i

@@ -1,6 +1,6 @@
 """Quick device-side timings of the hot-path pieces (development aid; bench.py is the contract).
 
-    python tools/gpu_probe.py [section ...]     sections: lbs trunk ief twoview gemm
+    python tools/gpu_probe.py [section ...]     sections: lbs trunk ief twoview gemm server preprocess
 Each section runs in its own process so a device fault in one does not poison the others.
 """
 import os
@@ -107,7 +107,51 @@ def sec_gemm(tmp):
               (M, N, K, ms, 2.0 * M * N * K / ms / 1e9, ms_t, 2.0 * M * N * K / ms_t / 1e9), flush=True)
 
 
-SECTIONS = {"lbs": sec_lbs, "trunk": sec_trunk, "ief": sec_ief, "twoview": sec_twoview, "gemm": sec_gemm}
+def sec_server(tmp):
+    """Per-message latency of the staged drone server (host wall clock around process(): H2D + device work + D2H + sync),
+    eager and CUDA-graph replay, against the slot budgets of airpose.yaml:9-11 (45 ms stage 0, 2.5 ms stages 1-2)."""
+    import numpy as np
+    import torch
+    from airpose_b200 import server, synthetic
+    sd = synthetic.make_network_state(123)
+    mp = synthetic.write_mean_params(os.path.join(tmp, "smpl_mean_params.npz"))
+    msgs = synthetic.server_messages(17, 1, sd["init_pose"], sd["init_shape"])
+    for graph in (False, True):
+        model = server.getmodel(mp)
+        model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+        try:
+            srv = server.StagedServer(model, graph=graph)
+            for _ in range(5):
+                for stage, data in msgs:
+                    srv.process(data, None, stage)
+            lat = {0: [], 1: [], 2: []}
+            for _ in range(100):
+                for stage, data in msgs:
+                    t0 = time.perf_counter()
+                    srv.process(data, None, stage)
+                    lat[stage].append((time.perf_counter() - t0) * 1e3)
+            print("server graph=%s: " % graph + "  ".join("stage %d median %.3f ms p99 %.3f ms" % (k, float(np.median(v)), float(np.percentile(v, 99)))
+                                                          for k, v in lat.items()), flush=True)
+        except Exception as e:      # report, keep the other mode's numbers
+            print("server graph=%s FAILED: %r" % (graph, e), flush=True)
+
+
+def sec_preprocess(tmp):
+    import numpy as np
+    import torch
+    from airpose_b200 import synthetic
+    from airpose_b200.preprocess import crop_resize_pad_normalize
+    n = 128
+    frames = torch.from_numpy(np.stack([synthetic.camera_frame(1080, 1920, s) for s in range(4)])).cuda()
+    frames = frames.repeat(n // 4, 1, 1, 1)                     # 128 full-HD BGR frames = 796 MB
+    rects = [(100 + (i % 7) * 10, 900 - (i % 5) * 20, 600 + (i % 3) * 30, 1300 + (i % 4) * 25) for i in range(n)]
+    out = torch.empty(n, 3, 224, 224, device="cuda")
+    ms = cuda_time(lambda: crop_resize_pad_normalize(frames, rects, out=out))
+    print("crop_resize_pad_normalize n=%d crops from 1080p frames: %.3f ms  %.1f k images/s  output %.1f GB/s" %
+          (n, ms, n / ms, n * 3 * 224 * 224 * 4 / 1e9 / (ms * 1e-3)), flush=True)
+
+
+SECTIONS = {"server": sec_server, "preprocess": sec_preprocess, "lbs": sec_lbs, "trunk": sec_trunk, "ief": sec_ief, "twoview": sec_twoview, "gemm": sec_gemm}
 
 if __name__ == "__main__":
     if len(sys.argv) >= 3 and sys.argv[1] == "--one":
