@@ -512,6 +512,13 @@ int launch_bn(const GemmLaunch& L, KP& kp, cudaStream_t stream) {
   SkWorkspace* w = nullptr;
   if (get_workspace(stream, &w)) return 1;
   kp.ws = w->ws; kp.flags = w->flags; kp.epoch = ++w->epoch;
+  {
+    // Under stream capture the epoch is frozen into the graph: a replay would find the flags of the previous replay (same
+    // value) already set.  Clear them inside the graph before every stream-K launch, so each replay starts from zero flags.
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    AP_CHECK_CUDA(cudaStreamIsCapturing(stream, &cs));
+    if (cs != cudaStreamCaptureStatusNone) AP_CHECK_CUDA(cudaMemsetAsync(w->flags, 0, (size_t)kMaxGrid * 2 * sizeof(uint32_t), stream));
+  }
   const int units = kp.tiles_m * kp.tiles_n * kp.num_kb;
   cudaLaunchConfig_t cfg{};
   // Stream-K pays a fixed price per cut tile (an fp32 partial tile through L2 and a gather at the end of

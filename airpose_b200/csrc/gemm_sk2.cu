@@ -533,6 +533,13 @@ int launch_gemm_sk2(const GemmLaunch& L, cudaStream_t stream) {
   SkWorkspace* w = nullptr;
   if (get_workspace2(stream, &w)) return 1;
   kp.ws = w->ws; kp.flags = w->flags; kp.epoch = ++w->epoch;
+  {
+    // Under stream capture the epoch is frozen into the graph: a replay would find the flags of the previous replay (same
+    // value) already set.  Clear them inside the graph before every stream-K launch, so each replay starts from zero flags.
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    AP_CHECK_CUDA(cudaStreamIsCapturing(stream, &cs));
+    if (cs != cudaStreamCaptureStatusNone) AP_CHECK_CUDA(cudaMemsetAsync(w->flags, 0, (size_t)kMaxGrid * 2 * sizeof(uint32_t), stream));
+  }
   const int units = kp.tiles_m * kp.tiles_n * kp.num_kb;
   const int tiles = kp.tiles_m * kp.tiles_n;
   const int pairs_max = std::min(num_sms(), kMaxGrid) / 2;

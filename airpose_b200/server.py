@@ -116,11 +116,15 @@ class StagedServer:
         if g is None:
             # warm up eagerly (weight packing, launch plans and workspaces are created on first use), restore the carried
             # state, then capture; the capture itself does not execute, so the replay below is this message's only pass
+            # The warm-up runs on the capture stream: the stream-K GEMMs keep one partial-tile workspace per stream.
+            cur = torch.cuda.current_stream()
             saved = [t.clone() for t in (self.xf, self.bb, self.curr_position, self.curr_theta, self.curr_shape)]
-            self._stage_device(stage)
-            torch.cuda.current_stream().synchronize()
-            for t, s in zip((self.xf, self.bb, self.curr_position, self.curr_theta, self.curr_shape), saved):
-                t.copy_(s)
+            self._stream.wait_stream(cur)
+            with torch.cuda.stream(self._stream):
+                self._stage_device(stage)
+                for t, s in zip((self.xf, self.bb, self.curr_position, self.curr_theta, self.curr_shape), saved):
+                    t.copy_(s)
+            self._stream.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self._stream):
                 self._stage_device(stage)
