@@ -186,6 +186,9 @@ SYMBOLS = {
     "airpose_backbone_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(BnTrainParams), C.c_void_p, C.c_void_p]),
     "airpose_backbone_bwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(BnTrainParams), C.c_void_p,
                                              C.POINTER(TrunkGrads), C.POINTER(C.c_void_p * 53), C.c_void_p]),
+    "airpose_backbone_fwd_train_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(BnTrainParams), C.c_void_p, C.c_void_p]),
+    "airpose_backbone_bwd_train_pair": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(BnTrainParams), C.c_void_p,
+                                                  C.POINTER(TrunkGrads), C.POINTER(C.c_void_p * 53), C.c_void_p]),
     "airpose_debug_conv_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int, C.c_void_p]),
     "airpose_debug_bn_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

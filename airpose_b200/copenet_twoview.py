@@ -276,8 +276,14 @@ class copenet_twoview(nn.Module):
         B = im0.shape[0]
         in_trans, in_trans_unscaled = self._init_translation(B, im0.device)
         reg_iters = getattr(self.hparams, "reg_iters", 3)
-        xf0 = self.model._forward_feat_ext_train(im0.contiguous(), tape=0)
-        xf1 = self.model._forward_feat_ext_train(im1.contiguous(), tape=1)
+        im0, im1 = im0.contiguous(), im1.contiguous()
+        paired = 2 <= B and 2 * B <= self.model.PAIR_MAX_IMAGES    # both views through one set of launches (BatchNorm still per view)
+        if paired:
+            xf = self.model._forward_feat_ext_train_pair(im0, im1, tape=0)
+            xf0, xf1 = xf[:B], xf[B:]
+        else:
+            xf0 = self.model._forward_feat_ext_train(im0, tape=0)
+            xf1 = self.model._forward_feat_ext_train(im1, tape=1)
         pred, ctx = self.model.ief_train_forward(xf0, xf1, input_batch["bb0"], input_batch["bb1"], in_trans, in_trans,
                                                  iters=reg_iters, mask1=mask1, mask2=mask2)
         out = self._after_regressor(pred, (input_batch["intr0"], input_batch["intr1"]), in_trans_unscaled)
@@ -285,8 +291,11 @@ class copenet_twoview(nn.Module):
         optimizer.zero_grad()
         gr = self.model.ief_train_backward(ctx, g["pred_pose0"], g["pred_betas0"], g["pred_pose1"], g["pred_betas1"],
                                            want_feature_grads=True, into_param_grads=True)
-        self.model.backward_feat_ext(im0, 0, gr["xf0"], accumulate=False, into_param_grads=True)
-        self.model.backward_feat_ext(im1, 1, gr["xf1"], accumulate=True, into_param_grads=True)
+        if paired:
+            self.model.backward_feat_ext(im0, 0, torch.cat([gr["xf0"], gr["xf1"]]), accumulate=False, into_param_grads=True, x1=im1)
+        else:
+            self.model.backward_feat_ext(im0, 0, gr["xf0"], accumulate=False, into_param_grads=True)
+            self.model.backward_feat_ext(im1, 1, gr["xf1"], accumulate=True, into_param_grads=True)
         scale = optimizer.allreduce_grads()
         optimizer.step(grad_scale=scale)
         return loss, losses

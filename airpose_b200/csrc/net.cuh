@@ -68,10 +68,12 @@ struct airpose_net {
   std::vector<int64_t> bn_save_off;
   // tape of a training-mode forward (one per view): what the trunk backward needs
   struct Tape {
-    int n = 0, cap = 0;
+    int n = 0, cap = 0;                 // images on the tape (both views together for a two-view tape)
+    int views = 1;                      // 2: images [0, n/2) are view 0, [n/2, n) view 1 (airpose_backbone_fwd_train_pair)
     std::vector<__nv_bfloat16*> z, y;   // per conv: raw output, and BN(+residual)+ReLU output
     __nv_bfloat16* pooled = nullptr;    // max-pooled stem output = input of layer1
     float* stats = nullptr;             // per conv [mean(C) | invstd(C)]
+    float* stats1 = nullptr;            // the same for view 1 of a two-view tape
   } tape[2];
   // scratch of the backward pass
   __nv_bfloat16* bw[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // gradient ping-pong / dz / dpre / dilated

@@ -571,8 +571,12 @@ static int bn_train(airpose_net* h, int idx, const __nv_bfloat16* z, int64_t M, 
   return 0;
 }
 
-static int backbone_fwd_train_tape(airpose_net* h, const float* x, int n, const airpose_bn_train_params* bn, float* out_feat,
-                                   cudaStream_t st);
+static int backbone_fwd_train_tape(airpose_net* h, const float* x, const float* x1, int n, int views, const airpose_bn_train_params* bn,
+                                   float* out_feat, cudaStream_t st);
+
+static int train_scratch_reserve(airpose_net* h);
+static int backbone_fwd_train_notape(airpose_net* h, const float* x, int n, const airpose_bn_train_params* bn, float* out_feat,
+                                     __nv_bfloat16* Z, __nv_bfloat16* const* buf, cudaStream_t st);
 
 extern "C" int64_t airpose_bn_saved_stats_floats(void) {
   int64_t n = 0;
@@ -589,6 +593,14 @@ extern "C" int airpose_backbone_fwd_train(airpose_net_t* h, const float* x, int 
   for (size_t i = 0; i < h->specs.size(); ++i)
     AP_REQUIRE(bn->bn_weight[i] && bn->bn_bias[i], "airpose_backbone_fwd_train: BatchNorm %zu has a null parameter", i);
   cudaStream_t st = (cudaStream_t)stream_;
+  if (train_scratch_reserve(h)) return 1;
+  if (bn->tape >= 0) return backbone_fwd_train_tape(h, x, nullptr, n, 1, bn, out_feat, st);
+  __nv_bfloat16* Z = h->ztrain;
+  __nv_bfloat16* const* buf = h->actS[0];
+  return backbone_fwd_train_notape(h, x, n, bn, out_feat, Z, buf, st);
+}
+
+static int train_scratch_reserve(airpose_net* h) {
   const size_t act_elems = (size_t)h->chunk * 112 * 112 * 64;
   if (!h->ztrain) {
     AP_CHECK_CUDA(cudaMalloc((void**)&h->ztrain, act_elems * 2));
@@ -599,9 +611,11 @@ extern "C" int airpose_backbone_fwd_train(airpose_net_t* h, const float* x, int 
     h->bn_save_off.clear();
     for (const ConvSpec& s : h->specs) { h->bn_save_off.push_back(off); off += 2 * s.cout; }
   }
-  if (bn->tape >= 0) return backbone_fwd_train_tape(h, x, n, bn, out_feat, st);
-  __nv_bfloat16* Z = h->ztrain;
-  __nv_bfloat16* const* buf = h->actS[0];
+  return 0;
+}
+
+static int backbone_fwd_train_notape(airpose_net* h, const float* x, int n, const airpose_bn_train_params* bn, float* out_feat,
+                                     __nv_bfloat16* Z, __nv_bfloat16* const* buf, cudaStream_t st) {
   // stem: pack, raw 7x7 conv, BN + ReLU in place, max-pool
   {
     const int64_t work = (int64_t)n * 2 * kStemPlaneRows * 112;
@@ -850,7 +864,7 @@ static void launch_im2colT(const __nv_bfloat16* x, int n, int H, int W, int C, i
 }
 
 // stem: out[(r*7+s)*3 + c][m] = x_nchw[n, c, 2p - 3 + r, 2q - 3 + s]  (147 rows; rows 147..191 are zero)
-__global__ void stem_im2colT_kernel(const float* __restrict__ x, int n, __nv_bfloat16* __restrict__ out) {
+__global__ void stem_im2colT_kernel(const float* __restrict__ x, int n, __nv_bfloat16* __restrict__ out, int64_t ld) {
   const int64_t M = (int64_t)n * 112 * 112;
   const int kk = blockIdx.y;                      // 0..191
   for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
@@ -861,7 +875,7 @@ __global__ void stem_im2colT_kernel(const float* __restrict__ x, int n, __nv_bfl
       const int h = 2 * p - 3 + r, w = 2 * q - 3 + s;
       if (h >= 0 && h < 224 && w >= 0 && w < 224) v = __ldg(x + (((int64_t)img * 3 + c) * 224 + h) * 224 + w);
     }
-    out[(int64_t)kk * M + m] = __float2bfloat16_rn(v);
+    out[(int64_t)kk * ld + m] = __float2bfloat16_rn(v);
   }
 }
 
@@ -990,7 +1004,7 @@ static int tape_reserve(airpose_net* h, int t, int n) {
   if (tp.cap < n) {
     for (auto p : tp.z) cudaFree(p);
     for (auto p : tp.y) cudaFree(p);
-    cudaFree(tp.pooled); cudaFree(tp.stats);
+    cudaFree(tp.pooled); cudaFree(tp.stats); cudaFree(tp.stats1);
     tp.z.assign(io.size(), nullptr); tp.y.assign(io.size(), nullptr);
     for (size_t i = 0; i < io.size(); ++i) {
       const size_t elems = (size_t)n * io[i].Hout * io[i].Hout * h->specs[i].cout;
@@ -1001,41 +1015,61 @@ static int tape_reserve(airpose_net* h, int t, int n) {
     size_t ns = 0;
     for (const ConvSpec& s : h->specs) ns += 2 * s.cout;
     AP_CHECK_CUDA(cudaMalloc((void**)&tp.stats, ns * sizeof(float)));
+    AP_CHECK_CUDA(cudaMalloc((void**)&tp.stats1, ns * sizeof(float)));
     tp.cap = n;
   }
   tp.n = n;
   return 0;
 }
 
-// training-mode forward that keeps every layer's z and y (called from airpose_backbone_fwd_train when bn->tape >= 0)
-static int backbone_fwd_train_tape(airpose_net* h, const float* x, int n, const airpose_bn_train_params* bn, float* out_feat,
-                                   cudaStream_t st) {
+// training-mode forward that keeps every layer's z and y (called from airpose_backbone_fwd_train when bn->tape >= 0, and from
+// airpose_backbone_fwd_train_pair).  views == 2: the tape holds BOTH views of a batch of pairs, images [0, n) from x and [n, 2n)
+// from x1.  Every conv GEMM, pooling and (in the backward) every dgrad / wgrad GEMM then runs ONCE over the 2n images, while
+// BatchNorm -- whose batch statistics are per forward_feat_ext call in the reference (model_copenet.py:140-141) -- runs per
+// view on its half of the rows, view 0 first, so the running statistics see the same two updates in the same order.
+static int backbone_fwd_train_tape(airpose_net* h, const float* x, const float* x1, int n, int views, const airpose_bn_train_params* bn,
+                                   float* out_feat, cudaStream_t st) {
   const int t = bn->tape;
   AP_REQUIRE(t == 0 || t == 1, "airpose_backbone_fwd_train: tape must be -1, 0 or 1");
-  if (tape_reserve(h, t, n)) return 1;
+  const int nt = views * n;
+  if (tape_reserve(h, t, nt)) return 1;
   airpose_net::Tape& tp = h->tape[t];
+  tp.views = views;
   const std::vector<ConvIO> io = resnet50_io();
-  airpose_bn_train_params b2 = *bn;
-  b2.saved_stats = tp.stats;
+  airpose_bn_train_params bv[2] = {*bn, *bn};
+  bv[0].saved_stats = tp.stats;
+  bv[1].saved_stats = tp.stats1;
+  // BatchNorm of conv i over the rows of each view
+  auto bn_views = [&](int i, int64_t M_total, int C, const __nv_bfloat16* res, int relu) -> int {
+    const int64_t Mv = M_total / views;
+    for (int v = 0; v < views; ++v) {
+      const size_t off = (size_t)v * Mv * C;
+      if (bn_train(h, i, tp.z[i] + off, Mv, C, &bv[v], res ? res + off : nullptr, relu, tp.y[i] + off, st)) return 1;
+    }
+    return 0;
+  };
   {
     const int64_t work = (int64_t)n * 2 * kStemPlaneRows * 112;
-    stem_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(work, 128), 148 * 32), 128, 0, st>>>(x, n, h->colS[0]);
-    AP_LAUNCH_CHECK();
+    const size_t per_view = (size_t)n * 2 * kStemPlaneRows * 112 * kStemTapK;
+    for (int v = 0; v < views; ++v) {
+      stem_pack_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(work, 128), 148 * 32), 128, 0, st>>>(v ? x1 : x, n, h->colS[0] + v * per_view);
+      AP_LAUNCH_CHECK();
+    }
     GemmLaunch L{};
-    if (build_stem_gemm(h, n, 0, &L, true)) return 1;
+    if (build_stem_gemm(h, nt, 0, &L, true)) return 1;
     L.epi.out_bf16 = tp.z[0];
     if (enable_tma_epilogue(&L)) return 1;
     if (launch_gemm(L, st)) return 1;
-    if (bn_train(h, 0, tp.z[0], (int64_t)n * 112 * 112, 64, &b2, nullptr, 1, tp.y[0], st)) return 1;
-    maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64((int64_t)n * 56 * 56 * 8, 256), 148 * 16), 256, 0, st>>>(tp.y[0], n, tp.pooled);
+    if (bn_views(0, (int64_t)nt * 112 * 112, 64, nullptr, 1)) return 1;
+    maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64((int64_t)nt * 56 * 56 * 8, 256), 148 * 16), 256, 0, st>>>(tp.y[0], nt, tp.pooled);
     AP_LAUNCH_CHECK();
   }
   auto src = [&](int s) -> const __nv_bfloat16* { return s == -1 ? tp.pooled : tp.y[s]; };
   auto run = [&](int i) -> int {
     GemmLaunch L{};
-    if (conv_launch(h, i, src(io[i].in_src), n, io[i].Hin, io[i].Hin, nullptr, 0, tp.z[i], &L, true) || launch_gemm(L, st)) return 1;
+    if (conv_launch(h, i, src(io[i].in_src), nt, io[i].Hin, io[i].Hin, nullptr, 0, tp.z[i], &L, true) || launch_gemm(L, st)) return 1;
     const __nv_bfloat16* res = io[i].res_src == -3 ? nullptr : src(io[i].res_src);
-    return bn_train(h, i, tp.z[i], (int64_t)n * io[i].Hout * io[i].Hout, h->specs[i].cout, &b2, res, io[i].relu, tp.y[i], st);
+    return bn_views(i, (int64_t)nt * io[i].Hout * io[i].Hout, h->specs[i].cout, res, io[i].relu);
   };
   for (int i = 1; i < (int)io.size(); ++i) {
     if (io[i].res_src > i) {                       // conv3 of a block with a downsample branch: the branch (next index) runs first
@@ -1048,9 +1082,22 @@ static int backbone_fwd_train_tape(airpose_net* h, const float* x, int n, const 
   // the last block's output: conv3 of layer4.2 = index 51 (52 convs + stem = 53; the last entry in forward order is conv3 of the
   // last block because downsample entries follow conv3 only in the first block of a layer)
   const int last = (int)io.size() - 1;
-  avgpool_kernel<<<ceil_div(n * kFeat, 256), 256, 0, st>>>(tp.y[last], n, out_feat);
+  avgpool_kernel<<<ceil_div(nt * kFeat, 256), 256, 0, st>>>(tp.y[last], nt, out_feat);
   AP_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int airpose_backbone_fwd_train_pair(airpose_net_t* h, const float* x0, const float* x1, int n, const airpose_bn_train_params* bn,
+                                               float* out_feat, void* stream_) {
+  AP_REQUIRE(h && x0 && x1 && bn && out_feat, "airpose_backbone_fwd_train_pair: null argument");
+  AP_REQUIRE(h->loaded, "airpose_backbone_fwd_train_pair: weights not loaded (call airpose_net_load)");
+  AP_REQUIRE(n >= 2 && 2 * n <= h->chunk, "airpose_backbone_fwd_train_pair: n=%d pairs must be in [2, %d] (one call handles one chunk of "
+             "images; larger batches go through airpose_backbone_fwd_train per view)", n, h->chunk / 2);
+  AP_REQUIRE(bn->tape == 0 || bn->tape == 1, "airpose_backbone_fwd_train_pair: a tape (0 / 1) is required");
+  for (size_t i = 0; i < h->specs.size(); ++i)
+    AP_REQUIRE(bn->bn_weight[i] && bn->bn_bias[i], "airpose_backbone_fwd_train_pair: BatchNorm %zu has a null parameter", i);
+  if (train_scratch_reserve(h)) return 1;
+  return backbone_fwd_train_tape(h, x0, x1, n, 2, bn, out_feat, (cudaStream_t)stream_);
 }
 
 static int bw_reserve(airpose_net* h, int n) {
@@ -1070,20 +1117,26 @@ static int bw_reserve(airpose_net* h, int n) {
 
 static unsigned ew_grid(int64_t n) { return (unsigned)std::min<int64_t>(ceil_div64(n, 256), 148 * 16); }
 
-// BatchNorm (+ReLU) backward of conv i: dy -> dz (and dpre when asked), dgamma / dbeta into the output struct
+// BatchNorm (+ReLU) backward of conv i: dy -> dz (and dpre when asked), dgamma / dbeta into the output struct.  M = rows of the whole
+// tape; with a two-view tape each view's half is reduced against its own statistics and the second view's dgamma / dbeta add.
 static int bn_bwd(airpose_net* h, const airpose_net::Tape& tp, int i, int64_t M, const airpose_bn_train_params* bn,
                   const airpose_trunk_grads* g, const __nv_bfloat16* dy, bool relu, __nv_bfloat16* dz, __nv_bfloat16* dpre,
                   cudaStream_t st) {
   const int C = h->specs[i].cout;
-  const float* stats = tp.stats + h->bn_save_off[i];
-  const __nv_bfloat16* y = relu ? tp.y[i] : nullptr;
-  bn_bwd_reduce_kernel<<<kBnSlabs, 256, 0, st>>>(dy, y, tp.z[i], stats, M, C, h->bn_part);
-  AP_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, bn->bn_weight[i], stats, g->g_bn_weight[i],
-                                                           g->g_bn_bias[i], g->accumulate, h->bw_coef);
-  AP_LAUNCH_CHECK();
-  bn_bwd_apply_kernel<<<ew_grid(M * (C / 8)), 256, 0, st>>>(dy, y, tp.z[i], stats, h->bw_coef, M, C, dz, dpre);
-  AP_LAUNCH_CHECK();
+  const int64_t Mv = M / tp.views;
+  for (int v = 0; v < tp.views; ++v) {
+    const size_t off = (size_t)v * Mv * C;
+    const float* stats = (v ? tp.stats1 : tp.stats) + h->bn_save_off[i];
+    const __nv_bfloat16* y = relu ? tp.y[i] + off : nullptr;
+    bn_bwd_reduce_kernel<<<kBnSlabs, 256, 0, st>>>(dy + off, y, tp.z[i] + off, stats, Mv, C, h->bn_part);
+    AP_LAUNCH_CHECK();
+    bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, Mv, C, bn->bn_weight[i], stats, g->g_bn_weight[i],
+                                                             g->g_bn_bias[i], (g->accumulate || v > 0) ? 1 : 0, h->bw_coef);
+    AP_LAUNCH_CHECK();
+    bn_bwd_apply_kernel<<<ew_grid(Mv * (C / 8)), 256, 0, st>>>(dy + off, y, tp.z[i] + off, stats, h->bw_coef, Mv, C, dz + off,
+                                                               dpre ? dpre + off : nullptr);
+    AP_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -1151,16 +1204,16 @@ static int conv_dgrad(airpose_net* h, int i, const float* w_f32, const __nv_bflo
   return airpose_conv_bf16(&ca, st);
 }
 
-extern "C" int airpose_backbone_bwd_train(airpose_net_t* h, const float* x, int n, int t, const airpose_bn_train_params* bn,
-                                          const float* g_feat, const airpose_trunk_grads* g, const float* const* conv_weights,
-                                          void* stream_) {
-  AP_REQUIRE(h && x && bn && g_feat && g && conv_weights, "airpose_backbone_bwd_train: null argument");
-  AP_REQUIRE(t == 0 || t == 1, "airpose_backbone_bwd_train: tape must be 0 or 1");
+// x / x1: the images of view 0 / view 1 (x1 only for a two-view tape); n_view images per view; the tape holds views * n_view.
+static int backbone_bwd_train_impl(airpose_net_t* h, const float* x, const float* x1, int n_view, int views, int t,
+                                   const airpose_bn_train_params* bn, const float* g_feat, const airpose_trunk_grads* g,
+                                   const float* const* conv_weights, cudaStream_t st) {
   const airpose_net::Tape& tp = h->tape[t];
-  AP_REQUIRE(tp.n == n && n > 0, "airpose_backbone_bwd_train: tape %d holds a forward of %d images, not %d", t, tp.n, n);
+  const int n = views * n_view;          // everything below except BatchNorm and the stem's image operand sees one batch of n images
+  AP_REQUIRE(tp.n == n && n > 0 && tp.views == views, "airpose_backbone_bwd_train: tape %d holds a forward of %d images in %d view(s), not %d in %d",
+             t, tp.n, tp.views, n, views);
   for (size_t i = 0; i < h->specs.size(); ++i)
     AP_REQUIRE(g->g_weight[i] && g->g_bn_weight[i] && g->g_bn_bias[i] && conv_weights[i], "airpose_backbone_bwd_train: null buffer (conv %zu)", i);
-  cudaStream_t st = (cudaStream_t)stream_;
   if (bw_reserve(h, n)) return 1;
   const std::vector<ConvIO> io = resnet50_io();
   auto src = [&](int s) -> const __nv_bfloat16* { return s == -1 ? tp.pooled : tp.y[s]; };
@@ -1214,8 +1267,10 @@ extern "C" int airpose_backbone_bwd_train(airpose_net_t* h, const float* x, int 
   {
     launch_transpose(DZ, M0, 64, h->bw_t0, M0, st);
     AP_LAUNCH_CHECK();
-    stem_im2colT_kernel<<<dim3(148 * 4, 192), 256, 0, st>>>(x, n, h->bw_t1);
-    AP_LAUNCH_CHECK();
+    for (int v = 0; v < views; ++v) {                       // columns [v * M0 / views, ...) of the K-major operand come from view v's images
+      stem_im2colT_kernel<<<dim3(148 * 4, 192), 256, 0, st>>>(v ? x1 : x, n_view, h->bw_t1 + (size_t)v * (M0 / views), M0);
+      AP_LAUNCH_CHECK();
+    }
     airpose_gemm_args ga{};
     ga.A = h->bw_t0; ga.lda = M0; ga.B = h->bw_t1; ga.ldb = M0;
     ga.M = 64; ga.N = 192; ga.K = (int)M0;
@@ -1225,6 +1280,22 @@ extern "C" int airpose_backbone_bwd_train(airpose_net_t* h, const float* x, int 
     AP_LAUNCH_CHECK();
   }
   return 0;
+}
+
+extern "C" int airpose_backbone_bwd_train(airpose_net_t* h, const float* x, int n, int t, const airpose_bn_train_params* bn,
+                                          const float* g_feat, const airpose_trunk_grads* g, const float* const* conv_weights,
+                                          void* stream_) {
+  AP_REQUIRE(h && x && bn && g_feat && g && conv_weights, "airpose_backbone_bwd_train: null argument");
+  AP_REQUIRE(t == 0 || t == 1, "airpose_backbone_bwd_train: tape must be 0 or 1");
+  return backbone_bwd_train_impl(h, x, nullptr, n, 1, t, bn, g_feat, g, conv_weights, (cudaStream_t)stream_);
+}
+
+extern "C" int airpose_backbone_bwd_train_pair(airpose_net_t* h, const float* x0, const float* x1, int n, int t,
+                                               const airpose_bn_train_params* bn, const float* g_feat, const airpose_trunk_grads* g,
+                                               const float* const* conv_weights, void* stream_) {
+  AP_REQUIRE(h && x0 && x1 && bn && g_feat && g && conv_weights, "airpose_backbone_bwd_train_pair: null argument");
+  AP_REQUIRE(t == 0 || t == 1, "airpose_backbone_bwd_train_pair: tape must be 0 or 1");
+  return backbone_bwd_train_impl(h, x0, x1, n, 2, t, bn, g_feat, g, conv_weights, (cudaStream_t)stream_);
 }
 
 // ---- building blocks of the trunk backward exported for the per-layer parity tests

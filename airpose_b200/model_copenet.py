@@ -258,14 +258,43 @@ class copenet(nn.Module):
                 m.running_mean._airpose_gen = getattr(m.running_mean, "_airpose_gen", 0) + 1
         return out
 
-    def backward_feat_ext(self, x, tape, g_feat, accumulate=False, into_param_grads=False, grads=None):
+    PAIR_MAX_IMAGES = 64     # one chunk of the trunk: the two-view tape of airpose_backbone_fwd_train_pair holds 2B <= 64 images
+
+    def _forward_feat_ext_train_pair(self, x0, x1, tape=0):
+        """Both views of a batch of pairs through one set of launches (``airpose_backbone_fwd_train_pair``): conv GEMMs over the
+        2B images, BatchNorm per view (its own batch statistics, view 0 first -- exactly the reference's two
+        ``forward_feat_ext`` calls, model_copenet.py:140-141).  Returns [2B,2048], rows [0,B) = view 0; the tape holds both views."""
+        device = x0.device
+        B = x0.shape[0]
+        if x1.shape[0] != B or 2 * B > self.PAIR_MAX_IMAGES:
+            raise ValueError("the two-view tape takes up to {} pairs with equal view batches".format(self.PAIR_MAX_IMAGES // 2))
+        lib, h = self._ensure(max(2 * B, 2), device, allow_training=True, need_regressor=False)
+        pairs = self._conv_bn_pairs()
+        bn = self._bn_train_params(tape)
+        out = torch.empty(2 * B, 2048, device=device, dtype=torch.float32)
+        with torch.cuda.device(device):
+            _lib.check(lib.airpose_backbone_fwd_train_pair(h, x0.data_ptr(), x1.data_ptr(), B, C.byref(bn), out.data_ptr(),
+                                                           _lib.current_stream()), "airpose_backbone_fwd_train_pair")
+        tracked = [m.num_batches_tracked for _, m in pairs if m.track_running_stats and m.num_batches_tracked is not None]
+        if tracked:
+            torch._foreach_add_(tracked, 2)          # one update per view
+        for _, m in pairs:
+            if m.track_running_stats and m.running_mean is not None:
+                m.running_mean._airpose_gen = getattr(m.running_mean, "_airpose_gen", 0) + 1
+        return out
+
+    def backward_feat_ext(self, x, tape, g_feat, accumulate=False, into_param_grads=False, grads=None, x1=None):
         """Backward of the training-mode ``forward_feat_ext`` call recorded on ``tape``: gradients of the 53 conv weights
         and of every BatchNorm weight / bias, given d loss / d features ``g_feat`` [n,2048] and the same images ``x``.
         Returns a dict keyed like ``state_dict``; ``into_param_grads`` writes into the parameters' ``.grad`` instead,
-        ``grads`` (a dict from an earlier call) into those buffers (``accumulate`` adds: the second view of a pair)."""
+        ``grads`` (a dict from an earlier call) into those buffers (``accumulate`` adds: the second view of a pair).
+        ``x1``: the tape is the two-view tape of ``_forward_feat_ext_train_pair`` (``x`` = view 0's images, ``g_feat`` [2B,2048]):
+        one backward over both views, the weight-gradient GEMMs contracting over the pixels of both."""
         device = self.conv1.weight.device
         lib, h = self._ensure(0, device, allow_training=True, need_regressor=False)
         x = x.detach().to(device=device, dtype=torch.float32).contiguous()
+        if x1 is not None:
+            x1 = x1.detach().to(device=device, dtype=torch.float32).contiguous()
         g_feat = g_feat.detach().to(device=device, dtype=torch.float32).contiguous()
         names = {id(p): n for n, p in self.named_parameters()}
         out = {}
@@ -288,9 +317,14 @@ class copenet(nn.Module):
         tg.accumulate = int(bool(accumulate))
         bn = self._bn_train_params(tape, update_running=False)
         with torch.cuda.device(device):
-            _lib.check(lib.airpose_backbone_bwd_train(h, x.data_ptr(), x.shape[0], int(tape), C.byref(bn), g_feat.data_ptr(),
-                                                      C.byref(tg), C.byref(wptr), _lib.current_stream()),
-                       "airpose_backbone_bwd_train")
+            if x1 is not None:
+                _lib.check(lib.airpose_backbone_bwd_train_pair(h, x.data_ptr(), x1.data_ptr(), x.shape[0], int(tape), C.byref(bn),
+                                                               g_feat.data_ptr(), C.byref(tg), C.byref(wptr), _lib.current_stream()),
+                           "airpose_backbone_bwd_train_pair")
+            else:
+                _lib.check(lib.airpose_backbone_bwd_train(h, x.data_ptr(), x.shape[0], int(tape), C.byref(bn), g_feat.data_ptr(),
+                                                          C.byref(tg), C.byref(wptr), _lib.current_stream()),
+                           "airpose_backbone_bwd_train")
         return out
 
     def forward_feat_ext_pair(self, x0, x1):
@@ -484,9 +518,15 @@ class _TwoViewTrainFn(torch.autograd.Function):
             if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
                 raise ValueError("copenet.forward expects [B,3,224,224] images, got {}".format(tuple(x.shape)))
         x0, x1 = f(x0), f(x1)
+        B = x0.shape[0]
+        ctx.paired = 2 * B <= net.PAIR_MAX_IMAGES and B >= 2
         with torch.no_grad():
-            xf0 = net._forward_feat_ext_train(x0, tape=0)
-            xf1 = net._forward_feat_ext_train(x1, tape=1)
+            if ctx.paired:                      # both views through one set of launches (BatchNorm still per view)
+                xf = net._forward_feat_ext_train_pair(x0, x1, tape=0)
+                xf0, xf1 = xf[:B], xf[B:]
+            else:
+                xf0 = net._forward_feat_ext_train(x0, tape=0)
+                xf1 = net._forward_feat_ext_train(x1, tape=1)
             # the caller rescales its init translations in place after the call (copenet_twoview.py:214-218): keep copies
             pred, ictx = net.ief_train_forward(xf0, xf1, bb0.detach().clone(), bb1.detach().clone(), pos0.detach().clone(),
                                                pos1.detach().clone(), iters=iters)
@@ -508,8 +548,11 @@ class _TwoViewTrainFn(torch.autograd.Function):
         with torch.no_grad():
             gr = net.ief_train_backward(ictx, z(g_pose0, 135), z(g_betas0, 10), z(g_pose1, 135), z(g_betas1, 10),
                                         want_feature_grads=True)
-            tg = net.backward_feat_ext(ctx.images[0], 0, gr["xf0"], accumulate=False)
-            net.backward_feat_ext(ctx.images[1], 1, gr["xf1"], accumulate=True, grads=tg)
+            if ctx.paired:
+                tg = net.backward_feat_ext(ctx.images[0], 0, torch.cat([gr["xf0"], gr["xf1"]]), accumulate=False, x1=ctx.images[1])
+            else:
+                tg = net.backward_feat_ext(ctx.images[0], 0, gr["xf0"], accumulate=False)
+                net.backward_feat_ext(ctx.images[1], 1, gr["xf1"], accumulate=True, grads=tg)
         gr.update(tg)
         out = [None] * _TwoViewTrainFn.N_FIXED
         for i, n in enumerate(ctx.param_names):

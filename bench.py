@@ -31,8 +31,8 @@ LBS_BYTES_PER_MESH = 128420
 LBS_CONST_BYTES = 68338900
 CPU_SAMPLE_PAIRS = 8
 # dram__bytes_read.sum + dram__bytes_write.sum summed over the 77 conv-GEMM launches of one 128-image trunk
-# forward (64 pairs), from the ncu capture profiles/r01d_layers_dispatch_vs_v1.txt (cold-cache, serialised)
-TRUNK_DRAM_BYTES_PER_64_PAIRS = 4808.5e6
+# forward (64 pairs), from the ncu --set full capture profiles/r01s_ncu_full_trunk_128img.csv (cold-cache, serialised)
+TRUNK_DRAM_BYTES_PER_64_PAIRS = 4954.3e6
 
 
 def load_peaks():
@@ -196,57 +196,83 @@ def run_ours(args):
     smplx_ms = sum(p["smplx"][0].elapsed_time(p["smplx"][1]) for p in prof) / len(prof)
 
     # ------------------------------------------------------------------ end to end from pinned host memory
-    host_sets = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in sets[:2]]
     copy_stream = torch.cuda.Stream(device=dev)
     d2h_stream = torch.cuda.Stream(device=dev)
     out_keys = ("pred_pose", "pred_betas", "pred_vertices_cam", "pred_joints_cam", "pred_joints_2d_cam")
-    host_out = None
-    h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
 
-    def e2e_step(i, staged):
-        nonlocal host_out
-        # stage step i+1 on the copy stream while step i computes
-        nxt = None
-        with torch.cuda.stream(copy_stream):
-            nxt = {k: v.to(dev, non_blocking=True) for k, v in host_sets[(i + 1) % 2].items()}
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        torch.cuda.current_stream().wait_event(staged[1])
-        for tns in staged[0].values():
-            tns.record_stream(torch.cuda.current_stream())
-        out = mod.fwd_pass(staged[0])
-        res = {k + str(v): out[k + str(v)] for k in out_keys for v in (0, 1)}
-        if host_out is None:
-            host_out = [{k: torch.empty(t.shape, dtype=t.dtype).pin_memory() for k, t in res.items()} for _ in range(2)]
-        # results leave on their own stream so the D2H of step i overlaps the compute of step i+1
-        done = torch.cuda.Event()
-        done.record()
-        with torch.cuda.stream(d2h_stream):
-            d2h_stream.wait_event(done)
-            for k, t in res.items():
-                t.record_stream(d2h_stream)
-                host_out[i % 2][k].copy_(t, non_blocking=True)
-        return (nxt, ev)
+    def run_e2e(host_sets, prepare):
+        """Timed pipeline: H2D of step i+1 (copy stream) | prepare + fwd_pass of step i | D2H of step i-1 (third stream).
+        Returns (ms per step, h2d bytes per step, d2h bytes per step)."""
+        host_out = None
+        h2d = sum(v.numel() * v.element_size() for v in host_sets[0].values())
 
-    def stage_first():
-        with torch.cuda.stream(copy_stream):
-            s = {k: v.to(dev, non_blocking=True) for k, v in host_sets[0].items()}
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return (s, ev)
+        def stage(k):
+            with torch.cuda.stream(copy_stream):
+                s = {n: v.to(dev, non_blocking=True) for n, v in host_sets[k % 2].items()}
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return (s, ev)
 
-    staged = stage_first()
-    for i in range(max(args.warmup, 2)):
-        staged = e2e_step(i, staged)
-    sync_all()
-    d2h = sum(t.numel() * t.element_size() for t in host_out[0].values())
-    e0.record()
-    for i in range(args.steps):
-        staged = e2e_step(i, staged)
-    torch.cuda.current_stream().wait_stream(d2h_stream)      # the last step's results must be on the host before the clock stops
-    e1.record()
-    sync_all()
-    e2e_ms = e0.elapsed_time(e1) / args.steps
+        def e2e_step(i, staged):
+            nonlocal host_out
+            nxt = stage(i + 1)                      # stage step i+1 on the copy stream while step i computes
+            torch.cuda.current_stream().wait_event(staged[1])
+            for tns in staged[0].values():
+                tns.record_stream(torch.cuda.current_stream())
+            out = mod.fwd_pass(prepare(staged[0]))
+            res = {k + str(v): out[k + str(v)] for k in out_keys for v in (0, 1)}
+            if host_out is None:
+                host_out = [{k: torch.empty(t.shape, dtype=t.dtype).pin_memory() for k, t in res.items()} for _ in range(2)]
+            # results leave on their own stream so the D2H of step i overlaps the compute of step i+1
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
+                for k, t in res.items():
+                    t.record_stream(d2h_stream)
+                    host_out[i % 2][k].copy_(t, non_blocking=True)
+            return nxt
+
+        staged = stage(0)
+        for i in range(max(args.warmup, 2)):
+            staged = e2e_step(i, staged)
+        sync_all()
+        d2h = sum(t.numel() * t.element_size() for t in host_out[0].values())
+        e0.record()
+        for i in range(args.steps):
+            staged = e2e_step(i, staged)
+        torch.cuda.current_stream().wait_stream(d2h_stream)      # the last step's results must be on the host before the clock stops
+        e1.record()
+        sync_all()
+        return e0.elapsed_time(e1) / args.steps, h2d, d2h
+
+    # (1) the reference's batch format: fp32 normalised images in pinned host memory (copenet_twoview.py:166-183)
+    host_sets = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in sets[:2]]
+    e2e_ms, h2d, d2h = run_e2e(host_sets, lambda s: s)
+    # what the host link of THIS box delivers for exactly that copy (explains e2e when it is PCIe-bound)
+    with torch.cuda.stream(copy_stream):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(copy_stream)
+        for _ in range(3):
+            tmp_dev = {k: v.to(dev, non_blocking=True) for k, v in host_sets[0].items()}
+        c1.record(copy_stream)
+    copy_stream.synchronize()
+    h2d_gbs = 3 * h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del tmp_dev
+    # (2) the wire / dataset format: u8 BGR 224 x 224 crops (airpose_server/server.py:38,91-98), normalised on the device by
+    # airpose_preprocess_bgr8 inside the timed region -- a quarter of the bytes over the host link
+    from airpose_b200.preprocess import bgr8_to_normalized
+    host_sets_u8 = []
+    for s in sets[:2]:
+        hs = {k: v.cpu().pin_memory() for k, v in s.items() if not k.startswith("im")}
+        for v in (0, 1):
+            hs["im%d" % v] = torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(7 + v)).pin_memory()
+        host_sets_u8.append(hs)
+
+    def prepare_u8(sd):
+        return {k: (bgr8_to_normalized(v) if k.startswith("im") else v) for k, v in sd.items()}
+
+    e2e_u8_ms, h2d_u8, _ = run_e2e(host_sets_u8, prepare_u8)
     clocks = sampler.stop() if rank == 0 else None
 
     # ------------------------------------------------------------------ SMPL-X lbs() roofline at config 3 (rank 0, N=1)
@@ -267,7 +293,7 @@ def run_ours(args):
         lbs = (nb, lbs_ms)
 
     from airpose_b200 import parallel
-    ms, e2e_ms, trunk_ms = parallel.max_over_ranks([ms, e2e_ms, trunk_ms], device=dev)
+    ms, e2e_ms, trunk_ms, e2e_u8_ms = parallel.max_over_ranks([ms, e2e_ms, trunk_ms, e2e_u8_ms], device=dev)
     if rank == 0:
         peaks = load_peaks()
         value = world * B / (ms * 1e-3)
@@ -280,13 +306,16 @@ def run_ours(args):
                        "pairs_per_gpu": B, "global_pairs": world * B, "reg_iters": 3, "parallelism": "batch-sharded x%d, no collective" % world,
                        "l2": "inputs rotate over %d distinct batches (%.0f MB) so no step's inputs are L2-resident" % (NSETS, NSETS * set_bytes / 1e6)},
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "pinned host fp32 images -> H2D (double-buffered on a copy stream) -> fwd_pass -> D2H of pose/betas/vertices_cam/joints_cam/joints_2d into pinned buffers on a third stream; the timed region ends with a device-wide synchronize, so every copy is inside it"},
+                    "h2d_gbs_measured": h2d_gbs, "h2d_bound_value": world * B / (h2d / (h2d_gbs * 1e9)),
+                    "note": "pinned host fp32 images -> H2D (double-buffered on a copy stream) -> fwd_pass -> D2H of pose/betas/vertices_cam/joints_cam/joints_2d into pinned buffers on a third stream; the timed region ends with a device-wide synchronize, so every copy is inside it. h2d_gbs_measured = this box's host->device rate for the same copy; h2d_bound_value = the pairs/s that rate alone allows (e2e is PCIe-bound when it is below `value`)"},
+            "e2e_u8": {"value": world * B / (e2e_u8_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
+                       "note": "same pipeline from u8 BGR crops (the drone server's wire format), normalised on the device by airpose_preprocess_bgr8 inside the timed region"},
             "gpu_launches": launches,
             "stage_ms": {"trunk": trunk_ms, "ief": ief_ms, "smplx_x2": smplx_ms},
             "roofline": {"bound": "tensor", "kernel": "gemm_tma_kernel / gemm_sk_kernel (tcgen05 implicit-GEMM convs of the ResNet-50 trunk, both views; 77 launches per 128 images)",
                          "achieved": tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tflops_sustained"],
                          "traffic": TRUNK_DRAM_BYTES_PER_64_PAIRS * B / 64.0,
-                         "traffic_note": "bytes per step summed over the trunk's GEMM launches (ncu, profiles/r01d_*); algorithmic HBM bytes 56.4 MB/image",
+                         "traffic_note": "bytes per step summed over the trunk's GEMM launches (ncu, profiles/r01s_ncu_full_trunk_128img.csv); algorithmic HBM bytes 56.4 MB/image",
                          "peak_source": peaks["source"] + ", sustained bf16"},
             "clocks": clocks,
         }
@@ -295,8 +324,8 @@ def run_ours(args):
             gbs = (nb * LBS_BYTES_PER_MESH + LBS_CONST_BYTES) / (lbs_ms * 1e-3) / 1e9
             out["roofline_lbs"] = {"bound": "hbm", "kernel": "smplx_vertex_tc_kernel (+pose/joints kernels), lbs() batch=%d" % nb,
                                    "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                                   "meshes_per_s": nb / (lbs_ms * 1e-3), "traffic": 1073.6e6,
-                                   "traffic_note": "dram read+write of smplx_vertex_tc_kernel per launch at B=8192 (ncu, profiles/r01c_ncu_full_lbs_b8192.csv)",
+                                   "meshes_per_s": nb / (lbs_ms * 1e-3), "traffic": 1095.5e6,
+                                   "traffic_note": "dram read+write of smplx_vertex_tc_kernel per launch at B=8192 (ncu, profiles/r01s_ncu_full_lbs_b8192.csv)",
                                    "peak_source": peaks["source"]}
             if not args.no_cpu_baseline:
                 v, cms, cores = cpu_reference(CPU_SAMPLE_PAIRS, 3, 1)

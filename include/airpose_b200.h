@@ -247,7 +247,18 @@ typedef struct {
 } airpose_trunk_grads;
 int airpose_backbone_bwd_train(airpose_net_t* h, const float* x_nchw, int n_images, int tape, const airpose_bn_train_params* bn,
                                const float* g_feat, const airpose_trunk_grads* grads, const float* const* conv_weights_f32,
-                               void* stream);    /* conv_weights_f32: the 53 live fp32 conv weights [Cout,Cin,kh,kw] (DEVICE) */
+                               void* stream);
+/* Both views of a batch of n pairs through ONE set of launches (2n <= chunk = 64 images): every conv GEMM, pooling and, in
+ * the backward, every data- / weight-gradient GEMM runs once over the 2n images (the weight gradient contracts over both
+ * views' pixels, so there is no second accumulation pass), while BatchNorm runs per view on its half of the rows with its own
+ * batch statistics -- the reference calls forward_feat_ext once per view (model_copenet.py:140-141) -- view 0 first, so the
+ * running statistics receive the same two updates in the same order.  out_feat / g_feat: [2n,2048], rows [0,n) = view 0.
+ * The tape (bn->tape = 0 / 1) then holds both views; the matching backward is airpose_backbone_bwd_train_pair. */
+int airpose_backbone_fwd_train_pair(airpose_net_t* h, const float* x0_nchw, const float* x1_nchw, int n_pairs,
+                                    const airpose_bn_train_params* bn, float* out_feat, void* stream);
+int airpose_backbone_bwd_train_pair(airpose_net_t* h, const float* x0_nchw, const float* x1_nchw, int n_pairs, int tape,
+                                    const airpose_bn_train_params* bn, const float* g_feat, const airpose_trunk_grads* grads,
+                                    const float* const* conv_weights, void* stream);    /* conv_weights_f32: the 53 live fp32 conv weights [Cout,Cin,kh,kw] (DEVICE) */
 /* Building blocks of the trunk backward, exported for the per-layer parity tests (same code paths as above).
  * conv_bwd: weight gradient (fp32 [Cout,Cin,k,k], overwritten or accumulated) and, when out_dx is given, data gradient
  * (+ add) of trunk conv `conv_idx` for n images: dz bf16 [n,Ho,Wo,Cout], x_in bf16 [n,Hin,Win,Cin].

@@ -1373,3 +1373,48 @@ def test_staged_server_matches_oracle_and_reference(tmp_path, net_state, graph):
         eager = server.StagedServer(model, device=DEV, graph=False)
         for i, (stage, data) in enumerate(msgs):
             assert np.array_equal(np.frombuffer(eager.process(data, None, stage), dtype=np.float32), replies[i]), i
+
+
+def test_trunk_train_pair_matches_per_view(tmp_path, net_state):
+    """airpose_backbone_fwd_train_pair / _bwd_train_pair (both views of a batch through one set of launches, BatchNorm per view)
+    against the per-view calls: features, running statistics and num_batches_tracked after the forward, and every parameter
+    gradient after the backward.  The conv GEMMs see the same rows (only the tiling of the row dimension differs), so the
+    forward agrees to bf16 rounding of a few stream-K layers; the gradients to the bf16 noise level of the backward."""
+    from airpose_b200.model_copenet import getcopenet
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+
+    def make():
+        net = getcopenet(mp, pretrained=False)
+        net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in net_state.items()}, strict=True)
+        return net.to(DEV).train()
+
+    B = 5
+    x = synthetic.make_inputs(B, 9)
+    x0, x1 = t(x["im0"]), t(x["im1"])
+    gf = torch.randn(2 * B, 2048, generator=torch.Generator(device="cpu").manual_seed(2)).to(DEV)
+    a, b = make(), make()
+    fa = torch.cat([a._forward_feat_ext_train(x0, tape=0), a._forward_feat_ext_train(x1, tape=1)])
+    fb = b._forward_feat_ext_train_pair(x0, x1, tape=0)
+    e_f = rel_err(fb.cpu().numpy(), fa.cpu().numpy())
+    e_rm = max(rel_err(mb.running_mean.cpu().numpy(), ma.running_mean.cpu().numpy())
+               for (_, ma), (_, mb) in zip(a._conv_bn_pairs(), b._conv_bn_pairs()))
+    e_rv = max(rel_err(mb.running_var.cpu().numpy(), ma.running_var.cpu().numpy())
+               for (_, ma), (_, mb) in zip(a._conv_bn_pairs(), b._conv_bn_pairs()))
+    print("pair vs per-view forward: features %.2e, running mean %.2e, running var %.2e" % (e_f, e_rm, e_rv))
+    assert e_f < 1e-2 and e_rm < 1e-2 and e_rv < 1e-2
+    assert int(b.bn1.num_batches_tracked) == int(a.bn1.num_batches_tracked) == 2
+    ga = a.backward_feat_ext(x0, 0, gf[:B], accumulate=False)
+    a.backward_feat_ext(x1, 1, gf[B:], accumulate=True, grads=ga)
+    gb = b.backward_feat_ext(x0, 0, gf, accumulate=False, x1=x1)
+    worst, worst_name, dots = 0.0, "", np.zeros(3)
+    for k in ga:
+        u, v = gb[k].double().flatten(), ga[k].double().flatten()
+        e = rel_err(u.cpu().numpy(), v.cpu().numpy())
+        if e > worst:
+            worst, worst_name = e, k
+        dots += np.array([float(torch.dot(u, v)), float(torch.dot(u, u)), float(torch.dot(v, v))])
+    cos = dots[0] / np.sqrt(dots[1] * dots[2])
+    print("pair vs per-view backward: worst tensor %.2e (%s), cosine over all gradients %.6f" % (worst, worst_name, cos))
+    assert worst < 2.5e-1 and cos > 0.995
+    with pytest.raises(_lib.AirposeError):          # the tape now holds two views: the one-view backward refuses it
+        b.backward_feat_ext(x0, 0, gf[:B])
