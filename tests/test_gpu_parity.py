@@ -1442,3 +1442,91 @@ def test_trunk_train_pair_matches_per_view(tmp_path, net_state):
     assert worst < 6e-1 and cos > 0.97
     with pytest.raises(_lib.AirposeError):          # the tape now holds two views: the one-view backward refuses it
         b.backward_feat_ext(x0, 0, gf[:B])
+
+
+# ----------------------------------------------------------------------------- BASELINE.json's full sizes, through size-independent properties
+def test_lbs_full_size_properties(smplx_gpu, smplx_oracle):
+    """lbs() at BASELINE config 3 (8192 meshes): the oracle cannot run that batch in seconds, so the full-size call is checked
+    through properties that do not depend on the size -- (1) a mesh's result does not depend on the batch it sits in (a sample
+    of rows recomputed in a batch of their own, bit for bit: every mesh is one independent MMA column and epilogue lane),
+    (2) rest-pose rows planted in the batch return the template (KAT 1), (3) the 21 extra joints are a bit-exact gather of
+    the kernel's own vertices (KAT 4), (4) a translation shifts vertices and joints by exactly that amount up to fp32 rounding
+    (KAT 5), (5) the sampled rows match the oracle within the north_star tolerance."""
+    B = 8192
+    li = synthetic.make_lbs_inputs(B, seed=1)
+    betas, body = li["betas"].copy(), li["body_pose"].copy()
+    rest = [0, 4097, B - 1]
+    betas[rest] = 0
+    body[rest] = np.eye(3, dtype=np.float32)
+    bt, pt = t(betas), t(body)
+    out = smplx_gpu.forward(betas=bt, body_pose=pt, pose2rot=False)
+    assert out.vertices.shape == (B, 10475, 3) and out.joints.shape == (B, 127, 3)
+    assert torch.isfinite(out.vertices).all() and torch.isfinite(out.joints).all()
+    sample = [1, 31, 32, 33, 1000, 4096, 5555, B - 2]
+    sub = smplx_gpu.forward(betas=bt[sample].contiguous(), body_pose=pt[sample].contiguous(), pose2rot=False)
+    assert torch.equal(sub.vertices, out.vertices[sample]) and torch.equal(sub.joints, out.joints[sample])
+    vt = t(smplx_oracle.v_template)
+    assert float((out.vertices[rest] - vt).abs().max()) < 1e-6
+    idx = torch.from_numpy(orc.SMPLX_EXTRA_JOINT_VERTS).to(DEV)
+    assert torch.equal(out.joints[:, 55:76], out.vertices[:, idx])
+    shift = torch.randn(B, 3, generator=torch.Generator(device="cpu").manual_seed(3)).to(DEV)
+    moved = smplx_gpu.forward(betas=bt, body_pose=pt, transl=shift, pose2rot=False)
+    assert float((moved.vertices - out.vertices - shift[:, None]).abs().max()) < 2e-6
+    assert float((moved.joints - out.joints - shift[:, None]).abs().max()) < 2e-6
+    v, j = orc.smplx_forward(smplx_oracle, betas[sample], body[sample])
+    assert rel_err(out.vertices[sample].cpu().numpy(), v) < TC_TOL and rel_err(out.joints[sample].cpu().numpy(), j) < TC_TOL
+
+
+@pytest.mark.parametrize("B", [64, 256])
+def test_twoview_full_size_properties(net_state, smplx_dir, smplx_oracle, tmp_path, B):
+    """copenet_twoview forward at BASELINE config 2 (64 pairs) and at config 5's per-GPU shard (256 pairs): (1) everything
+    downstream of the trunk for a sample of pairs against the oracle fed with the device's own features (north_star 1e-3),
+    (2) the sampled pairs recomputed in a small batch of their own agree to the trunk's bf16 summation-order tolerance (the
+    stream-K layers cut K at batch-dependent positions), the regressor / SMPL-X stage bit for bit given the same features,
+    (3) view-swap symmetry at full size (KAT 6), (4) the 2D joints are the projection of the camera-frame joints (KAT 8
+    generalised), (5) vertices_cam - R * vertices = translation for every vertex (transform_smpl is rigid)."""
+    from argparse import Namespace
+    from airpose_b200.copenet_twoview import copenet_twoview
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+    mod = copenet_twoview(Namespace(smpl_mean_params=mp, smplx_model_dir=smplx_dir, batch_size=B, val_batch_size=B, reg_iters=3))
+    mod.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in net_state.items()})
+    mod = mod.to(DEV).eval()
+    x = synthetic.make_inputs(B, 77)
+    xt = {k: t(v) for k, v in x.items()}
+    out = mod.fwd_pass(xt)
+    for k in ("pred_pose0", "pred_vertices_cam1", "pred_joints_2d_cam0"):
+        assert torch.isfinite(out[k]).all(), k
+    sample = [0, 1, B // 2, B - 1]
+    xs = {k: v[sample] for k, v in x.items()}
+    # (1) oracle downstream of the device features
+    xf = mod.model.forward_feat_ext_pair(xt["im0"], xt["im1"]).cpu().numpy()
+    ref = orc.twoview_forward(net_state, smplx_oracle, xs, feats=(xf[:B][sample], xf[B:][sample]))
+    for v in (0, 1):
+        for k in ("pred_pose", "pred_betas", "pred_vertices_cam", "pred_joints_cam", "pred_joints_2d_cam"):
+            e = rel_err(out["%s%d" % (k, v)][sample].cpu().numpy(), ref["%s%d" % (k, v)])
+            assert e < 1e-3, (k, v, e)
+    # (2) batch independence
+    small = mod.fwd_pass({k: t(v) for k, v in xs.items()})
+    e_pose = rel_err(small["pred_pose0"].cpu().numpy(), out["pred_pose0"][sample].cpu().numpy())
+    e_vert = rel_err(small["pred_vertices_cam1"].cpu().numpy(), out["pred_vertices_cam1"][sample].cpu().numpy())
+    print("twoview B=%d: sampled pairs alone vs in the batch: pose %.2e, vertices %.2e" % (B, e_pose, e_vert))
+    assert e_pose < 5e-3 and e_vert < 5e-3
+    # (3) view swap
+    sw = dict(xt)
+    for k in ("im", "bb", "intr"):
+        sw[k + "0"], sw[k + "1"] = xt[k + "1"], xt[k + "0"]
+    outs = mod.fwd_pass(sw)
+    e_sw = max(rel_err(outs["pred_pose0"].cpu().numpy(), out["pred_pose1"].cpu().numpy()),
+               rel_err(outs["pred_vertices_cam1"].cpu().numpy(), out["pred_vertices_cam0"].cpu().numpy()))
+    print("twoview B=%d: view swap %.2e" % (B, e_sw))
+    assert e_sw < 5e-3
+    # (4) projection, (5) rigidity -- recomputed with torch ops in fp64 from the kernel's own outputs
+    for v in (0, 1):
+        jc = out["pred_joints_cam%d" % v].double()
+        c = xt["intr%d" % v][:, :2, 2].double()
+        j2d = 1475.0 * jc[:, :, :2] / jc[:, :, 2:3] + c[:, None]
+        assert rel_err(out["pred_joints_2d_cam%d" % v].cpu().numpy(), j2d.cpu().numpy()) < 1e-5
+        R = out["pred_rotmat%d" % v][:, 0].double()
+        verts = out["pred_output_cam%d" % v].vertices.double()
+        resid = out["pred_vertices_cam%d" % v].double() - torch.bmm(verts, R.transpose(1, 2)) - out["pred_smpltrans%d" % v].double()[:, None]
+        assert float(resid.abs().max()) < 1e-4
