@@ -153,8 +153,14 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, int n, float
 // relu(z * scale + shift (+ residual)) in bf16.  All three are HBM-bound passes over [M, C].
 constexpr int kBnSlabs = 148 * 2;
 
-__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, int64_t M, int C, float* __restrict__ part) {
+// Every BatchNorm kernel below takes the two views of a two-view tape in ONE launch: blockIdx.y = view, whose rows start
+// view_elems elements further on (per-view statistics / partials / coefficients follow the same index).  gridDim.y = 1 and
+// view_elems = 0 is the one-view case.
+__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, int64_t M, int C, float* __restrict__ part,
+                                                       int64_t view_elems) {
   __shared__ float red[256][17];
+  z += (size_t)blockIdx.y * view_elems;
+  part += (size_t)blockIdx.y * gridDim.x * C * 2;
   const int groups = C / 8;                         // 8 channels (16 B) per thread
   const int lanes = 256 / groups;                   // row lanes per block (C <= 2048)
   const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
@@ -200,34 +206,41 @@ __device__ __forceinline__ void slab_sum(const float* __restrict__ part, int sla
   s = __shfl_sync(0xffffffffu, s, 0); q = __shfl_sync(0xffffffffu, q, 0);
 }
 
-// one warp per channel (blockDim = 128 -> 4 channels per CTA)
+// one warp per channel (blockDim = 128 -> 4 channels per CTA); the views one after the other, so that the running statistics
+// receive view 0's update before view 1's (the reference calls forward_feat_ext once per view)
 __global__ void bn_finalize_kernel(const float* __restrict__ part, int slabs, int64_t M, int C, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
-                                   float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+                                   float* __restrict__ save0, float* __restrict__ save1, int views) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= C) return;
-  double s, q;
-  slab_sum(part, slabs, C, c, s, q);
-  if ((threadIdx.x & 31) != 0) return;
-  const double mean = s / (double)M;
-  const double var = fmax(q / (double)M - mean * mean, 0.0);            // biased, as F.batch_norm normalises
-  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-  const float sc = gamma[c] * invstd;
-  scale[c] = sc;
-  shift[c] = beta[c] - (float)mean * sc;
-  if (running_mean) {
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * (double)M / (double)max((int64_t)1, M - 1));
+  for (int v = 0; v < views; ++v) {
+    double s, q;
+    slab_sum(part + (size_t)v * slabs * C * 2, slabs, C, c, s, q);
+    if ((threadIdx.x & 31) != 0) continue;
+    const double mean = s / (double)M;
+    const double var = fmax(q / (double)M - mean * mean, 0.0);            // biased, as F.batch_norm normalises
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * invstd;
+    scale[v * 2048 + c] = sc;
+    shift[v * 2048 + c] = beta[c] - (float)mean * sc;
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)(var * (double)M / (double)max((int64_t)1, M - 1));
+    }
+    float* save = v ? save1 : save0;
+    if (save) { save[c] = (float)mean; save[C + c] = invstd; }
   }
-  if (save_mean) { save_mean[c] = (float)mean; save_invstd[c] = invstd; }
 }
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __restrict__ z, int64_t M, int C, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual,
-                                                       int relu, __nv_bfloat16* __restrict__ y) {
+                                                       int relu, __nv_bfloat16* __restrict__ y, int64_t view_elems) {
   const int groups = C / 8;
   const int64_t total = M * groups;
+  z += (size_t)blockIdx.y * view_elems; y += (size_t)blockIdx.y * view_elems;
+  if (residual) residual += (size_t)blockIdx.y * view_elems;
+  scale += blockIdx.y * 2048; shift += blockIdx.y * 2048;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % groups);
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(z) + i);
@@ -555,18 +568,21 @@ extern "C" int airpose_backbone_stem(airpose_net_t* h, const float* x, int n, vo
 // trunk of `train_reg_only` runs too): every BatchNorm normalises with the statistics of THIS batch of n images and
 // updates its running statistics.  Per conv: raw GEMM -> bn_stats -> bn_finalize -> bn_apply (+residual, ReLU).
 // One call = one view (the reference calls forward_feat_ext once per view, so the statistics are per view).
+// M = rows per view; views = 2: rows [M, 2M) of z / residual / y are view 1 (two-view tape), statistics saved to save1
 static int bn_train(airpose_net* h, int idx, const __nv_bfloat16* z, int64_t M, int C, const airpose_bn_train_params* bn,
-                    const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t st) {
-  bn_stats_kernel<<<kBnSlabs, 256, 0, st>>>(z, M, C, h->bn_part);
+                    const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t st, int views = 1, float* save1_base = nullptr) {
+  const int64_t ve = M * C;
+  bn_stats_kernel<<<dim3(kBnSlabs, views), 256, 0, st>>>(z, M, C, h->bn_part, ve);
   AP_LAUNCH_CHECK();
   float* save = bn->saved_stats ? bn->saved_stats + h->bn_save_off[idx] : nullptr;
+  float* save1 = save1_base ? save1_base + h->bn_save_off[idx] : nullptr;
   bn_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, bn->bn_weight[idx], bn->bn_bias[idx], bn->eps,
                                                        bn->momentum, bn->running_mean[idx], bn->running_var[idx], h->bn_scale,
-                                                       h->bn_shift, save, save ? save + C : nullptr);
+                                                       h->bn_shift, save, save1, views);
   AP_LAUNCH_CHECK();
   const int64_t total = M * (C / 8);
-  bn_apply_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 16), 256, 0, st>>>(z, M, C, h->bn_scale, h->bn_shift,
-                                                                                                residual, relu, y);
+  bn_apply_kernel<<<dim3((unsigned)std::min<int64_t>(ceil_div64(total, 256), 148 * 16), views), 256, 0, st>>>(z, M, C, h->bn_scale, h->bn_shift,
+                                                                                                             residual, relu, y, ve);
   AP_LAUNCH_CHECK();
   return 0;
 }
@@ -604,9 +620,9 @@ static int train_scratch_reserve(airpose_net* h) {
   const size_t act_elems = (size_t)h->chunk * 112 * 112 * 64;
   if (!h->ztrain) {
     AP_CHECK_CUDA(cudaMalloc((void**)&h->ztrain, act_elems * 2));
-    AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_part, (size_t)kBnSlabs * 2048 * 2 * sizeof(float)));
-    AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_scale, 2048 * sizeof(float)));
-    AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_shift, 2048 * sizeof(float)));
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_part, (size_t)2 * kBnSlabs * 2048 * 2 * sizeof(float)));
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_scale, 2 * 2048 * sizeof(float)));
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_shift, 2 * 2048 * sizeof(float)));
     int64_t off = 0;
     h->bn_save_off.clear();
     for (const ConvSpec& s : h->specs) { h->bn_save_off.push_back(off); off += 2 * s.cout; }
@@ -695,9 +711,14 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ g_feat, int n, __nv
 
 // partial sums of dpre = dy * [y > 0] and dpre * xhat per channel (xhat = (z - mean) * invstd)
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                                                            const __nv_bfloat16* __restrict__ z, const float* __restrict__ stats,
-                                                            int64_t M, int C, float* __restrict__ part) {
+                                                            const __nv_bfloat16* __restrict__ z, const float* __restrict__ stats0,
+                                                            const float* __restrict__ stats1, int64_t M, int C, float* __restrict__ part,
+                                                            int64_t view_elems) {
   __shared__ float red[256][17];
+  const float* __restrict__ stats = blockIdx.y ? stats1 : stats0;
+  dy += (size_t)blockIdx.y * view_elems; z += (size_t)blockIdx.y * view_elems;
+  if (y) y += (size_t)blockIdx.y * view_elems;
+  part += (size_t)blockIdx.y * gridDim.x * C * 2;
   const int groups = C / 8, lanes = 256 / groups;
   const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
   const int64_t per = (M + gridDim.x - 1) / gridDim.x;
@@ -738,27 +759,37 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
   }
 }
 
-// dgamma, dbeta (fp32, overwritten or accumulated) and the coefficients of dz = c1 (dpre - c2 - xhat c3)
+// dgamma, dbeta (fp32, overwritten or accumulated; the views add in order) and per view the coefficients of dz = c1 (dpre - c2 - xhat c3)
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int slabs, int64_t M, int C, const float* __restrict__ gamma,
-                                       const float* __restrict__ stats, float* __restrict__ g_gamma, float* __restrict__ g_beta,
-                                       int accumulate, float* __restrict__ coef) {
+                                       const float* __restrict__ stats0, const float* __restrict__ stats1, float* __restrict__ g_gamma,
+                                       float* __restrict__ g_beta, int accumulate, float* __restrict__ coef, int views) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per channel
   if (c >= C) return;
-  double s, q;
-  slab_sum(part, slabs, C, c, s, q);
-  if ((threadIdx.x & 31) != 0) return;
-  if (g_gamma) { g_gamma[c] = (float)q + (accumulate ? g_gamma[c] : 0.f); g_beta[c] = (float)s + (accumulate ? g_beta[c] : 0.f); }
-  coef[c] = gamma[c] * stats[C + c];
-  coef[2048 + c] = (float)(s / (double)M);
-  coef[4096 + c] = (float)(q / (double)M);
+  for (int v = 0; v < views; ++v) {
+    double s, q;
+    slab_sum(part + (size_t)v * slabs * C * 2, slabs, C, c, s, q);
+    if ((threadIdx.x & 31) != 0) continue;
+    const bool acc = accumulate || v > 0;
+    if (g_gamma) { g_gamma[c] = (float)q + (acc ? g_gamma[c] : 0.f); g_beta[c] = (float)s + (acc ? g_beta[c] : 0.f); }
+    float* cf = coef + v * 3 * 2048;
+    cf[c] = gamma[c] * (v ? stats1 : stats0)[C + c];
+    cf[2048 + c] = (float)(s / (double)M);
+    cf[4096 + c] = (float)(q / (double)M);
+  }
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                                                           const __nv_bfloat16* __restrict__ z, const float* __restrict__ stats,
-                                                           const float* __restrict__ coef, int64_t M, int C,
-                                                           __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dpre_out) {
+                                                           const __nv_bfloat16* __restrict__ z, const float* __restrict__ stats0,
+                                                           const float* __restrict__ stats1, const float* __restrict__ coef, int64_t M, int C,
+                                                           __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dpre_out,
+                                                           int64_t view_elems) {
   const int groups = C / 8;
   const int64_t total = M * groups;
+  const float* __restrict__ stats = blockIdx.y ? stats1 : stats0;
+  coef += blockIdx.y * 3 * 2048;
+  dy += (size_t)blockIdx.y * view_elems; z += (size_t)blockIdx.y * view_elems; dz += (size_t)blockIdx.y * view_elems;
+  if (y) y += (size_t)blockIdx.y * view_elems;
+  if (dpre_out) dpre_out += (size_t)blockIdx.y * view_elems;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % groups);
     const uint4 vd = __ldg(reinterpret_cast<const uint4*>(dy) + i);
@@ -1036,17 +1067,11 @@ static int backbone_fwd_train_tape(airpose_net* h, const float* x, const float* 
   airpose_net::Tape& tp = h->tape[t];
   tp.views = views;
   const std::vector<ConvIO> io = resnet50_io();
-  airpose_bn_train_params bv[2] = {*bn, *bn};
-  bv[0].saved_stats = tp.stats;
-  bv[1].saved_stats = tp.stats1;
-  // BatchNorm of conv i over the rows of each view
+  airpose_bn_train_params b0 = *bn;
+  b0.saved_stats = tp.stats;
+  // BatchNorm of conv i: each view's half of the rows against its own batch statistics, both views in one set of launches
   auto bn_views = [&](int i, int64_t M_total, int C, const __nv_bfloat16* res, int relu) -> int {
-    const int64_t Mv = M_total / views;
-    for (int v = 0; v < views; ++v) {
-      const size_t off = (size_t)v * Mv * C;
-      if (bn_train(h, i, tp.z[i] + off, Mv, C, &bv[v], res ? res + off : nullptr, relu, tp.y[i] + off, st)) return 1;
-    }
-    return 0;
+    return bn_train(h, i, tp.z[i], M_total / views, C, &b0, res, relu, tp.y[i], st, views, tp.stats1);
   };
   {
     const int64_t work = (int64_t)n * 2 * kStemPlaneRows * 112;
@@ -1109,8 +1134,8 @@ static int bw_reserve(airpose_net* h, int n) {
   AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_t0, (act + 8 * 2048) * 2));                       // + the pitch padding of conv_wgrad
   AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_t1, (std::max((size_t)576 * 3136, (size_t)192 * 12544) * n + 8 * 4608) * 2));
   AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_w, (size_t)512 * 4608 * 2 * 2));
-  AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_coef, 3 * 2048 * sizeof(float)));
-  if (!h->bn_part) AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_part, (size_t)kBnSlabs * 2048 * 2 * sizeof(float)));
+  AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_coef, 2 * 3 * 2048 * sizeof(float)));
+  if (!h->bn_part) AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_part, (size_t)2 * kBnSlabs * 2048 * 2 * sizeof(float)));
   h->bw_cap = n;
   return 0;
 }
@@ -1123,20 +1148,18 @@ static int bn_bwd(airpose_net* h, const airpose_net::Tape& tp, int i, int64_t M,
                   const airpose_trunk_grads* g, const __nv_bfloat16* dy, bool relu, __nv_bfloat16* dz, __nv_bfloat16* dpre,
                   cudaStream_t st) {
   const int C = h->specs[i].cout;
-  const int64_t Mv = M / tp.views;
-  for (int v = 0; v < tp.views; ++v) {
-    const size_t off = (size_t)v * Mv * C;
-    const float* stats = (v ? tp.stats1 : tp.stats) + h->bn_save_off[i];
-    const __nv_bfloat16* y = relu ? tp.y[i] + off : nullptr;
-    bn_bwd_reduce_kernel<<<kBnSlabs, 256, 0, st>>>(dy + off, y, tp.z[i] + off, stats, Mv, C, h->bn_part);
-    AP_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, Mv, C, bn->bn_weight[i], stats, g->g_bn_weight[i],
-                                                             g->g_bn_bias[i], (g->accumulate || v > 0) ? 1 : 0, h->bw_coef);
-    AP_LAUNCH_CHECK();
-    bn_bwd_apply_kernel<<<ew_grid(Mv * (C / 8)), 256, 0, st>>>(dy + off, y, tp.z[i] + off, stats, h->bw_coef, Mv, C, dz + off,
-                                                               dpre ? dpre + off : nullptr);
-    AP_LAUNCH_CHECK();
-  }
+  const int views = tp.views;
+  const int64_t Mv = M / views, ve = Mv * C;
+  const float* stats0 = tp.stats + h->bn_save_off[i];
+  const float* stats1 = tp.stats1 + h->bn_save_off[i];
+  const __nv_bfloat16* y = relu ? tp.y[i] : nullptr;
+  bn_bwd_reduce_kernel<<<dim3(kBnSlabs, views), 256, 0, st>>>(dy, y, tp.z[i], stats0, stats1, Mv, C, h->bn_part, ve);
+  AP_LAUNCH_CHECK();
+  bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, Mv, C, bn->bn_weight[i], stats0, stats1, g->g_bn_weight[i],
+                                                           g->g_bn_bias[i], g->accumulate ? 1 : 0, h->bw_coef, views);
+  AP_LAUNCH_CHECK();
+  bn_bwd_apply_kernel<<<dim3(ew_grid(Mv * (C / 8)), views), 256, 0, st>>>(dy, y, tp.z[i], stats0, stats1, h->bw_coef, Mv, C, dz, dpre, ve);
+  AP_LAUNCH_CHECK();
   return 0;
 }
 
@@ -1322,12 +1345,13 @@ extern "C" int airpose_debug_bn_bwd(airpose_net_t* h, int64_t M, int C, const vo
   AP_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "airpose_debug_bn_bwd: unsupported channel count %d", C);
   cudaStream_t st = (cudaStream_t)stream_;
   if (bw_reserve(h, 8)) return 1;
-  bn_bwd_reduce_kernel<<<kBnSlabs, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats, M, C, h->bn_part);
+  bn_bwd_reduce_kernel<<<kBnSlabs, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats, stats, M, C,
+                                                 h->bn_part, 0);
   AP_LAUNCH_CHECK();
-  bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, gamma, stats, g_gamma, g_beta, accumulate, h->bw_coef);
+  bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, gamma, stats, stats, g_gamma, g_beta, accumulate, h->bw_coef, 1);
   AP_LAUNCH_CHECK();
-  bn_bwd_apply_kernel<<<ew_grid(M * (C / 8)), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats,
-                                                            h->bw_coef, M, C, (__nv_bfloat16*)out_dz, (__nv_bfloat16*)out_dpre);
+  bn_bwd_apply_kernel<<<ew_grid(M * (C / 8)), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats, stats,
+                                                            h->bw_coef, M, C, (__nv_bfloat16*)out_dz, (__nv_bfloat16*)out_dpre, 0);
   AP_LAUNCH_CHECK();
   return 0;
 }

@@ -214,6 +214,8 @@ class copenet(nn.Module):
         device = self.conv1.weight.device
         x = x.detach().to(device=device, dtype=torch.float32).contiguous()
         n = x.shape[0]
+        if n == 0:                                   # empty batch: nothing to launch (torch modules accept it too)
+            return torch.empty(0, 2048, device=device, dtype=torch.float32)
         if self.training:
             return self._forward_feat_ext_train(x)
         lib, h = self._ensure(n, device, need_regressor=False)
@@ -339,6 +341,8 @@ class copenet(nn.Module):
         x0 = x0.detach().to(device=device, dtype=torch.float32).contiguous()
         x1 = x1.detach().to(device=device, dtype=torch.float32).contiguous()
         B = x0.shape[0]
+        if B == 0:
+            return torch.empty(0, 2048, device=device, dtype=torch.float32)
         lib, h = self._ensure(2 * B, device, need_regressor=False)
         out = torch.empty(2 * B, 2048, device=device, dtype=torch.float32)
         with torch.cuda.device(device):
@@ -355,6 +359,8 @@ class copenet(nn.Module):
         lib, h = self._ensure(0, device)
         outs = [torch.empty(B, 135, device=device, dtype=torch.float32), torch.empty(B, 10, device=device, dtype=torch.float32),
                 torch.empty(B, 135, device=device, dtype=torch.float32), torch.empty(B, 10, device=device, dtype=torch.float32)]
+        if B == 0:
+            return tuple(outs)
         a = _lib.IefArgs()
         a.batch, a.iters = B, int(iters)
         a.xf0, a.xf1, a.bb0, a.bb1, a.pos0, a.pos1 = (t.data_ptr() for t in (xf0, xf1, bb0, bb1, pos0, pos1))

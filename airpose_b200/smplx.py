@@ -338,6 +338,12 @@ class SMPLX(nn.Module):
         vertices = torch.empty(B, V, 3, device=device, dtype=torch.float32)
         joints = torch.empty(B, nj, 3, device=device, dtype=torch.float32)
         cam = {}
+        if B == 0:                                   # empty batch: nothing to launch
+            if root_R is not None or root_t is not None:
+                cam["vertices_cam"], cam["joints_cam"] = torch.empty_like(vertices), torch.empty_like(joints)
+            if focal_length is not None:
+                cam["joints_2d"] = torch.empty(0, nj, 2, device=device, dtype=torch.float32)
+            return ModelOutput(vertices=vertices if return_verts else None, joints=joints, betas=betas, body_pose=body_pose), cam
         a = _lib.SmplxFwdArgs()
         a.batch = B
         a.num_betas = shape_comp.shape[1]
@@ -495,6 +501,8 @@ def rot6d_to_rotmat(x):
         raise _lib.AirposeError("airpose_b200.rot6d_to_rotmat runs on CUDA only")
     lib = _lib.load()
     x = x.detach()
+    if x.numel() == 0:
+        return torch.empty(0, 3, 3, device=x.device, dtype=torch.float32)
     if x.dim() == 2 and x.stride(1) == 1 and x.shape[1] % 6 == 0 and x.dtype == torch.float32:
         groups, per, stride = x.shape[0], x.shape[1] // 6, x.stride(0)       # e.g. pred_pose[:, 3:] in place
     else:
@@ -515,6 +523,8 @@ def joints_to_j14(joints, index_map=None):
     j = joints.detach().to(torch.float32).contiguous()
     B, nj = j.shape[0], j.shape[1]
     out = torch.empty(B, 14, 3, device=j.device, dtype=torch.float32)
+    if B == 0:
+        return out
     mp = None
     if index_map is not None:
         mp = (C.c_int32 * 14)(*[int(i) for i in index_map])

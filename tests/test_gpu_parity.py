@@ -1530,3 +1530,28 @@ def test_twoview_full_size_properties(net_state, smplx_dir, smplx_oracle, tmp_pa
         verts = out["pred_output_cam%d" % v].vertices.double()
         resid = out["pred_vertices_cam%d" % v].double() - torch.bmm(verts, R.transpose(1, 2)) - out["pred_smpltrans%d" % v].double()[:, None]
         assert float(resid.abs().max()) < 1e-4
+
+
+def test_empty_and_single_inputs(net_gpu, smplx_gpu):
+    """Edge cases of the drop-in objects: an empty batch goes through every forward entry point and returns empty tensors of
+    the right shape (torch semantics: the reference's modules accept B = 0 in eval mode), a single pair / single mesh works,
+    and malformed inputs raise instead of launching."""
+    from airpose_b200.smplx import rot6d_to_rotmat, joints_to_j14
+    z = lambda *s: torch.zeros(*s, device=DEV)
+    o = smplx_gpu.forward(betas=z(0, 10), body_pose=z(0, 21, 3, 3), pose2rot=False)
+    assert tuple(o.vertices.shape) == (0, 10475, 3) and tuple(o.joints.shape) == (0, 127, 3)
+    assert tuple(net_gpu.forward_feat_ext(z(0, 3, 224, 224)).shape) == (0, 2048)
+    p0, b0, p1, b1 = net_gpu(x0=z(0, 3, 224, 224), x1=z(0, 3, 224, 224), bb0=z(0, 3), bb1=z(0, 3), init_position0=z(0, 3),
+                             init_position1=z(0, 3), iters=3)
+    assert tuple(p0.shape) == (0, 135) and tuple(b1.shape) == (0, 10)
+    assert tuple(rot6d_to_rotmat(z(0, 132)).shape) == (0, 3, 3)
+    assert tuple(joints_to_j14(z(0, 127, 3)).shape) == (0, 14, 3)
+    # one pair: the regressor starts from the mean pose; one more iteration moves it
+    x = synthetic.make_inputs(1, 3)
+    a = net_gpu(x0=t(x["im0"]), x1=t(x["im1"]), bb0=t(x["bb0"]), bb1=t(x["bb1"]), init_position0=z(1, 3), init_position1=z(1, 3), iters=1)
+    b = net_gpu(x0=t(x["im0"]), x1=t(x["im1"]), bb0=t(x["bb0"]), bb1=t(x["bb1"]), init_position0=z(1, 3), init_position1=z(1, 3), iters=3)
+    assert tuple(a[0].shape) == (1, 135) and not torch.equal(a[0], b[0])
+    with pytest.raises(ValueError):
+        net_gpu.forward_feat_ext(z(2, 3, 200, 200))
+    with pytest.raises(NotImplementedError):
+        smplx_gpu.forward(betas=z(1, 10), body_pose=z(1, 63), pose2rot=True)
