@@ -72,6 +72,7 @@ struct airpose_net {
     int views = 1;                      // 2: images [0, n/2) are view 0, [n/2, n) view 1 (airpose_backbone_fwd_train_pair)
     std::vector<__nv_bfloat16*> z, y;   // per conv: raw output, and BN(+residual)+ReLU output
     __nv_bfloat16* pooled = nullptr;    // max-pooled stem output = input of layer1
+    uint8_t* pool_idx = nullptr;        // window position of each pooled element's (first) maximum, for the backward
     float* stats = nullptr;             // per conv [mean(C) | invstd(C)]
     float* stats1 = nullptr;            // the same for view 1 of a two-view tape
   } tape[2];

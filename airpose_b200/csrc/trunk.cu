@@ -104,15 +104,18 @@ __global__ void stem_pack_kernel(const float* __restrict__ x, int n, __nv_bfloat
 }
 
 // MaxPool2d(3, stride 2, pad 1) on NHWC bf16 [n,112,112,64] -> [n,56,56,64]; 8 channels per thread.
-__global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, int n, __nv_bfloat16* __restrict__ y) {
+// idx (optional, training tape): per output element the window position 3 r + s of its FIRST maximum in scan order
+// (PyTorch's tie rule), which is where the backward routes the gradient.
+__global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, int n, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx = nullptr) {
   const int64_t total = (int64_t)n * 56 * 56 * 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % 8);
     const int64_t pix = i / 8;
     const int q = (int)(pix % 56), pr = (int)((pix / 56) % 56), img = (int)(pix / (56 * 56));
     float m[8];
+    uint32_t am[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; am[j] = 0; }
     for (int r = 0; r < 3; ++r) {
       const int h = pr * 2 - 1 + r;
       if (h < 0 || h >= 112) continue;
@@ -122,11 +125,17 @@ __global__ void maxpool_kernel(const __nv_bfloat16* __restrict__ x, int n, __nv_
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)img * 112 + h) * 112 + w) * 64 + cg * 8));
         const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          m[2 * j] = fmaxf(m[2 * j], __uint_as_float(u[j] << 16));
-          m[2 * j + 1] = fmaxf(m[2 * j + 1], __uint_as_float(u[j] & 0xFFFF0000u));
+        for (int j = 0; j < 8; ++j) {
+          const float o = (j & 1) ? __uint_as_float(u[j >> 1] & 0xFFFF0000u) : __uint_as_float(u[j >> 1] << 16);
+          if (o > m[j]) { m[j] = o; am[j] = 3 * r + s; }
         }
       }
+    }
+    if (idx) {
+      uint2 pk;
+      pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+      pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+      *reinterpret_cast<uint2*>(idx + pix * 64 + cg * 8) = pk;
     }
     __align__(16) __nv_bfloat16 o[8];
 #pragma unroll
@@ -894,19 +903,24 @@ static void launch_im2colT(const __nv_bfloat16* x, int n, int H, int W, int C, i
   transpose64_kernel<true><<<dim3((unsigned)ceil_div64(M, 64), ceil_div(C, 64), k * k), 256, 0, st>>>(x, M, C, out, ld, H, W, k, stride, pad, Ho, Wo);
 }
 
-// stem: out[(r*7+s)*3 + c][m] = x_nchw[n, c, 2p - 3 + r, 2q - 3 + s]  (147 rows; rows 147..191 are zero)
+// stem: out[(r*7+s)*3 + c][m] = x_nchw[n, c, 2p - 3 + r, 2q - 3 + s]  (147 rows; rows 147..191 are zero).  One thread = 8
+// consecutive pixels of one output row (112 = 14 x 8) = one 16-byte store; ld = row pitch of out.
 __global__ void stem_im2colT_kernel(const float* __restrict__ x, int n, __nv_bfloat16* __restrict__ out, int64_t ld) {
-  const int64_t M = (int64_t)n * 112 * 112;
+  const int64_t M8 = (int64_t)n * 112 * 14;
   const int kk = blockIdx.y;                      // 0..191
-  for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    if (kk < 147) {
-      const int c = kk % 3, tap = kk / 3, r = tap / 7, s = tap % 7;
-      const int q = (int)(m % 112), p = (int)((m / 112) % 112), img = (int)(m / (112 * 112));
-      const int h = 2 * p - 3 + r, w = 2 * q - 3 + s;
-      if (h >= 0 && h < 224 && w >= 0 && w < 224) v = __ldg(x + (((int64_t)img * 3 + c) * 224 + h) * 224 + w);
+  const int c = kk % 3, tap = kk / 3, r = tap / 7, s = tap % 7;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < M8; g += (int64_t)gridDim.x * blockDim.x) {
+    const int q0 = (int)(g % 14) * 8, p = (int)((g / 14) % 112), img = (int)(g / (14 * 112));
+    __align__(16) __nv_bfloat16 v[8];
+    const int h = 2 * p - 3 + r;
+    const bool row_ok = kk < 147 && h >= 0 && h < 224;
+    const float* xr = x + (((int64_t)img * 3 + c) * 224 + (row_ok ? h : 0)) * 224;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int w = 2 * (q0 + j) - 3 + s;
+      v[j] = __float2bfloat16_rn((row_ok && w >= 0 && w < 224) ? __ldg(xr + w) : 0.f);
     }
-    out[(int64_t)kk * ld + m] = __float2bfloat16_rn(v);
+    *reinterpret_cast<uint4*>(out + (int64_t)kk * ld + g * 8) = *reinterpret_cast<const uint4*>(v);
   }
 }
 
@@ -944,56 +958,36 @@ __global__ void wgrad_unpack_kernel(const __nv_bfloat16* __restrict__ D, int cou
   }
 }
 
-// MaxPool2d(3, 2, 1) backward on NHWC bf16: every input pixel collects the gradient of the windows whose (first, in scan
-// order -- PyTorch's tie rule) maximum it is.  Gather form, 8 channels (one 16-byte load) per thread.
-__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gy, int n,
+// MaxPool2d(3, 2, 1) backward on NHWC bf16: every input pixel collects the gradient of the (at most four) windows whose recorded
+// argmax (maxpool_kernel's idx: the first maximum in scan order, PyTorch's tie rule) it is.  Gather form, 8 channels per thread.
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ gy, int n,
                                                           __nv_bfloat16* __restrict__ gx) {
   const int64_t total = (int64_t)n * 112 * 112 * 8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int cg = (int)(i % 8);
     const int64_t pix = i / 8;
     const int w = (int)(pix % 112), h = (int)((pix / 112) % 112), img = (int)(pix / (112 * 112));
-    float xv[8], g[8];
-    {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + pix * 64 + cg * 8));
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    float g[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { xv[2 * j] = __uint_as_float(u[j] << 16); xv[2 * j + 1] = __uint_as_float(u[j] & 0xFFFF0000u); }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = 0.f;
-    }
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
     // windows (pr, q) that contain (h, w): 2 pr - 1 <= h <= 2 pr + 1
     for (int pr = h / 2; pr <= min(55, (h + 1) / 2); ++pr)
       for (int q = w / 2; q <= min(55, (w + 1) / 2); ++q) {
-        unsigned is_max = 0xFFu;                     // bit j: (h, w) is still the first maximum of this window in channel j
-        for (int r = 0; r < 3; ++r) {
-          const int hh = pr * 2 - 1 + r;
-          if (hh < 0 || hh >= 112) continue;
-          for (int s = 0; s < 3; ++s) {
-            const int ww = q * 2 - 1 + s;
-            if (ww < 0 || ww >= 112 || (hh == h && ww == w)) continue;
-            const bool earlier = hh < h || (hh == h && ww < w);
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (((int64_t)img * 112 + hh) * 112 + ww) * 64 + cg * 8));
-            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        const uint32_t me = 3 * (h - (2 * pr - 1)) + (w - (2 * q - 1));          // this pixel's position inside that window
+        const int64_t o = (((int64_t)img * 56 + pr) * 56 + q) * 64 + cg * 8;
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + o));
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(gy + o));
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float o = (j & 1) ? __uint_as_float(u[j >> 1] & 0xFFFF0000u) : __uint_as_float(u[j >> 1] << 16);
-              if (o > xv[j] || (earlier && o == xv[j])) is_max &= ~(1u << j);
-            }
-          }
-        }
-        if (is_max) {
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(gy + (((int64_t)img * 56 + pr) * 56 + q) * 64 + cg * 8));
-          const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (is_max & (1u << j)) g[j] += (j & 1) ? __uint_as_float(u[j >> 1] & 0xFFFF0000u) : __uint_as_float(u[j >> 1] << 16);
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t a = ((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xFFu;
+          if (a == me) g[j] += (j & 1) ? __uint_as_float(u[j >> 1] & 0xFFFF0000u) : __uint_as_float(u[j >> 1] << 16);
         }
       }
-    __align__(16) __nv_bfloat16 o[8];
+    __align__(16) __nv_bfloat16 ov[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16_rn(g[j]);
-    *reinterpret_cast<uint4*>(gx + pix * 64 + cg * 8) = *reinterpret_cast<const uint4*>(o);
+    for (int j = 0; j < 8; ++j) ov[j] = __float2bfloat16_rn(g[j]);
+    *reinterpret_cast<uint4*>(gx + pix * 64 + cg * 8) = *reinterpret_cast<const uint4*>(ov);
   }
 }
 
@@ -1035,7 +1029,7 @@ static int tape_reserve(airpose_net* h, int t, int n) {
   if (tp.cap < n) {
     for (auto p : tp.z) cudaFree(p);
     for (auto p : tp.y) cudaFree(p);
-    cudaFree(tp.pooled); cudaFree(tp.stats); cudaFree(tp.stats1);
+    cudaFree(tp.pooled); cudaFree(tp.pool_idx); cudaFree(tp.stats); cudaFree(tp.stats1);
     tp.z.assign(io.size(), nullptr); tp.y.assign(io.size(), nullptr);
     for (size_t i = 0; i < io.size(); ++i) {
       const size_t elems = (size_t)n * io[i].Hout * io[i].Hout * h->specs[i].cout;
@@ -1043,6 +1037,7 @@ static int tape_reserve(airpose_net* h, int t, int n) {
       AP_CHECK_CUDA(cudaMalloc((void**)&tp.y[i], elems * 2));
     }
     AP_CHECK_CUDA(cudaMalloc((void**)&tp.pooled, (size_t)n * 56 * 56 * 64 * 2));
+    AP_CHECK_CUDA(cudaMalloc((void**)&tp.pool_idx, (size_t)n * 56 * 56 * 64));
     size_t ns = 0;
     for (const ConvSpec& s : h->specs) ns += 2 * s.cout;
     AP_CHECK_CUDA(cudaMalloc((void**)&tp.stats, ns * sizeof(float)));
@@ -1086,7 +1081,7 @@ static int backbone_fwd_train_tape(airpose_net* h, const float* x, const float* 
     if (enable_tma_epilogue(&L)) return 1;
     if (launch_gemm(L, st)) return 1;
     if (bn_views(0, (int64_t)nt * 112 * 112, 64, nullptr, 1)) return 1;
-    maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64((int64_t)nt * 56 * 56 * 8, 256), 148 * 16), 256, 0, st>>>(tp.y[0], nt, tp.pooled);
+    maxpool_kernel<<<(unsigned)std::min<int64_t>(ceil_div64((int64_t)nt * 56 * 56 * 8, 256), 148 * 16), 256, 0, st>>>(tp.y[0], nt, tp.pooled, tp.pool_idx);
     AP_LAUNCH_CHECK();
   }
   auto src = [&](int s) -> const __nv_bfloat16* { return s == -1 ? tp.pooled : tp.y[s]; };
@@ -1283,7 +1278,7 @@ static int backbone_bwd_train_impl(airpose_net_t* h, const float* x, const float
     // G now holds dL/d(block input)
   }
   // stem: max-pool backward, bn1 + ReLU backward, weight gradient of the 7x7 conv (no data gradient: the input is the image)
-  maxpool_bwd_kernel<<<ew_grid((int64_t)n * 112 * 112 * 8), 256, 0, st>>>(tp.y[0], G, n, G2);
+  maxpool_bwd_kernel<<<ew_grid((int64_t)n * 112 * 112 * 8), 256, 0, st>>>(tp.pool_idx, G, n, G2);
   AP_LAUNCH_CHECK();
   const int64_t M0 = (int64_t)n * 112 * 112;
   if (bn_bwd(h, tp, 0, M0, bn, g, G2, true, DZ, nullptr, st)) return 1;
