@@ -175,6 +175,9 @@ SYMBOLS = {
     "airpose_rot6d_to_rotmat_bwd_strided": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                                       C.c_int64, C.c_void_p]),
     "airpose_j14_gather": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_i32_p, C.c_void_p, C.c_void_p]),
+    "airpose_rotmat_to_angle_axis": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "airpose_angle_axis_to_rotmat": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "airpose_mean_distance": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "airpose_preprocess_bgr8": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, c_float_p, c_float_p, C.c_void_p, C.c_void_p]),
     "airpose_preprocess_crop_resize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                                  c_float_p, c_float_p, C.c_void_p, C.c_void_p]),

@@ -27,6 +27,59 @@ LOSS_NAMES = ("loss", "loss_regr_trans", "loss_keypoints", "loss_keypoints_3d", 
               "loss_regr_pose", "loss_regul_betas")           # order of the reference's `losses` dict (:152-159)
 
 
+def rotation_matrix_to_angle_axis(rotation_matrix):
+    """``tgm.rotation_matrix_to_angle_axis`` as the reference calls it (copenet_twoview.py:323-326): [N,3,4] (or [N,3,3]) -> [N,3].
+    torchgeometry 0.1.2 is absent offline: the arithmetic is restated in csrc/testmode.cu, PARITY UNPINNED."""
+    if rotation_matrix.device.type != "cuda":
+        raise _lib.AirposeError("airpose_b200.rotation_matrix_to_angle_axis runs on CUDA only; there is no CPU path")
+    if rotation_matrix.dim() != 3 or rotation_matrix.shape[1] != 3 or rotation_matrix.shape[2] not in (3, 4):
+        raise ValueError("Input size must be a N x 3 x 4 (or N x 3 x 3) tensor. Got {}".format(tuple(rotation_matrix.shape)))
+    R = rotation_matrix.detach().to(torch.float32).contiguous()
+    n, row = R.shape[0], R.shape[2]
+    out = torch.empty(n, 3, device=R.device, dtype=torch.float32)
+    if n:
+        with torch.cuda.device(R.device):
+            _lib.check(_lib.load().airpose_rotmat_to_angle_axis(R.data_ptr(), n, 3 * row, row, out.data_ptr(), _lib.current_stream()),
+                       "airpose_rotmat_to_angle_axis")
+    return out
+
+
+def angle_axis_to_rotation_matrix(angle_axis):
+    """``tgm.angle_axis_to_rotation_matrix`` (copenet_twoview.py:558-559): [N,3] -> [N,4,4] homogeneous, like torchgeometry returns it
+    (the 3x3 block comes from the kernel).  PARITY UNPINNED, as above."""
+    if angle_axis.device.type != "cuda":
+        raise _lib.AirposeError("airpose_b200.angle_axis_to_rotation_matrix runs on CUDA only; there is no CPU path")
+    aa = angle_axis.detach().to(torch.float32).reshape(-1, 3).contiguous()
+    n = aa.shape[0]
+    R = torch.empty(n, 3, 3, device=aa.device, dtype=torch.float32)
+    if n:
+        with torch.cuda.device(aa.device):
+            _lib.check(_lib.load().airpose_angle_axis_to_rotmat(aa.data_ptr(), n, R.data_ptr(), _lib.current_stream()),
+                       "airpose_angle_axis_to_rotmat")
+    out = torch.eye(4, device=aa.device, dtype=torch.float32).repeat(n, 1, 1)
+    out[:, :3, :3] = R
+    return out
+
+
+def mean_distance(a, b, points_used=None):
+    """mean over items and their first ``points_used`` points of ||a - b||: [N,P,3] x [N,P,3] -> 0-d device tensor.  MPJPE with
+    ``points_used=22`` (copenet_twoview.py:583-586), the mean position error for [N,3] inputs (:541-551)."""
+    if a.device.type != "cuda":
+        raise _lib.AirposeError("airpose_b200.mean_distance runs on CUDA only; there is no CPU path")
+    a = a.detach().to(torch.float32).contiguous()
+    b = b.detach().to(device=a.device, dtype=torch.float32).contiguous()
+    if a.shape != b.shape or a.shape[-1] != 3:
+        raise ValueError("mean_distance expects two [N,P,3] (or [N,3]) tensors of the same shape")
+    if a.dim() == 2:
+        a, b = a[:, None], b[:, None]
+    n, per = a.shape[0], a.shape[1]
+    out = torch.zeros(1, device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().airpose_mean_distance(a.data_ptr(), b.data_ptr(), n, per, int(points_used or per), out.data_ptr(),
+                                                     _lib.current_stream()), "airpose_mean_distance")
+    return out[0]
+
+
 class copenet_twoview(nn.Module):
     """``hparams`` needs: copenet_home-style paths are replaced by explicit ones:
     ``smpl_mean_params`` (npz path), ``smplx_model_dir``, ``batch_size``, ``val_batch_size``,
@@ -175,7 +228,7 @@ class copenet_twoview(nn.Module):
         ``copenet.forward`` in train() mode + ``SMPLX.forward``, see INTEGRATION.md.)"""
         out = self.fwd_pass(input_batch)
         if is_test:
-            loss, losses = None, None
+            return self._test_outputs(input_batch, out), None, None
         else:
             loss, losses = self.get_loss(input_batch, out["pred_smpltrans0"], out["pred_smpltrans1"], out["pred_rotmat0"],
                                          out["pred_rotmat1"], out["pred_betas0"], out["pred_betas1"],
@@ -185,6 +238,57 @@ class copenet_twoview(nn.Module):
                   "pred_smpltrans0": out["pred_smpltrans0"], "pred_smpltrans1": out["pred_smpltrans1"],
                   "in_smpltrans0": out["in_smpltrans0"], "in_smpltrans1": out["in_smpltrans1"]}
         return output, losses, loss
+
+    @torch.no_grad()
+    def _test_outputs(self, input_batch, out):
+        """The ``is_test`` branch of fwd_pass_and_loss (copenet_twoview.py:258-279,318-350): the extra SMPL-X passes with zero
+        betas placed at the INPUT translation with identity orientation, angle-axis forms of the predicted and ground-truth
+        rotations, and the reference's output dict (every entry ``.detach().cpu()`` like the reference's)."""
+        B = out["pred_pose0"].shape[0]
+        dev = out["pred_pose0"].device
+        cpu = lambda t_: t_.detach().cpu()
+        pad = torch.zeros(B, 22, 3, 1, device=dev)
+        aa = lambda R: rotation_matrix_to_angle_axis(torch.cat([R, pad], dim=3).view(-1, 3, 4)).view(B, 22, 3)       # :323-326
+        res = {}
+        for v in (0, 1):
+            rot = out["pred_rotmat%d" % v]
+            # :258-279 zero betas, predicted body pose, identity global orientation, then [I | in_smpltrans]
+            _, cam = self.smplx.forward_camera(betas=torch.zeros(B, 10, device=dev), body_pose=rot[:, 1:], global_orient=None, transl=None,
+                                               pose2rot=False, root_R=torch.eye(3, device=dev).expand(B, 3, 3).contiguous(),
+                                               root_t=out["in_smpltrans%d" % v])
+            gt_rot = torch.cat([input_batch["smplorient_rel%d" % v], input_batch["smplpose_rotmat"]], dim=1).to(dev).float()
+            res.update({"pred_vertices_cam%d" % v: cpu(out["pred_vertices_cam%d" % v]), "pred_vertices_cam_in%d" % v: cpu(cam["vertices_cam"]),
+                        "pred_j2d_cam%d" % v: cpu(out["pred_joints_2d_cam%d" % v]), "pred_j3d_cam%d" % v: cpu(out["pred_joints_cam%d" % v]),
+                        "pred_smpltrans%d" % v: cpu(out["pred_smpltrans%d" % v]), "pred_angles%d" % v: cpu(aa(rot)),
+                        "pred_betas%d" % v: cpu(out["pred_betas%d" % v]), "in_smpltrans%d" % v: cpu(out["in_smpltrans%d" % v]),
+                        "gt_angles%d" % v: cpu(aa(gt_rot)), "gt_smpltrans%d" % v: cpu(input_batch["smpltrans_rel%d" % v]),
+                        "smplorient_rel%d" % v: cpu(input_batch["smplorient_rel%d" % v])})
+        res["smplpose_rotmat"] = cpu(input_batch["smplpose_rotmat"])
+        return res
+
+    def test_step(self, batch, batch_idx=0, dset_idx=0):
+        """copenet_twoview.test_step (:537-546)."""
+        output, losses, loss = self.fwd_pass_and_loss(batch, is_val=True, is_test=True)
+        return {"test_loss": loss, "output": output}
+
+    @torch.no_grad()
+    def test_metrics(self, outputs):
+        """The numbers ``test_epoch_end`` prints (copenet_twoview.py:548-586) for ONE list of ``test_step`` results: the mean
+        position errors of the two views and the MPJPE over the first 22 joints between the SMPL-X meshes (zero betas -- the
+        module's own parameter, :575-582) of the ground-truth and of the predicted rotations, the latter taken through
+        angle-axis and back exactly as the reference does (:556-559).  Reductions run on the device; returns a dict of floats."""
+        dev = self.smplx.v_template.device
+        cat = lambda k: torch.cat([o["output"][k].to(dev) for o in outputs])
+        res = {"mpe0": float(mean_distance(cat("pred_smpltrans0"), cat("gt_smpltrans0"))),
+               "mpe1": float(mean_distance(cat("pred_smpltrans1"), cat("gt_smpltrans1")))}
+        body_gt = cat("smplpose_rotmat")
+        N = body_gt.shape[0]
+        for v in (0, 1):
+            pred = angle_axis_to_rotation_matrix(cat("pred_angles%d" % v).view(-1, 3)).view(N, 22, 4, 4)[:, :, :3, :3].contiguous()
+            j_gt = self.smplx.forward(body_pose=body_gt, global_orient=cat("smplorient_rel%d" % v), pose2rot=False).joints
+            j_pr = self.smplx.forward(body_pose=pred[:, 1:22].contiguous(), global_orient=pred[:, 0:1].contiguous(), pose2rot=False).joints
+            res["mpjpe%d" % v] = float(mean_distance(j_gt, j_pr, points_used=22))
+        return res
 
     @torch.no_grad()
     def loss_and_head_backward(self, input_batch, out):

@@ -318,7 +318,15 @@ class SMPLX(nn.Module):
             shape_comp = torch.cat([betas_t, self._f32c(self.expression, device)], dim=-1)
         else:
             shape_comp = betas_t          # zero expression contributes exactly nothing (body_models.py:943)
-        B = max(betas_t.shape[0], go.shape[0] if go is not None else 0, bp.shape[0] if bp is not None else 0)
+        pose_B = max(go.shape[0] if go is not None else 0, bp.shape[0] if bp is not None else 0)
+        if betas is None and pose_B > 0 and betas_t.shape[0] not in (1, pose_B):
+            # the reduced call of copenet_twoview.py:575-582 falls back to the module's own betas Parameter, created for
+            # ``batch_size`` meshes; it is all zeros there, so any runtime batch can be served (the reference needs them equal)
+            if not (self._is_zero("betas") and (expression is not None or self._is_zero("expression"))):
+                raise ValueError("the module's betas Parameter holds {} rows, the poses {}".format(betas_t.shape[0], pose_B))
+            shape_comp = torch.zeros(pose_B, shape_comp.shape[1], device=device, dtype=torch.float32)
+            betas_t = shape_comp
+        B = max(betas_t.shape[0], pose_B)
         if shape_comp.shape[0] != B:
             shape_comp = shape_comp.expand(B, -1).contiguous()
 

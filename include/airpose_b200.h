@@ -151,6 +151,21 @@ int airpose_j14_gather(const float* joints, int32_t batch, int32_t num_joints, c
                        float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Test-mode outputs and metrics (copenet/src/copenet/copenet_twoview.py:323-326,541-559,583-586)
+ * The two conversions restate torchgeometry 0.1.2 (requirements.txt), which is absent offline: PARITY UNPINNED, checked by
+ * known-answer identities only (csrc/testmode.cu).
+ * ---------------------------------------------------------------------------------- */
+/* tgm.rotation_matrix_to_angle_axis: n row-major rotation matrices, matrix i at R + i*mat_stride, its rows row_stride floats
+ * apart ((9, 3) for [n,3,3]; (12, 4) for the reference's [n,3,4] input, whose 4th column is ignored) -> out [n,3]. */
+int airpose_rotmat_to_angle_axis(const float* R, int64_t n, int32_t mat_stride, int32_t row_stride, float* out, void* stream);
+/* tgm.angle_axis_to_rotation_matrix (the 3x3 block of the 4x4 it returns): aa [n,3] -> R [n,3,3]. */
+int airpose_angle_axis_to_rotmat(const float* aa, int64_t n, float* R, void* stream);
+/* mean over items and over the first points_used of each item's points_per_item 3-vectors of ||a - b||_2 -> out[0]:
+ * MPJPE with (127, 22) (copenet_twoview.py:583-586), the mean position error with (1, 1) (:541-551).  Deterministic. */
+int airpose_mean_distance(const float* a, const float* b, int64_t items, int32_t points_per_item, int32_t points_used, float* out,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Input preprocessing (the step right before the path)
  * ---------------------------------------------------------------------------------- */
 /* The drone server's stage-0 conversion (catkin_ws/.../airpose_server/server.py:93-98): u8 BGR [n,size,size,3] (device) ->

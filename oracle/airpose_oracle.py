@@ -536,3 +536,82 @@ def dataset_preprocess(frame_bgr_u8: np.ndarray, rect, size: int = 224):
     chw = img.transpose(2, 0, 1).astype(np.float32)
     chw = (chw - IMAGENET_MEAN[:, None, None]) / IMAGENET_STD[:, None, None]
     return chw.astype(np.float32), scale, pad
+
+
+# --------------------------------------------------------------------------------------
+# test-mode conversions and metrics  --  PARITY UNPINNED
+# torchgeometry==0.1.2 (requirements.txt) is not under /root/reference and not installable offline; the two functions below
+# restate the published torchgeometry/core/conversions.py of that version, reading `1 - mask` on its boolean masks as logical
+# NOT (the literal expression raises under torch >= 1.2).  Pinned by known-answer identities only (tests/test_oracle_golden.py).
+# --------------------------------------------------------------------------------------
+def tgm_rotation_matrix_to_angle_axis(rotation_matrix, eps=1e-6):
+    """tgm.rotation_matrix_to_angle_axis on [N,3,4] / [N,3,3] (copenet_twoview.py:323-326): matrix -> quaternion (w,x,y,z)
+    through the transposed matrix and the four-branch trace test, quaternion -> angle-axis with the atan2 form."""
+    R = np.asarray(rotation_matrix, np.float32)[:, :3, :3]
+    t = np.transpose(R, (0, 2, 1))
+    d2 = t[:, 2, 2] < eps
+    d0_d1 = t[:, 0, 0] > t[:, 1, 1]
+    d0_nd1 = t[:, 0, 0] < -t[:, 1, 1]
+    t0 = 1 + t[:, 0, 0] - t[:, 1, 1] - t[:, 2, 2]
+    q0 = np.stack([t[:, 1, 2] - t[:, 2, 1], t0, t[:, 0, 1] + t[:, 1, 0], t[:, 2, 0] + t[:, 0, 2]], -1)
+    t1 = 1 - t[:, 0, 0] + t[:, 1, 1] - t[:, 2, 2]
+    q1 = np.stack([t[:, 2, 0] - t[:, 0, 2], t[:, 0, 1] + t[:, 1, 0], t1, t[:, 1, 2] + t[:, 2, 1]], -1)
+    t2 = 1 - t[:, 0, 0] - t[:, 1, 1] + t[:, 2, 2]
+    q2 = np.stack([t[:, 0, 1] - t[:, 1, 0], t[:, 2, 0] + t[:, 0, 2], t[:, 1, 2] + t[:, 2, 1], t2], -1)
+    t3 = 1 + t[:, 0, 0] + t[:, 1, 1] + t[:, 2, 2]
+    q3 = np.stack([t3, t[:, 1, 2] - t[:, 2, 1], t[:, 2, 0] - t[:, 0, 2], t[:, 0, 1] - t[:, 1, 0]], -1)
+    c0, c1, c2, c3 = d2 & d0_d1, d2 & ~d0_d1, ~d2 & d0_nd1, ~d2 & ~d0_nd1
+    f = lambda m: m[:, None].astype(np.float32)
+    q = q0 * f(c0) + q1 * f(c1) + q2 * f(c2) + q3 * f(c3)
+    q = q / np.sqrt(t0[:, None] * f(c0) + t1[:, None] * f(c1) + t2[:, None] * f(c2) + t3[:, None] * f(c3))
+    q = q * np.float32(0.5)
+    sin2 = q[:, 1] ** 2 + q[:, 2] ** 2 + q[:, 3] ** 2
+    sn = np.sqrt(sin2)
+    two_theta = 2.0 * np.where(q[:, 0] < 0.0, np.arctan2(-sn, -q[:, 0]), np.arctan2(sn, q[:, 0]))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        k = np.where(sin2 > 0.0, two_theta / sn, 2.0)
+    return (q[:, 1:] * k[:, None]).astype(np.float32)
+
+
+def tgm_angle_axis_to_rotation_matrix(angle_axis, eps=1e-6):
+    """tgm.angle_axis_to_rotation_matrix (copenet_twoview.py:558-559): [N,3] -> [N,4,4]; Rodrigues above theta^2 = 1e-6 (axis
+    = aa / (theta + 1e-6)), first-order Taylor below."""
+    aa = np.asarray(angle_axis, np.float32).reshape(-1, 3)
+    theta2 = (aa * aa).sum(1)
+    theta = np.sqrt(theta2)
+    w = aa / (theta + np.float32(eps))[:, None]
+    wx, wy, wz = w[:, 0], w[:, 1], w[:, 2]
+    c, s_ = np.cos(theta), np.sin(theta)
+    k = 1 - c
+    normal = np.stack([c + wx * wx * k, wx * wy * k - wz * s_, wy * s_ + wx * wz * k,
+                       wz * s_ + wx * wy * k, c + wy * wy * k, -wx * s_ + wy * wz * k,
+                       -wy * s_ + wx * wz * k, wx * s_ + wy * wz * k, c + wz * wz * k], 1).reshape(-1, 3, 3)
+    one = np.ones_like(theta)
+    taylor = np.stack([one, -aa[:, 2], aa[:, 1], aa[:, 2], one, -aa[:, 0], -aa[:, 1], aa[:, 0], one], 1).reshape(-1, 3, 3)
+    out = np.tile(np.eye(4, dtype=np.float32), (aa.shape[0], 1, 1))
+    out[:, :3, :3] = np.where((theta2 > eps)[:, None, None], normal, taylor)
+    return out.astype(np.float32)
+
+
+def mean_distance(a, b, points_used=None):
+    """np.mean(np.sqrt(np.sum((a - b) ** 2, -1))[:, :points_used])  (copenet_twoview.py:541-551,583-586)."""
+    d = np.sqrt(np.sum((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2, -1))
+    if d.ndim == 1:
+        return float(d.mean())
+    return float(d[:, :points_used].mean())
+
+
+def test_mode_outputs(sd, m: SmplxModel, batch, out):
+    """The extra outputs of the is_test branch (copenet_twoview.py:258-279,323-326) from ``twoview_forward``'s result."""
+    b = out["pred_pose0"].shape[0]
+    res = {}
+    for v in (0, 1):
+        R = out["pred_rotmat%d" % v]
+        verts, joints = smplx_forward(m, np.zeros((b, 10), np.float32), R[:, 1:], transl=np.zeros((b, 3), np.float32))
+        init = np.tile(np.array([0, 0, 10], dtype=np.float32), (b, 1))
+        tm = np.concatenate([np.tile(np.eye(3, dtype=np.float32), (b, 1, 1)), init[:, :, None]], axis=2)
+        res["pred_vertices_cam_in%d" % v] = transform_smpl(tm, verts, joints)[0]
+        res["pred_angles%d" % v] = tgm_rotation_matrix_to_angle_axis(R.reshape(-1, 3, 3)).reshape(b, 22, 3)
+        gt = np.concatenate([batch["smplorient_rel%d" % v], batch["smplpose_rotmat"]], axis=1)
+        res["gt_angles%d" % v] = tgm_rotation_matrix_to_angle_axis(gt.reshape(-1, 3, 3)).reshape(b, 22, 3)
+    return res

@@ -1555,3 +1555,79 @@ def test_empty_and_single_inputs(net_gpu, smplx_gpu):
         net_gpu.forward_feat_ext(z(2, 3, 200, 200))
     with pytest.raises(NotImplementedError):
         smplx_gpu.forward(betas=z(1, 10), body_pose=z(1, 63), pose2rot=True)
+
+
+# ----------------------------------------------------------------------------- test-mode outputs and metrics
+def test_test_mode_conversions_and_metrics():
+    """airpose_rotmat_to_angle_axis / airpose_angle_axis_to_rotmat / airpose_mean_distance against the oracle's restatement of
+    torchgeometry 0.1.2 (parity unpinned: pinned by scipy-checked known answers on the CPU side) -- fp32 agreement, all four
+    quaternion branches, the [N,3,4] layout the reference passes, round trips, empty inputs."""
+    from airpose_b200.copenet_twoview import angle_axis_to_rotation_matrix, mean_distance, rotation_matrix_to_angle_axis
+    from test_oracle_golden import _random_rotations
+    rv, R = _random_rotations(5000, 1)
+    aa = rotation_matrix_to_angle_axis(t(R)).cpu().numpy()
+    ref = orc.tgm_rotation_matrix_to_angle_axis(R)
+    assert np.abs(aa - ref).max() < 5e-5 and np.abs(aa - rv).max() < 3e-4
+    R34 = np.concatenate([R, np.zeros((5000, 3, 1), np.float32)], 2)
+    assert np.array_equal(rotation_matrix_to_angle_axis(t(R34)).cpu().numpy(), aa)
+    R4 = angle_axis_to_rotation_matrix(t(rv)).cpu().numpy()
+    assert R4.shape == (5000, 4, 4)
+    assert np.abs(R4 - orc.tgm_angle_axis_to_rotation_matrix(rv)).max() < 2e-6
+    back = rotation_matrix_to_angle_axis(t(np.ascontiguousarray(R4[:, :3, :3]))).cpu().numpy()
+    ok = np.linalg.norm(rv, axis=1) < 2.5
+    assert np.abs(back - rv)[ok].max() < 5e-5
+    assert tuple(rotation_matrix_to_angle_axis(torch.zeros(0, 3, 4, device=DEV)).shape) == (0, 3)
+    rng = np.random.default_rng(4)
+    a, b = rng.standard_normal((37, 127, 3)).astype(np.float32), rng.standard_normal((37, 127, 3)).astype(np.float32)
+    assert float(mean_distance(t(a), t(b), points_used=22)) == pytest.approx(orc.mean_distance(a, b, 22), rel=1e-6)
+    assert float(mean_distance(t(a[:, 0]), t(b[:, 0]))) == pytest.approx(orc.mean_distance(a[:, 0], b[:, 0]), rel=1e-6)
+
+
+def test_fwd_pass_and_loss_test_mode(tmp_path, smplx_dir, smplx_oracle, smplx_data, net_state):
+    """fwd_pass_and_loss(is_test=True) (copenet_twoview.py:258-279,318-350): the reference's output dict -- same keys, CPU
+    tensors -- with the zero-beta meshes at the input translation and the angle-axis rotations against the oracle fed with
+    the device's trunk features; then test_metrics (test_epoch_end's MPE / MPJPE, :548-586) against the same reductions done
+    in numpy over the oracle's SMPL-X."""
+    import torch_port as tp
+    mod = _loss_module(tmp_path, smplx_dir)
+    mod.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in net_state.items()})
+    mod = mod.to(DEV).eval()
+    B = 3
+    x = synthetic.make_inputs(B, 41)
+    _, m = _torch_smplx64(smplx_data)
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        gt = _synthetic_gt(tp, m, B, x)
+    finally:
+        torch.set_default_dtype(old)
+    batch = {k: t(v) for k, v in {**x, **gt}.items()}
+    step = mod.test_step(batch)
+    output = step["output"]
+    assert step["test_loss"] is None
+    assert set(output) == {"pred_vertices_cam0", "pred_vertices_cam1", "pred_vertices_cam_in0", "pred_vertices_cam_in1", "pred_j2d_cam0",
+                           "pred_j2d_cam1", "pred_j3d_cam0", "pred_j3d_cam1", "pred_smpltrans0", "pred_smpltrans1", "pred_angles0",
+                           "pred_angles1", "pred_betas0", "pred_betas1", "in_smpltrans0", "in_smpltrans1", "gt_angles0", "gt_angles1",
+                           "gt_smpltrans0", "gt_smpltrans1", "smplorient_rel0", "smplorient_rel1", "smplpose_rotmat"}
+    assert all(v.device.type == "cpu" for v in output.values())
+    xf = mod.model.forward_feat_ext_pair(batch["im0"], batch["im1"]).cpu().numpy()
+    ref = orc.twoview_forward(net_state, smplx_oracle, x, feats=(xf[:B], xf[B:]))
+    ext = orc.test_mode_outputs(net_state, smplx_oracle, gt, ref)
+    for v in (0, 1):
+        assert tuple(output["pred_angles%d" % v].shape) == (B, 22, 3)
+        assert rel_err(output["pred_vertices_cam_in%d" % v].numpy(), ext["pred_vertices_cam_in%d" % v]) < 1e-3
+        assert np.abs(output["pred_angles%d" % v].numpy() - ext["pred_angles%d" % v]).max() < 1e-3
+        assert np.abs(output["gt_angles%d" % v].numpy() - ext["gt_angles%d" % v]).max() < 5e-5
+        assert rel_err(output["pred_j3d_cam%d" % v].numpy(), ref["pred_joints_cam%d" % v]) < 1e-3
+        assert np.array_equal(output["in_smpltrans%d" % v].numpy(), np.tile(np.array([0, 0, 10], np.float32), (B, 1)))
+    # metrics over two "batches" (the same step twice), against numpy over the oracle
+    met = mod.test_metrics([step, step])
+    zero = np.zeros((B, 10), np.float32)
+    for v in (0, 1):
+        mpe = orc.mean_distance(output["pred_smpltrans%d" % v].numpy(), gt["smpltrans_rel%d" % v])
+        assert met["mpe%d" % v] == pytest.approx(mpe, rel=1e-5)
+        Rp = orc.tgm_angle_axis_to_rotation_matrix(output["pred_angles%d" % v].numpy().reshape(-1, 3)).reshape(B, 22, 4, 4)[:, :, :3, :3]
+        _, j_pr = orc.smplx_forward(smplx_oracle, zero, Rp[:, 1:], global_orient=Rp[:, :1])
+        _, j_gt = orc.smplx_forward(smplx_oracle, zero, gt["smplpose_rotmat"], global_orient=gt["smplorient_rel%d" % v])
+        assert met["mpjpe%d" % v] == pytest.approx(orc.mean_distance(j_gt, j_pr, 22), rel=1e-3)
+    print("test metrics:", met)

@@ -222,3 +222,44 @@ def test_dataset_preprocessing_matches_reference(golden_preprocess):
         # the letterbox is exactly (0 - mean) / std
         if pad[0] > 0:
             assert np.array_equal(img[:, :, 0], np.broadcast_to(((0 - orc.IMAGENET_MEAN) / orc.IMAGENET_STD)[:, None], (3, 224)))
+
+
+# ----------------------------------------------------------------------------- test-mode conversions (parity unpinned)
+def _random_rotations(n, seed, max_angle=3.1):
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(seed)
+    axis = rng.standard_normal((n, 3))
+    axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+    angle = rng.uniform(0.0, max_angle, size=(n, 1))
+    rv = axis * angle
+    return rv.astype(np.float32), Rotation.from_rotvec(rv).as_matrix().astype(np.float32)
+
+
+def test_tgm_conversions_known_answers():
+    """torchgeometry 0.1.2 is absent offline, so the restated rotation_matrix_to_angle_axis / angle_axis_to_rotation_matrix
+    (copenet_twoview.py:323-326,558-559) are pinned by known answers only: identity, a quarter turn about z, every branch of
+    the quaternion selection, and agreement with an independent implementation (scipy Rotation) on random rotations."""
+    eye = np.eye(3, dtype=np.float32)[None]
+    assert np.array_equal(orc.tgm_rotation_matrix_to_angle_axis(eye), np.zeros((1, 3), np.float32))
+    rz = np.array([[[0, -1, 0], [1, 0, 0], [0, 0, 1]]], np.float32)
+    assert np.allclose(orc.tgm_rotation_matrix_to_angle_axis(rz), [[0, 0, np.pi / 2]], atol=1e-6)
+    # the reference hands over [N,3,4] with a zero fourth column
+    assert np.array_equal(orc.tgm_rotation_matrix_to_angle_axis(np.concatenate([rz, np.zeros((1, 3, 1), np.float32)], 2)),
+                          orc.tgm_rotation_matrix_to_angle_axis(rz))
+    rv, R = _random_rotations(4000, 0)
+    t = np.transpose(R, (0, 2, 1))
+    d2, d01, d0n1 = t[:, 2, 2] < 1e-6, t[:, 0, 0] > t[:, 1, 1], t[:, 0, 0] < -t[:, 1, 1]
+    for m in (d2 & d01, d2 & ~d01, ~d2 & d0n1, ~d2 & ~d0n1):
+        assert m.sum() > 50                                   # all four branches are exercised
+    aa = orc.tgm_rotation_matrix_to_angle_axis(R)
+    assert np.abs(aa - rv).max() < 2e-4                      # fp32 matrix entries near pi lose digits in the trace test
+    small = np.linalg.norm(rv, axis=1) < 2.5
+    assert np.abs(aa - rv)[small].max() < 2e-5
+    R4 = orc.tgm_angle_axis_to_rotation_matrix(rv)
+    assert R4.shape == (4000, 4, 4) and np.array_equal(R4[:, 3], np.tile([0, 0, 0, 1], (4000, 1)).astype(np.float32))
+    big = np.linalg.norm(rv, axis=1) > 0.05                  # axis = aa / (theta + 1e-6): relative error 1e-6 / theta
+    assert np.abs(R4[:, :3, :3] - R)[big].max() < 5e-5
+    tiny = np.array([[1e-4, -2e-4, 3e-4]], np.float32)       # Taylor branch: I + [aa]_x
+    assert np.allclose(orc.tgm_angle_axis_to_rotation_matrix(tiny)[0, :3, :3],
+                       [[1, -3e-4, -2e-4], [3e-4, 1, -1e-4], [2e-4, 1e-4, 1]], atol=1e-9)
+    assert orc.mean_distance(np.zeros((2, 5, 3)), np.ones((2, 5, 3)), 3) == pytest.approx(np.sqrt(3.0))

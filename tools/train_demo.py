@@ -6,14 +6,12 @@ optimizer's flat gradient buffer (NCCL over NVLink).  Prints one JSON line on ra
 ranks), first/last loss, and whether the parameters are still bit-identical across ranks."""
 import argparse, json, os, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import numpy as np
 import torch
 import torch.distributed as dist
 from argparse import Namespace
 from airpose_b200 import parallel, synthetic
 from airpose_b200.copenet_twoview import copenet_twoview
-import airpose_oracle as orc
 
 
 def main():
@@ -41,10 +39,12 @@ def main():
     # global synthetic batch, sharded by pair (no overlap between ranks); GT = SMPL-X forward of an independent sample
     x = synthetic.make_inputs(B * world, 123)
     li = synthetic.make_lbs_inputs(B * world, seed=9)
-    sm = orc.SmplxModel(synthetic.make_smplx_model(0))
     rng = np.random.default_rng(5)
     b0, b1 = parallel.shard_range(B * world, world, rank)
-    gv, gj = orc.smplx_forward(sm, li["betas"][b0:b1], li["body_pose"][b0:b1])
+    with torch.no_grad():      # ground-truth meshes: the SMPL-X forward (the product's own kernels) of an independent seeded sample
+        gt_out = mod.smplx.forward(betas=torch.from_numpy(li["betas"][b0:b1]).to(dev), body_pose=torch.from_numpy(li["body_pose"][b0:b1]).to(dev),
+                                   pose2rot=False)
+    gv, gj = gt_out.vertices.cpu().numpy(), gt_out.joints.cpu().numpy()
     r6 = lambda: synthetic.rot6d_to_rotmat_np(np.array([1, 0, 0, 1, 0, 0], np.float32) + rng.standard_normal((B, 6)).astype(np.float32) * 0.3)[:, None]
     gt = {"smplpose_rotmat": li["body_pose"][b0:b1], "smplorient_rel0": r6(), "smplorient_rel1": r6(), "smpl_vertices": gv[:, None],
           "smpl_joints": gj[:, None], "smpl_joints_2d0": (rng.standard_normal((B, 1, 127, 2)) * 50 + 500).astype(np.float32),
