@@ -338,6 +338,14 @@ extern "C" int airpose_net_destroy(airpose_net_t* h) {
     cudaFree(h->colS[s]); cudaFree(h->stem_outS[s]);
     for (int i = 0; i < 4; ++i) cudaFree(h->actS[s][i]);
   }
+  // training tapes and the scratch of the backward pass
+  for (auto& tp : h->tape) {
+    for (auto p : tp.z) cudaFree(p);
+    for (auto p : tp.y) cudaFree(p);
+    cudaFree(tp.pooled); cudaFree(tp.pool_idx); cudaFree(tp.stats); cudaFree(tp.stats1);
+  }
+  for (auto p : h->bw) cudaFree(p);
+  cudaFree(h->bw_t0); cudaFree(h->bw_t1); cudaFree(h->bw_w); cudaFree(h->bw_coef);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
