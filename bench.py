@@ -137,6 +137,8 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: airpose_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
