@@ -99,3 +99,26 @@ def test_hmr_state_dict_keys_match_reference_layout(tmp_path):
     net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()}, strict=True)
     with pytest.raises(_lib.AirposeError):
         net.eval()(torch.zeros(1, 3, 224, 224))
+
+
+def test_server_wire_constants_and_letterbox_geometry():
+    """Host logic of the two 'next' rows that needs no GPU: the drone server's message sizes (server.py:37-39) and reply
+    lengths, the checkpoint-key fix-up (server.py:16-22), and the letterbox geometry of utils.resize_with_pad
+    (utils.py:218-229) against the values the reference itself returned for the golden crops."""
+    import airpose_oracle as orc
+    from airpose_b200 import server
+    from airpose_b200.preprocess import letterbox_geometry
+    assert (server.SIZE, server.BUFFERSIZE, server.BUFFERSIZE_STAGES) == (224, 150541, 545)
+    assert (server.BUFFERSIZE, server.BUFFERSIZE_STAGES) == (orc.SERVER_BUFFERSIZE, orc.SERVER_BUFFERSIZE_STAGES)
+    assert server.REPLY_FLOATS == (136, 136, 145)
+    sd = server.fix_state_dict({"model.fc1.weight": 1, "model.model.x": 2, "smplx.betas": 3})
+    assert list(sd) == ["fc1.weight", "model.x", "smplx.betas"]
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "preprocess.npz")))
+    for i, case in enumerate(g["cases"]):
+        _, _, _, y0, y1, x0, x1 = (int(v) for v in case)
+        scale, (dw, dh), pad = letterbox_geometry(y1 - y0, x1 - x0)
+        assert scale == float(g["scale_%d" % i]) and pad == g["pad_%d" % i].tolist()
+        assert max(dw, dh) in (223, 224) and min(pad) >= 0
+    with pytest.raises(_lib.AirposeError):          # CUDA only, no CPU path
+        import tempfile
+        server.StagedServer(server.getmodel(synthetic.write_mean_params(os.path.join(tempfile.mkdtemp(), "smpl_mean_params.npz"))), device="cpu")
