@@ -137,8 +137,10 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: airpose_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # rank 0 prints ONE JSON line: this image exports NCCL_DEBUG=VERSION, which makes NCCL print "NCCL version ..." on stdout
+    # at communicator creation (NCCL_DEBUG_FILE does not catch it).  Any other setting (WARN, INFO) is the caller's choice.
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ.pop("NCCL_DEBUG")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
