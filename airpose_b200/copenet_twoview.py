@@ -23,6 +23,10 @@ TRANS_SCALE = 0.05                   # copenet_twoview.py:199-203
 LOSS_WEIGHTS = {"shape_loss_weight": 50.0, "keypoint2d_loss_weight": 0.002, "keypoint3d_loss_weight": 1.0,
                 "limbs3d_loss_weight": 3.0, "limbstheta_loss_weight": 1.0, "trans_loss_weight": 10.0,
                 "rootrot_loss_weight": 1.0, "pose_loss_weight": 50.0, "beta_loss_weight": 1.0}
+# keys of the output dict of fwd_pass_and_loss(is_test=True) (copenet_twoview.py:328-350)
+TEST_OUTPUT_KEYS = tuple(sorted(
+    [k + v for v in "01" for k in ("pred_vertices_cam", "pred_vertices_cam_in", "pred_j2d_cam", "pred_j3d_cam", "pred_smpltrans", "pred_angles",
+                                   "pred_betas", "in_smpltrans", "gt_angles", "gt_smpltrans", "smplorient_rel")] + ["smplpose_rotmat"]))
 LOSS_NAMES = ("loss", "loss_regr_trans", "loss_keypoints", "loss_keypoints_3d", "loss_regr_shape", "loss_rootrot",
               "loss_regr_pose", "loss_regul_betas")           # order of the reference's `losses` dict (:152-159)
 
