@@ -288,3 +288,29 @@ def test_test_mode_outputs_match_reference(net_state, smplx_oracle):
         assert np.array_equal(g["in_smpltrans%d" % v], np.tile(np.array([0, 0, 10], np.float32), (B, 1)))
         assert np.array_equal(g["gt_smpltrans%d" % v], x["smpltrans_rel%d" % v])
         assert ext["pred_angles%d" % v].shape == (B, 22, 3)
+
+
+def test_torch_port_train_mode_regressor_matches_reference():
+    """The training-mode regressor loop (dropout active, model_copenet.py:118-159,178-204) of the PyTorch port -- the function the
+    GPU parity tests differentiate -- against the REAL reference network run in train() mode with its dropout masks recorded
+    (tests/golden/trainmode_b2.npz, oracle/gen_golden_trainmode.py): mask-to-(iteration, view) assignment, 1/(1-p) scaling,
+    state update between the iterations."""
+    import os
+    import torch
+    import torch_port as tp
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "trainmode_b2.npz")))
+    B, iters = int(g["batch"]), int(g["iters"])
+    sd = tp.to_torch(synthetic.make_network_state(int(g["net_seed"]), dec_gain=float(g["dec_gain"])))
+    x = synthetic.make_inputs(B, int(g["in_seed"]))
+    f = lambda a: torch.from_numpy(np.asarray(a, np.float32))
+    init = torch.tensor([0.0, 0.0, 10.0]).expand(B, -1).clone() * 0.05
+    m1, m2 = f(g["kept1"]) * 2.0, f(g["kept2"]) * 2.0
+    assert tuple(m1.shape) == (iters, 2, B, 1024) and 0.4 < float(g["kept1"].mean()) < 0.6
+    with torch.no_grad():
+        p0, s0, p1, s1 = tp.ief_train(sd, f(g["xf0"]), f(g["xf1"]), f(x["bb0"]), f(x["bb1"]), init, init, m1, m2, iters=iters)
+    for got, key in ((p0, "pred_pose0"), (s0, "pred_betas0"), (p1, "pred_pose1"), (s1, "pred_betas1")):
+        assert rel_err(got.numpy(), g[key]) < 2e-5, key
+    # the masks matter: without them (eval semantics) the outputs differ
+    with torch.no_grad():
+        q0, _, _, _ = tp.ief_train(sd, f(g["xf0"]), f(g["xf1"]), f(x["bb0"]), f(x["bb1"]), init, init, torch.ones_like(m1), torch.ones_like(m2), iters=iters)
+    assert rel_err(q0.numpy(), g["pred_pose0"]) > 1e-4
