@@ -141,6 +141,13 @@ class ConvArgs(C.Structure):
                 ("relu", C.c_int32), ("out", C.c_void_p)]
 
 
+class BneckTailArgs(C.Structure):
+    _fields_ = [("t1", C.c_void_p), ("n", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cm", C.c_int32),
+                ("w2", C.c_void_p), ("scale2", C.c_void_p), ("shift2", C.c_void_p),
+                ("w3", C.c_void_p), ("scale3", C.c_void_p), ("shift3", C.c_void_p),
+                ("residual", C.c_void_p), ("out", C.c_void_p)]
+
+
 class LossArgs(C.Structure):
     _fields_ = ([("batch", C.c_int32), ("num_verts", C.c_int32), ("num_joints", C.c_int32),
                  ("trans0", C.c_void_p), ("trans1", C.c_void_p), ("trans_stride", C.c_int32)] +
@@ -211,6 +218,7 @@ SYMBOLS = {
     "airpose_twoview_loss": (C.c_int, [C.POINTER(LossArgs), C.c_void_p]),
     "airpose_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "airpose_conv_bf16": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
+    "airpose_bneck_tail_bf16": (C.c_int, [C.POINTER(BneckTailArgs), C.c_void_p]),
     "airpose_backbone_stem": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
 }
 

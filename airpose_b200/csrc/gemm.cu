@@ -326,6 +326,23 @@ int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, const ConvGeom& g,
   return 0;
 }
 
+int make_tmap_nhwc4d_bf16(CUtensorMap* out, const void* base, int n, int H, int W, int C, int box_w, int box_h) {
+  static EncodeTiledFn fn = (EncodeTiledFn)driver_fn("cuTensorMapEncodeTiled");
+  AP_REQUIRE(fn, "cuTensorMapEncodeTiled is not available from the driver");
+  AP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && C % 64 == 0 && box_w >= 1 && box_w <= 256 && box_h >= 1 && box_h <= 256,
+             "make_tmap_nhwc4d_bf16: bad operand (C=%d box %dx%d)", C, box_w, box_h);
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  AP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (4-d) failed with %d (n=%d H=%d W=%d C=%d box %dx%d)", (int)r, n, H, W, C,
+             box_w, box_h);
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (!n) {

@@ -67,6 +67,21 @@ int make_tmap_tiled_bf16(CUtensorMap* out, const void* base, int64_t rows, int64
 int make_tmap_im2col_bf16(CUtensorMap* out, const void* base, const ConvGeom& g, int channels_per_pixel,
                           int pixels_per_column);
 
+// Tiled 4-d map over an NHWC bf16 tensor, dims (C, W, H, N), 128-byte swizzle, box (64 channels, box_w, box_h, 1 image).
+// Boxes may overhang the tensor on every side (halo loads: zero fill; stores: clipped).
+int make_tmap_nhwc4d_bf16(CUtensorMap* out, const void* base, int n, int H, int W, int C, int box_w, int box_h);
+
+// Fused bottleneck tail (bneck.cu): conv2 3x3 + BN + ReLU -> conv3 1x1 + BN + residual + ReLU in one launch.
+struct alignas(64) TailLaunch {
+  unsigned char storage[832];      // five tensor maps + the kernel parameters (TailLaunchImpl in bneck.cu)
+  int valid = 0;
+  int pdl = 0;
+};
+bool bneck_tail_supported(int H, int W, int Cm, int Cout);
+int build_bneck_tail(TailLaunch* L, const void* t1, const void* w2, const float* scale2, const float* shift2, const void* w3,
+                     const float* scale3, const float* shift3, const void* residual, void* out, int n, int H, int W);
+int launch_bneck_tail(const TailLaunch& L, cudaStream_t stream);
+
 int pick_block_n(int M, int N, int K);
 bool prefers_stream_k(int M, int N, int K);
 bool use_tma_epilogue();   // off with AIRPOSE_NO_TMA_EPI=1 (A/B runs)

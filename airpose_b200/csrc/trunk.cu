@@ -284,6 +284,10 @@ static int env_int(const char* name, int dflt) {
   const int c = e ? atoi(e) : dflt;
   return c > 0 ? c : dflt;
 }
+static bool use_fused_tail() {          // AIRPOSE_NO_FUSED_TAIL=1: every conv as its own implicit-GEMM launch (A/B runs)
+  static const bool on = getenv("AIRPOSE_NO_FUSED_TAIL") == nullptr;
+  return on;
+}
 static int default_chunk() { return env_int("AIRPOSE_TRUNK_CHUNK", 64); }
 static int default_group() { return env_int("AIRPOSE_TRUNK_GROUP", 128); }
 constexpr size_t kStageBElems = 28 * 28 * 512;      // per image: the largest stage-B tensor (layer3 input)
@@ -454,21 +458,36 @@ static int build_blocks(airpose_net* h, int n, int l0, int l1, int H, __nv_bfloa
       const int stride = h->specs[idx + 1].stride;
       const int Ho = H / stride;
       GemmLaunch L1{}, L2{}, L3{}, LD{};
+      auto push = [&](const GemmLaunch& L) { plan->ops.push_back({0, (int)plan->gemms.size()}); plan->gemms.push_back(L); };
       if (conv_launch(h, idx, buf[a], n, H, H, nullptr, 1, buf[b], &L1)) return 1;
-      if (conv_launch(h, idx + 1, buf[b], n, H, H, nullptr, 1, buf[c], &L2)) return 1;
-      plan->gemms.push_back(L1);
-      plan->gemms.push_back(L2);
+      push(L1);
       const __nv_bfloat16* res = buf[a];
       if (down) {
         if (conv_launch(h, idx + 3, buf[a], n, H, H, nullptr, 0, buf[d], &LD)) return 1;
-        plan->gemms.push_back(LD);
+        push(LD);
         res = buf[d];
       }
-      __nv_bfloat16* out = (last && final_out) ? final_out : buf[b];
-      if (conv_launch(h, idx + 2, buf[c], n, Ho, Ho, res, 1, out, &L3)) return 1;
-      plan->gemms.push_back(L3);
+      __nv_bfloat16* out = (last && final_out) ? final_out : buf[c];
+      const ConvSpec& s2 = h->specs[idx + 1];
+      const ConvSpec& s3 = h->specs[idx + 2];
+      if (use_fused_tail() && stride == 1 && bneck_tail_supported(H, H, s2.cout, s3.cout)) {
+        // conv2 + conv3 in one launch (bneck.cu): conv1's output never comes back from HBM nine times, conv2's never leaves the SM
+        TailLaunch T{};
+        if (build_bneck_tail(&T, buf[b], h->wq[idx + 1], h->scale[idx + 1], h->shift[idx + 1], h->wq[idx + 2], h->scale[idx + 2],
+                             h->shift[idx + 2], res, out, n, H, H)) return 1;
+        plan->ops.push_back({1, (int)plan->tails.size()});
+        plan->tails.push_back(T);
+        // roles: X <- out; the old X and T1 become scratch
+        if (out == buf[c]) { std::swap(a, c); }
+      } else {
+        if (out == buf[c]) out = buf[b];               // unfused: conv3 may overwrite T1
+        if (conv_launch(h, idx + 1, buf[b], n, H, H, nullptr, 1, buf[c], &L2)) return 1;
+        push(L2);
+        if (conv_launch(h, idx + 2, buf[c], n, Ho, Ho, res, 1, out, &L3)) return 1;
+        push(L3);
+        if (out == buf[b]) std::swap(a, b);
+      }
       plan->final_act = out;
-      std::swap(a, b);
       idx += down ? 4 : 3;
       H = Ho;
     }
@@ -478,7 +497,7 @@ static int build_blocks(airpose_net* h, int n, int l0, int l1, int H, __nv_bfloa
 // stage A: stem GEMM + layer1 + layer2 on `n` <= chunk images; output [n,28,28,512] lands at image
 // offset `first` of the stage-B input buffer.
 static int build_plan_a(airpose_net* h, int n, int first, int set, TrunkPlan* plan) {
-  plan->gemms.clear();
+  plan->gemms.clear(); plan->tails.clear(); plan->ops.clear();
   GemmLaunch L{};
   if (build_stem_gemm(h, n, set, &L)) return 1;
   plan->gemms.push_back(L);
@@ -488,8 +507,14 @@ static int build_plan_a(airpose_net* h, int n, int first, int set, TrunkPlan* pl
 
 // stage B: layer3 + layer4 on `n` <= group images, input in actB[0].
 static int build_plan_b(airpose_net* h, int n, TrunkPlan* plan) {
-  plan->gemms.clear();
+  plan->gemms.clear(); plan->tails.clear(); plan->ops.clear();
   return build_blocks(h, n, 2, 4, 28, h->actB, nullptr, plan);
+}
+
+static int launch_plan_ops(const TrunkPlan& plan, cudaStream_t st) {
+  for (const PlanOp& op : plan.ops)
+    if (op.kind == 0 ? launch_gemm(plan.gemms[op.idx], st) : launch_bneck_tail(plan.tails[op.idx], st)) return 1;
+  return 0;
 }
 
 static int launch_stem_front(airpose_net* h, const float* x, int n, int set, const GemmLaunch& stem, __nv_bfloat16* pooled, cudaStream_t st) {
@@ -534,8 +559,7 @@ static int backbone_fwd_segments(airpose_net_t* h, const float* x0, int n0, cons
       }
       const TrunkPlan& plan = it->second;
       if (launch_stem_front(h, src(first), n, set, plan.gemms[0], h->actS[set][0], cst)) return 1;
-      for (size_t g = 1; g < plan.gemms.size(); ++g)
-        if (launch_gemm(plan.gemms[g], cst)) return 1;
+      if (launch_plan_ops(plan, cst)) return 1;
     }
     if (fork) {
       AP_CHECK_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
@@ -548,8 +572,7 @@ static int backbone_fwd_segments(airpose_net_t* h, const float* x0, int n0, cons
       it = h->plansB.emplace(ng, std::move(plan)).first;
     }
     const TrunkPlan& plan = it->second;
-    for (size_t g = 0; g < plan.gemms.size(); ++g)
-      if (launch_gemm(plan.gemms[g], st)) return 1;
+    if (launch_plan_ops(plan, st)) return 1;
     avgpool_kernel<<<ceil_div(ng * kFeat, 256), 256, 0, st>>>(plan.final_act, ng, out_feat + (size_t)g0 * kFeat);
     AP_LAUNCH_CHECK();
   }

@@ -453,6 +453,19 @@ typedef struct {
 } airpose_conv_args;
 int airpose_conv_bf16(const airpose_conv_args* c, void* stream);
 
+/* Fused tail of a stride-1 bottleneck (Bottleneck.forward, model_copenet.py:33-46): conv2 3x3 pad 1 + bn2 + ReLU ->
+ * conv3 1x1 + bn3 + residual + ReLU in ONE launch (halo slab in shared memory, nine row-shifted tcgen05 windows).
+ * t1 [n,H,W,Cm] bf16 (conv1's output), w2 [Cm, 9*Cm] bf16 (tap-major, channel-minor), w3 [4*Cm, Cm] bf16,
+ * residual / out [n,H,W,4*Cm] bf16.  Supported: Cm = 64, 2*(W+2) <= 128 (the 56x56 stage). */
+typedef struct {
+  const void* t1; int32_t n, H, W, Cm;
+  const void* w2; const float* scale2; const float* shift2;
+  const void* w3; const float* scale3; const float* shift3;
+  const void* residual;
+  void* out;
+} airpose_bneck_tail_args;
+int airpose_bneck_tail_bf16(const airpose_bneck_tail_args* a, void* stream);
+
 /* Stem only (conv 7x7 s2 + BN + ReLU + MaxPool 3x3 s2, model_copenet.py:163-166):
  * x [n,3,224,224] fp32 NCHW -> out [n,56,56,64] bf16 NHWC.  n <= the handle's chunk size. */
 int airpose_backbone_stem(airpose_net_t* h, const float* x_nchw, int n_images, void* out_nhwc_bf16, void* stream);

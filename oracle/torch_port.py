@@ -130,11 +130,12 @@ def smplx_forward(m: Smplx, betas, body_pose):
     return verts, joints
 
 
-def twoview_forward(sd, m: Smplx, batch, iters=3, focal=(1475.0, 1475.0)):
-    """copenet_twoview.py:164-317 without the loss."""
+def twoview_forward(sd, m: Smplx, batch, iters=3, focal=(1475.0, 1475.0), feats=None):
+    """copenet_twoview.py:164-317 without the loss.  `feats` = (xf0, xf1) skips the trunk (used when the trunk ran under
+    autocast on the GPU baseline)."""
     b = batch["im0"].shape[0]
     init = torch.tensor([0.0, 0.0, 10.0]).expand(b, -1) * 0.05
-    xf0, xf1 = forward_feat_ext(batch["im0"], sd), forward_feat_ext(batch["im1"], sd)
+    xf0, xf1 = feats if feats is not None else (forward_feat_ext(batch["im0"], sd), forward_feat_ext(batch["im1"], sd))
     p0, s0, p1, s1 = ief(sd, xf0, xf1, batch["bb0"], batch["bb1"], init, init, iters)
     out = {"xf0": xf0, "xf1": xf1}
     for v, (p, s) in enumerate(((p0, s0), (p1, s1))):
