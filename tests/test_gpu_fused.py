@@ -62,3 +62,32 @@ def test_bneck_tail_matches_torch(n, H, W):
           (n, H, W, err.max().item(), err.mean().item(), int(bad.sum()), bad.numel()))
     assert not bad.any()
     assert err.mean().item() < 2e-3
+
+
+@pytest.mark.parametrize("n", [6, 58, 64])
+def test_bneck_tail_is_deterministic(n):
+    """No atomics, no data-dependent scheduling: the same launch twice gives the same bits (the trunk's chunk sizes)."""
+    lib = _lib.load()
+    Cm, Co, H = 64, 256, 56
+    g = torch.Generator(device="cpu").manual_seed(n)
+    t1 = _bf16(torch.relu(torch.randn(n, H, H, Cm, generator=g))).to(DEV)
+    w2k = _bf16(torch.randn(Cm, 9 * Cm, generator=g) * 0.06).to(DEV)
+    w3k = _bf16(torch.randn(Co, Cm, generator=g) * 0.17).to(DEV)
+    sc2, sh2 = (torch.rand(Cm, generator=g) + 0.5).to(DEV), (torch.randn(Cm, generator=g) * 0.3).to(DEV)
+    sc3, sh3 = (torch.rand(Co, generator=g) + 0.5).to(DEV), (torch.randn(Co, generator=g) * 0.3).to(DEV)
+    res = _bf16(torch.randn(n, H, H, Co, generator=g)).to(DEV)
+    outs = []
+    for rep in range(4):
+        out = torch.full((n, H, H, Co), float("nan"), device=DEV, dtype=torch.bfloat16)
+        a = _lib.BneckTailArgs()
+        a.t1, a.n, a.H, a.W, a.Cm = t1.data_ptr(), n, H, H, Cm
+        a.w2, a.scale2, a.shift2 = w2k.data_ptr(), sc2.data_ptr(), sh2.data_ptr()
+        a.w3, a.scale3, a.shift3 = w3k.data_ptr(), sc3.data_ptr(), sh3.data_ptr()
+        a.residual, a.out = res.data_ptr(), out.data_ptr()
+        _lib.check(lib.airpose_bneck_tail_bf16(C.byref(a), _lib.current_stream()), "bneck_tail")
+        torch.cuda.synchronize()
+        outs.append(out)
+    for rep in range(1, 4):
+        diff = (outs[rep].view(torch.int16) != outs[0].view(torch.int16))
+        assert not diff.any(), "run %d differs from run 0 in %d elements (first at %s)" % (
+            rep, int(diff.sum()), diff.nonzero()[0].tolist())
