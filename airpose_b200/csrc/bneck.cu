@@ -70,15 +70,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-// explicit shared-space accesses (the hand-aligned dynamic smem base hides the address space from the compiler)
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
+using ptx::lds128;
+using ptx::lds_f4;
+using ptx::sts128;
 
 // mbarrier arrive that carries a (otherwise unused) register operand: the instructions producing `dep` stay in the program
 // and are ordered before the arrive.
@@ -86,23 +80,32 @@ __device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep) {
   asm volatile("{\n\t.reg .b32 t;\n\tmov.b32 t, %1;\n\tmbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(ptx::smem_u32(bar)), "r"(dep) : "memory");
 }
 
-// 32 accumulator columns (r) * scale + shift + residual (four 16-byte groups q of bf16) -> ReLU -> bf16 -> output slot
-__device__ __forceinline__ void bn_res_relu_store(const uint32_t (&r)[32], const uint4* q, const float* s3, const float* h3,
-                                                  uint32_t orow, uint32_t swz, int j0) {
+// 32 accumulator columns (r) * scale + shift + residual (four 16-byte groups q of bf16) -> ReLU -> bf16 (four 16-byte groups).
+// s3 / h3: shared-space addresses of the 32 scales / shifts of these columns.
+__device__ __forceinline__ void bn_res_relu(const uint32_t (&r)[32], const uint4* q, uint32_t s3, uint32_t h3, uint4 (&out)[4]) {
+  // per 16 columns: the eight scale / shift loads first (volatile asm: they would otherwise queue behind the previous stores)
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
-    float v[8];
+  for (int jj = 0; jj < 2; ++jj) {
+    float4 S[4], Hs[4];
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      v[2 * h] = fmaf(__uint_as_float(r[j * 8 + 2 * h]), s3[j * 8 + 2 * h], h3[j * 8 + 2 * h]) + __uint_as_float(w[h] << 16);
-      v[2 * h + 1] = fmaf(__uint_as_float(r[j * 8 + 2 * h + 1]), s3[j * 8 + 2 * h + 1], h3[j * 8 + 2 * h + 1]) +
-                     __uint_as_float(w[h] & 0xFFFF0000u);
+    for (int g = 0; g < 4; ++g) { S[g] = lds_f4(s3 + jj * 64 + g * 16); Hs[g] = lds_f4(h3 + jj * 64 + g * 16); }
+#pragma unroll
+    for (int jl = 0; jl < 2; ++jl) {
+      const int j = jj * 2 + jl;
+      const float2 sc[4] = {make_float2(S[2 * jl].x, S[2 * jl].y), make_float2(S[2 * jl].z, S[2 * jl].w),
+                            make_float2(S[2 * jl + 1].x, S[2 * jl + 1].y), make_float2(S[2 * jl + 1].z, S[2 * jl + 1].w)};
+      const float2 sh[4] = {make_float2(Hs[2 * jl].x, Hs[2 * jl].y), make_float2(Hs[2 * jl].z, Hs[2 * jl].w),
+                            make_float2(Hs[2 * jl + 1].x, Hs[2 * jl + 1].y), make_float2(Hs[2 * jl + 1].z, Hs[2 * jl + 1].w)};
+      const uint32_t w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {     // (acc * scale + shift) + residual, each rounded to fp32 like the reference's two ops
+        const float2 a = make_float2(__uint_as_float(r[j * 8 + 2 * h]), __uint_as_float(r[j * 8 + 2 * h + 1]));
+        const float2 v = ptx::fadd2(ptx::ffma2(a, sc[h], sh[h]), ptx::bf16x2_to_f2(w[h]));
+        o[h] = ptx::cvt_bf16x2_relu(v.x, v.y);
+      }
+      out[j] = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    uint4 o;
-    o.x = pack_bf16(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f)); o.y = pack_bf16(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
-    o.z = pack_bf16(fmaxf(v[4], 0.f), fmaxf(v[5], 0.f)); o.w = pack_bf16(fmaxf(v[6], 0.f), fmaxf(v[7], 0.f));
-    sts128(orow + (((uint32_t)(j0 + j) ^ swz) << 4), o);
   }
 }
 
@@ -244,6 +247,7 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
     const uint32_t srow = ptx::smem_u32(smem + kStgOff + row * kRow);
     const uint32_t rrow = ptx::smem_u32(smem + kResOff + wg * kTileBytes + row * kRow);
     const uint32_t orow = ptx::smem_u32(smem + kOutOff + wg * kTileBytes + row * kRow);
+    const uint32_t sc2_a = ptx::smem_u32(sc2), sh2_a = ptx::smem_u32(sh2), sc3_a = ptx::smem_u32(sc3), sh3_a = ptx::smem_u32(sh3);
     // The residual of the NEXT chunk sits in registers while the current one is processed: the slot is handed back to the
     // producer as soon as it has been read, so a load is always in flight (the kernel is HBM-bound, not MMA-bound).
     uint4 resA[8], resB[8];
@@ -276,17 +280,22 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
         ptx::tmem_ld_32x32(lane_addr + wg * 32, r);
         ptx::tmem_ld_wait();
         ptx::mbar_wait(stg_empty, (uint32_t)((it & 1) ^ 1), 401);     // conv3 of the previous tile has read the staging tile
+        float4 S[8], Hs[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) { S[g] = lds_f4(sc2_a + wg * 128 + g * 16); Hs[g] = lds_f4(sh2_a + wg * 128 + g * 16); }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float v[8];
+          const float2 sc[4] = {make_float2(S[2 * j].x, S[2 * j].y), make_float2(S[2 * j].z, S[2 * j].w),
+                                make_float2(S[2 * j + 1].x, S[2 * j + 1].y), make_float2(S[2 * j + 1].z, S[2 * j + 1].w)};
+          const float2 sh[4] = {make_float2(Hs[2 * j].x, Hs[2 * j].y), make_float2(Hs[2 * j].z, Hs[2 * j].w),
+                                make_float2(Hs[2 * j + 1].x, Hs[2 * j + 1].y), make_float2(Hs[2 * j + 1].z, Hs[2 * j + 1].w)};
+          uint32_t o[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int c = wg * 32 + j * 8 + i;
-            v[i] = fmaxf(fmaf(__uint_as_float(r[j * 8 + i]), sc2[c], sh2[c]), 0.f);
+          for (int i = 0; i < 4; ++i) {
+            const float2 v = ptx::ffma2(make_float2(__uint_as_float(r[j * 8 + 2 * i]), __uint_as_float(r[j * 8 + 2 * i + 1])), sc[i], sh[i]);
+            o[i] = ptx::cvt_bf16x2_relu(v.x, v.y);
           }
-          uint4 q;
-          q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
-          sts128(srow + (((uint32_t)(wg * 4 + j) ^ swz) << 4), q);
+          sts128(srow + (((uint32_t)(wg * 4 + j) ^ swz) << 4), make_uint4(o[0], o[1], o[2], o[3]));
         }
         ptx::fence_proxy_async();
         ptx::tc_fence_before();
@@ -303,21 +312,25 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
         ptx::mbar_wait(&acc3_full[half], (uint32_t)(it & 1), 402 + half);
         ptx::tc_fence_after();
         const uint32_t taddr = lane_addr + kAcc3Col + half * 128 + wg * 64;
-        const float* s3 = sc3 + c * 64;
-        const float* h3 = sh3 + c * 64;
+        const uint32_t s3 = sc3_a + c * 256, h3 = sh3_a + c * 256;
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr, r);
         ptx::tmem_ld_wait();
+        uint4 o[4];
+        bn_res_relu(r, &cur[0], s3, h3, o);
         // the previous store of this warpgroup must have read the output slot before it is overwritten
         if (wgt == 0) ptx::tma_store_wait_read<0>();
         ptx::named_bar_sync(1 + wg, 128);
-        bn_res_relu_store(r, &cur[0], s3, h3, orow, swz, 0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts128(orow + (((uint32_t)j ^ swz) << 4), o[j]);
         ptx::tmem_ld_32x32(taddr + 32, r);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&acc3_empty[half]);
-        bn_res_relu_store(r, &cur[4], s3 + 32, h3 + 32, orow, swz, 4);
+        bn_res_relu(r, &cur[4], s3 + 128, h3 + 128, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts128(orow + (((uint32_t)(4 + j) ^ swz) << 4), o[j]);
         ptx::fence_proxy_async();
         ptx::named_bar_sync(3 + wg, 128);
         if (wgt == 0) {

@@ -64,11 +64,6 @@ struct Cfg {
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
 template <int BN, int BK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -202,6 +197,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quad = warp & 3;                       // TMEM lane quarter this warp may read
     const int row = quad * 32 + lane;                // row of the tile == TMEM lane
     const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t smem_a = ptx::smem_u32(smem), sc_a = ptx::smem_u32(sc_s), sh_a = ptx::smem_u32(sh_s);
     int it = 0, oc = 0, rs = 0;
     uint32_t rphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -210,8 +206,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int m0 = m_blk * kBlockM, n0 = n_blk * BN;
       for (int i = et; i < BN; i += kEpiThreads) {
         const int n = n0 + i;
-        sc_s[as * BN + i] = (n < p.N) ? (p.scale ? __ldg(p.scale + n) : 1.f) : 0.f;
-        sh_s[as * BN + i] = (n < p.N && p.shift) ? __ldg(p.shift + n) : 0.f;
+        ptx::sts_f32(sc_a + (as * BN + i) * 4, (n < p.N) ? (p.scale ? __ldg(p.scale + n) : 1.f) : 0.f);
+        ptx::sts_f32(sh_a + (as * BN + i) * 4, (n < p.N && p.shift) ? __ldg(p.shift + n) : 0.f);
       }
       ptx::named_bar_sync(1, kEpiThreads);
       ptx::mbar_wait(&tfull_bar[as], aphase, 400 + as);
@@ -230,47 +226,59 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
         }
-        const float4* sc4 = reinterpret_cast<const float4*>(sc_s + as * BN + c * kChunkN);
-        const float4* sh4 = reinterpret_cast<const float4*>(sh_s + as * BN + c * kChunkN);
-        float v[64];
+        const uint32_t sc4 = sc_a + (as * BN + c * kChunkN) * 4, sh4 = sh_a + (as * BN + c * kChunkN) * 4;
+        // v = acc * scale + shift with packed fp32 math (FFMA2); the shared-memory loads of each 32 columns go first (they are
+        // volatile asm and would otherwise queue behind other shared-memory traffic)
+        float2 V[32];
 #pragma unroll
-        for (int g = 0; g < 16; ++g) {
-          const float4 s4 = sc4[g], h4 = sh4[g];
-          v[4 * g + 0] = fmaf(__uint_as_float(r[4 * g + 0]), s4.x, h4.x);
-          v[4 * g + 1] = fmaf(__uint_as_float(r[4 * g + 1]), s4.y, h4.y);
-          v[4 * g + 2] = fmaf(__uint_as_float(r[4 * g + 2]), s4.z, h4.z);
-          v[4 * g + 3] = fmaf(__uint_as_float(r[4 * g + 3]), s4.w, h4.w);
+        for (int hh = 0; hh < 2; ++hh) {
+          float4 S[8], Hs[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) { S[g] = ptx::lds_f4(sc4 + hh * 128 + g * 16); Hs[g] = ptx::lds_f4(sh4 + hh * 128 + g * 16); }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int e = hh * 32 + g * 4;
+            V[e / 2] = ptx::ffma2(make_float2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), make_float2(S[g].x, S[g].y),
+                                  make_float2(Hs[g].x, Hs[g].y));
+            V[e / 2 + 1] = ptx::ffma2(make_float2(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3])), make_float2(S[g].z, S[g].w),
+                                      make_float2(Hs[g].z, Hs[g].w));
+          }
         }
-        if (p.has_res) {
+        if (p.has_res) {                       // the residual tile is waited for only now: the arithmetic above overlaps its arrival
           ptx::mbar_wait(&rfull_bar[rs], rphase, 600 + rs);
-          const uint8_t* rb = smem + C::kResOff + rs * kChunkBytes + row * 128;
+          const uint32_t rb = smem_a + C::kResOff + rs * kChunkBytes + row * 128;
+          uint4 Q[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) Q[j] = ptx::lds128(rb + (((uint32_t)j ^ swz) << 4));
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const uint4 q = *reinterpret_cast<const uint4*>(rb + (((uint32_t)j ^ swz) << 4));
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              v[j * 8 + 2 * h] += __uint_as_float(w[h] << 16);
-              v[j * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xFFFF0000u);
-            }
+            V[4 * j] = ptx::fadd2(V[4 * j], ptx::bf16x2_to_f2(Q[j].x));
+            V[4 * j + 1] = ptx::fadd2(V[4 * j + 1], ptx::bf16x2_to_f2(Q[j].y));
+            V[4 * j + 2] = ptx::fadd2(V[4 * j + 2], ptx::bf16x2_to_f2(Q[j].z));
+            V[4 * j + 3] = ptx::fadd2(V[4 * j + 3], ptx::bf16x2_to_f2(Q[j].w));
           }
+        }
+        uint4 O[8];
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            O[j] = make_uint4(ptx::cvt_bf16x2_relu(V[4 * j].x, V[4 * j].y), ptx::cvt_bf16x2_relu(V[4 * j + 1].x, V[4 * j + 1].y),
+                              ptx::cvt_bf16x2_relu(V[4 * j + 2].x, V[4 * j + 2].y), ptx::cvt_bf16x2_relu(V[4 * j + 3].x, V[4 * j + 3].y));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            O[j] = make_uint4(ptx::cvt_bf16x2(V[4 * j].x, V[4 * j].y), ptx::cvt_bf16x2(V[4 * j + 1].x, V[4 * j + 1].y),
+                              ptx::cvt_bf16x2(V[4 * j + 2].x, V[4 * j + 2].y), ptx::cvt_bf16x2(V[4 * j + 3].x, V[4 * j + 3].y));
+        }
+        uint8_t* ob = smem + C::kOutOff + (oc % C::kOutBufs) * kChunkBytes;
+        const uint32_t orow = smem_a + C::kOutOff + (oc % C::kOutBufs) * kChunkBytes + row * 128;
+        if (C::kOutBufs == 2) ptx::named_bar_sync(2, kEpiThreads);   // thread 0 arrives after its wait_read<1>
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ptx::sts128(orow + (((uint32_t)j ^ swz) << 4), O[j]);
+        if (p.has_res) {
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&rempty_bar[rs]);
           if (++rs == kResBufs) { rs = 0; rphase ^= 1; }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        uint8_t* ob = smem + C::kOutOff + (oc % C::kOutBufs) * kChunkBytes;
-        uint8_t* orow = ob + row * 128;
-        if (C::kOutBufs == 2) ptx::named_bar_sync(2, kEpiThreads);   // thread 0 arrives after its wait_read<1>
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 q;
-          q.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]); q.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
-          q.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]); q.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
-          *reinterpret_cast<uint4*>(orow + (((uint32_t)j ^ swz) << 4)) = q;
         }
         ptx::fence_proxy_async();
         ptx::named_bar_sync(1, kEpiThreads);
