@@ -52,7 +52,7 @@ constexpr int kOutOff = kResOff + 2 * kTileBytes;     // [2]: one output slot pe
 constexpr int kBarOff = kOutOff + 2 * kTileBytes;
 // barriers: w_full, slab_full, slab_empty, acc2_full, stg_full, stg_empty, acc3_full[2], acc3_empty[2], res_full[2], res_empty[2]
 constexpr int kNumBars = 14;
-constexpr int kScaleOff = kBarOff + kNumBars * 8 + 16;
+constexpr int kScaleOff = (kBarOff + kNumBars * 8 + 16 + 15) & ~15;        // read with 16-byte shared loads
 constexpr int kSmemBytes = 1024 + kScaleOff + (2 * kCM + 2 * kCO) * 4;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 constexpr int kTmemCols = 512;             // acc2: 64 columns from 0; acc3: 2 x 128 columns from 128

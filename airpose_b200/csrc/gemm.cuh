@@ -82,6 +82,18 @@ int build_bneck_tail(TailLaunch* L, const void* t1, const void* w2, const float*
                      const float* scale3, const float* shift3, const void* residual, void* out, int n, int H, int W);
 int launch_bneck_tail(const TailLaunch& L, cudaStream_t stream);
 
+// Fused stem (stem.cu): conv 7x7 s2 + BN + ReLU + MaxPool 3x3 s2 in one launch (plus the operand pack kernel).
+struct alignas(64) StemLaunch {
+  unsigned char storage[320];      // two tensor maps + the kernel parameters (StemLaunchImpl in stem.cu)
+  int valid = 0;
+  int pdl = 0;
+};
+size_t stem_pairs_operand_elems(int n);      // bf16 elements of the packed operand of n images
+size_t stem_pairs_weight_elems();
+int stem_pack_pairs_weight(const float* w_f32, void* out_bf16, cudaStream_t st);
+int build_stem_pool(StemLaunch* L, const void* x2p, const void* wp, const float* scale, const float* shift, void* out_nhwc, int n);
+int launch_stem_pool(const StemLaunch& L, const float* x_nchw, void* x2p, int n, cudaStream_t stream);
+
 int pick_block_n(int M, int N, int K);
 bool prefers_stream_k(int M, int N, int K);
 bool use_tma_epilogue();   // off with AIRPOSE_NO_TMA_EPI=1 (A/B runs)

@@ -59,7 +59,7 @@ struct Cfg {
   static constexpr int kResOff = kOutOff + kOutBufs * kChunkBytes;
   static constexpr int kBarOff = kResOff + kResBufs * kChunkBytes;
   static constexpr int kNumBars = 2 * kStages + 4 + 2 * kResBufs;
-  static constexpr int kScaleOff = kBarOff + kNumBars * 8 + 16;
+  static constexpr int kScaleOff = (kBarOff + kNumBars * 8 + 16 + 15) & ~15;   // read with 16-byte shared loads
   static constexpr int kSmemBytes = 1024 + kScaleOff + 2 * 2 * BN * 4;
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 };

@@ -17,6 +17,7 @@ struct PlanOp { int kind; int idx; };  // kind 0: gemms[idx] (one conv), 1: tail
 struct TrunkPlan {
   std::vector<GemmLaunch> gemms;       // [stem,] then per block conv1, conv2, [down], conv3 (conv2/conv3 absent when fused)
   std::vector<TailLaunch> tails;
+  StemLaunch stem;                     // stage-A plans: the fused stem (when enabled)
   std::vector<PlanOp> ops;             // launch order (the stem GEMM, gemms[0] of a stage-A plan, is not listed)
   const __nv_bfloat16* final_act = nullptr;
 };
@@ -47,6 +48,7 @@ struct airpose_net {
   bool loaded = false;
   std::vector<airpose::ConvSpec> specs;
   std::vector<__nv_bfloat16*> wq;       // packed conv weights
+  __nv_bfloat16* wq_stem_pairs = nullptr;   // conv1 in the column-pair layout of the fused stem (stem.cu)
   std::vector<float*> scale, shift;     // folded BN
   airpose::IefState ief;                // two-view regressor (model_copenet.py)
   airpose::IefState ief_hmr;            // single-view hmr regressor (model_hmr.py)
@@ -62,6 +64,9 @@ struct airpose_net {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int sets = 1;
   __nv_bfloat16* actB[4] = {nullptr, nullptr, nullptr, nullptr};   // stage B (layer3, layer4): `group` images
+  // split mode (trunk.cu): every chunk runs stage B itself, on its own stream, in its own buffers (set 1: actB1, `chunk` images)
+  __nv_bfloat16* actB1[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool split_b = false;
   int group = 0;
   // training-mode forward (airpose_backbone_fwd_train): raw conv output, BatchNorm partial sums, scale/shift of the layer
   __nv_bfloat16* ztrain = nullptr;

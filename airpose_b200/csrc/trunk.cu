@@ -284,8 +284,18 @@ static int env_int(const char* name, int dflt) {
   const int c = e ? atoi(e) : dflt;
   return c > 0 ? c : dflt;
 }
+static bool use_fused_stem() {          // AIRPOSE_NO_FUSED_STEM=1: pack + stem GEMM + max-pool as three launches (A/B runs)
+  static const bool on = getenv("AIRPOSE_NO_FUSED_STEM") == nullptr;
+  return on;
+}
 static bool use_fused_tail() {          // AIRPOSE_NO_FUSED_TAIL=1: every conv as its own implicit-GEMM launch (A/B runs)
   static const bool on = getenv("AIRPOSE_NO_FUSED_TAIL") == nullptr;
+  return on;
+}
+// AIRPOSE_TRUNK_SPLIT_B=1: each 64-image chunk runs the WHOLE trunk on its own stream (two independent pipelines whose
+// kernels fill each other's ramp-up / drain), instead of joining the chunks into one 128-image stage B.
+static bool use_split_b() {
+  static const bool on = getenv("AIRPOSE_TRUNK_SPLIT_B") != nullptr && atoi(getenv("AIRPOSE_TRUNK_SPLIT_B")) != 0;
   return on;
 }
 static int default_chunk() { return env_int("AIRPOSE_TRUNK_CHUNK", 64); }
@@ -310,6 +320,7 @@ extern "C" int airpose_net_create(airpose_net_t** out, int max_images, int devic
     AP_CHECK_CUDA(cudaMalloc((void**)&h->scale[i], s.cout * sizeof(float)));
     AP_CHECK_CUDA(cudaMalloc((void**)&h->shift[i], s.cout * sizeof(float)));
   }
+  AP_CHECK_CUDA(cudaMalloc((void**)&h->wq_stem_pairs, stem_pairs_weight_elems() * 2));
   if (ief_create(h)) return 1;
   const size_t act_elems = (size_t)h->chunk * 112 * 112 * 64;       // == 56*56*256, the largest activation
   // two stage-A buffer sets (and a side stream) only when a call can have more than one chunk
@@ -325,6 +336,9 @@ extern "C" int airpose_net_create(airpose_net_t** out, int max_images, int devic
     AP_CHECK_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   }
   for (int i = 0; i < 4; ++i) AP_CHECK_CUDA(cudaMalloc((void**)&h->actB[i], (size_t)h->group * kStageBElems * 2));
+  h->split_b = h->sets > 1 && use_split_b();
+  if (h->split_b)
+    for (int i = 0; i < 4; ++i) AP_CHECK_CUDA(cudaMalloc((void**)&h->actB1[i], (size_t)h->chunk * kStageBElems * 2));
   *out = h;
   return 0;
 }
@@ -333,10 +347,11 @@ extern "C" int airpose_net_destroy(airpose_net_t* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   for (auto p : h->wq) cudaFree(p);
+  cudaFree(h->wq_stem_pairs);
   for (auto p : h->scale) cudaFree(p);
   for (auto p : h->shift) cudaFree(p);
   ief_destroy(h);
-  void* ptrs[] = {h->actB[0], h->actB[1], h->actB[2], h->actB[3], h->ztrain, h->bn_part, h->bn_scale, h->bn_shift};
+  void* ptrs[] = {h->actB[0], h->actB[1], h->actB[2], h->actB[3], h->actB1[0], h->actB1[1], h->actB1[2], h->actB1[3], h->ztrain, h->bn_part, h->bn_scale, h->bn_shift};
   for (void* p : ptrs) cudaFree(p);
   for (int s = 0; s < airpose_net::kSets; ++s) {
     cudaFree(h->colS[s]); cudaFree(h->stem_outS[s]);
@@ -365,6 +380,7 @@ static int load_trunk(airpose_net_t* h, const airpose_conv_params* conv, float b
     const int kpad = (i == 0) ? kStemK : s.k * s.k * s.cin;
     pack_conv_weight_kernel<<<256, 256, 0, st>>>(c.weight, h->wq[i], s.cout, s.cin, s.k, kpad, i == 0);
     AP_LAUNCH_CHECK();
+    if (i == 0 && stem_pack_pairs_weight(c.weight, h->wq_stem_pairs, st)) return 1;
     fold_bn_kernel<<<ceil_div(s.cout, 256), 256, 0, st>>>(c.bn_weight, c.bn_bias, c.bn_mean, c.bn_var, bn_eps, s.cout,
                                                           h->scale[i], h->shift[i]);
     AP_LAUNCH_CHECK();
@@ -501,14 +517,15 @@ static int build_plan_a(airpose_net* h, int n, int first, int set, TrunkPlan* pl
   GemmLaunch L{};
   if (build_stem_gemm(h, n, set, &L)) return 1;
   plan->gemms.push_back(L);
-  __nv_bfloat16* out = h->actB[0] + (size_t)first * kStageBElems;
+  if (use_fused_stem() && build_stem_pool(&plan->stem, h->colS[set], h->wq_stem_pairs, h->scale[0], h->shift[0], h->actS[set][0], n)) return 1;
+  __nv_bfloat16* out = h->split_b ? (set ? h->actB1[0] : h->actB[0]) : h->actB[0] + (size_t)first * kStageBElems;
   return build_blocks(h, n, 0, 2, 56, h->actS[set], out, plan);
 }
 
 // stage B: layer3 + layer4 on `n` <= group images, input in actB[0].
-static int build_plan_b(airpose_net* h, int n, TrunkPlan* plan) {
+static int build_plan_b(airpose_net* h, int n, int set, TrunkPlan* plan) {
   plan->gemms.clear(); plan->tails.clear(); plan->ops.clear();
-  return build_blocks(h, n, 2, 4, 28, h->actB, nullptr, plan);
+  return build_blocks(h, n, 2, 4, 28, set ? h->actB1 : h->actB, nullptr, plan);
 }
 
 static int launch_plan_ops(const TrunkPlan& plan, cudaStream_t st) {
@@ -558,18 +575,32 @@ static int backbone_fwd_segments(airpose_net_t* h, const float* x0, int n0, cons
         it = h->plansA.emplace(key, std::move(plan)).first;
       }
       const TrunkPlan& plan = it->second;
-      if (launch_stem_front(h, src(first), n, set, plan.gemms[0], h->actS[set][0], cst)) return 1;
+      if (plan.stem.valid) {
+        if (launch_stem_pool(plan.stem, src(first), h->colS[set], n, cst)) return 1;
+      } else if (launch_stem_front(h, src(first), n, set, plan.gemms[0], h->actS[set][0], cst)) return 1;
       if (launch_plan_ops(plan, cst)) return 1;
+      if (h->split_b) {                     // this chunk's stage B right behind its stage A, on the same stream
+        auto itb = h->plansB.find(2 * n + set);
+        if (itb == h->plansB.end()) {
+          TrunkPlan pb;
+          if (build_plan_b(h, n, set, &pb)) return 1;
+          itb = h->plansB.emplace(2 * n + set, std::move(pb)).first;
+        }
+        if (launch_plan_ops(itb->second, cst)) return 1;
+        avgpool_kernel<<<ceil_div(n * kFeat, 256), 256, 0, cst>>>(itb->second.final_act, n, out_feat + (size_t)first * kFeat);
+        AP_LAUNCH_CHECK();
+      }
     }
     if (fork) {
       AP_CHECK_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
       AP_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
     }
-    auto it = h->plansB.find(ng);
+    if (h->split_b) continue;
+    auto it = h->plansB.find(2 * ng);
     if (it == h->plansB.end()) {
       TrunkPlan plan;
-      if (build_plan_b(h, ng, &plan)) return 1;
-      it = h->plansB.emplace(ng, std::move(plan)).first;
+      if (build_plan_b(h, ng, 0, &plan)) return 1;
+      it = h->plansB.emplace(2 * ng, std::move(plan)).first;
     }
     const TrunkPlan& plan = it->second;
     if (launch_plan_ops(plan, st)) return 1;
@@ -598,6 +629,11 @@ extern "C" int airpose_backbone_stem(airpose_net_t* h, const float* x, int n, vo
   AP_REQUIRE(h && x && out, "airpose_backbone_stem: null argument");
   AP_REQUIRE(h->loaded, "airpose_backbone_stem: weights not loaded (call airpose_net_load)");
   AP_REQUIRE(n > 0 && n <= h->chunk, "airpose_backbone_stem: n=%d exceeds the chunk size %d", n, h->chunk);
+  if (use_fused_stem()) {
+    StemLaunch sl{};
+    if (build_stem_pool(&sl, h->colS[0], h->wq_stem_pairs, h->scale[0], h->shift[0], out, n)) return 1;
+    return launch_stem_pool(sl, x, h->colS[0], n, (cudaStream_t)stream_);
+  }
   GemmLaunch stem{};
   if (build_stem_gemm(h, n, 0, &stem)) return 1;
   return launch_stem_front(h, x, n, 0, stem, (__nv_bfloat16*)out, (cudaStream_t)stream_);
