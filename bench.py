@@ -29,10 +29,9 @@ PAIRS_PER_GPU = 64
 GFLOP_PER_IMAGE = 8.174272512          # 4,087,136,256 MAC
 LBS_BYTES_PER_MESH = 128420
 LBS_CONST_BYTES = 68338900
-CPU_SAMPLE_PAIRS = 8
-# dram__bytes_read.sum + dram__bytes_write.sum summed over the 77 conv-GEMM launches of one 128-image trunk
-# forward (64 pairs), from the ncu --set full capture profiles/r01s_ncu_full_trunk_128img.csv (cold-cache, serialised)
-TRUNK_DRAM_BYTES_PER_64_PAIRS = 4954.3e6
+CPU_SAMPLE_PAIRS = 64             # the cpu_baseline leg of the default run: the full 64-pair batch, 3 steps
+WORKLOAD = "copenet_twoview fwd batch=64 pairs 224x224 bf16 trunk / fp32 SMPL-X (BASELINE.json configs[1])"
+_ALL_CPUS = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
 
 
 def load_peaks():
@@ -86,55 +85,195 @@ class ClockSampler:
 
 
 def cpu_reference(pairs, steps, warmup):
-    """The reference algorithm (PyTorch-CPU port, oracle/torch_port.py) on all host threads."""
-    import numpy as np
+    """The reference on all host threads.  Preferred: the UNMODIFIED reference LightningModule (`copenet_twoview.fwd_pass_and_loss`,
+    copenet/src/copenet/copenet_twoview.py:164-374) from oracle/_ref (oracle/make_ref.py; kind "reference").  Without that copy:
+    the PyTorch-CPU port of the same algorithm (oracle/torch_port.py; kind "port").  Returns (pairs/s, ms/step, threads, kind, what)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import torch_port as tp
     from airpose_b200 import synthetic
-    cores = os.cpu_count() or 1
+    if _ALL_CPUS:                    # the GPU arm binds the process to the GPU's NUMA node: the CPU arm gets every core back
+        os.sched_setaffinity(0, _ALL_CPUS)
+    cores = len(_ALL_CPUS) if _ALL_CPUS else (os.cpu_count() or 1)
     torch.set_num_threads(cores)
-    sd = tp.to_torch(synthetic.make_network_state(123))
-    m = tp.Smplx(synthetic.make_smplx_model(0))
-    x = {k: torch.from_numpy(v) for k, v in synthetic.make_inputs(pairs, 123).items()}
+    import ref_harness as rh
+    if rh.available():
+        rt = rh.import_reference("cpu")
+        module = rh.make_module(rt, pairs, device="cpu").eval()
+        batch = rh.make_batch(pairs, 123, 321, device="cpu")
+        step = lambda: module.fwd_pass_and_loss(batch, is_val=True, is_test=False)
+        kind, what = "reference", "unmodified reference LightningModule fwd_pass_and_loss(is_val=True) from oracle/_ref, PyTorch CPU fp32"
+    else:
+        import torch_port as tp
+        sd = tp.to_torch(synthetic.make_network_state(123))
+        m = tp.Smplx(synthetic.make_smplx_model(0))
+        x = {k: torch.from_numpy(v) for k, v in synthetic.make_inputs(pairs, 123).items()}
+        step = lambda: tp.twoview_forward(sd, m, x)
+        kind, what = "port", "PyTorch-CPU port of the reference (oracle/torch_port.py; oracle/_ref absent), fp32"
     with torch.no_grad():
         for _ in range(warmup):
-            tp.twoview_forward(sd, m, x)
+            step()
         t0 = time.perf_counter()
         for _ in range(steps):
-            tp.twoview_forward(sd, m, x)
+            step()
         dt = time.perf_counter() - t0
-    return pairs * steps / dt, dt / steps * 1e3, cores
+    return pairs * steps / dt, dt / steps * 1e3, cores, kind, what
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, ms, cores = cpu_reference(CPU_SAMPLE_PAIRS, args.steps, args.warmup)
-    sample = "%d pairs per step (bounded sample of the 64-pair workload), fp32, PyTorch-CPU port of the reference" % CPU_SAMPLE_PAIRS
+    pairs = args.pairs
+    value, ms, cores, kind, what = cpu_reference(pairs, args.steps, args.warmup)
+    sample = "%d pairs per step (the full per-GPU batch of the workload), %s" % (pairs, what)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "copenet_twoview fwd batch=64 pairs 224x224 (BASELINE.json configs[1])", "pairs_per_step": CPU_SAMPLE_PAIRS},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": pairs, "global_pairs": pairs, "reg_iters": 3,
+                   "note": "the CPU arm runs ONE rank's batch on all host threads whatever --gpus is"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
-def run_ours(args):
+def pin_to_gpu_numa(local):
+    """Bind this process (and therefore its pinned staging buffers, first-touch) to the CPUs NVML reports as local to the GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "bound to %d CPUs local to GPU %d" % (len(cpus), local)
+        return "NVML reports no local CPUs inside this cgroup"
+    except Exception as e:       # no NVML / not permitted: measured as is
+        return "not bound (%s)" % type(e).__name__
+
+
+def load_traffic():
+    """ncu DRAM bytes of the dominant kernels, written by tools/ncu_traffic.py from the round's `ncu --set full` captures
+    (profiles/traffic.json).  None when no capture of the current kernels is committed -- never a stale constant."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def make_module(B, dev, rank, train=False):
+    import numpy as np
+    import torch
+    from argparse import Namespace
+    from airpose_b200 import synthetic
+    from airpose_b200.copenet_twoview import copenet_twoview
+    tmp = tempfile.mkdtemp(prefix="airpose_bench_%d_" % rank)
+    mp = synthetic.write_mean_params(os.path.join(tmp, "smpl_mean_params.npz"))
+    synthetic.write_smplx_model(tmp, 0)
+    mod = copenet_twoview(Namespace(smpl_mean_params=mp, smplx_model_dir=tmp, batch_size=B, val_batch_size=B, reg_iters=3, lr=5e-5))
+    sd = synthetic.make_network_state(123, dec_gain=0.01) if train else synthetic.make_network_state(123)
+    mod.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()})
+    mod = mod.to(dev)
+    return mod.train() if train else mod.eval()
+
+
+def make_sets(B, dev, gen, nsets):
+    import torch
+    intr = torch.tensor([[1475.0, 0, 960.0], [0, 1475.0, 540.0], [0, 0, 1.0]], device=dev).expand(B, 3, 3).contiguous()
+    sets = []
+    for _ in range(nsets):
+        s = {"intr0": intr, "intr1": intr}
+        for v in (0, 1):
+            s["im%d" % v] = torch.randn(B, 3, 224, 224, device=dev, generator=gen)
+            bb = torch.rand(B, 3, device=dev, generator=gen)
+            bb[:, :2] = bb[:, :2] * 2 - 1
+            bb[:, 2] = bb[:, 2] * 1.9 + 0.1
+            s["bb%d" % v] = bb
+        sets.append(s)
+    return sets
+
+
+def train_leg(dev, world, rank, steps, warmup, sync_all):
+    """BASELINE.json configs[3]: the whole-network training step (forward, loss, backward, gradient all-reduce, Adam(amsgrad))
+    at 32 pairs per GPU (256 pairs on 8 GPUs), copenet_twoview.py:376-425 + DDP.  Returns the `train_step` object."""
     import numpy as np
     import torch
     import torch.distributed as dist
-    from argparse import Namespace
-    from airpose_b200 import _lib, synthetic
-    from airpose_b200.copenet_twoview import copenet_twoview
+    from airpose_b200 import parallel, synthetic
+    B = 32
+    mod = make_module(B, dev, rank, train=True)
+    opt = mod.configure_optimizers()
+    x = synthetic.make_inputs(B, 123 + rank)
+    li = synthetic.make_lbs_inputs(B, seed=9 + rank)
+    rng = np.random.default_rng(5 + rank)
+    with torch.no_grad():
+        gt_out = mod.smplx.forward(betas=torch.from_numpy(li["betas"]).to(dev), body_pose=torch.from_numpy(li["body_pose"]).to(dev), pose2rot=False)
+    r6 = lambda: synthetic.rot6d_to_rotmat_np(np.array([1, 0, 0, 1, 0, 0], np.float32) + rng.standard_normal((B, 6)).astype(np.float32) * 0.3)[:, None]
+    gt = {"smplpose_rotmat": li["body_pose"], "smplorient_rel0": r6(), "smplorient_rel1": r6(),
+          "smpl_joints_2d0": (rng.standard_normal((B, 1, 127, 2)) * 50 + 500).astype(np.float32),
+          "smpl_joints_2d1": (rng.standard_normal((B, 1, 127, 2)) * 50 + 500).astype(np.float32)}
+    batch = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in {**x, **gt}.items()}
+    batch["smpl_vertices"], batch["smpl_joints"] = gt_out.vertices[:, None].contiguous(), gt_out.joints[:, None].contiguous()
+    for _ in range(warmup):
+        mod.training_step(batch, opt)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, _ = mod.training_step(batch, opt)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1) / steps
+    ar_ms = 0.0
+    if world > 1:            # the collective alone: the same all-reduce of the flat gradient buffer, back to back
+        for _ in range(2):
+            opt.allreduce_grads()
+        sync_all()
+        e0.record()
+        for _ in range(5):
+            opt.allreduce_grads()
+        e1.record()
+        sync_all()
+        ar_ms = e0.elapsed_time(e1) / 5
+    chk = torch.stack([opt.flat.double().sum(), opt.flat.double().abs().sum()])
+    same = True
+    if world > 1:
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(lo, hi))
+    ms, ar_ms = parallel.max_over_ranks([ms, ar_ms], device=dev)
+    finite = bool(torch.isfinite(loss).item())
+    del mod, opt
+    torch.cuda.empty_cache()
+    return {"workload": "copenet_twoview train step (fwd + loss + bwd + grad all-reduce + Adam amsgrad), 32 pairs per GPU (BASELINE.json configs[3]: 256 pairs on 8 GPUs)",
+            "pairs_per_gpu": B, "global_pairs": world * B, "steps": steps, "ms_per_step": ms, "pairs_per_s": world * B / (ms * 1e-3),
+            "allreduce_ms": ar_ms, "allreduce_bytes": 0 if world == 1 else int(108.4e6),
+            "allreduce_note": "one NCCL all-reduce of the flat fp32 gradient buffer per step, timed alone back to back; inside the step it follows the last backward kernel",
+            "tensor_tflops": 3 * 2 * B * GFLOP_PER_IMAGE / (ms * 1e-3) / 1e3, "params_identical_across_ranks": same, "loss_finite": finite}
+
+
+def torch_gpu_leg(pairs, steps=8, warmup=3):
+    """north_star's denominator: the reference algorithm through stock PyTorch (cuDNN / cuBLAS) on the SAME B200, in the same run:
+    tools/torch_gpu_baseline.py (fp32, TF32, autocast(bf16) + channels_last).  Baseline infrastructure, outside every timed region of ours."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import torch_gpu_baseline as tgb
+        return tgb.measure(pairs, steps, warmup)
+    except Exception as e:       # the leg must never take the bench line down
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from airpose_b200 import _lib, parallel, synthetic
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: airpose_b200 has no CPU path (use --impl reference for the CPU arm)")
+    numa = pin_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     # rank 0 prints ONE JSON line: this image exports NCCL_DEBUG=VERSION, which makes NCCL print "NCCL version ..." on stdout
@@ -145,29 +284,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     B = args.pairs
-    tmp = tempfile.mkdtemp(prefix="airpose_bench_%d_" % rank)
-    mp = synthetic.write_mean_params(os.path.join(tmp, "smpl_mean_params.npz"))
-    synthetic.write_smplx_model(tmp, 0)
-    mod = copenet_twoview(Namespace(smpl_mean_params=mp, smplx_model_dir=tmp, batch_size=B, val_batch_size=B, reg_iters=3))
-    mod.model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in synthetic.make_network_state(123).items()})
-    mod = mod.to(dev).eval()
+    mod = make_module(B, dev, rank)
 
     # synthetic inputs: NSETS distinct batches rotated so a step's inputs are never L2-resident
     NSETS = 4
     gen = torch.Generator(device=dev).manual_seed(123 + rank)
-    intr = torch.tensor([[1475.0, 0, 960.0], [0, 1475.0, 540.0], [0, 0, 1.0]], device=dev).expand(B, 3, 3).contiguous()
-
-    def make_set():
-        s = {"intr0": intr, "intr1": intr}
-        for v in (0, 1):
-            s["im%d" % v] = torch.randn(B, 3, 224, 224, device=dev, generator=gen)
-            bb = torch.rand(B, 3, device=dev, generator=gen)
-            bb[:, :2] = bb[:, :2] * 2 - 1
-            bb[:, 2] = bb[:, 2] * 1.9 + 0.1
-            s["bb%d" % v] = bb
-        return s
-
-    sets = [make_set() for _ in range(NSETS)]
+    sets = make_sets(B, dev, gen, NSETS)
     set_bytes = 2 * B * 3 * 224 * 224 * 4
 
     def sync_all():
@@ -198,6 +320,24 @@ def run_ours(args):
     trunk_ms = sum(p["trunk"][0].elapsed_time(p["trunk"][1]) for p in prof) / len(prof)
     ief_ms = sum(p["ief"][0].elapsed_time(p["ief"][1]) for p in prof) / len(prof)
     smplx_ms = sum(p["smplx"][0].elapsed_time(p["smplx"][1]) for p in prof) / len(prof)
+
+    # ------------------------------------------------------------------ sustained leg: the same step for >= SUSTAIN_S seconds
+    sus_steps = max(args.steps, int(args.sustain_s * 1e3 / ms) + 1) if args.sustain_s > 0 else 0
+    sus_ms = trunk_sus_ms = None
+    if sus_steps:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        sprof = []
+        sync_all()
+        ev[0].record()
+        for i in range(sus_steps):
+            p = {} if i % 16 == 0 else None
+            mod.fwd_pass(sets[i % NSETS], profile=p)
+            if p is not None:
+                sprof.append(p)
+        ev[1].record()
+        sync_all()
+        sus_ms = ev[0].elapsed_time(ev[1]) / sus_steps
+        trunk_sus_ms = sum(p["trunk"][0].elapsed_time(p["trunk"][1]) for p in sprof) / len(sprof)
 
     # ------------------------------------------------------------------ end to end from pinned host memory
     copy_stream = torch.cuda.Stream(device=dev)
@@ -250,21 +390,8 @@ def run_ours(args):
         sync_all()
         return e0.elapsed_time(e1) / args.steps, h2d, d2h
 
-    # (1) the reference's batch format: fp32 normalised images in pinned host memory (copenet_twoview.py:166-183)
-    host_sets = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in sets[:2]]
-    e2e_ms, h2d, d2h = run_e2e(host_sets, lambda s: s)
-    # what the host link of THIS box delivers for exactly that copy (explains e2e when it is PCIe-bound)
-    with torch.cuda.stream(copy_stream):
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record(copy_stream)
-        for _ in range(3):
-            tmp_dev = {k: v.to(dev, non_blocking=True) for k, v in host_sets[0].items()}
-        c1.record(copy_stream)
-    copy_stream.synchronize()
-    h2d_gbs = 3 * h2d / (c0.elapsed_time(c1) * 1e-3) / 1e9
-    del tmp_dev
-    # (2) the wire / dataset format: u8 BGR 224 x 224 crops (airpose_server/server.py:38,91-98), normalised on the device by
-    # airpose_preprocess_bgr8 inside the timed region -- a quarter of the bytes over the host link
+    # (1) HEADLINE e2e -- the dataset / wire format: u8 BGR 224 x 224 crops (dsets/aerialpeople.py:125-141 reads u8 frames;
+    # airpose_server/server.py:38,91-98), normalised on the device by airpose_preprocess_bgr8 inside the timed region
     from airpose_b200.preprocess import bgr8_to_normalized
     host_sets_u8 = []
     for s in sets[:2]:
@@ -276,7 +403,20 @@ def run_ours(args):
     def prepare_u8(sd):
         return {k: (bgr8_to_normalized(v) if k.startswith("im") else v) for k, v in sd.items()}
 
-    e2e_u8_ms, h2d_u8, _ = run_e2e(host_sets_u8, prepare_u8)
+    e2e_ms, h2d, d2h = run_e2e(host_sets_u8, prepare_u8)
+    # (2) the reference's in-memory batch format: fp32 normalised images in pinned host memory (copenet_twoview.py:166-183)
+    host_sets = [{k: v.cpu().pin_memory() for k, v in s.items()} for s in sets[:2]]
+    e2e_f32_ms, h2d_f32, _ = run_e2e(host_sets, lambda s: s)
+    # what the host link of THIS box delivers for exactly that copy (explains e2e_fp32 when it is PCIe-bound)
+    with torch.cuda.stream(copy_stream):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(copy_stream)
+        for _ in range(3):
+            tmp_dev = {k: v.to(dev, non_blocking=True) for k, v in host_sets[0].items()}
+        c1.record(copy_stream)
+    copy_stream.synchronize()
+    h2d_gbs = 3 * h2d_f32 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del tmp_dev, host_sets, host_sets_u8
     clocks = sampler.stop() if rank == 0 else None
 
     # ------------------------------------------------------------------ SMPL-X lbs() roofline at config 3 (rank 0, N=1)
@@ -295,46 +435,100 @@ def run_ours(args):
         torch.cuda.synchronize()
         lbs_ms = e0.elapsed_time(e1) / 5
         lbs = (nb, lbs_ms)
+        del betas, body
 
-    from airpose_b200 import parallel
-    ms, e2e_ms, trunk_ms, e2e_u8_ms = parallel.max_over_ranks([ms, e2e_ms, trunk_ms, e2e_u8_ms], device=dev)
+    # ------------------------------------------------------------------ BASELINE.json configs[4]: 256 pairs per GPU (2048 on 8 GPUs)
+    big = None
+    if not args.no_extra_legs and B != 256:
+        del mod, sets
+        torch.cuda.empty_cache()
+        BB, nb_sets, bsteps = 256, 2, max(5, args.steps // 4)
+        modb = make_module(BB, dev, rank)
+        bsets = make_sets(BB, dev, gen, nb_sets)           # 2 x 308 MB of images: every step's inputs come from HBM
+        for i in range(3):
+            modb.fwd_pass(bsets[i % nb_sets])
+        sync_all()
+        e0.record()
+        for i in range(bsteps):
+            modb.fwd_pass(bsets[i % nb_sets])
+        e1.record()
+        sync_all()
+        big = (BB, bsteps, e0.elapsed_time(e1) / bsteps)
+        del modb, bsets
+        torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ BASELINE.json configs[3]: training step
+    train = None
+    if not args.no_extra_legs:
+        train = train_leg(dev, world, rank, max(5, args.steps // 4), 3, sync_all)
+
+    ms, e2e_ms, trunk_ms, e2e_f32_ms = parallel.max_over_ranks([ms, e2e_ms, trunk_ms, e2e_f32_ms], device=dev)
+    if sus_steps:
+        sus_ms, trunk_sus_ms = parallel.max_over_ranks([sus_ms, trunk_sus_ms], device=dev)
+    if big:
+        big = (big[0], big[1], parallel.max_over_ranks([big[2]], device=dev)[0])
     if rank == 0:
         peaks = load_peaks()
+        traffic = load_traffic()
         value = world * B / (ms * 1e-3)
         tf = 2 * B * GFLOP_PER_IMAGE / (trunk_ms * 1e-3) / 1e3
+        tr = traffic.get("trunk")
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "copenet_twoview fwd batch=64 pairs 224x224 bf16 trunk / fp32 SMPL-X (BASELINE.json configs[1])",
+            "config": {"workload": WORKLOAD,
                        "pairs_per_gpu": B, "global_pairs": world * B, "reg_iters": 3, "parallelism": "batch-sharded x%d, no collective" % world,
-                       "l2": "inputs rotate over %d distinct batches (%.0f MB) so no step's inputs are L2-resident" % (NSETS, NSETS * set_bytes / 1e6)},
+                       "l2": "inputs rotate over %d distinct batches (%.0f MB) so no step's inputs are L2-resident" % (NSETS, NSETS * set_bytes / 1e6),
+                       "host": numa},
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "h2d_gbs_measured": h2d_gbs, "h2d_bound_value": world * B / (h2d / (h2d_gbs * 1e9)),
-                    "note": "pinned host fp32 images -> H2D (double-buffered on a copy stream) -> fwd_pass -> D2H of pose/betas/vertices_cam/joints_cam/joints_2d into pinned buffers on a third stream; the timed region ends with a device-wide synchronize, so every copy is inside it. h2d_gbs_measured = this box's host->device rate for the same copy; h2d_bound_value = the pairs/s that rate alone allows (e2e is PCIe-bound when it is below `value`)"},
-            "e2e_u8": {"value": world * B / (e2e_u8_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
-                       "note": "same pipeline from u8 BGR crops (the drone server's wire format), normalised on the device by airpose_preprocess_bgr8 inside the timed region"},
+                    "note": "public API (bgr8_to_normalized + copenet_twoview.fwd_pass) from pinned host memory: u8 BGR 224x224 crops (the dataset's / drone server's image format) + bb/intr -> H2D (double-buffered on a copy stream) -> airpose_preprocess_bgr8 -> fwd_pass -> D2H of pose/betas/vertices_cam/joints_cam/joints_2d into pinned buffers on a third stream; the timed region ends with a device-wide synchronize, so every copy is inside it"},
+            "e2e_fp32": {"value": world * B / (e2e_f32_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_f32, "d2h_bytes_per_step": d2h,
+                         "h2d_gbs_measured": h2d_gbs, "h2d_bound_value": world * B / (h2d_f32 / (h2d_gbs * 1e9)),
+                         "note": "same pipeline fed with already-normalised fp32 images (the reference's in-memory batch format): 4x the bytes over the host link; h2d_gbs_measured = this box's host->device rate for that copy, h2d_bound_value = the pairs/s that rate alone allows"},
             "gpu_launches": launches,
             "stage_ms": {"trunk": trunk_ms, "ief": ief_ms, "smplx_x2": smplx_ms},
-            "roofline": {"bound": "tensor", "kernel": "gemm_tma_kernel / gemm_sk_kernel (tcgen05 implicit-GEMM convs of the ResNet-50 trunk, both views; 77 launches per 128 images)",
-                         "achieved": tf, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tflops_sustained"],
-                         "traffic": TRUNK_DRAM_BYTES_PER_64_PAIRS * B / 64.0,
-                         "traffic_note": "bytes per step summed over the trunk's GEMM launches (ncu, profiles/r01s_ncu_full_trunk_128img.csv); algorithmic HBM bytes 56.4 MB/image",
-                         "peak_source": peaks["source"] + ", sustained bf16"},
+            "roofline": {"bound": "tensor", "kernel": "tcgen05 conv kernels of the ResNet-50 trunk, both views (stem_pool_kernel, bneck_tail_kernel, gemm_tma_kernel, gemm_sk_kernel, gemm_sk2_kernel)",
+                         "achieved": tf, "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": tf / peaks["tflops_burst"],
+                         "frac_of_sustained_peak": tf / peaks["tflops_sustained"],
+                         "traffic": (tr["dram_bytes_per_128_images"] * B / 64.0) if tr else None,
+                         "traffic_note": (tr["source"] if tr else "no ncu --set full capture of the current kernels committed") + "; algorithmic HBM bytes 56.4 MB/image layer by layer",
+                         "peak_source": peaks["source"] + ", burst bf16 (the %.0f ms timed region runs at burst clocks)" % (ms * args.steps)},
             "clocks": clocks,
         }
+        if sus_steps:
+            tfs = 2 * B * GFLOP_PER_IMAGE / (trunk_sus_ms * 1e-3) / 1e3
+            out["sustained"] = {"value": world * B / (sus_ms * 1e-3), "unit": UNIT, "steps": sus_steps, "seconds": sus_steps * sus_ms * 1e-3,
+                                "ms_per_step": sus_ms, "trunk_ms": trunk_sus_ms, "trunk_tflops": tfs,
+                                "frac_of_sustained_peak": tfs / peaks["tflops_sustained"],
+                                "note": "the device-resident step repeated back to back; `clocks` covers this leg too"}
+        if big:
+            out["pairs256"] = {"workload": "copenet_twoview fwd batch=256 pairs per GPU (BASELINE.json configs[4]: 2048 pairs on 8 GPUs, batch-sharded, no collective)",
+                               "value": world * big[0] / (big[2] * 1e-3), "unit": UNIT, "pairs_per_gpu": big[0], "global_pairs": world * big[0],
+                               "steps": big[1], "ms_per_step": big[2]}
+        if train:
+            train["tensor_frac"] = train["tensor_tflops"] / peaks["tflops_burst"]
+            out["train_step"] = train
         if lbs:
             nb, lbs_ms = lbs
             gbs = (nb * LBS_BYTES_PER_MESH + LBS_CONST_BYTES) / (lbs_ms * 1e-3) / 1e9
+            tl = traffic.get("lbs")
             out["roofline_lbs"] = {"bound": "hbm", "kernel": "smplx_vertex_tc_kernel (+pose/joints kernels), lbs() batch=%d" % nb,
                                    "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
-                                   "meshes_per_s": nb / (lbs_ms * 1e-3), "traffic": 1095.5e6,
-                                   "traffic_note": "dram read+write of smplx_vertex_tc_kernel per launch at B=8192 (ncu, profiles/r01s_ncu_full_lbs_b8192.csv)",
+                                   "ms": lbs_ms, "meshes_per_s": nb / (lbs_ms * 1e-3), "traffic": tl["dram_bytes_per_launch"] if tl else None,
+                                   "traffic_note": tl["source"] if tl else "no ncu --set full capture of the current kernel committed",
                                    "peak_source": peaks["source"]}
+            if not args.no_extra_legs:
+                tg = torch_gpu_leg(B)
+                best = max([v["pairs_per_s"] for v in tg.values() if isinstance(v, dict) and "pairs_per_s" in v], default=None)
+                tg["ours_over_best_torch_gpu"] = (value / best) if best else None
+                tg["ours_over_torch_gpu_fp32"] = (value / tg["fp32"]["pairs_per_s"]) if "fp32" in tg else None
+                tg["note"] = "the reference algorithm through stock PyTorch on this B200 in this run (north_star's 10x denominator); `value` of this line divided by it"
+                out["torch_gpu_baseline"] = tg
             if not args.no_cpu_baseline:
-                v, cms, cores = cpu_reference(CPU_SAMPLE_PAIRS, 3, 1)
-                out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                       "sample": "%d pairs per step x 3 steps (1 warm-up), fp32, PyTorch-CPU port of the reference (oracle/torch_port.py)" % CPU_SAMPLE_PAIRS}
+                v, cms, cores, kind, what = cpu_reference(CPU_SAMPLE_PAIRS, 3, 1)
+                out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                                       "sample": "%d pairs per step x 3 steps (1 warm-up): %s" % (CPU_SAMPLE_PAIRS, what)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -348,6 +542,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the pairs256 / train_step / torch_gpu_baseline legs")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="length of the sustained leg in seconds (0: off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
