@@ -150,11 +150,21 @@ __global__ void __launch_bounds__(kMaxJoints) smplx_pose_kernel(SmplxDev m, Pose
         a.fl[(size_t)b * kTcK + (j - 1) * 9 + e] = __float2half_rn(f - __half2float(hi));
       }
     }
-    if (j < kTcK - 189) {                                        // zero the K padding
+    if (j < kTcKPose - 189) {                                    // zero the K padding of the pose blocks
       a.fh[(size_t)b * kTcK + 189 + j] = __float2half_rn(0.f);
       a.fl[(size_t)b * kTcK + 189 + j] = __float2half_rn(0.f);
     }
-    if (j < 12) rec[2 * (kTcRecBetas + j)] = j < a.nb ? beta_s[j] : 0.f;
+    if (j < kTcKShape) {                                         // template / shape k-block (smplx.cuh): 1 1 | b_hi | b_lo | b_hi
+      float val = 1.f;
+      if (j >= 2) {
+        const int l = (j - 2) % 10;
+        const float be = l < a.nb ? beta_s[l] : 0.f;
+        const float hi = __half2float(__float2half_rn(be));
+        val = (j >= 12 && j < 22) ? be - hi : hi;
+      }
+      a.fh[(size_t)b * kTcK + kTcKPose + j] = __float2half_rn(val);
+      a.fl[(size_t)b * kTcK + kTcKPose + j] = __float2half_rn(0.f);
+    }
     if (j >= 12 && j < 21) rec[2 * (kTcRecCam + (j - 12))] = a.root_R ? __ldg(a.root_R + (size_t)b * a.root_R_stride + (j - 12))
                                                                         : (((j - 12) % 4 == 0) ? 1.f : 0.f);
     if (j >= 21 && j < 24) rec[2 * (kTcRecCam + 9 + (j - 21))] = a.root_t ? __ldg(a.root_t + (size_t)b * a.root_t_stride + (j - 21)) : 0.f;

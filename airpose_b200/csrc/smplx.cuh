@@ -31,11 +31,16 @@ struct SmplxDev {
 
 // ---- tensor-core path (hot path only: 21 body rotations given, joints 22.. identity, <= 10 betas)
 constexpr int kTcBodyJoints = 22;              // joints whose A matrix is distinct on the hot path
-constexpr int kTcK = 192;                      // 21*9 = 189 pose features padded to 3 k-blocks of 64
+constexpr int kTcKPose = 192;                  // 21*9 = 189 pose features padded to 3 k-blocks of 64
+constexpr int kTcKShape = 32;                  // one 32-wide k-block: template + shape blend as split-fp16 products (below)
+constexpr int kTcK = kTcKPose + kTcKShape;     // row length of P and F
+// columns 192..223 -- vertex side (P):  T_hi  T_lo | S_hi[0..9] | S_hi[0..9] | S_lo[0..9]     (all x 2^10)
+//                     mesh side (F_hi): 1     1    | b_hi[0..9] | b_lo[0..9] | b_hi[0..9]
+// so that D = 2^10 (v_template + shapedirs . beta + posedirs . feat) to ~2^-22 relative (the S_lo b_lo term is dropped)
 constexpr int kTcMeshTile = 32;                // meshes per MMA tile (N)
-constexpr int kTcSub = 16;                     // meshes per record sub-batch (one bulk copy)
-constexpr int kTcRecFloats = 292;              // per-mesh record: A[22][12] | betas[10]+pad2 | camR[9] camt[3] | transl[3] pad
-constexpr int kTcRecBetas = 264, kTcRecCam = 276, kTcRecTransl = 288;
+constexpr int kTcSub = 8;                      // meshes per record sub-batch (one bulk copy, one epilogue warp's share of a tile)
+constexpr int kTcRecFloats = 280;              // per-mesh record: A[22][12] | camR[9] camt[3] | transl[3] pad
+constexpr int kTcRecCam = 264, kTcRecTransl = 276;
 constexpr int kTcMaxKW = 8;
 constexpr float kTcPScale = 1024.f;            // posedirs are stored as fp16(P * 2^10): keeps small entries normal
 
@@ -43,8 +48,9 @@ struct SmplxTc {
   bool ok = false;             // model supports the tensor-core path
   int KW = 0;                  // max non-zeros per vertex after folding joints 22.. onto their body ancestor
   int vtiles = 0;              // ceil(V / 128)
-  __half* P = nullptr;         // [3][vtiles*128][192] fp16, coordinate-major, K-major rows
-  CUtensorMap tmP;
+  __half* P = nullptr;         // [3][vtiles*128][224] fp16, coordinate-major, K-major rows
+  CUtensorMap tmP;             // 64-column boxes (128-byte swizzle): the pose k-blocks
+  CUtensorMap tmPx;            // 32-column boxes (64-byte swizzle): the template / shape k-block
   const int* sk_off = nullptr; // [KW][V] byte offset of the joint's A inside a record (j*48)
   const float* sk_w = nullptr; // [KW][V]
   const int* sk_cnt = nullptr; // [V]
@@ -52,9 +58,9 @@ struct SmplxTc {
 
 struct TcCall {
   int B, nb, has_transl;
-  const float* rec;            // [Bpad][292]
-  const __half* fh;            // [B][192]
-  const __half* fl;            // [B][192]
+  const float* rec;            // [Bpad][280], pairs of meshes element-interleaved
+  const __half* fh;            // [B][224]
+  const __half* fl;            // [B][224]
   float* out;                  // [B,V,3]
   float* out_cam;              // [B,V,3] or null
 };

@@ -8,25 +8,29 @@
 //
 // The pose-corrective term  offsets[b, 3v+c] = sum_p feat[b,p] * posedirs[p, 3v+c]  (189 x 3 FMAs per
 // vertex and mesh) is what bound the first kernel (2 % of the HBM roofline).  Here
-//   D_c[v, b] = P_c[v, :] . F[b, :]^T      c = x,y,z;  M = 128 vertices, N = 32 meshes, K = 192
-// runs on tcgen05 with P = fp16(posedirs * 2^10) RESIDENT in shared memory (144 KB per 128-vertex
+//   D_c[v, b] = P_c[v, :] . F[b, :]^T      c = x,y,z;  M = 128 vertices, N = 32 meshes, K = 192 + 32
+// runs on tcgen05 with P = fp16(posedirs * 2^10) RESIDENT in shared memory (168 KB per 128-vertex
 // tile) and the feature F = R - I split into two fp16 terms (hi + lo, 22 significant bits) streamed
 // through a TMA ring: 2 MMAs per k-step, fp32 accumulation in TMEM.  The only rounding beyond fp32 is
 // the 11-bit mantissa of the stored posedirs: <= 1e-5 of the vertex scale (tests; north_star 1e-3).
+// Round 2: the template and the SHAPE BLEND ride the same contraction as one more 32-wide k-block of
+// split-fp16 products (smplx.cuh: T_hi T_lo | S_hi | S_hi | S_lo  against  1 1 | b_hi | b_lo | b_hi), so
+// D * 2^-10 IS v_posed: 30 FMAs, 5 shared loads and 30 registers per vertex and mesh leave the epilogue,
+// which is what lets it run on 16 warps instead of 8 (it was issue/latency-bound at 17 % warp occupancy).
 //
 // Everything else stays fp32 on the CUDA cores, in the epilogue, straight out of TMEM (TMEM lane =
 // vertex, so per-vertex constants live in registers and a warp's stores of one mesh are contiguous):
-//   v_shaped = v_template + shapedirs . beta;  v_posed = v_shaped + D * 2^-10
+//   v_posed = D * 2^-10
 //   T = sum_k w_k A[b, joint_k]  over the vertex's non-zero skinning weights (A per mesh in smem)
 //   v = T [v_posed; 1] + transl;  v_cam = R v + t
 // On this call pattern A_j == A_ancestor(j) for every joint j >= 22 (identity local rotation:
 // G_j = G_p [I | J_j - J_p]  =>  A_j = [R_p | t_p + R_p (J_j - J_p) - R_p J_j] = A_p), so only 22
 // matrices per mesh are staged and the weights of folded joints are merged at create time.
 //
-// CTA = (128-vertex tile, range of mesh tiles), 11 warps:
-//   warp 0   TMA: P once, then F k-blocks (3-stage ring)      warp 1   MMA issuer (TMEM double-buffered)
-//   warp 2   bulk copies of per-mesh records (A, betas, camera; 16 meshes per copy, 3-stage ring)
-//   warps 3-10  epilogue: lane quarter = warp % 4, mesh half = (warp - 3) / 4
+// CTA = (128-vertex tile, range of mesh tiles), 19 warps:
+//   warp 0   TMA: P once, then F k-blocks (2-stage ring)      warp 1   MMA issuer (TMEM double-buffered)
+//   warp 2   bulk copies of per-mesh records (A, camera, transl; 8 meshes per copy, 4-stage ring)
+//   warps 3-18  epilogue: lane quarter = warp % 4, mesh quarter (8 of the tile's 32 meshes) = (warp - 3) / 4
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -41,15 +45,20 @@ namespace airpose {
 
 namespace {
 
-constexpr int kThreads = 352;
+constexpr int kThreads = 608;
 constexpr int kEpiWarp0 = 3;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kEpiGroups = kEpiWarps / 4;              // mesh quarters of a tile
 constexpr int kPTileBytes = 128 * 128;                 // 128 vertices x 64 fp16
-constexpr int kPBytes = 9 * kPTileBytes;               // 3 coordinates x 3 k-blocks
-constexpr int kFStages = 3;
+constexpr int kPxTileBytes = 128 * 64;                 // 128 vertices x 32 fp16 (template / shape k-block, 64-byte swizzle)
+constexpr int kPxOff = 9 * kPTileBytes;
+constexpr int kPBytes = 9 * kPTileBytes + 3 * kPxTileBytes;   // 3 coordinates x (3 pose k-blocks + the shape k-block)
+constexpr int kFStages = 2;
 constexpr int kFHalfBytes = kTcMeshTile * 128;         // 32 meshes x 64 fp16
 constexpr int kFStageBytes = 2 * kFHalfBytes;          // hi + lo
-constexpr int kRStages = 3;
+constexpr int kFxBytes = kTcMeshTile * 64;             // shape k-block: 32 meshes x 32 fp16, hi only
+constexpr int kRStages = 4;
+static_assert(kTcMeshTile == kEpiGroups * kTcSub, "one record sub-batch per epilogue group and tile");
 constexpr int kRecBytes = kTcRecFloats * 4;
 constexpr int kRStageBytes = kTcSub * kRecBytes;
 constexpr int kFOff = kPBytes;
@@ -64,8 +73,6 @@ static_assert(kRStageBytes % 16 == 0 && kROff % 16 == 0, "bulk copies need 16-by
 struct KArgs {
   int V, B, nb, NS, KW, has_transl;
   int tiles_total, tiles_per_cta;
-  const float* v_template;
-  const float* shapedirs;
   const int* sk_off;
   const float* sk_w;
   const int* sk_cnt;
@@ -128,8 +135,9 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
 
 template <bool kHasCam, int UN>
 __global__ void __launch_bounds__(kThreads, 1)
-smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmFh,
-                       const __grid_constant__ CUtensorMap tmFl, const KArgs a) {
+smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmPx,
+                       const __grid_constant__ CUtensorMap tmFh, const __grid_constant__ CUtensorMap tmFl,
+                       const __grid_constant__ CUtensorMap tmFx, const KArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* p_full = reinterpret_cast<uint64_t*>(smem + kBarOff);
@@ -147,13 +155,12 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
   const int t1 = min(a.tiles_total, t0 + a.tiles_per_cta);
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmP);
-    ptx::prefetch_tmap(&tmFh);
-    ptx::prefetch_tmap(&tmFl);
+    ptx::prefetch_tmap(&tmP); ptx::prefetch_tmap(&tmPx);
+    ptx::prefetch_tmap(&tmFh); ptx::prefetch_tmap(&tmFl); ptx::prefetch_tmap(&tmFx);
     ptx::mbar_init(p_full, 1);
     for (int s = 0; s < kFStages; ++s) { ptx::mbar_init(&f_full[s], 1); ptx::mbar_init(&f_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tfull[s], 1); ptx::mbar_init(&tempty[s], kEpiWarps); }
-    for (int s = 0; s < kRStages; ++s) { ptx::mbar_init(&r_full[s], 1); ptx::mbar_init(&r_empty[s], kEpiWarps / 2); }
+    for (int s = 0; s < kRStages; ++s) { ptx::mbar_init(&r_full[s], 1); ptx::mbar_init(&r_empty[s], 4); }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -169,17 +176,24 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
     // ------------------------------------------------------------------ P (once) + F ring
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(p_full, kPBytes);
-      for (int c = 0; c < 3; ++c)
+      for (int c = 0; c < 3; ++c) {
         for (int kb = 0; kb < 3; ++kb)
           ptx::tma_load_2d(&tmP, p_full, smem + (c * 3 + kb) * kPTileBytes, kb * 64, c * a.vrows + vtile * 128);
+        ptx::tma_load_2d(&tmPx, p_full, smem + kPxOff + c * kPxTileBytes, kTcKPose, c * a.vrows + vtile * 128);
+      }
       int stage = 0; uint32_t phase = 0;
       for (int t = t0; t < t1; ++t)
-        for (int kb = 0; kb < 3; ++kb) {
+        for (int kb = 0; kb < 4; ++kb) {
           ptx::mbar_wait(&f_empty[stage], phase ^ 1, 100 + stage);
           uint8_t* fs = smem + kFOff + stage * kFStageBytes;
-          ptx::mbar_arrive_expect_tx(&f_full[stage], kFStageBytes);
-          ptx::tma_load_2d(&tmFh, &f_full[stage], fs, kb * 64, t * kTcMeshTile);
-          ptx::tma_load_2d(&tmFl, &f_full[stage], fs + kFHalfBytes, kb * 64, t * kTcMeshTile);
+          if (kb < 3) {
+            ptx::mbar_arrive_expect_tx(&f_full[stage], kFStageBytes);
+            ptx::tma_load_2d(&tmFh, &f_full[stage], fs, kb * 64, t * kTcMeshTile);
+            ptx::tma_load_2d(&tmFl, &f_full[stage], fs + kFHalfBytes, kb * 64, t * kTcMeshTile);
+          } else {                                      // template / shape block: hi only, 64-byte rows
+            ptx::mbar_arrive_expect_tx(&f_full[stage], kFxBytes);
+            ptx::tma_load_2d(&tmFx, &f_full[stage], fs, kTcKPose, t * kTcMeshTile);
+          }
           if (++stage == kFStages) { stage = 0; phase ^= 1; }
         }
     }
@@ -194,20 +208,31 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
         const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
         ptx::mbar_wait(&tempty[as], aphase ^ 1, 210 + as);
         ptx::tc_fence_after();
-        for (int kb = 0; kb < 3; ++kb) {
+        for (int kb = 0; kb < 4; ++kb) {
           ptx::mbar_wait(&f_full[stage], phase, 220 + stage);
           ptx::tc_fence_after();
           const uint32_t fs = ptx::smem_u32(smem + kFOff + stage * kFStageBytes);
-          const uint64_t bh = ptx::make_kmajor_sw128_desc(fs);
-          const uint64_t bl = ptx::make_kmajor_sw128_desc(fs + kFHalfBytes);
+          if (kb < 3) {
+            const uint64_t bh = ptx::make_kmajor_sw128_desc(fs);
+            const uint64_t bl = ptx::make_kmajor_sw128_desc(fs + kFHalfBytes);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const uint64_t ad = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + (c * 3 + kb) * kPTileBytes));
-            const uint32_t d_tmem = tmem_base + as * 96 + c * kTcMeshTile;
+            for (int c = 0; c < 3; ++c) {
+              const uint64_t ad = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + (c * 3 + kb) * kPTileBytes));
+              const uint32_t d_tmem = tmem_base + as * 96 + c * kTcMeshTile;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              ptx::umma_bf16(d_tmem, ad + 2 * k, bh + 2 * k, idesc, (kb | k) != 0);
-              ptx::umma_bf16(d_tmem, ad + 2 * k, bl + 2 * k, idesc, 1);
+              for (int k = 0; k < 4; ++k) {
+                ptx::umma_bf16(d_tmem, ad + 2 * k, bh + 2 * k, idesc, (kb | k) != 0);
+                ptx::umma_bf16(d_tmem, ad + 2 * k, bl + 2 * k, idesc, 1);
+              }
+            }
+          } else {                                      // K = 32: template + shape blend (64-byte swizzled rows)
+            const uint64_t bx = ptx::make_kmajor_desc(fs, 64);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              const uint64_t ad = ptx::make_kmajor_desc(ptx::smem_u32(smem + kPxOff + c * kPxTileBytes), 64);
+              const uint32_t d_tmem = tmem_base + as * 96 + c * kTcMeshTile;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) ptx::umma_bf16(d_tmem, ad + 2 * k, bx + 2 * k, idesc, 1);
             }
           }
           ptx::umma_commit(&f_empty[stage]);
@@ -221,7 +246,7 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
     if (lane == 0) {
       int s = 0;
       for (int t = t0; t < t1; ++t)
-        for (int hf = 0; hf < 2; ++hf, ++s) {
+        for (int hf = 0; hf < kEpiGroups; ++hf, ++s) {
           const int slot = s % kRStages; const uint32_t ph = (s / kRStages) & 1;
           ptx::mbar_wait(&r_empty[slot], ph ^ 1, 300 + slot);
           ptx::mbar_arrive_expect_tx(&r_full[slot], kRStageBytes);
@@ -232,17 +257,11 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
   } else {
     // ------------------------------------------------------------------ epilogue
     const int quad = warp & 3;                        // TMEM lane quarter this warp may read
-    const int hf = (warp - kEpiWarp0) >> 2;           // which 16 meshes of the tile
+    const int hf = (warp - kEpiWarp0) >> 2;           // which 8 meshes of the tile
     const int v = vtile * 128 + quad * 32 + lane;
     const bool valid = v < a.V;
     const int vc = valid ? v : a.V - 1;
     // per-vertex constants
-    const float vt0 = __ldg(a.v_template + vc * 3), vt1 = __ldg(a.v_template + vc * 3 + 1), vt2 = __ldg(a.v_template + vc * 3 + 2);
-    float S[3][10];
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int l = 0; l < 10; ++l) S[c][l] = l < a.nb ? __ldg(a.shapedirs + ((size_t)vc * 3 + c) * a.NS + l) : 0.f;
     const int cnt = __ldg(a.sk_cnt + vc);
     int joff[kTcMaxKW]; float jw[kTcMaxKW];
 #pragma unroll
@@ -256,7 +275,7 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
     int it = 0;
     for (int t = t0; t < t1; ++t, ++it) {
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
-      const int s = 2 * it + hf;
+      const int s = kEpiGroups * it + hf;
       const int slot = s % kRStages; const uint32_t rph = (s / kRStages) & 1;
       ptx::mbar_wait(&tfull[as], aphase, 400 + as);
       ptx::tc_fence_after();
@@ -287,19 +306,10 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
           const bool second = b + 1 < a.B;
           // pair record: field f of meshes (b, b+1) = one float2 at index f
           const uint32_t rec = rbase + (uint32_t)(m >> 1) * 2 * kRecBytes;      // byte address; field f of the pair at rec + 8 f
-          // v_shaped (lbs.py:179) + pose offsets (:203)
-          float2 x = dup2(vt0), y = dup2(vt1), z = dup2(vt2);
-#pragma unroll
-          for (int l = 0; l < 10; l += 2) {
-            const float4 be = lds_f4(rec + 8 * (kTcRecBetas + l));                 // {beta_l(b), beta_l(b+1), beta_l+1(b), beta_l+1(b+1)}
-            const float2 e0 = make_float2(be.x, be.y), e1 = make_float2(be.z, be.w);
-            x = ffma2(dup2(S[0][l]), e0, x); y = ffma2(dup2(S[1][l]), e0, y); z = ffma2(dup2(S[2][l]), e0, z);
-            x = ffma2(dup2(S[0][l + 1]), e1, x); y = ffma2(dup2(S[1][l + 1]), e1, y); z = ffma2(dup2(S[2][l + 1]), e1, z);
-          }
-          const float2 is2 = dup2(inv_scale);
-          x = ffma2(make_float2(__uint_as_float(dx[2 * pi]), __uint_as_float(dx[2 * pi + 1])), is2, x);
-          y = ffma2(make_float2(__uint_as_float(dy[2 * pi]), __uint_as_float(dy[2 * pi + 1])), is2, y);
-          z = ffma2(make_float2(__uint_as_float(dz[2 * pi]), __uint_as_float(dz[2 * pi + 1])), is2, z);
+          // v_posed = v_template + shapedirs . beta + pose offsets (lbs.py:179, :203): all of it is the accumulator
+          const float2 x = make_float2(__uint_as_float(dx[2 * pi]) * inv_scale, __uint_as_float(dx[2 * pi + 1]) * inv_scale);
+          const float2 y = make_float2(__uint_as_float(dy[2 * pi]) * inv_scale, __uint_as_float(dy[2 * pi + 1]) * inv_scale);
+          const float2 z = make_float2(__uint_as_float(dz[2 * pi]) * inv_scale, __uint_as_float(dz[2 * pi + 1]) * inv_scale);
           // T = sum_k w_k A_k (lbs.py:209-213)
           float2 T[12];
 #pragma unroll
@@ -389,11 +399,38 @@ int smplx_tc_create(const airpose_smplx_model_host* mh, const SmplxDev& d, Smplx
     KW = std::max(KW, cnt[v]);
   }
   if (KW > kTcMaxKW) return 0;          // unusually dense skinning: the generic kernel handles it
+  // Slot assignment per WARP of the vertex kernel (32 consecutive vertices): when the union of the joints its vertices use fits
+  // the slot count, slot k means the SAME joint for all 32 lanes (weight 0 where a vertex does not use it), so every shared-
+  // memory load of A_j in the epilogue is a warp-uniform broadcast (1 wavefront instead of 4+: the kernel was bound by the
+  // shared-memory data pipe, profiles/r02y).  Consecutive vertices share their joints, so the union is barely larger than the
+  // densest row (synthetic model: 2.7 vs 2.5 slots on average).  Groups whose union does not fit keep per-lane slots.
+  for (int g0 = 0; g0 < V; g0 += 32) {
+    const int g1 = std::min(V, g0 + 32);
+    std::vector<int> uni;
+    for (int v = g0; v < g1; ++v)
+      for (auto& e : rows[v])
+        if (std::find(uni.begin(), uni.end(), e.first) == uni.end()) uni.push_back(e.first);
+    if ((int)uni.size() > kTcMaxKW) continue;
+    std::sort(uni.begin(), uni.end());
+    for (int v = g0; v < g1; ++v) {
+      std::vector<std::pair<int, float>> r;
+      for (int j : uni) {
+        float w = 0.f;
+        for (auto& e : rows[v])
+          if (e.first == j) w = e.second;
+        r.push_back({j, w});
+      }
+      rows[v] = r;
+      cnt[v] = (int)r.size();
+    }
+    KW = std::max(KW, (int)uni.size());
+  }
   std::vector<int> off((size_t)KW * V, 0);
   std::vector<float> w((size_t)KW * V, 0.f);
   for (int v = 0; v < V; ++v)
     for (int k = 0; k < cnt[v]; ++k) { off[(size_t)k * V + v] = rows[v][k].first * 48; w[(size_t)k * V + v] = rows[v][k].second; }
-  // P[c][v][p] = fp16(posedirs[p][3v+c] * 2^10), p < 189; zero padded to 192 columns / vtiles*128 rows
+  // P[c][v][p] = fp16(posedirs[p][3v+c] * 2^10), p < 189; zero padded to 192 columns / vtiles*128 rows; then the
+  // template / shape k-block (smplx.cuh): T_hi T_lo | S_hi[10] | S_hi[10] | S_lo[10], all x 2^10
   const int vtiles = ceil_div(V, 128), vrows = vtiles * 128;
   std::vector<__half> P((size_t)3 * vrows * kTcK, __float2half_rn(0.f));
   for (int p = 0; p < 189; ++p) {
@@ -401,6 +438,20 @@ int smplx_tc_create(const airpose_smplx_model_host* mh, const SmplxDev& d, Smplx
     for (int v = 0; v < V; ++v)
       for (int c = 0; c < 3; ++c) P[((size_t)c * vrows + v) * kTcK + p] = __float2half_rn(src[(size_t)v * 3 + c] * kTcPScale);
   }
+  auto split = [](float x, __half* hi, __half* lo) {
+    *hi = __float2half_rn(x);
+    *lo = __float2half_rn(x - __half2float(*hi));
+  };
+  for (int v = 0; v < V; ++v)
+    for (int c = 0; c < 3; ++c) {
+      __half* row = &P[((size_t)c * vrows + v) * kTcK + kTcKPose];
+      split(mh->v_template[(size_t)v * 3 + c] * kTcPScale, &row[0], &row[1]);
+      for (int l = 0; l < 10 && l < d.NS; ++l) {
+        __half hi, lo;
+        split(mh->shapedirs[((size_t)v * 3 + c) * d.NS + l] * kTcPScale, &hi, &lo);
+        row[2 + l] = hi; row[12 + l] = hi; row[22 + l] = lo;
+      }
+    }
   __half* dP; int* doff; float* dw; int* dcnt;
   if (device_upload(&dP, P.data(), P.size())) return 1;
   owned->push_back(dP);
@@ -413,11 +464,12 @@ int smplx_tc_create(const airpose_smplx_model_host* mh, const SmplxDev& d, Smplx
   tc->P = dP; tc->sk_off = doff; tc->sk_w = dw; tc->sk_cnt = dcnt;
   tc->KW = KW; tc->vtiles = vtiles;
   if (make_tmap_tiled_bf16(&tc->tmP, dP, (int64_t)3 * vrows, kTcK, kTcK, 128, 64)) return 1;   // 2-byte elements: fp16 rides the bf16 map
+  if (make_tmap_tiled_bf16(&tc->tmPx, dP, (int64_t)3 * vrows, kTcK, kTcK, 128, kTcKShape, 64)) return 1;
   tc->ok = true;
   return 0;
 }
 
-// Mesh tiles per CTA: enough CTAs to fill the SMs, few enough that the 144 KB of P per CTA amortise.
+// Mesh tiles per CTA: enough CTAs to fill the SMs, few enough that the 168 KB of P per CTA amortise.
 static int pick_tiles_per_cta(int vtiles, int tiles_total) {
   const int sms = num_sms();
   double best = 1e30; int best_s = 1;
@@ -439,25 +491,25 @@ int smplx_tc_forward(const SmplxDev& d, const SmplxTc& tc, const TcCall& c, cuda
     AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_tc_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
-  CUtensorMap tmFh, tmFl;
+  CUtensorMap tmFh, tmFl, tmFx;
   if (make_tmap_tiled_bf16(&tmFh, c.fh, c.B, kTcK, kTcK, kTcMeshTile, 64)) return 1;
   if (make_tmap_tiled_bf16(&tmFl, c.fl, c.B, kTcK, kTcK, kTcMeshTile, 64)) return 1;
+  if (make_tmap_tiled_bf16(&tmFx, c.fh, c.B, kTcK, kTcK, kTcMeshTile, kTcKShape, 64)) return 1;
   KArgs a{};
   a.V = d.V; a.B = c.B; a.nb = c.nb; a.NS = d.NS; a.KW = tc.KW; a.has_transl = c.has_transl;
   a.tiles_total = ceil_div(c.B, kTcMeshTile);
   a.tiles_per_cta = pick_tiles_per_cta(tc.vtiles, a.tiles_total);
-  a.v_template = d.v_template; a.shapedirs = d.shapedirs;
   a.sk_off = tc.sk_off; a.sk_w = tc.sk_w; a.sk_cnt = tc.sk_cnt;
   a.rec = c.rec; a.out = c.out; a.out_cam = c.out_cam;
   a.vrows = tc.vtiles * 128;
   dim3 grid(tc.vtiles, ceil_div(a.tiles_total, a.tiles_per_cta));
   static const int un = getenv("AIRPOSE_SMPLX_UNROLL") ? atoi(getenv("AIRPOSE_SMPLX_UNROLL")) : 4;
   if (un == 2) {
-    if (c.out_cam) smplx_vertex_tc_kernel<true, 2><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
-    else smplx_vertex_tc_kernel<false, 2><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
+    if (c.out_cam) smplx_vertex_tc_kernel<true, 2><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a);
+    else smplx_vertex_tc_kernel<false, 2><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a);
   } else {
-    if (c.out_cam) smplx_vertex_tc_kernel<true, 4><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
-    else smplx_vertex_tc_kernel<false, 4><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tmFh, tmFl, a);
+    if (c.out_cam) smplx_vertex_tc_kernel<true, 4><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a);
+    else smplx_vertex_tc_kernel<false, 4><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a);
   }
   AP_LAUNCH_CHECK();
   return 0;

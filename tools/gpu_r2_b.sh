@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, call B: SMPL-X kernel v2 (shape blend in the MMA, 16 epilogue warps): parity, timing, ncu
+TAG=${1:-r02y}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -x -k "smplx or lbs or twoview or hmr or loss or test_mode or server or empty" 2>&1 > $OUT/pytest_smplx.log; tail -15 $OUT/pytest_smplx.log
+echo "== lbs"; timeout 300 python tools/gpu_probe.py lbs 2>&1 | tail -8
+echo "== lbs unroll 2"; AIRPOSE_SMPLX_UNROLL=2 timeout 300 python tools/gpu_probe.py lbs 2>&1 | tail -4
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:smplx_ -s 3 -c 3 \
+    -o $OUT/prof_lbs python tools/run_once.py lbs 8192 2 > $OUT/ncu_lbs.log 2>&1
+echo "ncu lbs exit $?"
+ncu -i $OUT/prof_lbs.ncu-rep --page raw --csv > $OUT/prof_lbs_raw.csv 2>/dev/null
+ncu -i $OUT/prof_lbs.ncu-rep --page source --csv > $OUT/prof_lbs_source.csv 2>/dev/null
+find $OUT -name "*.ncu-rep" -size +24M -delete
+timeout 900 python -m pytest tests/test_gpu_dropin.py -q -s -x 2>&1 > $OUT/pytest_dropin.log; grep -n "gradient vs\|   [a-z]" $OUT/pytest_dropin.log | head -20
