@@ -37,6 +37,7 @@ struct PoseArgs {
   float* feat;               // [B,PF]    (generic vertex kernel) or null
   // tensor-core vertex kernel (smplx_tc.cu): per-mesh record + split-fp16 pose feature
   float* rec;                // [Bpad, kTcRecFloats] or null
+  int rec_plain;             // 1: one plain row per mesh (smplx_ml.cu); 0: pairs of meshes element-interleaved (smplx_tc.cu)
   __half* fh; __half* fl;    // [B, kTcK]
   const float* transl;
   const float* root_R; int root_R_stride;
@@ -136,10 +137,11 @@ __global__ void __launch_bounds__(kMaxJoints) smplx_pose_kernel(SmplxDev m, Pose
     // records are stored in PAIRS of meshes, element-interleaved (field f of mesh b at pair_base + 2 f + (b & 1)), so
     // that the vertex kernel reads {mesh 2p, mesh 2p+1} of a field with one 64-bit load and does its fp32 math with
     // packed FFMA2 (two meshes per instruction)
-    float* rec = a.rec + (size_t)(b >> 1) * 2 * kTcRecFloats + (b & 1);
+    const int rs = a.rec_plain ? 1 : 2;                          // element stride inside the record
+    float* rec = a.rec_plain ? a.rec + (size_t)b * kTcRecFloats : a.rec + (size_t)(b >> 1) * 2 * kTcRecFloats + (b & 1);
     if (j < kTcBodyJoints) {
 #pragma unroll
-      for (int e = 0; e < 12; ++e) rec[2 * (j * 12 + e)] = Aj[e];
+      for (int e = 0; e < 12; ++e) rec[rs * (j * 12 + e)] = Aj[e];
     }
     if (j >= 1 && j < kTcBodyJoints) {                           // split-fp16 pose feature: f = hi + lo
 #pragma unroll
@@ -165,10 +167,10 @@ __global__ void __launch_bounds__(kMaxJoints) smplx_pose_kernel(SmplxDev m, Pose
       a.fh[(size_t)b * kTcK + kTcKPose + j] = __float2half_rn(val);
       a.fl[(size_t)b * kTcK + kTcKPose + j] = __float2half_rn(0.f);
     }
-    if (j >= 12 && j < 21) rec[2 * (kTcRecCam + (j - 12))] = a.root_R ? __ldg(a.root_R + (size_t)b * a.root_R_stride + (j - 12))
+    if (j >= 12 && j < 21) rec[rs * (kTcRecCam + (j - 12))] = a.root_R ? __ldg(a.root_R + (size_t)b * a.root_R_stride + (j - 12))
                                                                         : (((j - 12) % 4 == 0) ? 1.f : 0.f);
-    if (j >= 21 && j < 24) rec[2 * (kTcRecCam + 9 + (j - 21))] = a.root_t ? __ldg(a.root_t + (size_t)b * a.root_t_stride + (j - 21)) : 0.f;
-    if (j >= 24 && j < 28) rec[2 * (kTcRecTransl + (j - 24))] = (a.transl && j < 27) ? __ldg(a.transl + (size_t)b * 3 + (j - 24)) : 0.f;
+    if (j >= 21 && j < 24) rec[rs * (kTcRecCam + 9 + (j - 21))] = a.root_t ? __ldg(a.root_t + (size_t)b * a.root_t_stride + (j - 21)) : 0.f;
+    if (j >= 24 && j < 28) rec[rs * (kTcRecTransl + (j - 24))] = (a.transl && j < 27) ? __ldg(a.transl + (size_t)b * 3 + (j - 24)) : 0.f;
   }
 }
 
@@ -527,6 +529,7 @@ extern "C" int airpose_smplx_create(airpose_smplx_t** out, const airpose_smplx_m
 #undef UP_F
 #undef UP_I
   if (smplx_tc_create(mh, d, &h->tc, &h->owned)) return 1;
+  if (smplx_ml_create(mh, d, &h->tc, &h->owned)) return 1;
   {  // backward constants: [posedirs | shapedirs] vertex-major, and the vertex -> gathered-joint lists
     h->ldq = (P + NS + 31) / 32 * 32;
     std::vector<float> Pt((size_t)V * 3 * h->ldq, 0.f);
@@ -613,7 +616,8 @@ extern "C" int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_arg
   pa.seg[1] = g->body_pose; pa.seg_stride[1] = g->body_pose_stride;
   pa.seg[2] = g->tail_pose; pa.seg_stride[2] = g->tail_pose_stride;
   pa.A = A; pa.Jt = Jt; pa.feat = feat;
-  pa.rec = rec; pa.fh = fh; pa.fl = fl;
+  const bool use_ml = use_tc && h->tc.ml_ok && B >= kMlMinBatch && ((int64_t)B + 128) * d.V * 3 < (int64_t)1 << 31;   // 32-bit element offsets
+  pa.rec = rec; pa.fh = fh; pa.fl = fl; pa.rec_plain = use_ml;
   pa.transl = g->transl;
   pa.root_R = g->root_R; pa.root_R_stride = g->root_R_stride;
   pa.root_t = g->root_t; pa.root_t_stride = g->root_t_stride;
@@ -625,7 +629,7 @@ extern "C" int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_arg
     tcall.B = B; tcall.nb = g->num_betas; tcall.has_transl = g->transl != nullptr;
     tcall.rec = rec; tcall.fh = fh; tcall.fl = fl;
     tcall.out = g->out_vertices; tcall.out_cam = g->out_vertices_cam;
-    if (smplx_tc_forward(d, h->tc, tcall, stream)) return 1;
+    if (use_ml ? smplx_ml_forward(d, h->tc, tcall, stream) : smplx_tc_forward(d, h->tc, tcall, stream)) return 1;
   } else {
     VertexArgs va{};
     va.B = B; va.nb = g->num_betas; va.PF = PF;

@@ -42,6 +42,8 @@ constexpr int kTcSub = 8;                      // meshes per record sub-batch (o
 constexpr int kTcRecFloats = 280;              // per-mesh record: A[22][12] | camR[9] camt[3] | transl[3] pad
 constexpr int kTcRecCam = 264, kTcRecTransl = 276;
 constexpr int kTcMaxKW = 8;
+constexpr int kMlVertTile = 32;                // vertices per tile of the mesh-lane kernel (smplx_ml.cu)
+constexpr int kMlMinBatch = 256;               // batches from here on run the mesh-lane kernel (128 meshes per CTA)
 constexpr float kTcPScale = 1024.f;            // posedirs are stored as fp16(P * 2^10): keeps small entries normal
 
 struct SmplxTc {
@@ -54,11 +56,16 @@ struct SmplxTc {
   const int* sk_off = nullptr; // [KW][V] byte offset of the joint's A inside a record (j*48)
   const float* sk_w = nullptr; // [KW][V]
   const int* sk_cnt = nullptr; // [V]
+  // mesh-lane kernel (smplx_ml.cu)
+  bool ml_ok = false;
+  const uint32_t* ml_vtab = nullptr;   // [ml_vtiles * 32][8]: 4 slot ids (float offset j * 12 in a record) + 4 weights per vertex
+  int ml_vtiles = 0;                   // ceil(V / 32)
+  CUtensorMap tmP32, tmPx32;           // 32-row boxes of P (pose k-blocks / shape k-block)
 };
 
 struct TcCall {
   int B, nb, has_transl;
-  const float* rec;            // [Bpad][280], pairs of meshes element-interleaved
+  const float* rec;            // [Bpad][280]: pairs of meshes element-interleaved (smplx_tc.cu) or plain rows (smplx_ml.cu)
   const __half* fh;            // [B][224]
   const __half* fl;            // [B][224]
   float* out;                  // [B,V,3]
@@ -67,5 +74,7 @@ struct TcCall {
 
 int smplx_tc_create(const airpose_smplx_model_host* mh, const SmplxDev& d, SmplxTc* tc, std::vector<void*>* owned);
 int smplx_tc_forward(const SmplxDev& d, const SmplxTc& tc, const TcCall& c, cudaStream_t stream);
+int smplx_ml_create(const airpose_smplx_model_host* mh, const SmplxDev& d, SmplxTc* tc, std::vector<void*>* owned);
+int smplx_ml_forward(const SmplxDev& d, const SmplxTc& tc, const TcCall& c, cudaStream_t stream);
 
 }  // namespace airpose

@@ -86,6 +86,33 @@ def test_smplx_generic_kernel_matches_oracle(smplx_dir, smplx_oracle, monkeypatc
     assert e12 < TC_TOL
 
 
+def test_smplx_mesh_lane_kernel(smplx_dir, smplx_gpu, smplx_oracle, monkeypatch):
+    """AIRPOSE_SMPLX_ML=1 routes batches >= 256 through the mesh-lane kernel (csrc/smplx_ml.cu: transposed tcgen05 product,
+    register cache of skinning matrices): against the oracle on sampled rows, against the default kernel on every row (same
+    split-fp16 products, other summation order), with a partial last mesh tile, a translation and the fused camera outputs."""
+    from airpose_b200.smplx import SMPLX
+    monkeypatch.setenv("AIRPOSE_SMPLX_ML", "1")
+    sm = SMPLX(smplx_dir, batch_size=4, create_transl=False).to(DEV)
+    monkeypatch.delenv("AIRPOSE_SMPLX_ML")
+    B = 300
+    li = synthetic.make_lbs_inputs(B, seed=21)
+    rng = np.random.default_rng(21)
+    Rr = synthetic.rot6d_to_rotmat_np(np.array([1, 0, 0, 1, 0, 0], np.float32) + rng.standard_normal((B, 6)).astype(np.float32) * 0.4)
+    tr = (np.array([0, 0, 9], np.float32) + rng.standard_normal((B, 3)).astype(np.float32))
+    shift = rng.standard_normal((B, 3)).astype(np.float32)
+    kw = dict(betas=t(li["betas"]), body_pose=t(li["body_pose"]), transl=t(shift), pose2rot=False, root_R=t(Rr), root_t=t(tr))
+    mo, cam = sm.forward_camera(**kw)
+    mo0, cam0 = smplx_gpu.forward_camera(**kw)
+    d_v = float((mo.vertices - mo0.vertices).abs().max())
+    d_c = float((cam["vertices_cam"] - cam0["vertices_cam"]).abs().max())
+    print("mesh-lane vs default kernel, B=%d: vertices max abs diff %.2e, camera-frame vertices %.2e" % (B, d_v, d_c))
+    assert d_v < 3e-6 and d_c < 2e-5
+    assert torch.equal(mo.joints[:, 55:76], mo.vertices[:, torch.from_numpy(orc.SMPLX_EXTRA_JOINT_VERTS).to(DEV)])
+    sample = [0, 1, 127, 128, 255, 256, 299]
+    v, j = orc.smplx_forward(smplx_oracle, li["betas"][sample], li["body_pose"][sample], transl=shift[sample])
+    assert rel_err(mo.vertices[sample].cpu().numpy(), v) < TC_TOL and rel_err(mo.joints[sample].cpu().numpy(), j) < TC_TOL
+
+
 def test_smplx_matches_reference_golden(smplx_gpu, golden_lbs):
     B = int(golden_lbs["batch"])
     li = synthetic.make_lbs_inputs(B, seed=int(golden_lbs["lbs_seed"]))
@@ -1463,8 +1490,11 @@ def test_lbs_full_size_properties(smplx_gpu, smplx_oracle):
     assert out.vertices.shape == (B, 10475, 3) and out.joints.shape == (B, 127, 3)
     assert torch.isfinite(out.vertices).all() and torch.isfinite(out.joints).all()
     sample = [1, 31, 32, 33, 1000, 4096, 5555, B - 2]
-    sub = smplx_gpu.forward(betas=bt[sample].contiguous(), body_pose=pt[sample].contiguous(), pose2rot=False)
-    assert torch.equal(sub.vertices, out.vertices[sample]) and torch.equal(sub.joints, out.joints[sample])
+    perm = sample + [i for i in range(300) if i not in sample]         # other batch size, other positions inside the MMA tiles
+    sub = smplx_gpu.forward(betas=bt[perm].contiguous(), body_pose=pt[perm].contiguous(), pose2rot=False)
+    assert torch.equal(sub.vertices[:len(sample)], out.vertices[sample]) and torch.equal(sub.joints[:len(sample)], out.joints[sample])
+    small = smplx_gpu.forward(betas=bt[sample].contiguous(), body_pose=pt[sample].contiguous(), pose2rot=False)
+    assert torch.equal(small.vertices, out.vertices[sample])
     vt = t(smplx_oracle.v_template)
     assert float((out.vertices[rest] - vt).abs().max()) < 1e-6
     idx = torch.from_numpy(orc.SMPLX_EXTRA_JOINT_VERTS).to(DEV)
