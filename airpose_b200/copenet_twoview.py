@@ -84,6 +84,10 @@ def mean_distance(a, b, points_used=None):
     return out[0]
 
 
+def dist_initialized():
+    return torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+
+
 class copenet_twoview(nn.Module):
     """``hparams`` needs: copenet_home-style paths are replaced by explicit ones:
     ``smpl_mean_params`` (npz path), ``smplx_model_dir``, ``batch_size``, ``val_batch_size``,
@@ -102,7 +106,7 @@ class copenet_twoview(nn.Module):
         return self.model(**kwargs)
 
     @torch.no_grad()
-    def fwd_pass(self, input_batch, profile=None):
+    def fwd_pass(self, input_batch, profile=None, is_test=False):
         """``profile``: optional dict that receives CUDA event pairs around the trunk, the regressor
         and the two SMPL-X calls (bench.py reads the stage times from them)."""
 
@@ -116,27 +120,49 @@ class copenet_twoview(nn.Module):
         bb0, bb1 = input_batch["bb0"], input_batch["bb1"]
         intr = (input_batch["intr0"], input_batch["intr1"])
         B = im0.shape[0]
-        in_trans, in_trans_unscaled = self._init_translation(B, im0.device)
+        in_trans, in_trans_unscaled = self._init_translation(B, im0.device, input_batch, is_test)
         reg_iters = getattr(self.hparams, "reg_iters", 3)
         mark("trunk")
         xf = self.model.forward_feat_ext_pair(im0, im1)                         # both views, one call (eval-mode BN)
         mark("trunk")
         mark("ief")
-        pred = self.model._ief(xf[:B], xf[B:], bb0, bb1, in_trans, in_trans, None, None, None, None, reg_iters)
+        pred = self.model._ief(xf[:B], xf[B:], bb0, bb1, in_trans[0], in_trans[1], None, None, None, None, reg_iters)
         mark("ief")
         mark("smplx")
         out = self._after_regressor(pred, intr, in_trans_unscaled)
         mark("smplx")
         return out
 
-    def _init_translation(self, B, dev):
-        """initial translation [0,0,10] * 0.05 (:184-203); cached per (B, device): building it from a Python list is a
-        synchronous host->device copy, i.e. a host sync in every step."""
+    def _init_translation(self, B, dev, input_batch=None, is_test=False):
+        """The regressor's initial translation per view (copenet_twoview.py:178-203), scaled by 0.05 and unscaled:
+        ``((scaled0, scaled1), (unscaled0, unscaled1))``.  Three branches, as in the reference:
+          * ``is_test`` on ``testdata == "aircapdata"``: the ground-truth ``smpltrans_rel*`` (:178-180);
+          * ``hparams.smpltrans_noise_sigma`` given: ground truth + sigma * N(0, 1), drawn the way ``add_noise_input_smpltrans``
+            draws it (utils/utils.py:273-279: two CPU ``torch.randn(B, 3)`` per view, the first one used), so that a seeded
+            run consumes the global generator identically;
+          * otherwise the constant [0, 0, 10] -- cached per (B, device): building it from a Python list is a synchronous
+            host->device copy, i.e. a host sync in every step."""
+        sigma = getattr(self.hparams, "smpltrans_noise_sigma", None)
+        aircap = is_test and str(getattr(self.hparams, "testdata", "")).lower() == "aircapdata"
+        if aircap or sigma is not None:
+            if input_batch is None or "smpltrans_rel0" not in input_batch or "smpltrans_rel1" not in input_batch:
+                raise KeyError("this configuration initialises the translation from the ground truth: the batch needs "
+                               "'smpltrans_rel0' / 'smpltrans_rel1' (copenet_twoview.py:169-170)")
+            uns = []
+            for v in (0, 1):
+                gt = input_batch["smpltrans_rel%d" % v].to(device=dev, dtype=torch.float32)
+                if not aircap:
+                    noise = torch.randn(B, 3)
+                    torch.randn(B, 3)                     # the reference's second, unused draw
+                    gt = gt + float(sigma) * noise.to(dev)
+                uns.append(gt.contiguous())
+            return (uns[0] * TRANS_SCALE, uns[1] * TRANS_SCALE), (uns[0], uns[1])
         key = (B, str(dev))
         cache = self.__dict__.setdefault("_init_cache", {})
         if key not in cache:
             it = torch.tensor([0.0, 0.0, 10.0], dtype=torch.float32).expand(B, -1).clone()
-            cache[key] = ((it * TRANS_SCALE).to(dev), it.to(dev))
+            sc, un = (it * TRANS_SCALE).to(dev), it.to(dev)
+            cache[key] = ((sc, sc), (un, un))
         return cache[key]
 
     def _after_regressor(self, pred, intr, in_trans_unscaled):
@@ -156,7 +182,7 @@ class copenet_twoview(nn.Module):
                 root_R=rotmat[:, 0], root_t=trans,                        # transform_smpl (:287-292)
                 focal_length=self.focal_length, camera_center=intr[v][:, :2, 2])   # :307-317
             out.update({"pred_pose%d" % v: pose, "pred_betas%d" % v: betas, "pred_rotmat%d" % v: rotmat,
-                        "pred_smpltrans%d" % v: trans, "in_smpltrans%d" % v: in_trans_unscaled,
+                        "pred_smpltrans%d" % v: trans, "in_smpltrans%d" % v: in_trans_unscaled[v],
                         "pred_output_cam%d" % v: mo,
                         "pred_vertices_cam%d" % v: cam["vertices_cam"], "pred_joints_cam%d" % v: cam["joints_cam"],
                         "pred_joints_2d_cam%d" % v: cam["joints_2d"]})
@@ -196,7 +222,15 @@ class copenet_twoview(nn.Module):
                  "gt_orient1": input_batch["smplorient_rel1"], "gt_verts": input_batch["smpl_vertices"],
                  "gt_joints": input_batch["smpl_joints"], "gt_j2d0": input_batch["smpl_joints_2d0"],
                  "gt_j2d1": input_batch["smpl_joints_2d1"]}
+        V, J = v0.shape[1], j0.shape[1]
+        # the kernel indexes every tensor with the PREDICTION's vertex / joint counts: check the layouts before the launch
+        expect = {"rotmat0": B * 22 * 9, "rotmat1": B * 22 * 9, "betas0": B * 10, "betas1": B * 10, "j2d0": B * J * 2, "j2d1": B * J * 2,
+                  "gt_pose_rotmat": B * 21 * 9, "gt_trans0": B * 3, "gt_trans1": B * 3, "gt_orient0": B * 9, "gt_orient1": B * 9,
+                  "gt_verts": B * V * 3, "gt_joints": B * J * 3, "gt_j2d0": B * J * 2, "gt_j2d1": B * J * 2}
         for n, t in names.items():
+            if t.numel() != expect[n]:
+                raise ValueError("get_loss: '{}' has shape {} ({} elements); the predictions have B={}, {} vertices, {} joints, "
+                                 "which needs {} elements".format(n, tuple(t.shape), t.numel(), B, V, J, expect[n]))
             t = f(t.to(dev))
             keep.append(t)
             setattr(a, n, t.data_ptr())
@@ -230,7 +264,7 @@ class copenet_twoview(nn.Module):
         """copenet_twoview.fwd_pass_and_loss (copenet_twoview.py:164-374): forward + get_loss + the
         reference's output dict.  (The backward half: ``training_step`` hand-scheduled, or autograd through
         ``copenet.forward`` in train() mode + ``SMPLX.forward``, see INTEGRATION.md.)"""
-        out = self.fwd_pass(input_batch)
+        out = self.fwd_pass(input_batch, is_test=is_test)
         if is_test:
             return self._test_outputs(input_batch, out), None, None
         else:
@@ -328,7 +362,12 @@ class copenet_twoview(nn.Module):
         ``train_reg_only`` switch leaves trainable (copenet_real/.../copenet_twoview.py:357-372): fc1, fc2, decpose,
         decshape (deccam has no gradient in the two-view model and is left out)."""
         from .optim import Adam
+        from .parallel import broadcast_buffers_
         params = dict(self.model.named_parameters())
+        if dist_initialized():                    # the frozen trunk must be identical across ranks too (DDP broadcasts the whole module)
+            for p in self.model.parameters():
+                torch.distributed.broadcast(p.data, src=0)
+        broadcast_buffers_(self.model)
         return Adam([params[n] for n in self.model.REG_PARAMS], lr=float(getattr(self.hparams, "lr", 5e-5)), amsgrad=True)
 
     @torch.no_grad()
@@ -342,13 +381,13 @@ class copenet_twoview(nn.Module):
         Returns ``(loss, losses)`` as device tensors (no host sync)."""
         im0, im1 = input_batch["im0"].float(), input_batch["im1"].float()
         B = im0.shape[0]
-        in_trans, in_trans_unscaled = self._init_translation(B, im0.device)
+        in_trans, in_trans_unscaled = self._init_translation(B, im0.device, input_batch)
         reg_iters = getattr(self.hparams, "reg_iters", 3)
         if self.model.training:       # train() mode, like the reference: batch-statistics BatchNorm, one call per view (:140-141)
             xf = torch.cat([self.model.forward_feat_ext(im0), self.model.forward_feat_ext(im1)])
         else:
             xf = self.model.forward_feat_ext_pair(im0, im1)
-        pred, ctx = self.model.ief_train_forward(xf[:B], xf[B:], input_batch["bb0"], input_batch["bb1"], in_trans, in_trans,
+        pred, ctx = self.model.ief_train_forward(xf[:B], xf[B:], input_batch["bb0"], input_batch["bb1"], in_trans[0], in_trans[1],
                                                  iters=reg_iters, mask1=mask1, mask2=mask2)
         out = self._after_regressor(pred, (input_batch["intr0"], input_batch["intr1"]), in_trans_unscaled)
         loss, losses, g = self.loss_and_head_backward(input_batch, out)
@@ -364,6 +403,8 @@ class copenet_twoview(nn.Module):
         """copenet_twoview.configure_optimizers (copenet_twoview.py:416-425): Adam(lr, weight_decay=0, amsgrad=True) over
         ``self.model.parameters()``, here as one launch over one flat buffer (``airpose_b200.optim.Adam``)."""
         from .optim import Adam
+        from .parallel import broadcast_buffers_
+        broadcast_buffers_(self.model)            # with Adam's parameter broadcast: every rank starts from rank 0's state, like DDP
         return Adam(self.model.parameters(), lr=float(getattr(self.hparams, "lr", 5e-5)), amsgrad=True)
 
     @torch.no_grad()
@@ -382,7 +423,7 @@ class copenet_twoview(nn.Module):
             raise RuntimeError("training_step needs the module in train() mode (batch-statistics BatchNorm, dropout)")
         im0, im1 = input_batch["im0"].float(), input_batch["im1"].float()
         B = im0.shape[0]
-        in_trans, in_trans_unscaled = self._init_translation(B, im0.device)
+        in_trans, in_trans_unscaled = self._init_translation(B, im0.device, input_batch)
         reg_iters = getattr(self.hparams, "reg_iters", 3)
         im0, im1 = im0.contiguous(), im1.contiguous()
         paired = 2 <= B and 2 * B <= self.model.PAIR_MAX_IMAGES    # both views through one set of launches (BatchNorm still per view)
@@ -392,7 +433,7 @@ class copenet_twoview(nn.Module):
         else:
             xf0 = self.model._forward_feat_ext_train(im0, tape=0)
             xf1 = self.model._forward_feat_ext_train(im1, tape=1)
-        pred, ctx = self.model.ief_train_forward(xf0, xf1, input_batch["bb0"], input_batch["bb1"], in_trans, in_trans,
+        pred, ctx = self.model.ief_train_forward(xf0, xf1, input_batch["bb0"], input_batch["bb1"], in_trans[0], in_trans[1],
                                                  iters=reg_iters, mask1=mask1, mask2=mask2)
         out = self._after_regressor(pred, (input_batch["intr0"], input_batch["intr1"]), in_trans_unscaled)
         loss, losses, g = self.loss_and_head_backward(input_batch, out)

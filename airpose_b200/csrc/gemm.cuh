@@ -73,7 +73,7 @@ int make_tmap_nhwc4d_bf16(CUtensorMap* out, const void* base, int n, int H, int 
 
 // Fused bottleneck tail (bneck.cu): conv2 3x3 + BN + ReLU -> conv3 1x1 + BN + residual + ReLU in one launch.
 struct alignas(64) TailLaunch {
-  unsigned char storage[832];      // five tensor maps + the kernel parameters (TailLaunchImpl in bneck.cu)
+  unsigned char storage[3456];     // five tensor maps + the kernel parameters incl. the folded BatchNorm vectors (TailLaunchImpl in bneck.cu)
   int valid = 0;
   int pdl = 0;
 };
@@ -100,5 +100,9 @@ bool use_tma_epilogue();   // off with AIRPOSE_NO_TMA_EPI=1 (A/B runs)
 bool use_pdl();            // off with AIRPOSE_NO_PDL=1
 int launch_gemm(const GemmLaunch& L, cudaStream_t stream);
 int num_sms();
+// Stage A of a multi-chunk trunk call runs its chunks on two streams: a cap below the SM count lets kernels of the two streams
+// be co-resident on disjoint SMs (their fixed per-launch latencies overlap).  0 = no cap.  Thread-local, set by trunk.cu.
+void set_grid_cap(int cap);
+int grid_limit();          // min(num_sms(), cap)
 
 }  // namespace airpose

@@ -312,7 +312,7 @@ int launch_bn(const GemmLaunch& L, const KP& kp, cudaStream_t stream) {
   }
   const int tiles = kp.tiles_m * kp.tiles_n;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)std::min(tiles, num_sms()));
+  cfg.gridDim = dim3((unsigned)std::min(tiles, grid_limit()));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg<BN, BK>::kSmemBytes;
   cfg.stream = stream;

@@ -351,7 +351,7 @@ int launch_stem_pool(const StemLaunch& L, const float* x_nchw, void* x2p, int n,
   stem_pack_pairs_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(work, 128), 148 * 32), 128, 0, stream>>>(x_nchw, n, (__nv_bfloat16*)x2p);
   AP_LAUNCH_CHECK();
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)std::min(I.p.num_tiles, num_sms()));
+  cfg.gridDim = dim3((unsigned)std::min(I.p.num_tiles, grid_limit()));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;

@@ -373,6 +373,7 @@ extern "C" int airpose_net_destroy(airpose_net_t* h) {
 }
 
 static int load_trunk(airpose_net_t* h, const airpose_conv_params* conv, float bn_eps, cudaStream_t st) {
+  h->plansA.clear(); h->plansB.clear();      // fused-kernel plans carry the folded BatchNorm vectors by value (bneck.cu)
   for (size_t i = 0; i < h->specs.size(); ++i) {
     const ConvSpec& s = h->specs[i];
     const airpose_conv_params& c = conv[i];
@@ -556,7 +557,9 @@ static int backbone_fwd_segments(airpose_net_t* h, const float* x0, int n0, cons
     // second stream's kernel start on every SM the first one's tail has already left, which hides the
     // ~5 us of ramp-up/drain each launch costs.  Stream order keeps each set's reuse safe.
     const bool fork = h->sets > 1 && ng > h->chunk;
+    static const int stage_a_cap = env_int("AIRPOSE_STAGEA_GRID", 0);
     if (fork) {
+      set_grid_cap(stage_a_cap);
       AP_CHECK_CUDA(cudaEventRecord(h->ev_fork, st));
       AP_CHECK_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
     }
@@ -570,6 +573,8 @@ static int backbone_fwd_segments(airpose_net_t* h, const float* x0, int n0, cons
       auto key = std::make_pair(n, 2 * i0 + set);
       auto it = h->plansA.find(key);
       if (it == h->plansA.end()) {
+        AP_CHECK_CUDA(cudaStreamSynchronize(cst));      // plan building reads the folded BatchNorm vectors back (bneck.cu)
+        AP_CHECK_CUDA(cudaStreamSynchronize(st));
         TrunkPlan plan;
         if (build_plan_a(h, n, i0, set, &plan)) return 1;
         it = h->plansA.emplace(key, std::move(plan)).first;
@@ -591,6 +596,7 @@ static int backbone_fwd_segments(airpose_net_t* h, const float* x0, int n0, cons
         AP_LAUNCH_CHECK();
       }
     }
+    set_grid_cap(0);
     if (fork) {
       AP_CHECK_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
       AP_CHECK_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
@@ -680,8 +686,9 @@ extern "C" int airpose_backbone_fwd_train(airpose_net_t* h, const float* x, int 
                                           void* stream_) {
   AP_REQUIRE(h && x && bn && out_feat, "airpose_backbone_fwd_train: null argument");
   AP_REQUIRE(h->loaded, "airpose_backbone_fwd_train: weights not loaded (call airpose_net_load)");
-  AP_REQUIRE(n >= 2 && n <= h->chunk, "airpose_backbone_fwd_train: n=%d must be in [2, %d] (batch statistics need at least two images; "
-             "one call handles at most one chunk)", n, h->chunk);
+  // n = 1 is legal, as in the reference: BatchNorm2d takes its statistics over N*H*W (49 values per channel at layer4)
+  AP_REQUIRE(n >= 1 && n <= h->chunk, "airpose_backbone_fwd_train: n=%d must be in [1, %d] (one call holds one chunk of images on its "
+             "tape; the batch statistics of a larger batch would span chunks)", n, h->chunk);
   for (size_t i = 0; i < h->specs.size(); ++i)
     AP_REQUIRE(bn->bn_weight[i] && bn->bn_bias[i], "airpose_backbone_fwd_train: BatchNorm %zu has a null parameter", i);
   cudaStream_t st = (cudaStream_t)stream_;

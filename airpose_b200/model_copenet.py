@@ -12,8 +12,9 @@ reference's names, so ``state_dict()`` has the same 331 keys, Lightning checkpoi
 ``.fc1/.fc2/.decpose/.decshape/.deccam`` / ``.parameters()`` are there for optimizers.  The
 children are parameter containers only: ``forward`` hands their tensors to
 libairpose_b200 (bf16 tcgen05 implicit-GEMM convs with fused BN/ReLU/residual; the regressor's
-affine chain collapsed into one fp32 matrix, csrc/ief.cu).  Eval mode only for now: training-mode BatchNorm
-statistics and dropout arrive with the backward kernels.
+affine chain collapsed into one fp32 matrix, csrc/ief.cu).  In ``train()`` mode the call is ONE autograd node
+(``_TwoViewTrainFn``): batch-statistics BatchNorm with the running-statistics update, dropout in the regressor, and a native
+backward (csrc/trunk.cu ``airpose_backbone_bwd_train``, csrc/ief_train.cu) that hands every parameter gradient to autograd.
 """
 from __future__ import annotations
 
@@ -243,6 +244,10 @@ class copenet(nn.Module):
         """``tape`` 0 / 1 keeps this call's activations in the native handle for ``backward_feat_ext`` (one tape per view)."""
         device = x.device
         n = x.shape[0]
+        if not 1 <= n <= self.TRAIN_MAX_IMAGES:
+            raise ValueError("train()-mode trunk: {} images per view; one call keeps one chunk of 1..{} images on its tape (BatchNorm "
+                             "batch statistics are taken over the whole call, copenet/models/model_copenet.py:140-141) -- split larger "
+                             "per-GPU batches across ranks".format(n, self.TRAIN_MAX_IMAGES))
         lib, h = self._ensure(max(n, 2), device, allow_training=True, need_regressor=False)
         pairs = self._conv_bn_pairs()
         bn = self._bn_train_params(tape)
@@ -260,6 +265,7 @@ class copenet(nn.Module):
                 m.running_mean._airpose_gen = getattr(m.running_mean, "_airpose_gen", 0) + 1
         return out
 
+    TRAIN_MAX_IMAGES = 64    # images per view of one train()-mode trunk call (one chunk: the tape and the batch statistics live in it)
     PAIR_MAX_IMAGES = 64     # one chunk of the trunk: the two-view tape of airpose_backbone_fwd_train_pair holds 2B <= 64 images
 
     def _forward_feat_ext_train_pair(self, x0, x1, tape=0):

@@ -53,13 +53,89 @@ class Adam:
                     g.copy_(p.grad)
                 p.grad = g
         self.offsets = offs
+        # torch.optim.Optimizer-compatible view of the hyper-parameters (schedulers / Lightning read and write ``lr`` here)
+        self.param_groups = [{"params": self.params, "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0,
+                              "amsgrad": self.amsgrad}]
+        self.sync_from_rank0()
+
+    def sync_from_rank0(self, group=None):
+        """What DistributedDataParallel does at construction: every rank starts from rank 0's parameters (one broadcast of
+        the flat buffer).  Module BUFFERS (BatchNorm running statistics) are the caller's:
+        ``airpose_b200.parallel.broadcast_buffers_(module)``."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.broadcast(self.flat, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
 
     def zero_grad(self, set_to_none=False):
+        """One memset of the flat gradient buffer.  ``set_to_none`` is accepted for signature compatibility and ignored: the
+        gradients must stay views of the flat buffer (the backward kernels write straight into it)."""
+        self._reattach_grads()
         self.flat_grad.zero_()
+
+    def _reattach_grads(self):
+        """``p.grad`` must be the parameter's slot of the flat gradient buffer.  Code outside this class can rebind it
+        (``nn.Module.zero_grad()`` sets grads to None by default; autograd then allocates fresh tensors): a fresh gradient is
+        copied into its slot and the view restored; a None gradient counts as zeros -- never silently skipped."""
+        for p, o in zip(self.params, self.offsets):
+            slot = self.flat_grad[o:o + p.numel()]
+            g = p.grad
+            if g is not None and g.data_ptr() == slot.data_ptr():
+                continue
+            with torch.no_grad():
+                if g is None:
+                    slot.zero_()
+                else:
+                    if g.shape != p.shape or g.device != self.device:
+                        raise _lib.AirposeError("airpose_b200.optim.Adam: a parameter's .grad was replaced by a tensor of another shape or device")
+                    slot.copy_(g.reshape(-1).to(torch.float32))
+            p.grad = slot.view_as(p)
+
+    def state_dict(self):
+        """``torch.optim.Adam.state_dict()`` layout: per-parameter ``step`` / ``exp_avg`` / ``exp_avg_sq`` / ``max_exp_avg_sq``
+        (clones, in parameter order) + ``param_groups`` with parameter indices -- loadable by ``torch.optim.Adam`` over the same
+        parameters and vice versa."""
+        state = {}
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            sl = slice(o, o + p.numel())
+            st = {"step": torch.tensor(float(self.step_count)), "exp_avg": self.exp_avg[sl].view_as(p).clone(),
+                  "exp_avg_sq": self.exp_avg_sq[sl].view_as(p).clone()}
+            if self.amsgrad:
+                st["max_exp_avg_sq"] = self.max_exp_avg_sq[sl].view_as(p).clone()
+            state[i] = st
+        g = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        g["params"] = list(range(len(self.params)))
+        return {"state": state, "param_groups": [g]}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("optimizer state does not match: expected one group of {} parameters".format(len(self.params)))
+        g = groups[0]
+        if bool(g.get("amsgrad", self.amsgrad)) != self.amsgrad:
+            raise ValueError("optimizer state was saved with amsgrad={}".format(g.get("amsgrad")))
+        self.lr, self.betas, self.eps = float(g["lr"]), (float(g["betas"][0]), float(g["betas"][1])), float(g["eps"])
+        self.param_groups[0].update(lr=self.lr, betas=self.betas, eps=self.eps)
+        steps = set()
+        with torch.no_grad():
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                st = sd["state"].get(i, sd["state"].get(str(i)))
+                sl = slice(o, o + p.numel())
+                if st is None:                       # a parameter that never received a gradient (torch keeps no state for it)
+                    self.exp_avg[sl].zero_(); self.exp_avg_sq[sl].zero_()
+                    if self.amsgrad:
+                        self.max_exp_avg_sq[sl].zero_()
+                    continue
+                self.exp_avg[sl].copy_(st["exp_avg"].reshape(-1)); self.exp_avg_sq[sl].copy_(st["exp_avg_sq"].reshape(-1))
+                if self.amsgrad:
+                    self.max_exp_avg_sq[sl].copy_(st["max_exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ ({}): the flat-buffer optimizer keeps one".format(sorted(steps)))
+        self.step_count = steps.pop() if steps else 0
 
     def allreduce_grads(self, group=None):
         """Gradient mean over the data-parallel ranks: one collective on the flat buffer (NCCL over NVLink)."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            self._reattach_grads()
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=group)
             return 1.0 / dist.get_world_size(group)
         return 1.0
@@ -67,6 +143,8 @@ class Adam:
     @torch.no_grad()
     def step(self, grad_scale=1.0):
         lib = _lib.load()
+        self._reattach_grads()
+        self.lr = float(self.param_groups[0]["lr"])          # a scheduler may have changed it
         self.step_count += 1
         a = _lib.AdamArgs()
         a.param, a.grad = self.flat.data_ptr(), self.flat_grad.data_ptr()

@@ -84,3 +84,22 @@ def allreduce_mean_(params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64
             off += g.numel()
         n += 1
     return n
+
+
+def broadcast_buffers_(module, src=0, group=None):
+    """Rank ``src``'s module buffers (BatchNorm running statistics, ``num_batches_tracked``, mean-pose buffers) to every rank,
+    as DistributedDataParallel does at construction (``broadcast_buffers``).  One flat broadcast per dtype."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return module
+    by_dtype = {}
+    for b in module.buffers():
+        by_dtype.setdefault(b.dtype, []).append(b)
+    for bufs in by_dtype.values():
+        flat = torch.cat([b.detach().reshape(-1) for b in bufs])
+        dist.broadcast(flat, src=src, group=group)
+        o = 0
+        with torch.no_grad():
+            for b in bufs:
+                b.copy_(flat[o:o + b.numel()].view_as(b))
+                o += b.numel()
+    return module

@@ -318,9 +318,10 @@ def test_trunk_matches_oracle_and_golden(net_gpu, net_state, golden_twoview):
     e_b, e_f = rel_err(xf, gold), rel_err(xf, gold32)
     m_b = np.abs(xf - gold).mean() / np.abs(gold).mean()
     print("trunk vs reference(bf16 rounding points): max-rel %.3e mean-rel %.3e ; vs reference fp32: %.3e" % (e_b, m_b, e_f))
-    # two bf16 implementations agree to ~1e-3 after 53 layers (tests/test_oracle_golden.py); bf16-vs-fp32 is 2.8e-3
-    assert e_b < 5e-3 and m_b < 2.5e-3
-    assert e_f < 1e-2
+    # two bf16 implementations with different fp32 summation orders after 53 layers: measured 1.3e-3 max-rel (1.5e-3 at 128
+    # images against the fp32 conv chain, tests/test_gpu_trunk_batch.py); bf16-vs-fp32 is 2.8e-3.  Bounds = 2x measured.
+    assert e_b < 3e-3 and m_b < 2.2e-3
+    assert e_f < 6e-3
 
 
 @pytest.mark.parametrize("B", [3, 70])
@@ -410,7 +411,7 @@ def test_ief_matches_oracle(net_gpu, net_state):
         ref = orc.ief_forward(net_state, xf0, xf1, bb0, bb1, pos, pos, iters)
         errs = [rel_err(g.cpu().numpy(), r) for g, r in zip(got, ref)]
         print("ief iters=%d rel errs %s" % (iters, ["%.2e" % e for e in errs]))
-        assert max(errs) < 1e-4          # split-bf16 tensor-core GEMMs, ~2^-16 per product
+        assert max(errs) < 2e-5          # fp32 CUDA-core kernels over the collapsed affine map (csrc/ief.cu): summation order only, measured 5e-7
 
 
 def test_twoview_end_to_end(net_gpu, net_state, smplx_dir, smplx_oracle, golden_twoview, tmp_path):

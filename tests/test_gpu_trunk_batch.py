@@ -168,7 +168,7 @@ def test_every_conv_teacher_forced(net, params, n):
     net.forward_feat_ext(x[:min(n, 64)])            # builds + loads the handle (stem entry point needs it)
     rows, worst = [], [0.0, ""]
 
-    def check(name, got, ref, one_ulp=2.0 ** -8, floor=2e-3, frac_tol=1e-3):
+    def check(name, got, ref, one_ulp=2.0 ** -8, floor=2e-3, frac_tol=2e-4):       # measured worst fraction: 7e-5 (layer4.2)
         assert torch.isfinite(got).all(), name + ": unwritten output"
         err = (got - ref).abs()
         off = (err > ref.abs() * one_ulp + floor).float().mean().item()          # |err| > 1 bf16 ulp (half-ulp rounding both sides)
@@ -227,5 +227,6 @@ def test_trunk_at_benchmark_batch(net, params, B):
     assert max_rel < TRUNK_MAX_REL and mean_rel < TRUNK_MEAN_REL
 
 
-TRUNK_MAX_REL = 5e-3
-TRUNK_MEAN_REL = 2.5e-3
+# measured on B200 (gpurun r02e2): 64 pairs max-rel 1.54e-3 / mean-rel 1.08e-3, 256 pairs 1.33e-3 / 1.09e-3
+TRUNK_MAX_REL = 3.1e-3
+TRUNK_MEAN_REL = 2.2e-3

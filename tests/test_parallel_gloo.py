@@ -1,5 +1,5 @@
 """world_size-2 gloo tests (CPU) of the multi-GPU host logic: pair sharding, the max-over-ranks timing
-reduction of the bench contract, and the bucketed gradient all-reduce of the training step."""
+reduction of the bench contract, the bucketed gradient all-reduce of the training step and the rank-0 broadcast of module buffers."""
 import os
 import socket
 
@@ -60,7 +60,17 @@ def _worker(rank, world, port, q):
         ok_grad = (torch.allclose(params[0].grad, torch.full((5, 3), mean_scale)) and
                    torch.allclose(params[1].grad, torch.arange(7.0) * mean_scale) and
                    torch.allclose(params[2].grad, torch.ones(2, 2) * 4 / world))
-        q.put((rank, ok_shard, ok_max, ok_grad, ncoll))
+        # (4) initial state: every rank starts from rank 0's buffers (what DDP's constructor does); float and integer buffers
+        torch.manual_seed(10 + rank)
+        bn = torch.nn.BatchNorm1d(6)
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0); bn.num_batches_tracked.fill_(3 + rank)
+        parallel.broadcast_buffers_(bn)
+        chk = torch.cat([bn.running_mean, bn.running_var, bn.num_batches_tracked.float().view(1)])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ok_buf = torch.equal(lo, hi) and int(bn.num_batches_tracked) == 3
+        q.put((rank, ok_shard, ok_max, ok_grad and ok_buf, ncoll))
     finally:
         dist.destroy_process_group()
 
