@@ -17,6 +17,8 @@
 //     into a 3-slot ring as (64 ch, W+2, RM, 1) boxes; the result overwrites the residual in place and leaves through a
 //     4-d TMA store (the two junk columns per padded row fall outside the tensor and are clipped by the store).
 // Both weight matrices stay resident in shared memory (72 + 32 KB) for the life of the CTA.
+// Measured and rejected (round 2, gpurun r02g2): the folded BatchNorm vectors as by-value kernel parameters read through the
+// constant bank (LDC.64) instead of warp-uniform 16-byte shared loads -- 52.1 -> 58.0 us per launch.
 //
 // CTA = 12 warps: 0 slab/weight TMA producer, 1 MMA issuer, 2 residual TMA producer, 3 TMEM allocator,
 //                 4-11 two epilogue warpgroups (each owns 32 resp. 64 of the columns of every accumulator).
@@ -52,7 +54,8 @@ constexpr int kOutOff = kResOff + 2 * kTileBytes;     // [2]: one output slot pe
 constexpr int kBarOff = kOutOff + 2 * kTileBytes;
 // barriers: w_full, slab_full, slab_empty, acc2_full, stg_full, stg_empty, acc3_full[2], acc3_empty[2], res_full[2], res_empty[2]
 constexpr int kNumBars = 14;
-constexpr int kSmemBytes = 1024 + kBarOff + kNumBars * 8 + 16;
+constexpr int kScaleOff = (kBarOff + kNumBars * 8 + 16 + 15) & ~15;        // read with 16-byte shared loads
+constexpr int kSmemBytes = 1024 + kScaleOff + (2 * kCM + 2 * kCO) * 4;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 constexpr int kTmemCols = 512;             // acc2: 64 columns from 0; acc3: 2 x 128 columns from 128
 constexpr int kAcc3Col = 128;
@@ -61,11 +64,8 @@ struct TailParams {
   int H, W, Wp;            // Wp = W + 2
   int RM;                  // image rows per tile = per 128-row M-tile (RM * Wp <= 128)
   int tiles_per_img, num_tiles;
-  // folded BatchNorm of conv2 / conv3 BY VALUE: read through the constant bank (LDC), not through shared memory -- a warp-
-  // uniform 16-byte shared load costs ~4 wavefronts of the shared-memory data pipe, and with 80 of them per tile and warp
-  // they were two thirds of this kernel's LSU wavefronts on a pipe that TMA and the UMMA operand reads saturate (r02t)
-  alignas(16) float sc2[kCM]; alignas(16) float sh2[kCM];
-  alignas(16) float sc3[kCO]; alignas(16) float sh3[kCO];
+  const float* scale2; const float* shift2;
+  const float* scale3; const float* shift3;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -83,17 +83,14 @@ __device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep) {
 }
 
 // 32 accumulator columns (r) * scale + shift + residual (four 16-byte groups q of bf16) -> ReLU -> bf16 (four 16-byte groups).
-// s3 / h3: the 32 scales / shifts of these columns (kernel parameter space).
-__device__ __forceinline__ void bn_res_relu(const uint32_t (&r)[32], const uint4* q, const float* s3, const float* h3, uint4 (&out)[4]) {
+// s3 / h3: shared-space addresses of the 32 scales / shifts of these columns.
+__device__ __forceinline__ void bn_res_relu(const uint32_t (&r)[32], const uint4* q, uint32_t s3, uint32_t h3, uint4 (&out)[4]) {
   // per 16 columns: the eight scale / shift loads first (volatile asm: they would otherwise queue behind the previous stores)
 #pragma unroll
   for (int jj = 0; jj < 2; ++jj) {
     float4 S[4], Hs[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      S[g] = *reinterpret_cast<const float4*>(s3 + jj * 16 + g * 4);
-      Hs[g] = *reinterpret_cast<const float4*>(h3 + jj * 16 + g * 4);
-    }
+    for (int g = 0; g < 4; ++g) { S[g] = lds_f4(s3 + jj * 64 + g * 16); Hs[g] = lds_f4(h3 + jj * 64 + g * 16); }
 #pragma unroll
     for (int jl = 0; jl < 2; ++jl) {
       const int j = jj * 2 + jl;
@@ -117,7 +114,7 @@ __device__ __forceinline__ void bn_res_relu(const uint32_t (&r)[32], const uint4
 __global__ void __launch_bounds__(kThreads, 1)
 bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant__ CUtensorMap tmW2,
                   const __grid_constant__ CUtensorMap tmW3, const __grid_constant__ CUtensorMap tmR,
-                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ TailParams p) {
+                  const __grid_constant__ CUtensorMap tmO, const TailParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBarOff);
@@ -132,6 +129,10 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
   uint64_t* res_full = bars + 10;       // [2] per warpgroup
   uint64_t* res_empty = bars + 12;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
+  float* sc2 = reinterpret_cast<float*>(smem + kScaleOff);
+  float* sh2 = sc2 + kCM;
+  float* sc3 = sh2 + kCM;
+  float* sh3 = sc3 + kCO;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt_rows = p.RM * p.Wp;                 // valid rows of the M-tile (<= 128)
@@ -152,6 +153,8 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
     ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < kCM; i += kThreads) { sc2[i] = __ldg(p.scale2 + i); sh2[i] = __ldg(p.shift2 + i); }
+  for (int i = threadIdx.x; i < kCO; i += kThreads) { sc3[i] = __ldg(p.scale3 + i); sh3[i] = __ldg(p.shift3 + i); }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -246,6 +249,7 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
     const uint32_t srow = ptx::smem_u32(smem + kStgOff + row * kRow);
     const uint32_t rrow = ptx::smem_u32(smem + kResOff + wg * kTileBytes + row * kRow);
     const uint32_t orow = ptx::smem_u32(smem + kOutOff + wg * kTileBytes + row * kRow);
+    const uint32_t sc2_a = ptx::smem_u32(sc2), sh2_a = ptx::smem_u32(sh2), sc3_a = ptx::smem_u32(sc3), sh3_a = ptx::smem_u32(sh3);
     // The residual of the NEXT chunk sits in registers while the current one is processed: the slot is handed back to the
     // producer as soon as it has been read, so a load is always in flight (the kernel is HBM-bound, not MMA-bound).
     uint4 resA[8], resB[8];
@@ -280,10 +284,7 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
         ptx::mbar_wait(stg_empty, (uint32_t)((it & 1) ^ 1), 401);     // conv3 of the previous tile has read the staging tile
         float4 S[8], Hs[8];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          S[g] = *reinterpret_cast<const float4*>(p.sc2 + wg * 32 + g * 4);
-          Hs[g] = *reinterpret_cast<const float4*>(p.sh2 + wg * 32 + g * 4);
-        }
+        for (int g = 0; g < 8; ++g) { S[g] = lds_f4(sc2_a + wg * 128 + g * 16); Hs[g] = lds_f4(sh2_a + wg * 128 + g * 16); }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 sc[4] = {make_float2(S[2 * j].x, S[2 * j].y), make_float2(S[2 * j].z, S[2 * j].w),
@@ -313,7 +314,7 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
         ptx::mbar_wait(&acc3_full[half], (uint32_t)(it & 1), 402 + half);
         ptx::tc_fence_after();
         const uint32_t taddr = lane_addr + kAcc3Col + half * 128 + wg * 64;
-        const float* s3 = p.sc3 + c * 64; const float* h3 = p.sh3 + c * 64;
+        const uint32_t s3 = sc3_a + c * 256, h3 = sh3_a + c * 256;
         uint32_t r[32];
         ptx::tmem_ld_32x32(taddr, r);
         ptx::tmem_ld_wait();
@@ -329,7 +330,7 @@ bneck_tail_kernel(const __grid_constant__ CUtensorMap tmT, const __grid_constant
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&acc3_empty[half]);
-        bn_res_relu(r, &cur[4], s3 + 32, h3 + 32, o);
+        bn_res_relu(r, &cur[4], s3 + 128, h3 + 128, o);
 #pragma unroll
         for (int j = 0; j < 4; ++j) sts128(orow + (((uint32_t)(4 + j) ^ swz) << 4), o[j]);
         ptx::fence_proxy_async();
@@ -374,11 +375,7 @@ int build_bneck_tail(TailLaunch* L, const void* t1, const void* w2, const float*
              "build_bneck_tail: the halo slab of a %dx%d band does not fit", p.RM, W);
   p.tiles_per_img = ceil_div(H, p.RM);
   p.num_tiles = n * p.tiles_per_img;
-  // the folded BatchNorm vectors travel by value (see TailParams); a plan is rebuilt whenever the weights are reloaded
-  AP_CHECK_CUDA(cudaMemcpy(p.sc2, scale2, kCM * sizeof(float), cudaMemcpyDeviceToHost));
-  AP_CHECK_CUDA(cudaMemcpy(p.sh2, shift2, kCM * sizeof(float), cudaMemcpyDeviceToHost));
-  AP_CHECK_CUDA(cudaMemcpy(p.sc3, scale3, kCO * sizeof(float), cudaMemcpyDeviceToHost));
-  AP_CHECK_CUDA(cudaMemcpy(p.sh3, shift3, kCO * sizeof(float), cudaMemcpyDeviceToHost));
+  p.scale2 = scale2; p.shift2 = shift2; p.scale3 = scale3; p.shift3 = shift3;
   if (make_tmap_nhwc4d_bf16(&I.tmT, t1, n, H, W, kCM, p.Wp, p.RM + 2)) return 1;
   if (make_tmap_tiled_bf16(&I.tmW2, w2, kCM, 9 * kCM, 9 * kCM, kCM, 64)) return 1;
   if (make_tmap_tiled_bf16(&I.tmW3, w3, kCO, kCM, kCM, kCO, 64)) return 1;

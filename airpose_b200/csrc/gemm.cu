@@ -350,13 +350,12 @@ int num_sms() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
   }
+  return n;
+}
 
 static thread_local int tl_grid_cap = 0;
 void set_grid_cap(int cap) { tl_grid_cap = cap; }
 int grid_limit() { return tl_grid_cap > 0 ? std::min(tl_grid_cap, num_sms()) : num_sms(); }
-
-  return n;
-}
 
 bool use_tma_epilogue() {
   static const bool on = getenv("AIRPOSE_NO_TMA_EPI") == nullptr;

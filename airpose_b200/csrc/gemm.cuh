@@ -73,7 +73,7 @@ int make_tmap_nhwc4d_bf16(CUtensorMap* out, const void* base, int n, int H, int 
 
 // Fused bottleneck tail (bneck.cu): conv2 3x3 + BN + ReLU -> conv3 1x1 + BN + residual + ReLU in one launch.
 struct alignas(64) TailLaunch {
-  unsigned char storage[3456];     // five tensor maps + the kernel parameters incl. the folded BatchNorm vectors (TailLaunchImpl in bneck.cu)
+  unsigned char storage[832];      // five tensor maps + the kernel parameters (TailLaunchImpl in bneck.cu)
   int valid = 0;
   int pdl = 0;
 };

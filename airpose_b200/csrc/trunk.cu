@@ -373,7 +373,6 @@ extern "C" int airpose_net_destroy(airpose_net_t* h) {
 }
 
 static int load_trunk(airpose_net_t* h, const airpose_conv_params* conv, float bn_eps, cudaStream_t st) {
-  h->plansA.clear(); h->plansB.clear();      // fused-kernel plans carry the folded BatchNorm vectors by value (bneck.cu)
   for (size_t i = 0; i < h->specs.size(); ++i) {
     const ConvSpec& s = h->specs[i];
     const airpose_conv_params& c = conv[i];
@@ -573,8 +572,6 @@ static int backbone_fwd_segments(airpose_net_t* h, const float* x0, int n0, cons
       auto key = std::make_pair(n, 2 * i0 + set);
       auto it = h->plansA.find(key);
       if (it == h->plansA.end()) {
-        AP_CHECK_CUDA(cudaStreamSynchronize(cst));      // plan building reads the folded BatchNorm vectors back (bneck.cu)
-        AP_CHECK_CUDA(cudaStreamSynchronize(st));
         TrunkPlan plan;
         if (build_plan_a(h, n, i0, set, &plan)) return 1;
         it = h->plansA.emplace(key, std::move(plan)).first;

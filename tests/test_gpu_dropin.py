@@ -169,3 +169,37 @@ GRAD_LOSS_REL = 1e-3
 GRAD_COS_ALL = 0.9995
 GRAD_COS_CONV = 0.5
 GRAD_COS_BN = 0.5
+
+
+def test_translation_init_branches_match_reference(tmp_path):
+    """copenet_twoview.py:178-188: ground-truth translation on aircapdata test runs, ground truth + noise when
+    hparams.smpltrans_noise_sigma is set (the reference's own add_noise_input_smpltrans under the same seed), [0, 0, 10] otherwise."""
+    if not rh.available():
+        pytest.skip("reference sources absent (oracle/_ref)")
+    from argparse import Namespace
+    from airpose_b200 import synthetic
+    from airpose_b200.copenet_twoview import copenet_twoview
+    rh.import_reference("cuda")
+    from copenet.utils.utils import add_noise_input_smpltrans
+    B = 5
+    mp = synthetic.write_mean_params(str(tmp_path / "m.npz"))
+    synthetic.write_smplx_model(str(tmp_path), 0)
+    batch = rh.make_batch(B, 11, 12, device="cuda")
+    hp = dict(smpl_mean_params=mp, smplx_model_dir=str(tmp_path), batch_size=B, val_batch_size=B, reg_iters=3)
+    mod = copenet_twoview(Namespace(smpltrans_noise_sigma=0.1, testdata="aerialpeople", **hp)).to("cuda").eval()
+    torch.manual_seed(99)
+    (s0, s1), (u0, u1) = mod._init_translation(B, torch.device("cuda"), batch)
+    torch.manual_seed(99)
+    r0, _ = add_noise_input_smpltrans(batch["smpltrans_rel0"], 0.1)
+    r1, _ = add_noise_input_smpltrans(batch["smpltrans_rel1"], 0.1)
+    assert torch.equal(u0, r0) and torch.equal(u1, r1)
+    assert torch.equal(s0, r0 * 0.05) and torch.equal(s1, r1 * 0.05)
+    out = mod.fwd_pass(batch)                                   # runs end to end with per-view initial translations
+    assert torch.isfinite(out["pred_vertices_cam0"]).all() and out["in_smpltrans1"].shape == (B, 3)
+    mod = copenet_twoview(Namespace(smpltrans_noise_sigma=None, testdata="aircapdata", **hp)).to("cuda").eval()
+    (s0, s1), (u0, u1) = mod._init_translation(B, torch.device("cuda"), batch, is_test=True)
+    assert torch.equal(u0, batch["smpltrans_rel0"]) and torch.equal(u1, batch["smpltrans_rel1"])
+    (s0, _), (u0, _) = mod._init_translation(B, torch.device("cuda"), batch, is_test=False)
+    assert torch.equal(u0, torch.tensor([0.0, 0.0, 10.0], device="cuda").expand(B, 3)) and torch.equal(s0, u0 * 0.05)
+    with pytest.raises(KeyError):
+        mod._init_translation(B, torch.device("cuda"), {"im0": batch["im0"]}, is_test=True)

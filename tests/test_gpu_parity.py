@@ -1253,7 +1253,7 @@ def test_autograd_training_step_matches_hand_scheduled(tmp_path, smplx_dir, smpl
     with torch.no_grad():
         xf = net._forward_feat_ext_train_pair(batch["im0"].contiguous(), batch["im1"].contiguous(), tape=0)
         xf0, xf1 = xf[:B], xf[B:]
-        pred, ctx = net.ief_train_forward(xf0, xf1, batch["bb0"], batch["bb1"], in_trans, in_trans, iters=3, mask1=m1, mask2=m2)
+        pred, ctx = net.ief_train_forward(xf0, xf1, batch["bb0"], batch["bb1"], in_trans[0], in_trans[1], iters=3, mask1=m1, mask2=m2)
         out = mod._after_regressor(pred, (batch["intr0"], batch["intr1"]), in_unscaled)
         loss_a, _, g = mod.loss_and_head_backward(batch, out)
         for p in net.parameters():
@@ -1276,7 +1276,7 @@ def test_autograd_training_step_matches_hand_scheduled(tmp_path, smplx_dir, smpl
     for p in net.parameters():
         p.grad = None
     torch.manual_seed(77)                       # the node draws the same masks in the same order
-    pos0, pos1 = in_trans.clone(), in_trans.clone()
+    pos0, pos1 = in_trans[0].clone(), in_trans[1].clone()
     p0, b0, p1, b1 = net(x0=batch["im0"], x1=batch["im1"], bb0=batch["bb0"], bb1=batch["bb1"], init_position0=pos0,
                          init_position1=pos1, iters=3)
     assert p0.requires_grad and b1.requires_grad and tuple(p0.shape) == (B, 135) and tuple(b0.shape) == (B, 10)
@@ -1321,9 +1321,9 @@ def test_autograd_training_step_matches_hand_scheduled(tmp_path, smplx_dir, smpl
     assert worst_reg < 1e-3
     assert worst_trunk < 2.5e-1 and worst_cos > 0.98 and total_cos > 0.995
     # one outstanding graph per module: a second train-mode forward invalidates the first one's tapes
-    q0, _, _, _ = net(x0=batch["im0"], x1=batch["im1"], bb0=batch["bb0"], bb1=batch["bb1"], init_position0=in_trans,
-                      init_position1=in_trans, iters=3)
-    net(x0=batch["im0"], x1=batch["im1"], bb0=batch["bb0"], bb1=batch["bb1"], init_position0=in_trans, init_position1=in_trans, iters=3)
+    q0, _, _, _ = net(x0=batch["im0"], x1=batch["im1"], bb0=batch["bb0"], bb1=batch["bb1"], init_position0=in_trans[0],
+                      init_position1=in_trans[1], iters=3)
+    net(x0=batch["im0"], x1=batch["im1"], bb0=batch["bb0"], bb1=batch["bb1"], init_position0=in_trans[0], init_position1=in_trans[1], iters=3)
     with pytest.raises(RuntimeError, match="overwritten"):
         q0.sum().backward()
 
