@@ -161,6 +161,15 @@ class LossArgs(C.Structure):
                                            "g_rotmat0", "g_rotmat1", "g_betas0", "g_betas1", "g_trans0", "g_trans1")])
 
 
+class RealLossArgs(C.Structure):
+    _fields_ = ([("batch", C.c_int32), ("num_joints", C.c_int32), ("gt_joints", C.c_int32),
+                 ("trans0", C.c_void_p), ("trans1", C.c_void_p), ("trans_stride", C.c_int32)] +
+                [(n, C.c_void_p) for n in ("rotmat0", "rotmat1", "betas0", "betas1", "j2d0", "j2d1", "gt_j2d0", "gt_j2d1")] +
+                [(n, C.c_float) for n in ("w_kp2d", "w_limbs2d", "w_beta", "w_pose", "w_vposer", "vposer_term")] +
+                [("out", C.c_void_p)] +
+                [(n, C.c_void_p) for n in ("g_j2d0", "g_j2d1", "g_rotmat0", "g_rotmat1", "g_betas0", "g_betas1", "g_trans0", "g_trans1")])
+
+
 class AdamArgs(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
                 ("max_exp_avg_sq", C.c_void_p), ("n", C.c_int64), ("lr", C.c_float), ("beta1", C.c_float),
@@ -216,6 +225,7 @@ SYMBOLS = {
     "airpose_hmr_ief_fwd": (C.c_int, [C.c_void_p, C.POINTER(HmrIefArgs), C.c_void_p]),
     "airpose_adam_step": (C.c_int, [C.POINTER(AdamArgs), C.c_void_p]),
     "airpose_twoview_loss": (C.c_int, [C.POINTER(LossArgs), C.c_void_p]),
+    "airpose_real_loss": (C.c_int, [C.POINTER(RealLossArgs), C.c_void_p]),
     "airpose_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "airpose_conv_bf16": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "airpose_bneck_tail_bf16": (C.c_int, [C.POINTER(BneckTailArgs), C.c_void_p]),

@@ -102,6 +102,11 @@ class copenet_twoview(nn.Module):
         self.smplx = SMPLX(hparams.smplx_model_dir, batch_size=hparams.batch_size, create_transl=False)
         self.focal_length = FOCAL_LENGTH
 
+    def _focal(self, view):
+        """Focal length pair of camera ``view`` (one constant for both in copenet, copenet_twoview.py:30-31; per camera in
+        copenet_real, see airpose_b200/copenet_real.py)."""
+        return self.focal_length
+
     def forward(self, **kwargs):
         return self.model(**kwargs)
 
@@ -180,7 +185,7 @@ class copenet_twoview(nn.Module):
                 global_orient=None,                                       # identity (:283)
                 transl=None, pose2rot=False,                              # the reference passes zeros (:284); None skips the add
                 root_R=rotmat[:, 0], root_t=trans,                        # transform_smpl (:287-292)
-                focal_length=self.focal_length, camera_center=intr[v][:, :2, 2])   # :307-317
+                focal_length=self._focal(v), camera_center=intr[v][:, :2, 2])   # :307-317
             out.update({"pred_pose%d" % v: pose, "pred_betas%d" % v: betas, "pred_rotmat%d" % v: rotmat,
                         "pred_smpltrans%d" % v: trans, "in_smpltrans%d" % v: in_trans_unscaled[v],
                         "pred_output_cam%d" % v: mo,
@@ -345,7 +350,7 @@ class copenet_twoview(nn.Module):
             sg = smplx_backward(self.smplx, betas, rotmat[:, 1:], None, grad_vertices=g["vertices%d" % v],
                                 grad_joints=g["joints%d" % v], grad_joints_2d=g["joints_2d%d" % v],
                                 joints=out["pred_output_cam%d" % v].joints, root_R=rotmat[:, 0], root_t=pose[:, :3],
-                                focal_length=self.focal_length)
+                                focal_length=self._focal(v))
             g_rot = g["rotmat%d" % v].clone()
             g_rot[:, 1:] += sg["body_pose"]
             g_rot[:, 0] += sg["root_R"]

@@ -190,6 +190,90 @@ __global__ void loss_final_kernel(LossK k, int nparts) {
 
 double* g_partial[16] = {nullptr};
 
+// ------------------------------------------------------------------------------ copenet_real's get_loss (VPoser-free part)
+// /root/reference/copenet_real/src/copenet_real/copenet_twoview.py:99-160: confidence-weighted 2D keypoints over the first 22
+// joints with the limb weights (:115-121), cross-view pose consistency (:137), beta regulariser + cross-view beta consistency
+// (:139-141), depth barrier exp(-t_z)^2 (:148-149), x60 (:151).  A few thousand elements: ONE CTA, every term a strided loop
+// with fp64 per-thread partials reduced in a fixed order (deterministic); gradients are elementwise and written in the same loops.
+constexpr int kRealThreads = 256;
+constexpr int kRealTerms = 4;          // keypoints, pose, betas, depth barrier
+
+__global__ void __launch_bounds__(kRealThreads) real_loss_kernel(airpose_real_loss_args a) {
+  __shared__ double red[kRealTerms][kRealThreads];
+  const int B = a.batch, J = a.num_joints, JG = a.gt_joints, t = threadIdx.x;
+  const bool grads = a.g_j2d0 != nullptr;
+  double acc[kRealTerms] = {0.0, 0.0, 0.0, 0.0};
+  const float wl = a.w_limbs2d;
+  // ---- 2D keypoints: mean over B * 22 * 2 of [(p0 - g0)^2 c0 + (p1 - g1)^2 c1] * limb weight             :115-121
+  {
+    const int n = B * 22 * 2;
+    const float gs = 60.f * a.w_kp2d * 2.f / (float)n;
+    if (grads)
+      for (int i = t; i < B * J * 2; i += kRealThreads) { a.g_j2d0[i] = 0.f; a.g_j2d1[i] = 0.f; }
+    __syncthreads();
+    for (int i = t; i < n; i += kRealThreads) {
+      const int b = i / 44, j = (i % 44) >> 1, c = i & 1;
+      const float lw = (j == 4 || j == 5 || j == 18 || j == 19) ? wl : ((j == 7 || j == 8 || j == 20 || j == 21) ? wl * wl : 1.f);
+      const int ip = (b * J + j) * 2 + c, ig = (b * JG + j) * 3;
+      const float d0 = a.j2d0[ip] - a.gt_j2d0[ig + c], d1 = a.j2d1[ip] - a.gt_j2d1[ig + c];
+      const float c0 = a.gt_j2d0[ig + 2], c1 = a.gt_j2d1[ig + 2];
+      acc[0] += (double)((d0 * d0 * c0 + d1 * d1 * c1) * lw);
+      if (grads) { a.g_j2d0[ip] = gs * lw * c0 * d0; a.g_j2d1[ip] = gs * lw * c1 * d1; }
+    }
+  }
+  // ---- cross-view pose consistency: mean over B * 21 * 9 of (R0 - R1)^2 on the body rotations              :137
+  {
+    const int n = B * 21 * 9;
+    const float gs = 60.f * a.w_pose * 2.f / (float)n;
+    for (int i = t; i < B * 22 * 9; i += kRealThreads) {
+      const int j = (i / 9) % 22;
+      float g = 0.f;
+      if (j > 0) {
+        const float d = a.rotmat0[i] - a.rotmat1[i];
+        acc[1] += (double)(d * d);
+        g = gs * d;
+      }
+      if (grads) { a.g_rotmat0[i] = g; a.g_rotmat1[i] = -g; }
+    }
+  }
+  // ---- betas: mean(b0^2) + mean(b1^2) + mean((b0 - b1)^2)                                                   :139-141
+  {
+    const int n = B * 10;
+    const float gs = 60.f * a.w_beta * 2.f / (float)n;
+    for (int i = t; i < n; i += kRealThreads) {
+      const float b0 = a.betas0[i], b1 = a.betas1[i], d = b0 - b1;
+      acc[2] += (double)(b0 * b0 + b1 * b1 + d * d);
+      if (grads) { a.g_betas0[i] = gs * (b0 + d); a.g_betas1[i] = gs * (b1 - d); }
+    }
+  }
+  // ---- depth barrier: mean_B exp(-t_z)^2 per view                                                            :148-149
+  for (int b = t; b < B; b += kRealThreads) {
+    const float e0 = expf(-a.trans0[(size_t)b * a.trans_stride + 2]), e1 = expf(-a.trans1[(size_t)b * a.trans_stride + 2]);
+    acc[3] += (double)(e0 * e0 + e1 * e1);
+    if (grads) {
+      const float gs = 60.f * -2.f / (float)B;
+      a.g_trans0[b * 3] = 0.f; a.g_trans0[b * 3 + 1] = 0.f; a.g_trans0[b * 3 + 2] = gs * e0 * e0;
+      a.g_trans1[b * 3] = 0.f; a.g_trans1[b * 3 + 1] = 0.f; a.g_trans1[b * 3 + 2] = gs * e1 * e1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kRealTerms; ++k) red[k][t] = acc[k];
+  __syncthreads();
+  for (int s = kRealThreads / 2; s > 0; s >>= 1) {          // fixed-order tree
+    if (t < s)
+#pragma unroll
+      for (int k = 0; k < kRealTerms; ++k) red[k][t] += red[k][t + s];
+    __syncthreads();
+  }
+  if (t == 0) {
+    const double l_kp = red[0][0] / (B * 22 * 2), l_pose = red[1][0] / (B * 21 * 9), l_beta = red[2][0] / (B * 10);
+    const double l_depth = red[3][0] / B;
+    const double loss = 60.0 * (a.w_kp2d * l_kp + a.w_beta * l_beta + a.w_vposer * a.vposer_term + a.w_pose * l_pose + l_depth);
+    // order of the reference's `losses` dict (:153-157)
+    a.out[0] = (float)loss; a.out[1] = a.vposer_term; a.out[2] = (float)l_pose; a.out[3] = (float)l_kp; a.out[4] = (float)l_beta;
+  }
+}
+
 }  // namespace
 }  // namespace airpose
 
@@ -221,6 +305,20 @@ extern "C" int airpose_twoview_loss(const airpose_twoview_loss_args* a, void* st
   loss_partial_kernel<<<kLossGrid, kLossThreads, 0, st>>>(k);
   AP_LAUNCH_CHECK();
   loss_final_kernel<<<1, 32, 0, st>>>(k, kLossGrid);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int airpose_real_loss(const airpose_real_loss_args* a, void* stream_) {
+  AP_REQUIRE(a, "airpose_real_loss: null argument");
+  AP_REQUIRE(a->batch > 0 && a->num_joints >= 22 && a->gt_joints >= 22, "airpose_real_loss: bad sizes (B=%d J=%d gt J=%d)", a->batch,
+             a->num_joints, a->gt_joints);
+  AP_REQUIRE(a->trans0 && a->trans1 && a->rotmat0 && a->rotmat1 && a->betas0 && a->betas1 && a->j2d0 && a->j2d1 && a->gt_j2d0 &&
+             a->gt_j2d1 && a->out, "airpose_real_loss: null argument");
+  const bool any_g = a->g_j2d0 || a->g_j2d1 || a->g_rotmat0 || a->g_rotmat1 || a->g_betas0 || a->g_betas1 || a->g_trans0 || a->g_trans1;
+  const bool all_g = a->g_j2d0 && a->g_j2d1 && a->g_rotmat0 && a->g_rotmat1 && a->g_betas0 && a->g_betas1 && a->g_trans0 && a->g_trans1;
+  AP_REQUIRE(!any_g || all_g, "airpose_real_loss: gradient buffers must be given all together or not at all");
+  real_loss_kernel<<<1, kRealThreads, 0, (cudaStream_t)stream_>>>(*a);
   AP_LAUNCH_CHECK();
   return 0;
 }

@@ -407,6 +407,25 @@ typedef struct {
 } airpose_twoview_loss_args;
 int airpose_twoview_loss(const airpose_twoview_loss_args* a, void* stream);
 
+/* copenet_real's get_loss without the VPoser prior (copenet_real/src/copenet_real/copenet_twoview.py:99-160; SURVEY.md 8(f)
+ * rank 4): confidence-weighted 2D keypoint loss over the first 22 joints with the limb weights, cross-view pose and beta
+ * consistency, beta regulariser, exp(-t_z)^2 depth barrier, x60; `vposer_term` (loss_regul_vposer, computed by the caller if it
+ * has the VPoser model, else 0) enters the total with `w_vposer`.  gt_j2d* = smpl_joints_2d{0,1}[:, 0]: [B, gt_joints, 3] =
+ * (x, y, confidence).  `out` receives 5 floats in the order of the reference's `losses` dict: loss, loss_regul_vposer,
+ * loss_regr_pose, loss_keypoints, loss_regul_betas.  Gradient buffers: all NULL or all given (g_trans* dense [B,3]). */
+typedef struct {
+  int32_t batch, num_joints, gt_joints;                 /* B, 127, joints per ground-truth row (>= 22) */
+  const float* trans0; const float* trans1; int32_t trans_stride;        /* pred_smpltrans  [B,3] */
+  const float* rotmat0; const float* rotmat1;           /* pred_rotmat        [B,22,3,3] */
+  const float* betas0; const float* betas1;             /* pred_betas         [B,10] */
+  const float* j2d0; const float* j2d1;                 /* pred_joints_2d_cam [B,127,2] */
+  const float* gt_j2d0; const float* gt_j2d1;           /* [B, gt_joints, 3] */
+  float w_kp2d, w_limbs2d, w_beta, w_pose, w_vposer, vposer_term;
+  float* out;                                           /* [5] */
+  float* g_j2d0; float* g_j2d1; float* g_rotmat0; float* g_rotmat1; float* g_betas0; float* g_betas1; float* g_trans0; float* g_trans1;
+} airpose_real_loss_args;
+int airpose_real_loss(const airpose_real_loss_args* a, void* stream);
+
 /* torch.optim.Adam(..., weight_decay=0, amsgrad=True) (copenet_twoview.py:416-425) over a FLAT fp32 buffer:
  * one launch per step for all 27.1 M parameters.  `step` is the 1-based step count (bias corrections are
  * formed on the host in fp64 like torch's python scalars).  max_exp_avg_sq = NULL gives plain Adam.

@@ -415,6 +415,29 @@ def get_loss(hp, gt, out):
                          "loss_regul_betas": float(l_beta)}
 
 
+def real_get_loss(hp, gt, out, vposer_term=0.0):
+    """copenet_real's get_loss (copenet_real/src/copenet_real/copenet_twoview.py:99-160) WITHOUT the VPoser prior (its
+    weights are an external download; ``vposer_term`` = loss_regul_vposer if the caller has it, 0 otherwise):
+    confidence-weighted 2D keypoint loss over the first 22 joints with the limb weights (:115-121), cross-view pose
+    consistency (:137), beta regulariser + cross-view beta consistency (:139-141), the exp(-t_z)^2 depth barrier (:148-149),
+    x60 (:151).  ``gt['smpl_joints_2d%d']`` is [B,1,J,3] = (x, y, confidence)."""
+    mse = lambda a, b: (a - b) ** 2
+    g0, g1 = gt["smpl_joints_2d0"][:, 0], gt["smpl_joints_2d1"][:, 0]
+    lk = (mse(out["pred_joints_2d_cam0"][:, :22], g0[:, :22, :2]) * g0[:, :22, 2:]
+          + mse(out["pred_joints_2d_cam1"][:, :22], g1[:, :22, :2]) * g1[:, :22, 2:])
+    lk[:, [4, 5, 18, 19]] *= hp["limbs2d_loss_weight"]
+    lk[:, [7, 8, 20, 21]] *= hp["limbs2d_loss_weight"] ** 2
+    l_kp = lk.mean()
+    l_pose = mse(out["pred_rotmat0"][:, 1:], out["pred_rotmat1"][:, 1:]).mean()
+    b0, b1 = out["pred_betas0"], out["pred_betas1"]
+    l_beta = (b0 * b0).mean() + (b1 * b1).mean() + mse(b0, b1).mean()
+    loss = (hp["keypoint2d_loss_weight"] * l_kp + hp["beta_loss_weight"] * l_beta + hp["vposer_loss_weight"] * vposer_term
+            + hp["pose_loss_weight"] * l_pose + (np.exp(-out["pred_smpltrans0"][:, 2]) ** 2).mean()
+            + (np.exp(-out["pred_smpltrans1"][:, 2]) ** 2).mean()) * 60
+    return float(loss), {"loss": float(loss), "loss_regul_vposer": float(vposer_term), "loss_regr_pose": float(l_pose),
+                         "loss_keypoints": float(l_kp), "loss_regul_betas": float(l_beta)}
+
+
 DEFAULT_LOSS_WEIGHTS = {   # copenet_twoview.py:655-677
     "shape_loss_weight": 50, "keypoint2d_loss_weight": 0.002, "keypoint3d_loss_weight": 1,
     "limbs3d_loss_weight": 3, "limbstheta_loss_weight": 1, "trans_loss_weight": 10,

@@ -56,9 +56,10 @@ def test_reference_fwd_pass_and_loss_over_airpose_objects(ref_module):
     rel_loss = abs(float(loss) - float(g["loss"])) / float(g["loss"])
     print("reference LightningModule over airpose_b200: vertices rel err %s, loss %.6g vs reference %.6g (rel %.2e)" %
           (worst, float(loss), float(g["loss"]), rel_loss))
-    # the only deviation is the bf16 trunk (the golden is the reference's fp32 run): 2.7e-3 on the features
-    assert max(worst.values()) < 1e-2
-    assert rel_loss < 3e-2
+    # the only deviation is the bf16 trunk (the golden is the reference's fp32 run): 2.7e-3 on the features.
+    # measured on B200: vertices 8.2e-4 / 1.1e-3, loss 3.6e-3; bounds = 2x
+    assert max(worst.values()) < 2.5e-3
+    assert rel_loss < 8e-3
     for k in ("loss_regr_pose", "loss_regr_shape", "loss_regul_betas"):
         assert abs(losses[k] - float(g["loss/" + k])) <= 5e-2 * abs(float(g["loss/" + k])) + 1e-4, k
 
@@ -167,8 +168,8 @@ def test_whole_network_gradient_matches_reference_fp32_backward(tmp_path):
 # there first (worst tensor 0.73).  fp32 dz for those layers is the known fix.
 GRAD_LOSS_REL = 1e-3
 GRAD_COS_ALL = 0.9995
-GRAD_COS_CONV = 0.5
-GRAD_COS_BN = 0.5
+GRAD_COS_CONV = 0.6          # measured 0.80
+GRAD_COS_BN = 0.45           # measured 0.73
 
 
 def test_translation_init_branches_match_reference(tmp_path):

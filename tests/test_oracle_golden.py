@@ -1,5 +1,7 @@
 """Pin the numpy oracle against outputs of the real reference (tests/golden, made by
 oracle/gen_golden.py) and against the known-answer identities of SURVEY.md section 8(c)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -314,3 +316,18 @@ def test_torch_port_train_mode_regressor_matches_reference():
     with torch.no_grad():
         q0, _, _, _ = tp.ief_train(sd, f(g["xf0"]), f(g["xf1"]), f(x["bb0"]), f(x["bb1"]), init, init, torch.ones_like(m1), torch.ones_like(m2), iters=iters)
     assert rel_err(q0.numpy(), g["pred_pose0"]) > 1e-4
+
+
+def test_real_loss_oracle_matches_reference_golden():
+    """copenet_real's get_loss (VPoser term stubbed to zero) restated in numpy against the reference's own function
+    (extracted with ast and run by oracle/gen_golden_real.py): loss and every entry of its `losses` dict."""
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "real_loss.npz"))
+    hp = {k[3:]: float(g[k]) for k in g.files if k.startswith("hp/")}
+    for B in (1, 6):
+        p = "b%d/" % B
+        case = {k[len(p):]: g[k] for k in g.files if k.startswith(p) and "/" not in k[len(p):]}
+        loss, losses = orc.real_get_loss(hp, case, case)
+        assert abs(loss - float(g[p + "loss"])) <= 2e-6 * abs(float(g[p + "loss"]))
+        for k in ("loss_regr_pose", "loss_keypoints", "loss_regul_betas", "loss_regul_vposer"):
+            assert abs(losses[k] - float(g[p + "losses/" + k])) <= 2e-6 * abs(float(g[p + "losses/" + k])) + 1e-12, k
