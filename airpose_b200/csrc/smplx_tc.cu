@@ -66,7 +66,8 @@ constexpr int kROff = kFOff + kFStages * kFStageBytes;
 constexpr int kBarOff = kROff + kRStages * kRStageBytes;
 constexpr int kNumBars = 1 + 2 * kFStages + 4 + 2 * kRStages;
 constexpr int kSmemBytes = 1024 + kBarOff + kNumBars * 8 + 16;
-constexpr int kTmemCols = 256;                         // 2 buffers x 3 coordinates x 32 columns = 192
+constexpr int kTmemCols = 512;                         // 2 buffers x 3 coordinates x (32 hi + 32 lo) columns = 384
+constexpr int kAccCols = 6 * kTcMeshTile;              // columns of one accumulator buffer
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget exceeded");
 static_assert(kRStageBytes % 16 == 0 && kROff % 16 == 0, "bulk copies need 16-byte alignment");
 
@@ -200,7 +201,11 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, kTcMeshTile);
+      // F_hi | F_lo of a k-block are 64 consecutive K-major rows of the stage: ONE N = 64 MMA per k-step and coordinate writes the
+      // hi products into columns 0..31 and the lo products into 32..63 (the epilogue adds them) -- the 128-row P operand is read
+      // from shared memory once per k-step instead of twice (UMMA operand reads were 39 % of the shared-memory data pipe)
+      constexpr uint32_t idesc = make_idesc_f16(128, 2 * kTcMeshTile);
+      constexpr uint32_t idesc_x = make_idesc_f16(128, kTcMeshTile);
       ptx::mbar_wait(p_full, 0, 200);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
@@ -213,26 +218,22 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
           ptx::tc_fence_after();
           const uint32_t fs = ptx::smem_u32(smem + kFOff + stage * kFStageBytes);
           if (kb < 3) {
-            const uint64_t bh = ptx::make_kmajor_sw128_desc(fs);
-            const uint64_t bl = ptx::make_kmajor_sw128_desc(fs + kFHalfBytes);
+            const uint64_t bhl = ptx::make_kmajor_sw128_desc(fs);          // rows 0..31 = hi, 32..63 = lo
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               const uint64_t ad = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem + (c * 3 + kb) * kPTileBytes));
-              const uint32_t d_tmem = tmem_base + as * 96 + c * kTcMeshTile;
+              const uint32_t d_tmem = tmem_base + as * kAccCols + c * 2 * kTcMeshTile;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                ptx::umma_bf16(d_tmem, ad + 2 * k, bh + 2 * k, idesc, (kb | k) != 0);
-                ptx::umma_bf16(d_tmem, ad + 2 * k, bl + 2 * k, idesc, 1);
-              }
+              for (int k = 0; k < 4; ++k) ptx::umma_bf16(d_tmem, ad + 2 * k, bhl + 2 * k, idesc, (kb | k) != 0);
             }
           } else {                                      // K = 32: template + shape blend (64-byte swizzled rows)
             const uint64_t bx = ptx::make_kmajor_desc(fs, 64);
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
               const uint64_t ad = ptx::make_kmajor_desc(ptx::smem_u32(smem + kPxOff + c * kPxTileBytes), 64);
-              const uint32_t d_tmem = tmem_base + as * 96 + c * kTcMeshTile;
+              const uint32_t d_tmem = tmem_base + as * kAccCols + c * 2 * kTcMeshTile;      // into the hi columns
 #pragma unroll
-              for (int k = 0; k < 2; ++k) ptx::umma_bf16(d_tmem, ad + 2 * k, bx + 2 * k, idesc, 1);
+              for (int k = 0; k < 2; ++k) ptx::umma_bf16(d_tmem, ad + 2 * k, bx + 2 * k, idesc_x, 1);
             }
           }
           ptx::umma_commit(&f_empty[stage]);
@@ -279,7 +280,7 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
       const int slot = s % kRStages; const uint32_t rph = (s / kRStages) & 1;
       ptx::mbar_wait(&tfull[as], aphase, 400 + as);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * 96 + hf * kTcSub;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * kAccCols + hf * kTcSub;
       ptx::mbar_wait(&r_full[slot], rph, 410 + slot);
       const uint32_t rbase = ptx::smem_u32(smem + kROff + slot * kRStageBytes);
       const int mesh0 = t * kTcMeshTile + hf * kTcSub;
@@ -289,8 +290,12 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
       for (int mq = 0; mq < kTcSub / UN; ++mq) {
         uint32_t dx[UN], dy[UN], dz[UN];
         tmem_ld_32xN(taddr + mq * UN, dx);
-        tmem_ld_32xN(taddr + kTcMeshTile + mq * UN, dy);
-        tmem_ld_32xN(taddr + 2 * kTcMeshTile + mq * UN, dz);
+        tmem_ld_32xN(taddr + 2 * kTcMeshTile + mq * UN, dy);
+        tmem_ld_32xN(taddr + 4 * kTcMeshTile + mq * UN, dz);
+        uint32_t lx[UN], ly[UN], lz[UN];                  // the lo products
+        tmem_ld_32xN(taddr + kTcMeshTile + mq * UN, lx);
+        tmem_ld_32xN(taddr + 3 * kTcMeshTile + mq * UN, ly);
+        tmem_ld_32xN(taddr + 5 * kTcMeshTile + mq * UN, lz);
         ptx::tmem_ld_wait();
         if (mq == kTcSub / UN - 1) {                      // accumulator is in registers: MMA may refill it
           ptx::tc_fence_before();
@@ -307,9 +312,12 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
           // pair record: field f of meshes (b, b+1) = one float2 at index f
           const uint32_t rec = rbase + (uint32_t)(m >> 1) * 2 * kRecBytes;      // byte address; field f of the pair at rec + 8 f
           // v_posed = v_template + shapedirs . beta + pose offsets (lbs.py:179, :203): all of it is the accumulator
-          const float2 x = make_float2(__uint_as_float(dx[2 * pi]) * inv_scale, __uint_as_float(dx[2 * pi + 1]) * inv_scale);
-          const float2 y = make_float2(__uint_as_float(dy[2 * pi]) * inv_scale, __uint_as_float(dy[2 * pi + 1]) * inv_scale);
-          const float2 z = make_float2(__uint_as_float(dz[2 * pi]) * inv_scale, __uint_as_float(dz[2 * pi + 1]) * inv_scale);
+          const float2 x = make_float2((__uint_as_float(dx[2 * pi]) + __uint_as_float(lx[2 * pi])) * inv_scale,
+                                       (__uint_as_float(dx[2 * pi + 1]) + __uint_as_float(lx[2 * pi + 1])) * inv_scale);
+          const float2 y = make_float2((__uint_as_float(dy[2 * pi]) + __uint_as_float(ly[2 * pi])) * inv_scale,
+                                       (__uint_as_float(dy[2 * pi + 1]) + __uint_as_float(ly[2 * pi + 1])) * inv_scale);
+          const float2 z = make_float2((__uint_as_float(dz[2 * pi]) + __uint_as_float(lz[2 * pi])) * inv_scale,
+                                       (__uint_as_float(dz[2 * pi + 1]) + __uint_as_float(lz[2 * pi + 1])) * inv_scale);
           // T = sum_k w_k A_k (lbs.py:209-213)
           float2 T[12];
 #pragma unroll
@@ -503,7 +511,7 @@ int smplx_tc_forward(const SmplxDev& d, const SmplxTc& tc, const TcCall& c, cuda
   a.rec = c.rec; a.out = c.out; a.out_cam = c.out_cam;
   a.vrows = tc.vtiles * 128;
   dim3 grid(tc.vtiles, ceil_div(a.tiles_total, a.tiles_per_cta));
-  static const int un = getenv("AIRPOSE_SMPLX_UNROLL") ? atoi(getenv("AIRPOSE_SMPLX_UNROLL")) : 4;
+  static const int un = getenv("AIRPOSE_SMPLX_UNROLL") ? atoi(getenv("AIRPOSE_SMPLX_UNROLL")) : 2;   // 4 spills at 96 registers (0.77 vs 0.64 ms)
   if (un == 2) {
     if (c.out_cam) smplx_vertex_tc_kernel<true, 2><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a);
     else smplx_vertex_tc_kernel<false, 2><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a);
