@@ -172,20 +172,40 @@ class copenet_twoview(nn.Module):
 
     def _after_regressor(self, pred, intr, in_trans_unscaled):
         """copenet_twoview.py:214-317 from the regressor outputs on: translation un-scaling, 6D -> rotation matrices,
-        SMPL-X, transform_smpl, perspective_projection (fused into one native call per view)."""
+        SMPL-X, transform_smpl, perspective_projection (fused into one native call).  When the two views' predictions are the
+        halves of one buffer (``copenet._ief`` allocates them that way) and share the focal length, BOTH views go through ONE
+        set of launches as a batch of 2B meshes; otherwise one call per view."""
         B = pred[0].shape[0]
         out = {}
+        pose2, betas2 = pred[0]._base, pred[1]._base
+        batched = (B > 0 and pose2 is not None and betas2 is not None and pose2.shape == (2 * B, 135) and betas2.shape == (2 * B, 10)
+                   and pred[2]._base is pose2 and pred[3]._base is betas2 and pred[0].data_ptr() == pose2.data_ptr()
+                   and pred[2].data_ptr() == pose2[B:].data_ptr() and tuple(self._focal(0)) == tuple(self._focal(1)))
+        if batched:
+            pose2[:, :3] /= TRANS_SCALE                                   # in-place, like :214-218
+            rotmat2 = rot6d_to_rotmat(pose2[:, 3:]).view(2 * B, 22, 3, 3)   # :222-223
+            centers = torch.cat([intr[0][:, :2, 2], intr[1][:, :2, 2]])
+            mo2, cam2 = self.smplx.forward_camera(betas=betas2, body_pose=rotmat2[:, 1:], global_orient=None, transl=None,
+                                                  pose2rot=False, root_R=rotmat2[:, 0], root_t=pose2[:, :3],
+                                                  focal_length=self._focal(0), camera_center=centers)
         for v in (0, 1):
             pose, betas = pred[2 * v], pred[2 * v + 1]
-            pose[:, :3] /= TRANS_SCALE                                   # in-place on the view, like :214-218
+            if batched:
+                sl = slice(v * B, (v + 1) * B)
+                rotmat = rotmat2[sl]
+                mo = type(mo2)(**{k: (val[sl] if torch.is_tensor(val) and val.shape[:1] == (2 * B,) else val)
+                                  for k, val in mo2._asdict().items()})
+                cam = {k: val[sl] for k, val in cam2.items()}
+            else:
+                pose[:, :3] /= TRANS_SCALE                                   # in-place on the view, like :214-218
+                rotmat = rot6d_to_rotmat(pose[:, 3:]).view(B, 22, 3, 3)      # :222-223
+                mo, cam = self.smplx.forward_camera(
+                    betas=betas, body_pose=rotmat[:, 1:],
+                    global_orient=None,                                       # identity (:283)
+                    transl=None, pose2rot=False,                              # the reference passes zeros (:284); None skips the add
+                    root_R=rotmat[:, 0], root_t=pose[:, :3],                  # transform_smpl (:287-292)
+                    focal_length=self._focal(v), camera_center=intr[v][:, :2, 2])   # :307-317
             trans = pose[:, :3]
-            rotmat = rot6d_to_rotmat(pose[:, 3:]).view(B, 22, 3, 3)      # :222-223
-            mo, cam = self.smplx.forward_camera(
-                betas=betas, body_pose=rotmat[:, 1:],
-                global_orient=None,                                       # identity (:283)
-                transl=None, pose2rot=False,                              # the reference passes zeros (:284); None skips the add
-                root_R=rotmat[:, 0], root_t=trans,                        # transform_smpl (:287-292)
-                focal_length=self._focal(v), camera_center=intr[v][:, :2, 2])   # :307-317
             out.update({"pred_pose%d" % v: pose, "pred_betas%d" % v: betas, "pred_rotmat%d" % v: rotmat,
                         "pred_smpltrans%d" % v: trans, "in_smpltrans%d" % v: in_trans_unscaled[v],
                         "pred_output_cam%d" % v: mo,
@@ -209,7 +229,9 @@ class copenet_twoview(nn.Module):
         if dev.type != "cuda":
             raise _lib.AirposeError("get_loss runs on CUDA only; there is no CPU path")
         lib = _lib.load()
-        f = lambda t: t.float().contiguous()
+        def f(t):                        # float32, contiguous, 16-byte aligned (the kernel reads the vertex tensors as float4;
+            t = t.float().contiguous()   # a view's half of a two-view [2B, V, 3] buffer is misaligned when B % 4 != 0)
+            return t if t.data_ptr() % 16 == 0 else t.clone()
         B = pred_betas0.shape[0]
         v0, v1 = f(pred_output_cam0.vertices), f(pred_output_cam1.vertices)
         j0, j1 = f(pred_output_cam0.joints), f(pred_output_cam1.joints)

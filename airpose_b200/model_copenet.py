@@ -363,8 +363,11 @@ class copenet(nn.Module):
         theta0, theta1, shape0, shape1 = map(f, (theta0, theta1, shape0, shape1))
         B = xf0.shape[0]
         lib, h = self._ensure(0, device)
-        outs = [torch.empty(B, 135, device=device, dtype=torch.float32), torch.empty(B, 10, device=device, dtype=torch.float32),
-                torch.empty(B, 135, device=device, dtype=torch.float32), torch.empty(B, 10, device=device, dtype=torch.float32)]
+        # the two views' outputs are the halves of ONE [2B, .] buffer each, so that the caller can hand both views to SMPL-X in
+        # one call (copenet_twoview._after_regressor); each half is an ordinary contiguous [B, .] tensor
+        pose2 = torch.empty(2 * B, 135, device=device, dtype=torch.float32)
+        betas2 = torch.empty(2 * B, 10, device=device, dtype=torch.float32)
+        outs = [pose2[:B], betas2[:B], pose2[B:], betas2[B:]]
         if B == 0:
             return tuple(outs)
         a = _lib.IefArgs()
