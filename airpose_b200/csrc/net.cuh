@@ -88,7 +88,11 @@ struct airpose_net {
   __nv_bfloat16* bw[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // gradient ping-pong / dz / dpre / dilated
   __nv_bfloat16* bw_t0 = nullptr;       // transposed dz   [Cout][M]
   __nv_bfloat16* bw_t1 = nullptr;       // transposed im2col(x) [K][M]
-  __nv_bfloat16* bw_w = nullptr;        // packed dgrad weights / wgrad output
+  __nv_bfloat16* bw_w = nullptr;        // packed dgrad weights / wgrad output (per-layer debug entry point)
+  __nv_bfloat16* bw_wd = nullptr;       // dgrad operands of ALL convs, packed by one launch per backward pass (bw_wd_off[i])
+  __nv_bfloat16* bw_wg = nullptr;       // wgrad GEMM outputs of ALL convs, unpacked by one launch at the end of the pass
+  size_t bw_w_off[64] = {0};            // element offset of conv i inside bw_wd / bw_wg
+  bool bw_batched = false;              // inside a whole backward pass: use the per-layer slots above
   float* bw_coef = nullptr;             // [3][2048] BatchNorm backward coefficients
   int bw_cap = 0;
   std::map<std::pair<int, int>, airpose::TrunkPlan> plansA;        // (images, 2 * first image inside the group + buffer set)

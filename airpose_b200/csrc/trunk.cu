@@ -71,6 +71,46 @@ __global__ void fold_bn_kernel(const float* __restrict__ g, const float* __restr
   shift[i] = b[i] - mean[i] * s;
 }
 
+// The same two kernels for ALL 53 convs in one launch each (blockIdx.y = conv): the per-layer launches were ~6 us of fixed
+// cost each for microseconds of work, 106 of them per weight reload (and one reload per training step).  Tables by value.
+constexpr int kMaxConvs = 53;
+struct PackTab {
+  const float* w[kMaxConvs]; __nv_bfloat16* out[kMaxConvs];
+  int cout[kMaxConvs], cin[kMaxConvs], k[kMaxConvs], kpad[kMaxConvs];
+};
+__global__ void pack_conv_weight_all_kernel(const __grid_constant__ PackTab t) {
+  const int l = blockIdx.y;
+  const float* __restrict__ w = t.w[l];
+  __nv_bfloat16* __restrict__ out = t.out[l];
+  const int cin = t.cin[l], k = t.k[l], kpad = t.kpad[l];
+  const int64_t total = (int64_t)t.cout[l] * kpad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i / kpad), kk = (int)(i % kpad);
+    float val = 0.f;
+    if (l == 0) {                     // stem: [o][r][s*3+c], 21 -> 32 zero padded per vertical tap r
+      const int r = kk / kStemTapK, e = kk % kStemTapK;
+      if (e < 21) val = w[(((int64_t)o * cin + (e % 3)) * k + r) * k + e / 3];
+    } else {
+      const int tap = kk / cin, c = kk % cin;
+      val = w[(((int64_t)o * cin + c) * k * k) + tap];
+    }
+    out[i] = __float2bfloat16_rn(val);
+  }
+}
+struct FoldTab {
+  const float* g[kMaxConvs]; const float* b[kMaxConvs]; const float* mean[kMaxConvs]; const float* var[kMaxConvs];
+  float* scale[kMaxConvs]; float* shift[kMaxConvs];
+  int c[kMaxConvs];
+};
+__global__ void fold_bn_all_kernel(const __grid_constant__ FoldTab t, float eps) {
+  const int l = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t.c[l]; i += gridDim.x * blockDim.x) {
+    const float s = t.g[l][i] / sqrtf(t.var[l][i] + eps);
+    t.scale[l][i] = s;
+    t.shift[l][i] = t.b[l][i] - t.mean[l][i] * s;
+  }
+}
+
 // ------------------------------------------------------------------------------ trunk kernels
 // Stem operand pack: x fp32 NCHW [n,3,224,224] -> bf16 [n][2 parities][115 rows][112 q][32]:
 //   out[n][par][hp][q][s*3+c] = x[n][c][2*(hp-2)+par][2q-3+s]   (zero outside the image / for hp in {0,1,114})
@@ -364,6 +404,7 @@ extern "C" int airpose_net_destroy(airpose_net_t* h) {
     cudaFree(tp.pooled); cudaFree(tp.pool_idx); cudaFree(tp.stats); cudaFree(tp.stats1);
   }
   for (auto p : h->bw) cudaFree(p);
+  cudaFree(h->bw_wd); cudaFree(h->bw_wg);
   cudaFree(h->bw_t0); cudaFree(h->bw_t1); cudaFree(h->bw_w); cudaFree(h->bw_coef);
   if (h->side_stream) cudaStreamDestroy(h->side_stream);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -373,18 +414,24 @@ extern "C" int airpose_net_destroy(airpose_net_t* h) {
 }
 
 static int load_trunk(airpose_net_t* h, const airpose_conv_params* conv, float bn_eps, cudaStream_t st) {
+  AP_REQUIRE(h->specs.size() <= (size_t)kMaxConvs, "load_trunk: %zu convs exceed the table size", h->specs.size());
+  PackTab pt{};
+  FoldTab ft{};
   for (size_t i = 0; i < h->specs.size(); ++i) {
     const ConvSpec& s = h->specs[i];
     const airpose_conv_params& c = conv[i];
     AP_REQUIRE(c.weight && c.bn_weight && c.bn_bias && c.bn_mean && c.bn_var, "airpose_net_load: conv %zu has a null parameter", i);
-    const int kpad = (i == 0) ? kStemK : s.k * s.k * s.cin;
-    pack_conv_weight_kernel<<<256, 256, 0, st>>>(c.weight, h->wq[i], s.cout, s.cin, s.k, kpad, i == 0);
-    AP_LAUNCH_CHECK();
-    if (i == 0 && stem_pack_pairs_weight(c.weight, h->wq_stem_pairs, st)) return 1;
-    fold_bn_kernel<<<ceil_div(s.cout, 256), 256, 0, st>>>(c.bn_weight, c.bn_bias, c.bn_mean, c.bn_var, bn_eps, s.cout,
-                                                          h->scale[i], h->shift[i]);
-    AP_LAUNCH_CHECK();
+    pt.w[i] = c.weight; pt.out[i] = h->wq[i]; pt.cout[i] = s.cout; pt.cin[i] = s.cin; pt.k[i] = s.k;
+    pt.kpad[i] = (i == 0) ? kStemK : s.k * s.k * s.cin;
+    ft.g[i] = c.bn_weight; ft.b[i] = c.bn_bias; ft.mean[i] = c.bn_mean; ft.var[i] = c.bn_var;
+    ft.scale[i] = h->scale[i]; ft.shift[i] = h->shift[i]; ft.c[i] = s.cout;
   }
+  const unsigned nl = (unsigned)h->specs.size();
+  pack_conv_weight_all_kernel<<<dim3(64, nl), 256, 0, st>>>(pt);
+  AP_LAUNCH_CHECK();
+  if (stem_pack_pairs_weight(conv[0].weight, h->wq_stem_pairs, st)) return 1;
+  fold_bn_all_kernel<<<dim3(2, nl), 256, 0, st>>>(ft, bn_eps);
+  AP_LAUNCH_CHECK();
   return 0;
 }
 
@@ -1029,6 +1076,36 @@ __global__ void wgrad_unpack_kernel(const __nv_bfloat16* __restrict__ D, int cou
   }
 }
 
+// Both for ALL convs of a backward pass in one launch each (blockIdx.y = conv): dgrad operands packed before the pass, wgrad GEMM
+// outputs unpacked after it (each conv keeps its own slot of one scratch buffer) -- 105 launches of ~6 us fixed cost less.
+struct DgradTab { const float* w[kMaxConvs]; __nv_bfloat16* out[kMaxConvs]; int cout[kMaxConvs], cin[kMaxConvs], k[kMaxConvs]; };
+__global__ void pack_dgrad_weight_all_kernel(const __grid_constant__ DgradTab t) {
+  const int l = blockIdx.y + 1;                       // the stem has no data gradient
+  const float* __restrict__ w = t.w[l];
+  __nv_bfloat16* __restrict__ out = t.out[l];
+  const int cout = t.cout[l], cin = t.cin[l], k = t.k[l];
+  const int64_t total = (int64_t)cin * k * k * cout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % cout), tap = (int)((i / cout) % (k * k)), c = (int)(i / ((int64_t)cout * k * k));
+    const int r = tap / k, s = tap % k;
+    out[i] = __float2bfloat16_rn(w[(((int64_t)o * cin + c) * k + (k - 1 - r)) * k + (k - 1 - s)]);
+  }
+}
+struct WgradTab { const __nv_bfloat16* D[kMaxConvs]; float* g[kMaxConvs]; int cout[kMaxConvs], cin[kMaxConvs], kk[kMaxConvs], ldd[kMaxConvs]; };
+__global__ void wgrad_unpack_all_kernel(const __grid_constant__ WgradTab t, int accumulate) {
+  const int l = blockIdx.y;
+  const __nv_bfloat16* __restrict__ D = t.D[l];
+  float* __restrict__ g = t.g[l];
+  if (!g) return;
+  const int cin = t.cin[l], kk = t.kk[l], ldd = t.ldd[l];
+  const int64_t total = (int64_t)t.cout[l] * cin * kk;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % kk), c = (int)((i / kk) % cin), o = (int)(i / ((int64_t)kk * cin));
+    const float v = __bfloat162float(D[(int64_t)o * ldd + tap * cin + c]);
+    g[i] = v + (accumulate ? g[i] : 0.f);
+  }
+}
+
 // MaxPool2d(3, 2, 1) backward on NHWC bf16: every input pixel collects the gradient of the (at most four) windows whose recorded
 // argmax (maxpool_kernel's idx: the first maximum in scan order, PyTorch's tie rule) it is.  Gather form, 8 channels per thread.
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ gy, int n,
@@ -1200,6 +1277,16 @@ static int bw_reserve(airpose_net* h, int n) {
   AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_t0, (act + 8 * 2048) * 2));                       // + the pitch padding of conv_wgrad
   AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_t1, (std::max((size_t)576 * 3136, (size_t)192 * 12544) * n + 8 * 4608) * 2));
   AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_w, (size_t)512 * 4608 * 2 * 2));
+  if (!h->bw_wd) {                                   // one slot per conv for the dgrad operand and for the wgrad GEMM output
+    size_t off = 0;
+    for (size_t i = 0; i < h->specs.size(); ++i) {
+      const ConvSpec& s = h->specs[i];
+      h->bw_w_off[i] = off;
+      off += ((size_t)s.cout * (i == 0 ? 192 : s.k * s.k * s.cin) + 63) & ~(size_t)63;       // 128-byte aligned slots
+    }
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_wd, off * 2));
+    AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_wg, off * 2));
+  }
   AP_CHECK_CUDA(cudaMalloc((void**)&h->bw_coef, 2 * 3 * 2048 * sizeof(float)));
   if (!h->bn_part) AP_CHECK_CUDA(cudaMalloc((void**)&h->bn_part, (size_t)2 * kBnSlabs * 2048 * 2 * sizeof(float)));
   h->bw_cap = n;
@@ -1246,8 +1333,9 @@ static int conv_wgrad(airpose_net* h, int i, const __nv_bfloat16* dz, const __nv
   airpose_gemm_args ga{};
   ga.A = h->bw_t0; ga.lda = ld; ga.B = h->bw_t1; ga.ldb = ld;
   ga.M = s.cout; ga.N = Kdim; ga.K = (int)M;
-  ga.out_bf16 = h->bw_w; ga.ldd = Kdim;
+  ga.out_bf16 = h->bw_batched ? h->bw_wg + h->bw_w_off[i] : h->bw_w; ga.ldd = Kdim;
   if (airpose_gemm_bf16(&ga, st)) return 1;
+  if (h->bw_batched) return 0;                      // unpacked with every other conv by ONE launch at the end of the pass
   const int64_t total = (int64_t)s.cout * Kdim;
   wgrad_unpack_kernel<<<ew_grid(total), 256, 0, st>>>(h->bw_w, s.cout, s.cin, s.k * s.k, Kdim, g->g_weight[i], g->accumulate);
   AP_LAUNCH_CHECK();
@@ -1258,9 +1346,11 @@ static int conv_wgrad(airpose_net* h, int i, const __nv_bfloat16* dz, const __nv
 static int conv_dgrad(airpose_net* h, int i, const float* w_f32, const __nv_bfloat16* dz, int n, int Hin, int Hout, const __nv_bfloat16* add,
                       __nv_bfloat16* dx, __nv_bfloat16* scratch, cudaStream_t st) {
   const ConvSpec& s = h->specs[i];
-  __nv_bfloat16* wd = h->bw_w + (size_t)512 * 4608;              // second half of the weight scratch
-  pack_dgrad_weight_kernel<<<ew_grid((int64_t)s.cin * s.k * s.k * s.cout), 256, 0, st>>>(w_f32, s.cout, s.cin, s.k, wd);
-  AP_LAUNCH_CHECK();
+  __nv_bfloat16* wd = h->bw_batched ? h->bw_wd + h->bw_w_off[i] : h->bw_w + (size_t)512 * 4608;   // pre-packed / second half of the scratch
+  if (!h->bw_batched) {
+    pack_dgrad_weight_kernel<<<ew_grid((int64_t)s.cin * s.k * s.k * s.cout), 256, 0, st>>>(w_f32, s.cout, s.cin, s.k, wd);
+    AP_LAUNCH_CHECK();
+  }
   if (s.k == 1 && s.stride == 1) {
     airpose_gemm_args ga{};
     ga.A = dz; ga.lda = s.cout; ga.B = wd; ga.ldb = s.cout;
@@ -1304,6 +1394,16 @@ static int backbone_bwd_train_impl(airpose_net_t* h, const float* x, const float
   for (size_t i = 0; i < h->specs.size(); ++i)
     AP_REQUIRE(g->g_weight[i] && g->g_bn_weight[i] && g->g_bn_bias[i] && conv_weights[i], "airpose_backbone_bwd_train: null buffer (conv %zu)", i);
   if (bw_reserve(h, n)) return 1;
+  {                                                  // every conv's dgrad operand (flipped, transposed bf16 weights), one launch
+    DgradTab dt{};
+    for (size_t i = 1; i < h->specs.size(); ++i) {
+      const ConvSpec& s = h->specs[i];
+      dt.w[i] = conv_weights[i]; dt.out[i] = h->bw_wd + h->bw_w_off[i]; dt.cout[i] = s.cout; dt.cin[i] = s.cin; dt.k[i] = s.k;
+    }
+    pack_dgrad_weight_all_kernel<<<dim3(48, (unsigned)h->specs.size() - 1), 256, 0, st>>>(dt);
+    AP_LAUNCH_CHECK();
+  }
+  h->bw_batched = true;                              // conv_wgrad / conv_dgrad use the per-conv slots; reset at the end of the pass
   const std::vector<ConvIO> io = resnet50_io();
   auto src = [&](int s) -> const __nv_bfloat16* { return s == -1 ? tp.pooled : tp.y[s]; };
   __nv_bfloat16 *G = h->bw[0], *G2 = h->bw[1], *DZ = h->bw[2], *DPRE = h->bw[3], *SCR = h->bw[4], *T = h->bw[5];
@@ -1363,11 +1463,20 @@ static int backbone_bwd_train_impl(airpose_net_t* h, const float* x, const float
     airpose_gemm_args ga{};
     ga.A = h->bw_t0; ga.lda = M0; ga.B = h->bw_t1; ga.ldb = M0;
     ga.M = 64; ga.N = 192; ga.K = (int)M0;
-    ga.out_bf16 = h->bw_w; ga.ldd = 192;
+    ga.out_bf16 = h->bw_wg + h->bw_w_off[0]; ga.ldd = 192;
     if (airpose_gemm_bf16(&ga, st)) return 1;
-    wgrad_unpack_kernel<<<ew_grid(64 * 147), 256, 0, st>>>(h->bw_w, 64, 3, 49, 192, g->g_weight[0], g->accumulate);
+  }
+  {                                                  // every conv's weight gradient out of its slot, one launch
+    WgradTab wt{};
+    for (size_t i = 0; i < h->specs.size(); ++i) {
+      const ConvSpec& s = h->specs[i];
+      wt.D[i] = h->bw_wg + h->bw_w_off[i]; wt.g[i] = g->g_weight[i]; wt.cout[i] = s.cout; wt.cin[i] = s.cin;
+      wt.kk[i] = s.k * s.k; wt.ldd[i] = i == 0 ? 192 : s.k * s.k * s.cin;
+    }
+    wgrad_unpack_all_kernel<<<dim3(48, (unsigned)h->specs.size()), 256, 0, st>>>(wt, g->accumulate);
     AP_LAUNCH_CHECK();
   }
+  h->bw_batched = false;
   return 0;
 }
 
@@ -1394,6 +1503,7 @@ extern "C" int airpose_debug_conv_bwd(airpose_net_t* h, int conv_idx, int n, con
   AP_REQUIRE(conv_idx >= 1 && conv_idx < (int)h->specs.size() && n > 0, "airpose_debug_conv_bwd: bad index / n");
   cudaStream_t st = (cudaStream_t)stream_;
   if (bw_reserve(h, n)) return 1;
+  h->bw_batched = false;                             // per-layer entry point: pack / unpack immediately (a failed whole pass may have left it set)
   const std::vector<ConvIO> io = resnet50_io();
   airpose_trunk_grads g{};
   g.g_weight[conv_idx] = out_gw;
