@@ -239,9 +239,11 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
     for (int l = 0; l < lanes; ++l)
 #pragma unroll
       for (int j = 0; j < 16; ++j) ts[j] += red[l * groups + threadIdx.x][j];
-    float* o = part + ((size_t)blockIdx.x * C + threadIdx.x * 8) * 2;
+    // partials are laid out [channel][slab][2] so that the finalize kernel's warp reads the slabs of a channel as one
+    // contiguous run (it was 32 scattered sectors per load with [slab][channel][2]: ~12 us per finalize launch)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { o[2 * j] = ts[j]; o[2 * j + 1] = ts[8 + j]; }
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float2*>(part + ((size_t)(threadIdx.x * 8 + j) * gridDim.x + blockIdx.x) * 2) = make_float2(ts[j], ts[8 + j]);
   }
 }
 
@@ -249,7 +251,10 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
 __device__ __forceinline__ void slab_sum(const float* __restrict__ part, int slabs, int C, int c, double& s, double& q) {
   const int lane = threadIdx.x & 31;
   s = 0.0; q = 0.0;
-  for (int i = lane; i < slabs; i += 32) { s += part[((size_t)i * C + c) * 2]; q += part[((size_t)i * C + c) * 2 + 1]; }
+  for (int i = lane; i < slabs; i += 32) {
+    const float2 v = *reinterpret_cast<const float2*>(part + ((size_t)c * slabs + i) * 2);
+    s += v.x; q += v.y;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s += __shfl_down_sync(0xffffffffu, s, o); q += __shfl_down_sync(0xffffffffu, q, o); }
   s = __shfl_sync(0xffffffffu, s, 0); q = __shfl_sync(0xffffffffu, q, 0);
@@ -880,9 +885,11 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
     for (int l = 0; l < lanes; ++l)
 #pragma unroll
       for (int j = 0; j < 16; ++j) ts[j] += red[l * groups + threadIdx.x][j];
-    float* o = part + ((size_t)blockIdx.x * C + threadIdx.x * 8) * 2;
+    // partials are laid out [channel][slab][2] so that the finalize kernel's warp reads the slabs of a channel as one
+    // contiguous run (it was 32 scattered sectors per load with [slab][channel][2]: ~12 us per finalize launch)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { o[2 * j] = ts[j]; o[2 * j + 1] = ts[8 + j]; }
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float2*>(part + ((size_t)(threadIdx.x * 8 + j) * gridDim.x + blockIdx.x) * 2) = make_float2(ts[j], ts[8 + j]);
   }
 }
 
