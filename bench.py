@@ -138,6 +138,8 @@ def run_reference(args):
 
 def pin_to_gpu_numa(local):
     """Bind this process (and therefore its pinned staging buffers, first-touch) to the CPUs NVML reports as local to the GPU."""
+    if os.environ.get("AIRPOSE_BENCH_NO_PIN"):
+        return "not bound (AIRPOSE_BENCH_NO_PIN)"
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -321,24 +323,6 @@ def run_ours(args):
     ief_ms = sum(p["ief"][0].elapsed_time(p["ief"][1]) for p in prof) / len(prof)
     smplx_ms = sum(p["smplx"][0].elapsed_time(p["smplx"][1]) for p in prof) / len(prof)
 
-    # ------------------------------------------------------------------ sustained leg: the same step for >= SUSTAIN_S seconds
-    sus_steps = max(args.steps, int(args.sustain_s * 1e3 / ms) + 1) if args.sustain_s > 0 else 0
-    sus_ms = trunk_sus_ms = None
-    if sus_steps:
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        sprof = []
-        sync_all()
-        ev[0].record()
-        for i in range(sus_steps):
-            p = {} if i % 16 == 0 else None
-            mod.fwd_pass(sets[i % NSETS], profile=p)
-            if p is not None:
-                sprof.append(p)
-        ev[1].record()
-        sync_all()
-        sus_ms = ev[0].elapsed_time(ev[1]) / sus_steps
-        trunk_sus_ms = sum(p["trunk"][0].elapsed_time(p["trunk"][1]) for p in sprof) / len(sprof)
-
     # ------------------------------------------------------------------ end to end from pinned host memory
     copy_stream = torch.cuda.Stream(device=dev)
     d2h_stream = torch.cuda.Stream(device=dev)
@@ -417,6 +401,24 @@ def run_ours(args):
     copy_stream.synchronize()
     h2d_gbs = 3 * h2d_f32 / (c0.elapsed_time(c1) * 1e-3) / 1e9
     del tmp_dev, host_sets, host_sets_u8
+    # ------------------------------------------------------------------ sustained leg: the same step for >= SUSTAIN_S seconds
+    sus_steps = max(args.steps, int(args.sustain_s * 1e3 / ms) + 1) if args.sustain_s > 0 else 0
+    sus_ms = trunk_sus_ms = None
+    if sus_steps:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        sprof = []
+        sync_all()
+        ev[0].record()
+        for i in range(sus_steps):
+            p = {} if i % 16 == 0 else None
+            mod.fwd_pass(sets[i % NSETS], profile=p)
+            if p is not None:
+                sprof.append(p)
+        ev[1].record()
+        sync_all()
+        sus_ms = ev[0].elapsed_time(ev[1]) / sus_steps
+        trunk_sus_ms = sum(p["trunk"][0].elapsed_time(p["trunk"][1]) for p in sprof) / len(sprof)
+
     clocks = sampler.stop() if rank == 0 else None
 
     # ------------------------------------------------------------------ SMPL-X lbs() roofline at config 3 (rank 0, N=1)
