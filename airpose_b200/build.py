@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libairpose_b200.so")
-SOURCES = ["capi.cu", "smplx.cu", "smplx_tc.cu", "smplx_ml.cu", "gemm.cu", "gemm_tma.cu", "gemm_sk.cu", "gemm_sk2.cu", "bneck.cu", "stem.cu", "trunk.cu", "ief.cu", "ief_train.cu", "loss.cu", "optim.cu", "preprocess.cu", "testmode.cu"]
+SOURCES = ["capi.cu", "smplx.cu", "smplx_tc.cu", "smplx_ml.cu", "gemm.cu", "gemm_tma.cu", "gemm_sk.cu", "gemm_sk2.cu", "bneck.cu", "conv3x3.cu", "stem.cu", "trunk.cu", "ief.cu", "ief_train.cu", "loss.cu", "optim.cu", "preprocess.cu", "testmode.cu"]
 HEADERS = ["common.cuh", "gemm.cuh", "ptx.cuh", "net.cuh", "smplx.cuh", "smplx_bwd.inl", os.path.join("..", "..", "include", "airpose_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",

@@ -489,6 +489,11 @@ extern "C" int airpose_gemm_bf16(const airpose_gemm_args* g, void* stream) {
 
 extern "C" int airpose_conv_bf16(const airpose_conv_args* c, void* stream) {
   AP_REQUIRE(c && c->x && c->w && c->out, "airpose_conv_bf16: null argument");
+  if (!c->residual && conv3x3_slab_supported(c->H, c->W, c->Cin, c->Cout, c->ksize, c->stride, c->pad)) {      // as trunk.cu dispatches it
+    SlabLaunch S{};
+    if (build_conv3x3_slab(&S, c->x, c->w, c->scale, c->shift, c->relu, c->out, c->n, c->H, c->W)) return 1;
+    return launch_conv3x3_slab(S, (cudaStream_t)stream);
+  }
   GemmLaunch L{};
   ConvGeom& g = L.geom;
   g.n = c->n; g.H = c->H; g.W = c->W; g.Cin = c->Cin;

@@ -82,6 +82,17 @@ int build_bneck_tail(TailLaunch* L, const void* t1, const void* w2, const float*
                      const float* scale3, const float* shift3, const void* residual, void* out, int n, int H, int W);
 int launch_bneck_tail(const TailLaunch& L, cudaStream_t stream);
 
+// 3x3 / stride 1 conv + BN + ReLU of the 128-channel stage with the input band resident in shared memory (conv3x3.cu)
+struct alignas(64) SlabLaunch {
+  unsigned char storage[512];      // three tensor maps + the kernel parameters (SlabLaunchImpl in conv3x3.cu)
+  int valid = 0;
+  int pdl = 0;
+};
+bool conv3x3_slab_supported(int H, int W, int Cin, int Cout, int ksize, int stride, int pad);
+int build_conv3x3_slab(SlabLaunch* L, const void* x, const void* w, const float* scale, const float* shift, int relu, void* out, int n, int H,
+                       int W);
+int launch_conv3x3_slab(const SlabLaunch& L, cudaStream_t stream);
+
 // Fused stem (stem.cu): conv 7x7 s2 + BN + ReLU + MaxPool 3x3 s2 in one launch (plus the operand pack kernel).
 struct alignas(64) StemLaunch {
   unsigned char storage[320];      // two tensor maps + the kernel parameters (StemLaunchImpl in stem.cu)

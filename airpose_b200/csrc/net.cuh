@@ -13,10 +13,11 @@ namespace airpose {
 
 struct ConvSpec { int cout, cin, k, stride, pad; };
 
-struct PlanOp { int kind; int idx; };  // kind 0: gemms[idx] (one conv), 1: tails[idx] (fused conv2 + conv3, bneck.cu)
+struct PlanOp { int kind; int idx; };  // kind 0: gemms[idx] (one conv), 1: tails[idx] (fused conv2 + conv3, bneck.cu), 2: slabs[idx] (conv3x3.cu)
 struct TrunkPlan {
   std::vector<GemmLaunch> gemms;       // [stem,] then per block conv1, conv2, [down], conv3 (conv2/conv3 absent when fused)
   std::vector<TailLaunch> tails;
+  std::vector<SlabLaunch> slabs;       // 3x3 convs of the 128-channel stage (conv3x3.cu)
   StemLaunch stem;                     // stage-A plans: the fused stem (when enabled)
   std::vector<PlanOp> ops;             // launch order (the stem GEMM, gemms[0] of a stage-A plan, is not listed)
   const __nv_bfloat16* final_act = nullptr;

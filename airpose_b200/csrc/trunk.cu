@@ -549,8 +549,15 @@ static int build_blocks(airpose_net* h, int n, int l0, int l1, int H, __nv_bfloa
         if (out == buf[c]) { std::swap(a, c); }
       } else {
         if (out == buf[c]) out = buf[b];               // unfused: conv3 may overwrite T1
-        if (conv_launch(h, idx + 1, buf[b], n, H, H, nullptr, 1, buf[c], &L2)) return 1;
-        push(L2);
+        if (conv3x3_slab_supported(H, H, s2.cin, s2.cout, s2.k, s2.stride, s2.pad)) {
+          SlabLaunch S{};                              // input band resident in shared memory instead of nine im2col passes
+          if (build_conv3x3_slab(&S, buf[b], h->wq[idx + 1], h->scale[idx + 1], h->shift[idx + 1], 1, buf[c], n, H, H)) return 1;
+          plan->ops.push_back({2, (int)plan->slabs.size()});
+          plan->slabs.push_back(S);
+        } else {
+          if (conv_launch(h, idx + 1, buf[b], n, H, H, nullptr, 1, buf[c], &L2)) return 1;
+          push(L2);
+        }
         if (conv_launch(h, idx + 2, buf[c], n, Ho, Ho, res, 1, out, &L3)) return 1;
         push(L3);
         if (out == buf[b]) std::swap(a, b);
@@ -565,7 +572,7 @@ static int build_blocks(airpose_net* h, int n, int l0, int l1, int H, __nv_bfloa
 // stage A: stem GEMM + layer1 + layer2 on `n` <= chunk images; output [n,28,28,512] lands at image
 // offset `first` of the stage-B input buffer.
 static int build_plan_a(airpose_net* h, int n, int first, int set, TrunkPlan* plan) {
-  plan->gemms.clear(); plan->tails.clear(); plan->ops.clear();
+  plan->gemms.clear(); plan->tails.clear(); plan->slabs.clear(); plan->ops.clear();
   GemmLaunch L{};
   if (build_stem_gemm(h, n, set, &L)) return 1;
   plan->gemms.push_back(L);
@@ -576,13 +583,16 @@ static int build_plan_a(airpose_net* h, int n, int first, int set, TrunkPlan* pl
 
 // stage B: layer3 + layer4 on `n` <= group images, input in actB[0].
 static int build_plan_b(airpose_net* h, int n, int set, TrunkPlan* plan) {
-  plan->gemms.clear(); plan->tails.clear(); plan->ops.clear();
+  plan->gemms.clear(); plan->tails.clear(); plan->slabs.clear(); plan->ops.clear();
   return build_blocks(h, n, 2, 4, 28, set ? h->actB1 : h->actB, nullptr, plan);
 }
 
 static int launch_plan_ops(const TrunkPlan& plan, cudaStream_t st) {
-  for (const PlanOp& op : plan.ops)
-    if (op.kind == 0 ? launch_gemm(plan.gemms[op.idx], st) : launch_bneck_tail(plan.tails[op.idx], st)) return 1;
+  for (const PlanOp& op : plan.ops) {
+    const int rc = op.kind == 0 ? launch_gemm(plan.gemms[op.idx], st)
+                 : op.kind == 1 ? launch_bneck_tail(plan.tails[op.idx], st) : launch_conv3x3_slab(plan.slabs[op.idx], st);
+    if (rc) return 1;
+  }
   return 0;
 }
 

@@ -91,3 +91,39 @@ def test_bneck_tail_is_deterministic(n):
         diff = (outs[rep].view(torch.int16) != outs[0].view(torch.int16))
         assert not diff.any(), "run %d differs from run 0 in %d elements (first at %s)" % (
             rep, int(diff.sum()), diff.nonzero()[0].tolist())
+
+
+@pytest.mark.parametrize("n,H,W,relu", [(1, 28, 28, True), (3, 28, 28, True), (2, 27, 28, False), (2, 14, 14, True), (2, 5, 9, True), (75, 28, 28, True)])
+def test_conv3x3_slab_matches_torch(n, H, W, relu):
+    """3x3 / stride 1 conv + BN (+ ReLU) of the 128-channel stage with the input band resident in shared memory (csrc/conv3x3.cu),
+    through airpose_conv_bf16 (which dispatches exactly like the trunk): the layer2 geometry, a height that is not a multiple of
+    the band (clipped last band), small images (one band per image, short rows) and more bands than SMs (barrier phases wrap)."""
+    lib = _lib.load()
+    Cc = 128
+    g = torch.Generator(device="cpu").manual_seed(77 * n + H + W)
+    x = _bf16(torch.relu(torch.randn(n, H, W, Cc, generator=g))).to(DEV)
+    w = _bf16(torch.randn(Cc, Cc, 3, 3, generator=g) * (2.0 / (9 * Cc)) ** 0.5).to(DEV)
+    sc, sh = (torch.rand(Cc, generator=g) + 0.5).to(DEV), (torch.randn(Cc, generator=g) * 0.3).to(DEV)
+    wk = w.permute(0, 2, 3, 1).contiguous().view(Cc, 9 * Cc)
+    out = torch.full((n, H, W, Cc), float("nan"), device=DEV, dtype=torch.bfloat16)
+    a = _lib.ConvArgs()
+    a.x, a.n, a.H, a.W, a.Cin = x.data_ptr(), n, H, W, Cc
+    a.w, a.Cout, a.ksize, a.stride, a.pad = wk.data_ptr(), Cc, 3, 1, 1
+    a.scale, a.shift, a.relu, a.out = sc.data_ptr(), sh.data_ptr(), int(relu), out.data_ptr()
+    n0 = _lib.launch_count()
+    _lib.check(lib.airpose_conv_bf16(C.byref(a), _lib.current_stream()), "conv")
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - n0 == 1
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    ref = (torch.relu(ref) if relu else ref).permute(0, 2, 3, 1)
+    got = out.float()
+    assert torch.isfinite(got).all(), "pixels were not written: %d" % int((~torch.isfinite(got)).sum())
+    err = (got - ref).abs()
+    bad = err > ref.abs() * 2.0 ** -8 + 2e-3
+    print("conv3x3 slab n=%d %dx%d: max abs err %.3e, bad %d / %d" % (n, H, W, err.max().item(), int(bad.sum()), bad.numel()))
+    assert not bad.any()
+    out2 = torch.empty_like(out)
+    a.out = out2.data_ptr()
+    _lib.check(lib.airpose_conv_bf16(C.byref(a), _lib.current_stream()), "conv")
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)                       # deterministic
