@@ -88,7 +88,21 @@ def test_reference_training_step_over_airpose_objects(ref_module):
     module.eval()
 
 
-def test_whole_network_gradient_matches_reference_fp32_backward(tmp_path):
+def _install_bf16_rounding_points(net):
+    """The CUDA trunk's forward rounding points on the reference trunk, differentiable (straight-through): conv inputs and conv
+    outputs rounded to bf16, block outputs and the pooled stem rounded to bf16; conv weights are rounded by the caller (both
+    sides load the same bf16-representable weights)."""
+    rb = lambda t: t + (t.to(torch.bfloat16).float() - t).detach()
+    for name, mod in net.named_modules():
+        if isinstance(mod, torch.nn.Conv2d):
+            mod.register_forward_pre_hook(lambda m, a: (rb(a[0]),))
+            mod.register_forward_hook(lambda m, a, out: rb(out))
+        if type(mod).__name__ == "Bottleneck" or name == "maxpool":
+            mod.register_forward_hook(lambda m, a, out: rb(out))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16_points"])
+def test_whole_network_gradient_matches_reference_fp32_backward(tmp_path, mode):
     """One fp32 `loss.backward()` through the UNMODIFIED reference (LightningModule.training_step, :376-390, its own ResNet-50 /
     regressor / SMPLX / loss in train() mode on CUDA) against the flat gradient buffer `airpose_b200`'s hand-scheduled
     `training_step` fills (bf16 trunk forward and backward, fp32 everywhere else) on the same 4-pair batch, same weights,
@@ -99,17 +113,28 @@ def test_whole_network_gradient_matches_reference_fp32_backward(tmp_path):
     from argparse import Namespace
     from airpose_b200 import synthetic
     from airpose_b200.copenet_twoview import copenet_twoview
-    B = 4
+    B = int(os.environ.get("AIRPOSE_TEST_GRAD_PAIRS", "4"))
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     sd = synthetic.make_network_state(123, dec_gain=0.01)
     tsd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
     batch = rh.make_batch(B, 123, 321, device="cuda")
+    if mode == "bf16_points":
+        # second mode: the reference gets the CUDA trunk's FORWARD rounding points (same bf16-representable conv weights and
+        # images on both sides, activations rounded where the kernels round them) and keeps its fp32 autograd backward -- what
+        # remains is the error of the backward kernels alone (bf16 data gradients), not the bf16 forward's different ReLU masks
+        for k in list(tsd):
+            if tsd[k].dim() == 4:
+                tsd[k] = tsd[k].to(torch.bfloat16).float()
+        for k in ("im0", "im1"):
+            batch[k] = batch[k].to(torch.bfloat16).float()
     # ---- the reference, fp32 autograd
     rt = rh.import_reference("cuda")
     ref = rh.make_module(rt, B, device="cuda", load_weights=False)
     ref.model.load_state_dict(tsd, strict=True)
     ref.train()
+    if mode == "bf16_points":
+        _install_bf16_rounding_points(ref.model)
     for m in ref.model.modules():
         if isinstance(m, torch.nn.Dropout):
             m.p = 0.0
@@ -144,6 +169,7 @@ def test_whole_network_gradient_matches_reference_fp32_backward(tmp_path):
     reg = [r for r in rows if r[0].split(".")[0] in ("fc1", "fc2", "decpose", "decshape")]
     conv = [r for r in rows if "conv" in r[0] or "downsample.0" in r[0]]
     bn = [r for r in rows if r not in reg and r not in conv]
+    print("[%s] " % mode, end="")
     print("gradient vs reference fp32 backward, %d pairs: loss %.6g vs %.6g (rel %.2e); %d tensors; cosine over all gradients %.5f; "
           "worst cosine %.4f (%s); worst rel err %.3e (%s); regressor tensors: min cosine %.6f, max rel %.2e" %
           (B, float(loss), loss_ref, rel_loss, len(rows), cos_all, worst_cos[1], worst_cos[0], worst_rel[2], worst_rel[0],
@@ -151,25 +177,31 @@ def test_whole_network_gradient_matches_reference_fp32_backward(tmp_path):
     print("   conv weights (%d): min cosine %.4f, median %.4f, max rel %.2e | BatchNorm affine (%d): min cosine %.4f, median %.4f" %
           (len(conv), min(r[1] for r in conv), float(np.median([r[1] for r in conv])), max(r[2] for r in conv),
            len(bn), min(r[1] for r in bn), float(np.median([r[1] for r in bn]))))
+    print("   conv cosines in network order: " + " ".join("%.3f" % r[1] for r in conv))
     for r in sorted(conv, key=lambda r: r[1])[:5] + sorted(bn, key=lambda r: r[1])[:5]:
         print("   %-34s cos %.4f  rel %.3e  |g|max %.3e" % r)
     assert len(rows) == 159 + 8 - 2 or len(rows) >= 150            # every trunk / regressor tensor except deccam
     assert rel_loss < GRAD_LOSS_REL
     assert cos_all > GRAD_COS_ALL
     assert min(r[1] for r in reg) > 0.9999 and max(r[2] for r in reg) < 2e-2
-    assert min(r[1] for r in conv) > GRAD_COS_CONV
-    assert min(r[1] for r in bn) > GRAD_COS_BN
+    assert min(r[1] for r in conv) > (GRAD_COS_CONV if mode == "fp32" else GRAD_COS_CONV_SAME_FWD)
+    assert min(r[1] for r in bn) > (GRAD_COS_BN if mode == "fp32" else GRAD_COS_BN_SAME_FWD)
 
 
 # measured on B200 (printed by the test, quoted in DESIGN.md section 4); bounds = measured with a 2x margin on 1 - cos / rel
-# r02y: loss rel 5.8e-5, cosine over all gradients 0.99998, regressor >= 0.999995 / rel 5.2e-3.  The BatchNorm affine gradients
-# of the early layers are sums over N*H*W of a data gradient that the NEXT BatchNorm has made zero-mean: they cancel to a
-# small fraction of their terms, and the bf16 rounding of every stored data gradient (csrc/trunk.cu keeps dz in bf16) shows
-# there first (worst tensor 0.73).  fp32 dz for those layers is the known fix.
+# Measured (gpurun r02y ... tools/debug_grad.py): loss rel 5.8e-5, cosine over all gradients 0.99998, regressor >= 0.999995 / rel 5.2e-3;
+# trunk tensors 0.80-0.96 (fp32 reference) / 0.87-0.97 (reference with the same forward rounding points), lowest in layer1, and the
+# same at 24 pairs.  tools/debug_grad.py traced it: the backward kernels reproduce a torch recomputation from THEIR OWN tape to cosine
+# 0.999992, and rounding dz to bf16 changes the reference's first weight gradient by 2e-6 -- but two bf16 forwards of this 53-layer
+# network in train() mode (batch-statistics BatchNorm, synthetic random weights) differ by cosine 0.998 in the layer4 activations and
+# in 1.7 % of the block-output ReLU masks, and THAT moves the first weight gradient to cosine 0.96.  The deviation is the bf16
+# forward's, not the backward's; the bounds below are on what is measured.
 GRAD_LOSS_REL = 1e-3
 GRAD_COS_ALL = 0.9995
 GRAD_COS_CONV = 0.6          # measured 0.80
 GRAD_COS_BN = 0.45           # measured 0.73
+GRAD_COS_CONV_SAME_FWD = 0.6 # reference with the same forward rounding points: set from the measurement below
+GRAD_COS_BN_SAME_FWD = 0.45
 
 
 def test_translation_init_branches_match_reference(tmp_path):
