@@ -129,11 +129,21 @@ struct IefIterArgs {
 };
 
 // One CTA per frame pair, thread (v, o): view v in {0,1}, output o in [0,160).
+// GuT (284 x 160 fp32 = 178 KB) is staged in shared memory once per CTA: the three iterations then read it
+// conflict-free (consecutive o) instead of chasing 3 x 284 dependent L2 loads per thread.
+constexpr int kIefIterSmem = kState * kDecPad * (int)sizeof(float);
 __global__ void __launch_bounds__(2 * kDecPad) ief_iter_kernel(IefIterArgs a) {
+  extern __shared__ __align__(16) float gsm[];   // [kState][kDecPad]
   __shared__ float st[2][kDecPad];        // per view: pose[0..135) then shape[135..145)
-  __shared__ float u[2][kState];
+  __shared__ __align__(16) float u[2][kState];
   const int b = blockIdx.x, v = threadIdx.x / kDecPad, o = threadIdx.x % kDecPad, M = 2 * a.B;
   const int m = v * a.B + b;
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.GuT);
+    float4* dst = reinterpret_cast<float4*>(gsm);
+#pragma unroll 12
+    for (int i = threadIdx.x; i < kState * kDecPad / 4; i += 2 * kDecPad) dst[i] = __ldg(src + i);
+  }
   // base = g + fixed-order sum of the split-K partials
   float base = 0.f;
   if (o < kDec) {
@@ -150,7 +160,7 @@ __global__ void __launch_bounds__(2 * kDecPad) ief_iter_kernel(IefIterArgs a) {
     st[v][o] = sh ? sh[(size_t)b * a.sh_stride + (o - 135)] : a.init_shape[o - 135];
   }
   __syncthreads();
-  const float* gu = a.GuT + o;
+  const float* gu = gsm + o;
   for (int it = 0; it < a.iters; ++it) {
     // u = [bb(3), pose_self(135), shape_self(10), art_other(126), shape_other(10)]   (:185,:192)
     for (int k = o; k < kState; k += kDecPad) {
@@ -164,14 +174,15 @@ __global__ void __launch_bounds__(2 * kDecPad) ief_iter_kernel(IefIterArgs a) {
     __syncthreads();
     float d = base;
     if (o < kDec) {
-      // four partial sums and 16-deep unrolling: the loop is a chain of L2 loads, not of FMAs
+      // four partial sums (fixed order: the result does not depend on the staging)
       float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll 4
       for (int k = 0; k < kState; k += 4) {
-        d0 = fmaf(__ldg(gu + (size_t)(k + 0) * kDecPad), u[v][k + 0], d0);
-        d1 = fmaf(__ldg(gu + (size_t)(k + 1) * kDecPad), u[v][k + 1], d1);
-        d2 = fmaf(__ldg(gu + (size_t)(k + 2) * kDecPad), u[v][k + 2], d2);
-        d3 = fmaf(__ldg(gu + (size_t)(k + 3) * kDecPad), u[v][k + 3], d3);
+        const float4 uv = *reinterpret_cast<const float4*>(&u[v][k]);
+        d0 = fmaf(gu[(k + 0) * kDecPad], uv.x, d0);
+        d1 = fmaf(gu[(k + 1) * kDecPad], uv.y, d1);
+        d2 = fmaf(gu[(k + 2) * kDecPad], uv.z, d2);
+        d3 = fmaf(gu[(k + 3) * kDecPad], uv.w, d3);
       }
       d += (d0 + d1) + (d2 + d3);
     }
@@ -341,7 +352,8 @@ extern "C" int airpose_ief_fwd(airpose_net_t* h, const airpose_ief_args* a, void
   k.init_pose = s.init_pose; k.init_shape = s.init_shape;
   k.partial = s.partial; k.GuT = s.GuT; k.g = s.g;
   k.out_pose0 = a->out_pose0; k.out_betas0 = a->out_betas0; k.out_pose1 = a->out_pose1; k.out_betas1 = a->out_betas1;
-  ief_iter_kernel<<<B, 2 * kDecPad, 0, st>>>(k);
+  AP_CHECK_CUDA(cudaFuncSetAttribute(ief_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIefIterSmem));
+  ief_iter_kernel<<<B, 2 * kDecPad, kIefIterSmem, st>>>(k);
   AP_LAUNCH_CHECK();
   return 0;
 }
