@@ -131,7 +131,8 @@ class GemmArgs(C.Structure):
                 ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
                 ("scale", C.c_void_p), ("shift", C.c_void_p),
                 ("residual", C.c_void_p), ("ldr", C.c_int64), ("relu", C.c_int32),
-                ("out_bf16", C.c_void_p), ("ldd", C.c_int64), ("out_f32", C.c_void_p), ("ldf", C.c_int64)]
+                ("out_bf16", C.c_void_p), ("ldd", C.c_int64), ("out_f32", C.c_void_p), ("ldf", C.c_int64),
+                ("a_t", C.c_int32), ("b_t", C.c_int32)]
 
 
 class ConvArgs(C.Structure):

@@ -469,6 +469,19 @@ extern "C" int airpose_gemm_bf16(const airpose_gemm_args* g, void* stream) {
   AP_REQUIRE(g && g->A && g->B, "airpose_gemm_bf16: null argument");
   GemmLaunch L{};
   L.M = g->M; L.N = g->N; L.K = g->K;
+  if (g->a_t || g->b_t) {                 // transposed operand(s): MN-major descriptors in the stream-K kernel
+    AP_REQUIRE(g->out_bf16 && !g->out_f32 && !g->residual && g->N % 64 == 0, "airpose_gemm_bf16: a_t / b_t need a bf16 output with N %% 64 == 0 and no residual");
+    AP_REQUIRE(!g->a_t || g->M % 8 == 0, "airpose_gemm_bf16: a_t needs M %% 8 == 0 (M=%d)", g->M);
+    L.block_n = g->N % 256 == 0 ? 256 : (g->N > 64 ? 128 : 64);
+    L.mn_a = g->a_t ? 1 : 0; L.mn_b = g->b_t ? 1 : 0;
+    if (L.mn_a ? make_tmap_tiled_bf16(&L.tmA, g->A, g->K, g->M, g->lda, 64, 64) : make_tmap_tiled_bf16(&L.tmA, g->A, g->M, g->K, g->lda, kBlockM, kBlockK)) return 1;
+    if (L.mn_b ? make_tmap_tiled_bf16(&L.tmB, g->B, g->K, g->N, g->ldb, 64, 64) : make_tmap_tiled_bf16(&L.tmB, g->B, g->N, g->K, g->ldb, L.block_n, kBlockK)) return 1;
+    L.epi.scale = g->scale; L.epi.shift = g->shift; L.epi.relu = g->relu;
+    L.epi.out_bf16 = g->out_bf16; L.epi.ldd = g->ldd;
+    AP_REQUIRE(tma_epilogue_eligible(L), "airpose_gemm_bf16: a_t / b_t need the TMA epilogue (aligned bf16 output)");
+    if (enable_tma_epilogue(&L)) return 1;
+    return launch_gemm_sk(L, (cudaStream_t)stream);
+  }
   L.block_n = pick_block_n(g->M, g->N, g->K);
   if (make_tmap_tiled_bf16(&L.tmA, g->A, g->M, g->K, g->lda, kBlockM, kBlockK)) return 1;
   const bool tma_ok = use_tma_epilogue() && g->out_bf16 && !g->out_f32 && g->N % 64 == 0;

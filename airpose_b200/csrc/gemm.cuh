@@ -42,6 +42,10 @@ struct GemmLaunch {
   int tma_epi = 0;     // 1: bf16 output through smem staging + TMA store (gemm_tma.cu); 0: direct stores (gemm.cu)
   int pdl = 0;         // launch with programmatic stream serialization (prologue overlaps the previous kernel's tail)
   int pair_b_box = 0;  // 1: planned for the cta_group::2 pair kernel (gemm_sk2.cu): block_n = 256, tmB boxes of 128 rows
+  // gemm_sk.cu only: the operand is given TRANSPOSED -- A as [K][M], B as [K][N], row-major (M / N contiguous) -- and read through
+  // MN-major UMMA descriptors; its tensor map has boxes of 64 columns x 64 rows (make_tmap_tiled_bf16(rows = K, cols = M or N)).
+  // The weight-gradient GEMMs contract over the pixels, which is the OUTER dimension of every NHWC tensor.
+  int mn_a = 0, mn_b = 0;      // mn_b == 2: B = im2col(x)^T, tmB an im2col map with boxes of 64 channels x 64 pixels, geom the conv
   ConvGeom geom;
   Epilogue epi;
 };
@@ -53,7 +57,15 @@ int enable_tma_epilogue(GemmLaunch* L);
 int launch_gemm_tma(const GemmLaunch& L, cudaStream_t stream);
 // Second-generation kernel (gemm_sk.cu): stream-K split, two epilogue warpgroups, resident weights.
 // Chosen per problem by prefers_stream_k(); AIRPOSE_GEMM_V1=1 / AIRPOSE_GEMM_SK=1 force one kernel for A/B runs.
-int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream);
+// With `sk` (ranges >= 2 on entry): plain split-K -- every tile is cut into `ranges` k-ranges, one CTA each, and EVERY range leaves
+// its fp32 partial tile in the stream's workspace instead of anything being stored through tmD; the caller sums the partials in a
+// fixed order with its own kernel, launched next on the same stream.  For GEMMs with a handful of tiles and a very long K (the
+// weight gradients of the early layers: 1-6 tiles, thousands of k-blocks), where stream-K's one-owner gather caps a tile at 16 ranges.
+// Partial of tile t (= m_blk * tiles_n + n_blk), range r: part + (t * ranges + r) * slot_floats; element (row, col) of the 128 x
+// block_n tile at float ((col / 64 * 16 + (col % 64) / 4) * 128 + row) * 4 + col % 4.
+struct SplitKInfo { int ranges; const float* part; int tiles_n, block_n, slot_floats; };
+int splitk_ranges(int M, int N, int K, int block_n);      // 0: stream-K fills the GPU by itself
+int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream, SplitKInfo* sk = nullptr);
 bool use_stream_k();
 // cta_group::2 pair kernel (gemm_sk2.cu): 256 x 256 tiles on CTA pairs.  prefers_pair() decides per problem.
 int launch_gemm_sk2(const GemmLaunch& L, cudaStream_t stream);

@@ -66,6 +66,8 @@ struct KP {
   int has_res, relu;
   int stages, res_bufs, b_res;      // shared-memory partition of this launch
   int split;                        // 1: stream-K (ranges of k-blocks)  0: whole tiles, round-robin over the CTAs
+  int mn_a, mn_b;                   // operand given as [K][M] / [K][N]: 64 x 64 boxes, MN-major descriptors
+  int splitk_r;                     // > 0: plain split-K, every tile cut into splitk_r ranges, EVERY range leaves its fp32 partial in ws (slot = CTA)
   const float* scale;
   const float* shift;
   float* ws;                        // [grid][128 x BN] fp32 partial accumulators
@@ -101,9 +103,16 @@ __device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
 struct Seg { int tile, kb0, kb1; };
 struct SegIter {
   int u, u1, num_kb, step;          // step == 0: stream-K range [u, u1) of k-block units; else tiles u, u+step, ... < u1
-  __device__ SegIter(int cta, int grid, int units, int nkb, int split)
+  __device__ SegIter(int cta, int grid, int units, int nkb, int split, int splitk_r = 0)
       : u(split ? (int)((int64_t)cta * units / grid) : cta), u1(split ? (int)((int64_t)(cta + 1) * units / grid) : units / nkb),
-        num_kb(nkb), step(split ? 0 : grid) {}
+        num_kb(nkb), step(split ? 0 : grid) {
+    if (splitk_r) {                   // CTA = (tile, r): k-blocks [r nkb / R, (r+1) nkb / R) of its tile
+      const int tile = cta / splitk_r, r = cta - tile * splitk_r;
+      u = tile * nkb + (int)((int64_t)r * nkb / splitk_r);
+      u1 = tile * nkb + (int)((int64_t)(r + 1) * nkb / splitk_r);
+      step = 0;
+    }
+  }
   __device__ bool next(Seg& s) {
     if (u >= u1) return false;
     if (step) {
@@ -190,7 +199,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < p.num_kb; ++kb) ptx::tma_load_2d(&tmB, bfull_bar, smem + bres_off + kb * kBBytes, kb * BK, 0);
       }
       int stage = 0; uint32_t phase = 0;
-      SegIter it(cta, grid, units, p.num_kb, p.split);
+      SegIter it(cta, grid, units, p.num_kb, p.split, p.splitk_r);
       Seg s;
       while (it.next(s)) {
         const int m_blk = s.tile / p.tiles_n, n_blk = s.tile - m_blk * p.tiles_n;
@@ -214,14 +223,22 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int img = m0 / p.stem_img_rows;
           stem_row = img * p.stem_img_stride + (m0 - img * p.stem_img_rows);
         }
-        const int tx_bytes = vmt * kASub + (p.b_res ? 0 : kBBytes);
+        // MN-major operands arrive as boxes of 64 MN columns x BK rows; boxes past the extent are not loaded (their rows / columns
+        // of the accumulator are never stored)
+        constexpr int kBoxBytes = 64 * BK * 2;
+        const int a_boxes = p.mn_a ? min(MT * 2, (p.M - m0 + 63) / 64) : 0;
+        const int b_boxes = p.mn_b ? min(BN / 64, (p.N - n0 + 63) / 64) : 0;
+        const int tx_bytes = (p.mn_a ? a_boxes * kBoxBytes : vmt * kASub) + (p.b_res ? 0 : (p.mn_b ? b_boxes * kBoxBytes : kBBytes));
         for (int kb = s.kb0; kb < s.kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
           uint8_t* sa = smem + stage * stage_bytes;
           ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          if (p.mn_a) {
+            for (int j = 0; j < a_boxes; ++j) ptx::tma_load_2d(&tmA, &full_bar[stage], sa + j * kBoxBytes, m0 + j * 64, kb * BK);
+          }
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
-            if (mt >= vmt) break;
+            if (mt >= vmt || p.mn_a) break;
             uint8_t* sam = sa + mt * kASub;
             if (BK == 32) {
               ptx::tma_load_2d(&tmA, &full_bar[stage], sam, 0, stem_row + p.stem_tap_off[kb]);
@@ -233,7 +250,23 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               ptx::tma_load_2d(&tmA, &full_bar[stage], sam, kb * BK, m0 + mt * kBlockM);
             }
           }
-          if (!p.b_res) ptx::tma_load_2d(&tmB, &full_bar[stage], sa + kABytes, kb * BK, n0);
+          if (p.mn_b == 2) {
+            // B = im2col(x)^T: k-block kb is 64 output pixels, column block j of the tile is (tap, 64 input channels) -- the box the
+            // forward conv loads as its A operand, 64 pixels tall
+            const int mm = kb * BK;
+            const int img = mm / p.HoWo, rem = mm - img * p.HoWo;
+            const int po = rem / p.Wo, qo = rem - po * p.Wo;
+            for (int j = 0; j < b_boxes; ++j) {
+              const int nb = (n0 >> 6) + j, tap = nb / p.cblks, cb = nb - tap * p.cblks;
+              const int r = tap / p.ksize, sx = tap - r * p.ksize;
+              ptx::tma_load_im2col_4d(&tmB, &full_bar[stage], sa + kABytes + j * kBoxBytes, cb * 64, qo * p.stride - p.pad,
+                                      po * p.stride - p.pad, img, (uint16_t)sx, (uint16_t)r);
+            }
+          } else if (p.mn_b) {
+            for (int j = 0; j < b_boxes; ++j) ptx::tma_load_2d(&tmB, &full_bar[stage], sa + kABytes + j * kBoxBytes, n0 + j * 64, kb * BK);
+          } else if (!p.b_res) {
+            ptx::tma_load_2d(&tmB, &full_bar[stage], sa + kABytes, kb * BK, n0);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -241,11 +274,13 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BN);
+      const uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BN) | (p.mn_a ? ptx::kIdescAMn : 0u) | (p.mn_b ? ptx::kIdescBMn : 0u);
+      constexpr int kBoxBytes = 64 * BK * 2;
+      const uint32_t a_kstep = p.mn_a ? (uint32_t)(kUmmaK * 128) >> 4 : 2u, b_kstep = p.mn_b ? (uint32_t)(kUmmaK * 128) >> 4 : 2u;
       if (p.b_res) ptx::mbar_wait(bfull_bar, 0, 250);
       int stage = 0; uint32_t phase = 0;
       int n = 0;
-      SegIter it(cta, grid, units, p.num_kb, p.split);
+      SegIter it(cta, grid, units, p.num_kb, p.split, p.splitk_r);
       Seg s;
       while (it.next(s)) {
         const int as = n % kAccBufs; const uint32_t aphase = (n / kAccBufs) & 1;
@@ -260,14 +295,14 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tc_fence_after();
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = p.b_res ? smem_base + bres_off + kb * kBBytes : sa + kABytes;
-          const uint64_t bdesc = ptx::make_kmajor_desc(sb, BK * 2);
+          const uint64_t bdesc = p.mn_b ? ptx::make_mnmajor_desc(sb, kBoxBytes) : ptx::make_kmajor_desc(sb, BK * 2);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             if (mt >= vmt) break;
-            const uint64_t adesc = ptx::make_kmajor_desc(sa + mt * kASub, BK * 2);
+            const uint64_t adesc = p.mn_a ? ptx::make_mnmajor_desc(sa + mt * kASub, kBoxBytes) : ptx::make_kmajor_desc(sa + mt * kASub, BK * 2);
 #pragma unroll
             for (int k = 0; k < BK / kUmmaK; ++k)
-              ptx::umma_bf16(d_tmem + mt * BN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != s.kb0 || k != 0) ? 1u : 0u);
+              ptx::umma_bf16(d_tmem + mt * BN, adesc + a_kstep * k, bdesc + b_kstep * k, idesc, (kb != s.kb0 || k != 0) ? 1u : 0u);
           }
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -279,10 +314,10 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ residual TMA producer
     if (lane == 0 && p.has_res) {
       int rq = 0;
-      SegIter it(cta, grid, units, p.num_kb, p.split);
+      SegIter it(cta, grid, units, p.num_kb, p.split, p.splitk_r);
       Seg s;
       while (it.next(s)) {
-        if (s.kb0 != 0) continue;                      // a partial handed to the tile's owner: no epilogue here
+        if (s.kb0 != 0 || p.splitk_r) continue;        // a partial handed to the tile's owner: no epilogue here
         const int m_blk = s.tile / p.tiles_n, n_blk = s.tile - m_blk * p.tiles_n;
         const int m0 = m_blk * kTileM, n0 = n_blk * BN;
         const int vmt = min(MT, (p.M - m0 + kBlockM - 1) / kBlockM);
@@ -309,7 +344,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int kSlotF4 = kTileM * BN / 4;         // float4s per CTA slot of the workspace
     float4* ws_mine = reinterpret_cast<float4*>(p.ws) + (size_t)cta * kSlotF4;
     int n = 0, q = 0, rq = 0;
-    SegIter it(cta, grid, units, p.num_kb, p.split);
+    SegIter it(cta, grid, units, p.num_kb, p.split, p.splitk_r);
     Seg s;
     while (it.next(s)) {
       const int as = n % kAccBufs; const uint32_t aphase = (n / kAccBufs) & 1;
@@ -319,7 +354,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int vmt = min(MT, (p.M - m0 + kBlockM - 1) / kBlockM);
       const int ncn = min(kChunks, (p.N - n0) / kChunkN);
       const int nchunks = vmt * ncn;
-      const bool contributor = s.kb0 != 0;
+      const bool contributor = p.splitk_r ? true : s.kb0 != 0;
       const bool gather = !contributor && s.kb1 < p.num_kb;     // owner of a tile other CTAs finish
       ptx::mbar_wait(&tfull_bar[as], aphase, 400 + as);
       ptx::tc_fence_after();
@@ -501,7 +536,7 @@ int launch_bn(const GemmLaunch& L, KP& kp, cudaStream_t stream) {
   kp.res_bufs = kp.has_res ? (kp.num_kb <= 2 ? 4 : 2) : 0;
   int avail = kSmemLimit - fixed - kp.res_bufs * kChunkBytes;
   const int b_total = kp.num_kb * kBBytes;
-  kp.b_res = (kp.tiles_n == 1 && kp.tiles_m > num_sms() && b_total <= 80 * 1024 && avail - b_total >= 3 * kABytes &&
+  kp.b_res = (!kp.mn_b && kp.tiles_n == 1 && kp.tiles_m > num_sms() && b_total <= 80 * 1024 && avail - b_total >= 3 * kABytes &&
               !getenv("AIRPOSE_NO_BRES")) ? 1 : 0;
   if (kp.b_res) avail -= b_total;
   const int stage_bytes = kp.b_res ? kABytes : kABytes + kBBytes;
@@ -529,10 +564,12 @@ int launch_bn(const GemmLaunch& L, KP& kp, cudaStream_t stream) {
   const int sms = std::min(num_sms(), kMaxGrid);
   static const int min_kb = getenv("AIRPOSE_SK_SPLIT_MINKB") ? atoi(getenv("AIRPOSE_SK_SPLIT_MINKB")) : 8;
   kp.split = (kp.num_kb >= min_kb && tiles < 8 * sms && tiles % sms != 0) ? 1 : 0;
+  if (kp.splitk_r) kp.split = 1;
   // a tile is never cut into more than 16 ranges: its owner gathers the partials one after the other, which at 70+
   // partials per tile (weight-gradient GEMMs: 2 tiles, 1500 k-blocks) cost more than the mainloop they parallelised
-  cfg.gridDim = dim3((unsigned)(kp.split ? std::min(sms, std::max(std::min(tiles, sms), std::min(units / 8, tiles * 16)))
-                                         : std::min(tiles, sms)));
+  cfg.gridDim = dim3((unsigned)(kp.splitk_r ? tiles * kp.splitk_r
+                                : kp.split ? std::min(sms, std::max(std::min(tiles, sms), std::min(units / 8, tiles * 16)))
+                                           : std::min(tiles, sms)));
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
@@ -548,7 +585,15 @@ int launch_bn(const GemmLaunch& L, KP& kp, cudaStream_t stream) {
 
 }  // namespace
 
-int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream) {
+int splitk_ranges(int M, int N, int K, int block_n) {
+  const int tiles = ceil_div(M, kBlockM) * ceil_div(N, block_n), num_kb = ceil_div(K, 64);
+  const int sms = std::min(num_sms(), kMaxGrid);
+  if (tiles * 16 >= sms || getenv("AIRPOSE_NO_SPLITK")) return 0;        // stream-K's 16 ranges per tile already fill the GPU
+  const int r = std::min(sms / tiles, num_kb / 4);
+  return r >= 2 ? r : 0;
+}
+
+int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream, SplitKInfo* sk) {
   AP_REQUIRE(L.M > 0 && L.N > 0 && L.K > 0, "launch_gemm_sk: empty problem %dx%dx%d", L.M, L.N, L.K);
   AP_REQUIRE(L.tma_epi, "launch_gemm_sk: tensor maps of the epilogue were not built");
   KP kp{};
@@ -556,7 +601,24 @@ int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream) {
   const int kBlockK = L.stem ? 32 : 64;
   kp.num_kb = ceil_div(L.K, kBlockK);
   kp.tiles_n = ceil_div(L.N, L.block_n);
+  if (sk) {
+    AP_REQUIRE(!L.stem && !L.epi.residual && !getenv("AIRPOSE_SK_MT2"), "launch_gemm_sk: split-K partials are for plain GEMMs");
+    kp.splitk_r = sk->ranges;
+    AP_REQUIRE(kp.splitk_r >= 2 && kp.splitk_r <= kp.num_kb && ceil_div(L.M, kBlockM) * kp.tiles_n * kp.splitk_r <= kMaxGrid,
+               "launch_gemm_sk: bad split-K range count %d", kp.splitk_r);
+    SkWorkspace* w = nullptr;
+    if (get_workspace(stream, &w)) return 1;
+    sk->part = w->ws; sk->tiles_n = kp.tiles_n; sk->block_n = L.block_n; sk->slot_floats = kBlockM * L.block_n;
+  }
   kp.im2col = L.im2col;
+  kp.mn_a = L.mn_a; kp.mn_b = L.mn_b;
+  AP_REQUIRE(!(L.mn_a || L.mn_b) || (!L.stem && !L.im2col), "launch_gemm_sk: MN-major operands are for plain GEMMs");
+  if (L.mn_b == 2) {                      // B = im2col(x)^T through an im2col tensor map with 64-pixel boxes (weight gradients)
+    const ConvGeom& g = L.geom;
+    AP_REQUIRE(g.Cin % 64 == 0 && L.N == g.ksize * g.ksize * g.Cin && L.K == g.n * g.Ho * g.Wo, "launch_gemm_sk: im2col B does not match the geometry");
+    kp.cblks = g.Cin / 64; kp.ksize = g.ksize; kp.stride = g.stride; kp.pad = g.pad;
+    kp.Wo = g.Wo; kp.HoWo = g.Ho * g.Wo;
+  }
   kp.has_res = L.epi.residual != nullptr;
   kp.relu = L.epi.relu;
   kp.scale = L.epi.scale; kp.shift = L.epi.shift;

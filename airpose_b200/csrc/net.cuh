@@ -94,6 +94,7 @@ struct airpose_net {
   __nv_bfloat16* bw_wg = nullptr;       // wgrad GEMM outputs of ALL convs, unpacked by one launch at the end of the pass
   size_t bw_w_off[64] = {0};            // element offset of conv i inside bw_wd / bw_wg
   bool bw_batched = false;              // inside a whole backward pass: use the per-layer slots above
+  bool bw_reduced[64] = {false};        // conv i's weight gradient was written by wgrad_reduce_kernel in this pass (no unpack)
   float* bw_coef = nullptr;             // [3][2048] BatchNorm backward coefficients
   int bw_cap = 0;
   std::map<std::pair<int, int>, airpose::TrunkPlan> plansA;        // (images, 2 * first image inside the group + buffer set)

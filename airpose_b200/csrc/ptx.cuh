@@ -179,6 +179,20 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, int swi
   return d;
 }
 
+// MN-major operand, SWIZZLE_128B: the tile is stored as [K rows][64 MN elements = 128 bytes] boxes (what a TMA box of 64 columns x
+// 64 rows of a row-major [K][MN] matrix lands as).  8 consecutive K rows are one 1024-byte swizzle atom (stride byte offset: the next
+// 8 K rows); the next 64 MN elements are the next box (leading byte offset).  A K step of 16 advances the start address by 2048 bytes.
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, int box_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((uint32_t)box_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t kIdescAMn = 1u << 15, kIdescBMn = 1u << 16;      // instruction-descriptor bits: A / B operand is MN-major
+
 // Instruction descriptor, kind::f16: bf16 A/B (K-major), fp32 accumulator, M x N tile.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

@@ -18,6 +18,7 @@
 //                           perspective projection.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -440,6 +441,9 @@ struct airpose_smplx {
   int* xoff = nullptr;         // [V+1] CSR: which extra joints / landmarks gather each vertex ...
   int* xj = nullptr;           // ... their row in the joints output ...
   float* xw = nullptr;         // ... and the weight (1 for the vertex-picked joints, barycentric for landmarks)
+  int* seg_off = nullptr;      // per 128-vertex tile: skinning weights regrouped by joint (smplx_vertex_bwd_kernel) ...
+  int* seg = nullptr;          // ... {joint, first entry, end entry, 0} ...
+  int* ent = nullptr;          // ... {vertex in tile, weight bits}
   float* bws = nullptr;        // backward workspace
   size_t bws_floats = 0;
 };
@@ -558,6 +562,30 @@ extern "C" int airpose_smplx_create(airpose_smplx_t** out, const airpose_smplx_m
     h->owned.push_back(h->xj);
     if (device_upload(&h->xw, xw.data(), xw.size())) return 1;
     h->owned.push_back(h->xw);
+    // skinning weights regrouped per vertex tile by joint: dL/dA_j of a tile is a fixed-order sum over these lists
+    const int vtiles = ceil_div(V, kVertsPerCta);
+    std::vector<int> seg_off(vtiles + 1, 0), seg, ent;
+    for (int t = 0; t < vtiles; ++t) {
+      const int v0 = t * kVertsPerCta, v1 = std::min(V, v0 + kVertsPerCta);
+      for (int j = 0; j < J; ++j) {
+        const int first = (int)ent.size() / 2;
+        for (int v = v0; v < v1; ++v) {
+          const float w = mh->lbs_weights[(size_t)v * J + j];
+          if (w == 0.f) continue;
+          int bits; std::memcpy(&bits, &w, sizeof(bits));
+          ent.push_back(v - v0); ent.push_back(bits);
+        }
+        const int end = (int)ent.size() / 2;
+        if (end > first) { seg.push_back(j); seg.push_back(first); seg.push_back(end); seg.push_back(0); }
+      }
+      seg_off[t + 1] = (int)seg.size() / 4;
+    }
+    if (device_upload(&h->seg_off, seg_off.data(), seg_off.size())) return 1;
+    h->owned.push_back(h->seg_off);
+    if (device_upload(&h->seg, seg.data(), seg.size())) return 1;
+    h->owned.push_back(h->seg);
+    if (device_upload(&h->ent, ent.data(), ent.size())) return 1;
+    h->owned.push_back(h->ent);
   }
   *out = h;
   return 0;
@@ -762,10 +790,12 @@ extern "C" int airpose_smplx_bwd(airpose_smplx_t* h, const airpose_smplx_bwd_arg
   va.betas = g->betas; va.betas_stride = g->betas_stride;
   va.A = A; va.feat = feat; va.g_verts = g->grad_vertices; va.g_jtot = gjt;
   va.Pt = h->Pt; va.xoff = h->xoff; va.xj = h->xj; va.xw = h->xw;
+  va.seg_off = h->seg_off; va.seg = reinterpret_cast<const int4*>(h->seg); va.ent = reinterpret_cast<const int2*>(h->ent);
   va.gA_part = gA_part; va.gq_part = gq_part;
   {
     constexpr int MB = kBwdMB;
-    const size_t smem = ((size_t)PF * MB + 2 * (size_t)MB * d.J * 12 + MB * kMaxShape + (size_t)MB * 3 * kVertsPerCta) * sizeof(float);
+    const size_t smem = ((size_t)kVertsPerCta * (3 * MB + 4) + (size_t)PF * MB + (size_t)MB * d.J * 12 + MB * kMaxShape +
+                         (size_t)kVertsPerCta * kBwdXStride) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
       AP_CHECK_CUDA(cudaFuncSetAttribute(smplx_vertex_bwd_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));

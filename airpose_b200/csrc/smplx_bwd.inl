@@ -10,7 +10,8 @@
 //   K1  smplx_pose_kernel         forward recompute of A_j, posed joints, pose feature (as in the forward call)
 //   K2  smplx_vertex_bwd_kernel   CTA = 128 vertices x MB meshes.  Phase 1 (thread = vertex): recompute v_posed and T_v,
 //                                 g = dL/dv (+ the extra-joint / landmark terms that gather this vertex),
-//                                 dL/dA_j += w g (x) [v_posed;1] (shared-memory accumulation), h = T_v.R^T g -> smem.
+//                                 X = g (x) [v_posed;1] -> smem, dL/dA_j = sum_v w_vj X_v over host-built per-tile
+//                                 (joint, vertex, weight) lists in a fixed order (no atomics), h = T_v.R^T g -> smem.
 //                                 Phase 2 (thread = column q of [posedirs | shapedirs] stored vertex-major): dL/dq =
 //                                 sum over the tile's vertices of Pt[3v+c][q] h[v][c] -- coalesced over q.
 //                                 Per-(vertex tile, mesh) partials go to a workspace: no global atomics.
@@ -100,20 +101,27 @@ struct BwdVertexArgs {
   const int* xoff;           // [V+1] CSR of the joints that gather each vertex
   const int* xj;             // joint row (>= J) ...
   const float* xw;           // ... and its weight
+  const int* seg_off;        // [vtiles+1] per vertex tile: its skinning segments (one per joint that has a non-zero weight there)
+  const int4* seg;           // {joint, first entry, end entry, 0}
+  const int2* ent;           // {vertex in tile, weight bits}, grouped by (tile, joint), vertices ascending
   float* gA_part;            // [vtiles][B][J*12]
   float* gq_part;            // [vtiles][B][NQ]     NQ = PF + nb
   int P;                     // column of the first shape direction in Pt
 };
 
+constexpr int kBwdXStride = 13;      // 12 floats of g (x) [v_posed; 1] per vertex, odd stride: conflict-free both ways
+constexpr int kBwdSegGroups = kVertsPerCta / 12;
+
 template <int MB>
 __global__ void __launch_bounds__(kVertsPerCta) smplx_vertex_bwd_kernel(SmplxDev m, BwdVertexArgs a) {
+  constexpr int HS = 3 * MB + 4;     // H_s row: [c][mesh] of one vertex, padded (16-byte rows, 4-way conflicts on the writes only)
   extern __shared__ __align__(16) float smem[];
   const int A_per_mesh = m.J * 12;
-  float* f_s = smem;                                   // [PF][MB]
-  float* A_s = f_s + (size_t)a.PF * MB;                // [MB][J*12]
-  float* beta_s = A_s + (size_t)MB * A_per_mesh;       // [MB][kMaxShape]
-  float* gA_s = beta_s + MB * kMaxShape;               // [MB][J*12]
-  float* H_s = gA_s + (size_t)MB * A_per_mesh;         // [MB][3][128]
+  float* H_s = smem;                                    // [128][HS]
+  float* f_s = H_s + (size_t)kVertsPerCta * HS;         // [PF][MB]
+  float* A_s = f_s + (size_t)a.PF * MB;                 // [MB][J*12]
+  float* beta_s = A_s + (size_t)MB * A_per_mesh;        // [MB][kMaxShape]
+  float* X_s = beta_s + MB * kMaxShape;                 // [128][13]  (one mesh at a time)
   const int tid = threadIdx.x;
   const int v = blockIdx.x * kVertsPerCta + tid;
   const int mesh0 = blockIdx.y * MB;
@@ -128,12 +136,14 @@ __global__ void __launch_bounds__(kVertsPerCta) smplx_vertex_bwd_kernel(SmplxDev
   for (int i = tid; i < MB * A_per_mesh; i += kVertsPerCta) {
     const int b = i / A_per_mesh;
     A_s[i] = (b < nmesh) ? __ldg(a.A + (size_t)(mesh0 + b) * A_per_mesh + (i - b * A_per_mesh)) : 0.f;
-    gA_s[i] = 0.f;
   }
   for (int i = tid; i < MB * kMaxShape; i += kVertsPerCta) {
     const int b = i / kMaxShape, l = i % kMaxShape;
     beta_s[i] = (b < nmesh && l < a.nb) ? __ldg(a.betas + (size_t)(mesh0 + b) * a.betas_stride + l) : 0.f;
   }
+  // dL/dA partials of this vertex tile: joints without a weight in the tile stay zero, the others are overwritten below
+  for (int i = tid; i < nmesh * A_per_mesh; i += kVertsPerCta)
+    a.gA_part[((size_t)blockIdx.x * a.B + mesh0) * A_per_mesh + i] = 0.f;
   __syncthreads();
 
   // ---- phase 1: thread = vertex.  Pose-corrective offsets exactly as in the forward kernel.
@@ -142,7 +152,7 @@ __global__ void __launch_bounds__(kVertsPerCta) smplx_vertex_bwd_kernel(SmplxDev
   for (int b = 0; b < MB; ++b) acc[b][0] = acc[b][1] = acc[b][2] = 0.f;
   const float* Pv = m.posedirs + (size_t)vc * 3;
   const size_t prow = (size_t)m.V * 3;
-#pragma unroll 2
+#pragma unroll 4
   for (int p = 0; p < a.PF; ++p) {
     const float p0 = __ldg(Pv + p * prow), p1 = __ldg(Pv + p * prow + 1), p2 = __ldg(Pv + p * prow + 2);
     const float4* fr = reinterpret_cast<const float4*>(f_s + (size_t)p * MB);
@@ -162,9 +172,14 @@ __global__ void __launch_bounds__(kVertsPerCta) smplx_vertex_bwd_kernel(SmplxDev
               vt2 = __ldg(m.v_template + vc * 3 + 2);
   const float* Sv = m.shapedirs + (size_t)vc * 3 * m.NS;
   const int x0 = __ldg(a.xoff + vc), x1 = __ldg(a.xoff + vc + 1);
+  const int seg0 = __ldg(a.seg_off + blockIdx.x), seg1 = __ldg(a.seg_off + blockIdx.x + 1);
+  const int se = tid % 12, sg = tid / 12;               // reduction role: element of A_j, segment group
 #pragma unroll
   for (int b = 0; b < MB; ++b) {
     float hx = 0.f, hy = 0.f, hz = 0.f;
+    float X[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) X[e] = 0.f;
     if (b < nmesh && valid) {
       float x = vt0, y = vt1, z = vt2;
       for (int l = 0; l < a.nb; ++l) {
@@ -185,61 +200,94 @@ __global__ void __launch_bounds__(kVertsPerCta) smplx_vertex_bwd_kernel(SmplxDev
         const float* gj = a.g_jtot + ((size_t)(mesh0 + b) * a.nj + __ldg(a.xj + e)) * 3;
         g0 = fmaf(w, __ldg(gj), g0); g1 = fmaf(w, __ldg(gj + 1), g1); g2 = fmaf(w, __ldg(gj + 2), g2);
       }
-      // T = sum_k w_k A_k; dL/dA_k += w_k g (x) [v_posed; 1]; h = T.R^T g
+      // T = sum_k w_k A_k;  h = T.R^T g;  X = g (x) [v_posed; 1]  (dL/dA_k = sum_v w_vk X_v, reduced below)
       float T[9];
 #pragma unroll
       for (int e = 0; e < 9; ++e) T[e] = 0.f;
-      const float vp[4] = {x, y, z, 1.f};
       for (int k = 0; k < m.KW; ++k) {
         const float w = __ldg(m.skin_w + (size_t)k * m.V + vc);
         if (w == 0.f) continue;
         const int jn = __ldg(m.skin_idx + (size_t)k * m.V + vc);
         const float* Aj = A_s + (size_t)b * A_per_mesh + jn * 12;
-        float* gAj = gA_s + (size_t)b * A_per_mesh + jn * 12;
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const float gr = w * (r == 0 ? g0 : (r == 1 ? g1 : g2));
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int c = 0; c < 3; ++c) T[r * 3 + c] = fmaf(w, Aj[r * 4 + c], T[r * 3 + c]);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) atomicAdd(gAj + r * 4 + c, gr * vp[c]);
-        }
       }
+      const float gv[3] = {g0, g1, g2}, vp[4] = {x, y, z, 1.f};
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) X[r * 4 + c] = gv[r] * vp[c];
       hx = T[0] * g0 + T[3] * g1 + T[6] * g2;
       hy = T[1] * g0 + T[4] * g1 + T[7] * g2;
       hz = T[2] * g0 + T[5] * g1 + T[8] * g2;
     }
-    H_s[(b * 3 + 0) * kVertsPerCta + tid] = hx;
-    H_s[(b * 3 + 1) * kVertsPerCta + tid] = hy;
-    H_s[(b * 3 + 2) * kVertsPerCta + tid] = hz;
+    H_s[tid * HS + 0 * MB + b] = hx;
+    H_s[tid * HS + 1 * MB + b] = hy;
+    H_s[tid * HS + 2 * MB + b] = hz;
+    if (b < nmesh) {                                    // block-uniform
+      if (b > 0) __syncthreads();                       // the previous mesh's reduction has read X_s
+#pragma unroll
+      for (int e = 0; e < 12; ++e) X_s[tid * kBwdXStride + e] = X[e];
+      __syncthreads();
+      // dL/dA_j[e] of this mesh over the tile: fixed order (entries ascend by vertex), no atomics
+      if (sg < kBwdSegGroups) {
+        for (int s = seg0 + sg; s < seg1; s += kBwdSegGroups) {
+          const int4 sd = __ldg(a.seg + s);
+          float r = 0.f;
+          for (int i = sd.y; i < sd.z; ++i) {
+            const int2 en = __ldg(a.ent + i);
+            r = fmaf(__int_as_float(en.y), X_s[en.x * kBwdXStride + se], r);
+          }
+          a.gA_part[((size_t)blockIdx.x * a.B + mesh0 + b) * A_per_mesh + sd.x * 12 + se] = r;
+        }
+      }
+    }
   }
   __syncthreads();
 
-  // ---- dL/dA partials of this vertex tile
-  for (int i = tid; i < nmesh * A_per_mesh; i += kVertsPerCta) {
-    const int b = i / A_per_mesh;
-    a.gA_part[((size_t)blockIdx.x * a.B + mesh0 + b) * A_per_mesh + (i - b * A_per_mesh)] = gA_s[i];
-  }
-  // ---- phase 2: thread = column q of Pt (pose feature rows, then shape directions)
+  // ---- phase 2: thread = columns q and q + 128 of Pt (pose feature rows, then shape directions)
   const int v_base = blockIdx.x * kVertsPerCta;
   const int nv = min(kVertsPerCta, m.V - v_base);
-  for (int q = tid; q < a.NQ; q += kVertsPerCta) {
-    const int col = q < a.PF ? q : a.P + (q - a.PF);
-    float s[MB];
+  for (int q0 = tid; q0 < a.NQ; q0 += 2 * kVertsPerCta) {
+    const int q1 = q0 + kVertsPerCta;
+    const bool two = q1 < a.NQ;
+    const int col0 = q0 < a.PF ? q0 : a.P + (q0 - a.PF);
+    const int col1 = two ? (q1 < a.PF ? q1 : a.P + (q1 - a.PF)) : col0;
+    float s0[MB], s1[MB];
 #pragma unroll
-    for (int b = 0; b < MB; ++b) s[b] = 0.f;
-    const float* pt = a.Pt + (size_t)v_base * 3 * a.ldq + col;
+    for (int b = 0; b < MB; ++b) s0[b] = s1[b] = 0.f;
+    const float* pt = a.Pt + (size_t)v_base * 3 * a.ldq;
+#pragma unroll 2
     for (int vv = 0; vv < nv; ++vv) {
+      float pa[3], pb[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float pv = __ldg(pt + (size_t)(vv * 3 + c) * a.ldq);
+        pa[c] = __ldg(pt + (size_t)(vv * 3 + c) * a.ldq + col0);
+        pb[c] = __ldg(pt + (size_t)(vv * 3 + c) * a.ldq + col1);
+      }
 #pragma unroll
-        for (int b = 0; b < MB; ++b) s[b] = fmaf(pv, H_s[(b * 3 + c) * kVertsPerCta + vv], s[b]);
+      for (int c = 0; c < 3; ++c) {
+        const float4* hr = reinterpret_cast<const float4*>(H_s + vv * HS + c * MB);
+#pragma unroll
+        for (int qd = 0; qd < MB / 4; ++qd) {
+          const float4 h4 = hr[qd];
+          const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            s0[qd * 4 + r] = fmaf(pa[c], hv[r], s0[qd * 4 + r]);
+            s1[qd * 4 + r] = fmaf(pb[c], hv[r], s1[qd * 4 + r]);
+          }
+        }
       }
     }
 #pragma unroll
     for (int b = 0; b < MB; ++b)
-      if (b < nmesh) a.gq_part[((size_t)blockIdx.x * a.B + mesh0 + b) * a.NQ + q] = s[b];
+      if (b < nmesh) {
+        a.gq_part[((size_t)blockIdx.x * a.B + mesh0 + b) * a.NQ + q0] = s0[b];
+        if (two) a.gq_part[((size_t)blockIdx.x * a.B + mesh0 + b) * a.NQ + q1] = s1[b];
+      }
   }
 }
 

@@ -1333,12 +1333,86 @@ static int bn_bwd(airpose_net* h, const airpose_net::Tape& tp, int i, int64_t M,
   return 0;
 }
 
-// weight gradient of conv i: g_weight (+)= dz^T . im2col(x_in)  on the tensor cores (both operands transposed to K-major)
+// Fixed-order sum of the split-K partial tiles of a weight-gradient GEMM (gemm.cuh SplitKInfo), written straight into the fp32
+// gradient in the parameter's own layout: g[cout][cin][tap] (+)= sum_r P_r[cout][tap * cin + c].  One thread = 4 columns of one row.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int R, int tiles_n, int BN, int slot_floats, int cout,
+                                                           int cin, int kk, float* __restrict__ g, int accumulate) {
+  const int N = cin * kk, n4 = (N + 3) / 4;
+  const int64_t total = (int64_t)n4 * cout;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % cout), col0 = (int)(i / cout) * 4;
+    const int n_blk = col0 / BN, cl = col0 - n_blk * BN, m_blk = o >> 7, row = o & 127;
+    const int tile = m_blk * tiles_n + n_blk;
+    const float4* src = reinterpret_cast<const float4*>(part + (size_t)tile * R * slot_floats) + (((cl >> 6) * 16 + ((cl & 63) >> 2)) * 128 + row);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < R; ++r) {
+      const float4 v = __ldcg(src + (size_t)r * (slot_floats / 4));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = col0 + e;
+      if (n >= N) break;
+      const int tap = n / cin, c = n - tap * cin;
+      const int64_t idx = ((int64_t)o * cin + c) * kk + tap;
+      g[idx] = av[e] + (accumulate ? g[idx] : 0.f);
+    }
+  }
+}
+
+// Runs one weight-gradient GEMM whose operands are described by L (dz as the transposed A operand).  Few tiles and a very long K
+// (the early layers): plain split-K over all SMs + wgrad_reduce_kernel straight into the fp32 gradient; otherwise stream-K into
+// the conv's bf16 slot, unpacked later (batched pass) or right away.
+static int run_wgrad_gemm(airpose_net* h, GemmLaunch& L, int i, int cin, int kk, const airpose_trunk_grads* g, cudaStream_t st) {
+  const int cout = L.M, ldd = L.N;
+  L.epi.out_bf16 = h->bw_batched ? h->bw_wg + h->bw_w_off[i] : h->bw_w; L.epi.ldd = ldd;
+  if (enable_tma_epilogue(&L)) return 1;
+  const int ranges = splitk_ranges(L.M, L.N, L.K, L.block_n);
+  if (ranges) {
+    SplitKInfo sk{};
+    sk.ranges = ranges;
+    if (launch_gemm_sk(L, st, &sk)) return 1;
+    const int64_t total = (int64_t)((cin * kk + 3) / 4) * cout;
+    wgrad_reduce_kernel<<<ew_grid(total), 256, 0, st>>>(sk.part, ranges, sk.tiles_n, sk.block_n, sk.slot_floats, cout, cin, kk, g->g_weight[i], g->accumulate);
+    AP_LAUNCH_CHECK();
+    if (h->bw_batched) h->bw_reduced[i] = true;       // the batched unpack at the end of the pass skips this conv
+    return 0;
+  }
+  if (launch_gemm_sk(L, st)) return 1;
+  if (h->bw_batched) return 0;                      // unpacked with every other conv by ONE launch at the end of the pass
+  wgrad_unpack_kernel<<<ew_grid((int64_t)cout * cin * kk), 256, 0, st>>>(h->bw_w, cout, cin, kk, ldd, g->g_weight[i], g->accumulate);
+  AP_LAUNCH_CHECK();
+  return 0;
+}
+
+// weight gradient of conv i: g_weight (+)= dz^T . im2col(x_in)  on the tensor cores.  Both operands contract over the pixels, the
+// OUTER dimension of the NHWC tensors: dz [pixels][cout] and, for 1x1 stride-1 convs, x_in [pixels][cin] are read as they lie
+// through MN-major descriptors; 3x3 / strided convs read im2col(x_in)^T through an im2col tensor map with 64-pixel boxes.
+// AIRPOSE_WGRAD_TRANSPOSE=1 restores the explicit transposes to K-major operands (A/B runs).
 static int conv_wgrad(airpose_net* h, int i, const __nv_bfloat16* dz, const __nv_bfloat16* x_in, int n, int Hin, int Hout,
                       const airpose_trunk_grads* g, cudaStream_t st) {
   const ConvSpec& s = h->specs[i];
   const int64_t M = (int64_t)n * Hout * Hout;
   const int Kdim = s.k * s.k * s.cin;
+  static const bool direct = getenv("AIRPOSE_WGRAD_TRANSPOSE") == nullptr;
+  if (direct && s.cin % 64 == 0) {
+    GemmLaunch L{};
+    L.M = s.cout; L.N = Kdim; L.K = (int)M;
+    L.block_n = Kdim % 256 == 0 ? 256 : (Kdim > 64 ? 128 : 64);
+    L.mn_a = 1;
+    if (make_tmap_tiled_bf16(&L.tmA, dz, M, s.cout, s.cout, 64, 64)) return 1;
+    if (s.k == 1 && s.stride == 1) {
+      L.mn_b = 1;
+      if (make_tmap_tiled_bf16(&L.tmB, x_in, M, s.cin, s.cin, 64, 64)) return 1;
+    } else {
+      L.mn_b = 2;
+      ConvGeom& cg = L.geom;
+      cg.n = n; cg.H = Hin; cg.W = Hin; cg.Cin = s.cin; cg.ksize = s.k; cg.stride = s.stride; cg.pad = s.pad; cg.Ho = Hout; cg.Wo = Hout;
+      if (make_tmap_im2col_bf16(&L.tmB, x_in, cg, 64, 64)) return 1;
+    }
+    return run_wgrad_gemm(h, L, i, s.cin, s.k * s.k, g, st);
+  }
   // K-major operands [channels][pixels]: the row pitch is rounded up to 8 elements (16-byte TMA pitch) so that any image
   // count works (196 and 49 pixels per image are not multiples of 8); the GEMM's K extent stays M, the pad is never read
   const int64_t ld = (M + 7) & ~(int64_t)7;
@@ -1471,23 +1545,37 @@ static int backbone_bwd_train_impl(airpose_net_t* h, const float* x, const float
   const int64_t M0 = (int64_t)n * 112 * 112;
   if (bn_bwd(h, tp, 0, M0, bn, g, G2, true, DZ, nullptr, st)) return 1;
   {
-    launch_transpose(DZ, M0, 64, h->bw_t0, M0, st);
-    AP_LAUNCH_CHECK();
+    static const bool direct = getenv("AIRPOSE_WGRAD_TRANSPOSE") == nullptr;      // as in conv_wgrad
+    if (!direct) {
+      launch_transpose(DZ, M0, 64, h->bw_t0, M0, st);
+      AP_LAUNCH_CHECK();
+    }
     for (int v = 0; v < views; ++v) {                       // columns [v * M0 / views, ...) of the K-major operand come from view v's images
       stem_im2colT_kernel<<<dim3(148 * 4, 192), 256, 0, st>>>(v ? x1 : x, n_view, h->bw_t1 + (size_t)v * (M0 / views), M0);
       AP_LAUNCH_CHECK();
     }
-    airpose_gemm_args ga{};
-    ga.A = h->bw_t0; ga.lda = M0; ga.B = h->bw_t1; ga.ldb = M0;
-    ga.M = 64; ga.N = 192; ga.K = (int)M0;
-    ga.out_bf16 = h->bw_wg + h->bw_w_off[0]; ga.ldd = 192;
-    if (airpose_gemm_bf16(&ga, st)) return 1;
+    if (direct) {
+      GemmLaunch L{};
+      L.M = 64; L.N = 192; L.K = (int)M0;
+      L.block_n = 128;
+      L.mn_a = 1;
+      if (make_tmap_tiled_bf16(&L.tmA, DZ, M0, 64, 64, 64, 64)) return 1;
+      if (make_tmap_tiled_bf16(&L.tmB, h->bw_t1, 192, M0, M0, L.block_n, 64)) return 1;
+      if (run_wgrad_gemm(h, L, 0, 3, 49, g, st)) return 1;
+    } else {
+      airpose_gemm_args ga{};
+      ga.A = h->bw_t0; ga.lda = M0; ga.B = h->bw_t1; ga.ldb = M0;
+      ga.M = 64; ga.N = 192; ga.K = (int)M0;
+      ga.out_bf16 = h->bw_wg + h->bw_w_off[0]; ga.ldd = 192;
+      if (airpose_gemm_bf16(&ga, st)) return 1;
+    }
   }
   {                                                  // every conv's weight gradient out of its slot, one launch
     WgradTab wt{};
     for (size_t i = 0; i < h->specs.size(); ++i) {
       const ConvSpec& s = h->specs[i];
-      wt.D[i] = h->bw_wg + h->bw_w_off[i]; wt.g[i] = g->g_weight[i]; wt.cout[i] = s.cout; wt.cin[i] = s.cin;
+      wt.D[i] = h->bw_wg + h->bw_w_off[i]; wt.g[i] = h->bw_reduced[i] ? nullptr : g->g_weight[i]; wt.cout[i] = s.cout; wt.cin[i] = s.cin;
+      h->bw_reduced[i] = false;
       wt.kk[i] = s.k * s.k; wt.ldd[i] = i == 0 ? 192 : s.k * s.k * s.cin;
     }
     wgrad_unpack_all_kernel<<<dim3(48, (unsigned)h->specs.size()), 256, 0, st>>>(wt, g->accumulate);

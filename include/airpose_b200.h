@@ -457,6 +457,11 @@ typedef struct {
   int32_t relu;
   void*  out_bf16; int64_t ldd;     /* bf16 [M,N] or NULL */
   float* out_f32;  int64_t ldf;     /* fp32 [M,N] or NULL */
+  /* a_t != 0: A is given transposed, bf16 [K,M] with row pitch lda (M contiguous); b_t likewise for B as [K,N].  The operand is
+   * then read through MN-major tcgen05 descriptors -- no transpose pass.  This is the weight-gradient form: both operands of
+   * dW = dZ^T . X contract over the pixels, the OUTER dimension of NHWC tensors (what torch autograd computes for
+   * copenet_twoview.py:378-386).  Needs out_bf16 with N % 64 == 0, and M % 8 == 0 (a_t) / N % 8 == 0 (b_t). */
+  int32_t a_t, b_t;
 } airpose_gemm_args;
 int airpose_gemm_bf16(const airpose_gemm_args* g, void* stream);
 

@@ -256,6 +256,38 @@ def test_gemm_tma_epilogue_bf16_out(M, N, K, res, relu):
     assert (out[M:] == 7.0).all()
 
 
+@pytest.mark.parametrize("M,N,K,a_t,b_t", [(128, 64, 64, 1, 1), (64, 256, 6272, 1, 1), (256, 64, 25088, 1, 1), (512, 2048, 3136, 1, 1),
+                                           (64, 576, 5000, 1, 0), (128, 1152, 1576, 1, 0), (192, 320, 777, 1, 1), (64, 192, 25088, 1, 0),
+                                           (256, 128, 4096, 0, 1), (2048, 512, 3136, 1, 1)])
+def test_gemm_transposed_operands(M, N, K, a_t, b_t):
+    """airpose_gemm_args.a_t / b_t: the operand is given as [K, M] / [K, N] (the weight-gradient form: both operands contract over
+    the pixels, the outer dimension of NHWC tensors) and read through MN-major tcgen05 descriptors.  M = 64 (half a tile), N tails,
+    K tails (zero-filled boxes) and stream-K cuts of the long K are all in the list; compared with fp32 torch on the same bf16 data."""
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + a_t + 2 * b_t)
+    A = _bf16(torch.randn(K, M, generator=g) if a_t else torch.randn(M, K, generator=g)).to(DEV)
+    Bm = _bf16((torch.randn(K, N, generator=g) if b_t else torch.randn(N, K, generator=g)) / K ** 0.5).to(DEV)
+    guard = 64
+    out = torch.full((M + guard, N), 7.0, device=DEV, dtype=torch.bfloat16)
+    a = _lib.GemmArgs()
+    a.A, a.lda = A.data_ptr(), A.shape[1]
+    a.B, a.ldb = Bm.data_ptr(), Bm.shape[1]
+    a.M, a.N, a.K = M, N, K
+    a.a_t, a.b_t = a_t, b_t
+    a.out_bf16, a.ldd = out.data_ptr(), N
+    for _ in range(2):
+        _lib.check(lib.airpose_gemm_bf16(C.byref(a), _lib.current_stream()), "gemm")
+    torch.cuda.synchronize()
+    Af = A.float().t() if a_t else A.float()
+    Bf = Bm.float().t() if b_t else Bm.float()
+    ref = Af @ Bf.t()
+    got = out[:M].float()
+    bad = (got - ref).abs() > ref.abs() * 2.0 ** -8 + 2e-3
+    print("gemm-t %dx%dx%d a_t=%d b_t=%d: max abs err %.3e bad %d" % (M, N, K, a_t, b_t, (got - ref).abs().max().item(), int(bad.sum())))
+    assert not bad.any()
+    assert (out[M:] == 7.0).all()
+
+
 def test_gemm_epilogue_scale_shift_residual_relu():
     lib = _lib.load()
     M, N, K = 700, 256, 192
