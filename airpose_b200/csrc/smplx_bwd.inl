@@ -22,7 +22,7 @@
 
 namespace airpose {
 
-constexpr int kBwdMB = 8;
+constexpr int kBwdMB = 4;       // meshes per CTA: the kernel is bound by the latency of its global loads, so more and smaller CTAs win
 
 struct BwdJointArgs {
   int B, nj;
@@ -152,19 +152,28 @@ __global__ void __launch_bounds__(kVertsPerCta) smplx_vertex_bwd_kernel(SmplxDev
   for (int b = 0; b < MB; ++b) acc[b][0] = acc[b][1] = acc[b][2] = 0.f;
   const float* Pv = m.posedirs + (size_t)vc * 3;
   const size_t prow = (size_t)m.V * 3;
-#pragma unroll 4
-  for (int p = 0; p < a.PF; ++p) {
-    const float p0 = __ldg(Pv + p * prow), p1 = __ldg(Pv + p * prow + 1), p2 = __ldg(Pv + p * prow + 2);
-    const float4* fr = reinterpret_cast<const float4*>(f_s + (size_t)p * MB);
+  // the loop is a chain of global-load latencies unless the loads of several rows are issued together: 8 rows (24 loads) per batch
+  for (int pb = 0; pb < a.PF; pb += 8) {
+    float pv[8][3];
 #pragma unroll
-    for (int q = 0; q < MB / 4; ++q) {
-      const float4 f4 = fr[q];
-      const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+    for (int k = 0; k < 8; ++k) {
+      const int p = min(pb + k, a.PF - 1);
+      const float ok = pb + k < a.PF ? 1.f : 0.f;       // straight-line code (no branch): ptxas keeps the 24 loads together
+      pv[k][0] = ok * __ldg(Pv + p * prow); pv[k][1] = ok * __ldg(Pv + p * prow + 1); pv[k][2] = ok * __ldg(Pv + p * prow + 2);
+    }
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        acc[q * 4 + r][0] = fmaf(fv[r], p0, acc[q * 4 + r][0]);
-        acc[q * 4 + r][1] = fmaf(fv[r], p1, acc[q * 4 + r][1]);
-        acc[q * 4 + r][2] = fmaf(fv[r], p2, acc[q * 4 + r][2]);
+    for (int k = 0; k < 8; ++k) {
+      const float4* fr = reinterpret_cast<const float4*>(f_s + (size_t)min(pb + k, a.PF - 1) * MB);
+#pragma unroll
+      for (int q = 0; q < MB / 4; ++q) {
+        const float4 f4 = fr[q];
+        const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          acc[q * 4 + r][0] = fmaf(fv[r], pv[k][0], acc[q * 4 + r][0]);
+          acc[q * 4 + r][1] = fmaf(fv[r], pv[k][1], acc[q * 4 + r][1]);
+          acc[q * 4 + r][2] = fmaf(fv[r], pv[k][2], acc[q * 4 + r][2]);
+        }
       }
     }
   }
@@ -259,25 +268,32 @@ __global__ void __launch_bounds__(kVertsPerCta) smplx_vertex_bwd_kernel(SmplxDev
 #pragma unroll
     for (int b = 0; b < MB; ++b) s0[b] = s1[b] = 0.f;
     const float* pt = a.Pt + (size_t)v_base * 3 * a.ldq;
-#pragma unroll 2
-    for (int vv = 0; vv < nv; ++vv) {
-      float pa[3], pb[3];
+    for (int vb = 0; vb < nv; vb += 4) {              // 4 vertices = 24 loads per batch, issued together
+      float pa[4][3], pb[4][3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        pa[c] = __ldg(pt + (size_t)(vv * 3 + c) * a.ldq + col0);
-        pb[c] = __ldg(pt + (size_t)(vv * 3 + c) * a.ldq + col1);
+      for (int k = 0; k < 4; ++k) {
+        const int vv = min(vb + k, nv - 1);
+        const float ok = vb + k < nv ? 1.f : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          pa[k][c] = ok * __ldg(pt + (size_t)(vv * 3 + c) * a.ldq + col0);
+          pb[k][c] = ok * __ldg(pt + (size_t)(vv * 3 + c) * a.ldq + col1);
+        }
       }
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float4* hr = reinterpret_cast<const float4*>(H_s + vv * HS + c * MB);
+      for (int k = 0; k < 4; ++k) {
 #pragma unroll
-        for (int qd = 0; qd < MB / 4; ++qd) {
-          const float4 h4 = hr[qd];
-          const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+        for (int c = 0; c < 3; ++c) {
+          const float4* hr = reinterpret_cast<const float4*>(H_s + min(vb + k, nv - 1) * HS + c * MB);
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            s0[qd * 4 + r] = fmaf(pa[c], hv[r], s0[qd * 4 + r]);
-            s1[qd * 4 + r] = fmaf(pb[c], hv[r], s1[qd * 4 + r]);
+          for (int qd = 0; qd < MB / 4; ++qd) {
+            const float4 h4 = hr[qd];
+            const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              s0[qd * 4 + r] = fmaf(pa[k][c], hv[r], s0[qd * 4 + r]);
+              s1[qd * 4 + r] = fmaf(pb[k][c], hv[r], s1[qd * 4 + r]);
+            }
           }
         }
       }

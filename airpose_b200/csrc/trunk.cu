@@ -218,17 +218,27 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __re
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  if (rl < lanes)
-    for (int64_t r = r0 + rl; r < r1; r += lanes) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(z + r * C + cg * 8));
-      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+  auto add_row = [&](const uint4& v) {
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float a = __uint_as_float(u[j] << 16), b = __uint_as_float(u[j] & 0xFFFF0000u);
-        s[2 * j] += a; q[2 * j] = fmaf(a, a, q[2 * j]);
-        s[2 * j + 1] += b; q[2 * j + 1] = fmaf(b, b, q[2 * j + 1]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float a = __uint_as_float(u[j] << 16), b = __uint_as_float(u[j] & 0xFFFF0000u);
+      s[2 * j] += a; q[2 * j] = fmaf(a, a, q[2 * j]);
+      s[2 * j + 1] += b; q[2 * j + 1] = fmaf(b, b, q[2 * j + 1]);
     }
+  };
+  if (rl < lanes) {
+    // four rows in flight per thread (the pass is latency-bound with one), accumulated in row order: same sums as a plain loop
+    int64_t r = r0 + rl;
+    for (; r + 3 * lanes < r1; r += 4 * lanes) {
+      uint4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const uint4*>(z + (r + k * lanes) * C + cg * 8));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) add_row(v[k]);
+    }
+    for (; r < r1; r += lanes) add_row(__ldg(reinterpret_cast<const uint4*>(z + r * C + cg * 8)));
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][8 + j] = q[j]; }
   __syncthreads();
@@ -868,22 +878,25 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16*
   float s[8], q[8], mean[8], istd[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = q[j] = 0.f; mean[j] = stats[cg * 8 + j]; istd[j] = stats[C + cg * 8 + j]; }
+  auto add_row = [&](const uint4& vd, const uint4& vz, const uint4& vy) {
+    const uint32_t ud[4] = {vd.x, vd.y, vd.z, vd.w}, uz[4] = {vz.x, vz.y, vz.z, vz.w}, uy[4] = {vy.x, vy.y, vy.z, vy.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d0 = __uint_as_float(uy[j] << 16) > 0.f ? __uint_as_float(ud[j] << 16) : 0.f;
+      const float d1 = __uint_as_float(uy[j] & 0xFFFF0000u) > 0.f ? __uint_as_float(ud[j] & 0xFFFF0000u) : 0.f;
+      const float x0 = (__uint_as_float(uz[j] << 16) - mean[2 * j]) * istd[2 * j];
+      const float x1 = (__uint_as_float(uz[j] & 0xFFFF0000u) - mean[2 * j + 1]) * istd[2 * j + 1];
+      s[2 * j] += d0; q[2 * j] = fmaf(d0, x0, q[2 * j]);
+      s[2 * j + 1] += d1; q[2 * j + 1] = fmaf(d1, x1, q[2 * j + 1]);
+    }
+  };
+  const uint4 pos = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);     // "positive" when there is no ReLU
+  // (three rows in flight per thread was measured SLOWER here: 1452 vs 983 us over the 53 launches of a step, profiles/r02t4)
   if (rl < lanes)
     for (int64_t r = r0 + rl; r < r1; r += lanes) {
-      const uint4 vd = __ldg(reinterpret_cast<const uint4*>(dy + r * C + cg * 8));
-      const uint4 vz = __ldg(reinterpret_cast<const uint4*>(z + r * C + cg * 8));
-      uint4 vy = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);     // "positive" when there is no ReLU
-      if (y) vy = __ldg(reinterpret_cast<const uint4*>(y + r * C + cg * 8));
-      const uint32_t ud[4] = {vd.x, vd.y, vd.z, vd.w}, uz[4] = {vz.x, vz.y, vz.z, vz.w}, uy[4] = {vy.x, vy.y, vy.z, vy.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float d0 = __uint_as_float(uy[j] << 16) > 0.f ? __uint_as_float(ud[j] << 16) : 0.f;
-        const float d1 = __uint_as_float(uy[j] & 0xFFFF0000u) > 0.f ? __uint_as_float(ud[j] & 0xFFFF0000u) : 0.f;
-        const float x0 = (__uint_as_float(uz[j] << 16) - mean[2 * j]) * istd[2 * j];
-        const float x1 = (__uint_as_float(uz[j] & 0xFFFF0000u) - mean[2 * j + 1]) * istd[2 * j + 1];
-        s[2 * j] += d0; q[2 * j] = fmaf(d0, x0, q[2 * j]);
-        s[2 * j + 1] += d1; q[2 * j + 1] = fmaf(d1, x1, q[2 * j + 1]);
-      }
+      const int64_t o = r * C + cg * 8;
+      add_row(__ldg(reinterpret_cast<const uint4*>(dy + o)), __ldg(reinterpret_cast<const uint4*>(z + o)),
+              y ? __ldg(reinterpret_cast<const uint4*>(y + o)) : pos);
     }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][8 + j] = q[j]; }
@@ -1334,30 +1347,45 @@ static int bn_bwd(airpose_net* h, const airpose_net::Tape& tp, int i, int64_t M,
 }
 
 // Fixed-order sum of the split-K partial tiles of a weight-gradient GEMM (gemm.cuh SplitKInfo), written straight into the fp32
-// gradient in the parameter's own layout: g[cout][cin][tap] (+)= sum_r P_r[cout][tap * cin + c].  One thread = 4 columns of one row.
+// gradient in the parameter's own layout: g[cout][cin][tap] (+)= sum_r P_r[cout][tap * cin + c].  An item = 4 columns of one row;
+// a CTA takes 32 items x 8 range groups (group k sums ranges k, k+8, ... in order, the groups are added in order through shared
+// memory): the early layers have few outputs and up to 148 partials each, one thread per item left most SMs idle.
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int R, int tiles_n, int BN, int slot_floats, int cout,
                                                            int cin, int kk, float* __restrict__ g, int accumulate) {
+  __shared__ float4 red[8][32];
   const int N = cin * kk, n4 = (N + 3) / 4;
   const int64_t total = (int64_t)n4 * cout;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int o = (int)(i % cout), col0 = (int)(i / cout) * 4;
-    const int n_blk = col0 / BN, cl = col0 - n_blk * BN, m_blk = o >> 7, row = o & 127;
-    const int tile = m_blk * tiles_n + n_blk;
-    const float4* src = reinterpret_cast<const float4*>(part + (size_t)tile * R * slot_floats) + (((cl >> 6) * 16 + ((cl & 63) >> 2)) * 128 + row);
+  const int il = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  for (int64_t base = (int64_t)blockIdx.x * 32; base < total; base += (int64_t)gridDim.x * 32) {
+    const int64_t i = base + il;
+    const bool valid = i < total;
+    const int o = valid ? (int)(i % cout) : 0, col0 = valid ? (int)(i / cout) * 4 : 0;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < R; ++r) {
-      const float4 v = __ldcg(src + (size_t)r * (slot_floats / 4));
-      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    if (valid) {
+      const int n_blk = col0 / BN, cl = col0 - n_blk * BN, m_blk = o >> 7, row = o & 127;
+      const int tile = m_blk * tiles_n + n_blk;
+      const float4* src = reinterpret_cast<const float4*>(part + (size_t)tile * R * slot_floats) + (((cl >> 6) * 16 + ((cl & 63) >> 2)) * 128 + row);
+      for (int r = rg; r < R; r += 8) {
+        const float4 v = __ldcg(src + (size_t)r * (slot_floats / 4));
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
     }
-    const float av[4] = {a.x, a.y, a.z, a.w};
+    red[rg][il] = a;
+    __syncthreads();
+    if (rg == 0 && valid) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int n = col0 + e;
-      if (n >= N) break;
-      const int tap = n / cin, c = n - tap * cin;
-      const int64_t idx = ((int64_t)o * cin + c) * kk + tap;
-      g[idx] = av[e] + (accumulate ? g[idx] : 0.f);
+      for (int k = 1; k < 8; ++k) { const float4 v = red[k][il]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int n = col0 + e;
+        if (n >= N) break;
+        const int tap = n / cin, c = n - tap * cin;
+        const int64_t idx = ((int64_t)o * cin + c) * kk + tap;
+        g[idx] = av[e] + (accumulate ? g[idx] : 0.f);
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -1374,7 +1402,7 @@ static int run_wgrad_gemm(airpose_net* h, GemmLaunch& L, int i, int cin, int kk,
     sk.ranges = ranges;
     if (launch_gemm_sk(L, st, &sk)) return 1;
     const int64_t total = (int64_t)((cin * kk + 3) / 4) * cout;
-    wgrad_reduce_kernel<<<ew_grid(total), 256, 0, st>>>(sk.part, ranges, sk.tiles_n, sk.block_n, sk.slot_floats, cout, cin, kk, g->g_weight[i], g->accumulate);
+    wgrad_reduce_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(total, 32), 148 * 8), 256, 0, st>>>(sk.part, ranges, sk.tiles_n, sk.block_n, sk.slot_floats, cout, cin, kk, g->g_weight[i], g->accumulate);
     AP_LAUNCH_CHECK();
     if (h->bw_batched) h->bw_reduced[i] = true;       // the batched unpack at the end of the pass skips this conv
     return 0;
