@@ -22,58 +22,74 @@ namespace {
 constexpr int kF = 2048, kU = 284, kZ = kF + kU, kH = 1024, kD = 145;   // feature, state part of z, fc1 in, hidden, decoded
 
 // C[M,N] = alpha * sum_k A(m,k) B(k,n) + beta * C[M,N];  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]
-constexpr int kTM = 32, kTN = 32, kTK = 32;      // small tiles: the products have 2B <= 128 rows, parallelism comes from the CTA count
+// 64 x 64 tiles, 4 x 4 outputs per thread (two 16-byte shared loads per 16 FMAs), k tiles of 16 with the next tile's global
+// loads in registers while the current one is multiplied.  The products have 2B <= 128 rows: parallelism comes from split-K.
+constexpr int kTM = 64, kTN = 64, kTK = 16, kTP = kTM + 4;      // row pitch 68 floats: 16-byte aligned, 2-way conflicts at worst
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
                                                     const float* __restrict__ B, int64_t sbk, int64_t sbn,
                                                     float* __restrict__ C, int64_t ldc, int M, int N, int K, float alpha, float beta,
                                                     int k_per_split, float* __restrict__ partial) {
-  __shared__ float As[kTK][kTM + 1], Bs[kTK][kTN + 1];
+  __shared__ __align__(16) float As[2][kTK][kTP], Bs[2][kTK][kTP];
   const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
-  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;        // 16 x 16 threads, 2 x 2 outputs each
-  constexpr int kR = kTM / 16;
-  float acc[kR][kR];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;        // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < kR; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < kR; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   // split-K (gridDim.z > 1): this CTA contracts k in [z * k_per_split, ...) and writes its partial tile to partial[z][M][N];
   // splitk_reduce_kernel adds the partials in a fixed order (no atomics: bitwise reproducible)
   const int k_begin = blockIdx.z * k_per_split;
   K = min(K, k_begin + k_per_split);
+  // element e of a 64 x 16 tile handled by this thread: 4 per operand; the faster index follows whichever stride is 1
+  int am[4], ak[4], bn[4], bk[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = threadIdx.x + e * 256;
+    if (sak == 1) { ak[e] = i % kTK; am[e] = i / kTK; } else { am[e] = i % kTM; ak[e] = i / kTM; }
+    if (sbk == 1) { bk[e] = i % kTK; bn[e] = i / kTK; } else { bn[e] = i % kTN; bk[e] = i / kTN; }
+  }
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int gm = m0 + am[e], gka = k0 + ak[e], gn = n0 + bn[e], gkb = k0 + bk[e];
+      ra[e] = (gm < M && gka < K) ? __ldg(A + gm * sam + gka * sak) : 0.f;
+      rb[e] = (gn < N && gkb < K) ? __ldg(B + gkb * sbk + gn * sbn) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { As[buf][ak[e]][am[e]] = ra[e]; Bs[buf][bk[e]][bn[e]] = rb[e]; }
+  };
+  if (k_begin < K) {
+    fetch(k_begin);
+    stash(0);
+  }
+  __syncthreads();
+  int buf = 0;
   for (int k0 = k_begin; k0 < K; k0 += kTK) {
-    for (int i = threadIdx.x; i < kTM * kTK; i += 256) {
-      // pick the faster-varying index along whichever stride is 1 so the loads coalesce
-      int m, k;
-      if (sak == 1) { k = i % kTK; m = i / kTK; } else { m = i % kTM; k = i / kTM; }
-      const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < M && gk < K) ? __ldg(A + gm * sam + gk * sak) : 0.f;
-    }
-    for (int i = threadIdx.x; i < kTN * kTK; i += 256) {
-      int n, k;
-      if (sbk == 1) { k = i % kTK; n = i / kTK; } else { n = i % kTN; k = i / kTN; }
-      const int gn = n0 + n, gk = k0 + k;
-      Bs[k][n] = (gn < N && gk < K) ? __ldg(B + gk * sbk + gn * sbn) : 0.f;
-    }
-    __syncthreads();
+    const bool more = k0 + kTK < K;
+    if (more) fetch(k0 + kTK);
 #pragma unroll
     for (int k = 0; k < kTK; ++k) {
-      float a[kR], b[kR];
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-      for (int i = 0; i < kR; ++i) a[i] = As[k][ty * kR + i];
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < kR; ++j) b[j] = Bs[k][tx * kR + j];
-#pragma unroll
-      for (int i = 0; i < kR; ++i)
-#pragma unroll
-        for (int j = 0; j < kR; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+    if (more) stash(buf ^ 1);
     __syncthreads();
+    buf ^= 1;
   }
 #pragma unroll
-  for (int i = 0; i < kR; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < kR; ++j) {
-      const int gm = m0 + ty * kR + i, gn = n0 + tx * kR + j;
+    for (int j = 0; j < 4; ++j) {
+      const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
       if (gm < M && gn < N) {
         if (gridDim.z > 1) {
           partial[((size_t)blockIdx.z * M + gm) * N + gn] = acc[i][j];
@@ -103,7 +119,7 @@ int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
   int splits = 1;
   if (splitk_ws) {
     const int tiles = (int)(grid.x * grid.y);
-    splits = std::min(std::min(16, 592 / std::max(tiles, 1)), K / (4 * kTK));
+    splits = std::min(std::min(32, 592 / std::max(tiles, 1)), K / (4 * kTK));
     while (splits > 1 && (int64_t)splits * M * N > kSplitKFloats) --splits;
     splits = std::max(splits, 1);
   }
