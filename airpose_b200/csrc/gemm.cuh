@@ -45,6 +45,7 @@ struct GemmLaunch {
   // gemm_sk.cu only: the operand is given TRANSPOSED -- A as [K][M], B as [K][N], row-major (M / N contiguous) -- and read through
   // MN-major UMMA descriptors; its tensor map has boxes of 64 columns x 64 rows (make_tmap_tiled_bf16(rows = K, cols = M or N)).
   // The weight-gradient GEMMs contract over the pixels, which is the OUTER dimension of every NHWC tensor.
+  int mt2 = 0;                 // gemm_sk.cu: 256 x block_n tiles (two 128-row sub-tiles share every B k-block; single-buffered accumulator)
   int mn_a = 0, mn_b = 0;      // mn_b == 2: B = im2col(x)^T, tmB an im2col map with boxes of 64 channels x 64 pixels, geom the conv
   ConvGeom geom;
   Epilogue epi;

@@ -67,6 +67,7 @@ struct KP {
   int stages, res_bufs, b_res;      // shared-memory partition of this launch
   int split;                        // 1: stream-K (ranges of k-blocks)  0: whole tiles, round-robin over the CTAs
   int mn_a, mn_b;                   // operand given as [K][M] / [K][N]: 64 x 64 boxes, MN-major descriptors
+  int b_warp;                       // transposed B: its boxes are issued by warp 2 (a second TMA issuer)
   int splitk_r;                     // > 0: plain split-K, every tile cut into splitk_r ranges, EVERY range leaves its fp32 partial in ws (slot = CTA)
   const float* scale;
   const float* shift;
@@ -250,7 +251,9 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               ptx::tma_load_2d(&tmA, &full_bar[stage], sam, kb * BK, m0 + mt * kBlockM);
             }
           }
-          if (p.mn_b == 2) {
+          if (p.mn_b && p.b_warp) {
+            // the B boxes of this k-block are issued by warp 2 (below)
+          } else if (p.mn_b == 2) {
             // B = im2col(x)^T: k-block kb is 64 output pixels, column block j of the tile is (tap, 64 input channels) -- the box the
             // forward conv loads as its A operand, 64 pixels tall
             const int mm = kb * BK;
@@ -312,7 +315,37 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ residual TMA producer
-    if (lane == 0 && p.has_res) {
+    if (lane == 0 && p.mn_b && p.b_warp) {
+      // second TMA issuer (transposed operands: a k-block is up to 6 boxes of 8 KB, and one thread issues a box per ~1000 clk):
+      // this warp loads the B boxes of every k-block, warp 0 the A boxes; both wait for the slot, warp 0 arms the barrier with
+      // the bytes of both (a complete_tx may precede the expect_tx of its phase: the pending arrival keeps the phase open)
+      constexpr int kBoxBytes = 64 * BK * 2;
+      int stage = 0; uint32_t phase = 0;
+      SegIter it(cta, grid, units, p.num_kb, p.split, p.splitk_r);
+      Seg s;
+      while (it.next(s)) {
+        const int n_blk = s.tile % p.tiles_n, n0 = n_blk * BN;
+        const int b_boxes = min(BN / 64, (p.N - n0 + 63) / 64);
+        for (int kb = s.kb0; kb < s.kb1; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 700 + stage);
+          uint8_t* sb = smem + stage * stage_bytes + kABytes;
+          if (p.mn_b == 2) {
+            const int mm = kb * BK;
+            const int img = mm / p.HoWo, rem = mm - img * p.HoWo;
+            const int po = rem / p.Wo, qo = rem - po * p.Wo;
+            for (int j = 0; j < b_boxes; ++j) {
+              const int nb = (n0 >> 6) + j, tap = nb / p.cblks, cb = nb - tap * p.cblks;
+              const int r = tap / p.ksize, sx = tap - r * p.ksize;
+              ptx::tma_load_im2col_4d(&tmB, &full_bar[stage], sb + j * kBoxBytes, cb * 64, qo * p.stride - p.pad,
+                                      po * p.stride - p.pad, img, (uint16_t)sx, (uint16_t)r);
+            }
+          } else {
+            for (int j = 0; j < b_boxes; ++j) ptx::tma_load_2d(&tmB, &full_bar[stage], sb + j * kBoxBytes, n0 + j * 64, kb * BK);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0 && p.has_res) {
       int rq = 0;
       SegIter it(cta, grid, units, p.num_kb, p.split, p.splitk_r);
       Seg s;
@@ -612,6 +645,7 @@ int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream, SplitKInfo* sk) {
   }
   kp.im2col = L.im2col;
   kp.mn_a = L.mn_a; kp.mn_b = L.mn_b;
+  kp.b_warp = (L.mn_b && !L.epi.residual && !getenv("AIRPOSE_SK_ONE_ISSUER")) ? 1 : 0;
   AP_REQUIRE(!(L.mn_a || L.mn_b) || (!L.stem && !L.im2col), "launch_gemm_sk: MN-major operands are for plain GEMMs");
   if (L.mn_b == 2) {                      // B = im2col(x)^T through an im2col tensor map with 64-pixel boxes (weight gradients)
     const ConvGeom& g = L.geom;
@@ -641,7 +675,7 @@ int launch_gemm_sk(const GemmLaunch& L, cudaStream_t stream, SplitKInfo* sk) {
   // binding limit of a cta_group::1 tile is shared-memory bandwidth (MMA operand reads + TMA writes share
   // 128 B/clk: a 128x256 tile needs 192 B/clk at full tensor rate), which MT = 2 barely changes (160 B/clk).
   static const bool want_mt2 = getenv("AIRPOSE_SK_MT2") != nullptr;
-  const bool mt2 = want_mt2 && L.M > kBlockM;
+  const bool mt2 = (want_mt2 || L.mt2) && L.M > kBlockM && !sk;
   switch (L.block_n) {
     case 64: return mt2 ? launch_bn<64, 64, 2>(L, kp, stream) : launch_bn<64, 64, 1>(L, kp, stream);
     case 128: return mt2 ? launch_bn<128, 64, 2>(L, kp, stream) : launch_bn<128, 64, 1>(L, kp, stream);

@@ -347,10 +347,27 @@ __global__ void __launch_bounds__(kMaxJoints) smplx_bwd_chain_kernel(SmplxDev m,
     float gA[12];
 #pragma unroll
     for (int e = 0; e < 12; ++e) gA[e] = 0.f;
-    for (int t = 0; t < a.vtiles; ++t) {
-      const float* src = a.gA_part + (((size_t)t * a.B + b) * m.J + j) * 12;
+    {
+      // four tiles (twelve 16-byte loads) in flight, added in tile order: the sums are serial chains of L2 latencies otherwise
+      const size_t tstride = (size_t)a.B * m.J * 12;
+      const float* src0 = a.gA_part + ((size_t)b * m.J + j) * 12;
+      int t = 0;
+      for (; t + 4 <= a.vtiles; t += 4) {
+        float4 v[4][3];
 #pragma unroll
-      for (int e = 0; e < 12; ++e) gA[e] += __ldg(src + e);
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int e = 0; e < 3; ++e) v[k][e] = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)(t + k) * tstride) + e);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int e = 0; e < 3; ++e) { gA[4 * e] += v[k][e].x; gA[4 * e + 1] += v[k][e].y; gA[4 * e + 2] += v[k][e].z; gA[4 * e + 3] += v[k][e].w; }
+      }
+      for (; t < a.vtiles; ++t) {
+        const float* src = src0 + (size_t)t * tstride;
+#pragma unroll
+        for (int e = 0; e < 12; ++e) gA[e] += __ldg(src + e);
+      }
     }
     const float* Aj = a.A + ((size_t)b * m.J + j) * 12;
 #pragma unroll
@@ -371,49 +388,54 @@ __global__ void __launch_bounds__(kMaxJoints) smplx_bwd_chain_kernel(SmplxDev m,
       gJr[j][c] = -(Rg[j][0 * 3 + c] * gAt[0] + Rg[j][1 * 3 + c] * gAt[1] + Rg[j][2 * 3 + c] * gAt[2]);
   }
   __syncthreads();
-  // reverse pass over the chain: children (larger index) before parents; 54 short sequential steps
-  if (j == 0) {
+  // reverse pass over the chain: children (larger index) before parents; 54 sequential steps, each spread over nine lanes of
+  // warp 0 (lane = element (r, c) of the 3x3 updates; one thread doing all of it was 80 us of shared-memory latencies per mesh)
+  if (j < 32) {
+    const int l = j, r = l / 3, c = l - r * 3;
     for (int i = m.J - 1; i >= 1; --i) {
       const int p = par_s[i];
-      float d[3], u[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) d[c] = Jr[i][c] - Jr[p][c];
-      // tg_i = Rg_p (Jr_i - Jr_p) + tg_p
-#pragma unroll
-      for (int c = 0; c < 3; ++c) u[c] = Rg[p][0 * 3 + c] * gtg[i][0] + Rg[p][1 * 3 + c] * gtg[i][1] + Rg[p][2 * 3 + c] * gtg[i][2];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) gRg[p][r * 3 + c] += gtg[i][r] * d[c];
-        gJr[i][r] += u[r];
-        gJr[p][r] -= u[r];
-        gtg[p][r] += gtg[i][r];
+      if (l < 3) {                                       // tg_i = Rg_p (Jr_i - Jr_p) + tg_p : lane = component
+        const float u = Rg[p][0 * 3 + l] * gtg[i][0] + Rg[p][1 * 3 + l] * gtg[i][1] + Rg[p][2 * 3 + l] * gtg[i][2];
+        gJr[i][l] += u;
+        gJr[p][l] -= u;
+        gtg[p][l] += gtg[i][l];
       }
-      // Rg_i = Rg_p R_i
+      if (l < 9) {                                       // Rg_i = Rg_p R_i
+        const float d = Jr[i][c] - Jr[p][c];
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            s1 += gRg[i][r * 3 + k] * Rl[i][c * 3 + k];      // gRg_p += gRg_i R_i^T
-            s2 += Rg[p][k * 3 + r] * gRg[i][k * 3 + c];      // gR_i = Rg_p^T gRg_i
-          }
-          gRg[p][r * 3 + c] += s1;
-          gR[i][r * 3 + c] = s2;
+        for (int k = 0; k < 3; ++k) {
+          s1 += gRg[i][r * 3 + k] * Rl[i][c * 3 + k];      // gRg_p += gRg_i R_i^T
+          s2 += Rg[p][k * 3 + r] * gRg[i][k * 3 + c];      // gR_i = Rg_p^T gRg_i
         }
+        float t = gRg[p][r * 3 + c];
+        t += gtg[i][r] * d;
+        t += s1;
+        gRg[p][r * 3 + c] = t;
+        gR[i][r * 3 + c] = s2;
+      }
+      __syncwarp();
     }
-#pragma unroll
-    for (int e = 0; e < 9; ++e) gR[0][e] = gRg[0][e];         // Rg_0 = R_0
-#pragma unroll
-    for (int c = 0; c < 3; ++c) gJr[0][c] += gtg[0][c];       // tg_0 = Jr_0
+    if (l < 9) gR[0][l] = gRg[0][l];                     // Rg_0 = R_0
+    if (l < 3) gJr[0][l] += gtg[0][l];                   // tg_0 = Jr_0
   }
   __syncthreads();
   // pose feature (lbs.py:197): R_i - I for i = 1..n_active, and the shape columns, summed over the vertex tiles
   for (int q = j; q < a.NQ; q += kMaxJoints) {
     float s = 0.f;
-    for (int t = 0; t < a.vtiles; ++t) s += __ldg(a.gq_part + ((size_t)t * a.B + b) * a.NQ + q);
+    {
+      const size_t tstride = (size_t)a.B * a.NQ;
+      const float* src0 = a.gq_part + (size_t)b * a.NQ + q;
+      int t = 0;
+      for (; t + 8 <= a.vtiles; t += 8) {               // eight loads in flight, added in tile order
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(src0 + (size_t)(t + k) * tstride);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[k];
+      }
+      for (; t < a.vtiles; ++t) s += __ldg(src0 + (size_t)t * tstride);
+    }
     if (q < a.PF) {
       gR[1 + q / 9][q % 9] += s;                              // distinct (joint, element) per q: no race
     } else {

@@ -201,17 +201,18 @@ __global__ void avgpool_kernel(const __nv_bfloat16* __restrict__ x, int n, float
 // bn_finalize turns them into scale/shift and updates the running statistics; bn_apply writes
 // relu(z * scale + shift (+ residual)) in bf16.  All three are HBM-bound passes over [M, C].
 constexpr int kBnSlabs = 148 * 2;
+constexpr int kBnRedThreads = 256;                // threads of the two reduction passes (512 measured slower: stats 722 vs 575 us, backward reduce 1204 vs 1003 us per step)
 
 // Every BatchNorm kernel below takes the two views of a two-view tape in ONE launch: blockIdx.y = view, whose rows start
 // view_elems elements further on (per-view statistics / partials / coefficients follow the same index).  gridDim.y = 1 and
 // view_elems = 0 is the one-view case.
-__global__ void __launch_bounds__(256) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, int64_t M, int C, float* __restrict__ part,
+__global__ void __launch_bounds__(kBnRedThreads) bn_stats_kernel(const __nv_bfloat16* __restrict__ z, int64_t M, int C, float* __restrict__ part,
                                                        int64_t view_elems) {
-  __shared__ float red[256][17];
+  __shared__ float red[kBnRedThreads][17];
   z += (size_t)blockIdx.y * view_elems;
   part += (size_t)blockIdx.y * gridDim.x * C * 2;
   const int groups = C / 8;                         // 8 channels (16 B) per thread
-  const int lanes = 256 / groups;                   // row lanes per block (C <= 2048)
+  const int lanes = kBnRedThreads / groups;         // row lanes per block (C <= 2048)
   const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
   const int64_t per = (M + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(M, r0 + per);
@@ -723,7 +724,7 @@ extern "C" int airpose_backbone_stem(airpose_net_t* h, const float* x, int n, vo
 static int bn_train(airpose_net* h, int idx, const __nv_bfloat16* z, int64_t M, int C, const airpose_bn_train_params* bn,
                     const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t st, int views = 1, float* save1_base = nullptr) {
   const int64_t ve = M * C;
-  bn_stats_kernel<<<dim3(kBnSlabs, views), 256, 0, st>>>(z, M, C, h->bn_part, ve);
+  bn_stats_kernel<<<dim3(kBnSlabs, views), kBnRedThreads, 0, st>>>(z, M, C, h->bn_part, ve);
   AP_LAUNCH_CHECK();
   float* save = bn->saved_stats ? bn->saved_stats + h->bn_save_off[idx] : nullptr;
   float* save1 = save1_base ? save1_base + h->bn_save_off[idx] : nullptr;
@@ -862,16 +863,16 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ g_feat, int n, __nv
 }
 
 // partial sums of dpre = dy * [y > 0] and dpre * xhat per channel (xhat = (z - mean) * invstd)
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+__global__ void __launch_bounds__(kBnRedThreads) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                             const __nv_bfloat16* __restrict__ z, const float* __restrict__ stats0,
                                                             const float* __restrict__ stats1, int64_t M, int C, float* __restrict__ part,
                                                             int64_t view_elems) {
-  __shared__ float red[256][17];
+  __shared__ float red[kBnRedThreads][17];
   const float* __restrict__ stats = blockIdx.y ? stats1 : stats0;
   dy += (size_t)blockIdx.y * view_elems; z += (size_t)blockIdx.y * view_elems;
   if (y) y += (size_t)blockIdx.y * view_elems;
   part += (size_t)blockIdx.y * gridDim.x * C * 2;
-  const int groups = C / 8, lanes = 256 / groups;
+  const int groups = C / 8, lanes = kBnRedThreads / groups;
   const int cg = threadIdx.x % groups, rl = threadIdx.x / groups;
   const int64_t per = (M + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(M, r0 + per);
@@ -1354,7 +1355,7 @@ static int bn_bwd(airpose_net* h, const airpose_net::Tape& tp, int i, int64_t M,
   const float* stats0 = tp.stats + h->bn_save_off[i];
   const float* stats1 = tp.stats1 + h->bn_save_off[i];
   const __nv_bfloat16* y = relu ? tp.y[i] : nullptr;
-  bn_bwd_reduce_kernel<<<dim3(kBnSlabs, views), 256, 0, st>>>(dy, y, tp.z[i], stats0, stats1, Mv, C, h->bn_part, ve);
+  bn_bwd_reduce_kernel<<<dim3(kBnSlabs, views), kBnRedThreads, 0, st>>>(dy, y, tp.z[i], stats0, stats1, Mv, C, h->bn_part, ve);
   AP_LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, Mv, C, bn->bn_weight[i], stats0, stats1, g->g_bn_weight[i],
                                                            g->g_bn_bias[i], g->accumulate ? 1 : 0, h->bw_coef, views);
@@ -1415,6 +1416,10 @@ static int run_wgrad_gemm(airpose_net* h, GemmLaunch& L, int i, int cin, int kk,
   L.epi.out_bf16 = h->bw_batched ? h->bw_wg + h->bw_w_off[i] : h->bw_w; L.epi.ldd = ldd;
   if (enable_tma_epilogue(&L)) return 1;
   const int ranges = splitk_ranges(L.M, L.N, L.K, L.block_n);
+  // AIRPOSE_WGRAD_MT2=1: 256 x 256 tiles (a third less operand bytes per flop) for the large layers -- measured slower, as on the
+  // forward convs: 12.51 vs 12.05 ms per step (gpurun r02t9), so off by default
+  static const bool use_mt2 = getenv("AIRPOSE_WGRAD_MT2") != nullptr;
+  L.mt2 = (use_mt2 && !ranges && L.M >= 256 && L.block_n == 256) ? 1 : 0;
   if (ranges) {
     SplitKInfo sk{};
     sk.ranges = ranges;
@@ -1672,7 +1677,7 @@ extern "C" int airpose_debug_bn_bwd(airpose_net_t* h, int64_t M, int C, const vo
   AP_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "airpose_debug_bn_bwd: unsupported channel count %d", C);
   cudaStream_t st = (cudaStream_t)stream_;
   if (bw_reserve(h, 8)) return 1;
-  bn_bwd_reduce_kernel<<<kBnSlabs, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats, stats, M, C,
+  bn_bwd_reduce_kernel<<<kBnSlabs, kBnRedThreads, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats, stats, M, C,
                                                  h->bn_part, 0);
   AP_LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, gamma, stats, stats, g_gamma, g_beta, accumulate, h->bw_coef, 1);
