@@ -81,9 +81,12 @@ class BnTrainParams(C.Structure):
                 ("tape", C.c_int32)]
 
 
+UPPER_DONE_FN = C.CFUNCTYPE(None, C.c_void_p)
+
+
 class TrunkGrads(C.Structure):
     _fields_ = [("g_weight", C.c_void_p * 53), ("g_bn_weight", C.c_void_p * 53), ("g_bn_bias", C.c_void_p * 53),
-                ("accumulate", C.c_int32)]
+                ("accumulate", C.c_int32), ("upper_done", UPPER_DONE_FN), ("user", C.c_void_p)]
 
 
 class HmrParams(C.Structure):

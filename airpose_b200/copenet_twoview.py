@@ -467,11 +467,32 @@ class copenet_twoview(nn.Module):
         optimizer.zero_grad()
         gr = self.model.ief_train_backward(ctx, g["pred_pose0"], g["pred_betas0"], g["pred_pose1"], g["pred_betas1"],
                                            want_feature_grads=True, into_param_grads=True)
+        # Data-parallel gradient mean, overlapped with the backward the way DDP's buckets are: the gradients of layer3, layer4 and
+        # the regressor (everything behind layer2 in the flat buffer: 95 % of the bytes) are final when the trunk backward has
+        # enqueued layer3.0 -- their all-reduce runs on NCCL's stream under the backward of layer2, layer1 and the stem; the
+        # rest is reduced at the end.  AIRPOSE_NO_OVERLAP_ALLREDUCE=1: one all-reduce of the whole buffer after the backward.
+        world = torch.distributed.get_world_size() if dist_initialized() else 1
+        split, works = 0, []
+        if world > 1 and not os.environ.get("AIRPOSE_NO_OVERLAP_ALLREDUCE"):
+            m = self.model
+            late = [p for mod in (m.conv1, m.bn1, m.layer1, m.layer2) for p in mod.parameters()]
+            split = optimizer.late_split(late)
+            if not 0 < split < optimizer.numel:
+                split = 0
+        hook = (lambda: works.append(optimizer.allreduce_begin(split))) if split else None
         if paired:
-            self.model.backward_feat_ext(im0, 0, torch.cat([gr["xf0"], gr["xf1"]]), accumulate=False, into_param_grads=True, x1=im1)
+            self.model.backward_feat_ext(im0, 0, torch.cat([gr["xf0"], gr["xf1"]]), accumulate=False, into_param_grads=True, x1=im1,
+                                         upper_done=hook)
         else:
             self.model.backward_feat_ext(im0, 0, gr["xf0"], accumulate=False, into_param_grads=True)
-            self.model.backward_feat_ext(im1, 1, gr["xf1"], accumulate=True, into_param_grads=True)
-        scale = optimizer.allreduce_grads()
+            self.model.backward_feat_ext(im1, 1, gr["xf1"], accumulate=True, into_param_grads=True, upper_done=hook)
+        if split and works and works[0] is not None:
+            works.append(optimizer.allreduce_begin(0, split))
+            for w in works:
+                if w is not None:
+                    w.wait()
+            scale = 1.0 / world
+        else:
+            scale = optimizer.allreduce_grads()
         optimizer.step(grad_scale=scale)
         return loss, losses

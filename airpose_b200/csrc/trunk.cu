@@ -1556,6 +1556,21 @@ static int backbone_bwd_train_impl(airpose_net_t* h, const float* x, const float
   const int layers[4] = {3, 4, 6, 3};
   std::vector<int> first_idx;          // conv1 index of every block, in forward order
   { int idx = 1; for (int li = 0; li < 4; ++li) for (int b = 0; b < layers[li]; ++b) { first_idx.push_back(idx); idx += (b == 0) ? 4 : 3; } }
+  // weight gradients of convs [lo, hi) out of their bf16 slots (those not already written by wgrad_reduce_kernel), one launch
+  auto unpack_range = [&](int lo, int hi) -> int {
+    WgradTab wt{};
+    for (int i = lo; i < hi; ++i) {
+      const ConvSpec& s = h->specs[i];
+      wt.D[i] = h->bw_wg + h->bw_w_off[i]; wt.g[i] = h->bw_reduced[i] ? nullptr : g->g_weight[i]; wt.cout[i] = s.cout; wt.cin[i] = s.cin;
+      wt.kk[i] = s.k * s.k; wt.ldd[i] = i == 0 ? 192 : s.k * s.k * s.cin;
+      h->bw_reduced[i] = false;
+    }
+    wgrad_unpack_all_kernel<<<dim3(48, (unsigned)h->specs.size()), 256, 0, st>>>(wt, g->accumulate);
+    AP_LAUNCH_CHECK();
+    return 0;
+  };
+  const int upper_block = layers[0] + layers[1];      // first block of layer3
+  int unpacked_from = (int)h->specs.size();           // convs [unpacked_from, end) have been unpacked
   for (int bi = (int)first_idx.size() - 1; bi >= 0; --bi) {
     const int i1 = first_idx[bi], i2 = i1 + 1, i3 = i1 + 2;
     // a block has a downsample branch iff its conv3 takes its residual from conv index i1 + 3
@@ -1589,6 +1604,13 @@ static int backbone_bwd_train_impl(airpose_net_t* h, const float* x, const float
       if (conv_dgrad(h, i1, conv_weights[i1], DZ, n, Hin, Hin, addend, G, SCR, st)) return 1;
     }
     // G now holds dL/d(block input)
+    if (bi == upper_block && g->upper_done) {
+      // every gradient of layer3 and layer4 (95 % of the trunk's parameters) is final once the work enqueued so far has run: the
+      // caller can start its all-reduce of that part while layer2, layer1 and the stem are still being differentiated
+      if (unpack_range(i1, unpacked_from)) return 1;
+      unpacked_from = i1;
+      g->upper_done(g->user);
+    }
   }
   // stem: max-pool backward, bn1 + ReLU backward, weight gradient of the 7x7 conv (no data gradient: the input is the image)
   maxpool_bwd_kernel<<<ew_grid((int64_t)n * 112 * 112 * 8), 256, 0, st>>>(tp.pool_idx, G, n, G2);
@@ -1621,17 +1643,7 @@ static int backbone_bwd_train_impl(airpose_net_t* h, const float* x, const float
       if (airpose_gemm_bf16(&ga, st)) return 1;
     }
   }
-  {                                                  // every conv's weight gradient out of its slot, one launch
-    WgradTab wt{};
-    for (size_t i = 0; i < h->specs.size(); ++i) {
-      const ConvSpec& s = h->specs[i];
-      wt.D[i] = h->bw_wg + h->bw_w_off[i]; wt.g[i] = h->bw_reduced[i] ? nullptr : g->g_weight[i]; wt.cout[i] = s.cout; wt.cin[i] = s.cin;
-      h->bw_reduced[i] = false;
-      wt.kk[i] = s.k * s.k; wt.ldd[i] = i == 0 ? 192 : s.k * s.k * s.cin;
-    }
-    wgrad_unpack_all_kernel<<<dim3(48, (unsigned)h->specs.size()), 256, 0, st>>>(wt, g->accumulate);
-    AP_LAUNCH_CHECK();
-  }
+  if (unpack_range(0, unpacked_from)) return 1;        // every remaining conv's weight gradient out of its slot, one launch
   h->bw_batched = false;
   return 0;
 }

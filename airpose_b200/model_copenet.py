@@ -291,13 +291,15 @@ class copenet(nn.Module):
                 m.running_mean._airpose_gen = getattr(m.running_mean, "_airpose_gen", 0) + 1
         return out
 
-    def backward_feat_ext(self, x, tape, g_feat, accumulate=False, into_param_grads=False, grads=None, x1=None):
+    def backward_feat_ext(self, x, tape, g_feat, accumulate=False, into_param_grads=False, grads=None, x1=None, upper_done=None):
         """Backward of the training-mode ``forward_feat_ext`` call recorded on ``tape``: gradients of the 53 conv weights
         and of every BatchNorm weight / bias, given d loss / d features ``g_feat`` [n,2048] and the same images ``x``.
         Returns a dict keyed like ``state_dict``; ``into_param_grads`` writes into the parameters' ``.grad`` instead,
         ``grads`` (a dict from an earlier call) into those buffers (``accumulate`` adds: the second view of a pair).
         ``x1``: the tape is the two-view tape of ``_forward_feat_ext_train_pair`` (``x`` = view 0's images, ``g_feat`` [2B,2048]):
-        one backward over both views, the weight-gradient GEMMs contracting over the pixels of both."""
+        one backward over both views, the weight-gradient GEMMs contracting over the pixels of both.
+        ``upper_done``: a callable invoked (on this thread, during the call) once everything that writes the gradients of layer3
+        and layer4 has been enqueued on the stream -- where a data-parallel caller starts all-reducing that part."""
         device = self.conv1.weight.device
         lib, h = self._ensure(0, device, allow_training=True, need_regressor=False)
         x = x.detach().to(device=device, dtype=torch.float32).contiguous()
@@ -323,6 +325,15 @@ class copenet(nn.Module):
             tg.g_weight[i], tg.g_bn_weight[i], tg.g_bn_bias[i] = (b.data_ptr() for b in bufs)
             wptr[i] = conv.weight.data_ptr()
         tg.accumulate = int(bool(accumulate))
+        hook_error = []
+        if upper_done is not None:
+            def _hook(_user):                     # exceptions cannot cross the C frame: keep the first, re-raise after the call
+                try:
+                    upper_done()
+                except BaseException as e:        # noqa: BLE001
+                    hook_error.append(e)
+            hook = _lib.UPPER_DONE_FN(_hook)      # referenced until the native call has returned
+            tg.upper_done = hook
         bn = self._bn_train_params(tape, update_running=False)
         with torch.cuda.device(device):
             if x1 is not None:
@@ -333,6 +344,8 @@ class copenet(nn.Module):
                 _lib.check(lib.airpose_backbone_bwd_train(h, x.data_ptr(), x.shape[0], int(tape), C.byref(bn), g_feat.data_ptr(),
                                                           C.byref(tg), C.byref(wptr), _lib.current_stream()),
                            "airpose_backbone_bwd_train")
+        if hook_error:
+            raise hook_error[0]
         return out
 
     def forward_feat_ext_pair(self, x0, x1):

@@ -250,7 +250,7 @@ def train_leg(dev, world, rank, steps, warmup, sync_all):
     return {"workload": "copenet_twoview train step (fwd + loss + bwd + grad all-reduce + Adam amsgrad), 32 pairs per GPU (BASELINE.json configs[3]: 256 pairs on 8 GPUs)",
             "pairs_per_gpu": B, "global_pairs": world * B, "steps": steps, "ms_per_step": ms, "pairs_per_s": world * B / (ms * 1e-3),
             "allreduce_ms": ar_ms, "allreduce_bytes": 0 if world == 1 else int(108.4e6),
-            "allreduce_note": "one NCCL all-reduce of the flat fp32 gradient buffer per step, timed alone back to back; inside the step it follows the last backward kernel",
+            "allreduce_note": "allreduce_ms = one NCCL all-reduce of the whole flat fp32 gradient buffer, timed alone back to back; inside the step the buffer is reduced in two parts: layer3 + layer4 + regressor (95 % of the bytes) is launched when the trunk backward has enqueued layer3.0 and runs on NCCL's stream under the backward of layer2 / layer1 / stem, the rest after the last backward kernel (AIRPOSE_NO_OVERLAP_ALLREDUCE=1: one all-reduce at the end)",
             "tensor_tflops": 3 * 2 * B * GFLOP_PER_IMAGE / (ms * 1e-3) / 1e3, "params_identical_across_ranks": same, "loss_finite": finite}
 
 

@@ -259,6 +259,12 @@ typedef struct {
   float* g_bn_weight[53];
   float* g_bn_bias[53];
   int32_t accumulate;
+  /* Optional (NULL = off): called on the calling thread, once, when everything that writes the gradients of layer3 and layer4
+   * (convs 24..52 and their BatchNorms: 95 % of the trunk's parameters) has been enqueued on the stream -- the point where a
+   * data-parallel caller can start all-reducing that part (DDP's bucketed overlap, copenet_twoview.py:376-390 under Lightning's
+   * DDP) while layer2, layer1 and the stem are still being differentiated. */
+  void (*upper_done)(void* user);
+  void* user;
 } airpose_trunk_grads;
 int airpose_backbone_bwd_train(airpose_net_t* h, const float* x_nchw, int n_images, int tape, const airpose_bn_train_params* bn,
                                const float* g_feat, const airpose_trunk_grads* grads, const float* const* conv_weights_f32,

@@ -1694,3 +1694,42 @@ def test_fwd_pass_and_loss_test_mode(tmp_path, smplx_dir, smplx_oracle, smplx_da
         _, j_gt = orc.smplx_forward(smplx_oracle, zero, gt["smplpose_rotmat"], global_orient=gt["smplorient_rel%d" % v])
         assert met["mpjpe%d" % v] == pytest.approx(orc.mean_distance(j_gt, j_pr, 22), rel=1e-3)
     print("test metrics:", met)
+
+
+def test_trunk_backward_upper_done_hook_and_late_split(tmp_path, net_state):
+    """airpose_trunk_grads.upper_done (the point where a data-parallel caller starts all-reducing layer3 + layer4 under the rest of
+    the backward): called exactly once, the gradients are bit-identical with and without it, an exception raised inside the hook
+    surfaces after the native call; optim.Adam.late_split puts exactly conv1 / bn1 / layer1 / layer2 in front of the split."""
+    from airpose_b200.model_copenet import getcopenet
+    from airpose_b200.optim import Adam
+    mp = synthetic.write_mean_params(str(tmp_path / "smpl_mean_params.npz"))
+    net = getcopenet(mp, pretrained=False)
+    net.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in net_state.items()}, strict=True)
+    net = net.to(DEV).train()
+    B = 3
+    x = synthetic.make_inputs(B, 4)
+    x0, x1 = t(x["im0"]), t(x["im1"])
+    gf = torch.randn(2 * B, 2048, generator=torch.Generator(device="cpu").manual_seed(5)).to(DEV)
+    net._forward_feat_ext_train_pair(x0, x1, tape=0)
+    g_plain = net.backward_feat_ext(x0, 0, gf, x1=x1)
+    calls = []
+    g_hook = net.backward_feat_ext(x0, 0, gf, x1=x1, upper_done=lambda: calls.append(1))
+    assert calls == [1]
+    for k in g_plain:
+        assert torch.equal(g_plain[k], g_hook[k]), k
+
+    def boom():
+        raise RuntimeError("from the hook")
+    with pytest.raises(RuntimeError, match="from the hook"):
+        net.backward_feat_ext(x0, 0, gf, x1=x1, upper_done=boom)
+
+    opt = Adam(net.parameters(), lr=1e-4, amsgrad=True)
+    late = [p for mod in (net.conv1, net.bn1, net.layer1, net.layer2) for p in mod.parameters()]
+    split = opt.late_split(late)
+    assert 0 < split < opt.numel
+    late_ids = {id(p) for p in late}
+    for p, o in zip(opt.params, opt.offsets):
+        assert (o < split) == (id(p) in late_ids)
+    print("late_split: %d of %d elements (%.1f %%) are reduced at the end of the backward" % (split, opt.numel, 100.0 * split / opt.numel))
+    assert opt.allreduce_begin(split) is None          # one process: nothing to reduce
+
