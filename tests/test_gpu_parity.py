@@ -1733,3 +1733,45 @@ def test_trunk_backward_upper_done_hook_and_late_split(tmp_path, net_state):
     print("late_split: %d of %d elements (%.1f %%) are reduced at the end of the backward" % (split, opt.numel, 100.0 * split / opt.numel))
     assert opt.allreduce_begin(split) is None          # one process: nothing to reduce
 
+
+_MASK_SCRIPT = r"""
+import hashlib, sys, numpy as np, torch
+sys.path.insert(0, %(root)r)
+from airpose_b200 import synthetic
+from airpose_b200.model_copenet import getcopenet
+mp = synthetic.write_mean_params(%(mp)r)
+torch.manual_seed(0)
+net = getcopenet(mp, pretrained=False).to("cuda:0").train()
+x = synthetic.make_inputs(3, 4)
+x0, x1 = (torch.from_numpy(np.ascontiguousarray(x[k])).to("cuda:0") for k in ("im0", "im1"))
+gf = torch.randn(6, 2048, generator=torch.Generator(device="cpu").manual_seed(5)).to("cuda:0")
+net._forward_feat_ext_train_pair(x0, x1, tape=0)
+g = net.backward_feat_ext(x0, 0, gf, x1=x1)
+hsh = hashlib.sha256()
+for k in sorted(g):
+    hsh.update(g[k].cpu().numpy().tobytes())
+print("GRADHASH", hsh.hexdigest())
+"""
+
+
+def test_bn_backward_mask_from_z_is_bit_identical(tmp_path):
+    """AIRPOSE_BN_BWD_MASK_FROM_Z=1: the BatchNorm backward of the ReLU layers without a residual re-derives the mask [y > 0] from z
+    (scale / shift rebuilt with the forward's own roundings) instead of reading y: every trunk gradient must be bit-identical with
+    the default y-reading path (which also shows the trunk backward is run-to-run deterministic).  Two fresh processes, since the
+    switch is read once per process."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = _MASK_SCRIPT % {"root": root, "mp": str(tmp_path / "smpl_mean_params.npz")}
+    hashes = []
+    for flag in ("", "1"):
+        env = dict(os.environ)
+        env.pop("AIRPOSE_BN_BWD_MASK_FROM_Z", None)
+        if flag:
+            env["AIRPOSE_BN_BWD_MASK_FROM_Z"] = flag
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        hashes.append([l for l in out.stdout.splitlines() if l.startswith("GRADHASH")][-1])
+    print(hashes)
+    assert hashes[0] == hashes[1]
+
