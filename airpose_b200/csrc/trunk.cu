@@ -308,12 +308,13 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* __re
   z += (size_t)blockIdx.y * view_elems; y += (size_t)blockIdx.y * view_elems;
   if (residual) residual += (size_t)blockIdx.y * view_elems;
   scale += blockIdx.y * 2048; shift += blockIdx.y * 2048;
+  // a thread keeps its channel group for the whole loop (the grid stride is a multiple of 256 and groups divides 256)
+  const int cg = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) % groups);
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
+  const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8)), h1 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
+  const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % groups);
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(z) + i);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(scale + cg * 8 + 4));
-    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8)), h1 = __ldg(reinterpret_cast<const float4*>(shift + cg * 8 + 4));
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w}, sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
     uint32_t ru[4] = {0, 0, 0, 0};
     if (residual) { const uint4 r = __ldg(reinterpret_cast<const uint4*>(residual) + i); ru[0] = r.x; ru[1] = r.y; ru[2] = r.z; ru[3] = r.w; }
@@ -726,6 +727,7 @@ extern "C" int airpose_backbone_stem(airpose_net_t* h, const float* x, int n, vo
 static int bn_train(airpose_net* h, int idx, const __nv_bfloat16* z, int64_t M, int C, const airpose_bn_train_params* bn,
                     const __nv_bfloat16* residual, int relu, __nv_bfloat16* y, cudaStream_t st, int views = 1, float* save1_base = nullptr) {
   const int64_t ve = M * C;
+  AP_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0, "bn_train: C=%d must be 8 x a power of two <= 2048 (the kernels keep one channel group per thread)", C);
   bn_stats_kernel<<<dim3(kBnSlabs, views), kBnRedThreads, 0, st>>>(z, M, C, h->bn_part, ve);
   AP_LAUNCH_CHECK();
   float* save = bn->saved_stats ? bn->saved_stats + h->bn_save_off[idx] : nullptr;
@@ -865,6 +867,7 @@ __global__ void avgpool_bwd_kernel(const float* __restrict__ g_feat, int n, __nv
 }
 
 // partial sums of dpre = dy * [y > 0] and dpre * xhat per channel (xhat = (z - mean) * invstd)
+template <bool kZMask>
 __global__ void __launch_bounds__(kBnRedThreads) bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                             const __nv_bfloat16* __restrict__ z, const float* __restrict__ stats0,
                                                             const float* __restrict__ stats1, int64_t M, int C, float* __restrict__ part,
@@ -883,7 +886,7 @@ __global__ void __launch_bounds__(kBnRedThreads) bn_bwd_reduce_kernel(const __nv
   for (int j = 0; j < 8; ++j) { s[j] = q[j] = 0.f; mean[j] = stats[cg * 8 + j]; istd[j] = stats[C + cg * 8 + j]; }
   // gamma != null (a ReLU without residual): the mask [y > 0] is re-derived from z -- y = relu(bf16(z scale + shift)) with scale
   // and shift rebuilt exactly as bn_finalize_kernel rounds them -- and y is not read at all
-  const bool zmask = gamma != nullptr;
+  constexpr bool zmask = kZMask;
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -950,12 +953,13 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ part, int slabs
   }
 }
 
+template <bool kZMask>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                                            const __nv_bfloat16* __restrict__ z, const float* __restrict__ stats0,
                                                            const float* __restrict__ stats1, const float* __restrict__ coef, int64_t M, int C,
                                                            __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ dpre_out,
                                                            int64_t view_elems, const float* __restrict__ gamma, const float* __restrict__ beta) {
-  const bool zmask = gamma != nullptr;               // as in bn_bwd_reduce_kernel: the ReLU mask from z, y is not read
+  constexpr bool zmask = kZMask;                     // as in bn_bwd_reduce_kernel: the ReLU mask from z, y is not read
   const int groups = C / 8;
   const int64_t total = M * groups;
   const float* __restrict__ stats = blockIdx.y ? stats1 : stats0;
@@ -963,31 +967,28 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const __nv_bfloat16* 
   dy += (size_t)blockIdx.y * view_elems; z += (size_t)blockIdx.y * view_elems; dz += (size_t)blockIdx.y * view_elems;
   if (y) y += (size_t)blockIdx.y * view_elems;
   if (dpre_out) dpre_out += (size_t)blockIdx.y * view_elems;
+  // a thread keeps its channel group for the whole loop (the grid stride is a multiple of 256 and groups divides 256): the five
+  // per-channel tables are loaded once (they were ten 16-byte loads and a 64-bit modulo per 8 elements)
+  const int cg = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) % groups);
+  float mean[8], istd[8], c1[8], c2[8], c3[8], gm[8], bt[8];
+  {
+    const float* tabs[5] = {stats + cg * 8, stats + C + cg * 8, coef + cg * 8, coef + 2048 + cg * 8, coef + 4096 + cg * 8};
+    float* dsts[5] = {mean, istd, c1, c2, c3};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(tabs[k])), b = __ldg(reinterpret_cast<const float4*>(tabs[k]) + 1);
+      dsts[k][0] = a.x; dsts[k][1] = a.y; dsts[k][2] = a.z; dsts[k][3] = a.w;
+      dsts[k][4] = b.x; dsts[k][5] = b.y; dsts[k][6] = b.z; dsts[k][7] = b.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { gm[j] = zmask ? gamma[cg * 8 + j] : 0.f; bt[j] = zmask ? beta[cg * 8 + j] : 0.f; }
+  }
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % groups);
     const uint4 vd = __ldg(reinterpret_cast<const uint4*>(dy) + i);
     const uint4 vz = __ldg(reinterpret_cast<const uint4*>(z) + i);
     uint4 vy = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
     if (y && !zmask) vy = __ldg(reinterpret_cast<const uint4*>(y) + i);
     const uint32_t ud[4] = {vd.x, vd.y, vd.z, vd.w}, uz[4] = {vz.x, vz.y, vz.z, vz.w}, uy[4] = {vy.x, vy.y, vy.z, vy.w};
-    // per-channel constants as 16-byte loads (five tables x 8 channels)
-    float mean[8], istd[8], c1[8], c2[8], c3[8], gm[8], bt[8];
-    if (zmask) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(gamma + cg * 8)), b = __ldg(reinterpret_cast<const float4*>(gamma + cg * 8) + 1);
-      const float4 c = __ldg(reinterpret_cast<const float4*>(beta + cg * 8)), d = __ldg(reinterpret_cast<const float4*>(beta + cg * 8) + 1);
-      gm[0] = a.x; gm[1] = a.y; gm[2] = a.z; gm[3] = a.w; gm[4] = b.x; gm[5] = b.y; gm[6] = b.z; gm[7] = b.w;
-      bt[0] = c.x; bt[1] = c.y; bt[2] = c.z; bt[3] = c.w; bt[4] = d.x; bt[5] = d.y; bt[6] = d.z; bt[7] = d.w;
-    }
-    {
-      const float* tabs[5] = {stats + cg * 8, stats + C + cg * 8, coef + cg * 8, coef + 2048 + cg * 8, coef + 4096 + cg * 8};
-      float* dsts[5] = {mean, istd, c1, c2, c3};
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(tabs[k])), b = __ldg(reinterpret_cast<const float4*>(tabs[k]) + 1);
-        dsts[k][0] = a.x; dsts[k][1] = a.y; dsts[k][2] = a.z; dsts[k][3] = a.w;
-        dsts[k][4] = b.x; dsts[k][5] = b.y; dsts[k][6] = b.z; dsts[k][7] = b.w;
-      }
-    }
     __align__(16) __nv_bfloat16 o[8], p[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -1389,12 +1390,14 @@ static int bn_bwd(airpose_net* h, const airpose_net::Tape& tp, int i, int64_t M,
   const bool zmask = relu && from_z && io[i].res_src == -3;
   const float* zg = zmask ? bn->bn_weight[i] : nullptr;
   const float* zb = zmask ? bn->bn_bias[i] : nullptr;
-  bn_bwd_reduce_kernel<<<dim3(kBnSlabs, views), kBnRedThreads, 0, st>>>(dy, y, tp.z[i], stats0, stats1, Mv, C, h->bn_part, ve, zg, zb);
+  if (zmask) bn_bwd_reduce_kernel<true><<<dim3(kBnSlabs, views), kBnRedThreads, 0, st>>>(dy, y, tp.z[i], stats0, stats1, Mv, C, h->bn_part, ve, zg, zb);
+  else bn_bwd_reduce_kernel<false><<<dim3(kBnSlabs, views), kBnRedThreads, 0, st>>>(dy, y, tp.z[i], stats0, stats1, Mv, C, h->bn_part, ve, zg, zb);
   AP_LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, Mv, C, bn->bn_weight[i], stats0, stats1, g->g_bn_weight[i],
                                                            g->g_bn_bias[i], g->accumulate ? 1 : 0, h->bw_coef, views);
   AP_LAUNCH_CHECK();
-  bn_bwd_apply_kernel<<<dim3(ew_grid(Mv * (C / 8)), views), 256, 0, st>>>(dy, y, tp.z[i], stats0, stats1, h->bw_coef, Mv, C, dz, dpre, ve, zg, zb);
+  if (zmask) bn_bwd_apply_kernel<true><<<dim3(ew_grid(Mv * (C / 8)), views), 256, 0, st>>>(dy, y, tp.z[i], stats0, stats1, h->bw_coef, Mv, C, dz, dpre, ve, zg, zb);
+  else bn_bwd_apply_kernel<false><<<dim3(ew_grid(Mv * (C / 8)), views), 256, 0, st>>>(dy, y, tp.z[i], stats0, stats1, h->bw_coef, Mv, C, dz, dpre, ve, zg, zb);
   AP_LAUNCH_CHECK();
   return 0;
 }
@@ -1723,12 +1726,12 @@ extern "C" int airpose_debug_bn_bwd(airpose_net_t* h, int64_t M, int C, const vo
   AP_REQUIRE(C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0, "airpose_debug_bn_bwd: unsupported channel count %d", C);
   cudaStream_t st = (cudaStream_t)stream_;
   if (bw_reserve(h, 8)) return 1;
-  bn_bwd_reduce_kernel<<<kBnSlabs, kBnRedThreads, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats, stats, M, C,
+  bn_bwd_reduce_kernel<false><<<kBnSlabs, kBnRedThreads, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats, stats, M, C,
                                                  h->bn_part, 0, nullptr, nullptr);
   AP_LAUNCH_CHECK();
   bn_bwd_finalize_kernel<<<ceil_div(C, 4), 128, 0, st>>>(h->bn_part, kBnSlabs, M, C, gamma, stats, stats, g_gamma, g_beta, accumulate, h->bw_coef, 1);
   AP_LAUNCH_CHECK();
-  bn_bwd_apply_kernel<<<ew_grid(M * (C / 8)), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats, stats,
+  bn_bwd_apply_kernel<false><<<ew_grid(M * (C / 8)), 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (const __nv_bfloat16*)z, stats, stats,
                                                             h->bw_coef, M, C, (__nv_bfloat16*)out_dz, (__nv_bfloat16*)out_dpre, 0, nullptr, nullptr);
   AP_LAUNCH_CHECK();
   return 0;
