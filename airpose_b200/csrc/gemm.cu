@@ -480,6 +480,7 @@ extern "C" int airpose_gemm_bf16(const airpose_gemm_args* g, void* stream) {
     L.epi.out_bf16 = g->out_bf16; L.epi.ldd = g->ldd;
     AP_REQUIRE(tma_epilogue_eligible(L), "airpose_gemm_bf16: a_t / b_t need the TMA epilogue (aligned bf16 output)");
     if (enable_tma_epilogue(&L)) return 1;
+    L.pdl = use_pdl();
     return launch_gemm_sk(L, (cudaStream_t)stream);
   }
   L.block_n = pick_block_n(g->M, g->N, g->K);
@@ -497,6 +498,7 @@ extern "C" int airpose_gemm_bf16(const airpose_gemm_args* g, void* stream) {
     L.pair_b_box = 0;
     if (make_tmap_tiled_bf16(&L.tmB, g->B, g->N, g->K, g->ldb, L.block_n, kBlockK)) return 1;
   }
+  L.pdl = use_pdl();           // the kernels wait (griddepcontrol.wait) before touching anything the previous kernel wrote
   return launch_gemm(L, (cudaStream_t)stream);
 }
 
@@ -528,5 +530,6 @@ extern "C" int airpose_conv_bf16(const airpose_conv_args* c, void* stream) {
     L.pair_b_box = 0;
     if (make_tmap_tiled_bf16(&L.tmB, c->w, L.N, L.K, L.K, L.block_n, kBlockK)) return 1;
   }
+  L.pdl = use_pdl();           // the kernels wait (griddepcontrol.wait) before touching anything the previous kernel wrote
   return launch_gemm(L, (cudaStream_t)stream);
 }

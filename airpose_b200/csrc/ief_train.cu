@@ -15,6 +15,7 @@
 // (copenet_real/src/copenet_real/copenet_twoview.py:357-372).
 #include <algorithm>
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace airpose {
 namespace {
@@ -29,6 +30,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
                                                     const float* __restrict__ B, int64_t sbk, int64_t sbn,
                                                     float* __restrict__ C, int64_t ldc, int M, int N, int K, float alpha, float beta,
                                                     int k_per_split, float* __restrict__ partial) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   __shared__ __align__(16) float As[2][kTK][kTP], Bs[2][kTK][kTP];
   const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;        // 16 x 16 threads, 4 x 4 outputs each
@@ -102,6 +105,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 }
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, float* __restrict__ C, int64_t ldc, int M, int N, float beta) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)M * N) return;
   float acc = 0.f;
@@ -129,11 +134,9 @@ int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
     splits = ceil_div(K, k_per);
     grid.z = splits;
   }
-  sgemm_kernel<<<grid, 256, 0, st>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, 1.f, beta, k_per, splitk_ws);
-  AP_LAUNCH_CHECK();
+  AP_CHECK_CUDA(launch_chain(sgemm_kernel, grid, dim3(256), st, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, 1.f, beta, k_per, splitk_ws));
   if (splits > 1) {
-    splitk_reduce_kernel<<<(unsigned)ceil_div64((int64_t)M * N, 256), 256, 0, st>>>(splitk_ws, splits, C, ldc, M, N, beta);
-    AP_LAUNCH_CHECK();
+    AP_CHECK_CUDA(launch_chain(splitk_reduce_kernel, dim3((unsigned)ceil_div64((int64_t)M * N, 256)), dim3(256), st, splitk_ws, splits, C, ldc, M, N, beta));
   }
   return 0;
 }
@@ -142,6 +145,8 @@ int sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk,
 __global__ void ief_init_state_kernel(int B, const float* pos0, const float* pos1, const float* th0, const float* th1, int th_stride,
                                       const float* sh0, const float* sh1, int sh_stride, const float* init_pose,
                                       const float* init_shape, float* state) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * B * kD) return;
   const int m = i / kD, o = i % kD, v = m / B, b = m % B;
@@ -154,6 +159,8 @@ __global__ void ief_init_state_kernel(int B, const float* pos0, const float* pos
 
 __global__ void ief_assemble_kernel(int B, const float* __restrict__ xf0, const float* __restrict__ xf1, const float* __restrict__ bb0,
                                     const float* __restrict__ bb1, const float* __restrict__ state, float* __restrict__ z) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)2 * B * kZ) return;
   const int m = (int)(i / kZ), k = (int)(i % kZ), v = m / B, b = m % B;
@@ -173,22 +180,30 @@ __global__ void ief_assemble_kernel(int B, const float* __restrict__ xf0, const 
 
 // h = (h + bias) * mask   (mask may be null = eval)
 __global__ void bias_mask_kernel(float* __restrict__ h, const float* __restrict__ bias, const float* __restrict__ mask, int rows, int cols) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const float x = h[i] + bias[i % cols];
   h[i] = mask ? x * mask[i] : x;
 }
 __global__ void mul_mask_kernel(float* __restrict__ g, const float* __restrict__ mask, int n) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && mask) g[i] *= mask[i];
 }
 // state += d + bdec
 __global__ void state_update_kernel(float* __restrict__ state, const float* __restrict__ d, const float* __restrict__ bdec, int rows) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows * kD) state[i] += d[i] + bdec[i % kD];
 }
 // out[c] (+)= sum_r g[r][c], rows summed in order (deterministic)
 __global__ void colsum_kernel(const float* __restrict__ g, int rows, int cols, float* __restrict__ out, float beta) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   float s = 0.f;
@@ -198,6 +213,8 @@ __global__ void colsum_kernel(const float* __restrict__ g, int rows, int cols, f
 // gradient of the assembled input back onto the previous iteration's states (the identity path state_new = state_old + d
 // is already in g_state): g_state[self] += gz[u-part of self], g_state[other] += gz[cross part]
 __global__ void scatter_gu_kernel(int B, const float* __restrict__ gz, float* __restrict__ g_state) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 2 * B * kD) return;
   const int m = i / kD, o = i % kD, v = m / B, b = m % B;
@@ -209,6 +226,8 @@ __global__ void scatter_gu_kernel(int B, const float* __restrict__ gz, float* __
   g_state[i] += g;
 }
 __global__ void copy_gxf_kernel(int B, const float* __restrict__ gz, float* __restrict__ g_xf0, float* __restrict__ g_xf1, float beta) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)2 * B * kF) return;
   const int m = (int)(i / kF), k = (int)(i % kF), v = m / B, b = m % B;
@@ -278,10 +297,9 @@ extern "C" int airpose_ief_train_fwd(const airpose_ief_train_args* a, void* stre
   const int B = a->batch, R = 2 * B;
   const Ws s = carve(a->workspace, B);
   if (load_dec(a, s, st)) return 1;
-  ief_init_state_kernel<<<blocks((int64_t)R * kD), 256, 0, st>>>(B, a->pos0, a->pos1, a->init_theta0, a->init_theta1, a->init_theta_stride,
+  AP_CHECK_CUDA(launch_chain(ief_init_state_kernel, dim3(blocks((int64_t)R * kD)), dim3(256), st, B, a->pos0, a->pos1, a->init_theta0, a->init_theta1, a->init_theta_stride,
                                                                 a->init_shape0, a->init_shape1, a->init_shape_stride, a->init_pose,
-                                                                a->init_shape, s.state);
-  AP_LAUNCH_CHECK();
+                                                                a->init_shape, s.state));
   const size_t per_it = (size_t)R * (kZ + kH + kH);
   for (int it = 0; it < a->iters; ++it) {
     float* z = a->saved + it * per_it;
@@ -289,17 +307,13 @@ extern "C" int airpose_ief_train_fwd(const airpose_ief_train_args* a, void* stre
     float* h2 = h1 + (size_t)R * kH;
     const float* m1 = a->mask1 ? a->mask1 + (size_t)it * R * kH : nullptr;
     const float* m2 = a->mask2 ? a->mask2 + (size_t)it * R * kH : nullptr;
-    ief_assemble_kernel<<<blocks((int64_t)R * kZ), 256, 0, st>>>(B, a->xf0, a->xf1, a->bb0, a->bb1, s.state, z);
-    AP_LAUNCH_CHECK();
+    AP_CHECK_CUDA(launch_chain(ief_assemble_kernel, dim3(blocks((int64_t)R * kZ)), dim3(256), st, B, a->xf0, a->xf1, a->bb0, a->bb1, s.state, z));
     if (sgemm(z, kZ, 1, a->fc1_w, 1, kZ, h1, kH, R, kH, kZ, 0.f, st, s.splitk)) return 1;                 // h1 = z W1^T
-    bias_mask_kernel<<<blocks((int64_t)R * kH), 256, 0, st>>>(h1, a->fc1_b, m1, R, kH);
-    AP_LAUNCH_CHECK();
+    AP_CHECK_CUDA(launch_chain(bias_mask_kernel, dim3(blocks((int64_t)R * kH)), dim3(256), st, h1, a->fc1_b, m1, R, kH));
     if (sgemm(h1, kH, 1, a->fc2_w, 1, kH, h2, kH, R, kH, kH, 0.f, st, s.splitk)) return 1;                // h2 = h1 W2^T
-    bias_mask_kernel<<<blocks((int64_t)R * kH), 256, 0, st>>>(h2, a->fc2_b, m2, R, kH);
-    AP_LAUNCH_CHECK();
+    AP_CHECK_CUDA(launch_chain(bias_mask_kernel, dim3(blocks((int64_t)R * kH)), dim3(256), st, h2, a->fc2_b, m2, R, kH));
     if (sgemm(h2, kH, 1, s.wdec, 1, kH, s.d, kD, R, kD, kH, 0.f, st, s.splitk)) return 1;                 // d = h2 Wdec^T
-    state_update_kernel<<<blocks((int64_t)R * kD), 256, 0, st>>>(s.state, s.d, s.bdec, R);
-    AP_LAUNCH_CHECK();
+    AP_CHECK_CUDA(launch_chain(state_update_kernel, dim3(blocks((int64_t)R * kD)), dim3(256), st, s.state, s.d, s.bdec, R));
   }
   // outputs: pose [B,135], betas [B,10] per view
   for (int v = 0; v < 2; ++v) {
@@ -339,30 +353,23 @@ extern "C" int airpose_ief_train_bwd(const airpose_ief_train_args* a, void* stre
     const float* gd = s.g_state;                                   // state_new = state_old + d  =>  dL/dd = dL/dstate_new
     // decoders: g_wdec += gd^T h2, g_bdec += colsum(gd), gh2 = (gd Wdec) * m2
     if (sgemm(gd, 1, kD, h2, kH, 1, s.g_wdec, kH, kD, kH, R, beta, st, s.splitk)) return 1;
-    colsum_kernel<<<ceil_div(kD, 128), 128, 0, st>>>(gd, R, kD, s.g_bdec, beta);
-    AP_LAUNCH_CHECK();
+    AP_CHECK_CUDA(launch_chain(colsum_kernel, dim3(ceil_div(kD, 128)), dim3(128), st, gd, R, kD, s.g_bdec, beta));
     if (sgemm(gd, kD, 1, s.wdec, kH, 1, s.gh2, kH, R, kH, kD, 0.f, st, s.splitk)) return 1;
-    mul_mask_kernel<<<blocks((int64_t)R * kH), 256, 0, st>>>(s.gh2, m2, R * kH);
-    AP_LAUNCH_CHECK();
+    AP_CHECK_CUDA(launch_chain(mul_mask_kernel, dim3(blocks((int64_t)R * kH)), dim3(256), st, s.gh2, m2, R * kH));
     // fc2
     if (sgemm(s.gh2, 1, kH, h1, kH, 1, a->g_fc2_w, kH, kH, kH, R, beta, st, s.splitk)) return 1;
-    colsum_kernel<<<ceil_div(kH, 128), 128, 0, st>>>(s.gh2, R, kH, a->g_fc2_b, beta);
-    AP_LAUNCH_CHECK();
+    AP_CHECK_CUDA(launch_chain(colsum_kernel, dim3(ceil_div(kH, 128)), dim3(128), st, s.gh2, R, kH, a->g_fc2_b, beta));
     if (sgemm(s.gh2, kH, 1, a->fc2_w, kH, 1, s.gh1, kH, R, kH, kH, 0.f, st, s.splitk)) return 1;
-    mul_mask_kernel<<<blocks((int64_t)R * kH), 256, 0, st>>>(s.gh1, m1, R * kH);
-    AP_LAUNCH_CHECK();
+    AP_CHECK_CUDA(launch_chain(mul_mask_kernel, dim3(blocks((int64_t)R * kH)), dim3(256), st, s.gh1, m1, R * kH));
     // fc1
     if (sgemm(s.gh1, 1, kH, z, kZ, 1, a->g_fc1_w, kZ, kH, kZ, R, beta, st, s.splitk)) return 1;
-    colsum_kernel<<<ceil_div(kH, 128), 128, 0, st>>>(s.gh1, R, kH, a->g_fc1_b, beta);
-    AP_LAUNCH_CHECK();
+    AP_CHECK_CUDA(launch_chain(colsum_kernel, dim3(ceil_div(kH, 128)), dim3(128), st, s.gh1, R, kH, a->g_fc1_b, beta));
     if (sgemm(s.gh1, kH, 1, a->fc1_w, kZ, 1, s.gz, kZ, R, kZ, kH, 0.f, st, s.splitk)) return 1;
     if (a->g_xf0) {
-      copy_gxf_kernel<<<blocks((int64_t)R * kF), 256, 0, st>>>(B, s.gz, a->g_xf0, a->g_xf1, beta);
-      AP_LAUNCH_CHECK();
+      AP_CHECK_CUDA(launch_chain(copy_gxf_kernel, dim3(blocks((int64_t)R * kF)), dim3(256), st, B, s.gz, a->g_xf0, a->g_xf1, beta));
     }
     if (it > 0) {                                                  // the first iteration's state is the constant initialisation
-      scatter_gu_kernel<<<blocks((int64_t)R * kD), 256, 0, st>>>(B, s.gz, s.g_state);
-      AP_LAUNCH_CHECK();
+      AP_CHECK_CUDA(launch_chain(scatter_gu_kernel, dim3(blocks((int64_t)R * kD)), dim3(256), st, B, s.gz, s.g_state));
     }
   }
   // split the concatenated decoder gradient
