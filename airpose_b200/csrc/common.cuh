@@ -46,9 +46,9 @@ inline bool chain_pdl() {
   return on;
 }
 template <typename... KArgs, typename... Args>
-cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+cudaError_t launch_chain_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -57,6 +57,11 @@ cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaSt
   const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
   if (e == cudaSuccess) count_launch();
   return e;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  return launch_chain_smem(kernel, grid, block, 0, st, args...);
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

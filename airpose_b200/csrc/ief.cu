@@ -14,6 +14,7 @@
 // i.e. 38 + 3*16 MMAC per 64 pairs instead of 840 MMAC in nine latency-bound GEMMs.  All fp32 FMA:
 // the result differs from the reference's fp32 chain only by summation order (~1e-6 relative).
 #include "common.cuh"
+#include "ptx.cuh"
 #include "net.cuh"
 
 namespace airpose {
@@ -69,6 +70,8 @@ __global__ void ief_fold_bias_kernel(const double* __restrict__ T, const float* 
 // partial[ks][m][o] = sum_{k in slice ks} GxT[k][o] * xf[m][k];  rows m in [0,2B): view m / B, pair m % B.
 __global__ void __launch_bounds__(kDecPad) ief_base_kernel(int B, const float* __restrict__ xf0, const float* __restrict__ xf1,
                                                            const float* __restrict__ GxT, float* __restrict__ partial) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   __shared__ float xs[kIefRows][kIefKPer];
   const int m0 = blockIdx.x * kIefRows, ks = blockIdx.y, o = threadIdx.x, M = 2 * B;
   for (int i = threadIdx.x; i < kIefRows * kIefKPer; i += kDecPad) {
@@ -133,6 +136,8 @@ struct IefIterArgs {
 // conflict-free (consecutive o) instead of chasing 3 x 284 dependent L2 loads per thread.
 constexpr int kIefIterSmem = kState * kDecPad * (int)sizeof(float);
 __global__ void __launch_bounds__(2 * kDecPad) ief_iter_kernel(IefIterArgs a) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   extern __shared__ __align__(16) float gsm[];   // [kState][kDecPad]
   __shared__ float st[2][kDecPad];        // per view: pose[0..135) then shape[135..145)
   __shared__ __align__(16) float u[2][kState];
@@ -342,8 +347,7 @@ extern "C" int airpose_ief_fwd(airpose_net_t* h, const airpose_ief_args* a, void
   cudaStream_t st = (cudaStream_t)stream_;
   IefState& s = h->ief;
   if (ensure_partial(s, M, st)) return 1;
-  ief_base_kernel<<<dim3(ceil_div(M, kIefRows), kIefKSlices), kDecPad, 0, st>>>(B, a->xf0, a->xf1, s.GxT, s.partial);
-  AP_LAUNCH_CHECK();
+  AP_CHECK_CUDA(launch_chain(ief_base_kernel, dim3(ceil_div(M, kIefRows), kIefKSlices), dim3(kDecPad), st, B, a->xf0, a->xf1, (const float*)s.GxT, s.partial));
   IefIterArgs k{};
   k.B = B; k.iters = a->iters;
   k.bb0 = a->bb0; k.bb1 = a->bb1; k.pos0 = a->pos0; k.pos1 = a->pos1;
@@ -353,8 +357,7 @@ extern "C" int airpose_ief_fwd(airpose_net_t* h, const airpose_ief_args* a, void
   k.partial = s.partial; k.GuT = s.GuT; k.g = s.g;
   k.out_pose0 = a->out_pose0; k.out_betas0 = a->out_betas0; k.out_pose1 = a->out_pose1; k.out_betas1 = a->out_betas1;
   AP_CHECK_CUDA(cudaFuncSetAttribute(ief_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kIefIterSmem));
-  ief_iter_kernel<<<B, 2 * kDecPad, kIefIterSmem, st>>>(k);
-  AP_LAUNCH_CHECK();
+  AP_CHECK_CUDA(launch_chain_smem(ief_iter_kernel, dim3(B), dim3(2 * kDecPad), kIefIterSmem, st, k));
   return 0;
 }
 

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "ptx.cuh"
 #include "smplx.cuh"
 
 namespace airpose {
@@ -60,6 +61,8 @@ __device__ __forceinline__ void load_rot(const PoseArgs& a, int b, int j, float 
 
 // lbs.py:316-370 batch_rigid_transform, one mesh per CTA, one joint per thread.
 __global__ void __launch_bounds__(kMaxJoints) smplx_pose_kernel(SmplxDev m, PoseArgs a) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   __shared__ float Ts[kMaxJoints][12];
   __shared__ float Js[kMaxJoints][3];
   __shared__ float beta_s[kMaxShape];
@@ -309,6 +312,8 @@ struct JointArgs {
 };
 
 __global__ void __launch_bounds__(128) smplx_joints_kernel(SmplxDev m, JointArgs a) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   const int b = blockIdx.x;
   const int nj = m.J + m.E + m.L;
   const float* vb = a.verts + (size_t)b * m.V * 3;
@@ -362,6 +367,8 @@ __global__ void __launch_bounds__(128) smplx_joints_kernel(SmplxDev m, JointArgs
 
 __global__ void rot6d_kernel(const float* __restrict__ x, int64_t groups, int per_group, int64_t row_stride,
                              float* __restrict__ R) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= groups * per_group) return;
   const float* s = x + (i / per_group) * row_stride + (i % per_group) * 6;
@@ -649,8 +656,7 @@ extern "C" int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_arg
   pa.transl = g->transl;
   pa.root_R = g->root_R; pa.root_R_stride = g->root_R_stride;
   pa.root_t = g->root_t; pa.root_t_stride = g->root_t_stride;
-  smplx_pose_kernel<<<B, kMaxJoints, 0, stream>>>(d, pa);
-  AP_LAUNCH_CHECK();
+  AP_CHECK_CUDA(launch_chain(smplx_pose_kernel, dim3(B), dim3(kMaxJoints), stream, d, pa));
 
   if (use_tc) {
     TcCall tcall{};
@@ -686,8 +692,7 @@ extern "C" int airpose_smplx_fwd(airpose_smplx_t* h, const airpose_smplx_fwd_arg
   ja.fx = g->focal_x; ja.fy = g->focal_y; ja.center = g->center; ja.center_stride = g->center_stride;
   ja.proj_t = g->proj_t; ja.proj_t_stride = g->proj_t_stride;
   ja.joints = g->out_joints; ja.joints_cam = g->out_joints_cam; ja.j2d = g->out_joints_2d;
-  smplx_joints_kernel<<<B, 128, 0, stream>>>(d, ja);
-  AP_LAUNCH_CHECK();
+  AP_CHECK_CUDA(launch_chain(smplx_joints_kernel, dim3(B), dim3(128), stream, d, ja));
   return 0;
 }
 
@@ -782,8 +787,7 @@ extern "C" int airpose_smplx_bwd(airpose_smplx_t* h, const airpose_smplx_bwd_arg
   pa.seg[0] = g->global_orient; pa.seg_stride[0] = g->global_orient_stride;
   pa.seg[1] = g->body_pose; pa.seg_stride[1] = g->body_pose_stride;
   pa.A = A; pa.Jt = Jt; pa.feat = feat;
-  smplx_pose_kernel<<<B, kMaxJoints, 0, stream>>>(d, pa);
-  AP_LAUNCH_CHECK();
+  AP_CHECK_CUDA(launch_chain(smplx_pose_kernel, dim3(B), dim3(kMaxJoints), stream, d, pa));
 
   BwdVertexArgs va{};
   va.B = B; va.nb = g->num_betas; va.PF = PF; va.NQ = NQ; va.ldq = h->ldq; va.nj = nj; va.P = d.P;

@@ -172,6 +172,9 @@ smplx_vertex_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlapped the previous kernel (smplx_pose_kernel); its output (the F operand, the per-mesh records) is read below
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ P (once) + F ring
@@ -513,13 +516,13 @@ int smplx_tc_forward(const SmplxDev& d, const SmplxTc& tc, const TcCall& c, cuda
   dim3 grid(tc.vtiles, ceil_div(a.tiles_total, a.tiles_per_cta));
   static const int un = getenv("AIRPOSE_SMPLX_UNROLL") ? atoi(getenv("AIRPOSE_SMPLX_UNROLL")) : 2;   // 4 spills at 96 registers (0.77 vs 0.64 ms)
   if (un == 2) {
-    if (c.out_cam) smplx_vertex_tc_kernel<true, 2><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a);
-    else smplx_vertex_tc_kernel<false, 2><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a);
+    if (c.out_cam) AP_CHECK_CUDA(launch_chain_smem(smplx_vertex_tc_kernel<true, 2>, grid, dim3(kThreads), kSmemBytes, stream, tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a));
+    else AP_CHECK_CUDA(launch_chain_smem(smplx_vertex_tc_kernel<false, 2>, grid, dim3(kThreads), kSmemBytes, stream, tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a));
   } else {
-    if (c.out_cam) smplx_vertex_tc_kernel<true, 4><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a);
-    else smplx_vertex_tc_kernel<false, 4><<<grid, kThreads, kSmemBytes, stream>>>(tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a);
+    if (c.out_cam) AP_CHECK_CUDA(launch_chain_smem(smplx_vertex_tc_kernel<true, 4>, grid, dim3(kThreads), kSmemBytes, stream, tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a));
+    else AP_CHECK_CUDA(launch_chain_smem(smplx_vertex_tc_kernel<false, 4>, grid, dim3(kThreads), kSmemBytes, stream, tc.tmP, tc.tmPx, tmFh, tmFl, tmFx, a));
   }
-  AP_LAUNCH_CHECK();
+  AP_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
