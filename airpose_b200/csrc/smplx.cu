@@ -778,8 +778,7 @@ extern "C" int airpose_smplx_bwd(airpose_smplx_t* h, const airpose_smplx_bwd_arg
   ja.root_R = g->root_R; ja.root_R_stride = g->root_R_stride; ja.root_t = g->root_t; ja.root_t_stride = g->root_t_stride;
   ja.fx = g->focal_x; ja.fy = g->focal_y;
   ja.g_tot = gjt; ja.g_root_R = g->grad_root_R; ja.g_root_t = g->grad_root_t;
-  smplx_bwd_joints_kernel<<<B, 128, 0, stream>>>(ja);
-  AP_LAUNCH_CHECK();
+  AP_CHECK_CUDA(launch_chain(smplx_bwd_joints_kernel, dim3(B), dim3(128), stream, ja));
 
   PoseArgs pa{};
   pa.B = B; pa.nb = g->num_betas; pa.n_active = n_active;
@@ -807,8 +806,7 @@ extern "C" int airpose_smplx_bwd(airpose_smplx_t* h, const airpose_smplx_bwd_arg
     }
     AP_REQUIRE(smem <= 160 * 1024, "airpose_smplx_bwd: shared memory %zu too large", smem);
     dim3 grid(vtiles, ceil_div(B, MB));
-    smplx_vertex_bwd_kernel<MB><<<grid, kVertsPerCta, smem, stream>>>(d, va);
-    AP_LAUNCH_CHECK();
+    AP_CHECK_CUDA(launch_chain_smem(smplx_vertex_bwd_kernel<MB>, grid, dim3(kVertsPerCta), smem, stream, d, va));
   }
 
   BwdChainArgs ca{};
@@ -819,7 +817,6 @@ extern "C" int airpose_smplx_bwd(airpose_smplx_t* h, const airpose_smplx_bwd_arg
   ca.seg[2] = nullptr; ca.seg_stride[2] = 0;
   ca.A = A; ca.gA_part = gA_part; ca.gq_part = gq_part; ca.g_jtot = gjt;
   ca.g_betas = g->grad_betas; ca.g_body_pose = g->grad_body_pose; ca.g_global_orient = g->grad_global_orient;
-  smplx_bwd_chain_kernel<<<B, kMaxJoints, 0, stream>>>(d, ca);
-  AP_LAUNCH_CHECK();
+  AP_CHECK_CUDA(launch_chain(smplx_bwd_chain_kernel, dim3(B), dim3(kMaxJoints), stream, d, ca));
   return 0;
 }

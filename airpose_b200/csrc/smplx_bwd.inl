@@ -39,6 +39,8 @@ struct BwdJointArgs {
 };
 
 __global__ void __launch_bounds__(128) smplx_bwd_joints_kernel(BwdJointArgs a) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   __shared__ float red[128][12];
   const int b = blockIdx.x, t = threadIdx.x;
   float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tr[3] = {0, 0, 0};
@@ -114,6 +116,8 @@ constexpr int kBwdSegGroups = kVertsPerCta / 12;
 
 template <int MB>
 __global__ void __launch_bounds__(kVertsPerCta) smplx_vertex_bwd_kernel(SmplxDev m, BwdVertexArgs a) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   constexpr int HS = 3 * MB + 4;     // H_s row: [c][mesh] of one vertex, padded (16-byte rows, 4-way conflicts on the writes only)
   extern __shared__ __align__(16) float smem[];
   const int A_per_mesh = m.J * 12;
@@ -320,6 +324,8 @@ struct BwdChainArgs {
 };
 
 __global__ void __launch_bounds__(kMaxJoints) smplx_bwd_chain_kernel(SmplxDev m, BwdChainArgs a) {
+  ptx::grid_dep_wait();      // launched through launch_chain (common.cuh)
+  ptx::grid_dep_launch();
   __shared__ float gRg[kMaxJoints][9], gtg[kMaxJoints][3], gJr[kMaxJoints][3];
   __shared__ float Rg[kMaxJoints][9], Rl[kMaxJoints][9], Jr[kMaxJoints][3];
   __shared__ float gR[kMaxJoints][9];
