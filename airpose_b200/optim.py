@@ -144,20 +144,15 @@ class Adam:
         """Offset (in elements of the flat buffers) after the last of ``late_params``: everything from there on belongs to other
         parameters.  The overlapped all-reduce of ``copenet_twoview.training_step`` reduces ``flat_grad[offset:]`` as soon as
         those gradients are final and ``flat_grad[:offset]`` at the end of the backward."""
+        from .parallel import late_split_offset
         late = {id(p) for p in late_params}
-        end = 0
-        for p, o in zip(self.params, self.offsets):
-            if id(p) in late:
-                end = max(end, o + (p.numel() + 3) // 4 * 4)
-        return end
+        return late_split_offset(self.offsets, [p.numel() for p in self.params], [id(p) in late for p in self.params])
 
     def allreduce_begin(self, lo, hi=None, group=None):
         """Asynchronous SUM all-reduce of ``flat_grad[lo:hi]`` (ordered after the work already enqueued on the current stream);
         returns the work handle (``.wait()`` orders the current stream after it), or None when there is nothing to reduce."""
-        hi = self.numel if hi is None else hi
-        if hi <= lo or not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
-            return None
-        return dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True)
+        from .parallel import allreduce_begin
+        return allreduce_begin(self.flat_grad, lo, self.numel if hi is None else hi, group=group)
 
     @torch.no_grad()
     def step(self, grad_scale=1.0):

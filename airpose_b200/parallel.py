@@ -103,3 +103,24 @@ def broadcast_buffers_(module, src=0, group=None):
                 b.copy_(flat[o:o + b.numel()].view_as(b))
                 o += b.numel()
     return module
+
+
+def late_split_offset(offsets, numels, late):
+    """Where the flat gradient buffer of ``optim.Adam`` is cut for the overlapped all-reduce: the end (rounded up to the 4-element
+    slot pitch) of the last parameter flagged ``late`` -- a parameter whose gradient is only final at the end of the backward
+    (conv1 / bn1 / layer1 / layer2).  Everything from that offset on is reduced while the rest of the backward still runs."""
+    end = 0
+    for o, n, is_late in zip(offsets, numels, late):
+        if is_late:
+            end = max(end, o + (n + 3) // 4 * 4)
+    return end
+
+
+def allreduce_begin(flat, lo, hi=None, group=None):
+    """Asynchronous SUM all-reduce of ``flat[lo:hi]``, ordered after the work already enqueued on the current stream (NCCL) /
+    issued immediately (gloo); returns the work handle, or None when there is nothing to reduce (one rank, empty range)."""
+    hi = flat.numel() if hi is None else hi
+    if hi <= lo or not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return None
+    return dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True)
+

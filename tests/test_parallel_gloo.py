@@ -70,7 +70,23 @@ def _worker(rank, world, port, q):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         ok_buf = torch.equal(lo, hi) and int(bn.num_batches_tracked) == 3
-        q.put((rank, ok_shard, ok_max, ok_grad and ok_buf, ncoll))
+        # (5) the two-part gradient all-reduce of copenet_twoview.training_step: the part behind the split is reduced first
+        # (asynchronously, while the "late" gradients are still being written), the front part afterwards; together they must
+        # equal one all-reduce of the whole flat buffer
+        offsets, numels = [0, 8, 20, 24], [6, 10, 3, 9]                 # 4-element slots, as optim.Adam lays them out
+        split = parallel.late_split_offset(offsets, numels, [True, True, False, False])
+        ok_two = split == 20 and parallel.late_split_offset(offsets, numels, [False] * 4) == 0
+        flat = torch.arange(36.0) * (rank + 1)
+        whole = flat.clone()
+        dist.all_reduce(whole)
+        flat[:split] = -1.0                                              # not final yet when the first part starts
+        w1 = parallel.allreduce_begin(flat, split)
+        flat[:split] = torch.arange(float(split)) * (rank + 1)           # the late gradients arrive
+        w2 = parallel.allreduce_begin(flat, 0, split)
+        for w in (w1, w2):
+            w.wait()
+        ok_two = ok_two and torch.equal(flat, whole) and parallel.allreduce_begin(flat, 5, 5) is None
+        q.put((rank, ok_shard, ok_max, ok_grad and ok_buf and ok_two, ncoll))
     finally:
         dist.destroy_process_group()
 
