@@ -24,6 +24,13 @@
 //     CTA two 128-row sub-tiles that share every B k-block (a 256xBN tile: half the B traffic per flop,
 //     accumulators MT*BN TMEM columns, double-buffered only while 2*MT*BN <= 512).
 //
+//   * round 2, for the weight-gradient GEMMs of the training step (dW = dZ^T . im2col(X), both operands contracting over the
+//     pixels = the OUTER dimension of NHWC tensors): operands given transposed are read through MN-major descriptors from
+//     64-column x 64-row TMA boxes (KP::mn_a / mn_b; mn_b == 2: the boxes come from an im2col tensor map), warp 2 -- idle without a
+//     residual -- issues the B boxes as a second TMA issuer, and GEMMs with a handful of tiles and thousands of k-blocks run as
+//     plain split-K over all SMs (KP::splitk_r): every range leaves its fp32 partial in the workspace and the caller's reduce
+//     kernel sums them in a fixed order (stream-K's one-owner gather caps a tile at 16 ranges).
+//
 // CTA = 11 warps, one CTA per SM:
 //   warp 0    A/B TMA producer     warp 1   MMA issuer (TMEM double-buffered)    warp 2   residual TMA producer
 //   warps 3-6 / 7-10   epilogue groups 0 / 1: tcgen05.ld -> scale/shift (+residual) -> relu -> bf16 ->
