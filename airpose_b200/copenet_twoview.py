@@ -443,7 +443,8 @@ class copenet_twoview(nn.Module):
                   running statistics updated); regressor with dropout; SMPL-X + transform + projection; get_loss
         backward  loss -> SMPL-X -> rot6d -> regressor (parameter gradients + d loss / d features) -> trunk, view 0 then
                   view 1 accumulating, every gradient written straight into the optimizer's flat gradient buffer
-        update    ONE all-reduce of the flat buffer over the ranks (NCCL over NVLink), ONE Adam(amsgrad) launch.
+        update    the flat gradient buffer all-reduced over the ranks (NCCL over NVLink) in two parts -- layer3 + layer4 + regressor
+                  under the rest of the backward, the remainder at its end --, ONE Adam(amsgrad) launch.
         ``deccam`` takes part with a zero gradient (it is unused by the two-view model, model_copenet.py:73).
         Returns ``(loss, losses)`` as device tensors (no host sync)."""
         if not self.model.training:

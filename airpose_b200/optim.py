@@ -4,7 +4,8 @@ amsgrad=True)`` (copenet/src/copenet/copenet_twoview.py:416-425) as ONE kernel l
 The parameters are re-homed into a single flat fp32 buffer (each ``p.data`` becomes a view of it, the
 module keeps working unchanged), and so are the gradients (``p.grad`` views of a flat gradient buffer):
 the optimizer step is one HBM-bound pass (csrc/optim.cu), ``zero_grad`` one memset, and the data-parallel
-gradient mean one all-reduce of the flat buffer (``allreduce_grads``) instead of DDP's bucket machinery.
+gradient mean one all-reduce of the flat buffer (``allreduce_grads``), or two slices of it overlapped with the backward
+(``late_split`` / ``allreduce_begin``), instead of DDP's bucket machinery.
 No CPU path.
 """
 from __future__ import annotations
