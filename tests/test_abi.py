@@ -122,3 +122,39 @@ def test_server_wire_constants_and_letterbox_geometry():
     with pytest.raises(_lib.AirposeError):          # CUDA only, no CPU path
         import tempfile
         server.StagedServer(server.getmodel(synthetic.write_mean_params(os.path.join(tempfile.mkdtemp(), "smpl_mean_params.npz"))), device="cpu")
+
+
+_STRUCTS = {   # header typedef -> ctypes mirror (airpose_b200/_lib.py)
+    "airpose_smplx_model_host": "SmplxModelHost", "airpose_smplx_fwd_args": "SmplxFwdArgs", "airpose_smplx_bwd_args": "SmplxBwdArgs",
+    "airpose_conv_params": "ConvParams", "airpose_net_params": "NetParams", "airpose_bn_train_params": "BnTrainParams",
+    "airpose_trunk_grads": "TrunkGrads", "airpose_ief_args": "IefArgs", "airpose_ief_train_args": "IefTrainArgs",
+    "airpose_hmr_params": "HmrParams", "airpose_hmr_ief_args": "HmrIefArgs", "airpose_twoview_loss_args": "LossArgs",
+    "airpose_real_loss_args": "RealLossArgs", "airpose_adam_args": "AdamArgs", "airpose_gemm_args": "GemmArgs",
+    "airpose_conv_args": "ConvArgs", "airpose_bneck_tail_args": "BneckTailArgs",
+}
+
+
+def test_struct_sizes_match_the_header(tmp_path):
+    """Every argument struct of include/airpose_b200.h has the size its ctypes mirror has (gcc compiles the header as plain C):
+    a field added on one side only would shift everything behind it silently."""
+    import ctypes
+    import shutil
+    import subprocess
+    from airpose_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sizes.c"
+    lines = ['#include <stdio.h>', '#include "airpose_b200.h"', "int main(void) {"]
+    lines += ['  printf("%s %%zu\\n", sizeof(%s));' % (name, name) for name in _STRUCTS]
+    lines += ["  return 0;", "}"]
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "sizes"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    sizes = dict(l.split() for l in out.splitlines())
+    assert set(sizes) == set(_STRUCTS)
+    for name, mirror in _STRUCTS.items():
+        assert int(sizes[name]) == ctypes.sizeof(getattr(_lib, mirror)), (name, mirror, sizes[name], ctypes.sizeof(getattr(_lib, mirror)))
+
