@@ -148,12 +148,19 @@ def test_struct_sizes_match_the_header(tmp_path):
     src = tmp_path / "sizes.c"
     lines = ['#include <stdio.h>', '#include "airpose_b200.h"', "int main(void) {"]
     lines += ['  printf("%s %%zu\\n", sizeof(%s));' % (name, name) for name in _STRUCTS]
+    fields = [("airpose_gemm_args", "GemmArgs", f) for f in ("K", "relu", "out_f32", "a_t", "b_t")] + \
+             [("airpose_trunk_grads", "TrunkGrads", f) for f in ("g_bn_bias", "accumulate", "upper_done", "user")] + \
+             [("airpose_conv_args", "ConvArgs", f) for f in ("w", "pad", "relu", "out")]
+    lines.insert(1, "#include <stddef.h>")
+    lines += ['  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (t, f, t, f) for t, _, f in fields]
     lines += ["  return 0;", "}"]
     src.write_text("\n".join(lines))
     exe = tmp_path / "sizes"
     subprocess.run([gcc, "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     sizes = dict(l.split() for l in out.splitlines())
+    for t, mirror, f in fields:                      # the fields added in round 2 and a few old ones sit where ctypes puts them
+        assert int(sizes.pop("%s.%s" % (t, f))) == getattr(getattr(_lib, mirror), f).offset, (t, f)
     assert set(sizes) == set(_STRUCTS)
     for name, mirror in _STRUCTS.items():
         assert int(sizes[name]) == ctypes.sizeof(getattr(_lib, mirror)), (name, mirror, sizes[name], ctypes.sizeof(getattr(_lib, mirror)))
